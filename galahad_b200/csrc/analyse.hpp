@@ -1,0 +1,75 @@
+// Symbolic analysis for the b200ldlt engine (CPU side; the north-star keeps ordering and symbolic
+// analysis on the host).  All arrays here are 0-based.  The integer results are required to be
+// bit-identical (after the +1 shift) to what the reference computes in
+//   src/ssids/anal.f90 (check_order :147, expand_pattern :37, build_map :1129, analyse_phase :940,
+//   find_subtree_partition :284) and src/spral/core_analyse.f90 (basic_analyse :38 and children).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace b200 {
+
+struct Symbolic {
+   int n = 0;
+   int64_t nz = 0;                 // entries of the lower triangle (CSC) handed to analyse
+   std::vector<int64_t> ptr;       // lower-CSC column pointers (copied at analyse)
+   std::vector<int> row;           // lower-CSC row indices
+   std::vector<int> order;         // order[i] = pivot position of variable i (-1: structurally absent)
+   std::vector<int> invp;          // invp[p] = variable at pivot position p
+   int nnodes = 0;
+   std::vector<int> sptr;          // nnodes+1, first pivot of each supernode
+   std::vector<int> sparent;       // nnodes, parent supernode (nnodes == virtual root)
+   std::vector<int64_t> rptr;      // nnodes+1
+   std::vector<int> rlist;         // row lists (pivot-order indices), ascending per node
+   std::vector<int64_t> nptr;      // nnodes+1
+   std::vector<int64_t> nlist;     // 2*nz: (src position in val, dest = col*blkm + row), per node
+   int64_t num_factor = 0;
+   int64_t num_flops = 0;
+   int maxfront = 0;               // max #columns of a supernode (anal.f90:1100)
+   int maxdepth = 0;
+   int matrix_rank = 0;            // structural rank = sptr[nnodes]
+   int realn = 0;
+   int flag = 0;                   // 0 ok, 6 = SSIDS_WARNING_ANAL_SINGULAR, <0 error
+   // subtree partition (find_subtree_partition); parts are contiguous node ranges
+   int nparts = 1;
+   std::vector<int> part;          // nparts+1
+   std::vector<int> exec_loc;      // nparts; -1 = root part, else owning device
+   std::vector<int> contrib_ptr;   // nparts+1
+   std::vector<int> contrib_idx;   // contributing parts
+   std::vector<int> contrib_dest;  // destination node of each contribution
+};
+
+enum : int {
+   SSIDS_SUCCESS = 0,
+   SSIDS_ERROR_CALL_SEQUENCE = -1,
+   SSIDS_ERROR_A_N_OOR = -2,
+   SSIDS_ERROR_A_PTR = -3,
+   SSIDS_ERROR_A_ALL_OOR = -4,
+   SSIDS_ERROR_SINGULAR = -5,
+   SSIDS_ERROR_NOT_POS_DEF = -6,
+   SSIDS_ERROR_PTR_ROW = -7,
+   SSIDS_ERROR_ORDER = -8,
+   SSIDS_ERROR_VAL = -9,
+   SSIDS_ERROR_X_SIZE = -10,
+   SSIDS_ERROR_JOB_OOR = -11,
+   SSIDS_ERROR_NOT_LLT = -13,
+   SSIDS_ERROR_NOT_LDLT = -14,
+   SSIDS_ERROR_NO_SAVED_SCALING = -15,
+   SSIDS_ERROR_ALLOCATION = -50,
+   SSIDS_ERROR_CUDA_UNKNOWN = -51,
+   SSIDS_ERROR_CUBLAS_UNKNOWN = -52,
+   SSIDS_ERROR_UNIMPLEMENTED = -98,
+   SSIDS_ERROR_UNKNOWN = -99,
+   SSIDS_WARNING_ANAL_SINGULAR = 6,
+   SSIDS_WARNING_FACT_SINGULAR = 7,
+};
+
+// Lower-triangular CSC pattern (ptr/row, 0-based) + user order (order[i] = position, 0-based).
+// Returns sym.flag.  nemin < 1 selects the reference default (32).
+int analyse(int n, const int64_t* ptr, const int* row, const int* order, int nemin, Symbolic& sym);
+
+// Partition the assembly tree into `ndev` leaf parts + one root part following
+// anal.f90:284-459 with a GPU-only topology of `ndev` equal devices.
+void find_subtree_partition(Symbolic& sym, int ndev, double max_load_inbalance, int64_t min_gpu_work);
+
+}  // namespace b200

@@ -1,0 +1,349 @@
+// C ABI of the b200ldlt engine (include/b200ldlt.h).  Thin: argument checking, index-base
+// shifts, handle ownership, flag bookkeeping.  Mirrors the call-sequence checks of
+// src/ssids/ssids.f90 (analyse :148, factor :770/:821-827, solve :1139/:1155-1195,
+// enquire :1255/:1299, alter :1347, free :1388).
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/b200ldlt.h"
+#include "analyse.hpp"
+#include "engine.hpp"
+
+using namespace b200;
+
+namespace {
+
+struct Akeep {
+   Symbolic sym;
+   Plan* plan = nullptr;
+   int plan_cuda_error = 0;
+   b200ldlt_inform inf_analyse;
+   // partition
+   std::vector<int64_t> part_flops;
+};
+
+struct Fkeep {
+   Akeep* ak = nullptr;
+   Numeric* num = nullptr;
+};
+
+void clear_inform(b200ldlt_inform* inf) {
+   if (inf) std::memset(inf, 0, sizeof(*inf));
+}
+
+int ensure_plan(Akeep* ak, int device) {
+   if (ak->plan) return 0;
+   ak->plan = plan_create(ak->sym, device, &ak->plan_cuda_error);
+   return ak->plan ? 0 : SSIDS_ERROR_CUDA_UNKNOWN;
+}
+
+FactorOptions to_engine(const b200ldlt_options* o, int posdef) {
+   FactorOptions f;
+   f.posdef = posdef;
+   f.action = o->action;
+   f.u = o->u;
+   f.small_ = o->small_;
+   f.multiplier = o->multiplier;
+   f.print_level = o->print_level;
+   return f;
+}
+
+}  // namespace
+
+extern "C" {
+
+void b200ldlt_default_options(b200ldlt_options* o) {
+   std::memset(o, 0, sizeof(*o));
+   o->array_base = 0;
+   o->print_level = -1;
+   o->nemin = 32;          // datatypes.f90:21 nemin_default
+   o->action = 1;
+   o->u = 0.01;
+   o->small_ = 1e-20;
+   o->multiplier = 1.1;
+   o->device = -1;
+}
+
+const char* b200ldlt_version(void) { return "b200ldlt 0.1 (sm_100a)"; }
+
+int b200ldlt_analyse_ptr64(void** akeep, int n, const int64_t* ptr, const int* row, int* order,
+                           const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   clear_inform(inf);
+   if (!akeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
+   if (n < 0) return inf->flag = SSIDS_ERROR_A_N_OOR;
+   if (n > 0 && (!ptr || !row || !order)) return inf->flag = SSIDS_ERROR_A_PTR;
+   auto t0 = std::chrono::steady_clock::now();
+   const int base = opt->array_base ? 1 : 0;
+   if (n > 0 && ptr[0] != base) return inf->flag = SSIDS_ERROR_A_PTR;
+   for (int i = 0; i < n; ++i)
+      if (ptr[i + 1] < ptr[i]) return inf->flag = SSIDS_ERROR_A_PTR;
+   Akeep* ak = new (std::nothrow) Akeep();
+   if (!ak) return inf->flag = SSIDS_ERROR_ALLOCATION;
+   int flag;
+   try {
+      const int64_t nz = n > 0 ? ptr[n] - base : 0;
+      std::vector<int64_t> p0(n + 1);
+      std::vector<int> r0(nz), o0(n);
+      for (int i = 0; i <= n; ++i) p0[i] = ptr[i] - base;
+      for (int64_t k = 0; k < nz; ++k) {
+         r0[k] = row[k] - base;
+         if (r0[k] < 0 || r0[k] >= n) { delete ak; return inf->flag = SSIDS_ERROR_A_ALL_OOR; }
+      }
+      for (int i = 0; i < n; ++i) {
+         int v = order[i] < 0 ? -order[i] : order[i];   // check_order: signs are reset (anal.f90:176-178)
+         o0[i] = v - base;
+      }
+      flag = analyse(n, p0.data(), r0.data(), o0.data(), opt->nemin, ak->sym);
+   } catch (const std::bad_alloc&) {
+      delete ak;
+      return inf->flag = SSIDS_ERROR_ALLOCATION;
+   }
+   if (flag < 0) {
+      delete ak;
+      return inf->flag = flag;
+   }
+   const Symbolic& s = ak->sym;
+   for (int i = 0; i < n; ++i) order[i] = s.order[i] < 0 ? (base - 1) : s.order[i] + base;
+   inf->flag = flag;
+   inf->matrix_rank = s.matrix_rank;
+   inf->maxdepth = s.maxdepth;
+   inf->maxfront = s.maxfront;
+   inf->num_factor = s.num_factor;
+   inf->num_flops = s.num_flops;
+   inf->num_sup = s.nnodes;
+   inf->nparts = 1;
+   inf->time_analyse = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+   ak->inf_analyse = *inf;
+   if (*akeep) {
+      void* none = nullptr;
+      b200ldlt_free(akeep, &none);
+   }
+   *akeep = ak;
+   return flag;
+}
+
+int b200ldlt_analyse(void** akeep, int n, const int* ptr, const int* row, int* order,
+                     const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   if (n < 0 || !ptr) {
+      clear_inform(inf);
+      if (inf) inf->flag = n < 0 ? SSIDS_ERROR_A_N_OOR : SSIDS_ERROR_A_PTR;
+      return n < 0 ? SSIDS_ERROR_A_N_OOR : SSIDS_ERROR_A_PTR;
+   }
+   std::vector<int64_t> p64(ptr, ptr + n + 1);
+   return b200ldlt_analyse_ptr64(akeep, n, p64.data(), row, order, opt, inf);
+}
+
+static int factor_common(void* akeep, void** fkeep, int posdef, const double* val, bool on_device,
+                         const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   *inf = ak->inf_analyse;
+   inf->time_analyse = 0;
+   if (ak->sym.n > 0 && !val) return inf->flag = SSIDS_ERROR_VAL;
+   if (ensure_plan(ak, opt->device)) {
+      inf->cuda_error = ak->plan_cuda_error;
+      return inf->flag = SSIDS_ERROR_CUDA_UNKNOWN;
+   }
+   Fkeep* fk = static_cast<Fkeep*>(*fkeep);
+   if (fk && fk->ak != ak) { b200ldlt_free_fkeep(fkeep); fk = nullptr; }
+   if (!fk) {
+      fk = new (std::nothrow) Fkeep();
+      if (!fk) return inf->flag = SSIDS_ERROR_ALLOCATION;
+      fk->ak = ak;
+      fk->num = numeric_create(ak->plan);
+      *fkeep = fk;
+   }
+   FactorStats st;
+   int flag = numeric_factor(fk->num, val, on_device, to_engine(opt, posdef), st);
+   inf->cuda_error = st.cuda_error;
+   inf->num_delay = st.num_delay;
+   inf->num_neg = st.num_neg;
+   inf->num_two = st.num_two;
+   inf->not_first_pass = st.not_first_pass;
+   inf->not_second_pass = st.not_second_pass;
+   inf->maxfront = st.maxfront > 0 ? st.maxfront : inf->maxfront;
+   inf->matrix_rank = ak->sym.matrix_rank - st.num_zero;   // cpu_iface.f90:71-88
+   inf->time_factor = st.t_total;
+   inf->time_factor_device = st.t_device;
+   inf->factor_bytes = st.factor_bytes;
+   inf->reserved[0] = (int)st.launches;
+   // singular: warning with action, error without (ssids.f90:1057-1066)
+   if (flag >= 0 && st.num_zero > 0) flag = opt->action ? SSIDS_WARNING_FACT_SINGULAR : SSIDS_ERROR_SINGULAR;
+   if (flag >= 0 && flag == 0 && ak->inf_analyse.flag > 0) flag = ak->inf_analyse.flag;
+   return inf->flag = flag;
+}
+
+int b200ldlt_factor(void* akeep, void** fkeep, int posdef, const double* val,
+                    const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   return factor_common(akeep, fkeep, posdef, val, false, opt, inf);
+}
+int b200ldlt_factor_device(void* akeep, void** fkeep, int posdef, const double* d_val,
+                           const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   return factor_common(akeep, fkeep, posdef, d_val, true, opt, inf);
+}
+
+static int solve_common(void* akeep, void* fkeep, int job, int nrhs, double* x, int ldx, bool on_device,
+                        b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
+   Fkeep* fk = static_cast<Fkeep*>(fkeep);
+   if (fk->ak != akeep || !fk->num || !numeric_has_factors(fk->num)) return inf->flag = SSIDS_ERROR_CALL_SEQUENCE;
+   if (job < 0 || job > 4) return inf->flag = SSIDS_ERROR_JOB_OOR;
+   if (nrhs < 1 || ldx < fk->ak->sym.n) return inf->flag = SSIDS_ERROR_X_SIZE;
+   if (fk->ak->sym.n == 0) return inf->flag = 0;
+   double secs = 0;
+   int64_t nl = 0;
+   int flag = numeric_solve(fk->num, job, nrhs, x, ldx, on_device, &secs, &nl);
+   inf->time_solve = secs;
+   inf->reserved[1] = (int)nl;
+   return inf->flag = flag;
+}
+
+int b200ldlt_solve(void* akeep, void* fkeep, int job, int nrhs, double* x, int ldx,
+                   const b200ldlt_options*, b200ldlt_inform* inf) {
+   return solve_common(akeep, fkeep, job, nrhs, x, ldx, false, inf);
+}
+int b200ldlt_solve_device(void* akeep, void* fkeep, int job, int nrhs, double* d_x, int ldx,
+                          const b200ldlt_options*, b200ldlt_inform* inf) {
+   return solve_common(akeep, fkeep, job, nrhs, d_x, ldx, true, inf);
+}
+
+int b200ldlt_enquire_indef(void* akeep, void* fkeep, int* piv_order, double* d,
+                           const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
+   Fkeep* fk = static_cast<Fkeep*>(fkeep);
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   if (fk->ak != ak || !numeric_has_factors(fk->num)) return inf->flag = SSIDS_ERROR_CALL_SEQUENCE;
+   if (numeric_is_posdef(fk->num)) return inf->flag = SSIDS_ERROR_NOT_LDLT;
+   const int n = ak->sym.n;
+   const int base = (opt && opt->array_base) ? 1 : 0;
+   std::vector<int> po(n, 0);
+   if (d) std::memset(d, 0, sizeof(double) * 2 * n);
+   int flag = numeric_enquire(fk->num, piv_order ? po.data() : nullptr, d);
+   if (flag < 0) return inf->flag = flag;
+   if (piv_order) {
+      // po is indexed by analysis pivot position and holds +-(position+1); map back to variables
+      // (fkeep.F90:405-410) and shift to the caller's base
+      for (int i = 0; i < n; ++i) {
+         int p = ak->sym.order[i];
+         if (p < 0) { piv_order[i] = 0; continue; }
+         int v = po[p];
+         if (v == 0) { piv_order[i] = 0; continue; }   // delayed beyond the root / never eliminated
+         int pos = (v < 0 ? -v : v) - 1 + base;
+         if (base == 0 && pos == 0 && v < 0) pos = 0;   // -0 is not representable; see INTEGRATION.md
+         piv_order[i] = v < 0 ? -pos : pos;
+      }
+   }
+   return inf->flag = 0;
+}
+
+int b200ldlt_enquire_posdef(void* akeep, void* fkeep, double* d, b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !inf || !d) return SSIDS_ERROR_CALL_SEQUENCE;
+   Fkeep* fk = static_cast<Fkeep*>(fkeep);
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   if (fk->ak != ak || !numeric_has_factors(fk->num)) return inf->flag = SSIDS_ERROR_CALL_SEQUENCE;
+   if (!numeric_is_posdef(fk->num)) return inf->flag = SSIDS_ERROR_NOT_LLT;
+   const int n = ak->sym.n;
+   std::vector<double> dd(2 * (size_t)n, 0.0);
+   int flag = numeric_enquire(fk->num, nullptr, dd.data());
+   if (flag < 0) return inf->flag = flag;
+   // we hold L D L^T with D^{-1} stored; the Cholesky diagonal is sqrt(D)
+   for (int i = 0; i < n; ++i) d[i] = dd[2 * i] > 0 ? 1.0 / std::sqrt(dd[2 * i]) : 0.0;
+   return inf->flag = 0;
+}
+
+int b200ldlt_alter(void* akeep, void* fkeep, const double* d, b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !inf || !d) return SSIDS_ERROR_CALL_SEQUENCE;
+   Fkeep* fk = static_cast<Fkeep*>(fkeep);
+   if (fk->ak != akeep || !numeric_has_factors(fk->num)) return inf->flag = SSIDS_ERROR_CALL_SEQUENCE;
+   return inf->flag = numeric_alter(fk->num, d);
+}
+
+int b200ldlt_free_fkeep(void** fkeep) {
+   if (!fkeep || !*fkeep) return 0;
+   Fkeep* fk = static_cast<Fkeep*>(*fkeep);
+   if (fk->num) numeric_destroy(fk->num);
+   delete fk;
+   *fkeep = nullptr;
+   return 0;
+}
+
+int b200ldlt_free(void** akeep, void** fkeep) {
+   if (fkeep) b200ldlt_free_fkeep(fkeep);
+   if (akeep && *akeep) {
+      Akeep* ak = static_cast<Akeep*>(*akeep);
+      if (ak->plan) plan_destroy(ak->plan);
+      delete ak;
+      *akeep = nullptr;
+   }
+   return 0;
+}
+
+int b200ldlt_akeep_sizes(void* akeep, int* nnodes, int64_t* nrlist, int64_t* nnlist) {
+   if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   const Symbolic& s = static_cast<Akeep*>(akeep)->sym;
+   if (nnodes) *nnodes = s.nnodes;
+   if (nrlist) *nrlist = (int64_t)s.rlist.size();
+   if (nnlist) *nnlist = (int64_t)s.nlist.size() / 2;
+   return 0;
+}
+
+int b200ldlt_akeep_get(void* akeep, int base, int* sptr, int* sparent, int64_t* rptr, int* rlist,
+                       int64_t* nptr, int64_t* nlist, int* invp) {
+   if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   const Symbolic& s = static_cast<Akeep*>(akeep)->sym;
+   base = base ? 1 : 0;
+   if (sptr) for (int i = 0; i <= s.nnodes; ++i) sptr[i] = s.sptr[i] + base;
+   if (sparent) for (int i = 0; i < s.nnodes; ++i) sparent[i] = s.sparent[i] + base;
+   if (rptr) for (int i = 0; i <= s.nnodes; ++i) rptr[i] = s.rptr[i] + base;
+   if (rlist) for (size_t i = 0; i < s.rlist.size(); ++i) rlist[i] = s.rlist[i] + base;
+   if (nptr) for (int i = 0; i <= s.nnodes; ++i) nptr[i] = s.nptr[i] + base;
+   if (nlist) for (size_t i = 0; i < s.nlist.size(); ++i) nlist[i] = s.nlist[i] + base;
+   if (invp) for (int i = 0; i < s.n; ++i) invp[i] = s.invp[i] + base;
+   return 0;
+}
+
+int b200ldlt_partition(void* akeep, int nranks) {
+   if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   find_subtree_partition(ak->sym, nranks, 1.2, 0);
+   return ak->sym.nparts;
+}
+
+int b200ldlt_part_info(void* akeep, int part, int* first_node, int* last_node, int* owner,
+                       int* dest_node, int64_t* flops) {
+   if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   const Symbolic& s = static_cast<Akeep*>(akeep)->sym;
+   if (part < 0 || part >= s.nparts) return SSIDS_ERROR_CALL_SEQUENCE;
+   if (first_node) *first_node = s.part[part];
+   if (last_node) *last_node = s.part[part + 1] - 1;
+   if (owner) *owner = s.exec_loc[part];
+   if (dest_node) {
+      int last = s.part[part + 1] - 1;
+      *dest_node = (last >= 0 && last < s.nnodes && s.sparent[last] < s.nnodes) ? s.sparent[last] : -1;
+   }
+   if (flops) {
+      int64_t fl = 0;
+      for (int node = s.part[part]; node < s.part[part + 1]; ++node) {
+         int64_t m = s.rptr[node + 1] - s.rptr[node], nc = s.sptr[node + 1] - s.sptr[node];
+         for (int64_t j = m - nc + 1; j <= m; ++j) fl += j * j;
+      }
+      *flops = fl;
+   }
+   return 0;
+}
+
+// per-node results (parity tests compare these with the oracle's)
+int b200ldlt_node_info(void* fkeep, int node, int* m, int* n, int* nelim) {
+   if (!fkeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   return numeric_node_info(static_cast<Fkeep*>(fkeep)->num, node, m, n, nelim);
+}
+int b200ldlt_node_copy(void* fkeep, int node, double* L, double* d, int* perm) {
+   if (!fkeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   return numeric_node_copy(static_cast<Fkeep*>(fkeep)->num, node, L, d, perm);
+}
+
+}  // extern "C"

@@ -1,0 +1,1674 @@
+// b200ldlt numeric engine: multifrontal LDL^T on one B200 (sm_100a), level-scheduled.
+//
+// Reference behaviour restated here (not ported): src/ssids/cpu/NumericSubtree.hxx:53-275
+// (assemble -> factor -> contribution, inertia count), kernels/assemble.hxx:142-437,
+// kernels/ldlt_app.cxx (a-posteriori threshold pivoting), kernels/block_ldlt.hxx:290-414
+// (complete pivoting in the diagonal block), kernels/ldlt_tpp.cxx:166-270 (TPP finish) and the
+// solves NumericSubtree.hxx:280-400.  The schedule is our own: the assembly tree is cut into depth
+// levels; all fronts of a level are assembled and factorised by batched kernels; every front is
+// eliminated 32 columns at a time (diag-block factor -> apply+a-posteriori test -> commit ->
+// trailing update); columns that fail are swapped behind the candidates, retried by a TPP kernel
+// and otherwise delayed to the parent.  Progress counters live in device memory, the host reads
+// them once per level.  Extend-add is atomic-free (one launch per child ordinal) so results are
+// bit-reproducible run to run.
+//
+// Data layout in HBM: per front, L is m x n column-major (ld = m rounded
+// up to 2), D^{-1} is 2n doubles in SSIDS's format (ldlt_app.cxx:324-329), perm is n ints, the
+// contribution block C is (m-n)^2 column-major and lives one level (ping-pong arenas).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "engine.hpp"
+
+namespace b200 {
+
+constexpr int NB = 32;          // panel width
+constexpr int LDS = NB + 1;     // padded shared leading dimension
+constexpr int EA_TR = 256;      // extend-add tile rows
+constexpr int EA_TC = 8;        // extend-add tile cols
+constexpr int UT = 64;          // update tile
+#define DINF (__longlong_as_double(0x7ff0000000000000LL))
+
+struct FrontDev {
+   double* L;
+   double* C;
+   double* D;
+   int* perm;
+   double* Wl;     // m x NB   L panel (front-row indexed)
+   double* Wld;    // m x NB   L*D panel
+   double* Wo;     // m x NB   permuted original panel
+   double* dbuf;   // L11[NB*NB] | LD11[NB*NB] | A0p[NB*NB] | dk[2*NB+2]
+   int* ibuf;      // lperm[NB] | ptype[NB] | permuted
+   int m, n, ldl, ldc;
+   int ncol, nrow, ndelay_in, first_piv;
+   int done, end, w, fail;
+   int nelim, flag, slot, pad;
+};
+
+struct SlotStatic {
+   int ncol, nrow, parent, first_piv;   // parent slot, -1 for roots
+   int64_t rl_off, rel_off;
+   int child_begin, child_end;
+};
+
+struct Params {
+   double u, small_, lim;
+   int action, posdef;
+};
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double* felem(const FrontDev& f, int r, int c) {
+   // element (r,c), r >= c, of the front: candidate columns live in L, the rest in C
+   return (c < f.n) ? (f.L + (size_t)c * f.ldl + r) : (f.C + (size_t)(c - f.n) * f.ldc + (r - f.n));
+}
+
+__device__ __forceinline__ int compute_nelim(int fail, int w, const int* ptype) {
+   int nelim = fail < w ? fail : w;
+   if (nelim < w && nelim > 0 && ptype[nelim] == 2) nelim -= 1;
+   return nelim;
+}
+
+// symmetric swap of front indices a < b (both candidates, so every touched column is in L)
+__device__ void warp_sym_swap(const FrontDev& f, int a, int b, int lane) {
+   double* L = f.L;
+   const size_t ld = f.ldl;
+   for (int c = lane; c < a; c += 32) {
+      double t = L[a + c * ld]; L[a + c * ld] = L[b + c * ld]; L[b + c * ld] = t;
+   }
+   if (lane == 0) {
+      double t = L[a + a * ld]; L[a + a * ld] = L[b + b * ld]; L[b + b * ld] = t;
+      int s = f.perm[a]; f.perm[a] = f.perm[b]; f.perm[b] = s;
+   }
+   for (int c = a + 1 + lane; c < b; c += 32) {
+      double t = L[c + a * ld]; L[c + a * ld] = L[b + c * ld]; L[b + c * ld] = t;
+   }
+   for (int r = b + 1 + lane; r < f.m; r += 32) {
+      double t = L[r + a * ld]; L[r + a * ld] = L[r + b * ld]; L[r + b * ld] = t;
+   }
+}
+
+// ------------------------------------------------------------------------------------------
+// assembly kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_setup(FrontDev* fr, const SlotStatic* ss, const int* child_idx,
+                        const int* child_doff, int slot0, int nslots) {
+   int s = slot0 + blockIdx.x;
+   if (s >= slot0 + nslots) return;
+   FrontDev& f = fr[s];
+   const SlotStatic st = ss[s];
+   for (int j = threadIdx.x; j < st.ncol; j += blockDim.x) f.perm[j] = st.first_piv + j;
+   for (int ci = st.child_begin; ci < st.child_end; ++ci) {
+      const FrontDev& fc = fr[child_idx[ci]];
+      int nd = fc.n - fc.nelim, off = child_doff[ci];
+      for (int d = threadIdx.x; d < nd; d += blockDim.x)
+         f.perm[st.ncol + off + d] = fc.perm[fc.nelim + d];
+   }
+}
+
+__global__ void k_scatter_a(const FrontDev* fr, const int* aslot, const int* asrc, const int* acol,
+                            const int* arow, const double* __restrict__ val, int64_t e0, int64_t e1) {
+   int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= e1) return;
+   const FrontDev& f = fr[aslot[e]];
+   int r = arow[e], c = acol[e];
+   if (r >= f.ncol) r += f.ndelay_in;
+   f.L[(size_t)c * f.ldl + r] = val[asrc[e]];
+}
+
+// children -> parent, one launch per child ordinal so that no two CTAs touch the same parent entry
+__global__ void k_extend_add(const FrontDev* fr, const SlotStatic* ss, const int* rel,
+                             const int* list, const int* doffs, const int64_t* tileptr, int nlist) {
+   __shared__ int sdc[EA_TC];
+   int64_t b = blockIdx.x;
+   int lo = 0, hi = nlist;   // find i: tileptr[i] <= b < tileptr[i+1]
+   while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (tileptr[mid] <= b) lo = mid; else hi = mid;
+   }
+   const int cs = list[lo];
+   const FrontDev& fc = fr[cs];
+   const SlotStatic sc = ss[cs];
+   const FrontDev& fp = fr[sc.parent];
+   const int doff = doffs[lo];
+   const int t = fc.m - fc.nelim, nd = fc.n - fc.nelim;
+   const int ntr = (t + EA_TR - 1) / EA_TR;
+   const int tile = (int)(b - tileptr[lo]);
+   const int tr = tile % ntr, tc = tile / ntr;
+   const int c0 = tc * EA_TC;
+   if (tr * EA_TR + EA_TR - 1 < c0) return;   // tile entirely above the diagonal
+   const int* relc = rel + sc.rel_off;
+   const int pncol = fp.ncol, pdel = fp.ndelay_in;
+   if (threadIdx.x < EA_TC) {
+      int cc = c0 + threadIdx.x, d = 0;
+      if (cc < t) {
+         if (cc < nd) d = pncol + doff + cc;
+         else { d = relc[cc - nd]; if (d >= pncol) d += pdel; }
+      }
+      sdc[threadIdx.x] = d;
+   }
+   __syncthreads();
+   const int r = tr * EA_TR + threadIdx.x;
+   if (r >= t) return;
+   int dr;
+   if (r < nd) dr = pncol + doff + r;
+   else { dr = relc[r - nd]; if (dr >= pncol) dr += pdel; }
+   const int cend = min(min(c0 + EA_TC, t), r + 1);
+   for (int cc = c0; cc < cend; ++cc) {
+      double v = *felem(fc, fc.nelim + r, fc.nelim + cc);
+      int dc = sdc[cc - c0];
+      int rr = dr > dc ? dr : dc, cl = dr > dc ? dc : dr;
+      double* p = felem(fp, rr, cl);
+      *p += v;
+   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: (finish previous panel) + factor the next diagonal block with complete pivoting
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_diag(FrontDev* fr, const int* list, Params prm, int finish_only) {
+   FrontDev& f = fr[list[blockIdx.x]];
+   const int lane = threadIdx.x;
+   __shared__ double sa[NB * LDS], sld[NB * LDS], s0[NB * LDS];
+   __shared__ double sd[2 * NB + 2];
+   __shared__ int sptype[NB], slperm[NB];
+
+   int done = f.done, end = f.end, w = f.w, fail = f.fail;
+   __syncwarp();
+   if (f.flag < 0) return;
+   if (w > 0) {
+      int nelim = compute_nelim(fail, w, f.ibuf + NB);
+      int nfail = w - nelim;
+      done += nelim;
+      for (int q = 0; q < nfail; ++q) {
+         int a = done + q, b = end - 1 - q;
+         if (a < b) warp_sym_swap(f, a, b, lane);
+         __syncwarp();
+      }
+      end -= nfail;
+      if (prm.posdef && nfail > 0 && lane == 0) f.flag = SSIDS_ERROR_NOT_POS_DEF;
+   }
+   w = end - done;
+   if (w > NB) w = NB;
+   if (w < 0) w = 0;
+   if (finish_only) w = 0;
+   __syncwarp();
+   if (lane == 0) { f.done = done; f.end = end; f.w = w; f.fail = w; f.nelim = done; }
+   if (w == 0) return;
+
+   // load the block, full symmetric, plus a copy of the original
+   for (int i = lane; i < NB * LDS; i += 32) { sa[i] = 0.0; sld[i] = 0.0; }
+   __syncwarp();
+   for (int c = 0; c < w; ++c) {
+      if (lane >= c && lane < w) {
+         double v = f.L[(size_t)(done + c) * f.ldl + done + lane];
+         sa[lane + c * LDS] = v;
+         sa[c + lane * LDS] = v;
+      }
+   }
+   __syncwarp();
+   for (int i = lane; i < NB * LDS; i += 32) s0[i] = sa[i];
+   if (lane < NB) { slperm[lane] = lane; sptype[lane] = 0; }
+   for (int i = lane; i < 2 * NB + 2; i += 32) sd[i] = 0.0;
+   __syncwarp();
+
+   int err = 0;
+   for (int p = 0; p < w;) {
+      int t = p, mm = p, pivsiz = 1;
+      double a11 = 0, a21 = 0, a22 = 0, detscale = 0, detpiv = 0;
+      if (prm.posdef) {
+         a11 = sa[p + p * LDS];
+         if (!(a11 > 0.0)) { err = SSIDS_ERROR_NOT_POS_DEF; break; }
+      } else {
+         double best = -1.0;
+         int key = 0;
+         if (lane >= p && lane < w) {
+            for (int c = p; c <= lane; ++c) {
+               double v = fabs(sa[lane + c * LDS]);
+               if (v > best) { best = v; key = c * 64 + lane; }
+            }
+         } else {
+            key = 1 << 30;
+         }
+#pragma unroll
+         for (int off = 16; off > 0; off >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, best, off);
+            int ok = __shfl_xor_sync(0xffffffffu, key, off);
+            if (ov > best || (ov == best && ok < key)) { best = ov; key = ok; }
+         }
+         t = key & 63;
+         mm = key >> 6;
+         if (best < prm.small_) {
+            if (!prm.action) { err = SSIDS_ERROR_SINGULAR; break; }
+            for (int pp = p; pp < w; ++pp) {
+               if (lane >= pp && lane < w) {
+                  sa[lane + pp * LDS] = 0.0;
+                  sa[pp + lane * LDS] = 0.0;
+                  sld[lane + pp * LDS] = 0.0;
+               }
+               if (lane == 0) { sd[2 * pp] = 0.0; sd[2 * pp + 1] = 0.0; sptype[pp] = 0; }
+            }
+            __syncwarp();
+            break;
+         }
+         if (t == mm) {
+            pivsiz = 1;
+            a11 = sa[t + t * LDS];
+         } else {
+            a11 = sa[mm + mm * LDS];
+            a22 = sa[t + t * LDS];
+            a21 = sa[t + mm * LDS];
+            detscale = 1.0 / fabs(a21);
+            detpiv = (a11 * detscale) * a22 - fabs(a21);
+            if (fabs(detpiv) >= fabs(a21) / 2) {
+               pivsiz = 2;
+            } else if (fabs(a11) > fabs(a22)) {
+               pivsiz = 1; t = mm;
+            } else {
+               pivsiz = 1; a11 = a22; mm = t;
+            }
+         }
+      }
+      __syncwarp();
+      // symmetric swaps bringing the pivot(s) to p (and p+1)
+      for (int i = 0; i < pivsiz; ++i) {
+         int dst = p + i;
+         int src = (pivsiz == 1) ? t : (i == 0 ? mm : t);
+         if (src != dst) {
+            if (lane < w) {
+               double s = sa[dst + lane * LDS]; sa[dst + lane * LDS] = sa[src + lane * LDS]; sa[src + lane * LDS] = s;
+            }
+            __syncwarp();
+            if (lane < w) {
+               double s = sa[lane + dst * LDS]; sa[lane + dst * LDS] = sa[lane + src * LDS]; sa[lane + src * LDS] = s;
+            }
+            if (lane < p) {
+               double s = sld[dst + lane * LDS]; sld[dst + lane * LDS] = sld[src + lane * LDS]; sld[src + lane * LDS] = s;
+            }
+            if (lane == 0) { int q = slperm[dst]; slperm[dst] = slperm[src]; slperm[src] = q; }
+            __syncwarp();
+         }
+      }
+      if (pivsiz == 1) {
+         double d11 = 1.0 / sa[p + p * LDS];
+         double lr = 0.0;
+         if (lane > p && lane < w) {
+            double ldr = sa[lane + p * LDS];
+            sld[lane + p * LDS] = ldr;
+            lr = ldr * d11;
+            sa[lane + p * LDS] = lr;
+         }
+         __syncwarp();
+         if (lane > p && lane < w)
+            for (int c = p + 1; c < w; ++c) sa[lane + c * LDS] -= lr * sld[c + p * LDS];
+         __syncwarp();
+         if (lane == 0) { sd[2 * p] = d11; sd[2 * p + 1] = 0.0; sptype[p] = 0; sa[p + p * LDS] = 1.0; }
+         if (lane > p && lane < w) sa[p + lane * LDS] = 0.0;
+         __syncwarp();
+         p += 1;
+      } else {
+         double d11 = (a22 * detscale) / detpiv, d22 = (a11 * detscale) / detpiv;
+         double d21 = (-a21 * detscale) / detpiv;
+         double l1 = 0.0, l2 = 0.0;
+         if (lane > p + 1 && lane < w) {
+            double w1 = sa[lane + p * LDS], w2 = sa[lane + (p + 1) * LDS];
+            sld[lane + p * LDS] = w1;
+            sld[lane + (p + 1) * LDS] = w2;
+            l1 = d11 * w1 + d21 * w2;
+            l2 = d21 * w1 + d22 * w2;
+            sa[lane + p * LDS] = l1;
+            sa[lane + (p + 1) * LDS] = l2;
+         }
+         __syncwarp();
+         if (lane > p + 1 && lane < w)
+            for (int c = p + 2; c < w; ++c)
+               sa[lane + c * LDS] -= l1 * sld[c + p * LDS] + l2 * sld[c + (p + 1) * LDS];
+         __syncwarp();
+         if (lane == 0) {
+            sd[2 * p] = d11; sd[2 * p + 1] = d21; sd[2 * p + 2] = DINF; sd[2 * p + 3] = d22;
+            sptype[p] = 1; sptype[p + 1] = 2;
+            sa[p + p * LDS] = 1.0; sa[p + 1 + p * LDS] = 0.0; sa[p + (p + 1) * LDS] = 0.0;
+            sa[p + 1 + (p + 1) * LDS] = 1.0;
+            sld[p + 1 + p * LDS] = 0.0;
+         }
+         if (lane > p + 1 && lane < w) { sa[p + lane * LDS] = 0.0; sa[p + 1 + lane * LDS] = 0.0; }
+         __syncwarp();
+         p += 2;
+      }
+   }
+   if (err) {
+      if (lane == 0) { f.flag = err; f.w = 0; }
+      return;
+   }
+   __syncwarp();
+   // publish: L11, (LD)11, permuted original block, D, lperm/ptype, and the block's own rows of
+   // the panel workspaces
+   double* L11 = f.dbuf;
+   double* LD11 = f.dbuf + NB * NB;
+   double* A0p = f.dbuf + 2 * NB * NB;
+   double* dk = f.dbuf + 3 * NB * NB;
+   int permuted = 0;
+   for (int k = 0; k < w; ++k) {
+      if (lane < w) {
+         int i = lane;
+         double lv = i > k ? sa[i + k * LDS] : (i == k ? 1.0 : 0.0);
+         double ldv = i > k ? sld[i + k * LDS] : 0.0;
+         L11[i + k * NB] = lv;
+         LD11[i + k * NB] = ldv;
+         A0p[i + k * NB] = s0[slperm[i] + slperm[k] * LDS];
+         f.Wl[(size_t)k * f.m + done + i] = lv;
+         f.Wld[(size_t)k * f.m + done + i] = ldv;
+      }
+      if (slperm[k] != k) permuted = 1;
+   }
+   for (int i = lane; i < 2 * NB + 2; i += 32) dk[i] = sd[i];
+   if (lane < NB) { f.ibuf[lane] = slperm[lane]; f.ibuf[NB + lane] = sptype[lane]; }
+   if (lane == 0) f.ibuf[2 * NB] = permuted;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: L21 = A21 P L11^{-T} D^{-1} for the rows below the block, with the a-posteriori test
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_apply(FrontDev* fr, const int* list, Params prm) {
+   FrontDev& f = fr[list[blockIdx.x]];
+   const int w = f.w;
+   if (w == 0 || f.flag < 0) return;
+   const int done = f.done, m = f.m;
+   const int r0 = done + w + blockIdx.y * 128;
+   if (r0 >= m) return;
+   __shared__ double sL[NB * NB];
+   __shared__ double sdk[2 * NB + 2];
+   __shared__ int slperm[NB], sptype[NB];
+   for (int i = threadIdx.x; i < NB * NB; i += 128) sL[i] = f.dbuf[i];
+   for (int i = threadIdx.x; i < 2 * NB + 2; i += 128) sdk[i] = f.dbuf[3 * NB * NB + i];
+   if (threadIdx.x < NB) { slperm[threadIdx.x] = f.ibuf[threadIdx.x]; sptype[threadIdx.x] = f.ibuf[NB + threadIdx.x]; }
+   __syncthreads();
+   const int r = r0 + threadIdx.x;
+   int myfail = w;
+   if (r < m) {
+      double x[NB];
+      const size_t ldl = f.ldl;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+         x[k] = 0.0;
+         if (k < w) {
+            x[k] = f.L[(size_t)(done + slperm[k]) * ldl + r];
+            f.Wo[(size_t)k * m + r] = x[k];
+         }
+      }
+#pragma unroll
+      for (int k = 1; k < NB; ++k) {
+         if (k < w) {
+            double s = x[k];
+#pragma unroll
+            for (int i = 0; i < k; ++i) s -= x[i] * sL[k + i * NB];
+            x[k] = s;
+         }
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+         if (k < w) {
+            int pt = sptype[k];
+            double l;
+            if (pt == 0) {
+               double d11 = sdk[2 * k];
+               if (d11 == 0.0) l = (fabs(x[k]) < prm.small_) ? 0.0 : DINF * x[k];
+               else l = x[k] * d11;
+            } else if (pt == 1) {
+               l = sdk[2 * k] * x[k] + sdk[2 * k + 1] * x[(k + 1) & (NB - 1)];
+            } else {
+               l = sdk[2 * k - 1] * x[(k - 1) & (NB - 1)] + sdk[2 * k + 1] * x[k];
+            }
+            f.Wl[(size_t)k * m + r] = l;
+            f.Wld[(size_t)k * m + r] = x[k];
+            if (!prm.posdef && (!(fabs(l) <= prm.lim)) && k < myfail) myfail = k;
+         }
+      }
+   }
+#pragma unroll
+   for (int off = 16; off > 0; off >>= 1) myfail = min(myfail, __shfl_xor_sync(0xffffffffu, myfail, off));
+   if ((threadIdx.x & 31) == 0 && myfail < w) atomicMin(&f.fail, myfail);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: commit the panel: accepted columns become L, failed columns get their (permuted)
+// original values back; finished L columns and the pivot list follow the block's permutation
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_commit(FrontDev* fr, const int* list) {
+   FrontDev& f = fr[list[blockIdx.x]];
+   const int w = f.w;
+   if (w == 0 || f.flag < 0) return;
+   const int done = f.done, m = f.m;
+   const int* lperm = f.ibuf;
+   const int nelim = compute_nelim(f.fail, w, f.ibuf + NB);
+   const int nrchunk = (m + 127) / 128;
+   const size_t ldl = f.ldl;
+   if ((int)blockIdx.y < nrchunk) {
+      const int r = blockIdx.y * 128 + threadIdx.x;
+      if (r < done || r >= m) return;
+      if (r >= done + w) {
+         for (int k = 0; k < w; ++k)
+            f.L[(size_t)(done + k) * ldl + r] = k < nelim ? f.Wl[(size_t)k * m + r] : f.Wo[(size_t)k * m + r];
+      } else {
+         const int i = r - done;
+         const double* L11 = f.dbuf;
+         const double* A0p = f.dbuf + 2 * NB * NB;
+         for (int k = 0; k <= i; ++k)
+            f.L[(size_t)(done + k) * ldl + r] = k < nelim ? (i == k ? 1.0 : L11[i + k * NB]) : A0p[i + k * NB];
+         if (i == 0) {
+            const double* dk = f.dbuf + 3 * NB * NB;
+            for (int k = 0; k < nelim; ++k) {
+               f.D[2 * (done + k)] = dk[2 * k];
+               f.D[2 * (done + k) + 1] = dk[2 * k + 1];
+            }
+            if (f.ibuf[2 * NB]) {
+               int tmp[NB];
+#pragma unroll
+               for (int q = 0; q < NB; ++q) tmp[q] = q < w ? f.perm[done + lperm[q]] : 0;
+#pragma unroll
+               for (int q = 0; q < NB; ++q) if (q < w) f.perm[done + q] = tmp[q];
+            }
+         }
+      }
+   } else {
+      if (!f.ibuf[2 * NB]) return;
+      const int c = (blockIdx.y - nrchunk) * 128 + threadIdx.x;
+      if (c >= done) return;
+      double tmp[NB];
+#pragma unroll
+      for (int q = 0; q < NB; ++q) tmp[q] = q < w ? f.L[(size_t)c * ldl + done + lperm[q]] : 0.0;
+#pragma unroll
+      for (int q = 0; q < NB; ++q) if (q < w) f.L[(size_t)c * ldl + done + q] = tmp[q];
+   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: trailing update  T(r,c) -= sum_k Wl(r,k) * Wld(c,k), r >= c >= done+nelim, lower tiles only
+// (FP64 FMA version; the DMMA version is k_update_mma below)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_from_id(int id, int& ti, int& tj) {
+   int t = (int)((sqrtf(8.0f * (float)id + 1.0f) - 1.0f) * 0.5f);
+   while ((t + 1) * (t + 2) / 2 <= id) ++t;
+   while (t * (t + 1) / 2 > id) --t;
+   ti = t;
+   tj = id - t * (t + 1) / 2;
+}
+
+__global__ void __launch_bounds__(256) k_update(FrontDev* fr, const int* list) {
+   const FrontDev& f = fr[list[blockIdx.x]];
+   const int w = f.w;
+   if (w == 0 || f.flag < 0) return;
+   const int nelim = compute_nelim(f.fail, w, f.ibuf + NB);
+   if (nelim == 0) return;
+   const int s0 = f.done + nelim, m = f.m;
+   const int nt = (m - s0 + UT - 1) / UT;
+   const int ntiles = nt * (nt + 1) / 2;
+   __shared__ double As[NB][UT + 1], Bs[NB][UT + 1];
+   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+   for (int id = blockIdx.y; id < ntiles; id += gridDim.y) {
+      int ti, tj;
+      tile_from_id(id, ti, tj);
+      const int rbase = s0 + ti * UT, cbase = s0 + tj * UT;
+      __syncthreads();
+      for (int i = threadIdx.x; i < NB * UT; i += 256) {
+         int k = i / UT, rr = i % UT;
+         double a = 0.0, b = 0.0;
+         if (k < nelim) {
+            if (rbase + rr < m) a = f.Wl[(size_t)k * m + rbase + rr];
+            if (cbase + rr < m) b = f.Wld[(size_t)k * m + cbase + rr];
+         }
+         As[k][rr] = a;
+         Bs[k][rr] = b;
+      }
+      __syncthreads();
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      for (int k = 0; k < nelim; ++k) {
+         double av[4], bv[4];
+#pragma unroll
+         for (int i = 0; i < 4; ++i) { av[i] = As[k][tx + 16 * i]; bv[i] = Bs[k][ty + 16 * i]; }
+#pragma unroll
+         for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+         int c = cbase + ty + 16 * j;
+         if (c >= m) continue;
+#pragma unroll
+         for (int i = 0; i < 4; ++i) {
+            int r = rbase + tx + 16 * i;
+            if (r >= m || r < c) continue;
+            double* p = felem(f, r, c);
+            *p -= acc[i][j];
+         }
+      }
+   }
+}
+
+// ------------------------------------------------------------------------------------------
+// TPP finish (ldlt_tpp.cxx:166-270), one CTA per front, right-looking on the whole trailing
+// matrix.  Rare path: only fronts whose a-posteriori pass left columns behind come here.
+// ------------------------------------------------------------------------------------------
+__device__ double block_max(double v, double* sred) {
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+   for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+   __syncthreads();
+   if (lane == 0) sred[wid] = v;
+   __syncthreads();
+   double r = sred[0];
+   for (int i = 1; i < nw; ++i) r = fmax(r, sred[i]);
+   return r;
+}
+
+// max |.| over row/col `col` of the trailing matrix from `from`, excluding `excl` and the diagonal
+__device__ double tpp_rc_max(const FrontDev& f, int from, int col, int excl, double* sred) {
+   double v = 0.0;
+   for (int c = from + threadIdx.x; c < col; c += blockDim.x)
+      if (c != excl) v = fmax(v, fabs(*felem(f, col, c)));
+   for (int r = col + 1 + threadIdx.x; r < f.m; r += blockDim.x)
+      if (r != excl) v = fmax(v, fabs(*felem(f, r, col)));
+   return block_max(v, sred);
+}
+
+__device__ void block_sym_swap(const FrontDev& f, int a, int b) {
+   if (a == b) return;
+   if (a > b) { int s = a; a = b; b = s; }
+   double* L = f.L;
+   const size_t ld = f.ldl;
+   for (int c = threadIdx.x; c < a; c += blockDim.x) {
+      double t = L[a + c * ld]; L[a + c * ld] = L[b + c * ld]; L[b + c * ld] = t;
+   }
+   if (threadIdx.x == 0) {
+      double t = L[a + a * ld]; L[a + a * ld] = L[b + b * ld]; L[b + b * ld] = t;
+      int s = f.perm[a]; f.perm[a] = f.perm[b]; f.perm[b] = s;
+   }
+   for (int c = a + 1 + threadIdx.x; c < b; c += blockDim.x) {
+      double t = L[c + a * ld]; L[c + a * ld] = L[b + c * ld]; L[b + c * ld] = t;
+   }
+   for (int r = b + 1 + threadIdx.x; r < f.m; r += blockDim.x) {
+      double t = L[r + a * ld]; L[r + a * ld] = L[r + b * ld]; L[r + b * ld] = t;
+   }
+   __syncthreads();
+}
+
+__device__ void tpp_elim1(const FrontDev& f, int ne, double d11) {
+   double* l1 = f.Wld;   // column 0 of the workspace, front-row indexed
+   const int m = f.m;
+   for (int r = ne + 1 + threadIdx.x; r < m; r += blockDim.x) {
+      double* p = f.L + (size_t)ne * f.ldl + r;
+      double v = *p;
+      l1[r] = v;
+      *p = v * d11;
+   }
+   __syncthreads();
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+   for (int c = ne + 1 + wid; c < m; c += nw) {
+      double b = l1[c];
+      if (b == 0.0) continue;
+      for (int r = c + lane; r < m; r += 32) *felem(f, r, c) -= f.L[(size_t)ne * f.ldl + r] * b;
+   }
+   __syncthreads();
+   if (threadIdx.x == 0) { f.L[(size_t)ne * f.ldl + ne] = 1.0; f.D[2 * ne] = d11; f.D[2 * ne + 1] = 0.0; }
+   __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_tpp(FrontDev* fr, const int* list, Params prm) {
+   FrontDev& f = fr[list[blockIdx.x]];
+   __shared__ double sred[32];
+   __shared__ int sidx[8];
+   if (f.flag < 0) return;
+   int ne = f.done;
+   const int n = f.n, m = f.m;
+   const size_t ldl = f.ldl;
+   double* l1 = f.Wld;
+   double* l2 = f.Wld + m;
+   while (ne < n) {
+      // zero column at ne?
+      {
+         double v = fabs(f.L[ne * ldl + ne]);
+         if (threadIdx.x != 0) v = 0.0;
+         v = fmax(v, tpp_rc_max(f, ne, ne, -1, sred));
+         v = block_max(v, sred);
+         if (v < prm.small_) {
+            if (!prm.action) { if (threadIdx.x == 0) f.flag = SSIDS_ERROR_SINGULAR; break; }
+            for (int r = ne + threadIdx.x; r < m; r += blockDim.x) f.L[ne * ldl + r] = 0.0;
+            __syncthreads();
+            if (threadIdx.x == 0) { f.L[ne * ldl + ne] = 1.0; f.D[2 * ne] = 0.0; f.D[2 * ne + 1] = 0.0; }
+            ne++;
+            __syncthreads();
+            continue;
+         }
+      }
+      bool found = false;
+      for (int p = ne + 1; p < n && !found; ++p) {
+         // zero column p?
+         {
+            double v = (threadIdx.x == 0) ? fabs(f.L[p * ldl + p]) : 0.0;
+            v = fmax(v, tpp_rc_max(f, ne, p, -1, sred));
+            v = block_max(v, sred);
+            if (v < prm.small_) {
+               if (!prm.action) { if (threadIdx.x == 0) f.flag = SSIDS_ERROR_SINGULAR; ne = n + 1; break; }
+               block_sym_swap(f, ne, p);
+               for (int r = ne + threadIdx.x; r < m; r += blockDim.x) f.L[ne * ldl + r] = 0.0;
+               __syncthreads();
+               if (threadIdx.x == 0) { f.L[ne * ldl + ne] = 1.0; f.D[2 * ne] = 0.0; f.D[2 * ne + 1] = 0.0; }
+               ne++;
+               found = true;
+               __syncthreads();
+               break;
+            }
+         }
+         // t = argmax |A(p, ne..p-1)| (first maximum)
+         double best = -1.0;
+         int bt = ne;
+         for (int c = ne + threadIdx.x; c < p; c += blockDim.x) {
+            double v = fabs(f.L[c * ldl + p]);
+            if (v > best) { best = v; bt = c; }
+         }
+         double gbest = block_max(best, sred);
+         __syncthreads();
+         if (threadIdx.x == 0) sidx[0] = 1 << 30;
+         __syncthreads();
+         if (best == gbest && best >= 0.0) atomicMin(&sidx[0], bt);
+         __syncthreads();
+         const int t = sidx[0];
+         double maxt = tpp_rc_max(f, ne, t, p, sred);
+         double maxp = tpp_rc_max(f, ne, p, t, sred);
+         double a11 = f.L[t * ldl + t], a21 = f.L[t * ldl + p], a22 = f.L[p * ldl + p];
+         double maxpiv = fmax(fabs(a11), fmax(fabs(a21), fabs(a22)));
+         bool ok2 = false;
+         double d11 = 0, d21 = 0, d22 = 0;
+         if (maxpiv >= prm.small_) {
+            double detscale = 1.0 / maxpiv;
+            double detpiv0 = (a11 * detscale) * a22, detpiv1 = (a21 * detscale) * a21;
+            double detpiv = detpiv0 - detpiv1;
+            if (!(fabs(detpiv) < fmax(prm.small_, fmax(fabs(detpiv0 / 2), fabs(detpiv1 / 2))))) {
+               d11 = (a22 * detscale) / detpiv; d21 = (-a21 * detscale) / detpiv; d22 = (a11 * detscale) / detpiv;
+               if (fmax(maxp, maxt) < prm.small_) ok2 = true;
+               else {
+                  double x1 = fabs(d11) * maxt + fabs(d21) * maxp, x2 = fabs(d21) * maxt + fabs(d22) * maxp;
+                  ok2 = (prm.u * fmax(x1, x2) < 1.0);
+               }
+            }
+         }
+         __syncthreads();
+         if (ok2) {
+            block_sym_swap(f, ne, t);
+            block_sym_swap(f, ne + 1, p);
+            for (int r = ne + 2 + threadIdx.x; r < m; r += blockDim.x) {
+               double w1 = f.L[ne * ldl + r], w2 = f.L[(ne + 1) * ldl + r];
+               l1[r] = w1; l2[r] = w2;
+               f.L[ne * ldl + r] = d11 * w1 + d21 * w2;
+               f.L[(ne + 1) * ldl + r] = d21 * w1 + d22 * w2;
+            }
+            __syncthreads();
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+            for (int c = ne + 2 + wid; c < m; c += nw) {
+               double b1 = l1[c], b2 = l2[c];
+               for (int r = c + lane; r < m; r += 32)
+                  *felem(f, r, c) -= f.L[ne * ldl + r] * b1 + f.L[(ne + 1) * ldl + r] * b2;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+               f.L[ne * ldl + ne] = 1.0; f.L[ne * ldl + ne + 1] = 0.0; f.L[(ne + 1) * ldl + ne + 1] = 1.0;
+               f.D[2 * ne] = d11; f.D[2 * ne + 1] = d21; f.D[2 * ne + 2] = DINF; f.D[2 * ne + 3] = d22;
+            }
+            ne += 2;
+            found = true;
+            __syncthreads();
+            break;
+         }
+         maxp = fmax(maxp, fabs(a21));
+         if (fabs(a22) >= prm.u * maxp) {
+            block_sym_swap(f, ne, p);
+            double dd = 1.0 / f.L[ne * ldl + ne];
+            __syncthreads();
+            tpp_elim1(f, ne, dd);
+            ne += 1;
+            found = true;
+            break;
+         }
+      }
+      if (ne > n) break;
+      if (!found) {
+         double maxp = tpp_rc_max(f, ne, ne, -1, sred);
+         double app = f.L[ne * ldl + ne];
+         __syncthreads();
+         if (fabs(app) >= prm.u * maxp) {
+            tpp_elim1(f, ne, 1.0 / app);
+            ne += 1;
+         } else {
+            break;
+         }
+      }
+   }
+   __syncthreads();
+   if (ne > n) ne = n;
+   if (threadIdx.x == 0) { f.done = ne; f.nelim = ne; }
+}
+
+__global__ void k_collect(const FrontDev* fr, int slot0, int nslots, int* out) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nslots) return;
+   out[2 * i] = fr[slot0 + i].done;
+   out[2 * i + 1] = fr[slot0 + i].flag;
+}
+
+// inertia: counters[0..2] = num_neg, num_two, num_zero  (NumericSubtree.hxx:242-274)
+__global__ void k_stats(const FrontDev* fr, int nslots, int* counters) {
+   const int lane = threadIdx.x & 31;
+   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   if (s >= nslots) return;
+   const FrontDev& f = fr[s];
+   int neg = 0, two = 0, zero = 0;
+   for (int i = lane; i < f.nelim; i += 32) {
+      double a11 = f.D[2 * i];
+      if (isinf(a11) && i > 0) continue;   // second column of a 2x2
+      if (i + 1 < f.nelim && isinf(f.D[2 * i + 2])) {
+         double a21 = f.D[2 * i + 1], a22 = f.D[2 * i + 3];
+         double det = a11 * a22 - a21 * a21, tr = a11 + a22;
+         two++;
+         if (det < 0) neg++;
+         else if (tr < 0) neg += 2;
+      } else {
+         if (a11 == 0.0) zero++;
+         if (a11 < 0.0) neg++;
+      }
+   }
+#pragma unroll
+   for (int off = 16; off > 0; off >>= 1) {
+      neg += __shfl_xor_sync(0xffffffffu, neg, off);
+      two += __shfl_xor_sync(0xffffffffu, two, off);
+      zero += __shfl_xor_sync(0xffffffffu, zero, off);
+   }
+   if (lane == 0) {
+      if (neg) atomicAdd(&counters[0], neg);
+      if (two) atomicAdd(&counters[1], two);
+      if (zero) atomicAdd(&counters[2], zero);
+   }
+}
+
+// ------------------------------------------------------------------------------------------
+// solve kernels (level scheduled; one CTA per front; per-front work vectors, no atomics)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int row_gidx(const FrontDev& f, const int* rl, int r) {
+   return r < f.n ? f.perm[r] : rl[f.ncol + (r - f.n)];
+}
+
+__global__ void k_permute_in(const double* __restrict__ x, double* __restrict__ xp, const int* order, int n) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && order[i] >= 0) xp[order[i]] = x[i];
+}
+__global__ void k_permute_out(double* __restrict__ x, const double* __restrict__ xp, const int* order, int n) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && order[i] >= 0) x[i] = xp[order[i]];
+}
+
+// forward: xw = [b(pivots); 0] + children, y = L11^{-1} xw1, xw2 -= L21 y, x(pivots) = y
+__global__ void __launch_bounds__(256) k_solve_fwd(const FrontDev* fr, const SlotStatic* ss,
+                                                   const int* child_idx, const int* child_doff,
+                                                   const int* rel, const int64_t* xw_off, double* XW,
+                                                   double* x, int slot0, int posdef_scale) {
+   const int s = slot0 + blockIdx.x;
+   const FrontDev& f = fr[s];
+   const SlotStatic st = ss[s];
+   double* xw = XW + xw_off[s];
+   const int m = f.m, ne = f.nelim;
+   __shared__ double ys[NB];
+   for (int r = threadIdx.x; r < m; r += blockDim.x) xw[r] = r < ne ? x[f.perm[r]] : 0.0;
+   __syncthreads();
+   for (int ci = st.child_begin; ci < st.child_end; ++ci) {
+      const int cs = child_idx[ci];
+      const FrontDev& fc = fr[cs];
+      const int t = fc.m - fc.nelim, nd = fc.n - fc.nelim, doff = child_doff[ci];
+      const double* xc = XW + xw_off[cs] + fc.nelim;
+      const int* relc = rel + ss[cs].rel_off;
+      for (int rr = threadIdx.x; rr < t; rr += blockDim.x) {
+         int d;
+         if (rr < nd) d = f.ncol + doff + rr;
+         else { d = relc[rr - nd]; if (d >= f.ncol) d += f.ndelay_in; }
+         xw[d] += xc[rr];
+      }
+      __syncthreads();
+   }
+   const size_t ldl = f.ldl;
+   for (int k0 = 0; k0 < ne; k0 += NB) {
+      const int kb = min(NB, ne - k0);
+      if (threadIdx.x < 32) {
+         const int i = threadIdx.x;
+         double xi = i < kb ? xw[k0 + i] : 0.0;
+         for (int j = 0; j < kb; ++j) {
+            double yj = __shfl_sync(0xffffffffu, xi, j);
+            if (i > j && i < kb) xi -= f.L[(size_t)(k0 + j) * ldl + k0 + i] * yj;
+         }
+         if (i < kb) { xw[k0 + i] = xi; ys[i] = xi; }
+      }
+      __syncthreads();
+      for (int r = k0 + kb + threadIdx.x; r < m; r += blockDim.x) {
+         double sacc = 0.0;
+         for (int j = 0; j < kb; ++j) sacc += f.L[(size_t)(k0 + j) * ldl + r] * ys[j];
+         xw[r] -= sacc;
+      }
+      __syncthreads();
+   }
+   for (int k = threadIdx.x; k < ne; k += blockDim.x) {
+      double v = xw[k];
+      if (posdef_scale) v *= sqrt(f.D[2 * k]);   // L_chol = L sqrt(D): y_chol = D^{-1/2} y  (D stored inverted)
+      x[f.perm[k]] = v;
+   }
+}
+
+__global__ void k_solve_diag(const FrontDev* fr, double* x, int nslots) {
+   const int lane = threadIdx.x & 31;
+   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   if (s >= nslots) return;
+   const FrontDev& f = fr[s];
+   for (int i = lane; i < f.nelim; i += 32) {
+      double a11 = f.D[2 * i];
+      if (isinf(a11) && i > 0) continue;
+      if (i + 1 < f.nelim && isinf(f.D[2 * i + 2])) {
+         double d21 = f.D[2 * i + 1], d22 = f.D[2 * i + 3];
+         double x1 = x[f.perm[i]], x2 = x[f.perm[i + 1]];
+         x[f.perm[i]] = a11 * x1 + d21 * x2;
+         x[f.perm[i + 1]] = d21 * x1 + d22 * x2;
+      } else {
+         x[f.perm[i]] *= a11;
+      }
+   }
+}
+
+// backward: x1 = L11^{-T} (y1 - L21^T x2); with do_diag the D^{-1} product is applied first
+__global__ void __launch_bounds__(256) k_solve_bwd(const FrontDev* fr, const SlotStatic* ss,
+                                                   const int* rlist, const int64_t* xw_off, double* XW,
+                                                   double* x, int slot0, int do_diag, int posdef_scale) {
+   const int s = slot0 + blockIdx.x;
+   const FrontDev& f = fr[s];
+   const int* rl = rlist + ss[s].rl_off;
+   double* xw = XW + xw_off[s];
+   const int m = f.m, ne = f.nelim;
+   __shared__ double dots[NB];
+   for (int r = threadIdx.x; r < m; r += blockDim.x) {
+      double v;
+      if (r >= ne) v = x[row_gidx(f, rl, r)];
+      else {
+         v = x[f.perm[r]];
+         if (posdef_scale) v *= sqrt(f.D[2 * r]);
+         else if (do_diag) {
+            double a11 = f.D[2 * r];
+            if (isinf(a11) && r > 0) {          // second of a 2x2: d21*x1 + d22*x2
+               v = f.D[2 * r - 1] * x[f.perm[r - 1]] + f.D[2 * r + 1] * v;
+            } else if (r + 1 < ne && isinf(f.D[2 * r + 2])) {
+               v = a11 * v + f.D[2 * r + 1] * x[f.perm[r + 1]];
+            } else {
+               v = a11 * v;
+            }
+         }
+      }
+      xw[r] = v;
+   }
+   __syncthreads();
+   const size_t ldl = f.ldl;
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+   const int nblk = (ne + NB - 1) / NB;
+   for (int b = nblk - 1; b >= 0; --b) {
+      const int k0 = b * NB, kb = min(NB, ne - k0);
+      for (int j = wid; j < kb; j += nw) {
+         double sacc = 0.0;
+         const double* col = f.L + (size_t)(k0 + j) * ldl;
+         for (int r = k0 + kb + lane; r < m; r += 32) sacc += col[r] * xw[r];
+#pragma unroll
+         for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+         if (lane == 0) dots[j] = sacc;
+      }
+      __syncthreads();
+      if (threadIdx.x < 32) {
+         const int i = threadIdx.x;
+         double v = i < kb ? xw[k0 + i] - dots[i] : 0.0;
+         for (int j = kb - 1; j >= 0; --j) {
+            double xj = __shfl_sync(0xffffffffu, v, j);
+            if (i < j) v -= f.L[(size_t)(k0 + i) * ldl + k0 + j] * xj;
+         }
+         if (i < kb) xw[k0 + i] = v;
+      }
+      __syncthreads();
+   }
+   for (int k = threadIdx.x; k < ne; k += blockDim.x) x[f.perm[k]] = xw[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Arena {
+   struct Chunk { char* p; size_t size; };
+   std::vector<Chunk> chunks;
+   size_t cur = 0, off = 0, min_chunk = (size_t)64 << 20;
+   int* err = nullptr;
+   void* alloc(size_t bytes) {
+      bytes = align_up(bytes ? bytes : 1, 256);
+      for (;;) {
+         if (cur < chunks.size() && off + bytes <= chunks[cur].size) {
+            void* p = chunks[cur].p + off;
+            off += bytes;
+            return p;
+         }
+         if (cur + 1 < chunks.size()) { ++cur; off = 0; continue; }
+         size_t sz = std::max(min_chunk, bytes);
+         char* p = nullptr;
+         cudaError_t e = cudaMalloc(&p, sz);
+         if (e != cudaSuccess) { if (err) *err = (int)e; return nullptr; }
+         chunks.push_back({p, sz});
+         cur = chunks.size() - 1;
+         off = 0;
+      }
+   }
+   void reserve(size_t bytes) {   // make sure the first chunk can hold `bytes`
+      if (!chunks.empty()) return;
+      bytes = align_up(std::max(bytes, (size_t)256), 256);
+      char* p = nullptr;
+      if (cudaMalloc(&p, bytes) == cudaSuccess) chunks.push_back({p, bytes});
+      else cudaGetLastError();
+   }
+   void reset() { cur = 0; off = 0; }
+   size_t capacity() const { size_t s = 0; for (auto& c : chunks) s += c.size; return s; }
+   void release() { for (auto& c : chunks) cudaFree(c.p); chunks.clear(); reset(); }
+};
+
+class Plan {
+  public:
+   const Symbolic* sym = nullptr;
+   int device = 0;
+   int nnodes = 0, nlevels = 0;
+   std::vector<int> lvl_ptr, slot_node, node_slot;
+   std::vector<SlotStatic> hss;
+   std::vector<int> child_idx;
+   std::vector<int64_t> lvl_a_ptr;
+   int max_children = 0;
+   // device
+   SlotStatic* d_ss = nullptr;
+   int *d_child_idx = nullptr, *d_rlist = nullptr, *d_rel = nullptr, *d_order = nullptr;
+   int *d_aslot = nullptr, *d_asrc = nullptr, *d_acol = nullptr, *d_arow = nullptr;
+   int64_t est_factor_doubles = 0, est_c_doubles[2] = {0, 0}, est_ws_doubles = 0;
+   ~Plan() {
+      cudaSetDevice(device);
+      cudaFree(d_ss); cudaFree(d_child_idx); cudaFree(d_rlist); cudaFree(d_rel); cudaFree(d_order);
+      cudaFree(d_aslot); cudaFree(d_asrc); cudaFree(d_acol); cudaFree(d_arow);
+   }
+};
+
+template <typename T>
+static cudaError_t upload(T** d, const std::vector<T>& h) {
+   size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+   cudaError_t e = cudaMalloc(d, bytes);
+   if (e != cudaSuccess) return e;
+   if (!h.empty()) e = cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+   return e;
+}
+
+Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
+   *cuda_error = 0;
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0) { *cuda_error = e != cudaSuccess ? (int)e : (int)cudaErrorNoDevice; cudaGetLastError(); return nullptr; }
+   if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+   if ((e = cudaSetDevice(device)) != cudaSuccess) { *cuda_error = (int)e; return nullptr; }
+   Plan* P = new Plan();
+   P->sym = &sym;
+   P->device = device;
+   const int nn = sym.nnodes;
+   P->nnodes = nn;
+   // depth levels, deepest first
+   std::vector<int> depth(nn + 1, 0);
+   int maxd = 0;
+   for (int i = nn - 1; i >= 0; --i) {
+      depth[i] = depth[sym.sparent[i]] + 1;
+      maxd = std::max(maxd, depth[i]);
+   }
+   P->nlevels = maxd;
+   std::vector<int> lvl(nn);
+   P->lvl_ptr.assign(maxd + 1, 0);
+   for (int i = 0; i < nn; ++i) { lvl[i] = maxd - depth[i]; P->lvl_ptr[lvl[i] + 1]++; }
+   for (int l = 0; l < maxd; ++l) P->lvl_ptr[l + 1] += P->lvl_ptr[l];
+   P->slot_node.assign(nn, 0);
+   P->node_slot.assign(nn, 0);
+   {
+      std::vector<int> pos(P->lvl_ptr.begin(), P->lvl_ptr.end() - 1);
+      for (int i = 0; i < nn; ++i) { int s = pos[lvl[i]]++; P->slot_node[s] = i; P->node_slot[i] = s; }
+   }
+   // static per-slot data, children (ascending node order), relative indices
+   P->hss.assign(nn, SlotStatic());
+   std::vector<int> nchild(nn + 1, 0);
+   for (int i = 0; i < nn; ++i) nchild[sym.sparent[i]]++;
+   std::vector<int> cptr(nn + 1, 0);
+   {
+      int acc = 0;
+      for (int s = 0; s < nn; ++s) { cptr[s] = acc; acc += nchild[P->slot_node[s]]; }
+      cptr[nn] = acc;
+      P->child_idx.assign(acc, 0);
+      std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+      for (int i = 0; i < nn; ++i) {
+         int p = sym.sparent[i];
+         if (p < nn) P->child_idx[fill[P->node_slot[p]]++] = P->node_slot[i];
+      }
+   }
+   std::vector<int> rel;
+   int64_t rel_total = 0;
+   for (int i = 0; i < nn; ++i) rel_total += (sym.rptr[i + 1] - sym.rptr[i]) - (sym.sptr[i + 1] - sym.sptr[i]);
+   rel.assign(rel_total, 0);
+   {
+      std::vector<int> map(sym.n, 0);
+      std::vector<int64_t> rel_off(nn, 0);
+      int64_t acc = 0;
+      for (int s = 0; s < nn; ++s) {
+         int i = P->slot_node[s];
+         rel_off[i] = acc;
+         acc += (sym.rptr[i + 1] - sym.rptr[i]) - (sym.sptr[i + 1] - sym.sptr[i]);
+      }
+      for (int s = 0; s < nn; ++s) {
+         int i = P->slot_node[s];
+         SlotStatic& st = P->hss[s];
+         st.ncol = sym.sptr[i + 1] - sym.sptr[i];
+         st.nrow = (int)(sym.rptr[i + 1] - sym.rptr[i]);
+         st.parent = sym.sparent[i] < nn ? P->node_slot[sym.sparent[i]] : -1;
+         st.first_piv = sym.sptr[i];
+         st.rl_off = sym.rptr[i];
+         st.rel_off = rel_off[i];
+         st.child_begin = cptr[s];
+         st.child_end = cptr[s + 1];
+         P->max_children = std::max(P->max_children, st.child_end - st.child_begin);
+      }
+      for (int p = 0; p < nn; ++p) {
+         int sp = P->node_slot[p];
+         const SlotStatic& st = P->hss[sp];
+         if (st.child_begin == st.child_end) continue;
+         for (int64_t j = sym.rptr[p]; j < sym.rptr[p + 1]; ++j) map[sym.rlist[j]] = (int)(j - sym.rptr[p]);
+         for (int ci = st.child_begin; ci < st.child_end; ++ci) {
+            int c = P->slot_node[P->child_idx[ci]];
+            int cn = sym.sptr[c + 1] - sym.sptr[c];
+            int64_t o = rel_off[c];
+            for (int64_t j = sym.rptr[c] + cn; j < sym.rptr[c + 1]; ++j) rel[o++] = map[sym.rlist[j]];
+         }
+      }
+   }
+   // A scatter map, grouped by level
+   int64_t na = sym.nptr[nn];
+   std::vector<int> aslot(na), asrc(na), acol(na), arow(na);
+   P->lvl_a_ptr.assign(P->nlevels + 1, 0);
+   {
+      int64_t o = 0;
+      for (int l = 0; l < P->nlevels; ++l) {
+         P->lvl_a_ptr[l] = o;
+         for (int s = P->lvl_ptr[l]; s < P->lvl_ptr[l + 1]; ++s) {
+            int i = P->slot_node[s];
+            int64_t blkm = sym.rptr[i + 1] - sym.rptr[i];
+            for (int64_t e2 = sym.nptr[i]; e2 < sym.nptr[i + 1]; ++e2) {
+               int64_t dest = sym.nlist[2 * e2 + 1];
+               aslot[o] = s;
+               asrc[o] = (int)sym.nlist[2 * e2];
+               acol[o] = (int)(dest / blkm);
+               arow[o] = (int)(dest % blkm);
+               ++o;
+            }
+         }
+      }
+      P->lvl_a_ptr[P->nlevels] = o;
+   }
+   // size estimates without delays
+   for (int l = 0; l < P->nlevels; ++l) {
+      int64_t c = 0, ws = 0;
+      for (int s = P->lvl_ptr[l]; s < P->lvl_ptr[l + 1]; ++s) {
+         const SlotStatic& st = P->hss[s];
+         int64_t ldl = align_up(st.nrow, 2), cm = st.nrow - st.ncol;
+         P->est_factor_doubles += ldl * st.ncol + 32;
+         c += align_up(cm, 2) * cm + 32;
+         ws += 3 * (int64_t)st.nrow * NB + 3 * NB * NB + 2 * NB + 2 + 3 * NB + 128;
+      }
+      P->est_c_doubles[l & 1] = std::max(P->est_c_doubles[l & 1], c);
+      P->est_ws_doubles = std::max(P->est_ws_doubles, ws);
+   }
+   std::vector<int> order(sym.order);
+   bool ok = upload(&P->d_ss, P->hss) == cudaSuccess && upload(&P->d_child_idx, P->child_idx) == cudaSuccess &&
+             upload(&P->d_rlist, sym.rlist) == cudaSuccess && upload(&P->d_rel, rel) == cudaSuccess &&
+             upload(&P->d_order, order) == cudaSuccess && upload(&P->d_aslot, aslot) == cudaSuccess &&
+             upload(&P->d_asrc, asrc) == cudaSuccess && upload(&P->d_acol, acol) == cudaSuccess &&
+             upload(&P->d_arow, arow) == cudaSuccess;
+   if (!ok) {
+      *cuda_error = (int)cudaGetLastError();
+      if (*cuda_error == 0) *cuda_error = (int)cudaErrorMemoryAllocation;
+      delete P;
+      return nullptr;
+   }
+   return P;
+}
+
+void plan_destroy(Plan* p) { delete p; }
+int plan_device(const Plan* p) { return p->device; }
+
+class Numeric {
+  public:
+   Plan* P;
+   bool posdef = false, have = false;
+   std::vector<FrontDev> hfr;
+   FrontDev* d_fr = nullptr;
+   FrontDev* pin_fr = nullptr;       // pinned staging, nslots entries
+   int* pin_i = nullptr;             // pinned ints: collect + lists staging
+   size_t pin_i_cap = 0;
+   int *d_child_doff = nullptr, *d_list = nullptr, *d_collect = nullptr, *d_counters = nullptr;
+   int64_t* d_tileptr = nullptr;
+   int64_t* d_xw_off = nullptr;
+   std::vector<int> child_doff;
+   double* d_val = nullptr;
+   double *d_x = nullptr, *d_xp = nullptr, *d_xw = nullptr;
+   size_t x_cap = 0, xw_cap = 0;
+   int64_t xw_total = 0;
+   Arena fac, dar, par, car[2], war;
+   cudaStream_t st = nullptr;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+   int cuda_err = 0;
+   int64_t launches = 0;
+   FactorStats last;
+   explicit Numeric(Plan* p) : P(p) {}
+   ~Numeric() {
+      cudaSetDevice(P->device);
+      fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release();
+      cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
+      cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
+      if (pin_fr) cudaFreeHost(pin_fr);
+      if (pin_i) cudaFreeHost(pin_i);
+      if (st) cudaStreamDestroy(st);
+      if (ev0) cudaEventDestroy(ev0);
+      if (ev1) cudaEventDestroy(ev1);
+      if (ev2) cudaEventDestroy(ev2);
+   }
+   int init();
+   int factor(const double* val, bool on_device, const FactorOptions& o, FactorStats& stats);
+   int solve(int job, int nrhs, double* x, int ldx, bool on_device, double* seconds, int64_t* nl);
+};
+
+#define CU(x)                                                          \
+   do {                                                                \
+      cudaError_t e_ = (x);                                            \
+      if (e_ != cudaSuccess) {                                         \
+         cuda_err = (int)e_;                                           \
+         cudaGetLastError();                                           \
+         return SSIDS_ERROR_CUDA_UNKNOWN;                              \
+      }                                                                \
+   } while (0)
+
+int Numeric::init() {
+   if (d_fr) return 0;
+   CU(cudaSetDevice(P->device));
+   const int nn = std::max(P->nnodes, 1);
+   CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+   CU(cudaEventCreate(&ev0));
+   CU(cudaEventCreate(&ev1));
+   CU(cudaEventCreate(&ev2));
+   CU(cudaMalloc(&d_fr, sizeof(FrontDev) * nn));
+   CU(cudaMemset(d_fr, 0, sizeof(FrontDev) * nn));
+   CU(cudaMallocHost(&pin_fr, sizeof(FrontDev) * nn));
+   pin_i_cap = (size_t)4 * nn + 64;
+   CU(cudaMallocHost(&pin_i, sizeof(int) * pin_i_cap));
+   CU(cudaMalloc(&d_child_doff, sizeof(int) * std::max<size_t>(P->child_idx.size(), 1)));
+   CU(cudaMalloc(&d_list, sizeof(int) * 2 * nn));
+   CU(cudaMalloc(&d_collect, sizeof(int) * 2 * nn));
+   CU(cudaMalloc(&d_counters, sizeof(int) * 8));
+   CU(cudaMalloc(&d_tileptr, sizeof(int64_t) * (nn + 1)));
+   CU(cudaMalloc(&d_xw_off, sizeof(int64_t) * (nn + 1)));
+   CU(cudaMalloc(&d_val, sizeof(double) * std::max<int64_t>(P->sym->nz, 1)));
+   child_doff.assign(P->child_idx.size(), 0);
+   hfr.assign(nn, FrontDev());
+   fac.err = dar.err = par.err = car[0].err = car[1].err = war.err = &cuda_err;
+   return 0;
+}
+
+int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, FactorStats& stats) {
+   stats = FactorStats();
+   int rc = init();
+   if (rc) { stats.cuda_error = cuda_err; return stats.flag = rc; }
+   CU(cudaSetDevice(P->device));
+   const Symbolic& sym = *P->sym;
+   const int nn = P->nnodes;
+   have = false;
+   posdef = o.posdef != 0;
+   launches = 0;
+   Params prm;
+   prm.u = std::min(std::max(o.u, 0.0), 0.5);
+   prm.small_ = o.small_;
+   prm.lim = prm.u > 0 ? 1.0 / prm.u : INFINITY;
+   prm.action = o.action;
+   prm.posdef = posdef;
+   double mult = std::max(o.multiplier, 1.0);
+   fac.reserve((size_t)(P->est_factor_doubles * mult) * 8 + (1 << 20));
+   dar.reserve((size_t)(2.0 * sym.n * mult) * 8 + 64 * (size_t)nn + (1 << 16));
+   par.reserve((size_t)(sym.n * mult) * 4 + 64 * (size_t)nn + (1 << 16));
+   car[0].reserve((size_t)(P->est_c_doubles[0] * mult) * 8 + (1 << 16));
+   car[1].reserve((size_t)(P->est_c_doubles[1] * mult) * 8 + (1 << 16));
+   war.reserve((size_t)(P->est_ws_doubles * mult) * 8 + (1 << 16));
+   fac.reset(); dar.reset(); par.reset();
+
+   CU(cudaEventRecord(ev0, st));
+   if (on_device) {
+      CU(cudaMemcpyAsync(d_val, val, sizeof(double) * sym.nz, cudaMemcpyDeviceToDevice, st));
+   } else {
+      CU(cudaMemcpyAsync(d_val, val, sizeof(double) * sym.nz, cudaMemcpyHostToDevice, st));
+   }
+   CU(cudaEventRecord(ev1, st));
+
+   int flag = 0, num_delay = 0, maxfront = 0, nfp = 0, nsp = 0;
+   std::vector<int> lvl_list, tpp_list;
+   std::vector<int64_t> tileptr;
+   for (int l = 0; l < P->nlevels && flag >= 0; ++l) {
+      const int s0 = P->lvl_ptr[l], s1 = P->lvl_ptr[l + 1], ns = s1 - s0;
+      Arena& ca = car[l & 1];
+      ca.reset();
+      war.reset();
+      // sizes with delays
+      size_t totL = 0, totC = 0, totD = 0, totP = 0, totW = 0;
+      for (int s = s0; s < s1; ++s) {
+         const SlotStatic& ss = P->hss[s];
+         FrontDev& f = hfr[s];
+         int nd = 0;
+         for (int ci = ss.child_begin; ci < ss.child_end; ++ci) {
+            const FrontDev& fc = hfr[P->child_idx[ci]];
+            child_doff[ci] = nd;
+            nd += fc.n - fc.nelim;
+         }
+         f = FrontDev();
+         f.slot = s;
+         f.ncol = ss.ncol; f.nrow = ss.nrow; f.first_piv = ss.first_piv;
+         f.ndelay_in = nd;
+         f.m = ss.nrow + nd; f.n = ss.ncol + nd;
+         f.ldl = (int)align_up(f.m, 2);
+         f.ldc = (int)align_up(f.m - f.n, 2);
+         f.done = 0; f.end = f.n; f.w = 0; f.fail = 0; f.nelim = 0; f.flag = 0;
+         totL += align_up((size_t)f.ldl * f.n, 32);
+         totC += align_up((size_t)f.ldc * (f.m - f.n), 32);
+         totD += align_up(2 * (size_t)f.n + 2, 32);
+         totP += align_up((size_t)f.n + 1, 32);
+         totW += align_up(3 * (size_t)f.m * NB + 3 * NB * NB + 2 * NB + 2, 32) + 128;
+         maxfront = std::max(maxfront, f.m);
+      }
+      double* Lb = (double*)fac.alloc(totL * 8);
+      double* Cb = (double*)ca.alloc(totC * 8);
+      double* Db = (double*)dar.alloc(totD * 8);
+      int* Pb = (int*)par.alloc(totP * 4);
+      double* Wb = (double*)war.alloc(totW * 8);
+      if (!Lb || !Cb || !Db || !Pb || !Wb) { stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_ALLOCATION; }
+      {
+         size_t oL = 0, oC = 0, oD = 0, oP = 0, oW = 0;
+         for (int s = s0; s < s1; ++s) {
+            FrontDev& f = hfr[s];
+            f.L = Lb + oL; oL += align_up((size_t)f.ldl * f.n, 32);
+            f.C = Cb + oC; oC += align_up((size_t)f.ldc * (f.m - f.n), 32);
+            f.D = Db + oD; oD += align_up(2 * (size_t)f.n + 2, 32);
+            f.perm = Pb + oP; oP += align_up((size_t)f.n + 1, 32);
+            double* wp = Wb + oW;
+            oW += align_up(3 * (size_t)f.m * NB + 3 * NB * NB + 2 * NB + 2, 32) + 128;
+            f.Wl = wp; f.Wld = wp + (size_t)f.m * NB; f.Wo = wp + 2 * (size_t)f.m * NB;
+            f.dbuf = wp + 3 * (size_t)f.m * NB;
+            f.ibuf = (int*)(f.dbuf + 3 * NB * NB + 2 * NB + 2);
+         }
+      }
+      memcpy(pin_fr + s0, hfr.data() + s0, sizeof(FrontDev) * ns);
+      CU(cudaMemcpyAsync(d_fr + s0, pin_fr + s0, sizeof(FrontDev) * ns, cudaMemcpyHostToDevice, st));
+      CU(cudaMemsetAsync(Lb, 0, totL * 8, st));
+      if (totC) CU(cudaMemsetAsync(Cb, 0, totC * 8, st));
+      CU(cudaMemsetAsync(Db, 0, totD * 8, st));
+      const int cb = P->hss[s0].child_begin, ce = P->hss[s1 - 1].child_end;
+      if (ce > cb)
+         CU(cudaMemcpyAsync(d_child_doff + cb, child_doff.data() + cb, sizeof(int) * (ce - cb), cudaMemcpyHostToDevice, st));
+      k_setup<<<ns, 128, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, s0, ns);
+      ++launches;
+      {
+         int64_t e0 = P->lvl_a_ptr[l], e1 = P->lvl_a_ptr[l + 1];
+         if (e1 > e0) {
+            k_scatter_a<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, st>>>(d_fr, P->d_aslot, P->d_asrc, P->d_acol, P->d_arow, d_val, e0, e1);
+            ++launches;
+         }
+      }
+      // extend-add, one launch per child ordinal.  The staging lists are consumed by async copies,
+      // so each ordinal gets its own region of the pinned buffer.
+      {
+         int maxc = 0;
+         for (int s = s0; s < s1; ++s) maxc = std::max(maxc, P->hss[s].child_end - P->hss[s].child_begin);
+         size_t pin_off = 0;
+         for (int k = 0; k < maxc; ++k) {
+            lvl_list.clear();
+            std::vector<int> doffs;
+            tileptr.clear();
+            tileptr.push_back(0);
+            for (int s = s0; s < s1; ++s) {
+               const SlotStatic& ss = P->hss[s];
+               if (ss.child_end - ss.child_begin <= k) continue;
+               int cs = P->child_idx[ss.child_begin + k];
+               const FrontDev& fc = hfr[cs];
+               int t = fc.m - fc.nelim;
+               if (t <= 0) continue;
+               int64_t nt = (int64_t)((t + EA_TR - 1) / EA_TR) * ((t + EA_TC - 1) / EA_TC);
+               lvl_list.push_back(cs);
+               doffs.push_back(child_doff[ss.child_begin + k]);
+               tileptr.push_back(tileptr.back() + nt);
+            }
+            int nl = (int)lvl_list.size();
+            if (nl == 0) continue;
+            // staging: [list nl][doffs nl] ints then tileptr (nl+1) int64
+            size_t need = 2 * (size_t)nl + 2 * (size_t)(nl + 1) + 4;
+            if (pin_off + need > pin_i_cap) {   // drain and reuse
+               CU(cudaStreamSynchronize(st));
+               pin_off = 0;
+            }
+            int* pl = pin_i + pin_off;
+            memcpy(pl, lvl_list.data(), sizeof(int) * nl);
+            memcpy(pl + nl, doffs.data(), sizeof(int) * nl);
+            size_t toff = align_up(pin_off + 2 * (size_t)nl, 2);
+            int64_t* pt = (int64_t*)(pin_i + toff);
+            memcpy(pt, tileptr.data(), sizeof(int64_t) * (nl + 1));
+            pin_off = toff + 2 * (size_t)(nl + 1);
+            CU(cudaMemcpyAsync(d_list, pl, sizeof(int) * 2 * nl, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(d_tileptr, pt, sizeof(int64_t) * (nl + 1), cudaMemcpyHostToDevice, st));
+            int64_t total = tileptr.back();
+            if (total > 0x7fffffffLL) { return stats.flag = SSIDS_ERROR_UNKNOWN; }
+            k_extend_add<<<(unsigned)total, EA_TR, 0, st>>>(d_fr, P->d_ss, P->d_rel, d_list, d_list + nl, d_tileptr, nl);
+            ++launches;
+         }
+         if (pin_off) CU(cudaStreamSynchronize(st));   // staging regions free again
+      }
+      // factor: fronts bucketed by size class, sorted by candidate count (descending) inside
+      {
+         std::vector<int> order(ns);
+         for (int i = 0; i < ns; ++i) order[i] = s0 + i;
+         auto cls = [&](int s) {
+            int m = hfr[s].m;
+            return m <= 64 ? 0 : m <= 256 ? 1 : m <= 1024 ? 2 : m <= 4096 ? 3 : 4;
+         };
+         std::sort(order.begin(), order.end(), [&](int a, int b) {
+            int ca2 = cls(a), cb2 = cls(b);
+            if (ca2 != cb2) return ca2 < cb2;
+            if (hfr[a].n != hfr[b].n) return hfr[a].n > hfr[b].n;
+            return a < b;
+         });
+         memcpy(pin_i, order.data(), sizeof(int) * ns);
+         CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+         int i0 = 0;
+         while (i0 < ns) {
+            int c = cls(order[i0]), i1 = i0;
+            int maxm = 0, maxn = 0;
+            while (i1 < ns && cls(order[i1]) == c) {
+               maxm = std::max(maxm, hfr[order[i1]].m);
+               maxn = std::max(maxn, hfr[order[i1]].n);
+               ++i1;
+            }
+            const int nsteps = (maxn + NB - 1) / NB;
+            const int* lst = d_list + i0;
+            for (int sidx = 0; sidx < nsteps; ++sidx) {
+               // active prefix: fronts with more than sidx panels
+               int na = 0;
+               while (i0 + na < i1 && (hfr[order[i0 + na]].n + NB - 1) / NB > sidx) ++na;
+               if (na == 0) break;
+               k_diag<<<na, 32, 0, st>>>(d_fr, lst, prm, 0);
+               int rows_below = maxm - sidx * 0;   // failures can keep `done` behind the host's guess
+               int ychunks = (rows_below + 127) / 128;
+               k_apply<<<dim3(na, std::max(ychunks, 1)), 128, 0, st>>>(d_fr, lst, prm);
+               int ycommit = (maxm + 127) / 128 + (maxn + 127) / 128;
+               k_commit<<<dim3(na, ycommit), 128, 0, st>>>(d_fr, lst);
+               int rem = std::max(maxm - (sidx + 1) * NB + NB, UT);
+               int nt = (rem + UT - 1) / UT;
+               int64_t tiles = (int64_t)nt * (nt + 1) / 2;
+               int ygrid = (int)std::min<int64_t>(tiles, std::max<int64_t>(1, (148 * 8) / std::max(na, 1)));
+               ygrid = std::max(ygrid, 1);
+               k_update<<<dim3(na, ygrid), 256, 0, st>>>(d_fr, lst);
+               launches += 4;
+            }
+            k_diag<<<i1 - i0, 32, 0, st>>>(d_fr, lst, prm, 1);
+            ++launches;
+            i0 = i1;
+         }
+      }
+      // read back progress
+      k_collect<<<(ns + 255) / 256, 256, 0, st>>>(d_fr, s0, ns, d_collect);
+      ++launches;
+      CU(cudaMemcpyAsync(pin_i, d_collect, sizeof(int) * 2 * ns, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      tpp_list.clear();
+      for (int i = 0; i < ns; ++i) {
+         FrontDev& f = hfr[s0 + i];
+         f.done = pin_i[2 * i];
+         f.nelim = f.done;
+         f.flag = pin_i[2 * i + 1];
+         if (f.flag < 0) flag = f.flag;
+         if (f.done < f.n) { tpp_list.push_back(s0 + i); nfp += f.n - f.done; }
+      }
+      if (flag < 0) break;
+      if (!tpp_list.empty() && !posdef) {
+         int nt = (int)tpp_list.size();
+         memcpy(pin_i, tpp_list.data(), sizeof(int) * nt);
+         CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * nt, cudaMemcpyHostToDevice, st));
+         k_tpp<<<nt, 256, 0, st>>>(d_fr, d_list, prm);
+         k_collect<<<(ns + 255) / 256, 256, 0, st>>>(d_fr, s0, ns, d_collect);
+         launches += 2;
+         CU(cudaMemcpyAsync(pin_i, d_collect, sizeof(int) * 2 * ns, cudaMemcpyDeviceToHost, st));
+         CU(cudaStreamSynchronize(st));
+         for (int i = 0; i < ns; ++i) {
+            FrontDev& f = hfr[s0 + i];
+            f.done = pin_i[2 * i];
+            f.nelim = f.done;
+            f.flag = pin_i[2 * i + 1];
+            if (f.flag < 0) flag = f.flag;
+            nsp += f.n - f.done;
+         }
+      } else if (!tpp_list.empty() && posdef) {
+         flag = SSIDS_ERROR_NOT_POS_DEF;
+      }
+      for (int s = s0; s < s1; ++s) num_delay += hfr[s].n - hfr[s].nelim;
+   }
+   if (flag >= 0) {
+      CU(cudaMemsetAsync(d_counters, 0, sizeof(int) * 8, st));
+      if (!posdef && nn > 0) {
+         k_stats<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, nn, d_counters);
+         ++launches;
+      }
+      CU(cudaMemcpyAsync(pin_i, d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+   }
+   CU(cudaEventRecord(ev2, st));
+   CU(cudaStreamSynchronize(st));
+   {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) { cuda_err = (int)e; stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
+   }
+   float ms_all = 0, ms_dev = 0;
+   cudaEventElapsedTime(&ms_all, ev0, ev2);
+   cudaEventElapsedTime(&ms_dev, ev1, ev2);
+   stats.t_total = ms_all * 1e-3;
+   stats.t_device = ms_dev * 1e-3;
+   stats.launches = launches;
+   stats.maxfront = maxfront;
+   stats.num_delay = num_delay;
+   stats.not_first_pass = nfp;
+   stats.not_second_pass = nsp;
+   stats.factor_bytes = (int64_t)(fac.capacity() + dar.capacity() + par.capacity());
+   if (flag < 0) return stats.flag = flag;
+   stats.num_neg = pin_i[0];
+   stats.num_two = pin_i[1];
+   stats.num_zero = pin_i[2];
+   if (stats.num_zero > 0) flag = SSIDS_WARNING_FACT_SINGULAR;
+   // solve work-vector offsets
+   {
+      std::vector<int64_t> off(nn + 1, 0);
+      for (int s = 0; s < nn; ++s) off[s + 1] = off[s] + align_up(hfr[s].m, 2);
+      xw_total = off[nn];
+      CU(cudaMemcpy(d_xw_off, off.data(), sizeof(int64_t) * (nn + 1), cudaMemcpyHostToDevice));
+      // child delay offsets must describe the final state for the solve
+      if (!child_doff.empty())
+         CU(cudaMemcpy(d_child_doff, child_doff.data(), sizeof(int) * child_doff.size(), cudaMemcpyHostToDevice));
+   }
+   have = true;
+   last = stats;
+   last.flag = flag;
+   return stats.flag = flag;
+}
+
+int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double* seconds, int64_t* nl) {
+   if (!have) return SSIDS_ERROR_CALL_SEQUENCE;
+   if (job < 0 || job > 4) return SSIDS_ERROR_JOB_OOR;
+   const Symbolic& sym = *P->sym;
+   const int n = sym.n, nn = P->nnodes;
+   if (ldx < n || nrhs < 1) return SSIDS_ERROR_X_SIZE;
+   if (posdef && (job == 2 || job == 4)) return SSIDS_ERROR_JOB_OOR;   // ssids.f90:1180-1190
+   CU(cudaSetDevice(P->device));
+   int64_t nlaunch = 0;
+   size_t need = (size_t)std::max(n, 1);
+   if (x_cap < need) {
+      cudaFree(d_x); cudaFree(d_xp);
+      d_x = d_xp = nullptr;
+      CU(cudaMalloc(&d_x, need * 8));
+      CU(cudaMalloc(&d_xp, need * 8));
+      x_cap = need;
+   }
+   if (xw_cap < (size_t)xw_total + 2) {
+      cudaFree(d_xw);
+      d_xw = nullptr;
+      CU(cudaMalloc(&d_xw, ((size_t)xw_total + 2) * 8));
+      xw_cap = (size_t)xw_total + 2;
+   }
+   CU(cudaEventRecord(ev0, st));
+   const int nb = (n + 255) / 256;
+   for (int j = 0; j < nrhs; ++j) {
+      double* xj = x + (size_t)j * ldx;
+      double* dx = d_x;
+      if (on_device) dx = xj;
+      else CU(cudaMemcpyAsync(d_x, xj, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+      if (n > 0) { k_permute_in<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, n); ++nlaunch; }
+      const bool fwd = (job == 0 || job == 1), bwd = (job == 0 || job == 3 || job == 4);
+      const bool diag = !posdef && (job == 0 || job == 2 || job == 4);
+      // posdef: LL^T semantics, L_chol = L sqrt(D).  A full solve needs D once; we fold sqrt(D^-1)
+      // into each of the two sweeps so that partial solves match SSIDS's posdef jobs.
+      if (fwd)
+         for (int l = 0; l < P->nlevels; ++l) {
+            int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
+            k_solve_fwd<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xp, s0, posdef ? 1 : 0);
+            ++nlaunch;
+         }
+      if (diag && !bwd && nn > 0) { k_solve_diag<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, d_xp, nn); ++nlaunch; }
+      if (bwd)
+         for (int l = P->nlevels - 1; l >= 0; --l) {
+            int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
+            k_solve_bwd<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_rlist, d_xw_off, d_xw, d_xp, s0, diag ? 1 : 0, posdef ? 1 : 0);
+            ++nlaunch;
+         }
+      if (n > 0) { k_permute_out<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, n); ++nlaunch; }
+      if (!on_device) CU(cudaMemcpyAsync(xj, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+   }
+   CU(cudaEventRecord(ev1, st));
+   CU(cudaStreamSynchronize(st));
+   {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) { cuda_err = (int)e; return SSIDS_ERROR_CUDA_UNKNOWN; }
+   }
+   float ms = 0;
+   cudaEventElapsedTime(&ms, ev0, ev1);
+   if (seconds) *seconds = ms * 1e-3;
+   if (nl) *nl = nlaunch;
+   return 0;
+}
+
+Numeric* numeric_create(Plan* p) { return new Numeric(p); }
+void numeric_destroy(Numeric* n) { delete n; }
+int numeric_factor(Numeric* n, const double* val, bool on_device, const FactorOptions& o, FactorStats& s) {
+   int rc = n->factor(val, on_device, o, s);
+   s.cuda_error = n->cuda_err;
+   return rc;
+}
+int numeric_solve(Numeric* n, int job, int nrhs, double* x, int ldx, bool on_device, double* seconds, int64_t* nl) {
+   return n->solve(job, nrhs, x, ldx, on_device, seconds, nl);
+}
+bool numeric_is_posdef(const Numeric* n) { return n->posdef; }
+bool numeric_has_factors(const Numeric* n) { return n->have; }
+
+int numeric_node_info(Numeric* N, int node, int* m, int* n, int* nelim) {
+   if (!N->have || node < 0 || node >= N->P->nnodes) return -1;
+   const FrontDev& f = N->hfr[N->P->node_slot[node]];
+   *m = f.m; *n = f.n; *nelim = f.nelim;
+   return 0;
+}
+int numeric_node_copy(Numeric* N, int node, double* L, double* d, int* perm) {
+   if (!N->have || node < 0 || node >= N->P->nnodes) return -1;
+   cudaSetDevice(N->P->device);
+   const FrontDev& f = N->hfr[N->P->node_slot[node]];
+   if (L && f.nelim > 0)
+      if (cudaMemcpy2D(L, sizeof(double) * f.m, f.L, sizeof(double) * f.ldl, sizeof(double) * f.m, f.nelim, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+   if (d && f.n > 0 && cudaMemcpy(d, f.D, sizeof(double) * 2 * f.n, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+   if (perm && f.n > 0 && cudaMemcpy(perm, f.perm, sizeof(int) * f.n, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+   return 0;
+}
+
+// piv_order / d in pivot-position indexing (enquire, NumericSubtree.hxx:418-462)
+int numeric_enquire(Numeric* N, int* piv_order, double* d) {
+   if (!N->have) return SSIDS_ERROR_CALL_SEQUENCE;
+   cudaSetDevice(N->P->device);
+   const int nn = N->P->nnodes;
+   std::vector<double> dd;
+   std::vector<int> pp;
+   int piv = 0;
+   for (int node = 0; node < nn; ++node) {
+      const FrontDev& f = N->hfr[N->P->node_slot[node]];
+      if (f.nelim == 0) continue;
+      dd.resize(2 * (size_t)f.n + 2);
+      pp.resize(f.n);
+      if (cudaMemcpy(dd.data(), f.D, sizeof(double) * (2 * (size_t)f.n + 2), cudaMemcpyDeviceToHost) != cudaSuccess) return SSIDS_ERROR_CUDA_UNKNOWN;
+      if (cudaMemcpy(pp.data(), f.perm, sizeof(int) * f.n, cudaMemcpyDeviceToHost) != cudaSuccess) return SSIDS_ERROR_CUDA_UNKNOWN;
+      for (int i = 0; i < f.nelim;) {
+         if (i + 1 == f.nelim || std::isfinite(dd[2 * i + 2])) {
+            if (piv_order) piv_order[pp[i]] = piv + 1;
+            if (d) { d[2 * piv] = dd[2 * i]; d[2 * piv + 1] = 0.0; }
+            piv += 1; i += 1;
+         } else {
+            if (piv_order) { piv_order[pp[i]] = -(piv + 1); piv_order[pp[i + 1]] = -(piv + 2); }
+            if (d) { d[2 * piv] = dd[2 * i]; d[2 * piv + 1] = dd[2 * i + 1]; d[2 * piv + 2] = dd[2 * i + 3]; d[2 * piv + 3] = 0.0; }
+            piv += 2; i += 2;
+         }
+      }
+   }
+   return 0;
+}
+
+// overwrite D^{-1} (alter, NumericSubtree.hxx:465-477); the 2x2 tags are kept
+int numeric_alter(Numeric* N, const double* d) {
+   if (!N->have) return SSIDS_ERROR_CALL_SEQUENCE;
+   if (N->posdef) return SSIDS_ERROR_NOT_LDLT;
+   cudaSetDevice(N->P->device);
+   const int nn = N->P->nnodes;
+   std::vector<double> dd;
+   int piv = 0;
+   for (int node = 0; node < nn; ++node) {
+      const FrontDev& f = N->hfr[N->P->node_slot[node]];
+      if (f.nelim == 0) continue;
+      dd.resize(2 * (size_t)f.n + 2);
+      if (cudaMemcpy(dd.data(), f.D, sizeof(double) * (2 * (size_t)f.n + 2), cudaMemcpyDeviceToHost) != cudaSuccess) return SSIDS_ERROR_CUDA_UNKNOWN;
+      for (int i = 0; i < f.nelim;) {
+         if (i + 1 == f.nelim || std::isfinite(dd[2 * i + 2])) {
+            dd[2 * i] = d[2 * piv];
+            piv += 1; i += 1;
+         } else {
+            dd[2 * i] = d[2 * piv]; dd[2 * i + 1] = d[2 * piv + 1]; dd[2 * i + 3] = d[2 * piv + 2];
+            piv += 2; i += 2;
+         }
+      }
+      if (cudaMemcpy(f.D, dd.data(), sizeof(double) * (2 * (size_t)f.n + 2), cudaMemcpyHostToDevice) != cudaSuccess) return SSIDS_ERROR_CUDA_UNKNOWN;
+   }
+   return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,55 @@
+// Numeric (GPU) side of b200ldlt: interface between the C ABI (capi.cpp) and the CUDA engine
+// (engine.cu).  No CPU numeric path exists behind this interface.
+#pragma once
+#include <cstdint>
+
+#include "analyse.hpp"
+
+namespace b200 {
+
+struct FactorOptions {
+   int posdef = 0;
+   int action = 1;
+   double u = 0.01;
+   double small_ = 1e-20;
+   double multiplier = 1.1;
+   int print_level = -1;
+};
+
+struct FactorStats {
+   int flag = 0;
+   int num_delay = 0, num_neg = 0, num_two = 0, num_zero = 0, maxfront = 0;
+   int not_first_pass = 0, not_second_pass = 0;
+   int cuda_error = 0;
+   double t_total = 0, t_device = 0;   // seconds (CUDA events)
+   int64_t factor_bytes = 0;
+   int64_t launches = 0;               // kernels launched by the last factor call
+};
+
+class Plan;      // static per-akeep structures (levels, maps) on host + device
+class Numeric;   // per-fkeep factors on device
+
+// Restrict a plan to the node range [first,last] (a part of the subtree partition); -1,-1 = all.
+Plan* plan_create(const Symbolic& sym, int device, int* cuda_error);
+void plan_destroy(Plan*);
+int plan_device(const Plan*);
+
+Numeric* numeric_create(Plan*);
+void numeric_destroy(Numeric*);
+int numeric_factor(Numeric*, const double* val, bool val_on_device, const FactorOptions&,
+                   FactorStats&);
+// x(ldx,nrhs) indexed by ORIGINAL variable; job 0..4
+int numeric_solve(Numeric*, int job, int nrhs, double* x, int ldx, bool x_on_device,
+                  double* seconds, int64_t* launches);
+// indexed by pivot position within the analysis order (perm values): piv_order[n], d[2n]
+int numeric_enquire(Numeric*, int* piv_order, double* d);
+int numeric_alter(Numeric*, const double* d);
+bool numeric_is_posdef(const Numeric*);
+bool numeric_has_factors(const Numeric*);
+
+// debugging / parity: per-node results copied to the host
+int numeric_node_info(Numeric*, int node, int* m, int* n, int* nelim);
+int numeric_node_copy(Numeric*, int node, double* L /*m*nelim, ld m*/, double* d /*2n*/,
+                      int* perm /*n*/);
+
+}  // namespace b200

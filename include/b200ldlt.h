@@ -1,0 +1,162 @@
+/* b200ldlt -- C ABI of the B200-native sparse symmetric-indefinite LDL^T engine.
+ *
+ * This is the drop-in boundary for GALAHAD's SLS package (seam B1): a new
+ * solver name 'b200ldlt' in src/sls/sls.f90 binds these entry points through ISO_C_BINDING, one per
+ * call the 'ssids' CASE blocks make today:
+ *
+ *   b200ldlt_analyse         <- SSIDS_analyse      (sls.f90:3115-3150  -> ssids.f90:93/148)
+ *   b200ldlt_factor          <- SSIDS_factor       (sls.f90:4273-4297  -> ssids.f90:736/770)
+ *   b200ldlt_solve           <- SSIDS_solve        (sls.f90:5392-5397, 5693 -> ssids.f90:1114/1139)
+ *   b200ldlt_enquire_indef   <- SSIDS_enquire_indef (sls.f90:6312      -> ssids.f90:1299)
+ *   b200ldlt_enquire_posdef  <- SSIDS_enquire_posdef                   (ssids.f90:1255)
+ *   b200ldlt_alter           <- SSIDS_alter        (sls.f90:6488       -> ssids.f90:1347)
+ *   b200ldlt_free            <- SSIDS_free         (sls.f90:5972       -> ssids.f90:1388-1419)
+ *
+ * Plain pointers and sizes only.  Handles are opaque, owned by the library.  The caller owns every
+ * array it passes and may release it on return (the pattern is copied at analyse).  Nothing throws
+ * or aborts across this boundary: every call returns an SSIDS-style flag (src/ssids/datatypes.f90:
+ * 25-59; 0 ok, <0 error, >0 warning) and records it in inform->flag.  There is no CPU fallback:
+ * without a usable CUDA device factor/solve return B200LDLT_ERROR_CUDA_UNKNOWN (-51).
+ */
+#ifndef B200LDLT_H
+#define B200LDLT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* flags: the SSIDS values (src/ssids/datatypes.f90:25-59) */
+#define B200LDLT_SUCCESS 0
+#define B200LDLT_ERROR_CALL_SEQUENCE (-1)
+#define B200LDLT_ERROR_A_N_OOR (-2)
+#define B200LDLT_ERROR_A_PTR (-3)
+#define B200LDLT_ERROR_SINGULAR (-5)
+#define B200LDLT_ERROR_NOT_POS_DEF (-6)
+#define B200LDLT_ERROR_ORDER (-8)
+#define B200LDLT_ERROR_X_SIZE (-10)
+#define B200LDLT_ERROR_JOB_OOR (-11)
+#define B200LDLT_ERROR_NOT_LLT (-13)
+#define B200LDLT_ERROR_NOT_LDLT (-14)
+#define B200LDLT_ERROR_ALLOCATION (-50)
+#define B200LDLT_ERROR_CUDA_UNKNOWN (-51)
+#define B200LDLT_ERROR_UNIMPLEMENTED (-98)
+#define B200LDLT_WARNING_ANAL_SINGULAR 6
+#define B200LDLT_WARNING_FACT_SINGULAR 7
+
+/* solve jobs (src/ssids/datatypes.f90:62-66) */
+#define B200LDLT_JOB_ALL 0
+#define B200LDLT_JOB_FWD 1
+#define B200LDLT_JOB_DIAG 2
+#define B200LDLT_JOB_BWD 3
+#define B200LDLT_JOB_DIAG_BWD 4
+
+/* Options: the subset of ssids_options (src/ssids/datatypes.f90:187-283) that SLS sets through
+ * SLS_copy_control_to_ssids (sls.f90:1385-1439), plus engine knobs. */
+typedef struct b200ldlt_options {
+   int array_base;      /* 0: C indexing of ptr/row/order; 1: Fortran indexing (the sls.f90 shim) */
+   int print_level;     /* <0 silent */
+   int nemin;           /* node amalgamation (SLS node_amalgamation), <1 -> 32 */
+   int action;          /* 1: continue on singular matrix with a warning (7); 0: error -5 */
+   double u;            /* relative pivot threshold (SLS relative_pivot_tolerance), clipped to [0,0.5] */
+   double small_;       /* |pivot| below this is zero (SLS absolute_pivot_tolerance) */
+   double multiplier;   /* factor-storage slack for delayed pivots (>= 1.0) */
+   int device;          /* CUDA device ordinal, -1: current device */
+   int panel_width;     /* reserved; 0 = engine default */
+   int reserved[7];
+} b200ldlt_options;
+
+/* Inform: shaped like ssids_inform (src/ssids/inform.f90:17-49). */
+typedef struct b200ldlt_inform {
+   int flag;
+   int matrix_dup;
+   int matrix_missing_diag;
+   int matrix_outrange;
+   int matrix_rank;
+   int maxdepth;
+   int maxfront;
+   int num_delay;
+   int64_t num_factor;
+   int64_t num_flops;
+   int num_neg;
+   int num_sup;
+   int num_two;
+   int stat;
+   int cuda_error;
+   int nparts;
+   int not_first_pass;   /* columns that failed the a-posteriori pass (ThreadStats.hxx) */
+   int not_second_pass;  /* columns still failing after the TPP pass */
+   double time_analyse;  /* seconds, host wall clock */
+   double time_factor;   /* seconds, CUDA events around the numeric phase incl. H2D of val */
+   double time_factor_device; /* seconds, CUDA events, val already resident */
+   double time_solve;
+   int64_t factor_bytes; /* device bytes held by L, D and pivot lists */
+   int reserved[8];
+} b200ldlt_inform;
+
+void b200ldlt_default_options(b200ldlt_options *opt);
+
+/* Symbolic phase (CPU).  ptr[n+1], row[ptr[n]-base]: LOWER triangle by columns == upper triangle by
+ * rows as SLS_coord_to_sorted_csr (sls.f90:8409) leaves it: sorted, diagonal first and present.
+ * order[n]: in = position of each variable in the pivot sequence; out = the order actually used. */
+int b200ldlt_analyse(void **akeep, int n, const int *ptr, const int *row, int *order,
+                     const b200ldlt_options *opt, b200ldlt_inform *inf);
+
+/* 64-bit ptr variant (ssids.f90:148 analyse_double takes int64 ptr). */
+int b200ldlt_analyse_ptr64(void **akeep, int n, const int64_t *ptr, const int *row, int *order,
+                           const b200ldlt_options *opt, b200ldlt_inform *inf);
+
+/* Numeric phase (GPU).  val[] aligned with ptr/row, HOST memory.  *fkeep may hold a previous
+ * factorization of the same akeep: its storage is reused. */
+int b200ldlt_factor(void *akeep, void **fkeep, int posdef, const double *val,
+                    const b200ldlt_options *opt, b200ldlt_inform *inf);
+
+/* As b200ldlt_factor, with val already resident in DEVICE memory (refactorization loops). */
+int b200ldlt_factor_device(void *akeep, void **fkeep, int posdef, const double *d_val,
+                           const b200ldlt_options *opt, b200ldlt_inform *inf);
+
+/* Solve with nrhs right-hand sides held by columns in HOST x(ldx,nrhs), overwritten by the solution.
+ * job as B200LDLT_JOB_*. */
+int b200ldlt_solve(void *akeep, void *fkeep, int job, int nrhs, double *x, int ldx,
+                   const b200ldlt_options *opt, b200ldlt_inform *inf);
+
+/* As b200ldlt_solve with x in DEVICE memory. */
+int b200ldlt_solve_device(void *akeep, void *fkeep, int job, int nrhs, double *d_x, int ldx,
+                          const b200ldlt_options *opt, b200ldlt_inform *inf);
+
+/* piv_order[n] (nullable): |piv_order[i]| = pivot position (array_base) of variable i, negative if
+ * part of a 2x2 pivot.  d[2*n] (nullable): D^{-1}, d[2k] diagonal, d[2k+1] off-diagonal of pivot k. */
+int b200ldlt_enquire_indef(void *akeep, void *fkeep, int *piv_order, double *d,
+                           const b200ldlt_options *opt, b200ldlt_inform *inf);
+/* d[n]: diagonal of the Cholesky factor L. */
+int b200ldlt_enquire_posdef(void *akeep, void *fkeep, double *d, b200ldlt_inform *inf);
+/* Overwrite D^{-1} with d[2*n] (layout as enquire_indef). */
+int b200ldlt_alter(void *akeep, void *fkeep, const double *d, b200ldlt_inform *inf);
+
+int b200ldlt_free_fkeep(void **fkeep);
+int b200ldlt_free(void **akeep, void **fkeep);
+
+/* ---- symbolic results, for parity checks against SSIDS's akeep (all array_base-shifted) -------- */
+int b200ldlt_akeep_sizes(void *akeep, int *nnodes, int64_t *nrlist, int64_t *nnlist);
+int b200ldlt_akeep_get(void *akeep, int array_base, int *sptr, int *sparent, int64_t *rptr,
+                       int *rlist, int64_t *nptr, int64_t *nlist, int *invp);
+
+/* ---- multi-GPU (one process per GPU; the host side moves contribution blocks with NCCL) -------- */
+/* Partition the assembly tree into leaf subtrees for `nranks` devices + a root part
+ * (after find_subtree_partition, anal.f90:284-459).  Returns the number of parts. */
+int b200ldlt_partition(void *akeep, int nranks);
+int b200ldlt_part_info(void *akeep, int part, int *first_node, int *last_node, int *owner,
+                       int *dest_node, int64_t *flops);
+
+/* ---- per-front results, for parity checks against the oracle ---------------------------------- */
+int b200ldlt_node_info(void *fkeep, int node, int *m, int *n, int *nelim);
+int b200ldlt_node_copy(void *fkeep, int node, double *L /* m*nelim */, double *d /* 2n */,
+                       int *perm /* n */);
+
+const char *b200ldlt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LDLT_H */
