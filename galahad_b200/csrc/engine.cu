@@ -39,6 +39,7 @@ struct FrontDev {
    double* C;
    double* D;
    int* perm;
+   int* orig;      // orig[r] = local index variable r had when the front was assembled (r < n)
    double* Wl;     // m x NB   L panel (front-row indexed)
    double* Wld;    // m x NB   L*D panel
    double* Wo;     // m x NB   permuted original panel
@@ -85,6 +86,7 @@ __device__ void warp_sym_swap(const FrontDev& f, int a, int b, int lane) {
    if (lane == 0) {
       double t = L[a + a * ld]; L[a + a * ld] = L[b + b * ld]; L[b + b * ld] = t;
       int s = f.perm[a]; f.perm[a] = f.perm[b]; f.perm[b] = s;
+      s = f.orig[a]; f.orig[a] = f.orig[b]; f.orig[b] = s;
    }
    for (int c = a + 1 + lane; c < b; c += 32) {
       double t = L[c + a * ld]; L[c + a * ld] = L[b + c * ld]; L[b + c * ld] = t;
@@ -104,6 +106,7 @@ __global__ void k_setup(FrontDev* fr, const SlotStatic* ss, const int* child_idx
    FrontDev& f = fr[s];
    const SlotStatic st = ss[s];
    for (int j = threadIdx.x; j < st.ncol; j += blockDim.x) f.perm[j] = st.first_piv + j;
+   for (int j = threadIdx.x; j < f.n; j += blockDim.x) f.orig[j] = j;
    for (int ci = st.child_begin; ci < st.child_end; ++ci) {
       const FrontDev& fc = fr[child_idx[ci]];
       int nd = fc.n - fc.nelim, off = child_doff[ci];
@@ -473,6 +476,10 @@ __global__ void __launch_bounds__(128) k_commit(FrontDev* fr, const int* list) {
                for (int q = 0; q < NB; ++q) tmp[q] = q < w ? f.perm[done + lperm[q]] : 0;
 #pragma unroll
                for (int q = 0; q < NB; ++q) if (q < w) f.perm[done + q] = tmp[q];
+#pragma unroll
+               for (int q = 0; q < NB; ++q) tmp[q] = q < w ? f.orig[done + lperm[q]] : 0;
+#pragma unroll
+               for (int q = 0; q < NB; ++q) if (q < w) f.orig[done + q] = tmp[q];
             }
          }
       }
@@ -593,6 +600,7 @@ __device__ void block_sym_swap(const FrontDev& f, int a, int b) {
    if (threadIdx.x == 0) {
       double t = L[a + a * ld]; L[a + a * ld] = L[b + b * ld]; L[b + b * ld] = t;
       int s = f.perm[a]; f.perm[a] = f.perm[b]; f.perm[b] = s;
+      s = f.orig[a]; f.orig[a] = f.orig[b]; f.orig[b] = s;
    }
    for (int c = a + 1 + threadIdx.x; c < b; c += blockDim.x) {
       double t = L[c + a * ld]; L[c + a * ld] = L[b + c * ld]; L[b + c * ld] = t;
@@ -820,15 +828,19 @@ __global__ void k_permute_out(double* __restrict__ x, const double* __restrict__
 __global__ void __launch_bounds__(256) k_solve_fwd(const FrontDev* fr, const SlotStatic* ss,
                                                    const int* child_idx, const int* child_doff,
                                                    const int* rel, const int64_t* xw_off, double* XW,
-                                                   double* x, int slot0, int posdef_scale) {
+                                                   double* XA, double* x, int slot0, int posdef_scale) {
    const int s = slot0 + blockIdx.x;
    const FrontDev& f = fr[s];
    const SlotStatic st = ss[s];
    double* xw = XW + xw_off[s];
+   double* acc = XA + xw_off[s];   // children's contributions, indexed by the parent's ASSEMBLY order
    const int m = f.m, ne = f.nelim;
    __shared__ double ys[NB];
-   for (int r = threadIdx.x; r < m; r += blockDim.x) xw[r] = r < ne ? x[f.perm[r]] : 0.0;
-   __syncthreads();
+   const bool has_children = st.child_end > st.child_begin;
+   if (has_children) {
+      for (int r = threadIdx.x; r < m; r += blockDim.x) acc[r] = 0.0;
+      __syncthreads();
+   }
    for (int ci = st.child_begin; ci < st.child_end; ++ci) {
       const int cs = child_idx[ci];
       const FrontDev& fc = fr[cs];
@@ -839,10 +851,17 @@ __global__ void __launch_bounds__(256) k_solve_fwd(const FrontDev* fr, const Slo
          int d;
          if (rr < nd) d = f.ncol + doff + rr;
          else { d = relc[rr - nd]; if (d >= f.ncol) d += f.ndelay_in; }
-         xw[d] += xc[rr];
+         acc[d] += xc[rr];
       }
       __syncthreads();
    }
+   // pivoting permuted the candidate rows after assembly: orig[] maps them back
+   for (int r = threadIdx.x; r < m; r += blockDim.x) {
+      double v = r < ne ? x[f.perm[r]] : 0.0;
+      if (has_children) v += acc[r < f.n ? f.orig[r] : r];
+      xw[r] = v;
+   }
+   __syncthreads();
    const size_t ldl = f.ldl;
    for (int k0 = 0; k0 < ne; k0 += NB) {
       const int kb = min(NB, ne - k0);
@@ -1253,7 +1272,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    double mult = std::max(o.multiplier, 1.0);
    fac.reserve((size_t)(P->est_factor_doubles * mult) * 8 + (1 << 20));
    dar.reserve((size_t)(2.0 * sym.n * mult) * 8 + 64 * (size_t)nn + (1 << 16));
-   par.reserve((size_t)(sym.n * mult) * 4 + 64 * (size_t)nn + (1 << 16));
+   par.reserve((size_t)(2.0 * sym.n * mult) * 4 + 512 * (size_t)nn + (1 << 16));
    car[0].reserve((size_t)(P->est_c_doubles[0] * mult) * 8 + (1 << 16));
    car[1].reserve((size_t)(P->est_c_doubles[1] * mult) * 8 + (1 << 16));
    war.reserve((size_t)(P->est_ws_doubles * mult) * 8 + (1 << 16));
@@ -1297,7 +1316,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          totL += align_up((size_t)f.ldl * f.n, 32);
          totC += align_up((size_t)f.ldc * (f.m - f.n), 32);
          totD += align_up(2 * (size_t)f.n + 2, 32);
-         totP += align_up((size_t)f.n + 1, 32);
+         totP += 2 * align_up((size_t)f.n + 1, 32);
          totW += align_up(3 * (size_t)f.m * NB + 3 * NB * NB + 2 * NB + 2, 32) + 128;
          maxfront = std::max(maxfront, f.m);
       }
@@ -1314,7 +1333,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             f.L = Lb + oL; oL += align_up((size_t)f.ldl * f.n, 32);
             f.C = Cb + oC; oC += align_up((size_t)f.ldc * (f.m - f.n), 32);
             f.D = Db + oD; oD += align_up(2 * (size_t)f.n + 2, 32);
-            f.perm = Pb + oP; oP += align_up((size_t)f.n + 1, 32);
+            f.perm = Pb + oP; f.orig = f.perm + align_up((size_t)f.n + 1, 32); oP += 2 * align_up((size_t)f.n + 1, 32);
             double* wp = Wb + oW;
             oW += align_up(3 * (size_t)f.m * NB + 3 * NB * NB + 2 * NB + 2, 32) + 128;
             f.Wl = wp; f.Wld = wp + (size_t)f.m * NB; f.Wo = wp + 2 * (size_t)f.m * NB;
@@ -1537,11 +1556,11 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
       CU(cudaMalloc(&d_xp, need * 8));
       x_cap = need;
    }
-   if (xw_cap < (size_t)xw_total + 2) {
+   if (xw_cap < 2 * ((size_t)xw_total + 2)) {   // two halves: work vectors | assembly-order accumulators
       cudaFree(d_xw);
       d_xw = nullptr;
-      CU(cudaMalloc(&d_xw, ((size_t)xw_total + 2) * 8));
-      xw_cap = (size_t)xw_total + 2;
+      CU(cudaMalloc(&d_xw, 2 * ((size_t)xw_total + 2) * 8));
+      xw_cap = 2 * ((size_t)xw_total + 2);
    }
    CU(cudaEventRecord(ev0, st));
    const int nb = (n + 255) / 256;
@@ -1558,7 +1577,7 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
       if (fwd)
          for (int l = 0; l < P->nlevels; ++l) {
             int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
-            k_solve_fwd<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xp, s0, posdef ? 1 : 0);
+            k_solve_fwd<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xw + xw_cap / 2, d_xp, s0, posdef ? 1 : 0);
             ++nlaunch;
          }
       if (diag && !bwd && nn > 0) { k_solve_diag<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, d_xp, nn); ++nlaunch; }
