@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- SLS factorize (FP64 TFLOP/s) + solve (ms) on BASELINE.json config C2
+(3-D 7-point Laplacian 64^3, 262,144 unknowns, geometric nested-dissection order, SLS default
+pivot_control=1 i.e. the pivoted LDL^T path) through the b200ldlt C ABI.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid G]
+
+A step = one numeric factorization + one solve (1 RHS) of the same matrix (analyse once, as the
+interior-point callers do).  `value` = num_flops / mean factorize time with A's values resident in
+HBM (num_flops = the reference's own count, core_analyse.f90:880-892); `solve_ms` rides along.
+`e2e` = the same through the host-buffer C-ABI calls (H2D of val and b, D2H of x inside the timed
+region).  N > 1: independent replicas, one per rank, scaling "weak".
+`--impl reference` times the reference's own C++ SSIDS CPU engine (oracle/_ref) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sls_factorize_fp64_tflops"
+UNIT = "TFLOP/s"
+
+
+def make_problem(grid):
+    from galahad_b200 import problems as P
+    return P.laplace_problem(grid)
+
+
+def workload_name(grid):
+    return f"C2: 3-D 7-point Laplacian {grid}^3 (n={grid ** 3}), geometric ND order, SLS pivot_control=1 (LDL^T, u=0.01), factor + 1-RHS solve"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = [s for s in sm if s > 0.5 * max(sm)]
+        return {"sm_mhz": float(np.median(hi if hi else sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measure_fp64_peak(torch):
+    """cuBLAS Dgemm through torch (float64 4096^3, best of 5): the FP64 denominator.  The driver's
+    MEASURED_PEAKS.json has no FP64 entry, so it is measured here, same method as its bf16 entry."""
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import refssids
+    if not refssids.have_ref():
+        try:
+            refssids.build_ref()
+        except Exception as e:  # the reference cannot be built on this box
+            print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref missing and not buildable: {e}"}))
+            return 0
+    from galahad_b200._lib import Solver
+    cores = os.cpu_count() or 1
+    # bounded sample: shrink the grid until (K+W) steps fit in ~3 minutes (flops ~ g^6, measured
+    # 0.035 TFLOP/s on 8 cores for g=64)
+    total_steps = args.steps + args.warmup
+    grid = args.grid
+    est_rate = 0.0045e12 * min(cores, 32)
+    for g in (args.grid, 56, 48, 40, 32, 24):
+        if g > args.grid:
+            continue
+        grid = g
+        est = 4.34e11 * (g / 64.0) ** 6 / est_rate
+        if est * total_steps <= 180.0:
+            break
+    prob = make_problem(grid)
+    s = Solver()
+    s.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"])
+    flops = float(s.inform.num_flops)
+    sym = s.symbolic()
+    ref = refssids.RefSSIDS(sym, prob["n"], u=0.01, small=1e-20)
+    rng = np.random.default_rng(20261018)
+    b = rng.uniform(-1, 1, prob["n"])
+    tf, ts = [], []
+    for it in range(total_steps):
+        st = ref.factor(prob["val"], False)
+        t0 = time.perf_counter()
+        refssids.permuted_solve(ref, s.order, b)
+        t1 = time.perf_counter() - t0
+        if it >= args.warmup:
+            tf.append(st["seconds"]); ts.append(t1)
+    mf, ms = float(np.mean(tf)), float(np.mean(ts))
+    val = flops / mf / 1e12
+    sample = f"full factor+solve of the {grid}^3 grid ({flops:.3e} flops) per step, {len(tf)} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": (mf + ms) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.grid), "sample_grid": grid, "threads": ref.nthreads()},
+        "factor_ms": mf * 1e3, "solve_ms": ms * 1e3,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.nthreads(), "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from galahad_b200._lib import Solver
+    prob = make_problem(args.grid)
+    n = prob["n"]
+    s = Solver(device=local)
+    s.analyse(n, prob["ptr"], prob["row"], prob["order"])
+    flops = float(s.inform.num_flops)
+    nfact = int(s.inform.num_factor)
+    rng = np.random.default_rng(20261018)
+    b = rng.uniform(-1, 1, n)
+    d_val = torch.from_numpy(prob["val"]).cuda()
+    d_b = torch.from_numpy(b).cuda()
+    d_x = torch.empty_like(d_b)
+    h_val = torch.from_numpy(prob["val"]).pin_memory()
+    h_b = torch.from_numpy(b.copy()).pin_memory()
+    h_x = torch.empty(n, dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        flush.zero_()                      # > L2 (126 MB) written between iterations
+        d_x.copy_(d_b)
+        torch.cuda.synchronize()
+        f = s.factor_device(d_val.data_ptr(), False)
+        assert f >= 0, f"factor flag {f}"
+        tf = s.inform.time_factor_device
+        nl = s.inform.reserved[0]
+        uf, us = s.inform.upd_flops, s.inform.upd_seconds
+        f = s.solve_device(d_x.data_ptr(), 1, n)
+        assert f >= 0, f"solve flag {f}"
+        return tf, s.inform.time_solve, nl + s.inform.reserved[1], uf, us
+
+    def step_host():
+        import ctypes as C
+        flush.zero_()
+        h_x.copy_(h_b)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        f = s.L.b200ldlt_factor(s.akeep, C.byref(s.fkeep), 0, C.cast(h_val.data_ptr(), C.POINTER(C.c_double)),
+                                C.byref(s.opt), C.byref(s.inform))
+        t1 = time.perf_counter()
+        assert f >= 0, f
+        f = s.L.b200ldlt_solve(s.akeep, s.fkeep, 0, 1, C.cast(h_x.data_ptr(), C.POINTER(C.c_double)), n,
+                               C.byref(s.opt), C.byref(s.inform))
+        t2 = time.perf_counter()
+        assert f >= 0, f
+        return t1 - t0, t2 - t1
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    s.opt.reserved[0] = 1                  # profile mode: events around every trailing update
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = [step_device() for _ in range(args.steps)]
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = e0.elapsed_time(e1)
+    s.opt.reserved[0] = 0
+    tf = float(np.mean([r[0] for r in res]))
+    ts = float(np.mean([r[1] for r in res]))
+    launches = int(np.sum([r[2] for r in res]))
+    upd_flops = float(np.sum([r[3] for r in res]))
+    upd_secs = float(np.sum([r[4] for r in res]))
+    # check the answer of the last step (not timed)
+    x = d_x.cpu().numpy()
+    from galahad_b200 import problems as P
+    berr = P.backward_error(prob, x, b)
+    # end to end through the host-buffer C ABI
+    for _ in range(2):
+        step_host()
+    barrier()
+    eh = [step_host() for _ in range(args.steps)]
+    barrier()
+    ef = float(np.mean([r[0] for r in eh]))
+    es = float(np.mean([r[1] for r in eh]))
+    # max over ranks
+    t = torch.tensor([tf, ts, total_ms, ef, es], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tf, ts, total_ms, ef, es = [float(v) for v in t.cpu()]
+    if rank == 0:
+        peak = measure_fp64_peak(torch)
+        value = world * flops / tf / 1e12
+        achieved = upd_flops / upd_secs / 1e12 if upd_secs > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.grid), "num_flops": flops, "num_factor": nfact,
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas",
+                       "l2": "256 MB buffer written between iterations; factor working set >> L2",
+                       "timing": "value = flops / mean CUDA-event time of the numeric factorization (engine stream, val resident); ms_per_step = CUDA events around the K steps / K"},
+            "factor_ms": tf * 1e3, "solve_ms": ts * 1e3,
+            "solve_gbs": (2 * 8 * nfact + 2 * 8 * n) / ts / 1e9,
+            "backward_error": berr,
+            "gpu_launches": launches,
+            "e2e": {"value": world * flops / ef / 1e12, "unit": UNIT, "h2d_bytes_per_step": int(8 * prob["val"].size + 8 * n),
+                    "d2h_bytes_per_step": int(8 * n), "factor_ms": ef * 1e3, "solve_ms": es * 1e3},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "k_update (trailing Schur update, FP64)",
+                         "peak_source": "measured here: cuBLAS Dgemm 4096^3 via torch.matmul(float64), best of 5 (MEASURED_PEAKS.json has no FP64 entry)",
+                         "share_of_factor_time": upd_secs / (tf * args.steps) if tf > 0 else None},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(prob, s, flops)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline(prob, s, flops):
+    """The reference's own CPU engine (oracle/_ref), one full factorization of the same matrix on
+    the box's host cores.  Reported context, not the target."""
+    try:
+        from oracle import refssids
+        if not refssids.have_ref():
+            refssids.build_ref()
+        sym = s.symbolic()
+        ref = refssids.RefSSIDS(sym, prob["n"], u=0.01, small=1e-20)
+        st = ref.factor(prob["val"], False)
+        out = {"value": flops / st["seconds"] / 1e12, "unit": UNIT, "cores": ref.nthreads(), "kind": "reference",
+               "sample": f"one full numeric factorization of the same matrix ({flops:.3e} flops, {st['seconds']:.2f} s)",
+               "num_neg": st["num_neg"]}
+        ref.close()
+        return out
+    except Exception as e:
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200ldlt")
+    ap.add_argument("--grid", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -52,6 +52,8 @@ class Inform(C.Structure):
         ("time_factor_device", C.c_double),
         ("time_solve", C.c_double),
         ("factor_bytes", C.c_int64),
+        ("upd_flops", C.c_double),
+        ("upd_seconds", C.c_double),
         ("reserved", C.c_int * 8),
     ]
 

@@ -49,6 +49,7 @@ FactorOptions to_engine(const b200ldlt_options* o, int posdef) {
    f.small_ = o->small_;
    f.multiplier = o->multiplier;
    f.print_level = o->print_level;
+   f.profile = o->reserved[0];
    return f;
 }
 
@@ -171,6 +172,9 @@ static int factor_common(void* akeep, void** fkeep, int posdef, const double* va
    inf->time_factor_device = st.t_device;
    inf->factor_bytes = st.factor_bytes;
    inf->reserved[0] = (int)st.launches;
+   inf->reserved[2] = (int)st.upd_launches;
+   inf->upd_flops = st.upd_flops;
+   inf->upd_seconds = st.upd_seconds;
    // singular: warning with action, error without (ssids.f90:1057-1066)
    if (flag >= 0 && st.num_zero > 0) flag = opt->action ? SSIDS_WARNING_FACT_SINGULAR : SSIDS_ERROR_SINGULAR;
    if (flag >= 0 && flag == 0 && ak->inf_analyse.flag > 0) flag = ak->inf_analyse.flag;

@@ -1199,6 +1199,9 @@ class Numeric {
    int cuda_err = 0;
    int64_t launches = 0;
    FactorStats last;
+   std::vector<cudaEvent_t> prof_ev;
+   size_t prof_used = 0;
+   double prof_flops = 0;
    explicit Numeric(Plan* p) : P(p) {}
    ~Numeric() {
       cudaSetDevice(P->device);
@@ -1263,6 +1266,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    have = false;
    posdef = o.posdef != 0;
    launches = 0;
+   prof_used = 0;
+   prof_flops = 0;
    Params prm;
    prm.u = std::min(std::max(o.u, 0.0), 0.5);
    prm.small_ = o.small_;
@@ -1448,7 +1453,21 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                int64_t tiles = (int64_t)nt * (nt + 1) / 2;
                int ygrid = (int)std::min<int64_t>(tiles, std::max<int64_t>(1, (148 * 8) / std::max(na, 1)));
                ygrid = std::max(ygrid, 1);
+               if (o.profile) {
+                  if (prof_used + 2 > prof_ev.size()) {
+                     size_t old = prof_ev.size();
+                     prof_ev.resize(old + 256);
+                     for (size_t q = old; q < prof_ev.size(); ++q) cudaEventCreate(&prof_ev[q]);
+                  }
+                  for (int q = 0; q < na; ++q) {
+                     const FrontDev& ff = hfr[order[i0 + q]];
+                     double dn = sidx * NB, ww = std::min<double>(NB, ff.n - dn), tt = ff.m - dn - ww;
+                     if (ww > 0 && tt > 0) prof_flops += ww * tt * (tt + 1);
+                  }
+                  cudaEventRecord(prof_ev[prof_used], st);
+               }
                k_update<<<dim3(na, ygrid), 256, 0, st>>>(d_fr, lst);
+               if (o.profile) { cudaEventRecord(prof_ev[prof_used + 1], st); prof_used += 2; }
                launches += 4;
             }
             k_diag<<<i1 - i0, 32, 0, st>>>(d_fr, lst, prm, 1);
@@ -1513,6 +1532,13 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    stats.t_total = ms_all * 1e-3;
    stats.t_device = ms_dev * 1e-3;
    stats.launches = launches;
+   if (o.profile) {
+      double ms_sum = 0;
+      for (size_t q = 0; q + 1 < prof_used; q += 2) { float t = 0; cudaEventElapsedTime(&t, prof_ev[q], prof_ev[q + 1]); ms_sum += t; }
+      stats.upd_seconds = ms_sum * 1e-3;
+      stats.upd_flops = prof_flops;
+      stats.upd_launches = (int64_t)(prof_used / 2);
+   }
    stats.maxfront = maxfront;
    stats.num_delay = num_delay;
    stats.not_first_pass = nfp;

@@ -14,6 +14,7 @@ struct FactorOptions {
    double small_ = 1e-20;
    double multiplier = 1.1;
    int print_level = -1;
+   int profile = 0;     // 1: bracket every trailing-update launch with CUDA events (bench roofline)
 };
 
 struct FactorStats {
@@ -24,6 +25,9 @@ struct FactorStats {
    double t_total = 0, t_device = 0;   // seconds (CUDA events)
    int64_t factor_bytes = 0;
    int64_t launches = 0;               // kernels launched by the last factor call
+   // profile mode: the dominant kernel (trailing update), measured with CUDA events on its stream
+   double upd_flops = 0, upd_seconds = 0;
+   int64_t upd_launches = 0;
 };
 
 class Plan;      // static per-akeep structures (levels, maps) on host + device

@@ -64,7 +64,7 @@ typedef struct b200ldlt_options {
    double multiplier;   /* factor-storage slack for delayed pivots (>= 1.0) */
    int device;          /* CUDA device ordinal, -1: current device */
    int panel_width;     /* reserved; 0 = engine default */
-   int reserved[7];
+   int reserved[7];     /* reserved[0] = 1: profile mode (CUDA events around every trailing update) */
 } b200ldlt_options;
 
 /* Inform: shaped like ssids_inform (src/ssids/inform.f90:17-49). */
@@ -92,7 +92,9 @@ typedef struct b200ldlt_inform {
    double time_factor_device; /* seconds, CUDA events, val already resident */
    double time_solve;
    int64_t factor_bytes; /* device bytes held by L, D and pivot lists */
-   int reserved[8];
+   double upd_flops;     /* profile mode: algorithmic flops of the trailing-update launches */
+   double upd_seconds;   /* profile mode: summed CUDA-event time of those launches */
+   int reserved[8];      /* [0] kernels launched by factor, [1] by solve, [2] update launches profiled */
 } b200ldlt_inform;
 
 void b200ldlt_default_options(b200ldlt_options *opt);

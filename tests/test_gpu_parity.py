@@ -1,0 +1,133 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the oracle on the same
+seeded inputs.  Integer results (inertia, delays reported by both as they use the same schedule)
+are compared exactly; solutions by scaled backward error <= 1e-14 and agreement with the oracle's
+solution to 1e-10 x a condition allowance."""
+import numpy as np
+import pytest
+
+from galahad_b200 import problems as P
+from galahad_b200._lib import Solver
+from oracle.refssids import Oracle, permuted_solve
+from util import bcsstk01_problem, golden, golden_cases, kat_problem, rhs_for
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+def gpu_factor(prob, posdef=False, **opts):
+    s = Solver(**opts)
+    assert s.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"]) >= 0
+    flag = s.factor(prob["val"], posdef)
+    assert flag != -51, "CUDA engine unavailable: the product path has no CPU fallback"
+    return s, flag
+
+
+@pytest.mark.parametrize("which", ["indef", "spd"])
+@pytest.mark.parametrize("order", ["identity", "reverse"])
+def test_kat_5x5(which, order):
+    prob, rhs, sol = kat_problem(which, order)
+    for posdef in ([False, True] if which == "spd" else [False]):
+        s, flag = gpu_factor(prob, posdef)
+        assert flag == 0
+        f, x = s.solve(rhs)
+        assert f == 0 and np.abs(x - sol).max() <= EPS ** 0.5
+        f, x2 = s.solve(np.stack([rhs, 2 * rhs], axis=1))        # 2 RHS (slst.f90)
+        assert np.abs(x2[:, 0] - sol).max() <= EPS ** 0.5 and np.abs(x2[:, 1] - 2 * sol).max() <= EPS ** 0.5
+
+
+def test_bcsstk01():
+    for order in ("identity", "reverse"):
+        prob = bcsstk01_problem(order)
+        s, flag = gpu_factor(prob)
+        assert flag == 0 and s.inform.num_neg == 0 and s.inform.matrix_rank == 48
+        b = P.full_from_lower(prob["n"], prob["ptr"], prob["row"], prob["val"]) @ np.ones(48)
+        f, x = s.solve(b)
+        assert P.backward_error(prob, x, b) <= 1e-14 and np.abs(x - 1).max() <= 1e-9
+
+
+def test_against_oracle_and_reference_runs():
+    gold = {r["name"]: r for r in golden("ref_runs.json")["runs"]}
+    for name, prob, posdef in golden_cases():
+        g = gold[name]
+        s, flag = gpu_factor(prob, posdef)
+        sym = s.symbolic()
+        orc = Oracle(sym, prob["n"])
+        so = orc.factor(prob["val"], posdef)
+        assert flag == so["flag"] == g["flag"], name
+        assert s.inform.num_neg == so["num_neg"] == g["num_neg"], name       # bit exact
+        assert s.inform.num_delay == so["num_delay"], name                    # same schedule as the oracle
+        xs, b = rhs_for(prob)
+        f, x = s.solve(b)
+        xo = permuted_solve(orc, s.order, b)
+        assert f == 0
+        assert P.backward_error(prob, x, b) <= max(1e-14, 10 * g["berr"]), name
+        assert np.abs(x - xo).max() <= 1e-10 * 1e4 * max(1.0, np.abs(xo).max()), name
+
+
+def test_partial_solves_and_enquire():
+    prob = P.kkt_grid_problem(8)
+    s, flag = gpu_factor(prob)
+    xs, b = rhs_for(prob)
+    f, x = s.solve(b)
+    f, y = s.solve(b, job=1)
+    f, z = s.solve(y, job=4)
+    assert np.abs(z - x).max() <= 1e-12 * max(1, np.abs(x).max())
+    f, y2 = s.solve(y, job=2)
+    f, z2 = s.solve(y2, job=3)
+    assert np.abs(z2 - x).max() <= 1e-12 * max(1, np.abs(x).max())
+    f, piv, d = s.enquire_indef()
+    assert f == 0 and sorted(np.abs(piv).tolist()) == list(range(prob["n"]))
+    # inertia from D^{-1}: 1x1 signs + 2x2 determinants
+    neg, k = 0, 0
+    while k < prob["n"]:
+        if d[k, 1] != 0.0:
+            det = d[k, 0] * d[k + 1, 0] - d[k, 1] ** 2
+            neg += 1 if det < 0 else (2 if d[k, 0] + d[k + 1, 0] < 0 else 0)
+            k += 2
+        else:
+            neg += d[k, 0] < 0
+            k += 1
+    assert neg == s.inform.num_neg == prob["inertia"][1]
+    # alter: scaling D^{-1} by 2 halves the solution
+    assert s.alter(2 * d) == 0
+    f, xh = s.solve(b)
+    assert np.abs(xh - 2 * x).max() <= 1e-12 * max(1, np.abs(x).max())
+
+
+def test_refactor_reuses_handles():
+    prob = P.kkt_grid_problem(8)
+    s, flag = gpu_factor(prob)
+    for it in range(3):
+        val = prob["val"].copy()
+        val[prob["ptr"][:-1]] *= (1.0 + 0.1 * it)             # scale the diagonal, same pattern
+        assert s.factor(val) >= 0
+        p2 = dict(prob, val=val)
+        xs, b = rhs_for(p2)
+        f, x = s.solve(b)
+        assert P.backward_error(p2, x, b) <= 1e-14
+
+
+def test_singular_and_not_posdef():
+    import scipy.sparse as sp
+    A = sp.csc_matrix(np.array([[1.0, 1.0, 0], [1.0, 1.0, 0], [0, 0, 2.0]]))
+    n, ptr, row, val = P.lower_csc(A)
+    prob = dict(n=n, ptr=ptr, row=row, val=val, order=np.arange(3, dtype=np.int32))
+    s, flag = gpu_factor(prob, small=1e-14)
+    assert flag == 7 and s.inform.matrix_rank == 2
+    s, flag = gpu_factor(prob, small=1e-14, action=0)
+    assert flag == -5
+    prob2, rhs, sol = kat_problem("indef")
+    s, flag = gpu_factor(prob2, posdef=True)
+    assert flag == -6                                         # SSIDS_ERROR_NOT_POS_DEF
+
+
+def test_medium_grid_properties():
+    """Size-independent properties at a size the oracle does not need to follow: exact inertia law
+    of the KKT matrix (n, m, 0) and the backward-error bound."""
+    for prob in (P.laplace_problem(24), P.kkt_grid_problem(16), P.qpband_problem(20000)):
+        s, flag = gpu_factor(prob)
+        assert flag == 0
+        assert s.inform.num_neg == prob["inertia"][1]
+        xs, b = rhs_for(prob)
+        f, x = s.solve(b)
+        assert P.backward_error(prob, x, b) <= 1e-14

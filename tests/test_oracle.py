@@ -1,0 +1,96 @@
+"""Pins the oracle: (i) the reference's own known-answer systems and bcsstk01, (ii) the committed
+outputs of the reference's C++ engine (tests/golden/ref_runs.json), and (iii) -- when oracle/_ref is
+present -- a live run of that engine on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from galahad_b200 import problems as P
+from galahad_b200._lib import Solver
+from oracle import refssids
+from oracle.refssids import Oracle, RefSSIDS, permuted_solve
+from util import bcsstk01_problem, golden, golden_cases, kat_problem, rhs_for
+
+EPS = np.finfo(float).eps
+
+
+def analyse(prob):
+    s = Solver()
+    assert s.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"]) >= 0
+    return s, s.symbolic()
+
+
+@pytest.mark.parametrize("which", ["indef", "spd"])
+@pytest.mark.parametrize("order", ["identity", "reverse"])
+def test_kat_5x5(which, order):
+    prob, rhs, sol = kat_problem(which, order)
+    s, sym = analyse(prob)
+    for eng in ([Oracle(sym, 5)] + ([RefSSIDS(sym, 5)] if refssids.have_ref() else [])):
+        st = eng.factor(prob["val"], False)
+        assert st["flag"] == 0
+        x = permuted_solve(eng, s.order, rhs)
+        assert np.abs(x - sol).max() <= EPS ** 0.5          # slst.f90:261-262
+    if which == "spd":
+        orc = Oracle(sym, 5)
+        assert orc.factor(prob["val"], True)["flag"] == 0   # Cholesky path
+        assert np.abs(permuted_solve(orc, s.order, rhs) - sol).max() <= EPS ** 0.5
+
+
+@pytest.mark.parametrize("order", ["identity", "reverse"])
+def test_bcsstk01(order):
+    prob = bcsstk01_problem(order)
+    s, sym = analyse(prob)
+    A = P.full_from_lower(prob["n"], prob["ptr"], prob["row"], prob["val"])
+    b = A @ np.ones(prob["n"])                              # runsls_rb.f90:126-137
+    orc = Oracle(sym, prob["n"])
+    st = orc.factor(prob["val"], False)
+    assert (st["flag"], st["num_neg"], st["num_zero"]) == (0, 0, 0)
+    x = permuted_solve(orc, s.order, b)
+    assert P.backward_error(prob, x, b) <= 1e-14
+    assert np.abs(x - 1).max() <= 1e-9                      # cond ~ 8.8e5
+
+
+def test_against_committed_reference_runs():
+    gold = {r["name"]: r for r in golden("ref_runs.json")["runs"]}
+    for name, prob, posdef in golden_cases():
+        g = gold[name]
+        s, sym = analyse(prob)
+        assert (sym["nnodes"], s.inform.num_factor, s.inform.num_flops) == (g["num_sup"], g["num_factor"], g["num_flops"])
+        orc = Oracle(sym, prob["n"])
+        st = orc.factor(prob["val"], posdef)
+        assert st["flag"] == g["flag"], name
+        assert st["num_neg"] == g["num_neg"], name          # inertia: bit exact
+        assert st["num_zero"] == g["num_zero"], name
+        xs, b = rhs_for(prob)
+        x = permuted_solve(orc, s.order, b)
+        assert P.backward_error(prob, x, b) <= max(1e-14, 10 * g["berr"]), name
+        scale = max(1.0, np.abs(x).max())
+        assert np.abs(x[:8] - np.array(g["x_head"])).max() <= 1e-8 * scale, name
+
+
+@pytest.mark.skipif(not refssids.have_ref(), reason="oracle/_ref not built")
+def test_live_reference_engine():
+    for name, prob, posdef in golden_cases()[:6] + golden_cases()[-3:]:
+        s, sym = analyse(prob)
+        ref, orc = RefSSIDS(sym, prob["n"]), Oracle(sym, prob["n"])
+        a, b_ = ref.factor(prob["val"], posdef), orc.factor(prob["val"], posdef)
+        assert (a["flag"], a["num_neg"], a["num_zero"]) == (b_["flag"], b_["num_neg"], b_["num_zero"]), name
+        xs, b = rhs_for(prob)
+        xr, xo = permuted_solve(ref, s.order, b), permuted_solve(orc, s.order, b)
+        assert np.abs(xr - xo).max() <= 1e-8 * max(1.0, np.abs(xr).max()), name
+        # partial solves (jobs 1..4, datatypes.f90:62-66) compose to the full solve
+        if not posdef:
+            y = permuted_solve(orc, s.order, b, job=1)
+            z = permuted_solve(orc, s.order, y, job=4)
+            assert np.abs(z - xo).max() <= 1e-12 * max(1.0, np.abs(xo).max())
+
+
+def test_singular_matrix_is_flagged():
+    import scipy.sparse as sp
+    A = sp.csc_matrix(np.array([[1.0, 1.0, 0], [1.0, 1.0, 0], [0, 0, 2.0]]))
+    n, ptr, row, val = P.lower_csc(A)
+    prob = dict(n=n, ptr=ptr, row=row, val=val, order=np.arange(3, dtype=np.int32))
+    s, sym = analyse(prob)
+    st = Oracle(sym, 3, small=1e-14).factor(val, False)
+    assert st["flag"] == 7 and st["num_zero"] == 1          # SSIDS_WARNING_FACT_SINGULAR
+    st = Oracle(sym, 3, small=1e-14, action=False).factor(val, False)
+    assert st["flag"] == -5                                 # SSIDS_ERROR_SINGULAR
