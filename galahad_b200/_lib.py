@@ -67,7 +67,7 @@ SYMBOLS = [
     "b200ldlt_factor_device", "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_enquire_indef",
     "b200ldlt_enquire_posdef", "b200ldlt_alter", "b200ldlt_free_fkeep", "b200ldlt_free",
     "b200ldlt_akeep_sizes", "b200ldlt_akeep_get", "b200ldlt_partition", "b200ldlt_part_info",
-    "b200ldlt_node_info", "b200ldlt_node_copy", "b200ldlt_version",
+    "b200ldlt_node_info", "b200ldlt_node_copy", "b200ldlt_version", "b200ldlt_ntree_sizes", "b200ldlt_ntree_get",
 ]
 
 _lib = None
@@ -100,6 +100,8 @@ def lib():
     L.b200ldlt_free.argtypes = [vpp, vpp]
     L.b200ldlt_akeep_sizes.argtypes = [vp, ip, lp, lp]
     L.b200ldlt_akeep_get.argtypes = [vp, C.c_int, ip, ip, lp, ip, lp, lp, ip]
+    L.b200ldlt_ntree_sizes.argtypes = [vp, ip, lp, lp]
+    L.b200ldlt_ntree_get.argtypes = [vp, C.c_int, ip, ip, lp, ip, lp, lp]
     L.b200ldlt_partition.argtypes = [vp, C.c_int]
     L.b200ldlt_part_info.argtypes = [vp, C.c_int, ip, ip, ip, ip, lp]
     L.b200ldlt_node_info.argtypes = [vp, C.c_int, ip, ip, ip]
@@ -160,6 +162,21 @@ class Solver:
                                   as_ptr(out["rptr"], C.c_int64), as_ptr(out["rlist"], C.c_int),
                                   as_ptr(out["nptr"], C.c_int64), as_ptr(out["nlist"], C.c_int64),
                                   as_ptr(out["invp"], C.c_int))
+        return out
+
+    def numeric_tree(self, base=0):
+        """The engine's own tree (chains fused); same keys as symbolic() minus invp."""
+        nn, nr, nl = C.c_int(), C.c_int64(), C.c_int64()
+        self.L.b200ldlt_ntree_sizes(self.akeep, C.byref(nn), C.byref(nr), C.byref(nl))
+        nn, nr, nl = nn.value, nr.value, nl.value
+        out = dict(
+            nnodes=nn,
+            sptr=np.zeros(nn + 1, np.int32), sparent=np.zeros(max(nn, 1), np.int32)[:nn],
+            rptr=np.zeros(nn + 1, np.int64), rlist=np.zeros(max(nr, 1), np.int32)[:nr],
+            nptr=np.zeros(nn + 1, np.int64), nlist=np.zeros(max(2 * nl, 1), np.int64)[:2 * nl])
+        self.L.b200ldlt_ntree_get(self.akeep, base, as_ptr(out["sptr"], C.c_int), as_ptr(out["sparent"], C.c_int),
+                                  as_ptr(out["rptr"], C.c_int64), as_ptr(out["rlist"], C.c_int),
+                                  as_ptr(out["nptr"], C.c_int64), as_ptr(out["nlist"], C.c_int64))
         return out
 
     def factor(self, val, posdef=False):

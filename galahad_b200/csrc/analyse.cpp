@@ -531,3 +531,107 @@ void find_subtree_partition(Symbolic& sym, int ndev, double max_load_inbalance, 
 }
 
 }  // namespace b200
+
+namespace b200 {
+
+// Engine-internal relaxation of the assembly tree.  The reference's amalgamation (do_merge,
+// core_analyse.f90:806-822) stops at nemin columns, which on nested-dissection orderings leaves
+// long chains parent(i) = i+1 of 32..62-column supernodes whose fronts differ by a handful of
+// rows (each link of a separator plane brings in 2-3 new boundary rows).  Every link would cost a
+// full extend-add of an (m-62)^2 contribution block.  The numeric engine therefore factorises a
+// chain as ONE front: node p absorbs its last child c = p-1 when the explicit zeros this adds to L
+// stay below `max_zero_frac` of the fused L.  The fused front's rows are cols(chain) ++ rlist(p)
+// (the child's contribution rows are a subset of the parent's rows in any assembly tree), so only
+// structural zeros are introduced and the factorisation is the same P A P^T = L D L^T.  What SLS
+// reports (sptr, sparent, rptr, rlist, num_factor, num_flops, ...) stays the reference's tree.
+void fuse_chains(const Symbolic& in, Symbolic& out, double max_zero_frac) {
+   const int nn = in.nnodes;
+   out = Symbolic();
+   out.n = in.n; out.nz = in.nz; out.ptr = in.ptr; out.row = in.row; out.order = in.order; out.invp = in.invp;
+   out.num_factor = in.num_factor; out.num_flops = in.num_flops; out.maxfront = in.maxfront;
+   out.maxdepth = in.maxdepth; out.matrix_rank = in.matrix_rank; out.realn = in.realn; out.flag = in.flag;
+   // group[i] = index of the fused node that original node i belongs to; groups are runs i..top
+   std::vector<int> first(nn, 0);          // first original node of the run ending at i
+   std::vector<int64_t> zeros(nn, 0);      // explicit zeros accumulated in the run ending at i
+   std::vector<char> absorbed(nn, 0);      // node i was absorbed by i+1
+   for (int p = 0; p < nn; ++p) {
+      first[p] = p;
+      zeros[p] = 0;
+      const int c = p - 1;
+      if (c < 0 || in.sparent[c] != p) continue;
+      const int64_t gcols = in.sptr[c + 1] - in.sptr[first[c]];
+      const int64_t ncol_p = in.sptr[p + 1] - in.sptr[p];
+      const int64_t nrow_p = in.rptr[p + 1] - in.rptr[p];
+      const int64_t contrib_c = (in.rptr[c + 1] - in.rptr[c]) - (in.sptr[c + 1] - in.sptr[c]);
+      const int64_t newz = gcols * (nrow_p - contrib_c);
+      const int64_t fused_m = gcols + nrow_p, fused_n = gcols + ncol_p;
+      const int64_t fused_entries = fused_m * fused_n - fused_n * (fused_n - 1) / 2;
+      if ((double)(zeros[c] + newz) <= max_zero_frac * (double)fused_entries) {
+         absorbed[c] = 1;
+         first[p] = first[c];
+         zeros[p] = zeros[c] + newz;
+      }
+   }
+   std::vector<int> gid(nn, -1);
+   int ng = 0;
+   for (int i = 0; i < nn; ++i) {
+      if (absorbed[i]) continue;            // i is not a top
+      for (int q = first[i]; q <= i; ++q) gid[q] = ng;
+      ++ng;
+   }
+   out.nnodes = ng;
+   out.sptr.assign(ng + 1, 0);
+   out.sparent.assign(ng, ng);
+   out.rptr.assign(ng + 1, 0);
+   out.nptr.assign(ng + 1, 0);
+   std::vector<int> top(ng, 0), bot(ng, 0);
+   for (int i = 0; i < nn; ++i) {
+      if (absorbed[i]) continue;
+      int g = gid[i];
+      top[g] = i;
+      bot[g] = first[i];
+   }
+   int64_t rtot = 0;
+   for (int g = 0; g < ng; ++g) {
+      const int t = top[g], b = bot[g];
+      out.sptr[g] = in.sptr[b];
+      out.sparent[g] = in.sparent[t] < nn ? gid[in.sparent[t]] : ng;
+      const int64_t gcols_below = in.sptr[t] - in.sptr[b];
+      out.rptr[g] = rtot;
+      rtot += gcols_below + (in.rptr[t + 1] - in.rptr[t]);
+   }
+   out.sptr[ng] = in.sptr[nn];
+   out.rptr[ng] = rtot;
+   out.rlist.assign(rtot, 0);
+   out.nlist.assign(in.nlist.size(), 0);
+   std::vector<int> map(in.n, 0);
+   int64_t pp = 0;
+   for (int g = 0; g < ng; ++g) {
+      const int t = top[g], b = bot[g];
+      int64_t o = out.rptr[g];
+      for (int piv = in.sptr[b]; piv < in.sptr[t]; ++piv) out.rlist[o++] = piv;
+      for (int64_t j = in.rptr[t]; j < in.rptr[t + 1]; ++j) out.rlist[o++] = in.rlist[j];
+      const int64_t blkm = out.rptr[g + 1] - out.rptr[g];
+      for (int64_t j = out.rptr[g]; j < out.rptr[g + 1]; ++j) map[out.rlist[j]] = (int)(j - out.rptr[g]);
+      out.nptr[g] = pp;
+      for (int q = b; q <= t; ++q) {
+         const int64_t qm = in.rptr[q + 1] - in.rptr[q];
+         const int coff = in.sptr[q] - in.sptr[b];
+         const int* qrl = in.rlist.data() + in.rptr[q];
+         for (int64_t e = in.nptr[q]; e < in.nptr[q + 1]; ++e) {
+            const int64_t dest = in.nlist[2 * e + 1];
+            const int col = (int)(dest / qm), row = (int)(dest % qm);
+            out.nlist[2 * pp] = in.nlist[2 * e];
+            out.nlist[2 * pp + 1] = (int64_t)(coff + col) * blkm + map[qrl[row]];
+            ++pp;
+         }
+      }
+   }
+   out.nptr[ng] = pp;
+   out.nparts = 1;
+   out.part = {0, ng};
+   out.exec_loc = {-1};
+   out.contrib_ptr = {0, 0};
+}
+
+}  // namespace b200

@@ -72,4 +72,8 @@ int analyse(int n, const int64_t* ptr, const int* row, const int* order, int nem
 // anal.f90:284-459 with a GPU-only topology of `ndev` equal devices.
 void find_subtree_partition(Symbolic& sym, int ndev, double max_load_inbalance, int64_t min_gpu_work);
 
+// Engine-internal tree: absorb chain links (last child into parent) while the explicit zeros stay
+// below max_zero_frac of the fused L.  Reported symbolic results remain those of `in`.
+void fuse_chains(const Symbolic& in, Symbolic& out, double max_zero_frac);
+
 }  // namespace b200

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -18,7 +19,8 @@ using namespace b200;
 namespace {
 
 struct Akeep {
-   Symbolic sym;
+   Symbolic sym;      // the reference's assembly tree (what SLS reports)
+   Symbolic nsym;     // the engine's tree: chains fused (analyse.cpp fuse_chains)
    Plan* plan = nullptr;
    int plan_cuda_error = 0;
    b200ldlt_inform inf_analyse;
@@ -37,7 +39,7 @@ void clear_inform(b200ldlt_inform* inf) {
 
 int ensure_plan(Akeep* ak, int device) {
    if (ak->plan) return 0;
-   ak->plan = plan_create(ak->sym, device, &ak->plan_cuda_error);
+   ak->plan = plan_create(ak->nsym, device, &ak->plan_cuda_error);
    return ak->plan ? 0 : SSIDS_ERROR_CUDA_UNKNOWN;
 }
 
@@ -106,6 +108,12 @@ int b200ldlt_analyse_ptr64(void** akeep, int n, const int64_t* ptr, const int* r
    if (flag < 0) {
       delete ak;
       return inf->flag = flag;
+   }
+   {
+      const char* fz = std::getenv("B200LDLT_FUSE_ZERO_FRAC");
+      double frac = fz ? std::atof(fz) : 0.05;
+      if (opt->reserved[1] == 1) frac = -1.0;     // reserved[1] = 1: engine runs on the reference tree as is
+      fuse_chains(ak->sym, ak->nsym, frac);
    }
    const Symbolic& s = ak->sym;
    for (int i = 0; i < n; ++i) order[i] = s.order[i] < 0 ? (base - 1) : s.order[i] + base;
@@ -307,6 +315,29 @@ int b200ldlt_akeep_get(void* akeep, int base, int* sptr, int* sparent, int64_t* 
    if (nptr) for (int i = 0; i <= s.nnodes; ++i) nptr[i] = s.nptr[i] + base;
    if (nlist) for (size_t i = 0; i < s.nlist.size(); ++i) nlist[i] = s.nlist[i] + base;
    if (invp) for (int i = 0; i < s.n; ++i) invp[i] = s.invp[i] + base;
+   return 0;
+}
+
+int b200ldlt_ntree_sizes(void* akeep, int* nnodes, int64_t* nrlist, int64_t* nnlist) {
+   if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   const Symbolic& s = static_cast<Akeep*>(akeep)->nsym;
+   if (nnodes) *nnodes = s.nnodes;
+   if (nrlist) *nrlist = (int64_t)s.rlist.size();
+   if (nnlist) *nnlist = (int64_t)s.nlist.size() / 2;
+   return 0;
+}
+
+int b200ldlt_ntree_get(void* akeep, int base, int* sptr, int* sparent, int64_t* rptr, int* rlist,
+                       int64_t* nptr, int64_t* nlist) {
+   if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   const Symbolic& s = static_cast<Akeep*>(akeep)->nsym;
+   base = base ? 1 : 0;
+   if (sptr) for (int i = 0; i <= s.nnodes; ++i) sptr[i] = s.sptr[i] + base;
+   if (sparent) for (int i = 0; i < s.nnodes; ++i) sparent[i] = s.sparent[i] + base;
+   if (rptr) for (int i = 0; i <= s.nnodes; ++i) rptr[i] = s.rptr[i] + base;
+   if (rlist) for (size_t i = 0; i < s.rlist.size(); ++i) rlist[i] = s.rlist[i] + base;
+   if (nptr) for (int i = 0; i <= s.nnodes; ++i) nptr[i] = s.nptr[i] + base;
+   if (nlist) for (size_t i = 0; i < s.nlist.size(); ++i) nlist[i] = s.nlist[i] + base;
    return 0;
 }
 

@@ -28,10 +28,10 @@
 namespace b200 {
 
 constexpr int NB = 32;          // panel width
+constexpr int NBO = 128;        // outer block: columns eliminated between two full trailing updates
 constexpr int LDS = NB + 1;     // padded shared leading dimension
 constexpr int EA_TR = 256;      // extend-add tile rows
 constexpr int EA_TC = 8;        // extend-add tile cols
-constexpr int UT = 64;          // update tile
 #define DINF (__longlong_as_double(0x7ff0000000000000LL))
 
 struct FrontDev {
@@ -40,15 +40,18 @@ struct FrontDev {
    double* D;
    int* perm;
    int* orig;      // orig[r] = local index variable r had when the front was assembled (r < n)
-   double* Wl;     // m x NB   L panel (front-row indexed)
-   double* Wld;    // m x NB   L*D panel
-   double* Wo;     // m x NB   permuted original panel
-   double* dbuf;   // L11[NB*NB] | LD11[NB*NB] | A0p[NB*NB] | dk[2*NB+2]
+   double* Wld;    // m x NBO  L*D of the current outer block (front-row indexed)
+   double* Wo;     // m x NB   permuted original panel (restore on failure)
+   double* dbuf;   // L11[NB*NB] | LD11[NB*NB] | A0p[NB*NB] | Linv[NB*NB] | dk[2*NB+2]
    int* ibuf;      // lperm[NB] | ptype[NB] | permuted
    int m, n, ldl, ldc;
    int ncol, nrow, ndelay_in, first_piv;
-   int done, end, w, fail;
-   int nelim, flag, slot, pad;
+   int done;       // columns eliminated so far (L columns [0,done) are final)
+   int oend;       // candidates of the current outer block are [done, oend)
+   int gend;       // candidates of the front are [done, gend); [gend, n) failed this pass
+   int w, fail;    // current panel width, first failed column of the panel (atomicMin)
+   int jstart, jend0;   // current outer block [jstart, jend0) as opened
+   int nelim, flag, slot;
 };
 
 struct SlotStatic {
@@ -74,26 +77,6 @@ __device__ __forceinline__ int compute_nelim(int fail, int w, const int* ptype) 
    int nelim = fail < w ? fail : w;
    if (nelim < w && nelim > 0 && ptype[nelim] == 2) nelim -= 1;
    return nelim;
-}
-
-// symmetric swap of front indices a < b (both candidates, so every touched column is in L)
-__device__ void warp_sym_swap(const FrontDev& f, int a, int b, int lane) {
-   double* L = f.L;
-   const size_t ld = f.ldl;
-   for (int c = lane; c < a; c += 32) {
-      double t = L[a + c * ld]; L[a + c * ld] = L[b + c * ld]; L[b + c * ld] = t;
-   }
-   if (lane == 0) {
-      double t = L[a + a * ld]; L[a + a * ld] = L[b + b * ld]; L[b + b * ld] = t;
-      int s = f.perm[a]; f.perm[a] = f.perm[b]; f.perm[b] = s;
-      s = f.orig[a]; f.orig[a] = f.orig[b]; f.orig[b] = s;
-   }
-   for (int c = a + 1 + lane; c < b; c += 32) {
-      double t = L[c + a * ld]; L[c + a * ld] = L[b + c * ld]; L[b + c * ld] = t;
-   }
-   for (int r = b + 1 + lane; r < f.m; r += 32) {
-      double t = L[r + a * ld]; L[r + a * ld] = L[r + b * ld]; L[r + b * ld] = t;
-   }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -172,396 +155,31 @@ __global__ void k_extend_add(const FrontDev* fr, const SlotStatic* ss, const int
    }
 }
 
-// ------------------------------------------------------------------------------------------
-// K1: (finish previous panel) + factor the next diagonal block with complete pivoting
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_diag(FrontDev* fr, const int* list, Params prm, int finish_only) {
-   FrontDev& f = fr[list[blockIdx.x]];
-   const int lane = threadIdx.x;
-   __shared__ double sa[NB * LDS], sld[NB * LDS], s0[NB * LDS];
-   __shared__ double sd[2 * NB + 2];
-   __shared__ int sptype[NB], slperm[NB];
-
-   int done = f.done, end = f.end, w = f.w, fail = f.fail;
-   __syncwarp();
-   if (f.flag < 0) return;
-   if (w > 0) {
-      int nelim = compute_nelim(fail, w, f.ibuf + NB);
-      int nfail = w - nelim;
-      done += nelim;
-      for (int q = 0; q < nfail; ++q) {
-         int a = done + q, b = end - 1 - q;
-         if (a < b) warp_sym_swap(f, a, b, lane);
-         __syncwarp();
-      }
-      end -= nfail;
-      if (prm.posdef && nfail > 0 && lane == 0) f.flag = SSIDS_ERROR_NOT_POS_DEF;
+// symmetric swap of two candidate columns/rows (every touched column lives in L); whole CTA
+__device__ void block_sym_swap(const FrontDev& f, int a, int b) {
+   if (a == b) return;
+   if (a > b) { int s = a; a = b; b = s; }
+   double* L = f.L;
+   const size_t ld = f.ldl;
+   for (int c = threadIdx.x; c < a; c += blockDim.x) {
+      double t = L[a + c * ld]; L[a + c * ld] = L[b + c * ld]; L[b + c * ld] = t;
    }
-   w = end - done;
-   if (w > NB) w = NB;
-   if (w < 0) w = 0;
-   if (finish_only) w = 0;
-   __syncwarp();
-   if (lane == 0) { f.done = done; f.end = end; f.w = w; f.fail = w; f.nelim = done; }
-   if (w == 0) return;
-
-   // load the block, full symmetric, plus a copy of the original
-   for (int i = lane; i < NB * LDS; i += 32) { sa[i] = 0.0; sld[i] = 0.0; }
-   __syncwarp();
-   for (int c = 0; c < w; ++c) {
-      if (lane >= c && lane < w) {
-         double v = f.L[(size_t)(done + c) * f.ldl + done + lane];
-         sa[lane + c * LDS] = v;
-         sa[c + lane * LDS] = v;
-      }
+   if (threadIdx.x == 0) {
+      double t = L[a + a * ld]; L[a + a * ld] = L[b + b * ld]; L[b + b * ld] = t;
+      int s = f.perm[a]; f.perm[a] = f.perm[b]; f.perm[b] = s;
+      s = f.orig[a]; f.orig[a] = f.orig[b]; f.orig[b] = s;
    }
-   __syncwarp();
-   for (int i = lane; i < NB * LDS; i += 32) s0[i] = sa[i];
-   if (lane < NB) { slperm[lane] = lane; sptype[lane] = 0; }
-   for (int i = lane; i < 2 * NB + 2; i += 32) sd[i] = 0.0;
-   __syncwarp();
-
-   int err = 0;
-   for (int p = 0; p < w;) {
-      int t = p, mm = p, pivsiz = 1;
-      double a11 = 0, a21 = 0, a22 = 0, detscale = 0, detpiv = 0;
-      if (prm.posdef) {
-         a11 = sa[p + p * LDS];
-         if (!(a11 > 0.0)) { err = SSIDS_ERROR_NOT_POS_DEF; break; }
-      } else {
-         double best = -1.0;
-         int key = 0;
-         if (lane >= p && lane < w) {
-            for (int c = p; c <= lane; ++c) {
-               double v = fabs(sa[lane + c * LDS]);
-               if (v > best) { best = v; key = c * 64 + lane; }
-            }
-         } else {
-            key = 1 << 30;
-         }
-#pragma unroll
-         for (int off = 16; off > 0; off >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, best, off);
-            int ok = __shfl_xor_sync(0xffffffffu, key, off);
-            if (ov > best || (ov == best && ok < key)) { best = ov; key = ok; }
-         }
-         t = key & 63;
-         mm = key >> 6;
-         if (best < prm.small_) {
-            if (!prm.action) { err = SSIDS_ERROR_SINGULAR; break; }
-            for (int pp = p; pp < w; ++pp) {
-               if (lane >= pp && lane < w) {
-                  sa[lane + pp * LDS] = 0.0;
-                  sa[pp + lane * LDS] = 0.0;
-                  sld[lane + pp * LDS] = 0.0;
-               }
-               if (lane == 0) { sd[2 * pp] = 0.0; sd[2 * pp + 1] = 0.0; sptype[pp] = 0; }
-            }
-            __syncwarp();
-            break;
-         }
-         if (t == mm) {
-            pivsiz = 1;
-            a11 = sa[t + t * LDS];
-         } else {
-            a11 = sa[mm + mm * LDS];
-            a22 = sa[t + t * LDS];
-            a21 = sa[t + mm * LDS];
-            detscale = 1.0 / fabs(a21);
-            detpiv = (a11 * detscale) * a22 - fabs(a21);
-            if (fabs(detpiv) >= fabs(a21) / 2) {
-               pivsiz = 2;
-            } else if (fabs(a11) > fabs(a22)) {
-               pivsiz = 1; t = mm;
-            } else {
-               pivsiz = 1; a11 = a22; mm = t;
-            }
-         }
-      }
-      __syncwarp();
-      // symmetric swaps bringing the pivot(s) to p (and p+1)
-      for (int i = 0; i < pivsiz; ++i) {
-         int dst = p + i;
-         int src = (pivsiz == 1) ? t : (i == 0 ? mm : t);
-         if (src != dst) {
-            if (lane < w) {
-               double s = sa[dst + lane * LDS]; sa[dst + lane * LDS] = sa[src + lane * LDS]; sa[src + lane * LDS] = s;
-            }
-            __syncwarp();
-            if (lane < w) {
-               double s = sa[lane + dst * LDS]; sa[lane + dst * LDS] = sa[lane + src * LDS]; sa[lane + src * LDS] = s;
-            }
-            if (lane < p) {
-               double s = sld[dst + lane * LDS]; sld[dst + lane * LDS] = sld[src + lane * LDS]; sld[src + lane * LDS] = s;
-            }
-            if (lane == 0) { int q = slperm[dst]; slperm[dst] = slperm[src]; slperm[src] = q; }
-            __syncwarp();
-         }
-      }
-      if (pivsiz == 1) {
-         double d11 = 1.0 / sa[p + p * LDS];
-         double lr = 0.0;
-         if (lane > p && lane < w) {
-            double ldr = sa[lane + p * LDS];
-            sld[lane + p * LDS] = ldr;
-            lr = ldr * d11;
-            sa[lane + p * LDS] = lr;
-         }
-         __syncwarp();
-         if (lane > p && lane < w)
-            for (int c = p + 1; c < w; ++c) sa[lane + c * LDS] -= lr * sld[c + p * LDS];
-         __syncwarp();
-         if (lane == 0) { sd[2 * p] = d11; sd[2 * p + 1] = 0.0; sptype[p] = 0; sa[p + p * LDS] = 1.0; }
-         if (lane > p && lane < w) sa[p + lane * LDS] = 0.0;
-         __syncwarp();
-         p += 1;
-      } else {
-         double d11 = (a22 * detscale) / detpiv, d22 = (a11 * detscale) / detpiv;
-         double d21 = (-a21 * detscale) / detpiv;
-         double l1 = 0.0, l2 = 0.0;
-         if (lane > p + 1 && lane < w) {
-            double w1 = sa[lane + p * LDS], w2 = sa[lane + (p + 1) * LDS];
-            sld[lane + p * LDS] = w1;
-            sld[lane + (p + 1) * LDS] = w2;
-            l1 = d11 * w1 + d21 * w2;
-            l2 = d21 * w1 + d22 * w2;
-            sa[lane + p * LDS] = l1;
-            sa[lane + (p + 1) * LDS] = l2;
-         }
-         __syncwarp();
-         if (lane > p + 1 && lane < w)
-            for (int c = p + 2; c < w; ++c)
-               sa[lane + c * LDS] -= l1 * sld[c + p * LDS] + l2 * sld[c + (p + 1) * LDS];
-         __syncwarp();
-         if (lane == 0) {
-            sd[2 * p] = d11; sd[2 * p + 1] = d21; sd[2 * p + 2] = DINF; sd[2 * p + 3] = d22;
-            sptype[p] = 1; sptype[p + 1] = 2;
-            sa[p + p * LDS] = 1.0; sa[p + 1 + p * LDS] = 0.0; sa[p + (p + 1) * LDS] = 0.0;
-            sa[p + 1 + (p + 1) * LDS] = 1.0;
-            sld[p + 1 + p * LDS] = 0.0;
-         }
-         if (lane > p + 1 && lane < w) { sa[p + lane * LDS] = 0.0; sa[p + 1 + lane * LDS] = 0.0; }
-         __syncwarp();
-         p += 2;
-      }
+   for (int c = a + 1 + threadIdx.x; c < b; c += blockDim.x) {
+      double t = L[c + a * ld]; L[c + a * ld] = L[b + c * ld]; L[b + c * ld] = t;
    }
-   if (err) {
-      if (lane == 0) { f.flag = err; f.w = 0; }
-      return;
+   for (int r = b + 1 + threadIdx.x; r < f.m; r += blockDim.x) {
+      double t = L[r + a * ld]; L[r + a * ld] = L[r + b * ld]; L[r + b * ld] = t;
    }
-   __syncwarp();
-   // publish: L11, (LD)11, permuted original block, D, lperm/ptype, and the block's own rows of
-   // the panel workspaces
-   double* L11 = f.dbuf;
-   double* LD11 = f.dbuf + NB * NB;
-   double* A0p = f.dbuf + 2 * NB * NB;
-   double* dk = f.dbuf + 3 * NB * NB;
-   int permuted = 0;
-   for (int k = 0; k < w; ++k) {
-      if (lane < w) {
-         int i = lane;
-         double lv = i > k ? sa[i + k * LDS] : (i == k ? 1.0 : 0.0);
-         double ldv = i > k ? sld[i + k * LDS] : 0.0;
-         L11[i + k * NB] = lv;
-         LD11[i + k * NB] = ldv;
-         A0p[i + k * NB] = s0[slperm[i] + slperm[k] * LDS];
-         f.Wl[(size_t)k * f.m + done + i] = lv;
-         f.Wld[(size_t)k * f.m + done + i] = ldv;
-      }
-      if (slperm[k] != k) permuted = 1;
-   }
-   for (int i = lane; i < 2 * NB + 2; i += 32) dk[i] = sd[i];
-   if (lane < NB) { f.ibuf[lane] = slperm[lane]; f.ibuf[NB + lane] = sptype[lane]; }
-   if (lane == 0) f.ibuf[2 * NB] = permuted;
-}
-
-// ------------------------------------------------------------------------------------------
-// K2: L21 = A21 P L11^{-T} D^{-1} for the rows below the block, with the a-posteriori test
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_apply(FrontDev* fr, const int* list, Params prm) {
-   FrontDev& f = fr[list[blockIdx.x]];
-   const int w = f.w;
-   if (w == 0 || f.flag < 0) return;
-   const int done = f.done, m = f.m;
-   const int r0 = done + w + blockIdx.y * 128;
-   if (r0 >= m) return;
-   __shared__ double sL[NB * NB];
-   __shared__ double sdk[2 * NB + 2];
-   __shared__ int slperm[NB], sptype[NB];
-   for (int i = threadIdx.x; i < NB * NB; i += 128) sL[i] = f.dbuf[i];
-   for (int i = threadIdx.x; i < 2 * NB + 2; i += 128) sdk[i] = f.dbuf[3 * NB * NB + i];
-   if (threadIdx.x < NB) { slperm[threadIdx.x] = f.ibuf[threadIdx.x]; sptype[threadIdx.x] = f.ibuf[NB + threadIdx.x]; }
    __syncthreads();
-   const int r = r0 + threadIdx.x;
-   int myfail = w;
-   if (r < m) {
-      double x[NB];
-      const size_t ldl = f.ldl;
-#pragma unroll
-      for (int k = 0; k < NB; ++k) {
-         x[k] = 0.0;
-         if (k < w) {
-            x[k] = f.L[(size_t)(done + slperm[k]) * ldl + r];
-            f.Wo[(size_t)k * m + r] = x[k];
-         }
-      }
-#pragma unroll
-      for (int k = 1; k < NB; ++k) {
-         if (k < w) {
-            double s = x[k];
-#pragma unroll
-            for (int i = 0; i < k; ++i) s -= x[i] * sL[k + i * NB];
-            x[k] = s;
-         }
-      }
-#pragma unroll
-      for (int k = 0; k < NB; ++k) {
-         if (k < w) {
-            int pt = sptype[k];
-            double l;
-            if (pt == 0) {
-               double d11 = sdk[2 * k];
-               if (d11 == 0.0) l = (fabs(x[k]) < prm.small_) ? 0.0 : DINF * x[k];
-               else l = x[k] * d11;
-            } else if (pt == 1) {
-               l = sdk[2 * k] * x[k] + sdk[2 * k + 1] * x[(k + 1) & (NB - 1)];
-            } else {
-               l = sdk[2 * k - 1] * x[(k - 1) & (NB - 1)] + sdk[2 * k + 1] * x[k];
-            }
-            f.Wl[(size_t)k * m + r] = l;
-            f.Wld[(size_t)k * m + r] = x[k];
-            if (!prm.posdef && (!(fabs(l) <= prm.lim)) && k < myfail) myfail = k;
-         }
-      }
-   }
-#pragma unroll
-   for (int off = 16; off > 0; off >>= 1) myfail = min(myfail, __shfl_xor_sync(0xffffffffu, myfail, off));
-   if ((threadIdx.x & 31) == 0 && myfail < w) atomicMin(&f.fail, myfail);
 }
 
-// ------------------------------------------------------------------------------------------
-// K3: commit the panel: accepted columns become L, failed columns get their (permuted)
-// original values back; finished L columns and the pivot list follow the block's permutation
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_commit(FrontDev* fr, const int* list) {
-   FrontDev& f = fr[list[blockIdx.x]];
-   const int w = f.w;
-   if (w == 0 || f.flag < 0) return;
-   const int done = f.done, m = f.m;
-   const int* lperm = f.ibuf;
-   const int nelim = compute_nelim(f.fail, w, f.ibuf + NB);
-   const int nrchunk = (m + 127) / 128;
-   const size_t ldl = f.ldl;
-   if ((int)blockIdx.y < nrchunk) {
-      const int r = blockIdx.y * 128 + threadIdx.x;
-      if (r < done || r >= m) return;
-      if (r >= done + w) {
-         for (int k = 0; k < w; ++k)
-            f.L[(size_t)(done + k) * ldl + r] = k < nelim ? f.Wl[(size_t)k * m + r] : f.Wo[(size_t)k * m + r];
-      } else {
-         const int i = r - done;
-         const double* L11 = f.dbuf;
-         const double* A0p = f.dbuf + 2 * NB * NB;
-         for (int k = 0; k <= i; ++k)
-            f.L[(size_t)(done + k) * ldl + r] = k < nelim ? (i == k ? 1.0 : L11[i + k * NB]) : A0p[i + k * NB];
-         if (i == 0) {
-            const double* dk = f.dbuf + 3 * NB * NB;
-            for (int k = 0; k < nelim; ++k) {
-               f.D[2 * (done + k)] = dk[2 * k];
-               f.D[2 * (done + k) + 1] = dk[2 * k + 1];
-            }
-            if (f.ibuf[2 * NB]) {
-               int tmp[NB];
-#pragma unroll
-               for (int q = 0; q < NB; ++q) tmp[q] = q < w ? f.perm[done + lperm[q]] : 0;
-#pragma unroll
-               for (int q = 0; q < NB; ++q) if (q < w) f.perm[done + q] = tmp[q];
-#pragma unroll
-               for (int q = 0; q < NB; ++q) tmp[q] = q < w ? f.orig[done + lperm[q]] : 0;
-#pragma unroll
-               for (int q = 0; q < NB; ++q) if (q < w) f.orig[done + q] = tmp[q];
-            }
-         }
-      }
-   } else {
-      if (!f.ibuf[2 * NB]) return;
-      const int c = (blockIdx.y - nrchunk) * 128 + threadIdx.x;
-      if (c >= done) return;
-      double tmp[NB];
-#pragma unroll
-      for (int q = 0; q < NB; ++q) tmp[q] = q < w ? f.L[(size_t)c * ldl + done + lperm[q]] : 0.0;
-#pragma unroll
-      for (int q = 0; q < NB; ++q) if (q < w) f.L[(size_t)c * ldl + done + q] = tmp[q];
-   }
-}
-
-// ------------------------------------------------------------------------------------------
-// K4: trailing update  T(r,c) -= sum_k Wl(r,k) * Wld(c,k), r >= c >= done+nelim, lower tiles only
-// (FP64 FMA version; the DMMA version is k_update_mma below)
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tile_from_id(int id, int& ti, int& tj) {
-   int t = (int)((sqrtf(8.0f * (float)id + 1.0f) - 1.0f) * 0.5f);
-   while ((t + 1) * (t + 2) / 2 <= id) ++t;
-   while (t * (t + 1) / 2 > id) --t;
-   ti = t;
-   tj = id - t * (t + 1) / 2;
-}
-
-__global__ void __launch_bounds__(256) k_update(FrontDev* fr, const int* list) {
-   const FrontDev& f = fr[list[blockIdx.x]];
-   const int w = f.w;
-   if (w == 0 || f.flag < 0) return;
-   const int nelim = compute_nelim(f.fail, w, f.ibuf + NB);
-   if (nelim == 0) return;
-   const int s0 = f.done + nelim, m = f.m;
-   const int nt = (m - s0 + UT - 1) / UT;
-   const int ntiles = nt * (nt + 1) / 2;
-   __shared__ double As[NB][UT + 1], Bs[NB][UT + 1];
-   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-   for (int id = blockIdx.y; id < ntiles; id += gridDim.y) {
-      int ti, tj;
-      tile_from_id(id, ti, tj);
-      const int rbase = s0 + ti * UT, cbase = s0 + tj * UT;
-      __syncthreads();
-      for (int i = threadIdx.x; i < NB * UT; i += 256) {
-         int k = i / UT, rr = i % UT;
-         double a = 0.0, b = 0.0;
-         if (k < nelim) {
-            if (rbase + rr < m) a = f.Wl[(size_t)k * m + rbase + rr];
-            if (cbase + rr < m) b = f.Wld[(size_t)k * m + cbase + rr];
-         }
-         As[k][rr] = a;
-         Bs[k][rr] = b;
-      }
-      __syncthreads();
-      double acc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-      for (int k = 0; k < nelim; ++k) {
-         double av[4], bv[4];
-#pragma unroll
-         for (int i = 0; i < 4; ++i) { av[i] = As[k][tx + 16 * i]; bv[i] = Bs[k][ty + 16 * i]; }
-#pragma unroll
-         for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-         int c = cbase + ty + 16 * j;
-         if (c >= m) continue;
-#pragma unroll
-         for (int i = 0; i < 4; ++i) {
-            int r = rbase + tx + 16 * i;
-            if (r >= m || r < c) continue;
-            double* p = felem(f, r, c);
-            *p -= acc[i][j];
-         }
-      }
-   }
-}
+#include "factor_kernels.cuh"
+constexpr int UPD_SMEM = 4 * BK * LDT * (int)sizeof(double);
 
 // ------------------------------------------------------------------------------------------
 // TPP finish (ldlt_tpp.cxx:166-270), one CTA per front, right-looking on the whole trailing
@@ -587,28 +205,6 @@ __device__ double tpp_rc_max(const FrontDev& f, int from, int col, int excl, dou
    for (int r = col + 1 + threadIdx.x; r < f.m; r += blockDim.x)
       if (r != excl) v = fmax(v, fabs(*felem(f, r, col)));
    return block_max(v, sred);
-}
-
-__device__ void block_sym_swap(const FrontDev& f, int a, int b) {
-   if (a == b) return;
-   if (a > b) { int s = a; a = b; b = s; }
-   double* L = f.L;
-   const size_t ld = f.ldl;
-   for (int c = threadIdx.x; c < a; c += blockDim.x) {
-      double t = L[a + c * ld]; L[a + c * ld] = L[b + c * ld]; L[b + c * ld] = t;
-   }
-   if (threadIdx.x == 0) {
-      double t = L[a + a * ld]; L[a + a * ld] = L[b + b * ld]; L[b + b * ld] = t;
-      int s = f.perm[a]; f.perm[a] = f.perm[b]; f.perm[b] = s;
-      s = f.orig[a]; f.orig[a] = f.orig[b]; f.orig[b] = s;
-   }
-   for (int c = a + 1 + threadIdx.x; c < b; c += blockDim.x) {
-      double t = L[c + a * ld]; L[c + a * ld] = L[b + c * ld]; L[b + c * ld] = t;
-   }
-   for (int r = b + 1 + threadIdx.x; r < f.m; r += blockDim.x) {
-      double t = L[r + a * ld]; L[r + a * ld] = L[r + b * ld]; L[r + b * ld] = t;
-   }
-   __syncthreads();
 }
 
 __device__ void tpp_elim1(const FrontDev& f, int ne, double d11) {
@@ -770,8 +366,9 @@ __global__ void __launch_bounds__(256) k_tpp(FrontDev* fr, const int* list, Para
 __global__ void k_collect(const FrontDev* fr, int slot0, int nslots, int* out) {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= nslots) return;
-   out[2 * i] = fr[slot0 + i].done;
-   out[2 * i + 1] = fr[slot0 + i].flag;
+   out[3 * i] = fr[slot0 + i].done;
+   out[3 * i + 1] = fr[slot0 + i].flag;
+   out[3 * i + 2] = fr[slot0 + i].gend;
 }
 
 // inertia: counters[0..2] = num_neg, num_two, num_zero  (NumericSubtree.hxx:242-274)
@@ -1153,7 +750,7 @@ Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
          int64_t ldl = align_up(st.nrow, 2), cm = st.nrow - st.ncol;
          P->est_factor_doubles += ldl * st.ncol + 32;
          c += align_up(cm, 2) * cm + 32;
-         ws += 3 * (int64_t)st.nrow * NB + 3 * NB * NB + 2 * NB + 2 + 3 * NB + 128;
+         ws += (int64_t)st.nrow * (NBO + NB) + 4 * NB * NB + 2 * NB + 2 + 3 * NB + 128;
       }
       P->est_c_doubles[l & 1] = std::max(P->est_c_doubles[l & 1], c);
       P->est_ws_doubles = std::max(P->est_ws_doubles, ws);
@@ -1233,6 +830,7 @@ class Numeric {
 int Numeric::init() {
    if (d_fr) return 0;
    CU(cudaSetDevice(P->device));
+   CU(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM));
    const int nn = std::max(P->nnodes, 1);
    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
    CU(cudaEventCreate(&ev0));
@@ -1241,11 +839,11 @@ int Numeric::init() {
    CU(cudaMalloc(&d_fr, sizeof(FrontDev) * nn));
    CU(cudaMemset(d_fr, 0, sizeof(FrontDev) * nn));
    CU(cudaMallocHost(&pin_fr, sizeof(FrontDev) * nn));
-   pin_i_cap = (size_t)4 * nn + 64;
+   pin_i_cap = (size_t)6 * nn + 64;
    CU(cudaMallocHost(&pin_i, sizeof(int) * pin_i_cap));
    CU(cudaMalloc(&d_child_doff, sizeof(int) * std::max<size_t>(P->child_idx.size(), 1)));
    CU(cudaMalloc(&d_list, sizeof(int) * 2 * nn));
-   CU(cudaMalloc(&d_collect, sizeof(int) * 2 * nn));
+   CU(cudaMalloc(&d_collect, sizeof(int) * 3 * nn));
    CU(cudaMalloc(&d_counters, sizeof(int) * 8));
    CU(cudaMalloc(&d_tileptr, sizeof(int64_t) * (nn + 1)));
    CU(cudaMalloc(&d_xw_off, sizeof(int64_t) * (nn + 1)));
@@ -1317,12 +915,12 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          f.m = ss.nrow + nd; f.n = ss.ncol + nd;
          f.ldl = (int)align_up(f.m, 2);
          f.ldc = (int)align_up(f.m - f.n, 2);
-         f.done = 0; f.end = f.n; f.w = 0; f.fail = 0; f.nelim = 0; f.flag = 0;
+         f.done = 0; f.oend = 0; f.gend = f.n; f.w = 0; f.fail = 0; f.jstart = 0; f.jend0 = 0; f.nelim = 0; f.flag = 0;
          totL += align_up((size_t)f.ldl * f.n, 32);
          totC += align_up((size_t)f.ldc * (f.m - f.n), 32);
          totD += align_up(2 * (size_t)f.n + 2, 32);
          totP += 2 * align_up((size_t)f.n + 1, 32);
-         totW += align_up(3 * (size_t)f.m * NB + 3 * NB * NB + 2 * NB + 2, 32) + 128;
+         totW += align_up((size_t)f.m * (NBO + NB) + 4 * NB * NB + 2 * NB + 2, 32) + 128;
          maxfront = std::max(maxfront, f.m);
       }
       double* Lb = (double*)fac.alloc(totL * 8);
@@ -1340,10 +938,10 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             f.D = Db + oD; oD += align_up(2 * (size_t)f.n + 2, 32);
             f.perm = Pb + oP; f.orig = f.perm + align_up((size_t)f.n + 1, 32); oP += 2 * align_up((size_t)f.n + 1, 32);
             double* wp = Wb + oW;
-            oW += align_up(3 * (size_t)f.m * NB + 3 * NB * NB + 2 * NB + 2, 32) + 128;
-            f.Wl = wp; f.Wld = wp + (size_t)f.m * NB; f.Wo = wp + 2 * (size_t)f.m * NB;
-            f.dbuf = wp + 3 * (size_t)f.m * NB;
-            f.ibuf = (int*)(f.dbuf + 3 * NB * NB + 2 * NB + 2);
+            oW += align_up((size_t)f.m * (NBO + NB) + 4 * NB * NB + 2 * NB + 2, 32) + 128;
+            f.Wld = wp; f.Wo = wp + (size_t)f.m * NBO;
+            f.dbuf = wp + (size_t)f.m * (NBO + NB);
+            f.ibuf = (int*)(f.dbuf + 4 * NB * NB + 2 * NB + 2);
          }
       }
       memcpy(pin_fr + s0, hfr.data() + s0, sizeof(FrontDev) * ns);
@@ -1410,7 +1008,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          }
          if (pin_off) CU(cudaStreamSynchronize(st));   // staging regions free again
       }
-      // factor: fronts bucketed by size class, sorted by candidate count (descending) inside
+      // factor: fronts bucketed by size class, sorted by candidate count (descending) inside.
+      // Each bucket runs rounds of outer blocks (NBO columns) of inner panels (NB columns); the
+      // device keeps the progress counters, the host only needs them once per round.
       {
          std::vector<int> order(ns);
          for (int i = 0; i < ns; ++i) order[i] = s0 + i;
@@ -1426,6 +1026,18 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          });
          memcpy(pin_i, order.data(), sizeof(int) * ns);
          CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+         auto prof_begin = [&]() {
+            if (prof_used + 2 > prof_ev.size()) {
+               size_t old = prof_ev.size();
+               prof_ev.resize(old + 256);
+               for (size_t q = old; q < prof_ev.size(); ++q) cudaEventCreate(&prof_ev[q]);
+            }
+            cudaEventRecord(prof_ev[prof_used], st);
+         };
+         auto prof_end = [&]() { cudaEventRecord(prof_ev[prof_used + 1], st); prof_used += 2; };
+         // remaining candidates per front as the host believes them (exact when nothing fails)
+         std::vector<int> rem_done(ns, 0), rem_gend(ns, 0);
+         for (int i = 0; i < ns; ++i) { rem_done[i] = 0; rem_gend[i] = hfr[order[i]].n; }
          int i0 = 0;
          while (i0 < ns) {
             int c = cls(order[i0]), i1 = i0;
@@ -1435,81 +1047,125 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                maxn = std::max(maxn, hfr[order[i1]].n);
                ++i1;
             }
-            const int nsteps = (maxn + NB - 1) / NB;
             const int* lst = d_list + i0;
-            for (int sidx = 0; sidx < nsteps; ++sidx) {
-               // active prefix: fronts with more than sidx panels
-               int na = 0;
-               while (i0 + na < i1 && (hfr[order[i0 + na]].n + NB - 1) / NB > sidx) ++na;
+            const int ncolchunks = (maxn + 127) / 128;
+            const int ycommit = 1 + ncolchunks + (maxm + 127) / 128;
+            const int yapply = std::max(1, (maxm + 127) / 128);
+            const int nouter = (maxn + NBO - 1) / NBO;
+            for (int ob = 0; ob < nouter; ++ob) {
+               int na = 0;   // active prefix: fronts that still have an outer block number ob
+               while (i0 + na < i1 && (hfr[order[i0 + na]].n + NBO - 1) / NBO > ob) ++na;
                if (na == 0) break;
-               k_diag<<<na, 32, 0, st>>>(d_fr, lst, prm, 0);
-               int rows_below = maxm - sidx * 0;   // failures can keep `done` behind the host's guess
-               int ychunks = (rows_below + 127) / 128;
-               k_apply<<<dim3(na, std::max(ychunks, 1)), 128, 0, st>>>(d_fr, lst, prm);
-               int ycommit = (maxm + 127) / 128 + (maxn + 127) / 128;
-               k_commit<<<dim3(na, ycommit), 128, 0, st>>>(d_fr, lst);
-               int rem = std::max(maxm - (sidx + 1) * NB + NB, UT);
-               int nt = (rem + UT - 1) / UT;
-               int64_t tiles = (int64_t)nt * (nt + 1) / 2;
-               int ygrid = (int)std::min<int64_t>(tiles, std::max<int64_t>(1, (148 * 8) / std::max(na, 1)));
-               ygrid = std::max(ygrid, 1);
-               if (o.profile) {
-                  if (prof_used + 2 > prof_ev.size()) {
-                     size_t old = prof_ev.size();
-                     prof_ev.resize(old + 256);
-                     for (size_t q = old; q < prof_ev.size(); ++q) cudaEventCreate(&prof_ev[q]);
+               int maxw_outer = 0;
+               for (int q = 0; q < na; ++q) maxw_outer = std::max(maxw_outer, std::min(NBO, hfr[order[i0 + q]].n - ob * NBO));
+               const int ninner = (maxw_outer + NB - 1) / NB;
+               for (int j = 0; j < ninner; ++j) {
+                  k_diag<<<na, 256, 0, st>>>(d_fr, lst, prm, j == 0 ? 1 : 0);
+                  k_apply<<<dim3(na, yapply), 128, 0, st>>>(d_fr, lst, prm);
+                  k_commit<<<dim3(na, ycommit), 128, 0, st>>>(d_fr, lst, ncolchunks);
+                  launches += 3;
+                  // inner update: columns of the outer block behind this panel
+                  const int colsleft = maxw_outer - (j + 1) * NB;
+                  if (colsleft > 0 || !posdef) {
+                     int ntr = (maxm + TM - 1) / TM;
+                     int ygrid = std::max(1, std::min(ntr, (148 * 2) / std::max(na, 1)));
+                     if (o.profile) {
+                        for (int q = 0; q < na; ++q) {
+                           const FrontDev& ff = hfr[order[i0 + q]];
+                           double dn = ob * NBO + j * NB, je = std::min<double>(ff.n, (ob + 1) * NBO);
+                           double ww = std::min<double>(NB, je - dn), cb = dn + ww;
+                           if (ww > 0 && je > cb) prof_flops += 2.0 * ww * ((je - cb) * (ff.m - cb) - 0.5 * (je - cb) * (je - cb - 1));
+                        }
+                        prof_begin();
+                     }
+                     k_update<<<dim3(na, ygrid), 256, UPD_SMEM, st>>>(d_fr, lst, 0);
+                     if (o.profile) prof_end();
+                     ++launches;
                   }
-                  for (int q = 0; q < na; ++q) {
-                     const FrontDev& ff = hfr[order[i0 + q]];
-                     double dn = sidx * NB, ww = std::min<double>(NB, ff.n - dn), tt = ff.m - dn - ww;
-                     if (ww > 0 && tt > 0) prof_flops += ww * tt * (tt + 1);
-                  }
-                  cudaEventRecord(prof_ev[prof_used], st);
                }
-               k_update<<<dim3(na, ygrid), 256, 0, st>>>(d_fr, lst);
-               if (o.profile) { cudaEventRecord(prof_ev[prof_used + 1], st); prof_used += 2; }
-               launches += 4;
+               // outer update: everything right of the outer block
+               {
+                  int rem = maxm - ob * NBO;
+                  int nt = std::max(1, (rem + TM - 1) / TM);
+                  int64_t tiles = (int64_t)nt * (nt + 1) / 2;
+                  int ygrid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, std::max<int64_t>(1, (148 * 4) / std::max(na, 1))));
+                  if (o.profile) {
+                     for (int q = 0; q < na; ++q) {
+                        const FrontDev& ff = hfr[order[i0 + q]];
+                        double je = std::min<double>(ff.n, (ob + 1) * NBO), kc2 = je - ob * NBO, tt = ff.m - je;
+                        if (kc2 > 0 && tt > 0) prof_flops += kc2 * tt * (tt + 1);
+                     }
+                     prof_begin();
+                  }
+                  k_update<<<dim3(na, ygrid), 256, UPD_SMEM, st>>>(d_fr, lst, 1);
+                  if (o.profile) prof_end();
+                  ++launches;
+               }
             }
-            k_diag<<<i1 - i0, 32, 0, st>>>(d_fr, lst, prm, 1);
+            k_diag<<<i1 - i0, 256, 0, st>>>(d_fr, lst, prm, 2);
             ++launches;
             i0 = i1;
          }
       }
-      // read back progress
-      k_collect<<<(ns + 255) / 256, 256, 0, st>>>(d_fr, s0, ns, d_collect);
-      ++launches;
-      CU(cudaMemcpyAsync(pin_i, d_collect, sizeof(int) * 2 * ns, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
+      // read back progress; fronts whose scheduled panels did not exhaust their candidates
+      // (only possible after failures) get further rounds
+      auto collect = [&]() -> int {
+         k_collect<<<(ns + 255) / 256, 256, 0, st>>>(d_fr, s0, ns, d_collect);
+         ++launches;
+         if (cudaMemcpyAsync(pin_i, d_collect, sizeof(int) * 3 * ns, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+         if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+         for (int i = 0; i < ns; ++i) {
+            FrontDev& f = hfr[s0 + i];
+            f.done = pin_i[3 * i];
+            f.nelim = f.done;
+            f.flag = pin_i[3 * i + 1];
+            f.gend = pin_i[3 * i + 2];
+            if (f.flag < 0) flag = f.flag;
+         }
+         return 0;
+      };
+      if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
+      if (flag < 0) break;
+      for (int round = 0; round < 1000; ++round) {
+         tpp_list.clear();
+         for (int i = 0; i < ns; ++i) if (hfr[s0 + i].done < hfr[s0 + i].gend) tpp_list.push_back(s0 + i);
+         if (tpp_list.empty()) break;
+         int nt = (int)tpp_list.size(), maxm = 0, maxn = 0;
+         for (int s : tpp_list) { maxm = std::max(maxm, hfr[s].m); maxn = std::max(maxn, hfr[s].n); }
+         memcpy(pin_i, tpp_list.data(), sizeof(int) * nt);
+         CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * nt, cudaMemcpyHostToDevice, st));
+         const int ncolchunks = (maxn + 127) / 128;
+         for (int j = 0; j < NBO / NB; ++j) {
+            k_diag<<<nt, 256, 0, st>>>(d_fr, d_list, prm, j == 0 ? 1 : 0);
+            k_apply<<<dim3(nt, std::max(1, (maxm + 127) / 128)), 128, 0, st>>>(d_fr, d_list, prm);
+            k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 127) / 128), 128, 0, st>>>(d_fr, d_list, ncolchunks);
+            k_update<<<dim3(nt, std::max(1, std::min((maxm + TM - 1) / TM, 64))), 256, UPD_SMEM, st>>>(d_fr, d_list, 0);
+            launches += 4;
+         }
+         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 1);
+         k_diag<<<nt, 256, 0, st>>>(d_fr, d_list, prm, 2);
+         launches += 2;
+         if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
+         if (flag < 0) break;
+      }
+      if (flag < 0) break;
       tpp_list.clear();
       for (int i = 0; i < ns; ++i) {
          FrontDev& f = hfr[s0 + i];
-         f.done = pin_i[2 * i];
-         f.nelim = f.done;
-         f.flag = pin_i[2 * i + 1];
-         if (f.flag < 0) flag = f.flag;
          if (f.done < f.n) { tpp_list.push_back(s0 + i); nfp += f.n - f.done; }
       }
-      if (flag < 0) break;
       if (!tpp_list.empty() && !posdef) {
          int nt = (int)tpp_list.size();
          memcpy(pin_i, tpp_list.data(), sizeof(int) * nt);
          CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * nt, cudaMemcpyHostToDevice, st));
          k_tpp<<<nt, 256, 0, st>>>(d_fr, d_list, prm);
-         k_collect<<<(ns + 255) / 256, 256, 0, st>>>(d_fr, s0, ns, d_collect);
-         launches += 2;
-         CU(cudaMemcpyAsync(pin_i, d_collect, sizeof(int) * 2 * ns, cudaMemcpyDeviceToHost, st));
-         CU(cudaStreamSynchronize(st));
-         for (int i = 0; i < ns; ++i) {
-            FrontDev& f = hfr[s0 + i];
-            f.done = pin_i[2 * i];
-            f.nelim = f.done;
-            f.flag = pin_i[2 * i + 1];
-            if (f.flag < 0) flag = f.flag;
-            nsp += f.n - f.done;
-         }
+         ++launches;
+         if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
+         for (int i = 0; i < ns; ++i) nsp += hfr[s0 + i].n - hfr[s0 + i].done;
       } else if (!tpp_list.empty() && posdef) {
          flag = SSIDS_ERROR_NOT_POS_DEF;
       }
+      if (flag < 0) break;
       for (int s = s0; s < s1; ++s) num_delay += hfr[s].n - hfr[s].nelim;
    }
    if (flag >= 0) {

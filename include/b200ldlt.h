@@ -64,7 +64,8 @@ typedef struct b200ldlt_options {
    double multiplier;   /* factor-storage slack for delayed pivots (>= 1.0) */
    int device;          /* CUDA device ordinal, -1: current device */
    int panel_width;     /* reserved; 0 = engine default */
-   int reserved[7];     /* reserved[0] = 1: profile mode (CUDA events around every trailing update) */
+   int reserved[7];     /* reserved[0] = 1: profile mode (CUDA events around every trailing update);
+                           reserved[1] = 1: do not fuse chains (engine tree == reference tree) */
 } b200ldlt_options;
 
 /* Inform: shaped like ssids_inform (src/ssids/inform.f90:17-49). */
@@ -143,6 +144,13 @@ int b200ldlt_free(void **akeep, void **fkeep);
 int b200ldlt_akeep_sizes(void *akeep, int *nnodes, int64_t *nrlist, int64_t *nnlist);
 int b200ldlt_akeep_get(void *akeep, int array_base, int *sptr, int *sparent, int64_t *rptr,
                        int *rlist, int64_t *nptr, int64_t *nlist, int *invp);
+
+/* The engine's own (numeric) tree: the reference tree with chain links fused into single fronts
+ * (explicit zeros bounded; analyse.cpp fuse_chains).  Same array conventions as akeep_get.  It is a
+ * valid assembly tree for the same matrix and order, so the oracles can be driven with it too. */
+int b200ldlt_ntree_sizes(void *akeep, int *nnodes, int64_t *nrlist, int64_t *nnlist);
+int b200ldlt_ntree_get(void *akeep, int array_base, int *sptr, int *sparent, int64_t *rptr,
+                       int *rlist, int64_t *nptr, int64_t *nlist);
 
 /* ---- multi-GPU (one process per GPU; the host side moves contribution blocks with NCCL) -------- */
 /* Partition the assembly tree into leaf subtrees for `nranks` devices + a root part

@@ -16,7 +16,7 @@ from oracle.refssids import Oracle, RefSSIDS, have_ref, permuted_solve  # noqa: 
 def check(prob, posdef=False, detail=True, use_ref=False, **opts):
     s = Solver(**opts)
     flag = s.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"])
-    sym = s.symbolic()
+    sym = s.numeric_tree()   # the engine's own (chain-fused) tree: a valid assembly tree for the oracles too
     inf = s.inform
     n = prob["n"]
     rng = np.random.default_rng(1)
