@@ -405,163 +405,7 @@ __global__ void k_stats(const FrontDev* fr, int nslots, int* counters) {
    }
 }
 
-// ------------------------------------------------------------------------------------------
-// solve kernels (level scheduled; one CTA per front; per-front work vectors, no atomics)
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int row_gidx(const FrontDev& f, const int* rl, int r) {
-   return r < f.n ? f.perm[r] : rl[f.ncol + (r - f.n)];
-}
-
-__global__ void k_permute_in(const double* __restrict__ x, double* __restrict__ xp, const int* order, int n) {
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n && order[i] >= 0) xp[order[i]] = x[i];
-}
-__global__ void k_permute_out(double* __restrict__ x, const double* __restrict__ xp, const int* order, int n) {
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n && order[i] >= 0) x[i] = xp[order[i]];
-}
-
-// forward: xw = [b(pivots); 0] + children, y = L11^{-1} xw1, xw2 -= L21 y, x(pivots) = y
-__global__ void __launch_bounds__(256) k_solve_fwd(const FrontDev* fr, const SlotStatic* ss,
-                                                   const int* child_idx, const int* child_doff,
-                                                   const int* rel, const int64_t* xw_off, double* XW,
-                                                   double* XA, double* x, int slot0, int posdef_scale) {
-   const int s = slot0 + blockIdx.x;
-   const FrontDev& f = fr[s];
-   const SlotStatic st = ss[s];
-   double* xw = XW + xw_off[s];
-   double* acc = XA + xw_off[s];   // children's contributions, indexed by the parent's ASSEMBLY order
-   const int m = f.m, ne = f.nelim;
-   __shared__ double ys[NB];
-   const bool has_children = st.child_end > st.child_begin;
-   if (has_children) {
-      for (int r = threadIdx.x; r < m; r += blockDim.x) acc[r] = 0.0;
-      __syncthreads();
-   }
-   for (int ci = st.child_begin; ci < st.child_end; ++ci) {
-      const int cs = child_idx[ci];
-      const FrontDev& fc = fr[cs];
-      const int t = fc.m - fc.nelim, nd = fc.n - fc.nelim, doff = child_doff[ci];
-      const double* xc = XW + xw_off[cs] + fc.nelim;
-      const int* relc = rel + ss[cs].rel_off;
-      for (int rr = threadIdx.x; rr < t; rr += blockDim.x) {
-         int d;
-         if (rr < nd) d = f.ncol + doff + rr;
-         else { d = relc[rr - nd]; if (d >= f.ncol) d += f.ndelay_in; }
-         acc[d] += xc[rr];
-      }
-      __syncthreads();
-   }
-   // pivoting permuted the candidate rows after assembly: orig[] maps them back
-   for (int r = threadIdx.x; r < m; r += blockDim.x) {
-      double v = r < ne ? x[f.perm[r]] : 0.0;
-      if (has_children) v += acc[r < f.n ? f.orig[r] : r];
-      xw[r] = v;
-   }
-   __syncthreads();
-   const size_t ldl = f.ldl;
-   for (int k0 = 0; k0 < ne; k0 += NB) {
-      const int kb = min(NB, ne - k0);
-      if (threadIdx.x < 32) {
-         const int i = threadIdx.x;
-         double xi = i < kb ? xw[k0 + i] : 0.0;
-         for (int j = 0; j < kb; ++j) {
-            double yj = __shfl_sync(0xffffffffu, xi, j);
-            if (i > j && i < kb) xi -= f.L[(size_t)(k0 + j) * ldl + k0 + i] * yj;
-         }
-         if (i < kb) { xw[k0 + i] = xi; ys[i] = xi; }
-      }
-      __syncthreads();
-      for (int r = k0 + kb + threadIdx.x; r < m; r += blockDim.x) {
-         double sacc = 0.0;
-         for (int j = 0; j < kb; ++j) sacc += f.L[(size_t)(k0 + j) * ldl + r] * ys[j];
-         xw[r] -= sacc;
-      }
-      __syncthreads();
-   }
-   for (int k = threadIdx.x; k < ne; k += blockDim.x) {
-      double v = xw[k];
-      if (posdef_scale) v *= sqrt(f.D[2 * k]);   // L_chol = L sqrt(D): y_chol = D^{-1/2} y  (D stored inverted)
-      x[f.perm[k]] = v;
-   }
-}
-
-__global__ void k_solve_diag(const FrontDev* fr, double* x, int nslots) {
-   const int lane = threadIdx.x & 31;
-   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-   if (s >= nslots) return;
-   const FrontDev& f = fr[s];
-   for (int i = lane; i < f.nelim; i += 32) {
-      double a11 = f.D[2 * i];
-      if (isinf(a11) && i > 0) continue;
-      if (i + 1 < f.nelim && isinf(f.D[2 * i + 2])) {
-         double d21 = f.D[2 * i + 1], d22 = f.D[2 * i + 3];
-         double x1 = x[f.perm[i]], x2 = x[f.perm[i + 1]];
-         x[f.perm[i]] = a11 * x1 + d21 * x2;
-         x[f.perm[i + 1]] = d21 * x1 + d22 * x2;
-      } else {
-         x[f.perm[i]] *= a11;
-      }
-   }
-}
-
-// backward: x1 = L11^{-T} (y1 - L21^T x2); with do_diag the D^{-1} product is applied first
-__global__ void __launch_bounds__(256) k_solve_bwd(const FrontDev* fr, const SlotStatic* ss,
-                                                   const int* rlist, const int64_t* xw_off, double* XW,
-                                                   double* x, int slot0, int do_diag, int posdef_scale) {
-   const int s = slot0 + blockIdx.x;
-   const FrontDev& f = fr[s];
-   const int* rl = rlist + ss[s].rl_off;
-   double* xw = XW + xw_off[s];
-   const int m = f.m, ne = f.nelim;
-   __shared__ double dots[NB];
-   for (int r = threadIdx.x; r < m; r += blockDim.x) {
-      double v;
-      if (r >= ne) v = x[row_gidx(f, rl, r)];
-      else {
-         v = x[f.perm[r]];
-         if (posdef_scale) v *= sqrt(f.D[2 * r]);
-         else if (do_diag) {
-            double a11 = f.D[2 * r];
-            if (isinf(a11) && r > 0) {          // second of a 2x2: d21*x1 + d22*x2
-               v = f.D[2 * r - 1] * x[f.perm[r - 1]] + f.D[2 * r + 1] * v;
-            } else if (r + 1 < ne && isinf(f.D[2 * r + 2])) {
-               v = a11 * v + f.D[2 * r + 1] * x[f.perm[r + 1]];
-            } else {
-               v = a11 * v;
-            }
-         }
-      }
-      xw[r] = v;
-   }
-   __syncthreads();
-   const size_t ldl = f.ldl;
-   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-   const int nblk = (ne + NB - 1) / NB;
-   for (int b = nblk - 1; b >= 0; --b) {
-      const int k0 = b * NB, kb = min(NB, ne - k0);
-      for (int j = wid; j < kb; j += nw) {
-         double sacc = 0.0;
-         const double* col = f.L + (size_t)(k0 + j) * ldl;
-         for (int r = k0 + kb + lane; r < m; r += 32) sacc += col[r] * xw[r];
-#pragma unroll
-         for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
-         if (lane == 0) dots[j] = sacc;
-      }
-      __syncthreads();
-      if (threadIdx.x < 32) {
-         const int i = threadIdx.x;
-         double v = i < kb ? xw[k0 + i] - dots[i] : 0.0;
-         for (int j = kb - 1; j >= 0; --j) {
-            double xj = __shfl_sync(0xffffffffu, v, j);
-            if (i < j) v -= f.L[(size_t)(k0 + i) * ldl + k0 + j] * xj;
-         }
-         if (i < kb) xw[k0 + i] = v;
-      }
-      __syncthreads();
-   }
-   for (int k = threadIdx.x; k < ne; k += blockDim.x) x[f.perm[k]] = xw[k];
-}
+#include "solve_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -785,6 +629,13 @@ class Numeric {
    int *d_child_doff = nullptr, *d_list = nullptr, *d_collect = nullptr, *d_counters = nullptr;
    int64_t* d_tileptr = nullptr;
    int64_t* d_xw_off = nullptr;
+   int64_t* d_part_off = nullptr;
+   int* d_slist = nullptr;
+   std::vector<int> slist, lvl_steps, lvl_maxm;
+   std::vector<std::vector<int>> lvl_nact, lvl_actm;
+   int64_t part_total = 0;
+   double* d_part = nullptr;
+   size_t part_cap = 0;
    std::vector<int> child_doff;
    double* d_val = nullptr;
    double *d_x = nullptr, *d_xp = nullptr, *d_xw = nullptr;
@@ -804,7 +655,7 @@ class Numeric {
       cudaSetDevice(P->device);
       fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
-      cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
+      cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
       if (st) cudaStreamDestroy(st);
@@ -847,6 +698,8 @@ int Numeric::init() {
    CU(cudaMalloc(&d_counters, sizeof(int) * 8));
    CU(cudaMalloc(&d_tileptr, sizeof(int64_t) * (nn + 1)));
    CU(cudaMalloc(&d_xw_off, sizeof(int64_t) * (nn + 1)));
+   CU(cudaMalloc(&d_part_off, sizeof(int64_t) * (nn + 1)));
+   CU(cudaMalloc(&d_slist, sizeof(int) * nn));
    CU(cudaMalloc(&d_val, sizeof(double) * std::max<int64_t>(P->sym->nz, 1)));
    child_doff.assign(P->child_idx.size(), 0);
    hfr.assign(nn, FrontDev());
@@ -1211,6 +1064,36 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       for (int s = 0; s < nn; ++s) off[s + 1] = off[s] + align_up(hfr[s].m, 2);
       xw_total = off[nn];
       CU(cudaMemcpy(d_xw_off, off.data(), sizeof(int64_t) * (nn + 1), cudaMemcpyHostToDevice));
+      // partial-dot workspace of the backward solve: (row chunks + 1) x KB per front
+      std::vector<int64_t> poff(nn + 1, 0);
+      for (int s = 0; s < nn; ++s) poff[s + 1] = poff[s] + (int64_t)((hfr[s].m + RD - 1) / RD + 1) * KB;
+      part_total = poff[nn];
+      CU(cudaMemcpy(d_part_off, poff.data(), sizeof(int64_t) * (nn + 1), cudaMemcpyHostToDevice));
+      // per level: fronts sorted by eliminated columns (descending) so that the fronts active in
+      // column block `step` form a prefix
+      slist.assign(nn, 0);
+      lvl_steps.assign(P->nlevels, 0);
+      lvl_nact.assign(P->nlevels, std::vector<int>());
+      lvl_actm.assign(P->nlevels, std::vector<int>());
+      for (int l = 0; l < P->nlevels; ++l) {
+         const int a0 = P->lvl_ptr[l], a1 = P->lvl_ptr[l + 1];
+         for (int s = a0; s < a1; ++s) slist[s] = s;
+         std::sort(slist.begin() + a0, slist.begin() + a1, [&](int x, int y) {
+            if (hfr[x].nelim != hfr[y].nelim) return hfr[x].nelim > hfr[y].nelim;
+            return x < y;
+         });
+         const int steps = a1 > a0 ? (hfr[slist[a0]].nelim + KB - 1) / KB : 0;
+         lvl_steps[l] = steps;
+         lvl_nact[l].assign(steps, 0);
+         lvl_actm[l].assign(steps, 0);
+         for (int st2 = 0; st2 < steps; ++st2) {
+            int na = 0, mm = 0;
+            while (a0 + na < a1 && (hfr[slist[a0 + na]].nelim + KB - 1) / KB > st2) { mm = std::max(mm, hfr[slist[a0 + na]].m); ++na; }
+            lvl_nact[l][st2] = na;
+            lvl_actm[l][st2] = mm;
+         }
+      }
+      if (nn > 0) CU(cudaMemcpy(d_slist, slist.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
       // child delay offsets must describe the final state for the solve
       if (!child_doff.empty())
          CU(cudaMemcpy(d_child_doff, child_doff.data(), sizeof(int) * child_doff.size(), cudaMemcpyHostToDevice));
@@ -1244,6 +1127,13 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
       CU(cudaMalloc(&d_xw, 2 * ((size_t)xw_total + 2) * 8));
       xw_cap = 2 * ((size_t)xw_total + 2);
    }
+   if (part_cap < (size_t)part_total + 2) {
+      cudaFree(d_part);
+      d_part = nullptr;
+      CU(cudaMalloc(&d_part, ((size_t)part_total + 2) * 8));
+      part_cap = (size_t)part_total + 2;
+   }
+   double* d_xa = d_xw + xw_cap / 2;
    CU(cudaEventRecord(ev0, st));
    const int nb = (n + 255) / 256;
    for (int j = 0; j < nrhs; ++j) {
@@ -1254,19 +1144,39 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
       if (n > 0) { k_permute_in<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, n); ++nlaunch; }
       const bool fwd = (job == 0 || job == 1), bwd = (job == 0 || job == 3 || job == 4);
       const bool diag = !posdef && (job == 0 || job == 2 || job == 4);
-      // posdef: LL^T semantics, L_chol = L sqrt(D).  A full solve needs D once; we fold sqrt(D^-1)
-      // into each of the two sweeps so that partial solves match SSIDS's posdef jobs.
+      // posdef: LL^T semantics with L_chol = L sqrt(D); sqrt(D^-1) is folded into each sweep so
+      // that the partial solves match SSIDS's posdef jobs
       if (fwd)
          for (int l = 0; l < P->nlevels; ++l) {
-            int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
-            k_solve_fwd<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xw + xw_cap / 2, d_xp, s0, posdef ? 1 : 0);
+            const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
+            k_fwd_gather<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xa, d_xp, s0);
+            ++nlaunch;
+            for (int sp = 0; sp < lvl_steps[l]; ++sp) {
+               const int na = lvl_nact[l][sp];
+               if (na == 0) break;
+               k_fwd_tri<<<na, 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, sp);
+               const int rows = lvl_actm[l][sp] - sp * KB - 1;
+               if (rows > 0) { k_fwd_upd<<<dim3(na, (rows + RC - 1) / RC), 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, sp); ++nlaunch; }
+               ++nlaunch;
+            }
+            k_fwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xw, d_xp, s0, posdef ? 1 : 0);
             ++nlaunch;
          }
       if (diag && !bwd && nn > 0) { k_solve_diag<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, d_xp, nn); ++nlaunch; }
       if (bwd)
          for (int l = P->nlevels - 1; l >= 0; --l) {
-            int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
-            k_solve_bwd<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_rlist, d_xw_off, d_xw, d_xp, s0, diag ? 1 : 0, posdef ? 1 : 0);
+            const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
+            k_bwd_gather<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_rlist, d_xw_off, d_xw, d_xp, s0, diag ? 1 : 0, posdef ? 1 : 0);
+            ++nlaunch;
+            for (int sp = lvl_steps[l] - 1; sp >= 0; --sp) {
+               const int na = lvl_nact[l][sp];
+               if (na == 0) continue;
+               const int rows = lvl_actm[l][sp] - sp * KB - 1;
+               if (rows > 0) { k_bwd_dots<<<dim3(na, (rows + RD - 1) / RD), 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, sp); ++nlaunch; }
+               k_bwd_tri<<<na, 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, sp);
+               ++nlaunch;
+            }
+            k_bwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xw, d_xp, s0);
             ++nlaunch;
          }
       if (n > 0) { k_permute_out<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, n); ++nlaunch; }

@@ -29,8 +29,7 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
    const bool new_outer = mode & 1, finish_only = mode & 2;
    __shared__ double sa[NB * LDS], sld[NB * LDS], s0[NB * LDS], sinv[NB * LDS];
    __shared__ double sd[2 * NB + 2];
-   __shared__ double sbest[8];
-   __shared__ int skey[8];
+   __shared__ unsigned long long skey[8];
    __shared__ int sptype[NB], slperm[NB];
 
    if (f.flag < 0) return;
@@ -74,12 +73,17 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
 
    for (int i = tid; i < NB * LDS; i += 256) { sa[i] = 0.0; sld[i] = 0.0; sinv[i] = 0.0; }
    __syncthreads();
-   for (int i = tid; i < NB * NB; i += 256) {
-      int r = i & 31, c = i >> 5;
-      if (r >= c && r < w) {
-         double v = f.L[(size_t)(done + c) * f.ldl + done + r];
-         sa[r + c * LDS] = v;
-         sa[c + r * LDS] = v;
+   {
+      double v4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+         int i = tid + q * 256, r = i & 31, c = i >> 5;
+         v4[q] = (r >= c && r < w) ? f.L[(size_t)(done + c) * f.ldl + done + r] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+         int i = tid + q * 256, r = i & 31, c = i >> 5;
+         if (r >= c && r < w) { sa[r + c * LDS] = v4[q]; sa[c + r * LDS] = v4[q]; }
       }
    }
    if (tid < NB) { slperm[tid] = tid; sptype[tid] = 0; sinv[tid + tid * LDS] = 1.0; }
@@ -97,35 +101,39 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
          a11 = sa[p + p * LDS];
          if (!(a11 > 0.0)) { err = SSIDS_ERROR_NOT_POS_DEF; break; }
       } else {
-         double best = -1.0;
-         int key = 1 << 30;
+         // argmax |a(r,c)| over the remaining lower triangle with one 64-bit integer key per
+         // candidate: the bit pattern of |v| (monotone for non-negative doubles) with its low 10
+         // bits replaced by 1023 - (c*32 + r), so that ties go to the smallest column, then row
+         unsigned long long key = 0ull;
          if (lane >= p && lane < w) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                int c = c0 + j;
                if (c >= p && c <= lane) {
-                  double v = fabs(sa[lane + c * LDS]);
-                  if (v > best) { best = v; key = c * 64 + lane; }
+                  unsigned long long kk = ((unsigned long long)__double_as_longlong(fabs(sa[lane + c * LDS])) & ~0x3FFull) |
+                                          (unsigned long long)(1023 - (c * 32 + lane));
+                  key = kk > key ? kk : key;
                }
             }
          }
-#pragma unroll
-         for (int off = 16; off > 0; off >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, best, off);
-            int ok = __shfl_xor_sync(0xffffffffu, key, off);
-            if (ov > best || (ov == best && ok < key)) { best = ov; key = ok; }
+         {
+            unsigned hi = (unsigned)(key >> 32);
+            unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+            unsigned lo = (hi == mhi) ? (unsigned)key : 0u;
+            unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+            key = ((unsigned long long)mhi << 32) | mlo;
          }
-         if (lane == 0) { sbest[grp] = best; skey[grp] = key; }
+         if (lane == 0) skey[grp] = key;
          __syncthreads();
-         best = sbest[0]; key = skey[0];
+         key = skey[0];
 #pragma unroll
-         for (int g = 1; g < 8; ++g) {
-            double ov = sbest[g];
-            int ok = skey[g];
-            if (ov > best || (ov == best && ok < key)) { best = ov; key = ok; }
+         for (int g = 1; g < 8; ++g) { unsigned long long ok = skey[g]; key = ok > key ? ok : key; }
+         const double best = __longlong_as_double((long long)(key & ~0x3FFull));
+         {
+            int idx = 1023 - (int)(key & 0x3FFull);
+            t = idx & 31;
+            mm = idx >> 5;
          }
-         t = key & 63;
-         mm = key >> 6;
          if (best < prm.small_) {
             if (!prm.action) { err = SSIDS_ERROR_SINGULAR; break; }
             __syncthreads();
@@ -297,14 +305,12 @@ __global__ void __launch_bounds__(128) k_apply(FrontDev* fr, const int* list, Pa
    if (r < m) {
       double a[NB], x[NB];
       const size_t ldl = f.ldl;
+      const double* Lr = f.L + r;
 #pragma unroll
-      for (int k = 0; k < NB; ++k) {
-         a[k] = 0.0;
-         if (k < w) {
-            a[k] = f.L[(size_t)(done + slperm[k]) * ldl + r];
-            f.Wo[(size_t)k * m + r] = a[k];
-         }
-      }
+      for (int k = 0; k < NB; ++k) a[k] = (k < w) ? Lr[(size_t)(done + slperm[k]) * ldl] : 0.0;
+      double* Wor = f.Wo + r;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) if (k < w) Wor[(size_t)k * m] = a[k];
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
          double s = 0.0;
@@ -313,8 +319,10 @@ __global__ void __launch_bounds__(128) k_apply(FrontDev* fr, const int* list, Pa
          x[k] = s;
       }
       const int kofs = done - f.jstart;
+      double lv[NB];
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
+         lv[k] = 0.0;
          if (k < w) {
             int pt = sptype[k];
             double l;
@@ -327,11 +335,14 @@ __global__ void __launch_bounds__(128) k_apply(FrontDev* fr, const int* list, Pa
             } else {
                l = sdk[2 * k - 1] * x[(k - 1) & (NB - 1)] + sdk[2 * k + 1] * x[k];
             }
-            f.L[(size_t)(done + k) * ldl + r] = l;
-            f.Wld[(size_t)(kofs + k) * m + r] = x[k];
+            lv[k] = l;
             if (!prm.posdef && (!(fabs(l) <= prm.lim)) && k < myfail) myfail = k;
          }
       }
+      double* Lw = f.L + (size_t)done * ldl + r;
+      double* Wr = f.Wld + (size_t)kofs * m + r;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) if (k < w) { Lw[(size_t)k * ldl] = lv[k]; Wr[(size_t)k * m] = x[k]; }
    }
 #pragma unroll
    for (int off = 16; off > 0; off >>= 1) myfail = min(myfail, __shfl_xor_sync(0xffffffffu, myfail, off));
@@ -439,10 +450,6 @@ __global__ void __launch_bounds__(256, 1) k_update(FrontDev* fr, const int* list
       const int rbase = cbeg + ti * TM, cbase = cbeg + tj * TN;
       if (rbase + TM - 1 < cbase) continue;   // tile entirely above the diagonal
       double acc[4][8][2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-         for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
       const int nchunk = (kc + BK - 1) / BK;
       // stage loader: 256 threads move BK x 128 doubles of A and of B (16 + 16 cp.async each)
       auto load_stage = [&](int chunk, int buf) {
@@ -462,6 +469,22 @@ __global__ void __launch_bounds__(256, 1) k_update(FrontDev* fr, const int* list
       };
       __syncthreads();   // previous tile's smem reads are done
       load_stage(0, 0);
+      // accumulators start as the C tile (one batch of independent loads, overlapped with the
+      // first stage); the product is subtracted by feeding -B to the MMA
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+         for (int h = 0; h < 2; ++h) {
+            const int c = cbase + wc * 64 + j * 8 + 2 * t4 + h;
+            const bool cv = c < cend;
+            const double* colp = (c < f.n) ? (f.L + (size_t)c * ldl) : (f.C + (size_t)(c - f.n) * f.ldc - f.n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+               const int r = rbase + wr * 32 + i * 8 + g;
+               acc[i][j][h] = (cv && r < m && r >= c) ? colp[r] : 0.0;
+            }
+         }
+      }
       for (int ch = 0; ch < nchunk; ++ch) {
          const int buf = ch & 1;
          if (ch + 1 < nchunk) { load_stage(ch + 1, buf ^ 1); cp_async_wait<1>(); }
@@ -475,7 +498,7 @@ __global__ void __launch_bounds__(256, 1) k_update(FrontDev* fr, const int* list
 #pragma unroll
             for (int i = 0; i < 4; ++i) af[i] = as[(ks + t4) * LDT + i * 8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bf[j] = bs[(ks + t4) * LDT + j * 8];
+            for (int j = 0; j < 8; ++j) bf[j] = -bs[(ks + t4) * LDT + j * 8];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -483,7 +506,7 @@ __global__ void __launch_bounds__(256, 1) k_update(FrontDev* fr, const int* list
          }
          __syncthreads();
       }
-      // epilogue: C -= acc on the lower triangle
+      // epilogue: store only
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -494,7 +517,7 @@ __global__ void __launch_bounds__(256, 1) k_update(FrontDev* fr, const int* list
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                const int r = rbase + wr * 32 + i * 8 + g;
-               if (r < m && r >= c) colp[r] -= acc[i][j][h];
+               if (r < m && r >= c) colp[r] = acc[i][j][h];
             }
          }
       }
