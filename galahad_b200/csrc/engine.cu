@@ -179,7 +179,7 @@ __device__ void block_sym_swap(const FrontDev& f, int a, int b) {
 }
 
 #include "factor_kernels.cuh"
-constexpr int UPD_SMEM = 4 * BK * LDT * (int)sizeof(double);
+constexpr int UPD_SMEM = 2 * BK * (LDA + LDB) * (int)sizeof(double);
 
 // ------------------------------------------------------------------------------------------
 // TPP finish (ldlt_tpp.cxx:166-270), one CTA per front, right-looking on the whole trailing
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) k_tpp(FrontDev* fr, const int* list, Para
    const int n = f.n, m = f.m;
    const size_t ldl = f.ldl;
    double* l1 = f.Wld;
-   double* l2 = f.Wld + m;
+   double* l2 = f.Wld + f.ldl;
    while (ne < n) {
       // zero column at ne?
       {
@@ -594,7 +594,7 @@ Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
          int64_t ldl = align_up(st.nrow, 2), cm = st.nrow - st.ncol;
          P->est_factor_doubles += ldl * st.ncol + 32;
          c += align_up(cm, 2) * cm + 32;
-         ws += (int64_t)st.nrow * (NBO + NB) + 4 * NB * NB + 2 * NB + 2 + 3 * NB + 128;
+         ws += (int64_t)(st.nrow + 1) * (NBO + NB) + 4 * NB * NB + 2 * NB + 2 + 3 * NB + 128;
       }
       P->est_c_doubles[l & 1] = std::max(P->est_c_doubles[l & 1], c);
       P->est_ws_doubles = std::max(P->est_ws_doubles, ws);
@@ -773,7 +773,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          totC += align_up((size_t)f.ldc * (f.m - f.n), 32);
          totD += align_up(2 * (size_t)f.n + 2, 32);
          totP += 2 * align_up((size_t)f.n + 1, 32);
-         totW += align_up((size_t)f.m * (NBO + NB) + 4 * NB * NB + 2 * NB + 2, 32) + 128;
+         totW += align_up((size_t)f.ldl * (NBO + NB) + 4 * NB * NB + 2 * NB + 2, 32) + 128;
          maxfront = std::max(maxfront, f.m);
       }
       double* Lb = (double*)fac.alloc(totL * 8);
@@ -791,9 +791,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             f.D = Db + oD; oD += align_up(2 * (size_t)f.n + 2, 32);
             f.perm = Pb + oP; f.orig = f.perm + align_up((size_t)f.n + 1, 32); oP += 2 * align_up((size_t)f.n + 1, 32);
             double* wp = Wb + oW;
-            oW += align_up((size_t)f.m * (NBO + NB) + 4 * NB * NB + 2 * NB + 2, 32) + 128;
-            f.Wld = wp; f.Wo = wp + (size_t)f.m * NBO;
-            f.dbuf = wp + (size_t)f.m * (NBO + NB);
+            oW += align_up((size_t)f.ldl * (NBO + NB) + 4 * NB * NB + 2 * NB + 2, 32) + 128;
+            f.Wld = wp; f.Wo = wp + (size_t)f.ldl * NBO;
+            f.dbuf = wp + (size_t)f.ldl * (NBO + NB);
             f.ibuf = (int*)(f.dbuf + 4 * NB * NB + 2 * NB + 2);
          }
       }
@@ -903,7 +903,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             const int* lst = d_list + i0;
             const int ncolchunks = (maxn + 127) / 128;
             const int ycommit = 1 + ncolchunks + (maxm + 127) / 128;
-            const int yapply = std::max(1, (maxm + 127) / 128);
+            const int yapply = std::max(1, (maxm + AR - 1) / AR);
             const int nouter = (maxn + NBO - 1) / NBO;
             for (int ob = 0; ob < nouter; ++ob) {
                int na = 0;   // active prefix: fronts that still have an outer block number ob
@@ -913,15 +913,15 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                for (int q = 0; q < na; ++q) maxw_outer = std::max(maxw_outer, std::min(NBO, hfr[order[i0 + q]].n - ob * NBO));
                const int ninner = (maxw_outer + NB - 1) / NB;
                for (int j = 0; j < ninner; ++j) {
-                  k_diag<<<na, 256, 0, st>>>(d_fr, lst, prm, j == 0 ? 1 : 0);
-                  k_apply<<<dim3(na, yapply), 128, 0, st>>>(d_fr, lst, prm);
+                  k_diag<<<na, 128, 0, st>>>(d_fr, lst, prm, j == 0 ? 1 : 0);
+                  k_apply<<<dim3(na, yapply), 256, 0, st>>>(d_fr, lst, prm);
                   k_commit<<<dim3(na, ycommit), 128, 0, st>>>(d_fr, lst, ncolchunks);
                   launches += 3;
                   // inner update: columns of the outer block behind this panel
                   const int colsleft = maxw_outer - (j + 1) * NB;
                   if (colsleft > 0 || !posdef) {
                      int ntr = (maxm + TM - 1) / TM;
-                     int ygrid = std::max(1, std::min(ntr, (148 * 2) / std::max(na, 1)));
+                     int ygrid = std::max(1, std::min(2 * ntr, std::max(1, 296 / std::max(na, 1))));
                      if (o.profile) {
                         for (int q = 0; q < na; ++q) {
                            const FrontDev& ff = hfr[order[i0 + q]];
@@ -941,7 +941,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   int rem = maxm - ob * NBO;
                   int nt = std::max(1, (rem + TM - 1) / TM);
                   int64_t tiles = (int64_t)nt * (nt + 1) / 2;
-                  int ygrid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, std::max<int64_t>(1, (148 * 4) / std::max(na, 1))));
+                  int ygrid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * tiles, std::max<int64_t>(1, 296 / std::max(na, 1))));
                   if (o.profile) {
                      for (int q = 0; q < na; ++q) {
                         const FrontDev& ff = hfr[order[i0 + q]];
@@ -955,7 +955,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   ++launches;
                }
             }
-            k_diag<<<i1 - i0, 256, 0, st>>>(d_fr, lst, prm, 2);
+            k_diag<<<i1 - i0, 128, 0, st>>>(d_fr, lst, prm, 2);
             ++launches;
             i0 = i1;
          }
@@ -989,14 +989,14 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * nt, cudaMemcpyHostToDevice, st));
          const int ncolchunks = (maxn + 127) / 128;
          for (int j = 0; j < NBO / NB; ++j) {
-            k_diag<<<nt, 256, 0, st>>>(d_fr, d_list, prm, j == 0 ? 1 : 0);
-            k_apply<<<dim3(nt, std::max(1, (maxm + 127) / 128)), 128, 0, st>>>(d_fr, d_list, prm);
+            k_diag<<<nt, 128, 0, st>>>(d_fr, d_list, prm, j == 0 ? 1 : 0);
+            k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, 0, st>>>(d_fr, d_list, prm);
             k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 127) / 128), 128, 0, st>>>(d_fr, d_list, ncolchunks);
             k_update<<<dim3(nt, std::max(1, std::min((maxm + TM - 1) / TM, 64))), 256, UPD_SMEM, st>>>(d_fr, d_list, 0);
             launches += 4;
          }
          k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 1);
-         k_diag<<<nt, 256, 0, st>>>(d_fr, d_list, prm, 2);
+         k_diag<<<nt, 128, 0, st>>>(d_fr, d_list, prm, 2);
          launches += 2;
          if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
          if (flag < 0) break;

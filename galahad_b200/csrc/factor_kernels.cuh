@@ -16,20 +16,21 @@
 #pragma once
 
 constexpr int TM = 128;          // update tile rows
-constexpr int TN = 128;          // update tile cols
+constexpr int TN = 64;           // update tile cols
 constexpr int BK = 32;           // k chunk staged in shared memory
-constexpr int LDT = TM + 4;      // padded smem leading dimension: t4*LDT + g distinct mod 16 per half warp
+constexpr int LDA = TM + 4;      // padded smem leading dimensions: t4*LD + g distinct mod 16 per half warp
+constexpr int LDB = TN + 4;
 
 // ------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Params prm, int mode) {
+__global__ void __launch_bounds__(128) k_diag(FrontDev* fr, const int* list, Params prm, int mode) {
    FrontDev& f = fr[list[blockIdx.x]];
    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
    const bool new_outer = mode & 1, finish_only = mode & 2;
    __shared__ double sa[NB * LDS], sld[NB * LDS], s0[NB * LDS], sinv[NB * LDS];
    __shared__ double sd[2 * NB + 2];
-   __shared__ unsigned long long skey[8];
+   __shared__ unsigned long long skey[4];
    __shared__ int sptype[NB], slperm[NB];
 
    if (f.flag < 0) return;
@@ -71,29 +72,28 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
    }
    if (w == 0) return;
 
-   for (int i = tid; i < NB * LDS; i += 256) { sa[i] = 0.0; sld[i] = 0.0; sinv[i] = 0.0; }
-   __syncthreads();
    {
-      double v4[4];
+      // block load: 8 independent global loads per thread, then shared stores (full symmetric)
+      double v8[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-         int i = tid + q * 256, r = i & 31, c = i >> 5;
-         v4[q] = (r >= c && r < w) ? f.L[(size_t)(done + c) * f.ldl + done + r] : 0.0;
+      for (int q = 0; q < 8; ++q) {
+         int i = tid + q * 128, r = i & 31, c = i >> 5;
+         v8[q] = (r >= c && r < w) ? f.L[(size_t)(done + c) * f.ldl + done + r] : 0.0;
       }
+      for (int i = tid; i < NB * LDS; i += 128) { sld[i] = 0.0; sinv[i] = 0.0; }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-         int i = tid + q * 256, r = i & 31, c = i >> 5;
-         if (r >= c && r < w) { sa[r + c * LDS] = v4[q]; sa[c + r * LDS] = v4[q]; }
+      for (int q = 0; q < 8; ++q) {
+         int i = tid + q * 128, r = i & 31, c = i >> 5;
+         if (r >= c) { sa[r + c * LDS] = v8[q]; sa[c + r * LDS] = v8[q]; s0[r + c * LDS] = v8[q]; s0[c + r * LDS] = v8[q]; }
       }
    }
-   if (tid < NB) { slperm[tid] = tid; sptype[tid] = 0; sinv[tid + tid * LDS] = 1.0; }
-   for (int i = tid; i < 2 * NB + 2; i += 256) sd[i] = 0.0;
    __syncthreads();
-   for (int i = tid; i < NB * LDS; i += 256) s0[i] = sa[i];
+   if (tid < NB) { slperm[tid] = tid; sptype[tid] = 0; sinv[tid + tid * LDS] = 1.0; }
+   for (int i = tid; i < 2 * NB + 2; i += 128) sd[i] = 0.0;
    __syncthreads();
 
    int err = 0;
-   const int c0 = grp * 4;      // this thread's 4 columns; its row is `lane`
+   const int c0 = grp * 8;      // this thread's 8 columns; its row is `lane`
    for (int p = 0; p < w;) {
       int t = p, mm = p, pivsiz = 1;
       double a11 = 0, a21 = 0, a22 = 0, detscale = 0, detpiv = 0;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
          unsigned long long key = 0ull;
          if (lane >= p && lane < w) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                int c = c0 + j;
                if (c >= p && c <= lane) {
                   unsigned long long kk = ((unsigned long long)__double_as_longlong(fabs(sa[lane + c * LDS])) & ~0x3FFull) |
@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
             key = ((unsigned long long)mhi << 32) | mlo;
          }
          if (lane == 0) skey[grp] = key;
-         __syncthreads();
+         __syncthreads();                                             // B1
          key = skey[0];
 #pragma unroll
-         for (int g = 1; g < 8; ++g) { unsigned long long ok = skey[g]; key = ok > key ? ok : key; }
+         for (int g = 1; g < 4; ++g) { unsigned long long ok = skey[g]; key = ok > key ? ok : key; }
          const double best = __longlong_as_double((long long)(key & ~0x3FFull));
          {
             int idx = 1023 - (int)(key & 0x3FFull);
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
          if (best < prm.small_) {
             if (!prm.action) { err = SSIDS_ERROR_SINGULAR; break; }
             __syncthreads();
-            for (int i = tid; i < NB * NB; i += 256) {
+            for (int i = tid; i < NB * NB; i += 128) {
                int r = i & 31, c = i >> 5;
                if (r >= p && c >= p && r < w && c < w) { sa[r + c * LDS] = 0.0; }
                if (r >= c && c >= p && r < w) sld[r + c * LDS] = 0.0;
@@ -164,12 +164,12 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
             }
          }
       }
-      __syncthreads();
       // symmetric swaps bringing the pivot(s) to p (and p+1); sinv follows (M' = P M P^T)
       for (int i = 0; i < pivsiz; ++i) {
          const int dst = p + i;
          const int src = (pivsiz == 1) ? t : (i == 0 ? mm : t);
          if (src != dst) {
+            __syncthreads();     // every thread is done reading the pivot entries
             if (tid < NB) {
                double s = sa[dst + tid * LDS]; sa[dst + tid * LDS] = sa[src + tid * LDS]; sa[src + tid * LDS] = s;
             } else if (tid < 2 * NB) {
@@ -193,23 +193,21 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
       }
       if (pivsiz == 1) {
          const double d11 = 1.0 / sa[p + p * LDS];
-         __syncthreads();
          if (tid > p && tid < w) {
             double ldr = sa[tid + p * LDS];
             sld[tid + p * LDS] = ldr;
             sa[tid + p * LDS] = ldr * d11;
          }
-         __syncthreads();
+         __syncthreads();                                             // B2
          if (lane > p && lane < w) {
             const double lr = sa[lane + p * LDS];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                int c = c0 + j;
                if (c > p) { if (c < w) sa[lane + c * LDS] -= lr * sld[c + p * LDS]; }
                else sinv[lane + c * LDS] -= lr * sinv[p + c * LDS];
             }
          }
-         __syncthreads();
          if (tid == 0) { sd[2 * p] = d11; sd[2 * p + 1] = 0.0; sptype[p] = 0; sa[p + p * LDS] = 1.0; }
          if (tid > p && tid < w) sa[p + tid * LDS] = 0.0;
          p += 1;
@@ -223,17 +221,16 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
             sa[tid + p * LDS] = d11 * w1 + d21 * w2;
             sa[tid + (p + 1) * LDS] = d21 * w1 + d22 * w2;
          }
-         __syncthreads();
+         __syncthreads();                                             // B2
          if (lane > p + 1 && lane < w) {
             const double l1 = sa[lane + p * LDS], l2 = sa[lane + (p + 1) * LDS];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                int c = c0 + j;
                if (c > p + 1) { if (c < w) sa[lane + c * LDS] -= l1 * sld[c + p * LDS] + l2 * sld[c + (p + 1) * LDS]; }
                else sinv[lane + c * LDS] -= l1 * sinv[p + c * LDS] + l2 * sinv[p + 1 + c * LDS];
             }
          }
-         __syncthreads();
          if (tid == 0) {
             sd[2 * p] = d11; sd[2 * p + 1] = d21; sd[2 * p + 2] = DINF; sd[2 * p + 3] = d22;
             sptype[p] = 1; sptype[p + 1] = 2;
@@ -244,7 +241,7 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
          if (tid > p + 1 && tid < w) { sa[p + tid * LDS] = 0.0; sa[p + 1 + tid * LDS] = 0.0; }
          p += 2;
       }
-      __syncthreads();
+      __syncthreads();                                                // B3
    }
    if (err) {
       if (tid == 0) { f.flag = err; f.w = 0; }
@@ -258,7 +255,7 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
    double* Linv = f.dbuf + 3 * NB * NB;      // row-major: Linv[k*NB + i] = (L11^{-1})(k,i)
    double* dk = f.dbuf + 4 * NB * NB;
    const int kofs = done - jstart;
-   for (int idx = tid; idx < NB * NB; idx += 256) {
+   for (int idx = tid; idx < NB * NB; idx += 128) {
       const int i = idx & 31, k = idx >> 5;
       if (i < w && k < w) {
          double lv = i > k ? sa[i + k * LDS] : (i == k ? 1.0 : 0.0);
@@ -266,15 +263,14 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
          L11[i + k * NB] = lv;
          LD11[i + k * NB] = ldv;
          A0p[i + k * NB] = s0[slperm[i] + slperm[k] * LDS];
-         f.Wld[(size_t)(kofs + k) * f.m + done + i] = ldv;
+         f.Wld[(size_t)(kofs + k) * f.ldl + done + i] = ldv;
       }
-      // transpose while writing: thread idx -> (k = idx&31 row of Linv, i = idx>>5)
       {
          const int kk = idx & 31, ii = idx >> 5;
          Linv[kk * NB + ii] = (kk < w && ii <= kk) ? sinv[kk + ii * LDS] : 0.0;
       }
    }
-   for (int i = tid; i < 2 * NB + 2; i += 256) dk[i] = sd[i];
+   for (int i = tid; i < 2 * NB + 2; i += 128) dk[i] = sd[i];
    if (tid < NB) { f.ibuf[tid] = slperm[tid]; f.ibuf[NB + tid] = sptype[tid]; }
    if (tid == 0) {
       int permuted = 0;
@@ -286,67 +282,96 @@ __global__ void __launch_bounds__(256) k_diag(FrontDev* fr, const int* list, Par
 // ------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_apply(FrontDev* fr, const int* list, Params prm) {
+constexpr int AR = 64;    // rows per CTA in k_apply
+
+__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, Params prm) {
    FrontDev& f = fr[list[blockIdx.x]];
    const int w = f.w;
    if (w == 0 || f.flag < 0) return;
    const int done = f.done, m = f.m;
-   const int r0 = done + w + blockIdx.y * 128;
+   const int r0 = done + w + blockIdx.y * AR;
    if (r0 >= m) return;
    __shared__ double sinv[NB * NB];
    __shared__ double sdk[2 * NB + 2];
    __shared__ int slperm[NB], sptype[NB];
-   for (int i = threadIdx.x; i < NB * NB; i += 128) sinv[i] = f.dbuf[3 * NB * NB + i];
-   for (int i = threadIdx.x; i < 2 * NB + 2; i += 128) sdk[i] = f.dbuf[4 * NB * NB + i];
-   if (threadIdx.x < NB) { slperm[threadIdx.x] = f.ibuf[threadIdx.x]; sptype[threadIdx.x] = f.ibuf[NB + threadIdx.x]; }
+   __shared__ double at[AR][NB + 1], xt[AR][NB + 1];
+   const int tid = threadIdx.x;
+   for (int i = tid; i < NB * NB; i += 256) sinv[i] = f.dbuf[3 * NB * NB + i];
+   for (int i = tid; i < 2 * NB + 2; i += 256) sdk[i] = f.dbuf[4 * NB * NB + i];
+   if (tid < NB) { slperm[tid] = f.ibuf[tid]; sptype[tid] = f.ibuf[NB + tid]; }
    __syncthreads();
-   const int r = r0 + threadIdx.x;
-   int myfail = w;
-   if (r < m) {
-      double a[NB], x[NB];
-      const size_t ldl = f.ldl;
-      const double* Lr = f.L + r;
+   const int rl = tid & (AR - 1), kq = tid >> 6;      // row within the tile, group of 8 columns
+   const int r = r0 + rl;
+   const bool rv = r < m;
+   const size_t ldl = f.ldl;
+   const int kofs = done - f.jstart;
+   {
+      double a8[8];
 #pragma unroll
-      for (int k = 0; k < NB; ++k) a[k] = (k < w) ? Lr[(size_t)(done + slperm[k]) * ldl] : 0.0;
-      double* Wor = f.Wo + r;
-#pragma unroll
-      for (int k = 0; k < NB; ++k) if (k < w) Wor[(size_t)k * m] = a[k];
-#pragma unroll
-      for (int k = 0; k < NB; ++k) {
-         double s = 0.0;
-#pragma unroll
-         for (int i = 0; i <= k; ++i) s += a[i] * sinv[k * NB + i];
-         x[k] = s;
+      for (int j = 0; j < 8; ++j) {
+         const int k = kq * 8 + j;
+         a8[j] = (rv && k < w) ? f.L[(size_t)(done + slperm[k]) * ldl + r] : 0.0;
       }
-      const int kofs = done - f.jstart;
-      double lv[NB];
 #pragma unroll
-      for (int k = 0; k < NB; ++k) {
-         lv[k] = 0.0;
+      for (int j = 0; j < 8; ++j) {
+         const int k = kq * 8 + j;
+         at[rl][k] = a8[j];
+         if (rv && k < w) f.Wo[(size_t)k * ldl + r] = a8[j];
+      }
+   }
+   __syncthreads();
+   {
+      double x8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x8[j] = 0.0;
+      const int kmax = kq * 8 + 7;
+      for (int i = 0; i <= kmax; ++i) {
+         const double ai = at[rl][i];
+#pragma unroll
+         for (int j = 0; j < 8; ++j) x8[j] += ai * sinv[(kq * 8 + j) * NB + i];   // Linv(k,i) = 0 for i > k
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xt[rl][kq * 8 + j] = x8[j];
+   }
+   __syncthreads();
+   int myfail = w;
+   {
+      double l8[8], x8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+         const int k = kq * 8 + j;
+         l8[j] = 0.0;
+         x8[j] = xt[rl][k];
          if (k < w) {
-            int pt = sptype[k];
+            const int pt = sptype[k];
             double l;
             if (pt == 0) {
-               double d11 = sdk[2 * k];
-               if (d11 == 0.0) l = (fabs(x[k]) < prm.small_) ? 0.0 : DINF * x[k];
-               else l = x[k] * d11;
+               const double d11 = sdk[2 * k];
+               if (d11 == 0.0) l = (fabs(x8[j]) < prm.small_) ? 0.0 : DINF * x8[j];
+               else l = x8[j] * d11;
             } else if (pt == 1) {
-               l = sdk[2 * k] * x[k] + sdk[2 * k + 1] * x[(k + 1) & (NB - 1)];
+               l = sdk[2 * k] * x8[j] + sdk[2 * k + 1] * xt[rl][(k + 1) & (NB - 1)];
             } else {
-               l = sdk[2 * k - 1] * x[(k - 1) & (NB - 1)] + sdk[2 * k + 1] * x[k];
+               l = sdk[2 * k - 1] * xt[rl][(k - 1) & (NB - 1)] + sdk[2 * k + 1] * x8[j];
             }
-            lv[k] = l;
-            if (!prm.posdef && (!(fabs(l) <= prm.lim)) && k < myfail) myfail = k;
+            l8[j] = l;
+            if (rv && !prm.posdef && (!(fabs(l) <= prm.lim)) && k < myfail) myfail = k;
          }
       }
-      double* Lw = f.L + (size_t)done * ldl + r;
-      double* Wr = f.Wld + (size_t)kofs * m + r;
+      if (rv) {
 #pragma unroll
-      for (int k = 0; k < NB; ++k) if (k < w) { Lw[(size_t)k * ldl] = lv[k]; Wr[(size_t)k * m] = x[k]; }
+         for (int j = 0; j < 8; ++j) {
+            const int k = kq * 8 + j;
+            if (k < w) {
+               f.L[(size_t)(done + k) * ldl + r] = l8[j];
+               f.Wld[(size_t)(kofs + k) * ldl + r] = x8[j];
+            }
+         }
+      }
    }
 #pragma unroll
    for (int off = 16; off > 0; off >>= 1) myfail = min(myfail, __shfl_xor_sync(0xffffffffu, myfail, off));
-   if ((threadIdx.x & 31) == 0 && myfail < w) atomicMin(&f.fail, myfail);
+   if ((tid & 31) == 0 && myfail < w) atomicMin(&f.fail, myfail);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -395,7 +420,7 @@ __global__ void __launch_bounds__(128) k_commit(FrontDev* fr, const int* list, i
       if (nelim == w) return;
       const int r = done + w + (y - 1 - ncolchunks) * 128 + threadIdx.x;
       if (r >= m) return;
-      for (int k = nelim; k < w; ++k) f.L[(size_t)(done + k) * ldl + r] = f.Wo[(size_t)k * m + r];
+      for (int k = nelim; k < w; ++k) f.L[(size_t)(done + k) * ldl + r] = f.Wo[(size_t)k * ldl + r];
    }
 }
 
@@ -419,7 +444,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-__global__ void __launch_bounds__(256, 1) k_update(FrontDev* fr, const int* list, int mode) {
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
+   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+
+// CTA = 256 threads = 8 warps (4 x 2); CTA tile 128 x 64; warp tile 32 x 32 = 4 x 4 m8n8k4 MMAs;
+// two CTAs per SM.  ncu (profiles/r1_notes.md) showed the kernel bound by per-warp instruction
+// issue around the MMAs, so interior tiles take a path without bounds predicates and with
+// strength-reduced addresses, and tile coordinates advance incrementally.
+__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int mode) {
    const FrontDev& f = fr[list[blockIdx.x]];
    const int w = f.w;
    if (f.flag < 0) return;
@@ -435,91 +469,162 @@ __global__ void __launch_bounds__(256, 1) k_update(FrontDev* fr, const int* list
    const int kofs = k0 - f.jstart;
    const int ntr = (m - cbeg + TM - 1) / TM;
    const int ntc = (cend - cbeg + TN - 1) / TN;
-   const int ntiles = ntr * ntc;
    extern __shared__ double smem[];
-   double* As = smem;                       // [2][BK][LDT]
-   double* Bs = smem + 2 * BK * LDT;        // [2][BK][LDT]
+   double* As = smem;                       // [2][BK][LDA]
+   double* Bs = smem + 2 * BK * LDA;        // [2][BK][LDB]
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   const int wr = warp & 3, wc = warp >> 2;  // warp tile origin: rows wr*32, cols wc*64
+   const int wr = warp & 3, wc = warp >> 2;  // 4 x 2 warps; warp tile origin: rows wr*32, cols wc*32
    const int g = lane >> 2, t4 = lane & 3;
    const size_t ldl = f.ldl;
-   const double* Abase = f.L + (size_t)k0 * ldl;
-   const double* Bbase = f.Wld + (size_t)kofs * m;
-   for (int id = blockIdx.y; id < ntiles; id += gridDim.y) {
-      const int tj = id / ntr, ti = id % ntr;
+   const int fn = f.n, ldc = f.ldc;
+   double* const Lp = f.L;
+   double* const Cp = f.C;
+   const double* Abase = Lp + (size_t)k0 * ldl;
+   const double* Bbase = f.Wld + (size_t)kofs * ldl;
+   const bool vec16 = (cbeg & 1) == 0;      // 16-byte cp.async needs even row offsets (ldl is even)
+   const int nchunk = (kc + BK - 1) / BK;
+   // tile (ti,tj) touches the lower triangle iff tj <= 2*ti+1 (TM = 2*TN, shared origin cbeg);
+   // tiles are numbered row by row; a CTA walks its tiles incrementally
+   int ti = 0, tj = blockIdx.y;
+   for (;;) {
+      // normalise (ti,tj)
+      while (ti < ntr) { const int wd = min(ntc, 2 * ti + 2); if (tj < wd) break; tj -= wd; ++ti; }
+      if (ti >= ntr) break;
       const int rbase = cbeg + ti * TM, cbase = cbeg + tj * TN;
-      if (rbase + TM - 1 < cbase) continue;   // tile entirely above the diagonal
-      double acc[4][8][2];
-      const int nchunk = (kc + BK - 1) / BK;
-      // stage loader: 256 threads move BK x 128 doubles of A and of B (16 + 16 cp.async each)
+      const bool full = (rbase + TM <= m) && (cbase + TN <= cend) && vec16;
+      const bool below = cbase + TN - 1 <= rbase;     // tile entirely below the diagonal
+      double acc[4][4][2];
       auto load_stage = [&](int chunk, int buf) {
          const int kb = chunk * BK;
-         double* as = As + buf * BK * LDT;
-         double* bs = Bs + buf * BK * LDT;
+         double* as = As + buf * BK * LDA;
+         double* bs = Bs + buf * BK * LDB;
+         if (full && kb + BK <= kc) {
+            // thread -> (k row = q*4 + tid/64, piece (tid%64)*2) for A; (q*8 + tid/32, (tid%32)*2) for B
+            const double* pa = Abase + (size_t)(kb + (tid >> 6)) * ldl + rbase + (tid & 63) * 2;
+            double* sa_ = as + (tid >> 6) * LDA + (tid & 63) * 2;
+            const size_t sta = 4 * ldl;
 #pragma unroll
-         for (int q = 0; q < 16; ++q) {
-            const int e = q * 256 + tid;
-            const int kk = e >> 7, rr = e & 127;
-            const bool kv = kb + kk < kc;
-            const int ra = rbase + rr, cb = cbase + rr;
-            cp_async8(as + kk * LDT + rr, Abase + (size_t)(kb + kk) * ldl + ra, kv && ra < m);
-            cp_async8(bs + kk * LDT + rr, Bbase + (size_t)(kb + kk) * m + cb, kv && cb < cend);
+            for (int q = 0; q < 8; ++q) cp_async16(sa_ + q * 4 * LDA, pa + q * sta, 16);
+            const double* pb = Bbase + (size_t)(kb + (tid >> 5)) * ldl + cbase + (tid & 31) * 2;
+            double* sb_ = bs + (tid >> 5) * LDB + (tid & 31) * 2;
+            const size_t stb = 8 * ldl;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cp_async16(sb_ + q * 8 * LDB, pb + q * stb, 16);
+         } else if (vec16) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+               const int e = q * 256 + tid, kk = e >> 6, rr = (e & 63) * 2;
+               const int ra = rbase + rr;
+               const int nb = (kb + kk < kc) ? (ra + 1 < m ? 16 : (ra < m ? 8 : 0)) : 0;
+               cp_async16(as + kk * LDA + rr, nb ? Abase + (size_t)(kb + kk) * ldl + ra : Abase, nb);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+               const int e = q * 256 + tid, kk = e >> 5, rr = (e & 31) * 2;
+               const int cb = cbase + rr;
+               const int nb = (kb + kk < kc) ? (cb + 1 < cend ? 16 : (cb < cend ? 8 : 0)) : 0;
+               cp_async16(bs + kk * LDB + rr, nb ? Bbase + (size_t)(kb + kk) * ldl + cb : Bbase, nb);
+            }
+         } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+               const int e = q * 256 + tid, kk = e >> 7, rr = e & 127;
+               const int ra = rbase + rr;
+               const bool ok = kb + kk < kc && ra < m;
+               cp_async8(as + kk * LDA + rr, ok ? Abase + (size_t)(kb + kk) * ldl + ra : Abase, ok);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+               const int e = q * 256 + tid, kk = e >> 6, rr = e & 63;
+               const int cb = cbase + rr;
+               const bool ok = kb + kk < kc && cb < cend;
+               cp_async8(bs + kk * LDB + rr, ok ? Bbase + (size_t)(kb + kk) * ldl + cb : Bbase, ok);
+            }
          }
          cp_async_commit();
       };
       __syncthreads();   // previous tile's smem reads are done
       load_stage(0, 0);
-      // accumulators start as the C tile (one batch of independent loads, overlapped with the
-      // first stage); the product is subtracted by feeding -B to the MMA
+      // accumulators start as the C tile; the product is subtracted by feeding -B to the MMA
+      const int r0 = rbase + wr * 32 + g, c0 = cbase + wc * 32 + 2 * t4;
+      if (full && below) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+         for (int j = 0; j < 4; ++j)
 #pragma unroll
-         for (int h = 0; h < 2; ++h) {
-            const int c = cbase + wc * 64 + j * 8 + 2 * t4 + h;
-            const bool cv = c < cend;
-            const double* colp = (c < f.n) ? (f.L + (size_t)c * ldl) : (f.C + (size_t)(c - f.n) * f.ldc - f.n);
+            for (int h = 0; h < 2; ++h) {
+               const int c = c0 + j * 8 + h;
+               const double* colp = (c < fn) ? (Lp + (size_t)c * ldl + r0) : (Cp + (size_t)(c - fn) * ldc + (r0 - fn));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-               const int r = rbase + wr * 32 + i * 8 + g;
-               acc[i][j][h] = (cv && r < m && r >= c) ? colp[r] : 0.0;
+               for (int i = 0; i < 4; ++i) acc[i][j][h] = colp[i * 8];
             }
-         }
+      } else {
+#pragma unroll
+         for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+               const int c = c0 + j * 8 + h;
+               const bool cv = c < cend;
+               const double* colp = (c < fn) ? (Lp + (size_t)c * ldl) : (Cp + (size_t)(c - fn) * ldc - fn);
+#pragma unroll
+               for (int i = 0; i < 4; ++i) {
+                  const int r = r0 + i * 8;
+                  acc[i][j][h] = (cv && r < m && r >= c) ? colp[r] : 0.0;
+               }
+            }
       }
       for (int ch = 0; ch < nchunk; ++ch) {
          const int buf = ch & 1;
          if (ch + 1 < nchunk) { load_stage(ch + 1, buf ^ 1); cp_async_wait<1>(); }
          else cp_async_wait<0>();
          __syncthreads();
-         const double* as = As + buf * BK * LDT + wr * 32 + g;
-         const double* bs = Bs + buf * BK * LDT + wc * 64 + g;
+         const double* as = As + buf * BK * LDA + wr * 32 + g + t4 * LDA;
+         const double* bs = Bs + buf * BK * LDB + wc * 32 + g + t4 * LDB;
+         double af[2][4], bf[2][4];
+#pragma unroll
+         for (int i = 0; i < 4; ++i) { af[0][i] = as[i * 8]; bf[0][i] = bs[i * 8]; }
 #pragma unroll
          for (int ks = 0; ks < BK; ks += 4) {
-            double af[4], bf[8];
+            const int cur = (ks >> 2) & 1, nxt = cur ^ 1;
+            if (ks + 4 < BK) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = as[(ks + t4) * LDT + i * 8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bf[j] = -bs[(ks + t4) * LDT + j * 8];
+               for (int i = 0; i < 4; ++i) {
+                  af[nxt][i] = as[(ks + 4) * LDA + i * 8];
+                  bf[nxt][i] = bs[(ks + 4) * LDB + i * 8];
+               }
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-               for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+               for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], -bf[cur][j]);
          }
          __syncthreads();
       }
       // epilogue: store only
+      if (full && below) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+         for (int j = 0; j < 4; ++j)
 #pragma unroll
-         for (int h = 0; h < 2; ++h) {
-            const int c = cbase + wc * 64 + j * 8 + 2 * t4 + h;
-            if (c >= cend) continue;
-            double* colp = (c < f.n) ? (f.L + (size_t)c * ldl) : (f.C + (size_t)(c - f.n) * f.ldc - f.n);
+            for (int h = 0; h < 2; ++h) {
+               const int c = c0 + j * 8 + h;
+               double* colp = (c < fn) ? (Lp + (size_t)c * ldl + r0) : (Cp + (size_t)(c - fn) * ldc + (r0 - fn));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-               const int r = rbase + wr * 32 + i * 8 + g;
-               if (r < m && r >= c) colp[r] = acc[i][j][h];
+               for (int i = 0; i < 4; ++i) colp[i * 8] = acc[i][j][h];
             }
-         }
+      } else {
+#pragma unroll
+         for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+               const int c = c0 + j * 8 + h;
+               if (c >= cend) continue;
+               double* colp = (c < fn) ? (Lp + (size_t)c * ldl) : (Cp + (size_t)(c - fn) * ldc - fn);
+#pragma unroll
+               for (int i = 0; i < 4; ++i) {
+                  const int r = r0 + i * 8;
+                  if (r < m && r >= c) colp[r] = acc[i][j][h];
+               }
+            }
       }
+      tj += gridDim.y;
    }
 }
