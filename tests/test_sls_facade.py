@@ -1,0 +1,141 @@
+"""The SLS host interface for solver 'b200ldlt', exercised the way the reference exercises its own:
+src/sls/C/slst.c (three storage schemes, 1 RHS, iterative refinement, partial solves) and
+src/sls/slst.f90:29-56 (5x5 KATs, provided reverse order)."""
+import numpy as np
+import pytest
+
+from galahad_b200 import problems as P
+from galahad_b200.sls import SLS, coord_to_sorted_csr
+from util import golden
+
+EPS = np.finfo(float).eps
+K = golden("kat_sls.json")
+N = 5
+ROW = np.array(K["indef"]["row"]) - 1            # slst.c:23-30 holds the same data 0-based
+COL = np.array(K["indef"]["col"]) - 1
+PTR = np.array([0, 1, 3, 5, 6, 7])
+VAL = np.array(K["indef"]["val"], float)
+DENSE = np.array([2.0, 3.0, 0.0, 0.0, 4.0, 1.0, 0.0, 0.0, 5.0, 0.0, 0.0, 6.0, 0.0, 0.0, 1.0])
+RHS = np.array(K["indef"]["rhs"], float)
+SOL = np.array(K["indef"]["sol"], float)
+
+
+def test_unknown_solver_and_defaults():
+    s = SLS("sils")
+    assert s.status.value == -26                                   # GALAHAD_error_unknown_solver
+    s = SLS("B200LDLT")
+    c = s.control
+    assert s.status.value == 0
+    # sls.f90:129-357 defaults (+ ordering -1 for the ssids class, :887-892)
+    assert (c.pivot_control, c.node_amalgamation, c.relative_pivot_tolerance, c.max_iterative_refinements) == (1, 32, 0.01, 0)
+    assert c.absolute_pivot_tolerance == EPS and c.ordering == -1
+
+
+def test_coord_to_sorted_csr_counts_and_map():
+    # duplicates, an upper-triangle entry, an out-of-range entry; row 4 has no entry at all, which
+    # the reference does not count as a missing diagonal (the test sits in the size > 0 branch,
+    # sls.f90:8529-8547) although it still reserves the diagonal slot
+    row = np.array([1, 2, 2, 3, 1, 2, 9, 4, 3])
+    col = np.array([1, 1, 2, 3, 2, 1, 1, 3, 3])
+    m, p, cnt = coord_to_sorted_csr(4, row, col)
+    assert cnt == dict(dup=3, oor=1, upper=1, missing_diagonals=0)
+    # a row with off-diagonal entries only IS counted
+    m2, p2, cnt2 = coord_to_sorted_csr(3, np.array([2, 3, 3]), np.array([1, 1, 3]))
+    assert cnt2["missing_diagonals"] == 1 and p2.tolist() == [1, 4, 5, 6] and m2.tolist() == [2, 3, 5]
+    assert p.tolist() == [1, 3, 4, 6, 7]
+    # (2,1), (1,2) and the second (2,1) all land on slot 2; the smallest entry index owns it
+    assert m.tolist() == [1, 2, 3, 4, -2, -2, 0, 5, -4]
+    # every row starts with its diagonal slot
+    assert all(p[i] <= p[i + 1] - 1 for i in range(4))
+
+
+def test_analyse_reports_structure_without_gpu():
+    s = SLS()
+    s.control.f_indexing = False
+    assert s.analyse_matrix(N, "coordinate", 7, ROW, COL) == 0
+    inf = s.information()
+    assert (inf.entries, inf.duplicates, inf.out_of_range, inf.upper, inf.missing_diagonals) == (7, 0, 0, 0, 1)
+    assert inf.rank == 5 and inf.nodes_assembly_tree >= 1 and inf.entries_in_factors >= 8
+    assert s.analyse_matrix(0, "coordinate", 0, ROW, COL) == -3      # n > 0 restriction (sls.h status -3)
+    assert s.analyse_matrix(N, "banded", 0, ROW, COL) == -3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("storage", ["coordinate", "sparse_by_rows", "dense"])
+def test_slst_c_flow(storage):
+    s = SLS()
+    s.control.f_indexing = False
+    if storage == "coordinate":
+        assert s.analyse_matrix(N, storage, 7, ROW, COL) == 0
+        assert s.factorize_matrix(VAL) == 0
+    elif storage == "sparse_by_rows":
+        assert s.analyse_matrix(N, storage, 7, None, COL, PTR) == 0
+        assert s.factorize_matrix(VAL) == 0
+    else:
+        assert s.analyse_matrix(N, storage, 15) == 0
+        assert s.factorize_matrix(DENSE) == 0
+    good_x = EPS ** 0.3333                                           # slst.c:36
+    st, x = s.solve_system(RHS)
+    assert st == 0 and np.abs(x - SOL).max() < good_x
+    inf = s.information()
+    assert inf.status == 0 and inf.rank == 5 and inf.negative_eigenvalues == 2
+    s.control.max_iterative_refinements = 1                          # resolve with refinement
+    s.reset_control()
+    st, x = s.solve_system(RHS)
+    assert st == 0 and np.abs(x - SOL).max() < good_x
+    st, y = s.partial_solve_system("L", RHS)                         # by parts
+    st, y = s.partial_solve_system("D", y)
+    st, y = s.partial_solve_system("U", y)
+    assert st == 0 and np.abs(y - SOL).max() < good_x
+    s.terminate()
+
+
+@pytest.mark.gpu
+def test_provided_order_and_definite_path():
+    d = K["spd"]
+    row, col, val = np.array(d["row"]) - 1, np.array(d["col"]) - 1, np.array(d["val"], float)
+    perm = np.array(K["order_reverse"]) - 1                          # slst.f90:54-56
+    for pc in (1, 2):
+        s = SLS()
+        s.control.pivot_control = pc
+        assert s.analyse_matrix(N, "coordinate", 7, row, col, perm=perm) == 0
+        assert s.factorize_matrix(val) == 0
+        st, x = s.solve_system(np.array(d["rhs"], float))
+        assert np.abs(x - np.array(d["sol"], float)).max() < EPS ** 0.5
+        assert s.information().negative_eigenvalues == 0
+    s = SLS()
+    s.control.pivot_control = 2                                      # indefinite matrix on the definite path
+    s.analyse_matrix(N, "coordinate", 7, ROW, COL)
+    assert s.factorize_matrix(VAL) == -20                            # sls.h: "not positive definite" status
+
+
+@pytest.mark.gpu
+def test_duplicates_are_summed():
+    # split every value of the KAT into two entries: same solution
+    row2, col2 = np.concatenate([ROW, ROW]), np.concatenate([COL, COL])
+    val2 = np.concatenate([0.25 * VAL, 0.75 * VAL])
+    s = SLS()
+    assert s.analyse_matrix(N, "coordinate", 14, row2, col2) == 0
+    assert s.information().duplicates == 7
+    assert s.factorize_matrix(val2) == 0
+    st, x = s.solve_system(RHS)
+    assert np.abs(x - SOL).max() < EPS ** 0.5
+
+
+@pytest.mark.gpu
+def test_kkt_through_sls_with_nd_order():
+    prob = P.kkt_grid_problem(8)
+    n = prob["n"]
+    colidx = np.repeat(np.arange(n), np.diff(prob["ptr"]))
+    s = SLS()
+    # lower triangle in coordinate form, shuffled, with the geometric ND order as PERM
+    rng = np.random.default_rng(3)
+    q = rng.permutation(prob["row"].size)
+    assert s.analyse_matrix(n, "coordinate", q.size, prob["row"][q], colidx[q], perm=prob["order"]) == 0
+    assert s.factorize_matrix(prob["val"][q]) == 0
+    inf = s.information()
+    assert inf.negative_eigenvalues == prob["inertia"][1] and inf.rank == n
+    xs = rng.uniform(-1, 1, n)
+    b = P.full_from_lower(n, prob["ptr"], prob["row"], prob["val"]) @ xs
+    st, x = s.solve_system(b)
+    assert P.backward_error(prob, x, b) <= 1e-14
