@@ -54,7 +54,7 @@ def test_analyse_reports_structure_without_gpu():
     s.control.f_indexing = False
     assert s.analyse_matrix(N, "coordinate", 7, ROW, COL) == 0
     inf = s.information()
-    assert (inf.entries, inf.duplicates, inf.out_of_range, inf.upper, inf.missing_diagonals) == (7, 0, 0, 0, 1)
+    assert (inf.entries, inf.duplicates, inf.out_of_range, inf.upper, inf.missing_diagonals) == (7, 0, 0, 1, 1)   # entry (2,5) of slst.f90:29-33 is given in the upper triangle
     assert inf.rank == 5 and inf.nodes_assembly_tree >= 1 and inf.entries_in_factors >= 8
     assert s.analyse_matrix(0, "coordinate", 0, ROW, COL) == -3      # n > 0 restriction (sls.h status -3)
     assert s.analyse_matrix(N, "banded", 0, ROW, COL) == -3
