@@ -344,14 +344,14 @@ int b200ldlt_ntree_get(void* akeep, int base, int* sptr, int* sparent, int64_t* 
 int b200ldlt_partition(void* akeep, int nranks) {
    if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
    Akeep* ak = static_cast<Akeep*>(akeep);
-   find_subtree_partition(ak->sym, nranks, 1.2, 0);
-   return ak->sym.nparts;
+   find_subtree_partition(ak->nsym, nranks, 1.2, 0);   // on the engine's (fused) tree
+   return ak->nsym.nparts;
 }
 
 int b200ldlt_part_info(void* akeep, int part, int* first_node, int* last_node, int* owner,
                        int* dest_node, int64_t* flops) {
    if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
-   const Symbolic& s = static_cast<Akeep*>(akeep)->sym;
+   const Symbolic& s = static_cast<Akeep*>(akeep)->nsym;
    if (part < 0 || part >= s.nparts) return SSIDS_ERROR_CALL_SEQUENCE;
    if (first_node) *first_node = s.part[part];
    if (last_node) *last_node = s.part[part + 1] - 1;
@@ -370,6 +370,85 @@ int b200ldlt_part_info(void* akeep, int part, int* first_node, int* last_node, i
    }
    return 0;
 }
+
+// ---- multi-GPU -------------------------------------------------------------------------------
+int b200ldlt_dist_init(void* akeep, void** fkeep, int rank, int nranks, const b200ldlt_options* opt,
+                       b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   *inf = ak->inf_analyse;
+   find_subtree_partition(ak->nsym, nranks, 1.2, 0);
+   inf->nparts = ak->nsym.nparts;
+   if (ensure_plan(ak, opt->device)) { inf->cuda_error = ak->plan_cuda_error; return inf->flag = SSIDS_ERROR_CUDA_UNKNOWN; }
+   if (*fkeep) b200ldlt_free_fkeep(fkeep);
+   Fkeep* fk = new (std::nothrow) Fkeep();
+   if (!fk) return inf->flag = SSIDS_ERROR_ALLOCATION;
+   fk->ak = ak;
+   fk->num = numeric_create(ak->plan);
+   *fkeep = fk;
+   return inf->flag = numeric_set_partition(fk->num, rank, nranks);
+}
+
+int b200ldlt_dist_factor(void* akeep, void* fkeep, int phase, int posdef, const double* val,
+                         const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   Fkeep* fk = static_cast<Fkeep*>(fkeep);
+   *inf = ak->inf_analyse;
+   FactorStats st;
+   int flag = numeric_factor_phase(fk->num, val, to_engine(opt, posdef), st, phase);
+   inf->cuda_error = st.cuda_error;
+   inf->num_delay = st.num_delay;
+   inf->num_neg = st.num_neg;
+   inf->num_two = st.num_two;
+   inf->not_first_pass = st.not_first_pass;
+   inf->not_second_pass = st.not_second_pass;
+   inf->maxfront = st.maxfront;
+   inf->matrix_rank = ak->sym.matrix_rank - st.num_zero;
+   inf->time_factor = st.t_total;
+   inf->time_factor_device = st.t_device;
+   inf->factor_bytes = st.factor_bytes;
+   inf->reserved[0] = (int)st.launches;
+   return inf->flag = flag;
+}
+
+// boundary fronts: roots of leaf parts whose parent lies in the root part
+int b200ldlt_dist_nboundary(void* akeep) {
+   if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   const Symbolic& s = static_cast<Akeep*>(akeep)->nsym;
+   int c = 0;
+   for (int p = 0; p < s.nparts; ++p) {
+      int last = s.part[p + 1] - 1;
+      if (s.exec_loc[p] >= 0 && last >= 0 && s.sparent[last] < s.nnodes) ++c;
+   }
+   return c;
+}
+int b200ldlt_dist_boundary(void* akeep, int i, int* node, int* owner) {
+   if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   const Symbolic& s = static_cast<Akeep*>(akeep)->nsym;
+   int c = 0;
+   for (int p = 0; p < s.nparts; ++p) {
+      int last = s.part[p + 1] - 1;
+      if (s.exec_loc[p] >= 0 && last >= 0 && s.sparent[last] < s.nnodes) {
+         if (c == i) { *node = last; *owner = s.exec_loc[p]; return 0; }
+         ++c;
+      }
+   }
+   return SSIDS_ERROR_CALL_SEQUENCE;
+}
+int64_t b200ldlt_dist_contrib_bytes(void* fkeep, int node) { return numeric_contrib_bytes(static_cast<Fkeep*>(fkeep)->num, node); }
+int b200ldlt_dist_contrib_pack(void* fkeep, int node, void* d_dst) { return numeric_contrib_pack(static_cast<Fkeep*>(fkeep)->num, node, d_dst); }
+int b200ldlt_dist_contrib_unpack(void* fkeep, int node, const void* d_src, int64_t bytes) {
+   return numeric_contrib_unpack(static_cast<Fkeep*>(fkeep)->num, node, d_src, bytes);
+}
+int64_t b200ldlt_dist_xtail_bytes(void* fkeep, int node) { return numeric_xtail_bytes(static_cast<Fkeep*>(fkeep)->num, node); }
+int b200ldlt_dist_xtail_pack(void* fkeep, int node, void* d_dst) { return numeric_xtail_pack(static_cast<Fkeep*>(fkeep)->num, node, d_dst); }
+int b200ldlt_dist_xtail_unpack(void* fkeep, int node, const void* d_src) { return numeric_xtail_unpack(static_cast<Fkeep*>(fkeep)->num, node, d_src); }
+int b200ldlt_dist_solve(void* fkeep, int step, double* d_x, const double* d_src) {
+   return numeric_dist_solve(static_cast<Fkeep*>(fkeep)->num, step, d_x, d_src);
+}
+void* b200ldlt_dist_xp(void* fkeep) { return numeric_xp(static_cast<Fkeep*>(fkeep)->num); }
+int b200ldlt_dist_xp_get(void* fkeep, void* d_dst, int n) { return numeric_xp_get(static_cast<Fkeep*>(fkeep)->num, d_dst, n); }
 
 // per-node results (parity tests compare these with the oracle's)
 int b200ldlt_node_info(void* fkeep, int node, int* m, int* n, int* nelim) {

@@ -52,6 +52,11 @@ struct FrontDev {
    int w, fail;    // current panel width, first failed column of the panel (atomicMin)
    int jstart, jend0;   // current outer block [jstart, jend0) as opened
    int nelim, flag, slot;
+   unsigned p2mask;     // bit k set: column k of the current panel is the second column of a 2x2 pivot
+   int state;           // 0 absent on this rank, 2 factorised here, 3 imported from another rank (child data only)
+   int active;          // 1 while this front is being assembled / factorised by the current call
+   int part_kind;       // 0 leaf part, 1 root part of the subtree partition (multi-GPU solve phases)
+   int pad2;
 };
 
 struct SlotStatic {
@@ -73,10 +78,14 @@ __device__ __forceinline__ double* felem(const FrontDev& f, int r, int c) {
    return (c < f.n) ? (f.L + (size_t)c * f.ldl + r) : (f.C + (size_t)(c - f.n) * f.ldc + (r - f.n));
 }
 
-__device__ __forceinline__ int compute_nelim(int fail, int w, const int* ptype) {
+__device__ __forceinline__ int compute_nelim(int fail, int w, unsigned p2mask) {
    int nelim = fail < w ? fail : w;
-   if (nelim < w && nelim > 0 && ptype[nelim] == 2) nelim -= 1;
+   if (nelim < w && nelim > 0 && ((p2mask >> nelim) & 1u)) nelim -= 1;   // never split a 2x2 (Column::adjust)
    return nelim;
+}
+// front handled by this CTA: bucket-contiguous slots, or an explicit list on the rare retry paths
+__device__ __forceinline__ int front_slot(const int* list, int slot0) {
+   return list ? list[blockIdx.x] : slot0 + (int)blockIdx.x;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -87,6 +96,7 @@ __global__ void k_setup(FrontDev* fr, const SlotStatic* ss, const int* child_idx
    int s = slot0 + blockIdx.x;
    if (s >= slot0 + nslots) return;
    FrontDev& f = fr[s];
+   if (!f.active) return;
    const SlotStatic st = ss[s];
    for (int j = threadIdx.x; j < st.ncol; j += blockDim.x) f.perm[j] = st.first_piv + j;
    for (int j = threadIdx.x; j < f.n; j += blockDim.x) f.orig[j] = j;
@@ -103,6 +113,7 @@ __global__ void k_scatter_a(const FrontDev* fr, const int* aslot, const int* asr
    int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (e >= e1) return;
    const FrontDev& f = fr[aslot[e]];
+   if (!f.active) return;
    int r = arow[e], c = acol[e];
    if (r >= f.ncol) r += f.ndelay_in;
    f.L[(size_t)c * f.ldl + r] = val[asrc[e]];
@@ -377,6 +388,7 @@ __global__ void k_stats(const FrontDev* fr, int nslots, int* counters) {
    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    if (s >= nslots) return;
    const FrontDev& f = fr[s];
+   if (f.state != 2) return;
    int neg = 0, two = 0, zero = 0;
    for (int i = lane; i < f.nelim; i += 32) {
       double a11 = f.D[2 * i];
@@ -407,10 +419,21 @@ __global__ void k_stats(const FrontDev* fr, int nslots, int* counters) {
 
 #include "solve_kernels.cuh"
 
+// multi-GPU: which pivots did this rank eliminate, and which of them in the root part
+__global__ void k_build_masks(const FrontDev* fr, int nslots, char* mine, char* root) {
+   const int lane = threadIdx.x & 31;
+   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   if (s >= nslots) return;
+   const FrontDev& f = fr[s];
+   if (f.state != 2) return;
+   for (int k = lane; k < f.nelim; k += 32) { mine[f.perm[k]] = 1; root[f.perm[k]] = f.part_kind == 1; }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int size_class(int m) { return m <= 64 ? 0 : m <= 256 ? 1 : m <= 1024 ? 2 : m <= 4096 ? 3 : 4; }
 
 struct Arena {
    struct Chunk { char* p; size_t size; };
@@ -506,7 +529,19 @@ Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
    P->node_slot.assign(nn, 0);
    {
       std::vector<int> pos(P->lvl_ptr.begin(), P->lvl_ptr.end() - 1);
-      for (int i = 0; i < nn; ++i) { int s = pos[lvl[i]]++; P->slot_node[s] = i; P->node_slot[i] = s; }
+      for (int i = 0; i < nn; ++i) { int s = pos[lvl[i]]++; P->slot_node[s] = i; }
+      // within a level: size class of the front, then wider fronts first, so that a bucket of the
+      // factorisation is a contiguous slot range (no indirection list on the hot path)
+      auto nrow_of = [&](int i) { return (int)(sym.rptr[i + 1] - sym.rptr[i]); };
+      auto ncol_of = [&](int i) { return sym.sptr[i + 1] - sym.sptr[i]; };
+      for (int l = 0; l < maxd; ++l)
+         std::sort(P->slot_node.begin() + P->lvl_ptr[l], P->slot_node.begin() + P->lvl_ptr[l + 1], [&](int a, int b) {
+            int ca = size_class(nrow_of(a)), cb = size_class(nrow_of(b));
+            if (ca != cb) return ca < cb;
+            if (ncol_of(a) != ncol_of(b)) return ncol_of(a) > ncol_of(b);
+            return a < b;
+         });
+      for (int s = 0; s < nn; ++s) P->node_slot[P->slot_node[s]] = s;
    }
    // static per-slot data, children (ascending node order), relative indices
    P->hss.assign(nn, SlotStatic());
@@ -641,7 +676,10 @@ class Numeric {
    double *d_x = nullptr, *d_xp = nullptr, *d_xw = nullptr;
    size_t x_cap = 0, xw_cap = 0;
    int64_t xw_total = 0;
-   Arena fac, dar, par, car[2], war;
+   Arena fac, dar, par, car[2], war, bar;   // bar: contribution blocks that cross a part boundary + imports
+   std::vector<char> active, boundary;
+   std::vector<int> part_kind, owner;      // per slot; owner -1 = root part
+   int my_rank = 0, nranks = 1;
    cudaStream_t st = nullptr;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
    int cuda_err = 0;
@@ -653,9 +691,9 @@ class Numeric {
    explicit Numeric(Plan* p) : P(p) {}
    ~Numeric() {
       cudaSetDevice(P->device);
-      fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release();
+      fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release(); bar.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
-      cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
+      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
       if (st) cudaStreamDestroy(st);
@@ -664,8 +702,21 @@ class Numeric {
       if (ev2) cudaEventDestroy(ev2);
    }
    int init();
-   int factor(const double* val, bool on_device, const FactorOptions& o, FactorStats& stats);
+   int factor(const double* val, bool on_device, const FactorOptions& o, FactorStats& stats, int phase = 0);
+   int set_partition(int rank, int nr);
+   int finish_factor(FactorStats& stats, int flag);
    int solve(int job, int nrhs, double* x, int ldx, bool on_device, double* seconds, int64_t* nl);
+   int solve_prepare();
+   void sweep_fwd(int kind, int64_t& nlaunch);
+   void sweep_bwd(int kind, bool diag, int64_t& nlaunch);
+   int64_t contrib_bytes(int node) const;
+   int contrib_pack(int node, char* dst);
+   int contrib_unpack(int node, const char* src, int64_t bytes);
+   int64_t xtail_bytes(int node) const;
+   int xtail_pack(int node, char* dst);
+   int xtail_unpack(int node, const char* src);
+   int dist_solve(int step, double* d_xio, const double* src);
+   char *d_root_mask = nullptr, *d_mine_mask = nullptr;
 };
 
 #define CU(x)                                                          \
@@ -703,11 +754,15 @@ int Numeric::init() {
    CU(cudaMalloc(&d_val, sizeof(double) * std::max<int64_t>(P->sym->nz, 1)));
    child_doff.assign(P->child_idx.size(), 0);
    hfr.assign(nn, FrontDev());
-   fac.err = dar.err = par.err = car[0].err = car[1].err = war.err = &cuda_err;
+   fac.err = dar.err = par.err = car[0].err = car[1].err = war.err = bar.err = &cuda_err;
+   active.assign(nn, 1);
+   boundary.assign(nn, 0);
+   part_kind.assign(nn, 0);
+   owner.assign(nn, 0);
    return 0;
 }
 
-int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, FactorStats& stats) {
+int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, FactorStats& stats, int phase) {
    stats = FactorStats();
    int rc = init();
    if (rc) { stats.cuda_error = cuda_err; return stats.flag = rc; }
@@ -732,10 +787,20 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    car[0].reserve((size_t)(P->est_c_doubles[0] * mult) * 8 + (1 << 16));
    car[1].reserve((size_t)(P->est_c_doubles[1] * mult) * 8 + (1 << 16));
    war.reserve((size_t)(P->est_ws_doubles * mult) * 8 + (1 << 16));
-   fac.reset(); dar.reset(); par.reset();
+   if (phase != 2) CU(cudaMemsetAsync(d_fr, 0, sizeof(FrontDev) * std::max(nn, 1), st));
+   // phase 0: everything (single GPU).  phase 1: the leaf parts this rank owns.  phase 2: the root
+   // part (its owner only), on top of what phase 1 and the imports left in place.
+   if (phase != 2) { fac.reset(); dar.reset(); par.reset(); bar.reset(); }
+   for (int s = 0; s < nn; ++s) {
+      const bool mine_leaf = owner[s] == my_rank, root_part = owner[s] < 0;
+      active[s] = phase == 0 ? 1 : phase == 1 ? (mine_leaf ? 1 : 0) : (root_part && my_rank == 0 ? 1 : 0);
+      if (phase != 2) { hfr[s] = FrontDev(); }
+   }
 
    CU(cudaEventRecord(ev0, st));
-   if (on_device) {
+   if (phase == 2) {
+      // values are already resident from phase 1
+   } else if (on_device) {
       CU(cudaMemcpyAsync(d_val, val, sizeof(double) * sym.nz, cudaMemcpyDeviceToDevice, st));
    } else {
       CU(cudaMemcpyAsync(d_val, val, sizeof(double) * sym.nz, cudaMemcpyHostToDevice, st));
@@ -752,7 +817,11 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       war.reset();
       // sizes with delays
       size_t totL = 0, totC = 0, totD = 0, totP = 0, totW = 0;
+      int nactive_lvl = 0;
+      for (int s = s0; s < s1; ++s) nactive_lvl += active[s];
+      if (nactive_lvl == 0) continue;
       for (int s = s0; s < s1; ++s) {
+         if (!active[s]) continue;
          const SlotStatic& ss = P->hss[s];
          FrontDev& f = hfr[s];
          int nd = 0;
@@ -769,8 +838,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          f.ldl = (int)align_up(f.m, 2);
          f.ldc = (int)align_up(f.m - f.n, 2);
          f.done = 0; f.oend = 0; f.gend = f.n; f.w = 0; f.fail = 0; f.jstart = 0; f.jend0 = 0; f.nelim = 0; f.flag = 0;
+         f.state = 2; f.active = 1; f.part_kind = part_kind[s];
          totL += align_up((size_t)f.ldl * f.n, 32);
-         totC += align_up((size_t)f.ldc * (f.m - f.n), 32);
+         if (!boundary[s]) totC += align_up((size_t)f.ldc * (f.m - f.n), 32);
          totD += align_up(2 * (size_t)f.n + 2, 32);
          totP += 2 * align_up((size_t)f.n + 1, 32);
          totW += align_up((size_t)f.ldl * (NBO + NB) + 4 * NB * NB + 2 * NB + 2, 32) + 128;
@@ -785,9 +855,18 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       {
          size_t oL = 0, oC = 0, oD = 0, oP = 0, oW = 0;
          for (int s = s0; s < s1; ++s) {
+            if (!active[s]) continue;
             FrontDev& f = hfr[s];
             f.L = Lb + oL; oL += align_up((size_t)f.ldl * f.n, 32);
-            f.C = Cb + oC; oC += align_up((size_t)f.ldc * (f.m - f.n), 32);
+            if (boundary[s]) {
+               // the contribution block crosses a part boundary: it must outlive the level arenas
+               size_t cb = align_up((size_t)f.ldc * (f.m - f.n), 32) * 8;
+               f.C = (double*)bar.alloc(cb);
+               if (!f.C) { stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_ALLOCATION; }
+               CU(cudaMemsetAsync(f.C, 0, cb, st));
+            } else {
+               f.C = Cb + oC; oC += align_up((size_t)f.ldc * (f.m - f.n), 32);
+            }
             f.D = Db + oD; oD += align_up(2 * (size_t)f.n + 2, 32);
             f.perm = Pb + oP; f.orig = f.perm + align_up((size_t)f.n + 1, 32); oP += 2 * align_up((size_t)f.n + 1, 32);
             double* wp = Wb + oW;
@@ -818,7 +897,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       // so each ordinal gets its own region of the pinned buffer.
       {
          int maxc = 0;
-         for (int s = s0; s < s1; ++s) maxc = std::max(maxc, P->hss[s].child_end - P->hss[s].child_begin);
+         for (int s = s0; s < s1; ++s) if (active[s]) maxc = std::max(maxc, P->hss[s].child_end - P->hss[s].child_begin);
          size_t pin_off = 0;
          for (int k = 0; k < maxc; ++k) {
             lvl_list.clear();
@@ -826,6 +905,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             tileptr.clear();
             tileptr.push_back(0);
             for (int s = s0; s < s1; ++s) {
+               if (!active[s]) continue;
                const SlotStatic& ss = P->hss[s];
                if (ss.child_end - ss.child_begin <= k) continue;
                int cs = P->child_idx[ss.child_begin + k];
@@ -867,18 +947,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       {
          std::vector<int> order(ns);
          for (int i = 0; i < ns; ++i) order[i] = s0 + i;
-         auto cls = [&](int s) {
-            int m = hfr[s].m;
-            return m <= 64 ? 0 : m <= 256 ? 1 : m <= 1024 ? 2 : m <= 4096 ? 3 : 4;
-         };
-         std::sort(order.begin(), order.end(), [&](int a, int b) {
-            int ca2 = cls(a), cb2 = cls(b);
-            if (ca2 != cb2) return ca2 < cb2;
-            if (hfr[a].n != hfr[b].n) return hfr[a].n > hfr[b].n;
-            return a < b;
-         });
-         memcpy(pin_i, order.data(), sizeof(int) * ns);
-         CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+         auto cls = [&](int s) { return size_class(P->hss[s].nrow); };   // static class: slots are pre-sorted by it
          auto prof_begin = [&]() {
             if (prof_used + 2 > prof_ev.size()) {
                size_t old = prof_ev.size();
@@ -888,34 +957,35 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             cudaEventRecord(prof_ev[prof_used], st);
          };
          auto prof_end = [&]() { cudaEventRecord(prof_ev[prof_used + 1], st); prof_used += 2; };
-         // remaining candidates per front as the host believes them (exact when nothing fails)
-         std::vector<int> rem_done(ns, 0), rem_gend(ns, 0);
-         for (int i = 0; i < ns; ++i) { rem_done[i] = 0; rem_gend[i] = hfr[order[i]].n; }
          int i0 = 0;
          while (i0 < ns) {
             int c = cls(order[i0]), i1 = i0;
             int maxm = 0, maxn = 0;
             while (i1 < ns && cls(order[i1]) == c) {
-               maxm = std::max(maxm, hfr[order[i1]].m);
-               maxn = std::max(maxn, hfr[order[i1]].n);
+               if (active[order[i1]]) {
+                  maxm = std::max(maxm, hfr[order[i1]].m);
+                  maxn = std::max(maxn, hfr[order[i1]].n);
+               }
                ++i1;
             }
-            const int* lst = d_list + i0;
+            if (maxm == 0) { i0 = i1; continue; }
+            const int* lst = nullptr;
+            const int b0 = s0 + i0;   // first slot of the bucket
             const int ncolchunks = (maxn + 127) / 128;
             const int ycommit = 1 + ncolchunks + (maxm + 127) / 128;
             const int yapply = std::max(1, (maxm + AR - 1) / AR);
             const int nouter = (maxn + NBO - 1) / NBO;
             for (int ob = 0; ob < nouter; ++ob) {
-               int na = 0;   // active prefix: fronts that still have an outer block number ob
-               while (i0 + na < i1 && (hfr[order[i0 + na]].n + NBO - 1) / NBO > ob) ++na;
+               int na = 0;   // slots [b0, b0+na) cover every front that still has an outer block number ob
+               for (int q = i0; q < i1; ++q) if (active[order[q]] && (hfr[order[q]].n + NBO - 1) / NBO > ob) na = q - i0 + 1;
                if (na == 0) break;
                int maxw_outer = 0;
-               for (int q = 0; q < na; ++q) maxw_outer = std::max(maxw_outer, std::min(NBO, hfr[order[i0 + q]].n - ob * NBO));
+               for (int q = 0; q < na; ++q) if (active[order[i0 + q]]) maxw_outer = std::max(maxw_outer, std::min(NBO, hfr[order[i0 + q]].n - ob * NBO));
                const int ninner = (maxw_outer + NB - 1) / NB;
                for (int j = 0; j < ninner; ++j) {
-                  k_diag<<<na, 128, 0, st>>>(d_fr, lst, prm, j == 0 ? 1 : 0);
-                  k_apply<<<dim3(na, yapply), 256, 0, st>>>(d_fr, lst, prm);
-                  k_commit<<<dim3(na, ycommit), 128, 0, st>>>(d_fr, lst, ncolchunks);
+                  k_diag<<<na, 128, 0, st>>>(d_fr, lst, b0, prm, j == 0 ? 1 : 0);
+                  k_apply<<<dim3(na, yapply), 256, 0, st>>>(d_fr, lst, b0, prm);
+                  k_commit<<<dim3(na, ycommit), 128, 0, st>>>(d_fr, lst, b0, ncolchunks);
                   launches += 3;
                   // inner update: columns of the outer block behind this panel
                   const int colsleft = maxw_outer - (j + 1) * NB;
@@ -925,13 +995,14 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                      if (o.profile) {
                         for (int q = 0; q < na; ++q) {
                            const FrontDev& ff = hfr[order[i0 + q]];
+                           if (!active[order[i0 + q]]) continue;
                            double dn = ob * NBO + j * NB, je = std::min<double>(ff.n, (ob + 1) * NBO);
                            double ww = std::min<double>(NB, je - dn), cb = dn + ww;
                            if (ww > 0 && je > cb) prof_flops += 2.0 * ww * ((je - cb) * (ff.m - cb) - 0.5 * (je - cb) * (je - cb - 1));
                         }
                         prof_begin();
                      }
-                     k_update<<<dim3(na, ygrid), 256, UPD_SMEM, st>>>(d_fr, lst, 0);
+                     k_update<<<dim3(na, ygrid), 256, UPD_SMEM, st>>>(d_fr, lst, b0, 0);
                      if (o.profile) prof_end();
                      ++launches;
                   }
@@ -945,17 +1016,18 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   if (o.profile) {
                      for (int q = 0; q < na; ++q) {
                         const FrontDev& ff = hfr[order[i0 + q]];
+                        if (!active[order[i0 + q]]) continue;
                         double je = std::min<double>(ff.n, (ob + 1) * NBO), kc2 = je - ob * NBO, tt = ff.m - je;
                         if (kc2 > 0 && tt > 0) prof_flops += kc2 * tt * (tt + 1);
                      }
                      prof_begin();
                   }
-                  k_update<<<dim3(na, ygrid), 256, UPD_SMEM, st>>>(d_fr, lst, 1);
+                  k_update<<<dim3(na, ygrid), 256, UPD_SMEM, st>>>(d_fr, lst, b0, 1);
                   if (o.profile) prof_end();
                   ++launches;
                }
             }
-            k_diag<<<i1 - i0, 128, 0, st>>>(d_fr, lst, prm, 2);
+            k_diag<<<i1 - i0, 128, 0, st>>>(d_fr, lst, b0, prm, 2);
             ++launches;
             i0 = i1;
          }
@@ -968,6 +1040,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          if (cudaMemcpyAsync(pin_i, d_collect, sizeof(int) * 3 * ns, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
          if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
          for (int i = 0; i < ns; ++i) {
+            if (!active[s0 + i]) continue;
             FrontDev& f = hfr[s0 + i];
             f.done = pin_i[3 * i];
             f.nelim = f.done;
@@ -981,7 +1054,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       if (flag < 0) break;
       for (int round = 0; round < 1000; ++round) {
          tpp_list.clear();
-         for (int i = 0; i < ns; ++i) if (hfr[s0 + i].done < hfr[s0 + i].gend) tpp_list.push_back(s0 + i);
+         for (int i = 0; i < ns; ++i) if (active[s0 + i] && hfr[s0 + i].done < hfr[s0 + i].gend) tpp_list.push_back(s0 + i);
          if (tpp_list.empty()) break;
          int nt = (int)tpp_list.size(), maxm = 0, maxn = 0;
          for (int s : tpp_list) { maxm = std::max(maxm, hfr[s].m); maxn = std::max(maxn, hfr[s].n); }
@@ -989,14 +1062,14 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * nt, cudaMemcpyHostToDevice, st));
          const int ncolchunks = (maxn + 127) / 128;
          for (int j = 0; j < NBO / NB; ++j) {
-            k_diag<<<nt, 128, 0, st>>>(d_fr, d_list, prm, j == 0 ? 1 : 0);
-            k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, 0, st>>>(d_fr, d_list, prm);
-            k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 127) / 128), 128, 0, st>>>(d_fr, d_list, ncolchunks);
-            k_update<<<dim3(nt, std::max(1, std::min((maxm + TM - 1) / TM, 64))), 256, UPD_SMEM, st>>>(d_fr, d_list, 0);
+            k_diag<<<nt, 128, 0, st>>>(d_fr, d_list, 0, prm, j == 0 ? 1 : 0);
+            k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, 0, st>>>(d_fr, d_list, 0, prm);
+            k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 127) / 128), 128, 0, st>>>(d_fr, d_list, 0, ncolchunks);
+            k_update<<<dim3(nt, std::max(1, std::min((maxm + TM - 1) / TM, 64))), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, 0);
             launches += 4;
          }
-         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 1);
-         k_diag<<<nt, 128, 0, st>>>(d_fr, d_list, prm, 2);
+         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, 1);
+         k_diag<<<nt, 128, 0, st>>>(d_fr, d_list, 0, prm, 2);
          launches += 2;
          if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
          if (flag < 0) break;
@@ -1004,6 +1077,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       if (flag < 0) break;
       tpp_list.clear();
       for (int i = 0; i < ns; ++i) {
+         if (!active[s0 + i]) continue;
          FrontDev& f = hfr[s0 + i];
          if (f.done < f.n) { tpp_list.push_back(s0 + i); nfp += f.n - f.done; }
       }
@@ -1014,12 +1088,12 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          k_tpp<<<nt, 256, 0, st>>>(d_fr, d_list, prm);
          ++launches;
          if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
-         for (int i = 0; i < ns; ++i) nsp += hfr[s0 + i].n - hfr[s0 + i].done;
+         for (int i = 0; i < ns; ++i) if (active[s0 + i]) nsp += hfr[s0 + i].n - hfr[s0 + i].done;
       } else if (!tpp_list.empty() && posdef) {
          flag = SSIDS_ERROR_NOT_POS_DEF;
       }
       if (flag < 0) break;
-      for (int s = s0; s < s1; ++s) num_delay += hfr[s].n - hfr[s].nelim;
+      for (int s = s0; s < s1; ++s) if (active[s]) { num_delay += hfr[s].n - hfr[s].nelim; hfr[s].active = 0; }
    }
    if (flag >= 0) {
       CU(cudaMemsetAsync(d_counters, 0, sizeof(int) * 8, st));
@@ -1079,16 +1153,18 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          const int a0 = P->lvl_ptr[l], a1 = P->lvl_ptr[l + 1];
          for (int s = a0; s < a1; ++s) slist[s] = s;
          std::sort(slist.begin() + a0, slist.begin() + a1, [&](int x, int y) {
-            if (hfr[x].nelim != hfr[y].nelim) return hfr[x].nelim > hfr[y].nelim;
+            const int ex = hfr[x].state == 2 ? hfr[x].nelim : 0, ey = hfr[y].state == 2 ? hfr[y].nelim : 0;
+            if (ex != ey) return ex > ey;
             return x < y;
          });
-         const int steps = a1 > a0 ? (hfr[slist[a0]].nelim + KB - 1) / KB : 0;
+         auto ne_of = [&](int s) { return hfr[s].state == 2 ? hfr[s].nelim : 0; };
+         const int steps = a1 > a0 ? (ne_of(slist[a0]) + KB - 1) / KB : 0;
          lvl_steps[l] = steps;
          lvl_nact[l].assign(steps, 0);
          lvl_actm[l].assign(steps, 0);
          for (int st2 = 0; st2 < steps; ++st2) {
             int na = 0, mm = 0;
-            while (a0 + na < a1 && (hfr[slist[a0 + na]].nelim + KB - 1) / KB > st2) { mm = std::max(mm, hfr[slist[a0 + na]].m); ++na; }
+            while (a0 + na < a1 && (ne_of(slist[a0 + na]) + KB - 1) / KB > st2) { mm = std::max(mm, hfr[slist[a0 + na]].m); ++na; }
             lvl_nact[l][st2] = na;
             lvl_actm[l][st2] = mm;
          }
@@ -1098,21 +1174,20 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       if (!child_doff.empty())
          CU(cudaMemcpy(d_child_doff, child_doff.data(), sizeof(int) * child_doff.size(), cudaMemcpyHostToDevice));
    }
+   if (d_mine_mask && nn > 0) {
+      CU(cudaMemset(d_mine_mask, 0, std::max(sym.n, 1)));
+      CU(cudaMemset(d_root_mask, 0, std::max(sym.n, 1)));
+      k_build_masks<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, nn, d_mine_mask, d_root_mask);
+      CU(cudaStreamSynchronize(st));
+   }
    have = true;
    last = stats;
    last.flag = flag;
    return stats.flag = flag;
 }
 
-int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double* seconds, int64_t* nl) {
-   if (!have) return SSIDS_ERROR_CALL_SEQUENCE;
-   if (job < 0 || job > 4) return SSIDS_ERROR_JOB_OOR;
-   const Symbolic& sym = *P->sym;
-   const int n = sym.n, nn = P->nnodes;
-   if (ldx < n || nrhs < 1) return SSIDS_ERROR_X_SIZE;
-   if (posdef && (job == 2 || job == 4)) return SSIDS_ERROR_JOB_OOR;   // ssids.f90:1180-1190
-   CU(cudaSetDevice(P->device));
-   int64_t nlaunch = 0;
+int Numeric::solve_prepare() {
+   const int n = P->sym->n;
    size_t need = (size_t)std::max(n, 1);
    if (x_cap < need) {
       cudaFree(d_x); cudaFree(d_xp);
@@ -1133,7 +1208,58 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
       CU(cudaMalloc(&d_part, ((size_t)part_total + 2) * 8));
       part_cap = (size_t)part_total + 2;
    }
+   return 0;
+}
+
+// forward sweep over the fronts of `kind` (-1: all)
+void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
    double* d_xa = d_xw + xw_cap / 2;
+   for (int l = 0; l < P->nlevels; ++l) {
+      const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
+      k_fwd_gather<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xa, d_xp, s0, kind);
+      ++nlaunch;
+      for (int sp = 0; sp < lvl_steps[l]; ++sp) {
+         const int na = lvl_nact[l][sp];
+         if (na == 0) break;
+         k_fwd_tri<<<na, 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, sp, kind);
+         const int rows = lvl_actm[l][sp] - sp * KB - 1;
+         if (rows > 0) { k_fwd_upd<<<dim3(na, (rows + RC - 1) / RC), 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, sp, kind); ++nlaunch; }
+         ++nlaunch;
+      }
+      k_fwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xw, d_xp, s0, posdef ? 1 : 0, kind);
+      ++nlaunch;
+   }
+}
+
+void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
+   for (int l = P->nlevels - 1; l >= 0; --l) {
+      const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
+      k_bwd_gather<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_rlist, d_xw_off, d_xw, d_xp, s0, diag ? 1 : 0, posdef ? 1 : 0, kind);
+      ++nlaunch;
+      for (int sp = lvl_steps[l] - 1; sp >= 0; --sp) {
+         const int na = lvl_nact[l][sp];
+         if (na == 0) continue;
+         const int rows = lvl_actm[l][sp] - sp * KB - 1;
+         if (rows > 0) { k_bwd_dots<<<dim3(na, (rows + RD - 1) / RD), 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, sp, kind); ++nlaunch; }
+         k_bwd_tri<<<na, 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, sp, kind);
+         ++nlaunch;
+      }
+      k_bwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xw, d_xp, s0, kind);
+      ++nlaunch;
+   }
+}
+
+int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double* seconds, int64_t* nl) {
+   if (!have) return SSIDS_ERROR_CALL_SEQUENCE;
+   if (job < 0 || job > 4) return SSIDS_ERROR_JOB_OOR;
+   const Symbolic& sym = *P->sym;
+   const int n = sym.n, nn = P->nnodes;
+   if (ldx < n || nrhs < 1) return SSIDS_ERROR_X_SIZE;
+   if (posdef && (job == 2 || job == 4)) return SSIDS_ERROR_JOB_OOR;   // ssids.f90:1180-1190
+   CU(cudaSetDevice(P->device));
+   int64_t nlaunch = 0;
+   int rc = solve_prepare();
+   if (rc) return rc;
    CU(cudaEventRecord(ev0, st));
    const int nb = (n + 255) / 256;
    for (int j = 0; j < nrhs; ++j) {
@@ -1146,39 +1272,9 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
       const bool diag = !posdef && (job == 0 || job == 2 || job == 4);
       // posdef: LL^T semantics with L_chol = L sqrt(D); sqrt(D^-1) is folded into each sweep so
       // that the partial solves match SSIDS's posdef jobs
-      if (fwd)
-         for (int l = 0; l < P->nlevels; ++l) {
-            const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
-            k_fwd_gather<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xa, d_xp, s0);
-            ++nlaunch;
-            for (int sp = 0; sp < lvl_steps[l]; ++sp) {
-               const int na = lvl_nact[l][sp];
-               if (na == 0) break;
-               k_fwd_tri<<<na, 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, sp);
-               const int rows = lvl_actm[l][sp] - sp * KB - 1;
-               if (rows > 0) { k_fwd_upd<<<dim3(na, (rows + RC - 1) / RC), 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, sp); ++nlaunch; }
-               ++nlaunch;
-            }
-            k_fwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xw, d_xp, s0, posdef ? 1 : 0);
-            ++nlaunch;
-         }
+      if (fwd) sweep_fwd(-1, nlaunch);
       if (diag && !bwd && nn > 0) { k_solve_diag<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, d_xp, nn); ++nlaunch; }
-      if (bwd)
-         for (int l = P->nlevels - 1; l >= 0; --l) {
-            const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
-            k_bwd_gather<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_rlist, d_xw_off, d_xw, d_xp, s0, diag ? 1 : 0, posdef ? 1 : 0);
-            ++nlaunch;
-            for (int sp = lvl_steps[l] - 1; sp >= 0; --sp) {
-               const int na = lvl_nact[l][sp];
-               if (na == 0) continue;
-               const int rows = lvl_actm[l][sp] - sp * KB - 1;
-               if (rows > 0) { k_bwd_dots<<<dim3(na, (rows + RD - 1) / RD), 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, sp); ++nlaunch; }
-               k_bwd_tri<<<na, 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, sp);
-               ++nlaunch;
-            }
-            k_bwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xw, d_xp, s0);
-            ++nlaunch;
-         }
+      if (bwd) sweep_bwd(-1, diag, nlaunch);
       if (n > 0) { k_permute_out<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, n); ++nlaunch; }
       if (!on_device) CU(cudaMemcpyAsync(xj, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
    }
@@ -1195,7 +1291,172 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
    return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU: subtree partition, boundary fronts, phased solve (one process per GPU; the host side
+// moves the packed boundary data between ranks with NCCL, galahad_b200/dist.py)
+// ---------------------------------------------------------------------------------------------
+int Numeric::set_partition(int rank, int nr) {
+   int rc = init();
+   if (rc) return rc;
+   const Symbolic& sym = *P->sym;
+   const int nn = P->nnodes;
+   my_rank = rank;
+   nranks = nr;
+   std::vector<int> node_owner(nn, -1);
+   for (int p = 0; p < sym.nparts; ++p)
+      for (int node = sym.part[p]; node < sym.part[p + 1]; ++node) node_owner[node] = sym.exec_loc[p];
+   std::vector<char> root_mask(std::max(sym.n, 1), 0), mine_mask(std::max(sym.n, 1), 0);
+   for (int node = 0; node < nn; ++node) {
+      const int s = P->node_slot[node];
+      owner[s] = node_owner[node];
+      part_kind[s] = node_owner[node] < 0 ? 1 : 0;
+      const int par = sym.sparent[node];
+      boundary[s] = (par < nn && node_owner[node] >= 0 && node_owner[par] < 0) ? 1 : 0;
+      const bool mine = node_owner[node] == rank || (node_owner[node] < 0 && rank == 0);
+      for (int piv = sym.sptr[node]; piv < sym.sptr[node + 1]; ++piv) {
+         root_mask[piv] = node_owner[node] < 0;
+         mine_mask[piv] = mine;
+      }
+   }
+   // delayed pivots cross part boundaries with their columns; the masks above are by ORIGINAL
+   // supernode, which is exact when nothing is delayed across a boundary (checked at import)
+   cudaFree(d_root_mask); cudaFree(d_mine_mask);
+   CU(cudaMalloc(&d_root_mask, root_mask.size()));
+   CU(cudaMalloc(&d_mine_mask, mine_mask.size()));
+   CU(cudaMemcpy(d_root_mask, root_mask.data(), root_mask.size(), cudaMemcpyHostToDevice));
+   CU(cudaMemcpy(d_mine_mask, mine_mask.data(), mine_mask.size(), cudaMemcpyHostToDevice));
+   return 0;
+}
+
+// packed boundary front: 8 x int64 header {m, n, nelim, ldl, ldc, 0,0,0} | perm[n-nelim] (padded to 8 B)
+// | L(:, nelim:n) (ldl x (n-nelim)) | C (ldc x (m-n))
+int64_t Numeric::contrib_bytes(int node) const {
+   const FrontDev& f = hfr[P->node_slot[node]];
+   const int64_t nd = f.n - f.nelim;
+   return 64 + (int64_t)align_up(nd * 4, 8) + 8 * (int64_t)f.ldl * nd + 8 * (int64_t)f.ldc * (f.m - f.n);
+}
+
+int Numeric::contrib_pack(int node, char* dst) {
+   CU(cudaSetDevice(P->device));
+   const FrontDev& f = hfr[P->node_slot[node]];
+   const int64_t nd = f.n - f.nelim;
+   int64_t hdr[8] = {f.m, f.n, f.nelim, f.ldl, f.ldc, 0, 0, 0};
+   CU(cudaMemcpyAsync(dst, hdr, 64, cudaMemcpyHostToDevice, st));
+   char* p = dst + 64;
+   if (nd > 0) {
+      CU(cudaMemcpyAsync(p, f.perm + f.nelim, nd * 4, cudaMemcpyDeviceToDevice, st));
+      p += align_up(nd * 4, 8);
+      CU(cudaMemcpyAsync(p, f.L + (size_t)f.nelim * f.ldl, 8 * (size_t)f.ldl * nd, cudaMemcpyDeviceToDevice, st));
+      p += 8 * (size_t)f.ldl * nd;
+   }
+   if (f.m > f.n) CU(cudaMemcpyAsync(p, f.C, 8 * (size_t)f.ldc * (f.m - f.n), cudaMemcpyDeviceToDevice, st));
+   CU(cudaStreamSynchronize(st));
+   return 0;
+}
+
+int Numeric::contrib_unpack(int node, const char* src, int64_t bytes) {
+   CU(cudaSetDevice(P->device));
+   const int s = P->node_slot[node];
+   int64_t hdr[8];
+   CU(cudaMemcpy(hdr, src, 64, cudaMemcpyDeviceToHost));
+   FrontDev f = FrontDev();
+   f.slot = s;
+   f.m = (int)hdr[0]; f.n = (int)hdr[1]; f.nelim = (int)hdr[2]; f.ldl = (int)hdr[3]; f.ldc = (int)hdr[4];
+   f.ncol = P->hss[s].ncol; f.nrow = P->hss[s].nrow; f.first_piv = P->hss[s].first_piv;
+   f.ndelay_in = f.m - f.nrow;
+   f.done = f.gend = f.nelim; f.oend = f.nelim; f.jstart = f.jend0 = f.nelim;
+   f.state = 3; f.part_kind = 0;
+   const int64_t nd = f.n - f.nelim;
+   const int64_t need = 64 + (int64_t)align_up(nd * 4, 8) + 8 * (int64_t)f.ldl * nd + 8 * (int64_t)f.ldc * (f.m - f.n);
+   if (need != bytes) return SSIDS_ERROR_UNKNOWN;
+   char* buf = (char*)bar.alloc((size_t)bytes);
+   if (!buf) return SSIDS_ERROR_ALLOCATION;
+   CU(cudaMemcpyAsync(buf, src, (size_t)bytes, cudaMemcpyDeviceToDevice, st));
+   char* p = buf + 64;
+   f.perm = (int*)p - f.nelim;                       // only perm[nelim..n) is ever read
+   f.orig = nullptr;
+   p += align_up(nd * 4, 8);
+   f.L = (double*)p - (size_t)f.nelim * f.ldl;      // only columns nelim..n are ever read
+   p += 8 * (size_t)f.ldl * nd;
+   f.C = (double*)p;
+   hfr[s] = f;
+   CU(cudaMemcpyAsync(d_fr + s, &hfr[s], sizeof(FrontDev), cudaMemcpyHostToDevice, st));
+   CU(cudaStreamSynchronize(st));
+   return 0;
+}
+
+int64_t Numeric::xtail_bytes(int node) const {
+   const FrontDev& f = hfr[P->node_slot[node]];
+   return 8 * (int64_t)(f.m - f.nelim);
+}
+int Numeric::xtail_pack(int node, char* dst) {
+   CU(cudaSetDevice(P->device));
+   const int s = P->node_slot[node];
+   const FrontDev& f = hfr[s];
+   std::vector<int64_t> off(1);
+   CU(cudaMemcpy(off.data(), d_xw_off + s, 8, cudaMemcpyDeviceToHost));
+   if (f.m > f.nelim) CU(cudaMemcpyAsync(dst, d_xw + off[0] + f.nelim, 8 * (size_t)(f.m - f.nelim), cudaMemcpyDeviceToDevice, st));
+   CU(cudaStreamSynchronize(st));
+   return 0;
+}
+int Numeric::xtail_unpack(int node, const char* src) {
+   CU(cudaSetDevice(P->device));
+   const int s = P->node_slot[node];
+   const FrontDev& f = hfr[s];
+   std::vector<int64_t> off(1);
+   CU(cudaMemcpy(off.data(), d_xw_off + s, 8, cudaMemcpyDeviceToHost));
+   if (f.m > f.nelim) CU(cudaMemcpyAsync(d_xw + off[0] + f.nelim, src, 8 * (size_t)(f.m - f.nelim), cudaMemcpyDeviceToDevice, st));
+   CU(cudaStreamSynchronize(st));
+   return 0;
+}
+
+// step 1: permute b in, forward over my leaf parts.  step 2 (root owner): forward, D, backward over
+// the root part.  step 3: take the root part's entries from `src` (the owner's pivot-order vector),
+// then D + backward over my leaf parts.  step 4: scatter my entries to x (zero elsewhere).
+int Numeric::dist_solve(int step, double* d_xio, const double* src) {
+   if (!have) return SSIDS_ERROR_CALL_SEQUENCE;
+   CU(cudaSetDevice(P->device));
+   const int n = P->sym->n, nb = (n + 255) / 256;
+   int64_t nl = 0;
+   int rc = solve_prepare();
+   if (rc) return rc;
+   if (step == 1) {
+      k_permute_in<<<nb, 256, 0, st>>>(d_xio, d_xp, P->d_order, n);
+      sweep_fwd(0, nl);
+   } else if (step == 2) {
+      sweep_fwd(1, nl);
+      sweep_bwd(1, !posdef, nl);
+   } else if (step == 3) {
+      if (src) k_merge_masked<<<nb, 256, 0, st>>>(d_xp, src, d_root_mask, n);
+      sweep_bwd(0, !posdef, nl);
+   } else if (step == 4) {
+      k_permute_out_masked<<<nb, 256, 0, st>>>(d_xio, d_xp, P->d_order, d_mine_mask, n);
+   }
+   CU(cudaStreamSynchronize(st));
+   cudaError_t e = cudaGetLastError();
+   if (e != cudaSuccess) { cuda_err = (int)e; return SSIDS_ERROR_CUDA_UNKNOWN; }
+   return 0;
+}
+
 Numeric* numeric_create(Plan* p) { return new Numeric(p); }
+int numeric_set_partition(Numeric* n, int rank, int nranks) { return n->set_partition(rank, nranks); }
+int numeric_factor_phase(Numeric* n, const double* val, const FactorOptions& o, FactorStats& s, int phase) {
+   int rc = n->factor(val, false, o, s, phase);
+   s.cuda_error = n->cuda_err;
+   return rc;
+}
+int64_t numeric_contrib_bytes(Numeric* n, int node) { return n->contrib_bytes(node); }
+int numeric_contrib_pack(Numeric* n, int node, void* dst) { return n->contrib_pack(node, (char*)dst); }
+int numeric_contrib_unpack(Numeric* n, int node, const void* src, int64_t bytes) { return n->contrib_unpack(node, (const char*)src, bytes); }
+int64_t numeric_xtail_bytes(Numeric* n, int node) { return n->xtail_bytes(node); }
+int numeric_xtail_pack(Numeric* n, int node, void* dst) { return n->xtail_pack(node, (char*)dst); }
+int numeric_xtail_unpack(Numeric* n, int node, const void* src) { return n->xtail_unpack(node, (const char*)src); }
+int numeric_dist_solve(Numeric* n, int step, double* d_x, const double* src) { return n->dist_solve(step, d_x, src); }
+double* numeric_xp(Numeric* n) { return n->d_xp; }
+int numeric_xp_get(Numeric* N, void* d_dst, int n) {
+   cudaSetDevice(N->P->device);
+   return cudaMemcpy(d_dst, N->d_xp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice) == cudaSuccess ? 0 : SSIDS_ERROR_CUDA_UNKNOWN;
+}
 void numeric_destroy(Numeric* n) { delete n; }
 int numeric_factor(Numeric* n, const double* val, bool on_device, const FactorOptions& o, FactorStats& s) {
    int rc = n->factor(val, on_device, o, s);

@@ -51,6 +51,19 @@ int numeric_alter(Numeric*, const double* d);
 bool numeric_is_posdef(const Numeric*);
 bool numeric_has_factors(const Numeric*);
 
+// multi-GPU (one process per GPU): the partition lives in Symbolic (part / exec_loc)
+int numeric_set_partition(Numeric*, int rank, int nranks);
+int numeric_factor_phase(Numeric*, const double* val, const FactorOptions&, FactorStats&, int phase);
+int64_t numeric_contrib_bytes(Numeric*, int node);
+int numeric_contrib_pack(Numeric*, int node, void* d_dst);
+int numeric_contrib_unpack(Numeric*, int node, const void* d_src, int64_t bytes);
+int64_t numeric_xtail_bytes(Numeric*, int node);
+int numeric_xtail_pack(Numeric*, int node, void* d_dst);
+int numeric_xtail_unpack(Numeric*, int node, const void* d_src);
+int numeric_dist_solve(Numeric*, int step, double* d_x, const double* d_src);
+double* numeric_xp(Numeric*);
+int numeric_xp_get(Numeric*, void* d_dst, int n);
+
 // debugging / parity: per-node results copied to the host
 int numeric_node_info(Numeric*, int node, int* m, int* n, int* nelim);
 int numeric_node_copy(Numeric*, int node, double* L /*m*nelim, ld m*/, double* d /*2n*/,

@@ -24,8 +24,8 @@ constexpr int LDB = TN + 4;
 // ------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_diag(FrontDev* fr, const int* list, Params prm, int mode) {
-   FrontDev& f = fr[list[blockIdx.x]];
+__global__ void __launch_bounds__(128) k_diag(FrontDev* fr, const int* list, int slot0, Params prm, int mode) {
+   FrontDev& f = fr[front_slot(list, slot0)];
    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
    const bool new_outer = mode & 1, finish_only = mode & 2;
    __shared__ double sa[NB * LDS], sld[NB * LDS], s0[NB * LDS], sinv[NB * LDS];
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) k_diag(FrontDev* fr, const int* list, Par
    const int fail = f.fail;
    __syncthreads();
    if (w > 0) {
-      const int nelim = compute_nelim(fail, w, f.ibuf + NB);
+      const int nelim = compute_nelim(fail, w, f.p2mask);
       const int nfail = w - nelim;
       done += nelim;
       for (int q = 0; q < nfail; ++q) {
@@ -274,8 +274,10 @@ __global__ void __launch_bounds__(128) k_diag(FrontDev* fr, const int* list, Par
    if (tid < NB) { f.ibuf[tid] = slperm[tid]; f.ibuf[NB + tid] = sptype[tid]; }
    if (tid == 0) {
       int permuted = 0;
-      for (int k = 0; k < w; ++k) if (slperm[k] != k) permuted = 1;
+      unsigned mask = 0;
+      for (int k = 0; k < w; ++k) { if (slperm[k] != k) permuted = 1; if (sptype[k] == 2) mask |= 1u << k; }
       f.ibuf[2 * NB] = permuted;
+      f.p2mask = mask;
    }
 }
 
@@ -284,8 +286,8 @@ __global__ void __launch_bounds__(128) k_diag(FrontDev* fr, const int* list, Par
 // ------------------------------------------------------------------------------------------
 constexpr int AR = 64;    // rows per CTA in k_apply
 
-__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, Params prm) {
-   FrontDev& f = fr[list[blockIdx.x]];
+__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, int slot0, Params prm) {
+   FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0) return;
    const int done = f.done, m = f.m;
@@ -378,13 +380,13 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, Pa
 // K3.  blockIdx.y == 0: the block's own rows, D, pivot lists.  Then cdiv(n,128) chunks for the
 // row permutation of finished columns, then cdiv(m,128) chunks restoring failed columns.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_commit(FrontDev* fr, const int* list, int ncolchunks) {
-   FrontDev& f = fr[list[blockIdx.x]];
+__global__ void __launch_bounds__(128) k_commit(FrontDev* fr, const int* list, int slot0, int ncolchunks) {
+   FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0) return;
    const int done = f.done, m = f.m;
    const int* lperm = f.ibuf;
-   const int nelim = compute_nelim(f.fail, w, f.ibuf + NB);
+   const int nelim = compute_nelim(f.fail, w, f.p2mask);
    const size_t ldl = f.ldl;
    const int y = blockIdx.y;
    if (y == 0) {
@@ -453,11 +455,11 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc,
 // two CTAs per SM.  ncu (profiles/r1_notes.md) showed the kernel bound by per-warp instruction
 // issue around the MMAs, so interior tiles take a path without bounds predicates and with
 // strength-reduced addresses, and tile coordinates advance incrementally.
-__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int mode) {
-   const FrontDev& f = fr[list[blockIdx.x]];
+__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0, int mode) {
+   const FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (f.flag < 0) return;
-   const int nel_cur = w > 0 ? compute_nelim(f.fail, w, f.ibuf + NB) : 0;
+   const int nel_cur = w > 0 ? compute_nelim(f.fail, w, f.p2mask) : 0;
    int k0, kc, cbeg, cend;
    const int m = f.m;
    if (mode == 0) {

@@ -26,13 +26,26 @@ __global__ void k_permute_out(double* __restrict__ x, const double* __restrict__
    if (i < n && order[i] >= 0) x[i] = xp[order[i]];
 }
 
+// multi-GPU: keep only the entries this rank produced (mask[p] != 0 for its pivots), zero elsewhere
+__global__ void k_permute_out_masked(double* __restrict__ x, const double* __restrict__ xp, const int* __restrict__ order,
+                                     const char* __restrict__ mask, int n) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) x[i] = (order[i] >= 0 && mask[order[i]]) ? xp[order[i]] : 0.0;
+}
+// multi-GPU: take the root part's solution entries from the owner's pivot-order vector
+__global__ void k_merge_masked(double* __restrict__ xp, const double* __restrict__ src, const char* __restrict__ mask, int n) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && mask[i]) xp[i] = src[i];
+}
+
 // xw = [b(pivot rows); 0] + sum over children (in child order) of their update vectors
 __global__ void __launch_bounds__(256) k_fwd_gather(const FrontDev* __restrict__ fr, const SlotStatic* __restrict__ ss,
                                                     const int* __restrict__ child_idx, const int* __restrict__ child_doff,
                                                     const int* __restrict__ rel, const int64_t* __restrict__ xw_off,
-                                                    double* XW, double* XA, const double* __restrict__ x, int slot0) {
+                                                    double* XW, double* XA, const double* __restrict__ x, int slot0, int kind) {
    const int s = slot0 + blockIdx.x;
    const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const SlotStatic st = ss[s];
    double* xw = XW + xw_off[s];
    double* acc = XA + xw_off[s];   // indexed by the parent's ASSEMBLY order
@@ -66,9 +79,10 @@ __global__ void __launch_bounds__(256) k_fwd_gather(const FrontDev* __restrict__
 
 // solve the KB x KB unit-lower triangle of block `step`; one CTA per front
 __global__ void __launch_bounds__(256) k_fwd_tri(const FrontDev* __restrict__ fr, const int* __restrict__ list,
-                                                 const int64_t* __restrict__ xw_off, double* XW, int step) {
+                                                 const int64_t* __restrict__ xw_off, double* XW, int step, int kind) {
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const int ne = f.nelim, k0 = step * KB;
    if (k0 >= ne) return;
    const int kb = min(KB, ne - k0);
@@ -112,9 +126,10 @@ __global__ void __launch_bounds__(256) k_fwd_tri(const FrontDev* __restrict__ fr
 
 // xw(r) -= L(r, block) y(block) for the rows below block `step`; RC rows per CTA, 4 threads per row
 __global__ void __launch_bounds__(256) k_fwd_upd(const FrontDev* __restrict__ fr, const int* __restrict__ list,
-                                                 const int64_t* __restrict__ xw_off, double* XW, int step) {
+                                                 const int64_t* __restrict__ xw_off, double* XW, int step, int kind) {
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const int ne = f.nelim, k0 = step * KB;
    if (k0 >= ne) return;
    const int kb = min(KB, ne - k0);
@@ -148,9 +163,10 @@ __global__ void __launch_bounds__(256) k_fwd_upd(const FrontDev* __restrict__ fr
 }
 
 __global__ void __launch_bounds__(256) k_fwd_store(const FrontDev* __restrict__ fr, const int64_t* __restrict__ xw_off,
-                                                   const double* __restrict__ XW, double* x, int slot0, int posdef_scale) {
+                                                   const double* __restrict__ XW, double* x, int slot0, int posdef_scale, int kind) {
    const int s = slot0 + blockIdx.x;
    const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const double* xw = XW + xw_off[s];
    for (int k = threadIdx.x; k < f.nelim; k += blockDim.x) {
       double v = xw[k];
@@ -164,6 +180,7 @@ __global__ void k_solve_diag(const FrontDev* __restrict__ fr, double* x, int nsl
    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    if (s >= nslots) return;
    const FrontDev& f = fr[s];
+   if (f.state != 2) return;
    for (int i = lane; i < f.nelim; i += 32) {
       double a11 = f.D[2 * i];
       if (isinf(a11) && i > 0) continue;
@@ -182,9 +199,10 @@ __global__ void k_solve_diag(const FrontDev* __restrict__ fr, double* x, int nsl
 __global__ void __launch_bounds__(256) k_bwd_gather(const FrontDev* __restrict__ fr, const SlotStatic* __restrict__ ss,
                                                     const int* __restrict__ rlist, const int64_t* __restrict__ xw_off,
                                                     double* XW, const double* __restrict__ x, int slot0, int do_diag,
-                                                    int posdef_scale) {
+                                                    int posdef_scale, int kind) {
    const int s = slot0 + blockIdx.x;
    const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const int* rl = rlist + ss[s].rl_off;
    double* xw = XW + xw_off[s];
    const int m = f.m, ne = f.nelim;
@@ -209,9 +227,10 @@ __global__ void __launch_bounds__(256) k_bwd_gather(const FrontDev* __restrict__
 // PART[front][chunk][j] = sum_{r in chunk} L(r, k0+j) xw(r)
 __global__ void __launch_bounds__(256) k_bwd_dots(const FrontDev* __restrict__ fr, const int* __restrict__ list,
                                                   const int64_t* __restrict__ xw_off, const double* __restrict__ XW,
-                                                  const int64_t* __restrict__ part_off, double* PART, int step) {
+                                                  const int64_t* __restrict__ part_off, double* PART, int step, int kind) {
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const int ne = f.nelim, k0 = step * KB;
    if (k0 >= ne) return;
    const int kb = min(KB, ne - k0);
@@ -242,9 +261,10 @@ __global__ void __launch_bounds__(256) k_bwd_dots(const FrontDev* __restrict__ f
 // x(block) = L(block,block)^{-T} (xw(block) - sum of partial dots); one CTA per front
 __global__ void __launch_bounds__(256) k_bwd_tri(const FrontDev* __restrict__ fr, const int* __restrict__ list,
                                                  const int64_t* __restrict__ xw_off, double* XW,
-                                                 const int64_t* __restrict__ part_off, const double* __restrict__ PART, int step) {
+                                                 const int64_t* __restrict__ part_off, const double* __restrict__ PART, int step, int kind) {
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const int ne = f.nelim, k0 = step * KB;
    if (k0 >= ne) return;
    const int kb = min(KB, ne - k0);
@@ -295,9 +315,10 @@ __global__ void __launch_bounds__(256) k_bwd_tri(const FrontDev* __restrict__ fr
 }
 
 __global__ void __launch_bounds__(256) k_bwd_store(const FrontDev* __restrict__ fr, const int64_t* __restrict__ xw_off,
-                                                   const double* __restrict__ XW, double* x, int slot0) {
+                                                   const double* __restrict__ XW, double* x, int slot0, int kind) {
    const int s = slot0 + blockIdx.x;
    const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const double* xw = XW + xw_off[s];
    for (int k = threadIdx.x; k < f.nelim; k += blockDim.x) x[f.perm[k]] = xw[k];
 }

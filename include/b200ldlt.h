@@ -159,6 +159,31 @@ int b200ldlt_partition(void *akeep, int nranks);
 int b200ldlt_part_info(void *akeep, int part, int *first_node, int *last_node, int *owner,
                        int *dest_node, int64_t *flops);
 
+/* Tree-parallel execution, one process per GPU.  The subtree partition assigns
+ * leaf subtrees to ranks and the rest of the tree (the root part) to rank 0.  Sequence per rank:
+ *   dist_init -> dist_factor(phase 1: my leaf parts) -> for every boundary front: owner packs,
+ *   the host side ships the packed block to rank 0 (NCCL), rank 0 unpacks -> rank 0:
+ *   dist_factor(phase 2: root part).  Solve: dist_solve step 1 (all ranks), x tails of the boundary
+ *   fronts to rank 0, step 2 (rank 0), broadcast of rank 0's pivot-order vector (dist_xp),
+ *   step 3 (all ranks), step 4 + sum over ranks.
+ * The packed boundary block is the wire format of SSIDS's contrib_type (src/ssids/contrib.f90:19-33):
+ * dimensions, delayed pivot list, delayed columns, dense lower contribution block. */
+int b200ldlt_dist_init(void *akeep, void **fkeep, int rank, int nranks, const b200ldlt_options *opt,
+                       b200ldlt_inform *inf);
+int b200ldlt_dist_factor(void *akeep, void *fkeep, int phase, int posdef, const double *val,
+                         const b200ldlt_options *opt, b200ldlt_inform *inf);
+int b200ldlt_dist_nboundary(void *akeep);
+int b200ldlt_dist_boundary(void *akeep, int i, int *node, int *owner);
+int64_t b200ldlt_dist_contrib_bytes(void *fkeep, int node);
+int b200ldlt_dist_contrib_pack(void *fkeep, int node, void *d_dst);
+int b200ldlt_dist_contrib_unpack(void *fkeep, int node, const void *d_src, int64_t bytes);
+int64_t b200ldlt_dist_xtail_bytes(void *fkeep, int node);
+int b200ldlt_dist_xtail_pack(void *fkeep, int node, void *d_dst);
+int b200ldlt_dist_xtail_unpack(void *fkeep, int node, const void *d_src);
+int b200ldlt_dist_solve(void *fkeep, int step, double *d_x, const double *d_src);
+void *b200ldlt_dist_xp(void *fkeep);
+int b200ldlt_dist_xp_get(void *fkeep, void *d_dst, int n);   /* copy the pivot-order vector (device to device) */
+
 /* ---- per-front results, for parity checks against the oracle ---------------------------------- */
 int b200ldlt_node_info(void *fkeep, int node, int *m, int *n, int *nelim);
 int b200ldlt_node_copy(void *fkeep, int node, double *L /* m*nelim */, double *d /* 2n */,

@@ -1,0 +1,29 @@
+"""Multi-GPU check: torchrun --nproc-per-node N tools/dist_check.py [grid]"""
+import os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np, torch, torch.distributed as dist
+from galahad_b200 import problems as P
+from galahad_b200.dist import DistSolver
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29511")
+if "RANK" in os.environ:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank = dist.get_rank() if dist.is_initialized() else 0
+grid = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+kind = sys.argv[2] if len(sys.argv) > 2 else "lap"
+prob = P.laplace_problem(grid) if kind == "lap" else P.kkt_grid_problem(grid)
+ds = DistSolver()
+ds.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"])
+rng = np.random.default_rng(1); xs = rng.uniform(-1, 1, prob["n"])
+b = P.full_from_lower(prob["n"], prob["ptr"], prob["row"], prob["val"]) @ xs
+for rep in range(3):
+    torch.cuda.synchronize(); 
+    if dist.is_initialized(): dist.barrier()
+    t0 = time.time(); flag = ds.factor(prob["val"]); torch.cuda.synchronize(); tf = time.time() - t0
+    t0 = time.time(); x = ds.solve(b); ts = time.time() - t0
+    if rank == 0:
+        print(f"[{ds.world} ranks] {prob['name']} flag {flag} neg {ds.num_neg} (expect {prob['inertia'][1]}) delay {ds.num_delay} "
+              f"boundaries {len(ds.boundaries)} moved {ds.bytes_moved/1e6:.1f} MB factor wall {tf*1e3:.1f} ms "
+              f"(leaves {ds.t_leaves*1e3:.1f} + root {ds.t_root*1e3:.1f}) solve wall {ts*1e3:.1f} ms berr {P.backward_error(prob, x, b):.2e}", flush=True)
+if dist.is_initialized(): dist.destroy_process_group()
