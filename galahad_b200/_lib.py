@@ -244,7 +244,8 @@ class Solver:
         Lm = np.zeros((max(ne, 1), max(m, 1)))
         d = np.zeros(2 * max(n, 1))
         perm = np.zeros(max(n, 1), np.int32)
-        self.L.b200ldlt_node_copy(self.fkeep, i, as_ptr(Lm, C.c_double), as_ptr(d, C.c_double), as_ptr(perm, C.c_int))
+        if self.L.b200ldlt_node_copy(self.fkeep, i, as_ptr(Lm, C.c_double), as_ptr(d, C.c_double), as_ptr(perm, C.c_int)) != 0:
+            return None
         return dict(m=m, n=n, nelim=ne, L=Lm[:ne, :m].T, d=d[:2 * n], perm=perm[:n])
 
     def free(self):

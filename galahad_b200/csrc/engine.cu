@@ -1427,7 +1427,7 @@ int Numeric::dist_solve(int step, double* d_xio, const double* src) {
       sweep_fwd(1, nl);
       sweep_bwd(1, !posdef, nl);
    } else if (step == 3) {
-      if (src) k_merge_masked<<<nb, 256, 0, st>>>(d_xp, src, d_root_mask, n);
+      if (src) k_merge_masked<<<nb, 256, 0, st>>>(d_xp, src, d_mine_mask, n);
       sweep_bwd(0, !posdef, nl);
    } else if (step == 4) {
       k_permute_out_masked<<<nb, 256, 0, st>>>(d_xio, d_xp, P->d_order, d_mine_mask, n);
@@ -1479,6 +1479,7 @@ int numeric_node_copy(Numeric* N, int node, double* L, double* d, int* perm) {
    if (!N->have || node < 0 || node >= N->P->nnodes) return -1;
    cudaSetDevice(N->P->device);
    const FrontDev& f = N->hfr[N->P->node_slot[node]];
+   if (f.state != 2) return -3;      // absent on this rank, or imported (only its trailing block lives here)
    if (L && f.nelim > 0)
       if (cudaMemcpy2D(L, sizeof(double) * f.m, f.L, sizeof(double) * f.ldl, sizeof(double) * f.m, f.nelim, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
    if (d && f.n > 0 && cudaMemcpy(d, f.D, sizeof(double) * 2 * f.n, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;

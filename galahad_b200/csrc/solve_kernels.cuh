@@ -33,9 +33,9 @@ __global__ void k_permute_out_masked(double* __restrict__ x, const double* __res
    if (i < n) x[i] = (order[i] >= 0 && mask[order[i]]) ? xp[order[i]] : 0.0;
 }
 // multi-GPU: take the root part's solution entries from the owner's pivot-order vector
-__global__ void k_merge_masked(double* __restrict__ xp, const double* __restrict__ src, const char* __restrict__ mask, int n) {
+__global__ void k_merge_masked(double* __restrict__ xp, const double* __restrict__ src, const char* __restrict__ mine, int n) {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n && mask[i]) xp[i] = src[i];
+   if (i < n && !mine[i]) xp[i] = src[i];   // everything this rank did not eliminate itself (its ancestors are among them)
 }
 
 // xw = [b(pivot rows); 0] + sum over children (in child order) of their update vectors

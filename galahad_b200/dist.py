@@ -34,6 +34,7 @@ def exchange_to_root(items, rank, nbytes_fn, pack_fn, unpack_fn, device, root=0)
             nb = int(sz.item())
             buf = torch.empty(max(nb, 1), dtype=torch.uint8, device=device)
             dist.recv(buf, src=owner)
+            torch.cuda.synchronize(device) if buf.is_cuda else None   # NCCL is async; the engine reads on its own stream
             unpack_fn(key, buf, nb)
             moved += nb
     return moved
@@ -97,6 +98,7 @@ class DistSolver:
     def solve(self, b):
         s = self.s
         x = torch.from_numpy(np.ascontiguousarray(b, np.float64)).to(self.device)
+        torch.cuda.synchronize(self.device)
         f = s.L.b200ldlt_dist_solve(s.fkeep, 1, C.c_void_p(x.data_ptr()), None)
         assert f >= 0, f
         exchange_to_root(
@@ -109,9 +111,11 @@ class DistSolver:
         if self.rank == 0:
             f = s.L.b200ldlt_dist_solve(s.fkeep, 2, C.c_void_p(x.data_ptr()), None)
             assert f >= 0, f
+            torch.cuda.synchronize(self.device)
             s.L.b200ldlt_dist_xp_get(s.fkeep, C.c_void_p(xp.data_ptr()), self.n)
         if self.world > 1:
             dist.broadcast(xp, src=0)
+            torch.cuda.synchronize(self.device)
         src = None if self.rank == 0 else C.c_void_p(xp.data_ptr())
         f = s.L.b200ldlt_dist_solve(s.fkeep, 3, C.c_void_p(x.data_ptr()), src)
         assert f >= 0, f

@@ -1,0 +1,109 @@
+"""Host-side logic of the multi-GPU path on CPU: the subtree partition (after
+find_subtree_partition, src/ssids/anal.f90:284-459) and the boundary exchange schedule of
+galahad_b200/dist.py, the latter over a world_size-2 gloo group with a mock engine."""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from galahad_b200 import problems as P
+from galahad_b200._lib import Solver
+
+
+def parts_of(s, nranks):
+    np_ = s.L.b200ldlt_partition(s.akeep, nranks)
+    out = []
+    for p in range(np_):
+        a, b, o, d, fl = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        s.L.b200ldlt_part_info(s.akeep, p, C.byref(a), C.byref(b), C.byref(o), C.byref(d), C.byref(fl))
+        out.append((a.value, b.value, o.value, d.value, fl.value))
+    return out
+
+
+def test_partition_invariants():
+    prob = P.laplace_problem(16)
+    s = Solver()
+    assert s.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"]) == 0
+    nt = s.numeric_tree()
+    nn, par = nt["nnodes"], nt["sparent"]
+    for nranks in (1, 2, 4, 8):
+        parts = parts_of(s, nranks)
+        # contiguous cover of all nodes
+        assert parts[0][0] == 0 and parts[-1][1] == nn - 1
+        assert all(parts[i][1] + 1 == parts[i + 1][0] for i in range(len(parts) - 1))
+        owner = np.full(nn, -9)
+        for a, b, o, d, fl in parts:
+            assert -1 <= o < nranks
+            owner[a:b + 1] = o
+        for a, b, o, d, fl in parts:
+            if o >= 0:
+                # a leaf part is a complete subtree: every node's parent is inside it, except the root's
+                for node in range(a, b):
+                    assert a <= par[node] <= b
+                assert d == (par[b] if par[b] < nn else -1)
+                if d >= 0:
+                    assert owner[d] == -1                      # it contributes into the root part
+        # the root part is closed upwards
+        for node in range(nn):
+            if owner[node] == -1 and par[node] < nn:
+                assert owner[par[node]] == -1
+        if nranks > 1:
+            loads = np.zeros(nranks)
+            for a, b, o, d, fl in parts:
+                if o >= 0:
+                    loads[o] += fl
+            # the partitioner minimises max(leaf load) + root-part flops (the root part is serial on
+            # its owner), so with many ranks it may leave devices idle rather than grow the root part
+            busy = loads[loads > 0]
+            assert busy.size >= 2
+            total = loads.sum() + sum(fl for a, b, o, d, fl in parts if o < 0)
+            assert loads.max() + (total - loads.sum()) < total   # estimated makespan beats one device
+        # boundary list = roots of leaf parts with a parent
+        nb = s.L.b200ldlt_dist_nboundary(s.akeep)
+        assert nb == sum(1 for a, b, o, d, fl in parts if o >= 0 and d >= 0)
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from galahad_b200.dist import exchange_to_root
+    items = [(10, 1), (11, 0), (12, 1), (13, 1)]            # (key, owner)
+    payload = {k: np.arange(k * 3, dtype=np.uint8) for k, _ in items}
+    got = {}
+
+    def nbytes(k):
+        return payload[k].size
+
+    def pack(k, buf):
+        buf.copy_(torch.from_numpy(payload[k]))
+
+    def unpack(k, buf, nb):
+        got[k] = buf[:nb].numpy().copy()
+
+    moved = exchange_to_root(items, rank, nbytes, pack, unpack, torch.device("cpu"))
+    if rank == 0:
+        ok = sorted(got) == [10, 12, 13] and all((got[k] == payload[k]).all() for k in got) and moved == 30 + 36 + 39
+    else:
+        ok = moved == 30 + 36 + 39 and not got
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t)
+    if rank == 0:
+        q.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+def test_exchange_schedule_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == 2
