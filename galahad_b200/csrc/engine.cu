@@ -983,7 +983,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                for (int q = 0; q < na; ++q) if (active[order[i0 + q]]) maxw_outer = std::max(maxw_outer, std::min(NBO, hfr[order[i0 + q]].n - ob * NBO));
                const int ninner = (maxw_outer + NB - 1) / NB;
                for (int j = 0; j < ninner; ++j) {
-                  k_diag<<<na, 128, 0, st>>>(d_fr, lst, b0, prm, j == 0 ? 1 : 0);
+                  k_diag<<<na, 32, 0, st>>>(d_fr, lst, b0, prm, j == 0 ? 1 : 0);
                   k_apply<<<dim3(na, yapply), 256, 0, st>>>(d_fr, lst, b0, prm);
                   k_commit<<<dim3(na, ycommit), 128, 0, st>>>(d_fr, lst, b0, ncolchunks);
                   launches += 3;
@@ -1027,7 +1027,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   ++launches;
                }
             }
-            k_diag<<<i1 - i0, 128, 0, st>>>(d_fr, lst, b0, prm, 2);
+            k_diag<<<i1 - i0, 32, 0, st>>>(d_fr, lst, b0, prm, 2);
             ++launches;
             i0 = i1;
          }
@@ -1062,14 +1062,14 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * nt, cudaMemcpyHostToDevice, st));
          const int ncolchunks = (maxn + 127) / 128;
          for (int j = 0; j < NBO / NB; ++j) {
-            k_diag<<<nt, 128, 0, st>>>(d_fr, d_list, 0, prm, j == 0 ? 1 : 0);
+            k_diag<<<nt, 32, 0, st>>>(d_fr, d_list, 0, prm, j == 0 ? 1 : 0);
             k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, 0, st>>>(d_fr, d_list, 0, prm);
             k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 127) / 128), 128, 0, st>>>(d_fr, d_list, 0, ncolchunks);
             k_update<<<dim3(nt, std::max(1, std::min((maxm + TM - 1) / TM, 64))), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, 0);
             launches += 4;
          }
          k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, 1);
-         k_diag<<<nt, 128, 0, st>>>(d_fr, d_list, 0, prm, 2);
+         k_diag<<<nt, 32, 0, st>>>(d_fr, d_list, 0, prm, 2);
          launches += 2;
          if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
          if (flag < 0) break;

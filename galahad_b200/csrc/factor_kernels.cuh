@@ -24,19 +24,38 @@ constexpr int LDB = TN + 4;
 // ------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_diag(FrontDev* fr, const int* list, int slot0, Params prm, int mode) {
+// One warp per front; lane r keeps row r of the (full, symmetric) block in registers, so a pivot
+// step is a register scan, two warp reductions, one shared-memory broadcast of the pivot column
+// and 32 FMAs -- no block barriers (the 128/256-thread shared-memory versions spent 2400 cycles
+// per pivot in barrier / dependent-issue stalls, profiles/r1_notes.md).  Rows and columns are
+// never moved: eliminated indices leave the `alive` mask and the pivot sequence is recorded.
+__device__ __forceinline__ double pick32(const double (&a)[NB], int q) {
+   switch (q) {   // q is warp-uniform: one indirect branch
+#define B200_PICK(i) case i: return a[i];
+      B200_PICK(0) B200_PICK(1) B200_PICK(2) B200_PICK(3) B200_PICK(4) B200_PICK(5) B200_PICK(6) B200_PICK(7)
+      B200_PICK(8) B200_PICK(9) B200_PICK(10) B200_PICK(11) B200_PICK(12) B200_PICK(13) B200_PICK(14) B200_PICK(15)
+      B200_PICK(16) B200_PICK(17) B200_PICK(18) B200_PICK(19) B200_PICK(20) B200_PICK(21) B200_PICK(22) B200_PICK(23)
+      B200_PICK(24) B200_PICK(25) B200_PICK(26) B200_PICK(27) B200_PICK(28) B200_PICK(29) B200_PICK(30) B200_PICK(31)
+#undef B200_PICK
+   }
+   return 0.0;
+}
+
+__global__ void __launch_bounds__(32) k_diag(FrontDev* fr, const int* list, int slot0, Params prm, int mode) {
    FrontDev& f = fr[front_slot(list, slot0)];
-   const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
+   const int lane = threadIdx.x;
    const bool new_outer = mode & 1, finish_only = mode & 2;
-   __shared__ double sa[NB * LDS], sld[NB * LDS], s0[NB * LDS], sinv[NB * LDS];
+   __shared__ double s0[NB * LDS];          // original block, full symmetric
+   __shared__ double sLc[NB * LDS];         // sLc[r + k*LDS]: multiplier of (original) row r for pivot k
+   __shared__ double sLd[NB][NB];           // sLd[k][r]: the same times D (pivot column before scaling), contiguous per pivot
+   __shared__ double sL[NB * LDS], sinv[NB * LDS];   // L11 in pivot order and its inverse
    __shared__ double sd[2 * NB + 2];
-   __shared__ unsigned long long skey[4];
-   __shared__ int sptype[NB], slperm[NB];
+   __shared__ int sptype[NB], spord[NB];
 
    if (f.flag < 0) return;
    int done = f.done, oend = f.oend, gend = f.gend, w = f.w, jstart = f.jstart, jend0 = f.jend0;
    const int fail = f.fail;
-   __syncthreads();
+   __syncwarp();
    if (w > 0) {
       const int nelim = compute_nelim(fail, w, f.p2mask);
       const int nfail = w - nelim;
@@ -47,7 +66,7 @@ __global__ void __launch_bounds__(128) k_diag(FrontDev* fr, const int* list, int
       }
       oend -= nfail;
       if (prm.posdef && nfail > 0) {
-         if (tid == 0) { f.flag = SSIDS_ERROR_NOT_POS_DEF; f.w = 0; }
+         if (lane == 0) { f.flag = SSIDS_ERROR_NOT_POS_DEF; f.w = 0; }
          return;
       }
    }
@@ -65,189 +84,165 @@ __global__ void __launch_bounds__(128) k_diag(FrontDev* fr, const int* list, int
    w = min(NB, oend - done);
    if (w < 0) w = 0;
    if (finish_only) w = 0;
-   __syncthreads();
-   if (tid == 0) {
+   __syncwarp();
+   if (lane == 0) {
       f.done = done; f.oend = oend; f.gend = gend; f.jstart = jstart; f.jend0 = jend0;
       f.w = w; f.fail = w; f.nelim = done;
    }
    if (w == 0) return;
 
+   // load: coalesced lower triangle -> shared (both triangles), then one row per lane
    {
-      // block load: 8 independent global loads per thread, then shared stores (full symmetric)
-      double v8[8];
+      const double* Lb = f.L + (size_t)done * f.ldl + done + lane;
+      double v[NB];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-         int i = tid + q * 128, r = i & 31, c = i >> 5;
-         v8[q] = (r >= c && r < w) ? f.L[(size_t)(done + c) * f.ldl + done + r] : 0.0;
-      }
-      for (int i = tid; i < NB * LDS; i += 128) { sld[i] = 0.0; sinv[i] = 0.0; }
+      for (int c = 0; c < NB; ++c) v[c] = (c < w && lane >= c && lane < w) ? Lb[(size_t)c * f.ldl] : 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-         int i = tid + q * 128, r = i & 31, c = i >> 5;
-         if (r >= c) { sa[r + c * LDS] = v8[q]; sa[c + r * LDS] = v8[q]; s0[r + c * LDS] = v8[q]; s0[c + r * LDS] = v8[q]; }
+      for (int c = 0; c < NB; ++c) {
+         if (lane >= c) { s0[lane + c * LDS] = v[c]; s0[c + lane * LDS] = v[c]; }
+         sLc[lane + c * LDS] = 0.0;
+         sLd[c][lane] = 0.0;
       }
    }
-   __syncthreads();
-   if (tid < NB) { slperm[tid] = tid; sptype[tid] = 0; sinv[tid + tid * LDS] = 1.0; }
-   for (int i = tid; i < 2 * NB + 2; i += 128) sd[i] = 0.0;
-   __syncthreads();
-
-   int err = 0;
-   const int c0 = grp * 8;      // this thread's 8 columns; its row is `lane`
-   for (int p = 0; p < w;) {
-      int t = p, mm = p, pivsiz = 1;
-      double a11 = 0, a21 = 0, a22 = 0, detscale = 0, detpiv = 0;
+   for (int i = lane; i < 2 * NB + 2; i += 32) sd[i] = 0.0;
+   sptype[lane] = 0;
+   spord[lane] = lane;
+   __syncwarp();
+   double a[NB];
+#pragma unroll
+   for (int c = 0; c < NB; ++c) a[c] = s0[lane + c * LDS];
+   double dg = s0[lane + lane * LDS];
+   unsigned alive = (w == NB) ? 0xffffffffu : ((1u << w) - 1u);
+   int np = 0, err = 0;
+   while (alive) {
+      int q1, q2 = -1;
+      double d11 = 0.0, d21 = 0.0, d22 = 0.0;
       if (prm.posdef) {
-         a11 = sa[p + p * LDS];
+         q1 = __ffs(alive) - 1;
+         const double a11 = __shfl_sync(0xffffffffu, dg, q1);
          if (!(a11 > 0.0)) { err = SSIDS_ERROR_NOT_POS_DEF; break; }
+         d11 = 1.0 / a11;
       } else {
-         // argmax |a(r,c)| over the remaining lower triangle with one 64-bit integer key per
-         // candidate: the bit pattern of |v| (monotone for non-negative doubles) with its low 10
-         // bits replaced by 1023 - (c*32 + r), so that ties go to the smallest column, then row
-         unsigned long long key = 0ull;
-         if (lane >= p && lane < w) {
+         // largest |a(r,c)| over the alive rows / columns; compared on the high word of the double
+         // (sign cleared): resolution 2^-20, ties -> smallest column, then row
+         unsigned bk = 0;
+         double bv = 0.0;
+         int bc = lane;
+         const bool rowalive = (alive >> lane) & 1u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-               int c = c0 + j;
-               if (c >= p && c <= lane) {
-                  unsigned long long kk = ((unsigned long long)__double_as_longlong(fabs(sa[lane + c * LDS])) & ~0x3FFull) |
-                                          (unsigned long long)(1023 - (c * 32 + lane));
-                  key = kk > key ? kk : key;
-               }
+         for (int c = 0; c < NB; ++c) {
+            if ((alive >> c) & 1u) {
+               const unsigned k = (unsigned)__double2hiint(a[c]) & 0x7fffffffu;
+               if (k > bk) { bk = k; bv = a[c]; bc = c; }
             }
          }
-         {
-            unsigned hi = (unsigned)(key >> 32);
-            unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-            unsigned lo = (hi == mhi) ? (unsigned)key : 0u;
-            unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
-            key = ((unsigned long long)mhi << 32) | mlo;
-         }
-         if (lane == 0) skey[grp] = key;
-         __syncthreads();                                             // B1
-         key = skey[0];
-#pragma unroll
-         for (int g = 1; g < 4; ++g) { unsigned long long ok = skey[g]; key = ok > key ? ok : key; }
-         const double best = __longlong_as_double((long long)(key & ~0x3FFull));
-         {
-            int idx = 1023 - (int)(key & 0x3FFull);
-            t = idx & 31;
-            mm = idx >> 5;
-         }
-         if (best < prm.small_) {
+         if (!rowalive) bk = 0;
+         const unsigned mk = __reduce_max_sync(0xffffffffu, bk);
+         const int lo = min(lane, bc), hi = max(lane, bc);
+         const unsigned idx = (rowalive && bk == mk) ? (unsigned)(lo * 32 + hi) : 0xffffu;
+         const unsigned mi = __reduce_min_sync(0xffffffffu, idx);
+         const int mm = (int)(mi >> 5), t = (int)(mi & 31u);
+         const int wl = __ffs(__ballot_sync(0xffffffffu, idx == mi)) - 1;
+         const double a21 = __shfl_sync(0xffffffffu, bv, wl);
+         if (fabs(a21) < prm.small_) {
             if (!prm.action) { err = SSIDS_ERROR_SINGULAR; break; }
-            __syncthreads();
-            for (int i = tid; i < NB * NB; i += 128) {
-               int r = i & 31, c = i >> 5;
-               if (r >= p && c >= p && r < w && c < w) { sa[r + c * LDS] = 0.0; }
-               if (r >= c && c >= p && r < w) sld[r + c * LDS] = 0.0;
+            // everything left is numerically zero: record zero pivots (block_ldlt.hxx:303-318)
+            while (alive) {
+               const int q = __ffs(alive) - 1;
+               if (lane == 0) { spord[np] = q; sptype[np] = 0; sd[2 * np] = 0.0; sd[2 * np + 1] = 0.0; }
+               alive &= ~(1u << q);
+               ++np;
             }
-            if (tid >= p && tid < w) { sd[2 * tid] = 0.0; sd[2 * tid + 1] = 0.0; sptype[tid] = 0; }
-            __syncthreads();
             break;
          }
+         const double a11 = __shfl_sync(0xffffffffu, dg, mm), a22 = __shfl_sync(0xffffffffu, dg, t);
          if (t == mm) {
-            pivsiz = 1;
-            a11 = sa[t + t * LDS];
+            q1 = t;
+            d11 = 1.0 / a11;
          } else {
-            a11 = sa[mm + mm * LDS];
-            a22 = sa[t + t * LDS];
-            a21 = sa[t + mm * LDS];
-            detscale = 1.0 / fabs(a21);
-            detpiv = (a11 * detscale) * a22 - fabs(a21);
+            const double detscale = 1.0 / fabs(a21);
+            const double detpiv = (a11 * detscale) * a22 - fabs(a21);
             if (fabs(detpiv) >= fabs(a21) / 2) {
-               pivsiz = 2;
+               q1 = mm; q2 = t;
+               d11 = (a22 * detscale) / detpiv;
+               d22 = (a11 * detscale) / detpiv;
+               d21 = (-a21 * detscale) / detpiv;
             } else if (fabs(a11) > fabs(a22)) {
-               pivsiz = 1; t = mm;
+               q1 = mm; d11 = 1.0 / a11;
             } else {
-               pivsiz = 1; a11 = a22; mm = t;
+               q1 = t; d11 = 1.0 / a22;
             }
          }
       }
-      // symmetric swaps bringing the pivot(s) to p (and p+1); sinv follows (M' = P M P^T)
-      for (int i = 0; i < pivsiz; ++i) {
-         const int dst = p + i;
-         const int src = (pivsiz == 1) ? t : (i == 0 ? mm : t);
-         if (src != dst) {
-            __syncthreads();     // every thread is done reading the pivot entries
-            if (tid < NB) {
-               double s = sa[dst + tid * LDS]; sa[dst + tid * LDS] = sa[src + tid * LDS]; sa[src + tid * LDS] = s;
-            } else if (tid < 2 * NB) {
-               int q = tid - NB;
-               double s = sinv[dst + q * LDS]; sinv[dst + q * LDS] = sinv[src + q * LDS]; sinv[src + q * LDS] = s;
-            } else if (tid < 3 * NB) {
-               int q = tid - 2 * NB;
-               if (q < p) { double s = sld[dst + q * LDS]; sld[dst + q * LDS] = sld[src + q * LDS]; sld[src + q * LDS] = s; }
-            } else if (tid == 3 * NB) {
-               int q = slperm[dst]; slperm[dst] = slperm[src]; slperm[src] = q;
-            }
-            __syncthreads();
-            if (tid < NB) {
-               double s = sa[tid + dst * LDS]; sa[tid + dst * LDS] = sa[tid + src * LDS]; sa[tid + src * LDS] = s;
-            } else if (tid < 2 * NB) {
-               int q = tid - NB;
-               double s = sinv[q + dst * LDS]; sinv[q + dst * LDS] = sinv[q + src * LDS]; sinv[q + src * LDS] = s;
-            }
-            __syncthreads();
-         }
-      }
-      if (pivsiz == 1) {
-         const double d11 = 1.0 / sa[p + p * LDS];
-         if (tid > p && tid < w) {
-            double ldr = sa[tid + p * LDS];
-            sld[tid + p * LDS] = ldr;
-            sa[tid + p * LDS] = ldr * d11;
-         }
-         __syncthreads();                                             // B2
-         if (lane > p && lane < w) {
-            const double lr = sa[lane + p * LDS];
+      if (q2 < 0) {
+         alive &= ~(1u << q1);
+         const bool upd = (alive >> lane) & 1u;
+         const double ldr = upd ? pick32(a, q1) : 0.0;
+         const double l = ldr * d11;
+         sLd[np][lane] = ldr;
+         sLc[lane + np * LDS] = l;
+         __syncwarp();
+         const double2* ldv = reinterpret_cast<const double2*>(&sLd[np][0]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-               int c = c0 + j;
-               if (c > p) { if (c < w) sa[lane + c * LDS] -= lr * sld[c + p * LDS]; }
-               else sinv[lane + c * LDS] -= lr * sinv[p + c * LDS];
-            }
+         for (int c2 = 0; c2 < NB / 2; ++c2) {
+            const double2 v = ldv[c2];
+            a[2 * c2] -= l * v.x;
+            a[2 * c2 + 1] -= l * v.y;
          }
-         if (tid == 0) { sd[2 * p] = d11; sd[2 * p + 1] = 0.0; sptype[p] = 0; sa[p + p * LDS] = 1.0; }
-         if (tid > p && tid < w) sa[p + tid * LDS] = 0.0;
-         p += 1;
+         dg -= l * ldr;
+         if (lane == 0) { spord[np] = q1; sptype[np] = 0; sd[2 * np] = d11; sd[2 * np + 1] = 0.0; }
+         np += 1;
       } else {
-         const double d11 = (a22 * detscale) / detpiv, d22 = (a11 * detscale) / detpiv;
-         const double d21 = (-a21 * detscale) / detpiv;
-         if (tid > p + 1 && tid < w) {
-            double w1 = sa[tid + p * LDS], w2 = sa[tid + (p + 1) * LDS];
-            sld[tid + p * LDS] = w1;
-            sld[tid + (p + 1) * LDS] = w2;
-            sa[tid + p * LDS] = d11 * w1 + d21 * w2;
-            sa[tid + (p + 1) * LDS] = d21 * w1 + d22 * w2;
-         }
-         __syncthreads();                                             // B2
-         if (lane > p + 1 && lane < w) {
-            const double l1 = sa[lane + p * LDS], l2 = sa[lane + (p + 1) * LDS];
+         alive &= ~((1u << q1) | (1u << q2));
+         const bool upd = (alive >> lane) & 1u;
+         const double w1 = upd ? pick32(a, q1) : 0.0, w2 = upd ? pick32(a, q2) : 0.0;
+         const double l1 = d11 * w1 + d21 * w2, l2 = d21 * w1 + d22 * w2;
+         sLd[np][lane] = w1;
+         sLd[np + 1][lane] = w2;
+         sLc[lane + np * LDS] = l1;
+         sLc[lane + (np + 1) * LDS] = l2;
+         __syncwarp();
+         const double2* ldv1 = reinterpret_cast<const double2*>(&sLd[np][0]);
+         const double2* ldv2 = reinterpret_cast<const double2*>(&sLd[np + 1][0]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-               int c = c0 + j;
-               if (c > p + 1) { if (c < w) sa[lane + c * LDS] -= l1 * sld[c + p * LDS] + l2 * sld[c + (p + 1) * LDS]; }
-               else sinv[lane + c * LDS] -= l1 * sinv[p + c * LDS] + l2 * sinv[p + 1 + c * LDS];
-            }
+         for (int c2 = 0; c2 < NB / 2; ++c2) {
+            const double2 v1 = ldv1[c2], v2 = ldv2[c2];
+            a[2 * c2] -= l1 * v1.x + l2 * v2.x;
+            a[2 * c2 + 1] -= l1 * v1.y + l2 * v2.y;
          }
-         if (tid == 0) {
-            sd[2 * p] = d11; sd[2 * p + 1] = d21; sd[2 * p + 2] = DINF; sd[2 * p + 3] = d22;
-            sptype[p] = 1; sptype[p + 1] = 2;
-            sa[p + p * LDS] = 1.0; sa[p + 1 + p * LDS] = 0.0; sa[p + (p + 1) * LDS] = 0.0;
-            sa[p + 1 + (p + 1) * LDS] = 1.0;
-            sld[p + 1 + p * LDS] = 0.0;
+         dg -= l1 * w1 + l2 * w2;
+         if (lane == 0) {
+            spord[np] = q1; spord[np + 1] = q2;
+            sptype[np] = 1; sptype[np + 1] = 2;
+            sd[2 * np] = d11; sd[2 * np + 1] = d21; sd[2 * np + 2] = DINF; sd[2 * np + 3] = d22;
          }
-         if (tid > p + 1 && tid < w) { sa[p + tid * LDS] = 0.0; sa[p + 1 + tid * LDS] = 0.0; }
-         p += 2;
+         np += 2;
       }
-      __syncthreads();                                                // B3
    }
    if (err) {
-      if (tid == 0) { f.flag = err; f.w = 0; }
+      if (lane == 0) { f.flag = err; f.w = 0; }
       return;
    }
-   __syncthreads();
+   __syncwarp();
+   // L11 in pivot order (unit lower), then its inverse: lane j solves L11 z = e_j
+#pragma unroll 4
+   for (int k = 0; k < NB; ++k) {
+      double lv = 0.0;
+      if (lane < w && k < w) lv = lane > k ? sLc[spord[lane] + k * LDS] : (lane == k ? 1.0 : 0.0);
+      sL[lane + k * LDS] = lv;
+      sinv[lane + k * LDS] = 0.0;
+   }
+   __syncwarp();
+   if (lane < w) {
+      const int j = lane;
+      sinv[j + j * LDS] = 1.0;
+      for (int i = j + 1; i < w; ++i) {
+         double s = 0.0;
+         for (int t = j; t < i; ++t) s += sL[i + t * LDS] * sinv[t + j * LDS];
+         sinv[i + j * LDS] = -s;
+      }
+   }
+   __syncwarp();
    // publish
    double* L11 = f.dbuf;
    double* LD11 = f.dbuf + NB * NB;
@@ -255,29 +250,27 @@ __global__ void __launch_bounds__(128) k_diag(FrontDev* fr, const int* list, int
    double* Linv = f.dbuf + 3 * NB * NB;      // row-major: Linv[k*NB + i] = (L11^{-1})(k,i)
    double* dk = f.dbuf + 4 * NB * NB;
    const int kofs = done - jstart;
-   for (int idx = tid; idx < NB * NB; idx += 128) {
-      const int i = idx & 31, k = idx >> 5;
+   const int pl = spord[lane];
+   for (int k = 0; k < NB; ++k) {
+      const int i = lane;
       if (i < w && k < w) {
-         double lv = i > k ? sa[i + k * LDS] : (i == k ? 1.0 : 0.0);
-         double ldv = i > k ? sld[i + k * LDS] : 0.0;
-         L11[i + k * NB] = lv;
+         const double ldv = i > k ? sLd[k][pl] : 0.0;
+         L11[i + k * NB] = sL[i + k * LDS];
          LD11[i + k * NB] = ldv;
-         A0p[i + k * NB] = s0[slperm[i] + slperm[k] * LDS];
+         A0p[i + k * NB] = s0[pl + spord[k] * LDS];
          f.Wld[(size_t)(kofs + k) * f.ldl + done + i] = ldv;
       }
-      {
-         const int kk = idx & 31, ii = idx >> 5;
-         Linv[kk * NB + ii] = (kk < w && ii <= kk) ? sinv[kk + ii * LDS] : 0.0;
-      }
+      // Linv row k, column `lane`
+      Linv[k * NB + lane] = (k < w && lane <= k) ? sinv[k + lane * LDS] : 0.0;
    }
-   for (int i = tid; i < 2 * NB + 2; i += 128) dk[i] = sd[i];
-   if (tid < NB) { f.ibuf[tid] = slperm[tid]; f.ibuf[NB + tid] = sptype[tid]; }
-   if (tid == 0) {
-      int permuted = 0;
-      unsigned mask = 0;
-      for (int k = 0; k < w; ++k) { if (slperm[k] != k) permuted = 1; if (sptype[k] == 2) mask |= 1u << k; }
-      f.ibuf[2 * NB] = permuted;
-      f.p2mask = mask;
+   for (int i = lane; i < 2 * NB + 2; i += 32) dk[i] = sd[i];
+   f.ibuf[lane] = spord[lane];
+   f.ibuf[NB + lane] = sptype[lane];
+   {
+      const bool moved = lane < w && spord[lane] != lane;
+      const bool second = lane < w && sptype[lane] == 2;
+      const unsigned pm = __ballot_sync(0xffffffffu, moved), m2 = __ballot_sync(0xffffffffu, second);
+      if (lane == 0) { f.ibuf[2 * NB] = pm != 0; f.p2mask = m2; }
    }
 }
 
