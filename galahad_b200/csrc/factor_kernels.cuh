@@ -124,26 +124,25 @@ __global__ void __launch_bounds__(32) k_diag(FrontDev* fr, const int* list, int 
          d11 = 1.0 / a11;
       } else {
          // largest |a(r,c)| over the alive rows / columns; compared on the high word of the double
-         // (sign cleared): resolution 2^-20, ties -> smallest column, then row
-         unsigned bk = 0;
-         double bv = 0.0;
-         int bc = lane;
+         // (sign cleared, 15 mantissa bits): ties -> smallest column, then row
+         // per-lane keys (|a| high word with the low 5 bits replaced by 31-c), reduced by a max tree
          const bool rowalive = (alive >> lane) & 1u;
+         unsigned kb[NB];
 #pragma unroll
-         for (int c = 0; c < NB; ++c) {
-            if ((alive >> c) & 1u) {
-               const unsigned k = (unsigned)__double2hiint(a[c]) & 0x7fffffffu;
-               if (k > bk) { bk = k; bv = a[c]; bc = c; }
-            }
-         }
-         if (!rowalive) bk = 0;
-         const unsigned mk = __reduce_max_sync(0xffffffffu, bk);
+         for (int c = 0; c < NB; ++c)
+            kb[c] = ((alive >> c) & 1u) ? ((((unsigned)__double2hiint(a[c])) & 0x7fffffe0u) | (unsigned)(31 - c)) : 0u;
+#pragma unroll
+         for (int st = NB / 2; st > 0; st >>= 1)
+#pragma unroll
+            for (int c = 0; c < st; ++c) kb[c] = max(kb[c], kb[c + st]);
+         const unsigned bk = rowalive ? kb[0] : 0u;
+         const int bc = 31 - (int)(bk & 31u);
+         const unsigned mk = __reduce_max_sync(0xffffffffu, bk & ~31u);
          const int lo = min(lane, bc), hi = max(lane, bc);
-         const unsigned idx = (rowalive && bk == mk) ? (unsigned)(lo * 32 + hi) : 0xffffu;
+         const unsigned idx = (rowalive && (bk & ~31u) == mk) ? (unsigned)(lo * 32 + hi) : 0xffffu;
          const unsigned mi = __reduce_min_sync(0xffffffffu, idx);
          const int mm = (int)(mi >> 5), t = (int)(mi & 31u);
-         const int wl = __ffs(__ballot_sync(0xffffffffu, idx == mi)) - 1;
-         const double a21 = __shfl_sync(0xffffffffu, bv, wl);
+         const double a21 = __shfl_sync(0xffffffffu, pick32(a, mm), t);   // A(t, mm)
          if (fabs(a21) < prm.small_) {
             if (!prm.action) { err = SSIDS_ERROR_SINGULAR; break; }
             // everything left is numerically zero: record zero pivots (block_ldlt.hxx:303-318)
