@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -27,8 +28,8 @@
 
 namespace b200 {
 
-constexpr int NB = 32;          // panel width
-constexpr int NBO = 128;        // outer block: columns eliminated between two full trailing updates
+constexpr int NB = 32;          // sub-panel width: complete pivoting inside 32x32 diagonal sub-blocks
+constexpr int PB = 128;         // block: columns eliminated between two trailing updates
 constexpr int LDS = NB + 1;     // padded shared leading dimension
 constexpr int EA_TR = 256;      // extend-add tile rows
 constexpr int EA_TC = 8;        // extend-add tile cols
@@ -40,23 +41,21 @@ struct FrontDev {
    double* D;
    int* perm;
    int* orig;      // orig[r] = local index variable r had when the front was assembled (r < n)
-   double* Wld;    // m x NBO  L*D of the current outer block (front-row indexed)
-   double* Wo;     // m x NB   permuted original panel (restore on failure)
-   double* dbuf;   // L11[NB*NB] | LD11[NB*NB] | A0p[NB*NB] | Linv[NB*NB] | dk[2*NB+2]
-   int* ibuf;      // lperm[NB] | ptype[NB] | permuted
+   double* Wld;    // ldl x wc  L*D of the current block (front-row indexed)
+   double* Wo;     // ldl x wc  permuted original columns of the block (restore on failure)
+   double* dbuf;   // L11[PB*wc] | A0[PB*wc] | dk[2*PB+2]
+   int* ibuf;      // lperm[PB] | ptype[PB] | permuted
    int m, n, ldl, ldc;
    int ncol, nrow, ndelay_in, first_piv;
    int done;       // columns eliminated so far (L columns [0,done) are final)
-   int oend;       // candidates of the current outer block are [done, oend)
    int gend;       // candidates of the front are [done, gend); [gend, n) failed this pass
-   int w, fail;    // current panel width, first failed column of the panel (atomicMin)
-   int jstart, jend0;   // current outer block [jstart, jend0) as opened
+   int w, fail;    // current block width, first failed column of the block (atomicMin)
    int nelim, flag, slot;
-   unsigned p2mask;     // bit k set: column k of the current panel is the second column of a 2x2 pivot
+   int wc;         // block workspace width: min(n, PB) rounded up to a multiple of NB
+   unsigned p2mask[4];  // bit k set: column k of the current block is the second column of a 2x2 pivot
    int state;           // 0 absent on this rank, 2 factorised here, 3 imported from another rank (child data only)
    int active;          // 1 while this front is being assembled / factorised by the current call
    int part_kind;       // 0 leaf part, 1 root part of the subtree partition (multi-GPU solve phases)
-   int pad2;
 };
 
 struct SlotStatic {
@@ -78,9 +77,9 @@ __device__ __forceinline__ double* felem(const FrontDev& f, int r, int c) {
    return (c < f.n) ? (f.L + (size_t)c * f.ldl + r) : (f.C + (size_t)(c - f.n) * f.ldc + (r - f.n));
 }
 
-__device__ __forceinline__ int compute_nelim(int fail, int w, unsigned p2mask) {
+__device__ __forceinline__ int compute_nelim(int fail, int w, const unsigned* p2mask) {
    int nelim = fail < w ? fail : w;
-   if (nelim < w && nelim > 0 && ((p2mask >> nelim) & 1u)) nelim -= 1;   // never split a 2x2 (Column::adjust)
+   if (nelim < w && nelim > 0 && ((p2mask[nelim >> 5] >> (nelim & 31)) & 1u)) nelim -= 1;   // never split a 2x2 (Column::adjust)
    return nelim;
 }
 // front handled by this CTA: bucket-contiguous slots, or an explicit list on the rare retry paths
@@ -433,6 +432,12 @@ __global__ void k_build_masks(const FrontDev* fr, int nslots, char* mine, char* 
 // host side
 // ------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int block_wc(int n) { return std::max(NB, (std::min(n, PB) + NB - 1) / NB * NB); }
+// doubles of block workspace of a front: Wld | Wo | L11 | A0 | dk | ibuf
+static inline size_t front_ws_doubles(size_t ldl, int n) {
+   const size_t wc = (size_t)block_wc(n);
+   return align_up(2 * ldl * wc + 2 * (size_t)PB * wc + 2 * PB + 2 + (2 * PB + 8) / 2, 32) + 128;
+}
 static inline int size_class(int m) { return m <= 64 ? 0 : m <= 256 ? 1 : m <= 1024 ? 2 : m <= 4096 ? 3 : 4; }
 
 struct Arena {
@@ -629,7 +634,7 @@ Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
          int64_t ldl = align_up(st.nrow, 2), cm = st.nrow - st.ncol;
          P->est_factor_doubles += ldl * st.ncol + 32;
          c += align_up(cm, 2) * cm + 32;
-         ws += (int64_t)(st.nrow + 1) * (NBO + NB) + 4 * NB * NB + 2 * NB + 2 + 3 * NB + 128;
+         ws += (int64_t)front_ws_doubles(align_up(st.nrow, 2), st.ncol);
       }
       P->est_c_doubles[l & 1] = std::max(P->est_c_doubles[l & 1], c);
       P->est_ws_doubles = std::max(P->est_ws_doubles, ws);
@@ -733,6 +738,8 @@ int Numeric::init() {
    if (d_fr) return 0;
    CU(cudaSetDevice(P->device));
    CU(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM));
+   CU(cudaFuncSetAttribute(k_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(PB)));
+   CU(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes(PB)));
    const int nn = std::max(P->nnodes, 1);
    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
    CU(cudaEventCreate(&ev0));
@@ -808,6 +815,17 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    CU(cudaEventRecord(ev1, st));
 
    int flag = 0, num_delay = 0, maxfront = 0, nfp = 0, nsp = 0;
+   // B200LDLT_TRACE=1: print the progress counters of every front after each block step (debugging aid;
+   // synchronises the stream)
+   const bool trace = getenv("B200LDLT_TRACE") != nullptr;
+   auto trace_fronts = [&](const char* what, int slot_first, int count) {
+      std::vector<FrontDev> tmp(count);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(tmp.data(), d_fr + slot_first, sizeof(FrontDev) * count, cudaMemcpyDeviceToHost);
+      for (int q = 0; q < count; ++q)
+         fprintf(stderr, "[b200ldlt] %s slot %d m=%d n=%d done=%d gend=%d w=%d fail=%d flag=%d\n", what, slot_first + q,
+                 tmp[q].m, tmp[q].n, tmp[q].done, tmp[q].gend, tmp[q].w, tmp[q].fail, tmp[q].flag);
+   };
    std::vector<int> lvl_list, tpp_list;
    std::vector<int64_t> tileptr;
    for (int l = 0; l < P->nlevels && flag >= 0; ++l) {
@@ -837,13 +855,13 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          f.m = ss.nrow + nd; f.n = ss.ncol + nd;
          f.ldl = (int)align_up(f.m, 2);
          f.ldc = (int)align_up(f.m - f.n, 2);
-         f.done = 0; f.oend = 0; f.gend = f.n; f.w = 0; f.fail = 0; f.jstart = 0; f.jend0 = 0; f.nelim = 0; f.flag = 0;
+         f.done = 0; f.gend = f.n; f.w = 0; f.fail = 0; f.nelim = 0; f.flag = 0; f.wc = block_wc(f.n);
          f.state = 2; f.active = 1; f.part_kind = part_kind[s];
          totL += align_up((size_t)f.ldl * f.n, 32);
          if (!boundary[s]) totC += align_up((size_t)f.ldc * (f.m - f.n), 32);
          totD += align_up(2 * (size_t)f.n + 2, 32);
          totP += 2 * align_up((size_t)f.n + 1, 32);
-         totW += align_up((size_t)f.ldl * (NBO + NB) + 4 * NB * NB + 2 * NB + 2, 32) + 128;
+         totW += front_ws_doubles(f.ldl, f.n);
          maxfront = std::max(maxfront, f.m);
       }
       double* Lb = (double*)fac.alloc(totL * 8);
@@ -870,10 +888,10 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             f.D = Db + oD; oD += align_up(2 * (size_t)f.n + 2, 32);
             f.perm = Pb + oP; f.orig = f.perm + align_up((size_t)f.n + 1, 32); oP += 2 * align_up((size_t)f.n + 1, 32);
             double* wp = Wb + oW;
-            oW += align_up((size_t)f.ldl * (NBO + NB) + 4 * NB * NB + 2 * NB + 2, 32) + 128;
-            f.Wld = wp; f.Wo = wp + (size_t)f.ldl * NBO;
-            f.dbuf = wp + (size_t)f.ldl * (NBO + NB);
-            f.ibuf = (int*)(f.dbuf + 4 * NB * NB + 2 * NB + 2);
+            oW += front_ws_doubles(f.ldl, f.n);
+            f.Wld = wp; f.Wo = wp + (size_t)f.ldl * f.wc;
+            f.dbuf = wp + 2 * (size_t)f.ldl * f.wc;
+            f.ibuf = (int*)(f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2);
          }
       }
       memcpy(pin_fr + s0, hfr.data() + s0, sizeof(FrontDev) * ns);
@@ -942,7 +960,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          if (pin_off) CU(cudaStreamSynchronize(st));   // staging regions free again
       }
       // factor: fronts bucketed by size class, sorted by candidate count (descending) inside.
-      // Each bucket runs rounds of outer blocks (NBO columns) of inner panels (NB columns); the
+      // Each bucket runs rounds of blocks (PB columns, four launches each); the
       // device keeps the progress counters, the host only needs them once per round.
       {
          std::vector<int> order(ns);
@@ -971,63 +989,44 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             if (maxm == 0) { i0 = i1; continue; }
             const int* lst = nullptr;
             const int b0 = s0 + i0;   // first slot of the bucket
-            const int ncolchunks = (maxn + 127) / 128;
-            const int ycommit = 1 + ncolchunks + (maxm + 127) / 128;
-            const int yapply = std::max(1, (maxm + AR - 1) / AR);
-            const int nouter = (maxn + NBO - 1) / NBO;
+            const int ncolchunks = (maxn + 63) / 64;
+            const int ycommit = 1 + ncolchunks + (maxm + 255) / 256;
+            const int nouter = (maxn + PB - 1) / PB;
             for (int ob = 0; ob < nouter; ++ob) {
-               int na = 0;   // slots [b0, b0+na) cover every front that still has an outer block number ob
-               for (int q = i0; q < i1; ++q) if (active[order[q]] && (hfr[order[q]].n + NBO - 1) / NBO > ob) na = q - i0 + 1;
+               int na = 0;   // slots [b0, b0+na) cover every front that still has a block number ob
+               for (int q = i0; q < i1; ++q) if (active[order[q]] && (hfr[order[q]].n + PB - 1) / PB > ob) na = q - i0 + 1;
                if (na == 0) break;
-               int maxw_outer = 0;
-               for (int q = 0; q < na; ++q) if (active[order[i0 + q]]) maxw_outer = std::max(maxw_outer, std::min(NBO, hfr[order[i0 + q]].n - ob * NBO));
-               const int ninner = (maxw_outer + NB - 1) / NB;
-               for (int j = 0; j < ninner; ++j) {
-                  k_diag<<<na, 32, 0, st>>>(d_fr, lst, b0, prm, j == 0 ? 1 : 0);
-                  k_apply<<<dim3(na, yapply), 256, 0, st>>>(d_fr, lst, b0, prm);
-                  k_commit<<<dim3(na, ycommit), 128, 0, st>>>(d_fr, lst, b0, ncolchunks);
-                  launches += 3;
-                  // inner update: columns of the outer block behind this panel
-                  const int colsleft = maxw_outer - (j + 1) * NB;
-                  if (colsleft > 0 || !posdef) {
-                     int ntr = (maxm + TM - 1) / TM;
-                     int ygrid = std::max(1, std::min(2 * ntr, std::max(1, 296 / std::max(na, 1))));
-                     if (o.profile) {
-                        for (int q = 0; q < na; ++q) {
-                           const FrontDev& ff = hfr[order[i0 + q]];
-                           if (!active[order[i0 + q]]) continue;
-                           double dn = ob * NBO + j * NB, je = std::min<double>(ff.n, (ob + 1) * NBO);
-                           double ww = std::min<double>(NB, je - dn), cb = dn + ww;
-                           if (ww > 0 && je > cb) prof_flops += 2.0 * ww * ((je - cb) * (ff.m - cb) - 0.5 * (je - cb) * (je - cb - 1));
-                        }
-                        prof_begin();
-                     }
-                     k_update<<<dim3(na, ygrid), 256, UPD_SMEM, st>>>(d_fr, lst, b0, 0);
-                     if (o.profile) prof_end();
-                     ++launches;
-                  }
-               }
-               // outer update: everything right of the outer block
+               int maxw = 0;
+               for (int q = 0; q < na; ++q) if (active[order[i0 + q]]) maxw = std::max(maxw, std::min(PB, hfr[order[i0 + q]].n - ob * PB));
+               const int wcap = (maxw + NB - 1) / NB * NB;
+               const int rem = maxm - ob * PB;     // rows of the tallest front from this block on (without failures)
+               // blocks shortened by failed pivots leave `done` behind ob*PB, so the row grid covers the
+               // whole front; CTAs above the block exit at once
+               const int yapply = std::max(1, (maxm + AR - 1) / AR);
+               k_block<<<na, 256, block_smem_bytes(wcap), st>>>(d_fr, lst, b0, prm, 0, wcap);
+               k_apply<<<dim3(na, yapply), AR, apply_smem_bytes(wcap), st>>>(d_fr, lst, b0, prm, wcap);
+               k_commit<<<dim3(na, ycommit), 256, 0, st>>>(d_fr, lst, b0, ncolchunks);
+               launches += 3;
                {
-                  int rem = maxm - ob * NBO;
                   int nt = std::max(1, (rem + TM - 1) / TM);
-                  int64_t tiles = (int64_t)nt * (nt + 1) / 2;
-                  int ygrid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * tiles, std::max<int64_t>(1, 296 / std::max(na, 1))));
+                  int64_t tiles = (int64_t)nt * (nt + 1);
+                  int ygrid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, std::max<int64_t>(1, 296 / std::max(na, 1))));
                   if (o.profile) {
                      for (int q = 0; q < na; ++q) {
                         const FrontDev& ff = hfr[order[i0 + q]];
                         if (!active[order[i0 + q]]) continue;
-                        double je = std::min<double>(ff.n, (ob + 1) * NBO), kc2 = je - ob * NBO, tt = ff.m - je;
+                        double je = std::min<double>(ff.n, (ob + 1) * PB), kc2 = je - ob * PB, tt = ff.m - je;
                         if (kc2 > 0 && tt > 0) prof_flops += kc2 * tt * (tt + 1);
                      }
                      prof_begin();
                   }
-                  k_update<<<dim3(na, ygrid), 256, UPD_SMEM, st>>>(d_fr, lst, b0, 1);
+                  k_update<<<dim3(na, ygrid), 256, UPD_SMEM, st>>>(d_fr, lst, b0);
                   if (o.profile) prof_end();
                   ++launches;
                }
+               if (trace) trace_fronts("block", b0, na);
             }
-            k_diag<<<i1 - i0, 32, 0, st>>>(d_fr, lst, b0, prm, 2);
+            k_block<<<i1 - i0, 256, block_smem_bytes(NB), st>>>(d_fr, lst, b0, prm, 1, NB);
             ++launches;
             i0 = i1;
          }
@@ -1060,17 +1059,15 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          for (int s : tpp_list) { maxm = std::max(maxm, hfr[s].m); maxn = std::max(maxn, hfr[s].n); }
          memcpy(pin_i, tpp_list.data(), sizeof(int) * nt);
          CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * nt, cudaMemcpyHostToDevice, st));
-         const int ncolchunks = (maxn + 127) / 128;
-         for (int j = 0; j < NBO / NB; ++j) {
-            k_diag<<<nt, 32, 0, st>>>(d_fr, d_list, 0, prm, j == 0 ? 1 : 0);
-            k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, 0, st>>>(d_fr, d_list, 0, prm);
-            k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 127) / 128), 128, 0, st>>>(d_fr, d_list, 0, ncolchunks);
-            k_update<<<dim3(nt, std::max(1, std::min((maxm + TM - 1) / TM, 64))), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, 0);
-            launches += 4;
-         }
-         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, 1);
-         k_diag<<<nt, 32, 0, st>>>(d_fr, d_list, 0, prm, 2);
-         launches += 2;
+         const int ncolchunks = (maxn + 63) / 64;
+         const int wcap = (std::min(maxn, PB) + NB - 1) / NB * NB;
+         k_block<<<nt, 256, block_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, 0, wcap);
+         k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), AR, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap);
+         k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks);
+         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0);
+         if (trace) for (int s : tpp_list) trace_fronts("retry", s, 1);
+         k_block<<<nt, 256, block_smem_bytes(NB), st>>>(d_fr, d_list, 0, prm, 1, NB);
+         launches += 5;
          if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
          if (flag < 0) break;
       }
@@ -1364,7 +1361,7 @@ int Numeric::contrib_unpack(int node, const char* src, int64_t bytes) {
    f.m = (int)hdr[0]; f.n = (int)hdr[1]; f.nelim = (int)hdr[2]; f.ldl = (int)hdr[3]; f.ldc = (int)hdr[4];
    f.ncol = P->hss[s].ncol; f.nrow = P->hss[s].nrow; f.first_piv = P->hss[s].first_piv;
    f.ndelay_in = f.m - f.nrow;
-   f.done = f.gend = f.nelim; f.oend = f.nelim; f.jstart = f.jend0 = f.nelim;
+   f.done = f.gend = f.nelim;
    f.state = 3; f.part_kind = 0;
    const int64_t nd = f.n - f.nelim;
    const int64_t need = 64 + (int64_t)align_up(nd * 4, 8) + 8 * (int64_t)f.ldl * nd + 8 * (int64_t)f.ldc * (f.m - f.n);

@@ -1,18 +1,21 @@
 // Dense front factorisation kernels (included by engine.cu).
 //
-// One elimination step of a front = four launches, batched over all fronts of a level bucket:
-//   k_diag    one CTA per front: close the previous panel (count accepted pivots, park failed
-//             columns behind the candidates), then factor the next 32x32 diagonal block with
-//             complete pivoting (block_ldlt.hxx:290-414) while accumulating L11^{-1}.
-//   k_apply   rows below the block: X = A21 P L11^{-T} (as a product with the explicit inverse),
-//             L21 = X D^{-1} written IN PLACE, X = L21 D kept in Wld for the Schur updates, the
-//             a-posteriori test |l_ij| <= 1/u (ldlt_app.cxx:304-323) by warp shuffle + atomicMin.
+// A front is eliminated PB = 128 columns at a time; one block step = four launches, batched over
+// all fronts of a level bucket:
+//   k_block   one CTA per front: close the previous block (count accepted pivots, park failed
+//             columns behind the candidates), then factorise the next 128x128 diagonal block
+//             entirely in shared memory: sub-panels of 32 columns, complete pivoting inside each
+//             32x32 diagonal sub-block by ONE WARP holding the sub-block in registers
+//             (block_ldlt.hxx:290-414), forward substitution + a-posteriori test for the rows of
+//             the block below it, FP64 FMA update of the rest of the block.
+//   k_apply   rows below the block: X = A21 P L11^{-T} by forward substitution (one thread per
+//             row, 32 columns in registers at a time), L21 = X D^{-1} written IN PLACE, X = L21 D
+//             kept in Wld for the Schur update, a-posteriori test |l_ij| <= 1/u
+//             (ldlt_app.cxx:304-323) by warp shuffle + atomicMin.
 //   k_commit  the block's own rows, D, pivot lists, row permutation of finished columns; restores
 //             failed columns from the saved originals (CopyBackup, ldlt_app.cxx:423).
-//   k_update  C -= L (LD)^T on FP64 tensor cores (mma.sync m8n8k4 -> DMMA), lower tiles only.
-// Two-level blocking: panels of NB=32 update only the current outer block of NBO=128 columns
-// (mode 0); the rest of the front is updated once per outer block with k <= 128 (mode 1), which
-// cuts the HBM traffic of the trailing matrix by 4.
+//   k_update  C -= L (LD)^T on FP64 tensor cores (mma.sync m8n8k4 -> DMMA), lower tiles only,
+//             k <= 128.
 #pragma once
 
 constexpr int TM = 128;          // update tile rows
@@ -20,113 +23,33 @@ constexpr int TN = 64;           // update tile cols
 constexpr int BK = 32;           // k chunk staged in shared memory
 constexpr int LDA = TM + 4;      // padded smem leading dimensions: t4*LD + g distinct mod 16 per half warp
 constexpr int LDB = TN + 4;
+constexpr int XLD = PB - NB + 1; // leading dimension of the in-block X = L*D buffer
 
 // ------------------------------------------------------------------------------------------
-// K1
+// Complete pivoting on a symmetric block of order wj <= 32 by one warp.  Lane r holds row r of the
+// (full) block in registers; rows and columns are never moved: eliminated indices leave the
+// `alive` mask and the pivot sequence is recorded.  A pivot step = one packed-key max reduction
+// (magnitude, column, row in 32 bits), the pivot row(s) broadcast through shared memory, 32 FMAs.
+// Outputs (shared): spord[k] original index of pivot k, sptype[k] (0 = 1x1, 1/2 = first/second of
+// a 2x2), sd = D^{-1} in SSIDS's format, sdd = D itself (for L*D), sLc[r + k*LDS] = multiplier of
+// original row r for pivot k.  Returns 0 or an SSIDS error flag.
 // ------------------------------------------------------------------------------------------
-// One warp per front; lane r keeps row r of the (full, symmetric) block in registers, so a pivot
-// step is a register scan, two warp reductions, one shared-memory broadcast of the pivot column
-// and 32 FMAs -- no block barriers (the 128/256-thread shared-memory versions spent 2400 cycles
-// per pivot in barrier / dependent-issue stalls, profiles/r1_notes.md).  Rows and columns are
-// never moved: eliminated indices leave the `alive` mask and the pivot sequence is recorded.
-__device__ __forceinline__ double pick32(const double (&a)[NB], int q) {
-   switch (q) {   // q is warp-uniform: one indirect branch
-#define B200_PICK(i) case i: return a[i];
-      B200_PICK(0) B200_PICK(1) B200_PICK(2) B200_PICK(3) B200_PICK(4) B200_PICK(5) B200_PICK(6) B200_PICK(7)
-      B200_PICK(8) B200_PICK(9) B200_PICK(10) B200_PICK(11) B200_PICK(12) B200_PICK(13) B200_PICK(14) B200_PICK(15)
-      B200_PICK(16) B200_PICK(17) B200_PICK(18) B200_PICK(19) B200_PICK(20) B200_PICK(21) B200_PICK(22) B200_PICK(23)
-      B200_PICK(24) B200_PICK(25) B200_PICK(26) B200_PICK(27) B200_PICK(28) B200_PICK(29) B200_PICK(30) B200_PICK(31)
-#undef B200_PICK
-   }
-   return 0.0;
-}
-
-__global__ void __launch_bounds__(32) k_diag(FrontDev* fr, const int* list, int slot0, Params prm, int mode) {
-   FrontDev& f = fr[front_slot(list, slot0)];
-   const int lane = threadIdx.x;
-   const bool new_outer = mode & 1, finish_only = mode & 2;
-   __shared__ double s0[NB * LDS];          // original block, full symmetric
-   __shared__ double sLc[NB * LDS];         // sLc[r + k*LDS]: multiplier of (original) row r for pivot k
-   __shared__ double sLd[NB][NB];           // sLd[k][r]: the same times D (pivot column before scaling), contiguous per pivot
-   __shared__ double sL[NB * LDS], sinv[NB * LDS];   // L11 in pivot order and its inverse
-   __shared__ double sd[2 * NB + 2];
-   __shared__ int sptype[NB], spord[NB];
-
-   if (f.flag < 0) return;
-   int done = f.done, oend = f.oend, gend = f.gend, w = f.w, jstart = f.jstart, jend0 = f.jend0;
-   const int fail = f.fail;
-   __syncwarp();
-   if (w > 0) {
-      const int nelim = compute_nelim(fail, w, f.p2mask);
-      const int nfail = w - nelim;
-      done += nelim;
-      for (int q = 0; q < nfail; ++q) {
-         int a = done + q, b = oend - 1 - q;
-         if (a < b) block_sym_swap(f, a, b);
-      }
-      oend -= nfail;
-      if (prm.posdef && nfail > 0) {
-         if (lane == 0) { f.flag = SSIDS_ERROR_NOT_POS_DEF; f.w = 0; }
-         return;
-      }
-   }
-   if (new_outer || finish_only) {
-      const int nfo = jend0 - oend;            // failed columns parked at [oend, jend0)
-      for (int q = 0; q < nfo; ++q) {
-         int a = oend + q, b = gend - 1 - q;
-         if (a < b) block_sym_swap(f, a, b);
-      }
-      gend -= nfo;
-      jstart = done;
-      jend0 = min(done + NBO, gend);
-      oend = jend0;
-   }
-   w = min(NB, oend - done);
-   if (w < 0) w = 0;
-   if (finish_only) w = 0;
-   __syncwarp();
-   if (lane == 0) {
-      f.done = done; f.oend = oend; f.gend = gend; f.jstart = jstart; f.jend0 = jend0;
-      f.w = w; f.fail = w; f.nelim = done;
-   }
-   if (w == 0) return;
-
-   // load: coalesced lower triangle -> shared (both triangles), then one row per lane
-   {
-      const double* Lb = f.L + (size_t)done * f.ldl + done + lane;
-      double v[NB];
-#pragma unroll
-      for (int c = 0; c < NB; ++c) v[c] = (c < w && lane >= c && lane < w) ? Lb[(size_t)c * f.ldl] : 0.0;
-#pragma unroll
-      for (int c = 0; c < NB; ++c) {
-         if (lane >= c) { s0[lane + c * LDS] = v[c]; s0[c + lane * LDS] = v[c]; }
-         sLc[lane + c * LDS] = 0.0;
-         sLd[c][lane] = 0.0;
-      }
-   }
-   for (int i = lane; i < 2 * NB + 2; i += 32) sd[i] = 0.0;
-   sptype[lane] = 0;
-   spord[lane] = lane;
-   __syncwarp();
-   double a[NB];
-#pragma unroll
-   for (int c = 0; c < NB; ++c) a[c] = s0[lane + c * LDS];
-   double dg = s0[lane + lane * LDS];
-   unsigned alive = (w == NB) ? 0xffffffffu : ((1u << w) - 1u);
-   int np = 0, err = 0;
+__device__ __forceinline__ int warp_ldlt32(double (&a)[NB], int wj, const Params& prm, int lane,
+                                           double* srow, double* sLc, double* sd, double* sdd,
+                                           int* spord, int* sptype) {
+   unsigned alive = (wj == NB) ? 0xffffffffu : ((1u << wj) - 1u);
+   int np = 0;
    while (alive) {
-      int q1, q2 = -1;
-      double d11 = 0.0, d21 = 0.0, d22 = 0.0;
+      __syncwarp();   // the previous step's reads of srow are done
+      int q1, q2 = -1, m1, t1;
+      double d11 = 0.0, d21 = 0.0, d22 = 0.0, a11, a21 = 0.0, a22 = 0.0;
       if (prm.posdef) {
          q1 = __ffs(alive) - 1;
-         const double a11 = __shfl_sync(0xffffffffu, dg, q1);
-         if (!(a11 > 0.0)) { err = SSIDS_ERROR_NOT_POS_DEF; break; }
-         d11 = 1.0 / a11;
+         m1 = t1 = q1;
       } else {
-         // largest |a(r,c)| over the alive rows / columns; compared on the high word of the double
-         // (sign cleared, 15 mantissa bits): ties -> smallest column, then row
-         // per-lane keys (|a| high word with the low 5 bits replaced by 31-c), reduced by a max tree
-         const bool rowalive = (alive >> lane) & 1u;
+         // largest |a(r,c)| over the alive rows / columns, compared on the high word of the double
+         // (sign cleared, 15 mantissa bits, the low 5 bits carry 31-col); ties -> smallest column,
+         // then smallest row
          unsigned kb[NB];
 #pragma unroll
          for (int c = 0; c < NB; ++c)
@@ -135,244 +58,457 @@ __global__ void __launch_bounds__(32) k_diag(FrontDev* fr, const int* list, int 
          for (int st = NB / 2; st > 0; st >>= 1)
 #pragma unroll
             for (int c = 0; c < st; ++c) kb[c] = max(kb[c], kb[c + st]);
+         const bool rowalive = (alive >> lane) & 1u;
          const unsigned bk = rowalive ? kb[0] : 0u;
          const int bc = 31 - (int)(bk & 31u);
          const unsigned mk = __reduce_max_sync(0xffffffffu, bk & ~31u);
-         const int lo = min(lane, bc), hi = max(lane, bc);
-         const unsigned idx = (rowalive && (bk & ~31u) == mk) ? (unsigned)(lo * 32 + hi) : 0xffffu;
-         const unsigned mi = __reduce_min_sync(0xffffffffu, idx);
-         const int mm = (int)(mi >> 5), t = (int)(mi & 31u);
-         const double a21 = __shfl_sync(0xffffffffu, pick32(a, mm), t);   // A(t, mm)
-         if (fabs(a21) < prm.small_) {
-            if (!prm.action) { err = SSIDS_ERROR_SINGULAR; break; }
-            // everything left is numerically zero: record zero pivots (block_ldlt.hxx:303-318)
+         if ((mk >> 20) == 0u) {
+            // everything left is (sub)normal-tiny or zero: zero pivots (block_ldlt.hxx:303-318)
+            if (!prm.action) return SSIDS_ERROR_SINGULAR;
             while (alive) {
                const int q = __ffs(alive) - 1;
-               if (lane == 0) { spord[np] = q; sptype[np] = 0; sd[2 * np] = 0.0; sd[2 * np + 1] = 0.0; }
+               if (lane == 0) { spord[np] = q; sptype[np] = 0; sd[2 * np] = 0.0; sd[2 * np + 1] = 0.0; sdd[2 * np] = 0.0; sdd[2 * np + 1] = 0.0; }
+               sLc[lane + np * LDS] = 0.0;
                alive &= ~(1u << q);
                ++np;
             }
             break;
          }
-         const double a11 = __shfl_sync(0xffffffffu, dg, mm), a22 = __shfl_sync(0xffffffffu, dg, t);
-         if (t == mm) {
-            q1 = t;
+         const int lo = min(lane, bc), hi = max(lane, bc);
+         const unsigned idx = (rowalive && (bk & ~31u) == mk) ? (unsigned)(lo * 32 + hi) : 0xffffu;
+         const unsigned mi = __reduce_min_sync(0xffffffffu, idx);
+         m1 = (int)(mi >> 5);
+         t1 = (int)(mi & 31u);
+         q1 = m1;
+      }
+      // rows m1 and t1 of the current Schur complement -> shared
+      if (lane == m1 || lane == t1) {
+         double2* dst = reinterpret_cast<double2*>(srow + (lane == m1 ? 0 : NB));
+#pragma unroll
+         for (int c2 = 0; c2 < NB / 2; ++c2) dst[c2] = make_double2(a[2 * c2], a[2 * c2 + 1]);
+      }
+      __syncwarp();
+      a11 = srow[m1];
+      int voff = 0;
+      if (prm.posdef) {
+         if (!(a11 > 0.0)) return SSIDS_ERROR_NOT_POS_DEF;
+         d11 = 1.0 / a11;
+      } else {
+         a21 = srow[t1];
+         a22 = srow[NB + t1];
+         if (fabs(a21) < prm.small_) {
+            // the largest entry is below `small`: all remaining pivots are zero pivots
+            if (!prm.action) return SSIDS_ERROR_SINGULAR;
+            while (alive) {
+               const int q = __ffs(alive) - 1;
+               if (lane == 0) { spord[np] = q; sptype[np] = 0; sd[2 * np] = 0.0; sd[2 * np + 1] = 0.0; sdd[2 * np] = 0.0; sdd[2 * np + 1] = 0.0; }
+               sLc[lane + np * LDS] = 0.0;
+               alive &= ~(1u << q);
+               ++np;
+            }
+            break;
+         }
+         if (t1 == m1) {
             d11 = 1.0 / a11;
          } else {
             const double detscale = 1.0 / fabs(a21);
             const double detpiv = (a11 * detscale) * a22 - fabs(a21);
             if (fabs(detpiv) >= fabs(a21) / 2) {
-               q1 = mm; q2 = t;
-               d11 = (a22 * detscale) / detpiv;
-               d22 = (a11 * detscale) / detpiv;
-               d21 = (-a21 * detscale) / detpiv;
+               q2 = t1;
+               const double rdet = 1.0 / detpiv;
+               d11 = (a22 * detscale) * rdet;
+               d22 = (a11 * detscale) * rdet;
+               d21 = (-a21 * detscale) * rdet;
             } else if (fabs(a11) > fabs(a22)) {
-               q1 = mm; d11 = 1.0 / a11;
+               d11 = 1.0 / a11;
             } else {
-               q1 = t; d11 = 1.0 / a22;
+               q1 = t1; voff = NB; a11 = a22;
+               d11 = 1.0 / a22;
             }
          }
       }
       if (q2 < 0) {
          alive &= ~(1u << q1);
          const bool upd = (alive >> lane) & 1u;
-         const double ldr = upd ? pick32(a, q1) : 0.0;
+         const double ldr = upd ? srow[voff + lane] : 0.0;
          const double l = ldr * d11;
-         sLd[np][lane] = ldr;
          sLc[lane + np * LDS] = l;
-         __syncwarp();
-         const double2* ldv = reinterpret_cast<const double2*>(&sLd[np][0]);
+         const double2* ldv = reinterpret_cast<const double2*>(srow + voff);
 #pragma unroll
          for (int c2 = 0; c2 < NB / 2; ++c2) {
             const double2 v = ldv[c2];
             a[2 * c2] -= l * v.x;
             a[2 * c2 + 1] -= l * v.y;
          }
-         dg -= l * ldr;
-         if (lane == 0) { spord[np] = q1; sptype[np] = 0; sd[2 * np] = d11; sd[2 * np + 1] = 0.0; }
+         if (lane == 0) { spord[np] = q1; sptype[np] = 0; sd[2 * np] = d11; sd[2 * np + 1] = 0.0; sdd[2 * np] = a11; sdd[2 * np + 1] = 0.0; }
          np += 1;
       } else {
          alive &= ~((1u << q1) | (1u << q2));
          const bool upd = (alive >> lane) & 1u;
-         const double w1 = upd ? pick32(a, q1) : 0.0, w2 = upd ? pick32(a, q2) : 0.0;
+         const double w1 = upd ? srow[lane] : 0.0, w2 = upd ? srow[NB + lane] : 0.0;
          const double l1 = d11 * w1 + d21 * w2, l2 = d21 * w1 + d22 * w2;
-         sLd[np][lane] = w1;
-         sLd[np + 1][lane] = w2;
          sLc[lane + np * LDS] = l1;
          sLc[lane + (np + 1) * LDS] = l2;
-         __syncwarp();
-         const double2* ldv1 = reinterpret_cast<const double2*>(&sLd[np][0]);
-         const double2* ldv2 = reinterpret_cast<const double2*>(&sLd[np + 1][0]);
+         const double2* ldv1 = reinterpret_cast<const double2*>(srow);
+         const double2* ldv2 = reinterpret_cast<const double2*>(srow + NB);
 #pragma unroll
          for (int c2 = 0; c2 < NB / 2; ++c2) {
             const double2 v1 = ldv1[c2], v2 = ldv2[c2];
             a[2 * c2] -= l1 * v1.x + l2 * v2.x;
             a[2 * c2 + 1] -= l1 * v1.y + l2 * v2.y;
          }
-         dg -= l1 * w1 + l2 * w2;
          if (lane == 0) {
             spord[np] = q1; spord[np + 1] = q2;
             sptype[np] = 1; sptype[np + 1] = 2;
             sd[2 * np] = d11; sd[2 * np + 1] = d21; sd[2 * np + 2] = DINF; sd[2 * np + 3] = d22;
+            sdd[2 * np] = a11; sdd[2 * np + 1] = a21; sdd[2 * np + 2] = a22; sdd[2 * np + 3] = a21;
          }
          np += 2;
       }
    }
-   if (err) {
-      if (lane == 0) { f.flag = err; f.w = 0; }
-      return;
-   }
-   __syncwarp();
-   // L11 in pivot order (unit lower), then its inverse: lane j solves L11 z = e_j
-#pragma unroll 4
-   for (int k = 0; k < NB; ++k) {
-      double lv = 0.0;
-      if (lane < w && k < w) lv = lane > k ? sLc[spord[lane] + k * LDS] : (lane == k ? 1.0 : 0.0);
-      sL[lane + k * LDS] = lv;
-      sinv[lane + k * LDS] = 0.0;
-   }
-   __syncwarp();
-   if (lane < w) {
-      const int j = lane;
-      sinv[j + j * LDS] = 1.0;
-      for (int i = j + 1; i < w; ++i) {
-         double s = 0.0;
-         for (int t = j; t < i; ++t) s += sL[i + t * LDS] * sinv[t + j * LDS];
-         sinv[i + j * LDS] = -s;
+   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: factorise the next diagonal block (<= PB columns) of a front in shared memory
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t block_smem_bytes(int wcap) {
+   // sA wcap x (wcap+1) | sX NB x XLD | sLc NB x LDS | sLj NB x NB | srow 2 NB | sd, sdd 2 PB + 2 each | ints
+   return sizeof(double) * ((size_t)wcap * (wcap + 1) + NB * XLD + NB * LDS + NB * NB + 2 * NB + 2 * (2 * PB + 2)) +
+          sizeof(int) * (2 * PB + 2 * NB + 8);
+}
+
+__global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only, int wcap) {
+   FrontDev& f = fr[front_slot(list, slot0)];
+   if (f.flag < 0) return;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   extern __shared__ __align__(16) double smem[];
+   const int sld = wcap + 1;
+   double* sA = smem;                        // element (r,c) of the block at sA[r + c*sld]
+   double* sX = sA + (size_t)wcap * sld;     // X(r1+i, k) of the current sub-panel at sX[k*XLD + i]
+   double* sLc = sX + NB * XLD;
+   double* sLj = sLc + NB * LDS;             // L_jj in pivot order, sLj[i + k*NB]
+   double* srow = sLj + NB * NB;
+   double* sdk = srow + 2 * NB;              // D^{-1} of the block (SSIDS format)
+   double* sdd = sdk + 2 * PB + 2;           // D of the block: diagonal, off-diagonal
+   int* slperm = reinterpret_cast<int*>(sdd + 2 * PB + 2);
+   int* sptype = slperm + PB;
+   int* spord = sptype + PB;
+   int* sptj = spord + NB;
+   int* smisc = sptj + NB;                   // 0: error flag, 1: first failed column of the sub-panel, 2: moved
+
+   // ---- close the previous block
+   int done = f.done, gend = f.gend, w = f.w;
+   if (w > 0) {
+      const int nelim = compute_nelim(f.fail, w, f.p2mask);
+      const int nfail = w - nelim;
+      done += nelim;
+      if (prm.posdef && nfail > 0) {
+         __syncthreads();
+         if (tid == 0) { f.flag = SSIDS_ERROR_NOT_POS_DEF; f.w = 0; }
+         return;
       }
-   }
-   __syncwarp();
-   // publish
-   double* L11 = f.dbuf;
-   double* LD11 = f.dbuf + NB * NB;
-   double* A0p = f.dbuf + 2 * NB * NB;
-   double* Linv = f.dbuf + 3 * NB * NB;      // row-major: Linv[k*NB + i] = (L11^{-1})(k,i)
-   double* dk = f.dbuf + 4 * NB * NB;
-   const int kofs = done - jstart;
-   const int pl = spord[lane];
-   for (int k = 0; k < NB; ++k) {
-      const int i = lane;
-      if (i < w && k < w) {
-         const double ldv = i > k ? sLd[k][pl] : 0.0;
-         L11[i + k * NB] = sL[i + k * LDS];
-         LD11[i + k * NB] = ldv;
-         A0p[i + k * NB] = s0[pl + spord[k] * LDS];
-         f.Wld[(size_t)(kofs + k) * f.ldl + done + i] = ldv;
+      for (int q = 0; q < nfail; ++q) {
+         const int a = done + q, b = gend - 1 - q;
+         if (a < b) block_sym_swap(f, a, b);
       }
-      // Linv row k, column `lane`
-      Linv[k * NB + lane] = (k < w && lane <= k) ? sinv[k + lane * LDS] : 0.0;
+      gend -= nfail;
    }
-   for (int i = lane; i < 2 * NB + 2; i += 32) dk[i] = sd[i];
-   f.ibuf[lane] = spord[lane];
-   f.ibuf[NB + lane] = sptype[lane];
+   __syncthreads();
+   w = finish_only ? 0 : max(0, min(wcap, gend - done));   // wcap <= PB: the launch's shared-memory capacity
+   if (tid == 0) {
+      f.done = done; f.gend = gend; f.w = w; f.fail = w; f.nelim = done;
+      f.p2mask[0] = f.p2mask[1] = f.p2mask[2] = f.p2mask[3] = 0u;
+   }
+   if (w == 0) return;
+
+   // ---- load the lower triangle (and keep a copy for the restore path)
+   const size_t ldl = f.ldl;
+   double* L11g = f.dbuf;
+   double* A0g = f.dbuf + (size_t)PB * f.wc;
    {
-      const bool moved = lane < w && spord[lane] != lane;
-      const bool second = lane < w && sptype[lane] == 2;
-      const unsigned pm = __ballot_sync(0xffffffffu, moved), m2 = __ballot_sync(0xffffffffu, second);
-      if (lane == 0) { f.ibuf[2 * NB] = pm != 0; f.p2mask = m2; }
+      const double* Lb = f.L + (size_t)done * ldl + done;
+      for (int c = warp; c < w; c += 8)
+         for (int r = lane + (c & ~31); r < w; r += 32)
+            if (r >= c) {
+               const double v = Lb[(size_t)c * ldl + r];
+               sA[r + c * sld] = v;
+               A0g[r + c * PB] = v;
+            }
+   }
+   if (tid < 8) smisc[tid] = 0;
+   __syncthreads();
+
+   int fail_blk = w;
+   unsigned anymoved = 0;
+   for (int c0 = 0; c0 < w; c0 += NB) {
+      const int wj = min(NB, w - c0), r1 = c0 + NB;
+      // a. complete pivoting on the diagonal sub-block
+      if (warp == 0) {
+         double a[NB];
+#pragma unroll
+         for (int c = 0; c < NB; ++c) {
+            double v = 0.0;
+            if (c < wj && lane < wj) v = (c <= lane) ? sA[(c0 + lane) + (c0 + c) * sld] : sA[(c0 + c) + (c0 + lane) * sld];
+            a[c] = v;
+         }
+         const int err = warp_ldlt32(a, wj, prm, lane, srow, sLc, sdk + 2 * c0, sdd + 2 * c0, spord, sptj);
+         __syncwarp();
+         const bool mv = lane < wj && spord[lane] != lane;
+         const unsigned pm = __ballot_sync(0xffffffffu, mv);
+         if (lane == 0) { smisc[0] = err; smisc[1] = wj; smisc[2] = pm != 0u; }
+      }
+      __syncthreads();
+      if (smisc[0] != 0) {
+         if (tid == 0) { f.flag = smisc[0]; f.w = 0; }
+         return;
+      }
+      const bool moved = smisc[2] != 0;
+      anymoved |= moved ? 1u : 0u;
+      // b. rows of the sub-block in the earlier columns of the block follow the pivot order; L_jj
+      {
+         double tmp[(PB - NB) / 8];
+         if (moved) {
+#pragma unroll
+            for (int s = 0; s < (PB - NB) / 8; ++s) {
+               const int c = warp + 8 * s;
+               tmp[s] = (c < c0 && lane < wj) ? sA[(c0 + spord[lane]) + c * sld] : 0.0;
+            }
+         }
+         __syncthreads();
+         if (moved) {
+#pragma unroll
+            for (int s = 0; s < (PB - NB) / 8; ++s) {
+               const int c = warp + 8 * s;
+               if (c < c0 && lane < wj) sA[(c0 + lane) + c * sld] = tmp[s];
+            }
+         }
+         for (int k = warp; k < NB; k += 8) {
+            double lv = 0.0;
+            if (lane < wj && k < wj) lv = lane > k ? sLc[spord[lane] + k * LDS] : (lane == k ? 1.0 : 0.0);
+            sLj[lane + k * NB] = lv;
+            sA[(c0 + lane) + (c0 + k) * sld] = lv;
+         }
+         if (tid < NB) {
+            slperm[c0 + tid] = c0 + (tid < wj ? spord[tid] : tid);
+            sptype[c0 + tid] = tid < wj ? sptj[tid] : 0;
+         }
+      }
+      __syncthreads();
+      if (r1 >= w) break;
+      // c. rows of the block below the sub-panel: forward substitution, D^{-1}, a-posteriori test
+      if (tid < w - r1) {
+         const int r = r1 + tid;
+         double x[NB];
+#pragma unroll
+         for (int k = 0; k < NB; ++k) x[k] = sA[r + (c0 + spord[k]) * sld];
+#pragma unroll
+         for (int k = 0; k < NB; ++k) {
+            const double xk = x[k];
+#pragma unroll
+            for (int c = k + 1; c < NB; ++c) x[c] -= xk * sLj[c + k * NB];
+         }
+         int myfail = NB;
+#pragma unroll
+         for (int k = NB - 1; k >= 0; --k) {
+            const int pt = sptj[k];
+            double l;
+            if (pt == 0) {
+               const double d11 = sdk[2 * (c0 + k)];
+               if (d11 == 0.0) l = (fabs(x[k]) < prm.small_) ? 0.0 : DINF * x[k];
+               else l = x[k] * d11;
+            } else if (pt == 1) {
+               l = sdk[2 * (c0 + k)] * x[k] + sdk[2 * (c0 + k) + 1] * x[(k + 1) & (NB - 1)];
+            } else {
+               l = sdk[2 * (c0 + k) - 1] * x[(k - 1) & (NB - 1)] + sdk[2 * (c0 + k) + 1] * x[k];
+            }
+            if (!prm.posdef && !(fabs(l) <= prm.lim)) myfail = min(myfail, k);
+            sA[r + (c0 + k) * sld] = l;
+            sX[k * XLD + tid] = x[k];
+         }
+         if (myfail < NB) atomicMin(&smisc[1], myfail);
+      }
+      __syncthreads();
+      if (smisc[1] < NB) {
+         // a column failed inside the block: the block ends with this sub-panel; the columns after
+         // it stay candidates and are treated as ordinary rows by k_apply
+         fail_blk = c0 + smisc[1];
+         w = r1;
+         break;
+      }
+      // e. update the rest of the block: A(r,c) -= sum_k L(r,k) X(c,k), 4x4 micro-tiles of the lower triangle
+      {
+         const int nt = (w - r1 + 3) >> 2, ntile = nt * (nt + 1) / 2;
+         for (int idx = tid; idx < ntile; idx += 256) {
+            int ti = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+            while (ti * (ti + 1) / 2 > idx) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= idx) ++ti;
+            const int tj = idx - ti * (ti + 1) / 2;
+            const int rb = r1 + 4 * ti, cb = 4 * tj;
+            double acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+               for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < NB; ++k) {
+               double lr[4], xc[4];
+#pragma unroll
+               for (int i = 0; i < 4; ++i) { lr[i] = sA[(rb + i) + (c0 + k) * sld]; xc[i] = sX[k * XLD + cb + i]; }
+#pragma unroll
+               for (int i = 0; i < 4; ++i)
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) acc[i][j] += lr[i] * xc[j];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+               for (int j = 0; j < 4; ++j) sA[(rb + i) + (r1 + cb + j) * sld] -= acc[i][j];
+         }
+      }
+      __syncthreads();
+   }
+   __syncthreads();
+
+   // ---- publish: L11 (unit lower, pivot order), L11*D into Wld, D^{-1}, pivot lists
+   {
+      const int wr = (w + NB - 1) & ~(NB - 1);
+      for (int k = warp; k < wr; k += 8)
+         for (int i = lane; i < wr; i += 32) {
+            double lv = 0.0;
+            if (i < w && k < w) lv = i > k ? sA[i + k * sld] : (i == k ? 1.0 : 0.0);
+            L11g[i + (size_t)k * PB] = lv;
+            if (i > k && i < w) {
+               const int pt = sptype[k];
+               double x;
+               if (pt == 0) x = lv * sdd[2 * k];
+               else if (pt == 1) x = lv * sdd[2 * k] + sA[i + (k + 1) * sld] * sdd[2 * k + 1];
+               else x = sA[i + (k - 1) * sld] * sdd[2 * k + 1] + lv * sdd[2 * k];
+               f.Wld[(size_t)k * ldl + done + i] = x;
+            }
+         }
+      double* dkg = f.dbuf + 2 * (size_t)PB * f.wc;
+      for (int i = tid; i < 2 * w + 2; i += 256) dkg[i] = i < 2 * w ? sdk[i] : 0.0;
+      if (tid < w) { f.ibuf[tid] = slperm[tid]; f.ibuf[PB + tid] = sptype[tid]; }
+      if (tid < 4) {
+         unsigned mask = 0u;
+         for (int b = 0; b < 32; ++b) { const int k = tid * 32 + b; if (k < w && sptype[k] == 2) mask |= 1u << b; }
+         f.p2mask[tid] = mask;
+      }
+      if (tid == 0) { f.ibuf[2 * PB] = (int)anymoved; f.w = w; f.fail = fail_blk; }
    }
 }
 
 // ------------------------------------------------------------------------------------------
-// K2
+// K2: rows below the block.  One thread per row; the row's 32 entries of the current sub-panel live
+// in registers, earlier sub-panels' X in shared memory, L11 is read through the read-only path.
 // ------------------------------------------------------------------------------------------
 constexpr int AR = 64;    // rows per CTA in k_apply
+__host__ __device__ inline size_t apply_smem_bytes(int wcap) {
+   return sizeof(double) * ((size_t)(wcap - NB) * AR + 2 * PB + 2) + sizeof(int) * 2 * PB;
+}
 
-__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, int slot0, Params prm) {
+__global__ void __launch_bounds__(AR) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap) {
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0) return;
    const int done = f.done, m = f.m;
    const int r0 = done + w + blockIdx.y * AR;
    if (r0 >= m) return;
-   __shared__ double sinv[NB * NB];
-   __shared__ double sdk[2 * NB + 2];
-   __shared__ int slperm[NB], sptype[NB];
-   __shared__ double at[AR][NB + 1], xt[AR][NB + 1];
+   extern __shared__ __align__(16) double smem[];
+   double* xs = smem;                                  // xs[k*AR + tid], k < wcap - NB
+   double* sdk = xs + (size_t)(wcap - NB) * AR;
+   int* slperm = reinterpret_cast<int*>(sdk + 2 * PB + 2);
+   int* sptype = slperm + PB;
    const int tid = threadIdx.x;
-   for (int i = tid; i < NB * NB; i += 256) sinv[i] = f.dbuf[3 * NB * NB + i];
-   for (int i = tid; i < 2 * NB + 2; i += 256) sdk[i] = f.dbuf[4 * NB * NB + i];
-   if (tid < NB) { slperm[tid] = f.ibuf[tid]; sptype[tid] = f.ibuf[NB + tid]; }
+   {
+      const double* dkg = f.dbuf + 2 * (size_t)PB * f.wc;
+      for (int i = tid; i < 2 * w + 2; i += AR) sdk[i] = dkg[i];
+      for (int i = tid; i < w; i += AR) { slperm[i] = f.ibuf[i]; sptype[i] = f.ibuf[PB + i]; }
+   }
    __syncthreads();
-   const int rl = tid & (AR - 1), kq = tid >> 6;      // row within the tile, group of 8 columns
-   const int r = r0 + rl;
+   const int r = r0 + tid;
    const bool rv = r < m;
    const size_t ldl = f.ldl;
-   const int kofs = done - f.jstart;
-   {
-      double a8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-         const int k = kq * 8 + j;
-         a8[j] = (rv && k < w) ? f.L[(size_t)(done + slperm[k]) * ldl + r] : 0.0;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-         const int k = kq * 8 + j;
-         at[rl][k] = a8[j];
-         if (rv && k < w) f.Wo[(size_t)k * ldl + r] = a8[j];
-      }
-   }
-   __syncthreads();
-   {
-      double x8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x8[j] = 0.0;
-      const int kmax = kq * 8 + 7;
-      for (int i = 0; i <= kmax; ++i) {
-         const double ai = at[rl][i];
-#pragma unroll
-         for (int j = 0; j < 8; ++j) x8[j] += ai * sinv[(kq * 8 + j) * NB + i];   // Linv(k,i) = 0 for i > k
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xt[rl][kq * 8 + j] = x8[j];
-   }
-   __syncthreads();
+   const double* __restrict__ L11 = f.dbuf;
+   double* const Lp = f.L;
+   double* const Wld = f.Wld;
+   double* const Wo = f.Wo;
    int myfail = w;
-   {
-      double l8[8], x8[8];
+   const int nblk = (w + NB - 1) / NB;
+   for (int j = 0; j < nblk; ++j) {
+      const int c0 = j * NB;
+      double x[NB];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-         const int k = kq * 8 + j;
-         l8[j] = 0.0;
-         x8[j] = xt[rl][k];
-         if (k < w) {
-            const int pt = sptype[k];
-            double l;
-            if (pt == 0) {
-               const double d11 = sdk[2 * k];
-               if (d11 == 0.0) l = (fabs(x8[j]) < prm.small_) ? 0.0 : DINF * x8[j];
-               else l = x8[j] * d11;
-            } else if (pt == 1) {
-               l = sdk[2 * k] * x8[j] + sdk[2 * k + 1] * xt[rl][(k + 1) & (NB - 1)];
-            } else {
-               l = sdk[2 * k - 1] * xt[rl][(k - 1) & (NB - 1)] + sdk[2 * k + 1] * x8[j];
-            }
-            l8[j] = l;
-            if (rv && !prm.posdef && (!(fabs(l) <= prm.lim)) && k < myfail) myfail = k;
-         }
+      for (int k = 0; k < NB; ++k) {
+         const int kk = c0 + k;
+         x[k] = (rv && kk < w) ? Lp[(size_t)(done + slperm[kk < w ? kk : 0]) * ldl + r] : 0.0;
       }
       if (rv) {
 #pragma unroll
-         for (int j = 0; j < 8; ++j) {
-            const int k = kq * 8 + j;
-            if (k < w) {
-               f.L[(size_t)(done + k) * ldl + r] = l8[j];
-               f.Wld[(size_t)(kofs + k) * ldl + r] = x8[j];
+         for (int k = 0; k < NB; ++k)
+            if (c0 + k < w) Wo[(size_t)(c0 + k) * ldl + r] = x[k];
+      }
+      for (int i = 0; i < j; ++i) {
+#pragma unroll 2
+         for (int kk = 0; kk < NB; ++kk) {
+            const double xi = xs[(size_t)(i * NB + kk) * AR + tid];
+            const double2* lc = reinterpret_cast<const double2*>(L11 + (size_t)(i * NB + kk) * PB + c0);
+#pragma unroll
+            for (int c2 = 0; c2 < NB / 2; ++c2) {
+               const double2 v = __ldg(lc + c2);
+               x[2 * c2] -= xi * v.x;
+               x[2 * c2 + 1] -= xi * v.y;
+            }
+         }
+      }
+#pragma unroll
+      for (int kk = 0; kk < NB; ++kk) {
+         const double xk = x[kk];
+         const double* lc = L11 + (size_t)(c0 + kk) * PB + c0;
+#pragma unroll
+         for (int c = kk + 1; c < NB; ++c) x[c] -= xk * __ldg(lc + c);
+      }
+      if (j + 1 < nblk) {
+#pragma unroll
+         for (int k = 0; k < NB; ++k) xs[(size_t)(c0 + k) * AR + tid] = x[k];
+      }
+#pragma unroll
+      for (int k = NB - 1; k >= 0; --k) {
+         const int kk = c0 + k;
+         if (kk < w) {
+            const int pt = sptype[kk];
+            double l;
+            if (pt == 0) {
+               const double d11 = sdk[2 * kk];
+               if (d11 == 0.0) l = (fabs(x[k]) < prm.small_) ? 0.0 : DINF * x[k];
+               else l = x[k] * d11;
+            } else if (pt == 1) {
+               l = sdk[2 * kk] * x[k] + sdk[2 * kk + 1] * x[(k + 1) & (NB - 1)];
+            } else {
+               l = sdk[2 * kk - 1] * x[(k - 1) & (NB - 1)] + sdk[2 * kk + 1] * x[k];
+            }
+            if (rv) {
+               if (!prm.posdef && !(fabs(l) <= prm.lim)) myfail = min(myfail, kk);
+               Lp[(size_t)(done + kk) * ldl + r] = l;
+               Wld[(size_t)kk * ldl + r] = x[k];
             }
          }
       }
    }
+   // blocks are visited in ascending order and columns in descending order inside a block, so the
+   // smallest failing column needs a min over what was seen
 #pragma unroll
    for (int off = 16; off > 0; off >>= 1) myfail = min(myfail, __shfl_xor_sync(0xffffffffu, myfail, off));
    if ((tid & 31) == 0 && myfail < w) atomicMin(&f.fail, myfail);
 }
 
 // ------------------------------------------------------------------------------------------
-// K3.  blockIdx.y == 0: the block's own rows, D, pivot lists.  Then cdiv(n,128) chunks for the
-// row permutation of finished columns, then cdiv(m,128) chunks restoring failed columns.
+// K3.  blockIdx.y == 0: the block's own rows, D, pivot lists.  Then `ncolchunks` chunks of 64
+// finished columns whose rows [done, done+w) follow the pivot order, then chunks of 256 rows
+// restoring failed columns.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_commit(FrontDev* fr, const int* list, int slot0, int ncolchunks) {
+__global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, int slot0, int ncolchunks) {
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0) return;
@@ -380,39 +516,48 @@ __global__ void __launch_bounds__(128) k_commit(FrontDev* fr, const int* list, i
    const int* lperm = f.ibuf;
    const int nelim = compute_nelim(f.fail, w, f.p2mask);
    const size_t ldl = f.ldl;
-   const int y = blockIdx.y;
+   const int y = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    if (y == 0) {
       const double* L11 = f.dbuf;
-      const double* A0p = f.dbuf + 2 * NB * NB;
-      for (int idx = threadIdx.x; idx < NB * NB; idx += 128) {
-         const int i = idx & 31, k = idx >> 5;
-         if (i < w && k <= i)
-            f.L[(size_t)(done + k) * ldl + done + i] = k < nelim ? (i == k ? 1.0 : L11[i + k * NB]) : A0p[i + k * NB];
+      const double* A0 = f.dbuf + (size_t)PB * f.wc;
+      for (int k = warp; k < w; k += 8) {
+         const int pk = lperm[k];
+         for (int i = k + lane; i < w; i += 32) {
+            double v;
+            if (k < nelim) v = L11[i + (size_t)k * PB];
+            else { const int pi = lperm[i]; v = A0[max(pi, pk) + (size_t)min(pi, pk) * PB]; }
+            f.L[(size_t)(done + k) * ldl + done + i] = v;
+         }
       }
-      const double* dk = f.dbuf + 4 * NB * NB;
-      for (int k = threadIdx.x; k < nelim; k += 128) {
+      const double* dk = f.dbuf + 2 * (size_t)PB * f.wc;
+      for (int k = tid; k < nelim; k += 256) {
          f.D[2 * (done + k)] = dk[2 * k];
          f.D[2 * (done + k) + 1] = dk[2 * k + 1];
       }
-      if (f.ibuf[2 * NB] && threadIdx.x < 64) {
-         int* arr = threadIdx.x < 32 ? f.perm : f.orig;
-         const int q = threadIdx.x & 31;
-         int v = q < w ? arr[done + lperm[q]] : 0;
-         __syncwarp();
+      if (f.ibuf[2 * PB]) {
+         int* arr = tid < 128 ? f.perm : f.orig;
+         const int q = tid & 127;
+         const int v = q < w ? arr[done + lperm[q]] : 0;
+         __syncthreads();
          if (q < w) arr[done + q] = v;
       }
    } else if (y <= ncolchunks) {
-      if (!f.ibuf[2 * NB]) return;
-      const int c = (y - 1) * 128 + threadIdx.x;
-      if (c >= done) return;
-      double tmp[NB];
+      if (!f.ibuf[2 * PB]) return;
+      // one warp per column, 8 columns per warp
+      for (int s = 0; s < 8; ++s) {
+         const int c = (y - 1) * 64 + warp * 8 + s;
+         if (c >= done) return;
+         double* col = f.L + (size_t)c * ldl + done;
+         double tmp[PB / 32];
 #pragma unroll
-      for (int q = 0; q < NB; ++q) tmp[q] = q < w ? f.L[(size_t)c * ldl + done + lperm[q]] : 0.0;
+         for (int q = 0; q < PB / 32; ++q) { const int i = lane + 32 * q; tmp[q] = i < w ? col[lperm[i]] : 0.0; }
+         __syncwarp();
 #pragma unroll
-      for (int q = 0; q < NB; ++q) if (q < w) f.L[(size_t)c * ldl + done + q] = tmp[q];
+         for (int q = 0; q < PB / 32; ++q) { const int i = lane + 32 * q; if (i < w) col[i] = tmp[q]; }
+      }
    } else {
       if (nelim == w) return;
-      const int r = done + w + (y - 1 - ncolchunks) * 128 + threadIdx.x;
+      const int r = done + w + (y - 1 - ncolchunks) * 256 + tid;
       if (r >= m) return;
       for (int k = nelim; k < w; ++k) f.L[(size_t)(done + k) * ldl + r] = f.Wo[(size_t)k * ldl + r];
    }
@@ -447,20 +592,17 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc,
 // two CTAs per SM.  ncu (profiles/r1_notes.md) showed the kernel bound by per-warp instruction
 // issue around the MMAs, so interior tiles take a path without bounds predicates and with
 // strength-reduced addresses, and tile coordinates advance incrementally.
-__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0, int mode) {
+__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0) {
    const FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
-   if (f.flag < 0) return;
-   const int nel_cur = w > 0 ? compute_nelim(f.fail, w, f.p2mask) : 0;
-   int k0, kc, cbeg, cend;
+   if (f.flag < 0 || w == 0) return;
+   // pivots accepted in the current block; the region starts right behind them, so columns of the
+   // block that failed (restored by k_commit) receive the update as well
+   const int kc = compute_nelim(f.fail, w, f.p2mask);
    const int m = f.m;
-   if (mode == 0) {
-      k0 = f.done; kc = nel_cur; cbeg = f.done + nel_cur; cend = f.jend0;
-   } else {
-      k0 = f.jstart; kc = f.done + nel_cur - f.jstart; cbeg = f.jend0; cend = m;
-   }
+   const int k0 = f.done, cbeg = f.done + kc, cend = m;
    if (kc <= 0 || cbeg >= cend) return;
-   const int kofs = k0 - f.jstart;
+   const int kofs = 0;
    const int ntr = (m - cbeg + TM - 1) / TM;
    const int ntc = (cend - cbeg + TN - 1) / TN;
    extern __shared__ double smem[];
