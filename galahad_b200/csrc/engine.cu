@@ -43,7 +43,7 @@ struct FrontDev {
    int* orig;      // orig[r] = local index variable r had when the front was assembled (r < n)
    double* Wld;    // ldl x wc  L*D of the current block (front-row indexed)
    double* Wo;     // ldl x wc  permuted original columns of the block (restore on failure)
-   double* dbuf;   // L11[PB*wc] | A0[PB*wc] | dk[2*PB+2]
+   double* dbuf;   // L11[PB*wc] | A0[PB*wc] | dk[2*PB+2] | Linv[NB*wc] (inverses of the 32x32 diagonal blocks of L11)
    int* ibuf;      // lperm[PB] | ptype[PB] | permuted
    int m, n, ldl, ldc;
    int ncol, nrow, ndelay_in, first_piv;
@@ -433,10 +433,10 @@ __global__ void k_build_masks(const FrontDev* fr, int nslots, char* mine, char* 
 // ------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int block_wc(int n) { return std::max(NB, (std::min(n, PB) + NB - 1) / NB * NB); }
-// doubles of block workspace of a front: Wld | Wo | L11 | A0 | dk | ibuf
+// doubles of block workspace of a front: Wld | Wo | L11 | A0 | dk | Linv | ibuf
 static inline size_t front_ws_doubles(size_t ldl, int n) {
    const size_t wc = (size_t)block_wc(n);
-   return align_up(2 * ldl * wc + 2 * (size_t)PB * wc + 2 * PB + 2 + (2 * PB + 8) / 2, 32) + 128;
+   return align_up(2 * ldl * wc + 2 * (size_t)PB * wc + 2 * PB + 2 + (size_t)NB * wc + (2 * PB + 8) / 2, 32) + 128;
 }
 static inline int size_class(int m) { return m <= 64 ? 0 : m <= 256 ? 1 : m <= 1024 ? 2 : m <= 4096 ? 3 : 4; }
 
@@ -891,7 +891,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             oW += front_ws_doubles(f.ldl, f.n);
             f.Wld = wp; f.Wo = wp + (size_t)f.ldl * f.wc;
             f.dbuf = wp + 2 * (size_t)f.ldl * f.wc;
-            f.ibuf = (int*)(f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2);
+            f.ibuf = (int*)(f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2 + (size_t)NB * f.wc);
          }
       }
       memcpy(pin_fr + s0, hfr.data() + s0, sizeof(FrontDev) * ns);
@@ -1004,7 +1004,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                // whole front; CTAs above the block exit at once
                const int yapply = std::max(1, (maxm + AR - 1) / AR);
                k_block<<<na, 256, block_smem_bytes(wcap), st>>>(d_fr, lst, b0, prm, 0, wcap);
-               k_apply<<<dim3(na, yapply), AR, apply_smem_bytes(wcap), st>>>(d_fr, lst, b0, prm, wcap);
+               k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), st>>>(d_fr, lst, b0, prm, wcap);
                k_commit<<<dim3(na, ycommit), 256, 0, st>>>(d_fr, lst, b0, ncolchunks);
                launches += 3;
                {
@@ -1062,7 +1062,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          const int ncolchunks = (maxn + 63) / 64;
          const int wcap = (std::min(maxn, PB) + NB - 1) / NB * NB;
          k_block<<<nt, 256, block_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, 0, wcap);
-         k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), AR, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap);
+         k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap);
          k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks);
          k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0);
          if (trace) for (int s : tpp_list) trace_fronts("retry", s, 1);

@@ -25,6 +25,27 @@ constexpr int LDA = TM + 4;      // padded smem leading dimensions: t4*LD + g di
 constexpr int LDB = TN + 4;
 constexpr int XLD = PB - NB + 1; // leading dimension of the in-block X = L*D buffer
 
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(d0), "+d"(d1)
+                : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+   int sz = valid ? 8 : 0;
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
+   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+
+
 // ------------------------------------------------------------------------------------------
 // Complete pivoting on a symmetric block of order wj <= 32 by one warp.  Lane r holds row r of the
 // (full) block in registers; rows and columns are never moved: eliminated indices leave the
@@ -34,19 +55,85 @@ constexpr int XLD = PB - NB + 1; // leading dimension of the in-block X = L*D bu
 // a 2x2), sd = D^{-1} in SSIDS's format, sdd = D itself (for L*D), sLc[r + k*LDS] = multiplier of
 // original row r for pivot k.  Returns 0 or an SSIDS error flag.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int warp_ldlt32(double (&a)[NB], int wj, const Params& prm, int lane,
+__device__ __forceinline__ void warp_zero_pivots(unsigned& alive, int& np, int lane, double* sLc, double* sd, double* sdd,
+                                                int* spord, int* sptype) {
+   // everything left is numerically zero: record zero pivots (block_ldlt.hxx:303-318)
+   while (alive) {
+      const int q = __ffs(alive) - 1;
+      if (lane == 0) { spord[np] = q; sptype[np] = 0; sd[2 * np] = 0.0; sd[2 * np + 1] = 0.0; sdd[2 * np] = 0.0; sdd[2 * np + 1] = 0.0; }
+      sLc[lane + np * LDS] = 0.0;
+      alive &= ~(1u << q);
+      ++np;
+   }
+}
+
+// srow: 2*NB + 2 doubles (two broadcast rows, the pivot's reciprocal)
+__device__ __forceinline__ int warp_ldlt32(double (&a)[NB], double dg, int wj, const Params& prm, int lane,
                                            double* srow, double* sLc, double* sd, double* sdd,
                                            int* spord, int* sptype) {
    unsigned alive = (wj == NB) ? 0xffffffffu : ((1u << wj) - 1u);
    int np = 0;
+   double rdg = 1.0 / dg;       // every lane keeps the reciprocal of its own diagonal entry: no division
+                                // between choosing a 1x1 pivot and using it
    while (alive) {
       __syncwarp();   // the previous step's reads of srow are done
+      const bool rowalive = (alive >> lane) & 1u;
+      // ---- fast path: the largest diagonal entry is taken as a 1x1 pivot when it dominates its
+      // column, |a_qq| >= max_r |a_rq| / 2 (multipliers <= 2 inside the block).  Costs two warp
+      // reductions and no scan of the block.  posdef: pivots in order, no test.
+      {
+         int q;
+         if (prm.posdef) {
+            q = __ffs(alive) - 1;
+         } else {
+            const unsigned dkey = rowalive ? ((((unsigned)__double2hiint(dg)) & 0x7fffffe0u) | (unsigned)(31 - lane)) : 0u;
+            q = 31 - (int)(__reduce_max_sync(0xffffffffu, dkey) & 31u);
+         }
+         if (lane == q) {
+            double2* dst = reinterpret_cast<double2*>(srow);
+#pragma unroll
+            for (int c2 = 0; c2 < NB / 2; ++c2) dst[c2] = make_double2(a[2 * c2], a[2 * c2 + 1]);
+            srow[2 * NB] = rdg;
+         }
+         __syncwarp();
+         const double vown = srow[lane];
+         const double aqq = srow[q];
+         bool ok;
+         if (prm.posdef) {
+            if (!(aqq > 0.0)) return SSIDS_ERROR_NOT_POS_DEF;
+            ok = true;
+         } else {
+            const unsigned lkey = (rowalive && lane != q) ? ((unsigned)__double2hiint(vown) & 0x7fffffffu) : 0u;
+            const unsigned mlk = __reduce_max_sync(0xffffffffu, lkey);
+            const double lam = __hiloint2double((int)mlk, 0);   // lam <= max_r |a_rq| < lam (1 + 2^-20)
+            ok = fabs(aqq) >= prm.small_ && fabs(aqq) >= 0.5000005 * lam;
+         }
+         if (ok) {
+            const double d11 = srow[2 * NB];
+            alive &= ~(1u << q);
+            const bool upd = (alive >> lane) & 1u;
+            const double ldr = upd ? vown : 0.0;
+            const double l = ldr * d11;
+            sLc[lane + np * LDS] = l;
+            const double2* ldv = reinterpret_cast<const double2*>(srow);
+#pragma unroll
+            for (int c2 = 0; c2 < NB / 2; ++c2) {
+               const double2 v = ldv[c2];
+               a[2 * c2] -= l * v.x;
+               a[2 * c2 + 1] -= l * v.y;
+            }
+            dg -= l * ldr;
+            rdg = 1.0 / dg;
+            if (lane == 0) { spord[np] = q; sptype[np] = 0; sd[2 * np] = d11; sd[2 * np + 1] = 0.0; sdd[2 * np] = aqq; sdd[2 * np + 1] = 0.0; }
+            np += 1;
+            continue;
+         }
+         __syncwarp();   // srow is rewritten below
+      }
+      // ---- general step: complete pivoting (block_ldlt.hxx:290-414)
       int q1, q2 = -1, m1, t1;
       double d11 = 0.0, d21 = 0.0, d22 = 0.0, a11, a21 = 0.0, a22 = 0.0;
-      if (prm.posdef) {
-         q1 = __ffs(alive) - 1;
-         m1 = t1 = q1;
-      } else {
+      {
          // largest |a(r,c)| over the alive rows / columns, compared on the high word of the double
          // (sign cleared, 15 mantissa bits, the low 5 bits carry 31-col); ties -> smallest column,
          // then smallest row
@@ -58,20 +145,12 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], int wj, const Params
          for (int st = NB / 2; st > 0; st >>= 1)
 #pragma unroll
             for (int c = 0; c < st; ++c) kb[c] = max(kb[c], kb[c + st]);
-         const bool rowalive = (alive >> lane) & 1u;
          const unsigned bk = rowalive ? kb[0] : 0u;
          const int bc = 31 - (int)(bk & 31u);
          const unsigned mk = __reduce_max_sync(0xffffffffu, bk & ~31u);
          if ((mk >> 20) == 0u) {
-            // everything left is (sub)normal-tiny or zero: zero pivots (block_ldlt.hxx:303-318)
             if (!prm.action) return SSIDS_ERROR_SINGULAR;
-            while (alive) {
-               const int q = __ffs(alive) - 1;
-               if (lane == 0) { spord[np] = q; sptype[np] = 0; sd[2 * np] = 0.0; sd[2 * np + 1] = 0.0; sdd[2 * np] = 0.0; sdd[2 * np + 1] = 0.0; }
-               sLc[lane + np * LDS] = 0.0;
-               alive &= ~(1u << q);
-               ++np;
-            }
+            warp_zero_pivots(alive, np, lane, sLc, sd, sdd, spord, sptype);
             break;
          }
          const int lo = min(lane, bc), hi = max(lane, bc);
@@ -90,41 +169,30 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], int wj, const Params
       __syncwarp();
       a11 = srow[m1];
       int voff = 0;
-      if (prm.posdef) {
-         if (!(a11 > 0.0)) return SSIDS_ERROR_NOT_POS_DEF;
+      a21 = srow[t1];
+      a22 = srow[NB + t1];
+      if (fabs(a21) < prm.small_) {
+         // the largest entry is below `small`: all remaining pivots are zero pivots
+         if (!prm.action) return SSIDS_ERROR_SINGULAR;
+         warp_zero_pivots(alive, np, lane, sLc, sd, sdd, spord, sptype);
+         break;
+      }
+      if (t1 == m1) {
          d11 = 1.0 / a11;
       } else {
-         a21 = srow[t1];
-         a22 = srow[NB + t1];
-         if (fabs(a21) < prm.small_) {
-            // the largest entry is below `small`: all remaining pivots are zero pivots
-            if (!prm.action) return SSIDS_ERROR_SINGULAR;
-            while (alive) {
-               const int q = __ffs(alive) - 1;
-               if (lane == 0) { spord[np] = q; sptype[np] = 0; sd[2 * np] = 0.0; sd[2 * np + 1] = 0.0; sdd[2 * np] = 0.0; sdd[2 * np + 1] = 0.0; }
-               sLc[lane + np * LDS] = 0.0;
-               alive &= ~(1u << q);
-               ++np;
-            }
-            break;
-         }
-         if (t1 == m1) {
+         const double detscale = 1.0 / fabs(a21);
+         const double detpiv = (a11 * detscale) * a22 - fabs(a21);
+         if (fabs(detpiv) >= fabs(a21) / 2) {
+            q2 = t1;
+            const double rdet = 1.0 / detpiv;
+            d11 = (a22 * detscale) * rdet;
+            d22 = (a11 * detscale) * rdet;
+            d21 = (-a21 * detscale) * rdet;
+         } else if (fabs(a11) > fabs(a22)) {
             d11 = 1.0 / a11;
          } else {
-            const double detscale = 1.0 / fabs(a21);
-            const double detpiv = (a11 * detscale) * a22 - fabs(a21);
-            if (fabs(detpiv) >= fabs(a21) / 2) {
-               q2 = t1;
-               const double rdet = 1.0 / detpiv;
-               d11 = (a22 * detscale) * rdet;
-               d22 = (a11 * detscale) * rdet;
-               d21 = (-a21 * detscale) * rdet;
-            } else if (fabs(a11) > fabs(a22)) {
-               d11 = 1.0 / a11;
-            } else {
-               q1 = t1; voff = NB; a11 = a22;
-               d11 = 1.0 / a22;
-            }
+            q1 = t1; voff = NB; a11 = a22;
+            d11 = 1.0 / a22;
          }
       }
       if (q2 < 0) {
@@ -140,6 +208,7 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], int wj, const Params
             a[2 * c2] -= l * v.x;
             a[2 * c2 + 1] -= l * v.y;
          }
+         dg -= l * ldr;
          if (lane == 0) { spord[np] = q1; sptype[np] = 0; sd[2 * np] = d11; sd[2 * np + 1] = 0.0; sdd[2 * np] = a11; sdd[2 * np + 1] = 0.0; }
          np += 1;
       } else {
@@ -157,6 +226,7 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], int wj, const Params
             a[2 * c2] -= l1 * v1.x + l2 * v2.x;
             a[2 * c2 + 1] -= l1 * v1.y + l2 * v2.y;
          }
+         dg -= l1 * w1 + l2 * w2;
          if (lane == 0) {
             spord[np] = q1; spord[np + 1] = q2;
             sptype[np] = 1; sptype[np + 1] = 2;
@@ -165,8 +235,26 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], int wj, const Params
          }
          np += 2;
       }
+      rdg = 1.0 / dg;
    }
    return 0;
+}
+
+// inverse of the unit lower triangular L_jj (sLj[i + k*NB]) by one warp: lane c solves L z = e_c and
+// writes row c of the k-major operand k_apply wants, dst[c*NB + i] = inv(L_jj)(i, c)
+__device__ __forceinline__ void warp_inv32(const double* sLj, double* dst, int lane) {
+   double z[NB];
+#pragma unroll
+   for (int i = 0; i < NB; ++i) z[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+   for (int k = 0; k < NB - 1; ++k) {
+      const double zk = z[k];
+#pragma unroll
+      for (int i = k + 1; i < NB; ++i) z[i] -= zk * sLj[i + k * NB];
+   }
+   double2* d2 = reinterpret_cast<double2*>(dst + lane * NB);
+#pragma unroll
+   for (int i2 = 0; i2 < NB / 2; ++i2) d2[i2] = make_double2(z[2 * i2], z[2 * i2 + 1]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -174,7 +262,7 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], int wj, const Params
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t block_smem_bytes(int wcap) {
    // sA wcap x (wcap+1) | sX NB x XLD | sLc NB x LDS | sLj NB x NB | srow 2 NB | sd, sdd 2 PB + 2 each | ints
-   return sizeof(double) * ((size_t)wcap * (wcap + 1) + NB * XLD + NB * LDS + NB * NB + 2 * NB + 2 * (2 * PB + 2)) +
+   return sizeof(double) * ((size_t)wcap * (wcap + 1) + NB * XLD + NB * LDS + NB * NB + 2 * NB + 2 + 2 * (2 * PB + 2)) +
           sizeof(int) * (2 * PB + 2 * NB + 8);
 }
 
@@ -189,7 +277,7 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
    double* sLc = sX + NB * XLD;
    double* sLj = sLc + NB * LDS;             // L_jj in pivot order, sLj[i + k*NB]
    double* srow = sLj + NB * NB;
-   double* sdk = srow + 2 * NB;              // D^{-1} of the block (SSIDS format)
+   double* sdk = srow + 2 * NB + 2;          // D^{-1} of the block (SSIDS format)
    double* sdd = sdk + 2 * PB + 2;           // D of the block: diagonal, off-diagonal
    int* slperm = reinterpret_cast<int*>(sdd + 2 * PB + 2);
    int* sptype = slperm + PB;
@@ -241,9 +329,12 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
 
    int fail_blk = w;
    unsigned anymoved = 0;
+   double* Linvg = f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2;
+   int jinv = -1;      // sub-panel whose L_jj sits in sLj and still needs its inverse
    for (int c0 = 0; c0 < w; c0 += NB) {
       const int wj = min(NB, w - c0), r1 = c0 + NB;
-      // a. complete pivoting on the diagonal sub-block
+      // a. pivoting on the diagonal sub-block (warp 0); meanwhile warp 1 inverts the previous L_jj
+      if (warp == 1 && jinv >= 0) warp_inv32(sLj, Linvg + (size_t)jinv * NB * NB, lane);
       if (warp == 0) {
          double a[NB];
 #pragma unroll
@@ -252,7 +343,8 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
             if (c < wj && lane < wj) v = (c <= lane) ? sA[(c0 + lane) + (c0 + c) * sld] : sA[(c0 + c) + (c0 + lane) * sld];
             a[c] = v;
          }
-         const int err = warp_ldlt32(a, wj, prm, lane, srow, sLc, sdk + 2 * c0, sdd + 2 * c0, spord, sptj);
+         const double dg = lane < wj ? sA[(c0 + lane) + (c0 + lane) * sld] : 1.0;
+         const int err = warp_ldlt32(a, dg, wj, prm, lane, srow, sLc, sdk + 2 * c0, sdd + 2 * c0, spord, sptj);
          __syncwarp();
          const bool mv = lane < wj && spord[lane] != lane;
          const unsigned pm = __ballot_sync(0xffffffffu, mv);
@@ -295,6 +387,7 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
          }
       }
       __syncthreads();
+      jinv = c0 / NB;
       if (r1 >= w) break;
       // c. rows of the block below the sub-panel: forward substitution, D^{-1}, a-posteriori test
       if (tid < w - r1) {
@@ -369,6 +462,7 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
       __syncthreads();
    }
    __syncthreads();
+   if (warp == 1 && jinv >= 0) warp_inv32(sLj, Linvg + (size_t)jinv * NB * NB, lane);
 
    // ---- publish: L11 (unit lower, pivot order), L11*D into Wld, D^{-1}, pivot lists
    {
@@ -400,15 +494,22 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: rows below the block.  One thread per row; the row's 32 entries of the current sub-panel live
-// in registers, earlier sub-panels' X in shared memory, L11 is read through the read-only path.
+// K2: rows below the block, X L11^T = A21 P as a blocked triangular solve on the FP64 tensor pipe.
+// CTA = 64 rows x the whole block (w <= 128 columns), 8 warps.  Stage j (32 columns):
+//    Y   = A_j - sum_{i<j} X_i L_ji^T        DMMA, X_i and the L11 blocks in shared memory
+//    X_j = Y inv(L_jj)^T                      DMMA with the explicit 32x32 inverses from k_block
+//    L_j = X_j D^{-1} (in place), X_j kept in Wld, a-posteriori test |l| <= 1/u
 // ------------------------------------------------------------------------------------------
-constexpr int AR = 64;    // rows per CTA in k_apply
+constexpr int AR = 64;             // rows per CTA in k_apply
+constexpr int LDX = AR + 4;        // k-major smem leading dimensions, = 4 mod 16: conflict-free fragments
+constexpr int LDBB = NB + 4;
 __host__ __device__ inline size_t apply_smem_bytes(int wcap) {
-   return sizeof(double) * ((size_t)(wcap - NB) * AR + 2 * PB + 2) + sizeof(int) * 2 * PB;
+   const int nb = wcap / NB;
+   return sizeof(double) * ((size_t)wcap * LDX + NB * LDX + (size_t)(nb * (nb - 1) / 2 + nb) * NB * LDBB + 2 * PB + 2) +
+          sizeof(int) * 2 * PB;
 }
 
-__global__ void __launch_bounds__(AR) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap) {
+__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap) {
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0) return;
@@ -416,91 +517,128 @@ __global__ void __launch_bounds__(AR) k_apply(FrontDev* fr, const int* list, int
    const int r0 = done + w + blockIdx.y * AR;
    if (r0 >= m) return;
    extern __shared__ __align__(16) double smem[];
-   double* xs = smem;                                  // xs[k*AR + tid], k < wcap - NB
-   double* sdk = xs + (size_t)(wcap - NB) * AR;
+   const int nbc = wcap / NB;
+   double* Xs = smem;                                    // Xs[k*LDX + r]: A, then X, k < wcap
+   double* Ys = Xs + (size_t)wcap * LDX;                 // Ys[k*LDX + r], k < NB
+   double* Bl = Ys + NB * LDX;                           // strictly lower blocks (j,i): [k*LDBB + c] = L11(32j+c, 32i+k)
+   double* Bi = Bl + (size_t)(nbc * (nbc - 1) / 2) * NB * LDBB;   // [j][k*LDBB + c] = inv(L_jj)(c,k)
+   double* sdk = Bi + (size_t)nbc * NB * LDBB;
    int* slperm = reinterpret_cast<int*>(sdk + 2 * PB + 2);
    int* sptype = slperm + PB;
-   const int tid = threadIdx.x;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int nb = (w + NB - 1) / NB, wr = nb * NB;
    {
       const double* dkg = f.dbuf + 2 * (size_t)PB * f.wc;
-      for (int i = tid; i < 2 * w + 2; i += AR) sdk[i] = dkg[i];
-      for (int i = tid; i < w; i += AR) { slperm[i] = f.ibuf[i]; sptype[i] = f.ibuf[PB + i]; }
+      for (int i = tid; i < 2 * w + 2; i += 256) sdk[i] = dkg[i];
+      for (int i = tid; i < wr; i += 256) { slperm[i] = i < w ? f.ibuf[i] : 0; sptype[i] = i < w ? f.ibuf[PB + i] : 0; }
    }
    __syncthreads();
-   const int r = r0 + tid;
-   const bool rv = r < m;
    const size_t ldl = f.ldl;
-   const double* __restrict__ L11 = f.dbuf;
    double* const Lp = f.L;
-   double* const Wld = f.Wld;
-   double* const Wo = f.Wo;
-   int myfail = w;
-   const int nblk = (w + NB - 1) / NB;
-   for (int j = 0; j < nblk; ++j) {
-      const int c0 = j * NB;
-      double x[NB];
-#pragma unroll
-      for (int k = 0; k < NB; ++k) {
-         const int kk = c0 + k;
-         x[k] = (rv && kk < w) ? Lp[(size_t)(done + slperm[kk < w ? kk : 0]) * ldl + r] : 0.0;
+   {
+      // A tile (8-byte copies: the row offset may be odd), L11 blocks and inverses (16-byte copies)
+      for (int e = tid; e < wr * AR; e += 256) {
+         const int k = e >> 6, rr = e & (AR - 1);
+         const bool ok = k < w && r0 + rr < m;
+         cp_async8(Xs + k * LDX + rr, ok ? Lp + (size_t)(done + slperm[k]) * ldl + r0 + rr : Lp, ok);
       }
-      if (rv) {
-#pragma unroll
-         for (int k = 0; k < NB; ++k)
-            if (c0 + k < w) Wo[(size_t)(c0 + k) * ldl + r] = x[k];
-      }
-      for (int i = 0; i < j; ++i) {
-#pragma unroll 2
-         for (int kk = 0; kk < NB; ++kk) {
-            const double xi = xs[(size_t)(i * NB + kk) * AR + tid];
-            const double2* lc = reinterpret_cast<const double2*>(L11 + (size_t)(i * NB + kk) * PB + c0);
-#pragma unroll
-            for (int c2 = 0; c2 < NB / 2; ++c2) {
-               const double2 v = __ldg(lc + c2);
-               x[2 * c2] -= xi * v.x;
-               x[2 * c2 + 1] -= xi * v.y;
+      const double* L11 = f.dbuf;
+      for (int j = 1; j < nb; ++j)
+         for (int i = 0; i < j; ++i) {
+            double* dst = Bl + (size_t)(j * (j - 1) / 2 + i) * NB * LDBB;
+            for (int e = tid; e < NB * NB / 2; e += 256) {
+               const int k = e >> 4, c = (e & 15) * 2;
+               cp_async16(dst + k * LDBB + c, L11 + (size_t)(i * NB + k) * PB + j * NB + c, 16);
             }
+         }
+      const double* Linv = f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2;
+      for (int e = tid; e < nb * NB * NB / 2; e += 256) {
+         const int j = e >> 9, k = (e >> 4) & 31, c = (e & 15) * 2;
+         cp_async16(Bi + (size_t)j * NB * LDBB + k * LDBB + c, Linv + (size_t)j * NB * NB + k * NB + c, 16);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+   }
+   __syncthreads();
+   // keep the permuted originals for the restore path
+   for (int e = tid; e < w * AR; e += 256) {
+      const int k = e >> 6, rr = e & (AR - 1);
+      if (r0 + rr < m) f.Wo[(size_t)k * ldl + r0 + rr] = Xs[k * LDX + rr];
+   }
+   const int rg = warp & 1, cg = warp >> 1;      // warp tile: rows rg*32..+31, columns cg*8..+7 of the stage
+   const int g = lane >> 2, t4 = lane & 3;
+   const int srow_ = tid & (AR - 1), skq = tid >> 6;   // scaling pass: row, group of 8 columns
+   const bool rv = r0 + srow_ < m;
+   int myfail = w;
+   for (int j = 0; j < nb; ++j) {
+      const int c0 = j * NB;
+      double acc[4][2];
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4)
+#pragma unroll
+         for (int h = 0; h < 2; ++h) acc[i4][h] = Xs[(c0 + cg * 8 + 2 * t4 + h) * LDX + rg * 32 + i4 * 8 + g];
+      for (int i = 0; i < j; ++i) {
+         const double* as = Xs + (i * NB + t4) * LDX + rg * 32 + g;
+         const double* bs = Bl + (size_t)(j * (j - 1) / 2 + i) * NB * LDBB + t4 * LDBB + cg * 8 + g;
+#pragma unroll
+         for (int ks = 0; ks < NB; ks += 4) {
+            const double b = -bs[ks * LDBB];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) dmma(acc[i4][0], acc[i4][1], as[ks * LDX + i4 * 8], b);
          }
       }
 #pragma unroll
-      for (int kk = 0; kk < NB; ++kk) {
-         const double xk = x[kk];
-         const double* lc = L11 + (size_t)(c0 + kk) * PB + c0;
+      for (int i4 = 0; i4 < 4; ++i4)
 #pragma unroll
-         for (int c = kk + 1; c < NB; ++c) x[c] -= xk * __ldg(lc + c);
+         for (int h = 0; h < 2; ++h) Ys[(cg * 8 + 2 * t4 + h) * LDX + rg * 32 + i4 * 8 + g] = acc[i4][h];
+      __syncthreads();
+      double x[4][2];
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) x[i4][0] = x[i4][1] = 0.0;
+      {
+         const double* as = Ys + t4 * LDX + rg * 32 + g;
+         const double* bs = Bi + (size_t)j * NB * LDBB + t4 * LDBB + cg * 8 + g;
+         const int kend = 8 * (cg + 1);            // inv(L_jj)(c,k) = 0 for k > c
+         for (int ks = 0; ks < kend; ks += 4) {
+            const double b = bs[ks * LDBB];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) dmma(x[i4][0], x[i4][1], as[ks * LDX + i4 * 8], b);
+         }
       }
-      if (j + 1 < nblk) {
 #pragma unroll
-         for (int k = 0; k < NB; ++k) xs[(size_t)(c0 + k) * AR + tid] = x[k];
-      }
+      for (int i4 = 0; i4 < 4; ++i4)
 #pragma unroll
-      for (int k = NB - 1; k >= 0; --k) {
-         const int kk = c0 + k;
-         if (kk < w) {
-            const int pt = sptype[kk];
-            double l;
-            if (pt == 0) {
-               const double d11 = sdk[2 * kk];
-               if (d11 == 0.0) l = (fabs(x[k]) < prm.small_) ? 0.0 : DINF * x[k];
-               else l = x[k] * d11;
-            } else if (pt == 1) {
-               l = sdk[2 * kk] * x[k] + sdk[2 * kk + 1] * x[(k + 1) & (NB - 1)];
-            } else {
-               l = sdk[2 * kk - 1] * x[(k - 1) & (NB - 1)] + sdk[2 * kk + 1] * x[k];
-            }
-            if (rv) {
+         for (int h = 0; h < 2; ++h) Xs[(c0 + cg * 8 + 2 * t4 + h) * LDX + rg * 32 + i4 * 8 + g] = x[i4][h];
+      __syncthreads();
+      // D^{-1}, a-posteriori test, results to global (coalesced along the rows)
+      if (rv) {
+         const int r = r0 + srow_;
+#pragma unroll
+         for (int q = 7; q >= 0; --q) {
+            const int kk = c0 + skq * 8 + q;
+            if (kk < w) {
+               const double xv = Xs[kk * LDX + srow_];
+               const int pt = sptype[kk];
+               double l;
+               if (pt == 0) {
+                  const double d11 = sdk[2 * kk];
+                  if (d11 == 0.0) l = (fabs(xv) < prm.small_) ? 0.0 : DINF * xv;
+                  else l = xv * d11;
+               } else if (pt == 1) {
+                  l = sdk[2 * kk] * xv + sdk[2 * kk + 1] * Xs[(kk + 1) * LDX + srow_];
+               } else {
+                  l = sdk[2 * kk - 1] * Xs[(kk - 1) * LDX + srow_] + sdk[2 * kk + 1] * xv;
+               }
                if (!prm.posdef && !(fabs(l) <= prm.lim)) myfail = min(myfail, kk);
                Lp[(size_t)(done + kk) * ldl + r] = l;
-               Wld[(size_t)kk * ldl + r] = x[k];
+               f.Wld[(size_t)kk * ldl + r] = xv;
             }
          }
       }
    }
-   // blocks are visited in ascending order and columns in descending order inside a block, so the
-   // smallest failing column needs a min over what was seen
 #pragma unroll
    for (int off = 16; off > 0; off >>= 1) myfail = min(myfail, __shfl_xor_sync(0xffffffffu, myfail, off));
-   if ((tid & 31) == 0 && myfail < w) atomicMin(&f.fail, myfail);
+   if (lane == 0 && myfail < w) atomicMin(&f.fail, myfail);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -568,26 +706,6 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
 // the region cols [cbeg, cend), rows >= col, with A = L(:, k0:k0+kc) and B = Wld(:, kofs:kofs+kc).
 // CTA = 256 threads = 8 warps (4 x 2); CTA tile 128 x 128; warp tile 32 x 64 = 4 x 8 m8n8k4 MMAs.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
-   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                : "+d"(d0), "+d"(d1)
-                : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
-   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-   int sz = valid ? 8 : 0;
-   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gsrc), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
-   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gsrc), "r"(src_bytes));
-}
-
 // CTA = 256 threads = 8 warps (4 x 2); CTA tile 128 x 64; warp tile 32 x 32 = 4 x 4 m8n8k4 MMAs;
 // two CTAs per SM.  ncu (profiles/r1_notes.md) showed the kernel bound by per-warp instruction
 // issue around the MMAs, so interior tiles take a path without bounds predicates and with
