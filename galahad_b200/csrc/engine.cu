@@ -67,6 +67,7 @@ struct SlotStatic {
 struct Params {
    double u, small_, lim;
    int action, posdef;
+   int debug;      // B200LDLT_TRACE=2: k_block prints its phase timings (clock64) for the first front of a launch
 };
 
 // ------------------------------------------------------------------------------------------
@@ -787,6 +788,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    prm.lim = prm.u > 0 ? 1.0 / prm.u : INFINITY;
    prm.action = o.action;
    prm.posdef = posdef;
+   { const char* tr = getenv("B200LDLT_TRACE"); prm.debug = tr && atoi(tr) >= 2; }
    double mult = std::max(o.multiplier, 1.0);
    fac.reserve((size_t)(P->est_factor_doubles * mult) * 8 + (1 << 20));
    dar.reserve((size_t)(2.0 * sym.n * mult) * 8 + 64 * (size_t)nn + (1 << 16));

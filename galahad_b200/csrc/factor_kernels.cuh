@@ -23,7 +23,7 @@ constexpr int TN = 64;           // update tile cols
 constexpr int BK = 32;           // k chunk staged in shared memory
 constexpr int LDA = TM + 4;      // padded smem leading dimensions: t4*LD + g distinct mod 16 per half warp
 constexpr int LDB = TN + 4;
-constexpr int XLD = PB - NB + 1; // leading dimension of the in-block X = L*D buffer
+constexpr int XLD = 100;         // leading dimension of the k-major in-block buffers (rows <= 96), = 4 mod 16
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -67,7 +67,7 @@ __device__ __forceinline__ void warp_zero_pivots(unsigned& alive, int& np, int l
    }
 }
 
-// srow: 2*NB + 2 doubles (two broadcast rows, the pivot's reciprocal)
+// srow: 2*NB + 2 doubles (two broadcast rows)
 __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], double dg, int wj, const Params& prm, int lane,
                                            double* srow, double* sLc, double* sd, double* sdd,
                                            int* spord, int* sptype) {
@@ -75,45 +75,44 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], double dg, int wj, c
    int np = 0;
    double rdg = 1.0 / dg;       // every lane keeps the reciprocal of its own diagonal entry: no division
                                 // between choosing a 1x1 pivot and using it
+   const unsigned small_hi = (unsigned)__double2hiint(prm.small_) & 0x7fffffffu;
+   // candidate of the fast path: the alive row with the largest |diagonal| (posdef: the next row)
+   auto next_q = [&](unsigned al) -> int {
+      if (prm.posdef) return al ? __ffs(al) - 1 : 0;
+      const unsigned dkey = ((al >> lane) & 1u) ? ((((unsigned)__double2hiint(dg)) & 0x7fffffe0u) | (unsigned)(31 - lane)) : 0u;
+      return 31 - (int)(__reduce_max_sync(0xffffffffu, dkey) & 31u);
+   };
+   int q = next_q(alive);
    while (alive) {
       __syncwarp();   // the previous step's reads of srow are done
       const bool rowalive = (alive >> lane) & 1u;
-      // ---- fast path: the largest diagonal entry is taken as a 1x1 pivot when it dominates its
-      // column, |a_qq| >= max_r |a_rq| / 2 (multipliers <= 2 inside the block).  Costs two warp
-      // reductions and no scan of the block.  posdef: pivots in order, no test.
+      // ---- fast path: the largest diagonal entry is taken as a 1x1 pivot when all multipliers of
+      // the block stay <= 2 in modulus (checked on the multipliers themselves by a vote).  One warp
+      // reduction per pivot, issued right after the new diagonal is known so that it overlaps
+      // the rank-1 update.  posdef: pivots in order, only positivity is checked.
       {
-         int q;
-         if (prm.posdef) {
-            q = __ffs(alive) - 1;
-         } else {
-            const unsigned dkey = rowalive ? ((((unsigned)__double2hiint(dg)) & 0x7fffffe0u) | (unsigned)(31 - lane)) : 0u;
-            q = 31 - (int)(__reduce_max_sync(0xffffffffu, dkey) & 31u);
-         }
          if (lane == q) {
             double2* dst = reinterpret_cast<double2*>(srow);
 #pragma unroll
             for (int c2 = 0; c2 < NB / 2; ++c2) dst[c2] = make_double2(a[2 * c2], a[2 * c2 + 1]);
-            srow[2 * NB] = rdg;
          }
+         const double d11 = __shfl_sync(0xffffffffu, rdg, q);
          __syncwarp();
          const double vown = srow[lane];
-         const double aqq = srow[q];
-         bool ok;
-         if (prm.posdef) {
-            if (!(aqq > 0.0)) return SSIDS_ERROR_NOT_POS_DEF;
-            ok = true;
-         } else {
-            const unsigned lkey = (rowalive && lane != q) ? ((unsigned)__double2hiint(vown) & 0x7fffffffu) : 0u;
-            const unsigned mlk = __reduce_max_sync(0xffffffffu, lkey);
-            const double lam = __hiloint2double((int)mlk, 0);   // lam <= max_r |a_rq| < lam (1 + 2^-20)
-            ok = fabs(aqq) >= prm.small_ && fabs(aqq) >= 0.5000005 * lam;
-         }
-         if (ok) {
-            const double d11 = srow[2 * NB];
-            alive &= ~(1u << q);
-            const bool upd = (alive >> lane) & 1u;
-            const double ldr = upd ? vown : 0.0;
-            const double l = ldr * d11;
+         const unsigned alive2 = alive & ~(1u << q);
+         const bool upd = (alive2 >> lane) & 1u;
+         const double ldr = upd ? vown : 0.0;
+         const double l = ldr * d11;
+         bool bad;
+         if (prm.posdef) bad = (lane == q) && !(dg > 0.0);
+         else bad = (lane == q) ? (((unsigned)__double2hiint(dg) & 0x7fffffffu) < small_hi || small_hi == 0u && dg == 0.0)
+                                : (((unsigned)__double2hiint(l) & 0x7fffffffu) > 0x40000000u);
+         if (!__any_sync(0xffffffffu, bad)) {
+            const double aqq = dg;                     // meaningful on lane q
+            alive = alive2;
+            dg -= l * ldr;
+            const int qn = next_q(alive);              // overlaps the update below
+            rdg = 1.0 / dg;
             sLc[lane + np * LDS] = l;
             const double2* ldv = reinterpret_cast<const double2*>(srow);
 #pragma unroll
@@ -122,12 +121,12 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], double dg, int wj, c
                a[2 * c2] -= l * v.x;
                a[2 * c2 + 1] -= l * v.y;
             }
-            dg -= l * ldr;
-            rdg = 1.0 / dg;
-            if (lane == 0) { spord[np] = q; sptype[np] = 0; sd[2 * np] = d11; sd[2 * np + 1] = 0.0; sdd[2 * np] = aqq; sdd[2 * np + 1] = 0.0; }
+            if (lane == q) { spord[np] = q; sptype[np] = 0; sd[2 * np] = d11; sd[2 * np + 1] = 0.0; sdd[2 * np] = aqq; sdd[2 * np + 1] = 0.0; }
             np += 1;
+            q = qn;
             continue;
          }
+         if (prm.posdef) return SSIDS_ERROR_NOT_POS_DEF;
          __syncwarp();   // srow is rewritten below
       }
       // ---- general step: complete pivoting (block_ldlt.hxx:290-414)
@@ -236,33 +235,20 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], double dg, int wj, c
          np += 2;
       }
       rdg = 1.0 / dg;
+      q = next_q(alive);
    }
    return 0;
-}
-
-// inverse of the unit lower triangular L_jj (sLj[i + k*NB]) by one warp: lane c solves L z = e_c and
-// writes row c of the k-major operand k_apply wants, dst[c*NB + i] = inv(L_jj)(i, c)
-__device__ __forceinline__ void warp_inv32(const double* sLj, double* dst, int lane) {
-   double z[NB];
-#pragma unroll
-   for (int i = 0; i < NB; ++i) z[i] = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-   for (int k = 0; k < NB - 1; ++k) {
-      const double zk = z[k];
-#pragma unroll
-      for (int i = k + 1; i < NB; ++i) z[i] -= zk * sLj[i + k * NB];
-   }
-   double2* d2 = reinterpret_cast<double2*>(dst + lane * NB);
-#pragma unroll
-   for (int i2 = 0; i2 < NB / 2; ++i2) d2[i2] = make_double2(z[2 * i2], z[2 * i2 + 1]);
 }
 
 // ------------------------------------------------------------------------------------------
 // K1: factorise the next diagonal block (<= PB columns) of a front in shared memory
 // ------------------------------------------------------------------------------------------
+constexpr int LDBB = NB + 4;       // k-major 32-column operand, = 4 mod 16: conflict-free MMA fragments
 __host__ __device__ inline size_t block_smem_bytes(int wcap) {
-   // sA wcap x (wcap+1) | sX NB x XLD | sLc NB x LDS | sLj NB x NB | srow 2 NB | sd, sdd 2 PB + 2 each | ints
-   return sizeof(double) * ((size_t)wcap * (wcap + 1) + NB * XLD + NB * LDS + NB * NB + 2 * NB + 2 + 2 * (2 * PB + 2)) +
+   // sA wcap x (wcap+4) | sX, sXa NB x XLD each (only when the block has more than one sub-panel; sLc
+   // aliases sXa) | sLj NB x NB | sInv NB x LDBB | srow | sdk, sdd | ints
+   const size_t xbuf = wcap > NB ? 2 * (size_t)NB * XLD : (size_t)NB * LDS;
+   return sizeof(double) * ((size_t)wcap * (wcap + 4) + xbuf + NB * NB + NB * LDBB + 2 * NB + 2 + 2 * (2 * PB + 2)) +
           sizeof(int) * (2 * PB + 2 * NB + 8);
 }
 
@@ -270,13 +256,16 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
    FrontDev& f = fr[front_slot(list, slot0)];
    if (f.flag < 0) return;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int g = lane >> 2, t4 = lane & 3;
    extern __shared__ __align__(16) double smem[];
-   const int sld = wcap + 1;
+   const int sld = wcap + 4;
    double* sA = smem;                        // element (r,c) of the block at sA[r + c*sld]
    double* sX = sA + (size_t)wcap * sld;     // X(r1+i, k) of the current sub-panel at sX[k*XLD + i]
-   double* sLc = sX + NB * XLD;
-   double* sLj = sLc + NB * LDS;             // L_jj in pivot order, sLj[i + k*NB]
-   double* srow = sLj + NB * NB;
+   double* sXa = wcap > NB ? sX + NB * XLD : sX;   // permuted rows below the sub-panel, k-major
+   double* sLc = sXa;                        // multipliers of the pivot loop (dead before sXa is filled)
+   double* sLj = sXa + (wcap > NB ? NB * XLD : NB * LDS);   // L_jj in pivot order, sLj[i + k*NB]
+   double* sInv = sLj + NB * NB;             // sInv[k*LDBB + c] = inv(L_jj)(c,k)
+   double* srow = sInv + NB * LDBB;
    double* sdk = srow + 2 * NB + 2;          // D^{-1} of the block (SSIDS format)
    double* sdd = sdk + 2 * PB + 2;           // D of the block: diagonal, off-diagonal
    int* slperm = reinterpret_cast<int*>(sdd + 2 * PB + 2);
@@ -285,6 +274,11 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
    int* sptj = spord + NB;
    int* smisc = sptj + NB;                   // 0: error flag, 1: first failed column of the sub-panel, 2: moved
 
+   const bool dbg = prm.debug && blockIdx.x == 0 && tid == 0;
+   long long tq[16];
+   int ntq = 0;
+#define B200_TICK() do { if (dbg && ntq < 16) tq[ntq++] = clock64(); } while (0)
+   B200_TICK();
    // ---- close the previous block
    int done = f.done, gend = f.gend, w = f.w;
    if (w > 0) {
@@ -302,6 +296,16 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
       }
       gend -= nfail;
    }
+   // everything the rest of the kernel needs from the front record (the stores below may alias it)
+   const size_t ldl = f.ldl;
+   const int wc = f.wc;
+   double* const fL = f.L;
+   double* const fWld = f.Wld;
+   double* const L11g = f.dbuf;
+   double* const A0g = f.dbuf + (size_t)PB * wc;
+   double* const dkg = f.dbuf + 2 * (size_t)PB * wc;
+   double* const Linvg = dkg + 2 * PB + 2;
+   int* const ibuf = f.ibuf;
    __syncthreads();
    w = finish_only ? 0 : max(0, min(wcap, gend - done));   // wcap <= PB: the launch's shared-memory capacity
    if (tid == 0) {
@@ -310,31 +314,28 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
    }
    if (w == 0) return;
 
-   // ---- load the lower triangle (and keep a copy for the restore path)
-   const size_t ldl = f.ldl;
-   double* L11g = f.dbuf;
-   double* A0g = f.dbuf + (size_t)PB * f.wc;
+   // ---- load the lower triangle (asynchronous copies), then keep a copy for the restore path
    {
-      const double* Lb = f.L + (size_t)done * ldl + done;
+      const double* Lb = fL + (size_t)done * ldl + done;
       for (int c = warp; c < w; c += 8)
          for (int r = lane + (c & ~31); r < w; r += 32)
-            if (r >= c) {
-               const double v = Lb[(size_t)c * ldl + r];
-               sA[r + c * sld] = v;
-               A0g[r + c * PB] = v;
-            }
+            if (r >= c) cp_async8(sA + r + c * sld, Lb + (size_t)c * ldl + r, true);
+      cp_async_commit();
+      if (tid < 8) smisc[tid] = 0;
+      cp_async_wait<0>();
+      __syncthreads();
+      for (int c = warp; c < w; c += 8)
+         for (int r = lane + (c & ~31); r < w; r += 32)
+            if (r >= c) A0g[r + c * PB] = sA[r + c * sld];
    }
-   if (tid < 8) smisc[tid] = 0;
-   __syncthreads();
+   B200_TICK();   // 1: closed + loaded
 
    int fail_blk = w;
    unsigned anymoved = 0;
-   double* Linvg = f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2;
-   int jinv = -1;      // sub-panel whose L_jj sits in sLj and still needs its inverse
    for (int c0 = 0; c0 < w; c0 += NB) {
       const int wj = min(NB, w - c0), r1 = c0 + NB;
-      // a. pivoting on the diagonal sub-block (warp 0); meanwhile warp 1 inverts the previous L_jj
-      if (warp == 1 && jinv >= 0) warp_inv32(sLj, Linvg + (size_t)jinv * NB * NB, lane);
+      const int nr = max(0, w - r1);            // rows of the block below the sub-panel
+      // a. pivoting on the diagonal sub-block (warp 0)
       if (warp == 0) {
          double a[NB];
 #pragma unroll
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
          if (lane == 0) { smisc[0] = err; smisc[1] = wj; smisc[2] = pm != 0u; }
       }
       __syncthreads();
+      if (c0 == 0) B200_TICK();   // 2: first sub-panel pivoted
       if (smisc[0] != 0) {
          if (tid == 0) { f.flag = smisc[0]; f.w = 0; }
          return;
@@ -367,7 +369,14 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
                tmp[s] = (c < c0 && lane < wj) ? sA[(c0 + spord[lane]) + c * sld] : 0.0;
             }
          }
-         __syncthreads();
+         double lv[NB / 8];
+#pragma unroll
+         for (int s = 0; s < NB / 8; ++s) {
+            const int k = warp + 8 * s;
+            lv[s] = 0.0;
+            if (lane < wj && k < wj) lv[s] = lane > k ? sLc[spord[lane] + k * LDS] : (lane == k ? 1.0 : 0.0);
+         }
+         __syncthreads();          // sLc (aliased by sXa) and the old rows have been read
          if (moved) {
 #pragma unroll
             for (int s = 0; s < (PB - NB) / 8; ++s) {
@@ -375,53 +384,100 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
                if (c < c0 && lane < wj) sA[(c0 + lane) + c * sld] = tmp[s];
             }
          }
-         for (int k = warp; k < NB; k += 8) {
-            double lv = 0.0;
-            if (lane < wj && k < wj) lv = lane > k ? sLc[spord[lane] + k * LDS] : (lane == k ? 1.0 : 0.0);
-            sLj[lane + k * NB] = lv;
-            sA[(c0 + lane) + (c0 + k) * sld] = lv;
+#pragma unroll
+         for (int s = 0; s < NB / 8; ++s) {
+            const int k = warp + 8 * s;
+            sLj[lane + k * NB] = lv[s];
+            sA[(c0 + lane) + (c0 + k) * sld] = lv[s];
          }
          if (tid < NB) {
             slperm[c0 + tid] = c0 + (tid < wj ? spord[tid] : tid);
             sptype[c0 + tid] = tid < wj ? sptj[tid] : 0;
          }
+         // rows below the sub-panel, columns in pivot order, k-major: the A operand of X = A inv(L_jj)^T
+         for (int k = warp; k < NB; k += 8) {
+            const int src = c0 + spord[k];
+            for (int i = lane; i < ((nr + 7) & ~7); i += 32) sXa[k * XLD + i] = i < nr ? sA[(r1 + i) + src * sld] : 0.0;
+         }
       }
       __syncthreads();
-      jinv = c0 / NB;
+      if (c0 == 0) B200_TICK();   // 3: phase b
+      // b2. inverse of L_jj (one warp): needed by k_apply and by the rows below
+      if (warp == 0) {
+         double z[NB];
+#pragma unroll
+         for (int i = 0; i < NB; ++i) z[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+         for (int k = 0; k < NB - 1; ++k) {
+            const double zk = z[k];
+#pragma unroll
+            for (int i = k + 1; i < NB; ++i) z[i] -= zk * sLj[i + k * NB];
+         }
+         // lane c holds column c of the inverse: row c of the k-major operand
+         double2* d2 = reinterpret_cast<double2*>(Linvg + (size_t)(c0 / NB) * NB * NB + lane * NB);
+         double2* s2 = reinterpret_cast<double2*>(sInv + lane * LDBB);
+#pragma unroll
+         for (int i2 = 0; i2 < NB / 2; ++i2) {
+            const double2 v = make_double2(z[2 * i2], z[2 * i2 + 1]);
+            d2[i2] = v;
+            s2[i2] = v;
+         }
+      }
       if (r1 >= w) break;
-      // c. rows of the block below the sub-panel: forward substitution, D^{-1}, a-posteriori test
-      if (tid < w - r1) {
-         const int r = r1 + tid;
-         double x[NB];
+      __syncthreads();
+      if (c0 == 0) B200_TICK();   // 4: inverse
+      // c. rows below: X = A inv(L_jj)^T on the tensor pipe.  Warp = column tile ct (8 columns) x
+      //    every second row tile; inv(L_jj)(c,k) = 0 for k > c bounds the k loop.
+      {
+         const int ct = warp & 3, rt0 = warp >> 2, nrt = (nr + 7) >> 3;
+         double acc[6][2];
 #pragma unroll
-         for (int k = 0; k < NB; ++k) x[k] = sA[r + (c0 + spord[k]) * sld];
+         for (int i = 0; i < 6; ++i) acc[i][0] = acc[i][1] = 0.0;
+         const double* as = sXa + t4 * XLD + rt0 * 8 + g;
+         const double* bs = sInv + t4 * LDBB + ct * 8 + g;
+         const int kend = 8 * (ct + 1);
+         for (int ks = 0; ks < kend; ks += 4) {
+            const double b = bs[ks * LDBB];
 #pragma unroll
-         for (int k = 0; k < NB; ++k) {
-            const double xk = x[k];
-#pragma unroll
-            for (int c = k + 1; c < NB; ++c) x[c] -= xk * sLj[c + k * NB];
+            for (int i = 0; i < 6; ++i)
+               if (rt0 + 2 * i < nrt) dmma(acc[i][0], acc[i][1], as[ks * XLD + 16 * i], b);
          }
-         int myfail = NB;
 #pragma unroll
-         for (int k = NB - 1; k >= 0; --k) {
-            const int pt = sptj[k];
-            double l;
-            if (pt == 0) {
-               const double d11 = sdk[2 * (c0 + k)];
-               if (d11 == 0.0) l = (fabs(x[k]) < prm.small_) ? 0.0 : DINF * x[k];
-               else l = x[k] * d11;
-            } else if (pt == 1) {
-               l = sdk[2 * (c0 + k)] * x[k] + sdk[2 * (c0 + k) + 1] * x[(k + 1) & (NB - 1)];
-            } else {
-               l = sdk[2 * (c0 + k) - 1] * x[(k - 1) & (NB - 1)] + sdk[2 * (c0 + k) + 1] * x[k];
+         for (int i = 0; i < 6; ++i)
+            if (rt0 + 2 * i < nrt) {
+               sX[(ct * 8 + 2 * t4) * XLD + (rt0 + 2 * i) * 8 + g] = acc[i][0];
+               sX[(ct * 8 + 2 * t4 + 1) * XLD + (rt0 + 2 * i) * 8 + g] = acc[i][1];
             }
-            if (!prm.posdef && !(fabs(l) <= prm.lim)) myfail = min(myfail, k);
-            sA[r + (c0 + k) * sld] = l;
-            sX[k * XLD + tid] = x[k];
-         }
-         if (myfail < NB) atomicMin(&smisc[1], myfail);
       }
       __syncthreads();
+      // c2. L = X D^{-1}, a-posteriori test; thread = (row, half of the columns)
+      {
+         const int i = tid & 127, kq = tid >> 7;
+         if (i < nr) {
+            int myfail = NB;
+#pragma unroll
+            for (int q = NB / 2 - 1; q >= 0; --q) {
+               const int k = kq * (NB / 2) + q;
+               const double xv = sX[k * XLD + i];
+               const int pt = sptj[k];
+               double l;
+               if (pt == 0) {
+                  const double d11 = sdk[2 * (c0 + k)];
+                  if (d11 == 0.0) l = (fabs(xv) < prm.small_) ? 0.0 : DINF * xv;
+                  else l = xv * d11;
+               } else if (pt == 1) {
+                  l = sdk[2 * (c0 + k)] * xv + sdk[2 * (c0 + k) + 1] * sX[(k + 1) * XLD + i];
+               } else {
+                  l = sdk[2 * (c0 + k) - 1] * sX[(k - 1) * XLD + i] + sdk[2 * (c0 + k) + 1] * xv;
+               }
+               if (!prm.posdef && !(fabs(l) <= prm.lim)) myfail = min(myfail, k);
+               sA[(r1 + i) + (c0 + k) * sld] = l;
+            }
+            if (myfail < NB) atomicMin(&smisc[1], myfail);
+         }
+      }
+      __syncthreads();
+      if (c0 == 0) B200_TICK();   // 5: phase c
       if (smisc[1] < NB) {
          // a column failed inside the block: the block ends with this sub-panel; the columns after
          // it stay candidates and are treated as ordinary rows by k_apply
@@ -429,68 +485,73 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
          w = r1;
          break;
       }
-      // e. update the rest of the block: A(r,c) -= sum_k L(r,k) X(c,k), 4x4 micro-tiles of the lower triangle
+      // e. update the rest of the block on the tensor pipe: A(r,c) -= sum_k L(r,k) X(c,k); work items
+      //    are strips of 8 rows x 32 columns that touch the lower triangle, dealt round robin to warps
       {
-         const int nt = (w - r1 + 3) >> 2, ntile = nt * (nt + 1) / 2;
-         for (int idx = tid; idx < ntile; idx += 256) {
-            int ti = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
-            while (ti * (ti + 1) / 2 > idx) --ti;
-            while ((ti + 1) * (ti + 2) / 2 <= idx) ++ti;
-            const int tj = idx - ti * (ti + 1) / 2;
-            const int rb = r1 + 4 * ti, cb = 4 * tj;
-            double acc[4][4];
+         const int nrt = (nr + 7) >> 3;
+         int item = 0;
+         for (int st = 0; st < nrt; ++st)
+            for (int cb = 0; cb <= ((8 * st + 7) >> 5); ++cb, ++item) {
+               if ((item & 7) != warp) continue;
+               double acc[4][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+               for (int jt = 0; jt < 4; ++jt) acc[jt][0] = acc[jt][1] = 0.0;
+               const double* as = sA + (r1 + 8 * st + g) + (size_t)(c0 + t4) * sld;
+               const double* bs = sX + t4 * XLD + cb * 32 + g;
 #pragma unroll
-               for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < NB; ++k) {
-               double lr[4], xc[4];
+               for (int ks = 0; ks < NB; ks += 4) {
+                  const double av = as[ks * sld];
 #pragma unroll
-               for (int i = 0; i < 4; ++i) { lr[i] = sA[(rb + i) + (c0 + k) * sld]; xc[i] = sX[k * XLD + cb + i]; }
+                  for (int jt = 0; jt < 4; ++jt) dmma(acc[jt][0], acc[jt][1], av, bs[ks * XLD + jt * 8]);
+               }
+               double* cs = sA + (r1 + 8 * st + g) + (size_t)(r1 + cb * 32 + 2 * t4) * sld;
 #pragma unroll
-               for (int i = 0; i < 4; ++i)
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) acc[i][j] += lr[i] * xc[j];
+               for (int jt = 0; jt < 4; ++jt) {
+                  cs[(jt * 8) * sld] -= acc[jt][0];
+                  cs[(jt * 8 + 1) * sld] -= acc[jt][1];
+               }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-               for (int j = 0; j < 4; ++j) sA[(rb + i) + (r1 + cb + j) * sld] -= acc[i][j];
-         }
       }
       __syncthreads();
+      if (c0 == 0) B200_TICK();   // 6: phase e
    }
    __syncthreads();
-   if (warp == 1 && jinv >= 0) warp_inv32(sLj, Linvg + (size_t)jinv * NB * NB, lane);
+   B200_TICK();      // all sub-panels
 
    // ---- publish: L11 (unit lower, pivot order), L11*D into Wld, D^{-1}, pivot lists
    {
       const int wr = (w + NB - 1) & ~(NB - 1);
-      for (int k = warp; k < wr; k += 8)
+      for (int k = warp; k < wr; k += 8) {
+         const int pt = k < w ? sptype[k] : 0;
+         const double dd0 = sdd[2 * (k < w ? k : 0)], dd1 = sdd[2 * (k < w ? k : 0) + 1];
+         const int kn = pt == 1 ? k + 1 : (pt == 2 ? k - 1 : k);   // partner column of a 2x2
          for (int i = lane; i < wr; i += 32) {
             double lv = 0.0;
             if (i < w && k < w) lv = i > k ? sA[i + k * sld] : (i == k ? 1.0 : 0.0);
             L11g[i + (size_t)k * PB] = lv;
             if (i > k && i < w) {
-               const int pt = sptype[k];
-               double x;
-               if (pt == 0) x = lv * sdd[2 * k];
-               else if (pt == 1) x = lv * sdd[2 * k] + sA[i + (k + 1) * sld] * sdd[2 * k + 1];
-               else x = sA[i + (k - 1) * sld] * sdd[2 * k + 1] + lv * sdd[2 * k];
-               f.Wld[(size_t)k * ldl + done + i] = x;
+               double x = lv * dd0;
+               if (pt != 0) x += sA[i + kn * sld] * dd1;
+               fWld[(size_t)k * ldl + done + i] = x;
             }
          }
-      double* dkg = f.dbuf + 2 * (size_t)PB * f.wc;
+      }
       for (int i = tid; i < 2 * w + 2; i += 256) dkg[i] = i < 2 * w ? sdk[i] : 0.0;
-      if (tid < w) { f.ibuf[tid] = slperm[tid]; f.ibuf[PB + tid] = sptype[tid]; }
+      if (tid < w) { ibuf[tid] = slperm[tid]; ibuf[PB + tid] = sptype[tid]; }
       if (tid < 4) {
          unsigned mask = 0u;
          for (int b = 0; b < 32; ++b) { const int k = tid * 32 + b; if (k < w && sptype[k] == 2) mask |= 1u << b; }
          f.p2mask[tid] = mask;
       }
-      if (tid == 0) { f.ibuf[2 * PB] = (int)anymoved; f.w = w; f.fail = fail_blk; }
+      if (tid == 0) { ibuf[2 * PB] = (int)anymoved; f.w = w; f.fail = fail_blk; }
    }
+   B200_TICK();      // published
+   if (dbg) {
+      printf("[k_block] w=%d ticks:", w);
+      for (int i = 1; i < ntq; ++i) printf(" %lld", tq[i] - tq[i - 1]);
+      printf("\n");
+   }
+#undef B200_TICK
 }
 
 // ------------------------------------------------------------------------------------------
@@ -501,8 +562,7 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
 //    L_j = X_j D^{-1} (in place), X_j kept in Wld, a-posteriori test |l| <= 1/u
 // ------------------------------------------------------------------------------------------
 constexpr int AR = 64;             // rows per CTA in k_apply
-constexpr int LDX = AR + 4;        // k-major smem leading dimensions, = 4 mod 16: conflict-free fragments
-constexpr int LDBB = NB + 4;
+constexpr int LDX = AR + 4;        // k-major smem leading dimension, = 4 mod 16: conflict-free fragments
 __host__ __device__ inline size_t apply_smem_bytes(int wcap) {
    const int nb = wcap / NB;
    return sizeof(double) * ((size_t)wcap * LDX + NB * LDX + (size_t)(nb * (nb - 1) / 2 + nb) * NB * LDBB + 2 * PB + 2) +
