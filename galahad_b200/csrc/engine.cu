@@ -669,6 +669,8 @@ class Numeric {
    size_t pin_i_cap = 0;
    int *d_child_doff = nullptr, *d_list = nullptr, *d_collect = nullptr, *d_counters = nullptr;
    int64_t* d_tileptr = nullptr;
+   int *d_updmap = nullptr, *pin_updmap = nullptr;   // CTA -> (front, part, parts) maps of the trailing updates
+   static constexpr size_t UPDMAP_CAP = (size_t)3 << 20;   // ints
    int64_t* d_xw_off = nullptr;
    int64_t* d_part_off = nullptr;
    int* d_slist = nullptr;
@@ -702,6 +704,8 @@ class Numeric {
       cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
+      if (pin_updmap) cudaFreeHost(pin_updmap);
+      cudaFree(d_updmap);
       if (st) cudaStreamDestroy(st);
       if (ev0) cudaEventDestroy(ev0);
       if (ev1) cudaEventDestroy(ev1);
@@ -756,6 +760,8 @@ int Numeric::init() {
    CU(cudaMalloc(&d_collect, sizeof(int) * 3 * nn));
    CU(cudaMalloc(&d_counters, sizeof(int) * 8));
    CU(cudaMalloc(&d_tileptr, sizeof(int64_t) * (nn + 1)));
+   CU(cudaMalloc(&d_updmap, sizeof(int) * UPDMAP_CAP));
+   CU(cudaMallocHost(&pin_updmap, sizeof(int) * UPDMAP_CAP));
    CU(cudaMalloc(&d_xw_off, sizeof(int64_t) * (nn + 1)));
    CU(cudaMalloc(&d_part_off, sizeof(int64_t) * (nn + 1)));
    CU(cudaMalloc(&d_slist, sizeof(int) * nn));
@@ -830,11 +836,13 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    };
    std::vector<int> lvl_list, tpp_list;
    std::vector<int64_t> tileptr;
+   size_t updmap_used = 0;
    for (int l = 0; l < P->nlevels && flag >= 0; ++l) {
       const int s0 = P->lvl_ptr[l], s1 = P->lvl_ptr[l + 1], ns = s1 - s0;
       Arena& ca = car[l & 1];
       ca.reset();
       war.reset();
+      updmap_used = 0;   // the previous level ended with a stream synchronisation
       // sizes with delays
       size_t totL = 0, totC = 0, totD = 0, totP = 0, totW = 0;
       int nactive_lvl = 0;
@@ -994,14 +1002,55 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             const int ncolchunks = (maxn + 63) / 64;
             const int ycommit = 1 + ncolchunks + (maxm + 255) / 256;
             const int nouter = (maxn + PB - 1) / PB;
+            // trailing-update work maps of this bucket: CTAs in proportion to the fronts' tile counts
+            // (shapes without failed pivots; every front of the launch keeps at least one CTA, so a
+            // front that lags behind is still updated correctly, only slower)
+            std::vector<int> map_off(nouter + 1, 0), map_na(nouter, 0);
+            {
+               std::vector<int> hmap;
+               std::vector<int64_t> tl;
+               for (int ob = 0; ob < nouter; ++ob) {
+                  int na = 0;
+                  for (int q = i0; q < i1; ++q) if (active[order[q]] && (hfr[order[q]].n + PB - 1) / PB > ob) na = q - i0 + 1;
+                  map_na[ob] = na;
+                  tl.assign(na, 0);
+                  int64_t total = 0;
+                  for (int q = 0; q < na; ++q) {
+                     const FrontDev& ff = hfr[order[i0 + q]];
+                     if (!active[order[i0 + q]]) continue;
+                     const int t = ff.m - std::min(ff.n, (ob + 1) * PB);
+                     if (t <= 0 || ff.n <= ob * PB) continue;
+                     const int ntr = (t + TM - 1) / TM, ntc = (t + TN - 1) / TN;
+                     int64_t cnt = 0;
+                     for (int ti = 0; ti < ntr; ++ti) cnt += std::min(ntc, 2 * ti + 2);
+                     tl[q] = cnt;
+                     total += cnt;
+                  }
+                  const int64_t target = std::min<int64_t>(std::max<int64_t>(total, 1), 2 * 296);
+                  for (int q = 0; q < na; ++q) {
+                     int parts = total > 0 ? (int)((tl[q] * target + total / 2) / total) : 1;
+                     parts = std::max(1, (int)std::min<int64_t>(parts, std::max<int64_t>(tl[q], 1)));
+                     for (int pp = 0; pp < parts; ++pp) { hmap.push_back(q); hmap.push_back(pp); hmap.push_back(parts); }
+                  }
+                  map_off[ob + 1] = (int)hmap.size();
+               }
+               if (updmap_used + hmap.size() > UPDMAP_CAP) {   // staging in use by earlier copies: drain first
+                  CU(cudaStreamSynchronize(st));
+                  updmap_used = 0;
+               }
+               if (hmap.size() > UPDMAP_CAP) return stats.flag = SSIDS_ERROR_ALLOCATION;
+               memcpy(pin_updmap + updmap_used, hmap.data(), sizeof(int) * hmap.size());
+               if (!hmap.empty())
+                  CU(cudaMemcpyAsync(d_updmap + updmap_used, pin_updmap + updmap_used, sizeof(int) * hmap.size(), cudaMemcpyHostToDevice, st));
+               for (int ob = 0; ob <= nouter; ++ob) map_off[ob] += (int)updmap_used;
+               updmap_used += hmap.size();
+            }
             for (int ob = 0; ob < nouter; ++ob) {
-               int na = 0;   // slots [b0, b0+na) cover every front that still has a block number ob
-               for (int q = i0; q < i1; ++q) if (active[order[q]] && (hfr[order[q]].n + PB - 1) / PB > ob) na = q - i0 + 1;
+               const int na = map_na[ob];   // slots [b0, b0+na) cover every front that still has a block number ob
                if (na == 0) break;
                int maxw = 0;
                for (int q = 0; q < na; ++q) if (active[order[i0 + q]]) maxw = std::max(maxw, std::min(PB, hfr[order[i0 + q]].n - ob * PB));
                const int wcap = (maxw + NB - 1) / NB * NB;
-               const int rem = maxm - ob * PB;     // rows of the tallest front from this block on (without failures)
                // blocks shortened by failed pivots leave `done` behind ob*PB, so the row grid covers the
                // whole front; CTAs above the block exit at once
                const int yapply = std::max(1, (maxm + AR - 1) / AR);
@@ -1010,9 +1059,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                k_commit<<<dim3(na, ycommit), 256, 0, st>>>(d_fr, lst, b0, ncolchunks);
                launches += 3;
                {
-                  int nt = std::max(1, (rem + TM - 1) / TM);
-                  int64_t tiles = (int64_t)nt * (nt + 1);
-                  int ygrid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, std::max<int64_t>(1, 296 / std::max(na, 1))));
+                  const int nct = (map_off[ob + 1] - map_off[ob]) / 3;
                   if (o.profile) {
                      for (int q = 0; q < na; ++q) {
                         const FrontDev& ff = hfr[order[i0 + q]];
@@ -1022,7 +1069,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                      }
                      prof_begin();
                   }
-                  k_update<<<dim3(na, ygrid), 256, UPD_SMEM, st>>>(d_fr, lst, b0);
+                  k_update<<<nct, 256, UPD_SMEM, st>>>(d_fr, lst, b0, d_updmap + map_off[ob]);
                   if (o.profile) prof_end();
                   ++launches;
                }
@@ -1066,7 +1113,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          k_block<<<nt, 256, block_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, 0, wcap);
          k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap);
          k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks);
-         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0);
+         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, nullptr);
          if (trace) for (int s : tpp_list) trace_fronts("retry", s, 1);
          k_block<<<nt, 256, block_smem_bytes(NB), st>>>(d_fr, d_list, 0, prm, 1, NB);
          launches += 5;

@@ -770,8 +770,13 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
 // two CTAs per SM.  ncu (profiles/r1_notes.md) showed the kernel bound by per-warp instruction
 // issue around the MMAs, so interior tiles take a path without bounds predicates and with
 // strength-reduced addresses, and tile coordinates advance incrementally.
-__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0) {
-   const FrontDev& f = fr[front_slot(list, slot0)];
+// Work distribution: with `map` (one int3 per CTA: front offset, part, parts) CTAs are dealt to the fronts
+// of the launch in proportion to their tile counts; without it the grid is (fronts, parts).
+__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0, const int* __restrict__ map) {
+   int fq, part, nparts;
+   if (map) { fq = map[3 * blockIdx.x]; part = map[3 * blockIdx.x + 1]; nparts = map[3 * blockIdx.x + 2]; }
+   else { fq = blockIdx.x; part = blockIdx.y; nparts = gridDim.y; }
+   const FrontDev& f = fr[list ? list[fq] : slot0 + fq];
    const int w = f.w;
    if (f.flag < 0 || w == 0) return;
    // pivots accepted in the current block; the region starts right behind them, so columns of the
@@ -799,7 +804,7 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    const int nchunk = (kc + BK - 1) / BK;
    // tile (ti,tj) touches the lower triangle iff tj <= 2*ti+1 (TM = 2*TN, shared origin cbeg);
    // tiles are numbered row by row; a CTA walks its tiles incrementally
-   int ti = 0, tj = blockIdx.y;
+   int ti = 0, tj = part;
    for (;;) {
       // normalise (ti,tj)
       while (ti < ntr) { const int wd = min(ntc, 2 * ti + 2); if (tj < wd) break; tj -= wd; ++ti; }
@@ -939,6 +944,6 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
                }
             }
       }
-      tj += gridDim.y;
+      tj += nparts;
    }
 }
