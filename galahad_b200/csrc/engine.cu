@@ -689,6 +689,9 @@ class Numeric {
    std::vector<int> part_kind, owner;      // per slot; owner -1 = root part
    int my_rank = 0, nranks = 1;
    cudaStream_t st = nullptr;
+   static constexpr int NAUX = 4;
+   cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+   cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
    int cuda_err = 0;
    int64_t launches = 0;
@@ -707,6 +710,8 @@ class Numeric {
       if (pin_updmap) cudaFreeHost(pin_updmap);
       cudaFree(d_updmap);
       if (st) cudaStreamDestroy(st);
+      for (int g = 0; g < NAUX; ++g) { if (aux[g]) cudaStreamDestroy(aux[g]); if (ev_join[g]) cudaEventDestroy(ev_join[g]); }
+      if (ev_fork) cudaEventDestroy(ev_fork);
       if (ev0) cudaEventDestroy(ev0);
       if (ev1) cudaEventDestroy(ev1);
       if (ev2) cudaEventDestroy(ev2);
@@ -747,6 +752,11 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes(PB)));
    const int nn = std::max(P->nnodes, 1);
    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+   for (int g = 0; g < NAUX; ++g) {
+      CU(cudaStreamCreateWithFlags(&aux[g], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ev_join[g], cudaEventDisableTiming));
+   }
+   CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
    CU(cudaEventCreate(&ev0));
    CU(cudaEventCreate(&ev1));
    CU(cudaEventCreate(&ev2));
@@ -826,6 +836,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    // B200LDLT_TRACE=1: print the progress counters of every front after each block step (debugging aid;
    // synchronises the stream)
    const bool trace = getenv("B200LDLT_TRACE") != nullptr;
+   const int upd_share = getenv("B200LDLT_UPD_SHARE") ? atoi(getenv("B200LDLT_UPD_SHARE")) : 148;
+   const int max_groups = getenv("B200LDLT_GROUPS") ? std::max(1, std::min((int)NAUX, atoi(getenv("B200LDLT_GROUPS")))) : (int)NAUX;
    auto trace_fronts = [&](const char* what, int slot_first, int count) {
       std::vector<FrontDev> tmp(count);
       cudaStreamSynchronize(st);
@@ -984,21 +996,15 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             }
             cudaEventRecord(prof_ev[prof_used], st);
          };
-         auto prof_end = [&]() { cudaEventRecord(prof_ev[prof_used + 1], st); prof_used += 2; };
-         int i0 = 0;
-         while (i0 < ns) {
-            int c = cls(order[i0]), i1 = i0;
+         auto prof_end = [&]() { cudaEventRecord(prof_ev[prof_used + 1], st); prof_used += 2; };   // profile mode is single-stream
+         // one chunk = a contiguous slot range of one size class, processed block by block on stream sx
+         auto run_chunk = [&](int j0, int j1, cudaStream_t sx, bool single) -> int {
             int maxm = 0, maxn = 0;
-            while (i1 < ns && cls(order[i1]) == c) {
-               if (active[order[i1]]) {
-                  maxm = std::max(maxm, hfr[order[i1]].m);
-                  maxn = std::max(maxn, hfr[order[i1]].n);
-               }
-               ++i1;
-            }
-            if (maxm == 0) { i0 = i1; continue; }
+            for (int q = j0; q < j1; ++q)
+               if (active[order[q]]) { maxm = std::max(maxm, hfr[order[q]].m); maxn = std::max(maxn, hfr[order[q]].n); }
+            if (maxm == 0) return 0;
             const int* lst = nullptr;
-            const int b0 = s0 + i0;   // first slot of the bucket
+            const int b0 = s0 + j0;   // first slot of the bucket
             const int ncolchunks = (maxn + 63) / 64;
             const int ycommit = 1 + ncolchunks + (maxm + 255) / 256;
             const int nouter = (maxn + PB - 1) / PB;
@@ -1011,13 +1017,13 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                std::vector<int64_t> tl;
                for (int ob = 0; ob < nouter; ++ob) {
                   int na = 0;
-                  for (int q = i0; q < i1; ++q) if (active[order[q]] && (hfr[order[q]].n + PB - 1) / PB > ob) na = q - i0 + 1;
+                  for (int q = j0; q < j1; ++q) if (active[order[q]] && (hfr[order[q]].n + PB - 1) / PB > ob) na = q - j0 + 1;
                   map_na[ob] = na;
                   tl.assign(na, 0);
                   int64_t total = 0;
                   for (int q = 0; q < na; ++q) {
-                     const FrontDev& ff = hfr[order[i0 + q]];
-                     if (!active[order[i0 + q]]) continue;
+                     const FrontDev& ff = hfr[order[j0 + q]];
+                     if (!active[order[j0 + q]]) continue;
                      const int t = ff.m - std::min(ff.n, (ob + 1) * PB);
                      if (t <= 0 || ff.n <= ob * PB) continue;
                      const int ntr = (t + TM - 1) / TM, ntc = (t + TN - 1) / TN;
@@ -1026,7 +1032,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                      tl[q] = cnt;
                      total += cnt;
                   }
-                  const int64_t target = std::min<int64_t>(std::max<int64_t>(total, 1), 2 * 296);
+                  // chunks that share the GPU with other streams keep to about half of the CTA slots, so that
+                  // another chunk's block factorisation finds a free SM while this update runs
+                  const int64_t target = std::min<int64_t>(std::max<int64_t>(total, 1), single ? 2 * 296 : upd_share);
                   for (int q = 0; q < na; ++q) {
                      int parts = total > 0 ? (int)((tl[q] * target + total / 2) / total) : 1;
                      parts = std::max(1, (int)std::min<int64_t>(parts, std::max<int64_t>(tl[q], 1)));
@@ -1036,12 +1044,13 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                }
                if (updmap_used + hmap.size() > UPDMAP_CAP) {   // staging in use by earlier copies: drain first
                   CU(cudaStreamSynchronize(st));
+                  for (int g2 = 0; g2 < NAUX; ++g2) CU(cudaStreamSynchronize(aux[g2]));
                   updmap_used = 0;
                }
-               if (hmap.size() > UPDMAP_CAP) return stats.flag = SSIDS_ERROR_ALLOCATION;
+               if (hmap.size() > UPDMAP_CAP) return SSIDS_ERROR_ALLOCATION;
                memcpy(pin_updmap + updmap_used, hmap.data(), sizeof(int) * hmap.size());
                if (!hmap.empty())
-                  CU(cudaMemcpyAsync(d_updmap + updmap_used, pin_updmap + updmap_used, sizeof(int) * hmap.size(), cudaMemcpyHostToDevice, st));
+                  CU(cudaMemcpyAsync(d_updmap + updmap_used, pin_updmap + updmap_used, sizeof(int) * hmap.size(), cudaMemcpyHostToDevice, sx));
                for (int ob = 0; ob <= nouter; ++ob) map_off[ob] += (int)updmap_used;
                updmap_used += hmap.size();
             }
@@ -1049,34 +1058,75 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                const int na = map_na[ob];   // slots [b0, b0+na) cover every front that still has a block number ob
                if (na == 0) break;
                int maxw = 0;
-               for (int q = 0; q < na; ++q) if (active[order[i0 + q]]) maxw = std::max(maxw, std::min(PB, hfr[order[i0 + q]].n - ob * PB));
+               for (int q = 0; q < na; ++q) if (active[order[j0 + q]]) maxw = std::max(maxw, std::min(PB, hfr[order[j0 + q]].n - ob * PB));
                const int wcap = (maxw + NB - 1) / NB * NB;
                // blocks shortened by failed pivots leave `done` behind ob*PB, so the row grid covers the
                // whole front; CTAs above the block exit at once
                const int yapply = std::max(1, (maxm + AR - 1) / AR);
-               k_block<<<na, 256, block_smem_bytes(wcap), st>>>(d_fr, lst, b0, prm, 0, wcap);
-               k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), st>>>(d_fr, lst, b0, prm, wcap);
-               k_commit<<<dim3(na, ycommit), 256, 0, st>>>(d_fr, lst, b0, ncolchunks);
+               k_block<<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap);
+               k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, wcap);
+               k_commit<<<dim3(na, ycommit), 256, 0, sx>>>(d_fr, lst, b0, ncolchunks);
                launches += 3;
                {
                   const int nct = (map_off[ob + 1] - map_off[ob]) / 3;
                   if (o.profile) {
                      for (int q = 0; q < na; ++q) {
-                        const FrontDev& ff = hfr[order[i0 + q]];
-                        if (!active[order[i0 + q]]) continue;
+                        const FrontDev& ff = hfr[order[j0 + q]];
+                        if (!active[order[j0 + q]]) continue;
                         double je = std::min<double>(ff.n, (ob + 1) * PB), kc2 = je - ob * PB, tt = ff.m - je;
                         if (kc2 > 0 && tt > 0) prof_flops += kc2 * tt * (tt + 1);
                      }
                      prof_begin();
                   }
-                  k_update<<<nct, 256, UPD_SMEM, st>>>(d_fr, lst, b0, d_updmap + map_off[ob]);
+                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob]);
                   if (o.profile) prof_end();
                   ++launches;
                }
                if (trace) trace_fronts("block", b0, na);
             }
-            k_block<<<i1 - i0, 256, block_smem_bytes(NB), st>>>(d_fr, lst, b0, prm, 1, NB);
+            k_block<<<j1 - j0, 256, block_smem_bytes(NB), sx>>>(d_fr, lst, b0, prm, 1, NB);
             ++launches;
+            return 0;
+         };
+         int i0 = 0;
+         bool forked = false;
+         while (i0 < ns) {
+            int c = cls(order[i0]), i1 = i0;
+            int nact = 0;
+            double work = 0;
+            while (i1 < ns && cls(order[i1]) == c) {
+               if (active[order[i1]]) { ++nact; work += (double)hfr[order[i1]].n * hfr[order[i1]].m * hfr[order[i1]].m; }
+               ++i1;
+            }
+            // a few large fronts: split them over streams so that one group's block factorisation
+            // overlaps another group's trailing update
+            int G = 1;
+            if (!o.profile && !trace && nact >= 2 && nact <= 128 && c >= 2) G = std::min(nact, max_groups);
+            if (G == 1) {
+               int rc2 = run_chunk(i0, i1, st, true);
+               if (rc2) return stats.flag = rc2;
+            } else {
+               if (!forked) { CU(cudaEventRecord(ev_fork, st)); forked = true; }
+               int j0 = i0;
+               double acc = 0;
+               for (int g2 = 0; g2 < G; ++g2) {
+                  int j1 = j0;
+                  const double goal = work * (g2 + 1) / G;
+                  while (j1 < i1 && (acc < goal || g2 == G - 1)) {
+                     if (active[order[j1]]) acc += (double)hfr[order[j1]].n * hfr[order[j1]].m * hfr[order[j1]].m;
+                     ++j1;
+                  }
+                  if (g2 == G - 1) j1 = i1;
+                  if (j1 > j0) {
+                     CU(cudaStreamWaitEvent(aux[g2], ev_fork, 0));
+                     int rc2 = run_chunk(j0, j1, aux[g2], false);
+                     if (rc2) return stats.flag = rc2;
+                     CU(cudaEventRecord(ev_join[g2], aux[g2]));
+                     CU(cudaStreamWaitEvent(st, ev_join[g2], 0));
+                  }
+                  j0 = j1;
+               }
+            }
             i0 = i1;
          }
       }

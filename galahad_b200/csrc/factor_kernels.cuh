@@ -803,67 +803,77 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    const bool vec16 = (cbeg & 1) == 0;      // 16-byte cp.async needs even row offsets (ldl is even)
    const int nchunk = (kc + BK - 1) / BK;
    // tile (ti,tj) touches the lower triangle iff tj <= 2*ti+1 (TM = 2*TN, shared origin cbeg);
-   // tiles are numbered row by row; a CTA walks its tiles incrementally
-   int ti = 0, tj = part;
-   for (;;) {
-      // normalise (ti,tj)
+   // tiles are numbered row by row; a CTA walks its tiles incrementally.  The first k-chunk of the
+   // NEXT tile is requested while the last chunk of the current one is multiplied, and its C tile
+   // is pulled towards L2.
+   auto normalise = [&](int& ti, int& tj) -> bool {
       while (ti < ntr) { const int wd = min(ntc, 2 * ti + 2); if (tj < wd) break; tj -= wd; ++ti; }
-      if (ti >= ntr) break;
+      return ti < ntr;
+   };
+   auto load_stage = [&](int rbase, int cbase, bool full, int chunk, int buf) {
+      const int kb = chunk * BK;
+      double* as = As + buf * BK * LDA;
+      double* bs = Bs + buf * BK * LDB;
+      if (full && kb + BK <= kc) {
+         // thread -> (k row = q*4 + tid/64, piece (tid%64)*2) for A; (q*8 + tid/32, (tid%32)*2) for B
+         const double* pa = Abase + (size_t)(kb + (tid >> 6)) * ldl + rbase + (tid & 63) * 2;
+         double* sa_ = as + (tid >> 6) * LDA + (tid & 63) * 2;
+         const size_t sta = 4 * ldl;
+#pragma unroll
+         for (int q = 0; q < 8; ++q) cp_async16(sa_ + q * 4 * LDA, pa + q * sta, 16);
+         const double* pb = Bbase + (size_t)(kb + (tid >> 5)) * ldl + cbase + (tid & 31) * 2;
+         double* sb_ = bs + (tid >> 5) * LDB + (tid & 31) * 2;
+         const size_t stb = 8 * ldl;
+#pragma unroll
+         for (int q = 0; q < 4; ++q) cp_async16(sb_ + q * 8 * LDB, pb + q * stb, 16);
+      } else if (vec16) {
+#pragma unroll
+         for (int q = 0; q < 8; ++q) {
+            const int e = q * 256 + tid, kk = e >> 6, rr = (e & 63) * 2;
+            const int ra = rbase + rr;
+            const int nb = (kb + kk < kc) ? (ra + 1 < m ? 16 : (ra < m ? 8 : 0)) : 0;
+            cp_async16(as + kk * LDA + rr, nb ? Abase + (size_t)(kb + kk) * ldl + ra : Abase, nb);
+         }
+#pragma unroll
+         for (int q = 0; q < 4; ++q) {
+            const int e = q * 256 + tid, kk = e >> 5, rr = (e & 31) * 2;
+            const int cb = cbase + rr;
+            const int nb = (kb + kk < kc) ? (cb + 1 < cend ? 16 : (cb < cend ? 8 : 0)) : 0;
+            cp_async16(bs + kk * LDB + rr, nb ? Bbase + (size_t)(kb + kk) * ldl + cb : Bbase, nb);
+         }
+      } else {
+#pragma unroll
+         for (int q = 0; q < 16; ++q) {
+            const int e = q * 256 + tid, kk = e >> 7, rr = e & 127;
+            const int ra = rbase + rr;
+            const bool ok = kb + kk < kc && ra < m;
+            cp_async8(as + kk * LDA + rr, ok ? Abase + (size_t)(kb + kk) * ldl + ra : Abase, ok);
+         }
+#pragma unroll
+         for (int q = 0; q < 8; ++q) {
+            const int e = q * 256 + tid, kk = e >> 6, rr = e & 63;
+            const int cb = cbase + rr;
+            const bool ok = kb + kk < kc && cb < cend;
+            cp_async8(bs + kk * LDB + rr, ok ? Bbase + (size_t)(kb + kk) * ldl + cb : Bbase, ok);
+         }
+      }
+      cp_async_commit();
+   };
+   int ti = 0, tj = part;
+   if (!normalise(ti, tj)) return;
+   int buf = 0;
+   {
+      const int rbase = cbeg + ti * TM, cbase = cbeg + tj * TN;
+      load_stage(rbase, cbase, (rbase + TM <= m) && (cbase + TN <= cend) && vec16, 0, 0);
+   }
+   for (;;) {
       const int rbase = cbeg + ti * TM, cbase = cbeg + tj * TN;
       const bool full = (rbase + TM <= m) && (cbase + TN <= cend) && vec16;
       const bool below = cbase + TN - 1 <= rbase;     // tile entirely below the diagonal
+      int nti = ti, ntj = tj + nparts;
+      const bool has_next = normalise(nti, ntj);
+      const int nrbase = cbeg + nti * TM, ncbase = cbeg + ntj * TN;
       double acc[4][4][2];
-      auto load_stage = [&](int chunk, int buf) {
-         const int kb = chunk * BK;
-         double* as = As + buf * BK * LDA;
-         double* bs = Bs + buf * BK * LDB;
-         if (full && kb + BK <= kc) {
-            // thread -> (k row = q*4 + tid/64, piece (tid%64)*2) for A; (q*8 + tid/32, (tid%32)*2) for B
-            const double* pa = Abase + (size_t)(kb + (tid >> 6)) * ldl + rbase + (tid & 63) * 2;
-            double* sa_ = as + (tid >> 6) * LDA + (tid & 63) * 2;
-            const size_t sta = 4 * ldl;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) cp_async16(sa_ + q * 4 * LDA, pa + q * sta, 16);
-            const double* pb = Bbase + (size_t)(kb + (tid >> 5)) * ldl + cbase + (tid & 31) * 2;
-            double* sb_ = bs + (tid >> 5) * LDB + (tid & 31) * 2;
-            const size_t stb = 8 * ldl;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) cp_async16(sb_ + q * 8 * LDB, pb + q * stb, 16);
-         } else if (vec16) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-               const int e = q * 256 + tid, kk = e >> 6, rr = (e & 63) * 2;
-               const int ra = rbase + rr;
-               const int nb = (kb + kk < kc) ? (ra + 1 < m ? 16 : (ra < m ? 8 : 0)) : 0;
-               cp_async16(as + kk * LDA + rr, nb ? Abase + (size_t)(kb + kk) * ldl + ra : Abase, nb);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-               const int e = q * 256 + tid, kk = e >> 5, rr = (e & 31) * 2;
-               const int cb = cbase + rr;
-               const int nb = (kb + kk < kc) ? (cb + 1 < cend ? 16 : (cb < cend ? 8 : 0)) : 0;
-               cp_async16(bs + kk * LDB + rr, nb ? Bbase + (size_t)(kb + kk) * ldl + cb : Bbase, nb);
-            }
-         } else {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-               const int e = q * 256 + tid, kk = e >> 7, rr = e & 127;
-               const int ra = rbase + rr;
-               const bool ok = kb + kk < kc && ra < m;
-               cp_async8(as + kk * LDA + rr, ok ? Abase + (size_t)(kb + kk) * ldl + ra : Abase, ok);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-               const int e = q * 256 + tid, kk = e >> 6, rr = e & 63;
-               const int cb = cbase + rr;
-               const bool ok = kb + kk < kc && cb < cend;
-               cp_async8(bs + kk * LDB + rr, ok ? Bbase + (size_t)(kb + kk) * ldl + cb : Bbase, ok);
-            }
-         }
-         cp_async_commit();
-      };
-      __syncthreads();   // previous tile's smem reads are done
-      load_stage(0, 0);
       // accumulators start as the C tile; the product is subtracted by feeding -B to the MMA
       const int r0 = rbase + wr * 32 + g, c0 = cbase + wc * 32 + 2 * t4;
       if (full && below) {
@@ -892,9 +902,24 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
             }
       }
       for (int ch = 0; ch < nchunk; ++ch) {
-         const int buf = ch & 1;
-         if (ch + 1 < nchunk) { load_stage(ch + 1, buf ^ 1); cp_async_wait<1>(); }
-         else cp_async_wait<0>();
+         if (ch + 1 < nchunk) {
+            load_stage(rbase, cbase, full, ch + 1, buf ^ 1);
+            cp_async_wait<1>();
+         } else if (has_next) {
+            load_stage(nrbase, ncbase, (nrbase + TM <= m) && (ncbase + TN <= cend) && vec16, 0, buf ^ 1);
+            {
+               // next C tile towards L2: 64 columns x 128 rows = 8 lines of 128 B per column
+               const int c = ncbase + (tid >> 2), r = nrbase + (tid & 3) * 32;
+               if (c < cend && r < m) {
+                  const double* pp = (c < fn) ? (Lp + (size_t)c * ldl + r) : (Cp + (size_t)(c - fn) * ldc + (r - fn));
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 16));
+               }
+            }
+            cp_async_wait<1>();
+         } else {
+            cp_async_wait<0>();
+         }
          __syncthreads();
          const double* as = As + buf * BK * LDA + wr * 32 + g + t4 * LDA;
          const double* bs = Bs + buf * BK * LDB + wc * 32 + g + t4 * LDB;
@@ -917,6 +942,7 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], -bf[cur][j]);
          }
          __syncthreads();
+         buf ^= 1;
       }
       // epilogue: store only
       if (full && below) {
@@ -944,6 +970,7 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
                }
             }
       }
-      tj += nparts;
+      if (!has_next) break;
+      ti = nti; tj = ntj;
    }
 }
