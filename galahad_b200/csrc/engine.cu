@@ -836,7 +836,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    // B200LDLT_TRACE=1: print the progress counters of every front after each block step (debugging aid;
    // synchronises the stream)
    const bool trace = getenv("B200LDLT_TRACE") != nullptr;
-   const int upd_share = getenv("B200LDLT_UPD_SHARE") ? atoi(getenv("B200LDLT_UPD_SHARE")) : 148;
+   const int upd_share = getenv("B200LDLT_UPD_SHARE") ? atoi(getenv("B200LDLT_UPD_SHARE")) : 296;
    const int max_groups = getenv("B200LDLT_GROUPS") ? std::max(1, std::min((int)NAUX, atoi(getenv("B200LDLT_GROUPS")))) : (int)NAUX;
    auto trace_fronts = [&](const char* what, int slot_first, int count) {
       std::vector<FrontDev> tmp(count);
