@@ -63,7 +63,12 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark(self):
+        """Start of the timed region: earlier samples (warm-up) are only used if nvidia-smi delivers
+        none inside the region (it samples every 100 ms and needs about a second to start)."""
+        self.t_mark = time.time()
 
     def stop(self):
         if not self.proc:
@@ -75,7 +80,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        inside = [ln for (t, ln) in self.lines if t >= t_mark]
+        window = "timed region"
+        if len(inside) < 2:
+            inside = [ln for (t, ln) in self.lines]
+            window = "warm-up + timed region (GPU under the same load)"
+        for ln in inside:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 7:
                 continue
@@ -90,7 +101,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         hi = [s for s in sm if s > 0.5 * max(sm)]
         return {"sm_mhz": float(np.median(hi if hi else sm)), "sm_max_mhz": float(max(mx)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def measure_fp64_peak(torch):
@@ -233,26 +244,34 @@ def run_ours(args):
         assert f >= 0, f
         return t1 - t0, t2 - t1
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    s.opt.reserved[0] = 1                  # profile mode: events around every trailing update
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
     barrier()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     res = [step_device() for _ in range(args.steps)]
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = e0.elapsed_time(e1)
-    s.opt.reserved[0] = 0
     tf = float(np.mean([r[0] for r in res]))
     ts = float(np.mean([r[1] for r in res]))
     launches = int(np.sum([r[2] for r in res]))
-    upd_flops = float(np.sum([r[3] for r in res]))
-    upd_secs = float(np.sum([r[4] for r in res]))
+    # roofline pass: the same K steps with CUDA events around every launch of the dominant kernel
+    # (profile mode keeps the factorisation on one stream so that a launch is timed alone)
+    s.opt.reserved[0] = 1
+    step_device()
+    barrier()
+    resp = [step_device() for _ in range(args.steps)]
+    barrier()
+    s.opt.reserved[0] = 0
+    clocks = sampler.stop() if rank == 0 else None
+    upd_flops = float(np.sum([r[3] for r in resp]))
+    upd_secs = float(np.sum([r[4] for r in resp]))
+    tf_prof = float(np.mean([r[0] for r in resp]))
     # check the answer of the last step (not timed)
     x = d_x.cpu().numpy()
     from galahad_b200 import problems as P
@@ -292,7 +311,8 @@ def run_ours(args):
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "kernel": "k_update (trailing Schur update, FP64)",
                          "peak_source": "measured here: cuBLAS Dgemm 4096^3 via torch.matmul(float64), best of 5 (MEASURED_PEAKS.json has no FP64 entry)",
-                         "share_of_factor_time": upd_secs / (tf * args.steps) if tf > 0 else None},
+                         "share_of_factor_time": upd_secs / (tf_prof * args.steps) if tf_prof > 0 else None,
+                         "measured": "second pass of the same K steps with CUDA events around every k_update launch on the engine stream (single-stream mode, factor_ms %.2f)" % (tf_prof * 1e3)},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
@@ -335,12 +355,13 @@ def run_tree_parallel(args, prob, torch, dist, rank, world, local):
         t2 = time.perf_counter()
         return t1 - t0, t2 - t1, x
 
-    for _ in range(max(args.warmup, 3)):
-        step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
     barrier()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     res = [step() for _ in range(args.steps)]
