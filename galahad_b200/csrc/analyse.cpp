@@ -554,12 +554,17 @@ void fuse_chains(const Symbolic& in, Symbolic& out, double max_zero_frac) {
    std::vector<int> first(nn, 0);          // first original node of the run ending at i
    std::vector<int64_t> zeros(nn, 0);      // explicit zeros accumulated in the run ending at i
    std::vector<char> absorbed(nn, 0);      // node i was absorbed by i+1
+   std::vector<int> nchild(nn + 1, 0);
+   for (int i = 0; i < nn; ++i) nchild[in.sparent[i]]++;
    for (int p = 0; p < nn; ++p) {
       first[p] = p;
       zeros[p] = 0;
       const int c = p - 1;
       if (c < 0 || in.sparent[c] != p) continue;
       const int64_t gcols = in.sptr[c + 1] - in.sptr[first[c]];
+      // a node with siblings is only absorbed while it is small: a large child fused into its parent is
+      // eliminated after its siblings instead of beside them (the fronts of a level run concurrently)
+      if (nchild[p] > 1 && gcols > 128) continue;
       const int64_t ncol_p = in.sptr[p + 1] - in.sptr[p];
       const int64_t nrow_p = in.rptr[p + 1] - in.rptr[p];
       const int64_t contrib_c = (in.rptr[c + 1] - in.rptr[c]) - (in.sptr[c + 1] - in.sptr[c]);

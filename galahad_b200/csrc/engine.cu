@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -849,8 +850,11 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    std::vector<int> lvl_list, tpp_list;
    std::vector<int64_t> tileptr;
    size_t updmap_used = 0;
+   const bool lvl_times = getenv("B200LDLT_LEVELTIMES") != nullptr;   // wall time per level (each level ends with a sync)
    for (int l = 0; l < P->nlevels && flag >= 0; ++l) {
       const int s0 = P->lvl_ptr[l], s1 = P->lvl_ptr[l + 1], ns = s1 - s0;
+      const auto lvl_t0 = std::chrono::steady_clock::now();
+      const int64_t lvl_l0 = launches;
       Arena& ca = car[l & 1];
       ca.reset();
       war.reset();
@@ -979,7 +983,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             k_extend_add<<<(unsigned)total, EA_TR, 0, st>>>(d_fr, P->d_ss, P->d_rel, d_list, d_list + nl, d_tileptr, nl);
             ++launches;
          }
-         if (pin_off) CU(cudaStreamSynchronize(st));   // staging regions free again
+         // the staging regions stay untouched until the level's closing synchronisation (collect)
       }
       // factor: fronts bucketed by size class, sorted by candidate count (descending) inside.
       // Each bucket runs rounds of blocks (PB columns, four launches each); the
@@ -1190,6 +1194,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       }
       if (flag < 0) break;
       for (int s = s0; s < s1; ++s) if (active[s]) { num_delay += hfr[s].n - hfr[s].nelim; hfr[s].active = 0; }
+      if (lvl_times)
+         fprintf(stderr, "[b200ldlt] level %d fronts %d launches %lld wall %.3f ms\n", l, ns, (long long)(launches - lvl_l0),
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - lvl_t0).count());
    }
    if (flag >= 0) {
       CU(cudaMemsetAsync(d_counters, 0, sizeof(int) * 8, st));

@@ -67,67 +67,101 @@ __device__ __forceinline__ void warp_zero_pivots(unsigned& alive, int& np, int l
    }
 }
 
-// srow: 2*NB + 2 doubles (two broadcast rows)
-__device__ __forceinline__ int warp_ldlt32(double (&a)[NB], double dg, int wj, const Params& prm, int lane,
-                                           double* srow, double* sLc, double* sd, double* sdd,
-                                           int* spord, int* sptype) {
+__device__ __forceinline__ void bar128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ double sel8(const double (&a)[8], int i) {
+   const double s0 = (i & 1) ? a[1] : a[0], s1 = (i & 1) ? a[3] : a[2], s2 = (i & 1) ? a[5] : a[4], s3 = (i & 1) ? a[7] : a[6];
+   const double t0 = (i & 2) ? s1 : s0, t1 = (i & 2) ? s3 : s2;
+   return (i & 4) ? t1 : t0;
+}
+
+// Pivoting on a symmetric block of order wj <= 32 by FOUR warps (threads 0..127 of the CTA, named
+// barrier 1).  Thread (wq, lane) holds A(lane, 8*wq .. 8*wq+7) in registers, so a pivot step is 8 FMAs
+// per thread; every warp keeps its own copy of the diagonal (and of its reciprocal), so that the
+// pivot candidate is found without talking to the other warps.  Rows and columns are never moved:
+// eliminated indices leave the `alive` mask and the pivot sequence is recorded.
+//   fast step   the largest diagonal entry as a 1x1 pivot when all multipliers of the block stay
+//               <= 2 in modulus (checked on the multipliers by a vote): one warp reduction, one
+//               shared-memory broadcast of the pivot column, one barrier
+//   general     complete pivoting with 1x1 / 2x2 pivots exactly as block_ldlt.hxx:290-414
+// Outputs (shared): spord[k] original index of pivot k, sptype[k] (0 = 1x1, 1/2 = first/second of
+// a 2x2), sd = D^{-1} in SSIDS's format, sdd = D itself (diagonal, off-diagonal), sLc[r + k*LDS] =
+// multiplier of original row r for pivot k.  Returns 0 or an SSIDS error flag (uniform).
+// sv: 2*NB + 2 doubles (two broadcast columns, reciprocal and value of the pivot); skey: 8 ints.
+__device__ __forceinline__ int ldlt32_4w(double (&a)[8], double dg, int wj, const Params& prm, int lane, int wq,
+                                         double* sv, unsigned* skey, double* sLc, double* sd, double* sdd,
+                                         int* spord, int* sptype) {
    unsigned alive = (wj == NB) ? 0xffffffffu : ((1u << wj) - 1u);
    int np = 0;
-   double rdg = 1.0 / dg;       // every lane keeps the reciprocal of its own diagonal entry: no division
-                                // between choosing a 1x1 pivot and using it
-   const unsigned small_hi = (unsigned)__double2hiint(prm.small_) & 0x7fffffffu;
-   // candidate of the fast path: the alive row with the largest |diagonal| (posdef: the next row)
+   double rdg = 1.0 / dg;
+   // a pivot must be at least `small` (and a normal number): compared on the high word
+   const unsigned small_hi_pos = max((unsigned)__double2hiint(prm.small_) & 0x7fffffffu, 0x00100000u);
+   const bool rec = wq == 0 && lane == 0;       // the thread that records the pivot sequence
+   if (wq == 0) { sptype[lane] = 0; sd[lane] = 0.0; sd[NB + lane] = 0.0; sdd[lane] = 0.0; sdd[NB + lane] = 0.0; }
+   const int cbase = 8 * wq;
    auto next_q = [&](unsigned al) -> int {
       if (prm.posdef) return al ? __ffs(al) - 1 : 0;
       const unsigned dkey = ((al >> lane) & 1u) ? ((((unsigned)__double2hiint(dg)) & 0x7fffffe0u) | (unsigned)(31 - lane)) : 0u;
       return 31 - (int)(__reduce_max_sync(0xffffffffu, dkey) & 31u);
    };
+   auto zero_pivots = [&]() {
+      // everything left is numerically zero: record zero pivots (block_ldlt.hxx:303-318)
+      while (alive) {
+         const int q = __ffs(alive) - 1;
+         if (rec) { spord[np] = q; sptype[np] = 0; sd[2 * np] = 0.0; sd[2 * np + 1] = 0.0; sdd[2 * np] = 0.0; sdd[2 * np + 1] = 0.0; }
+         if (wq == 0) sLc[lane + np * LDS] = 0.0;
+         alive &= ~(1u << q);
+         ++np;
+      }
+   };
+   long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+#define TK(i) do { if (prm.debug) { long long t_ = clock64(); if (i > 0) tk[i] += t_ - tlast; tlast = t_; } } while (0)
    int q = next_q(alive);
+   bar128();
    while (alive) {
-      __syncwarp();   // the previous step's reads of srow are done
       const bool rowalive = (alive >> lane) & 1u;
-      // ---- fast path: the largest diagonal entry is taken as a 1x1 pivot when all multipliers of
-      // the block stay <= 2 in modulus (checked on the multipliers themselves by a vote).  One warp
-      // reduction per pivot, issued right after the new diagonal is known so that it overlaps
-      // the rank-1 update.  posdef: pivots in order, only positivity is checked.
+      // ---- fast step
       {
-         if (lane == q) {
-            double2* dst = reinterpret_cast<double2*>(srow);
-#pragma unroll
-            for (int c2 = 0; c2 < NB / 2; ++c2) dst[c2] = make_double2(a[2 * c2], a[2 * c2 + 1]);
+         TK(0);
+         if (wq == (q >> 3)) {
+            sv[lane] = sel8(a, q & 7);
          }
-         const double d11 = __shfl_sync(0xffffffffu, rdg, q);
-         __syncwarp();
-         const double vown = srow[lane];
+         TK(1);
+         bar128();
+         TK(2);
+         // every warp holds the diagonal and its reciprocal: no division between the broadcast and its use
+         const double vown = sv[lane], d11 = __shfl_sync(0xffffffffu, rdg, q), aqq = __shfl_sync(0xffffffffu, dg, q);
          const unsigned alive2 = alive & ~(1u << q);
          const bool upd = (alive2 >> lane) & 1u;
          const double ldr = upd ? vown : 0.0;
          const double l = ldr * d11;
-         bool bad;
-         if (prm.posdef) bad = (lane == q) && !(dg > 0.0);
-         else bad = (lane == q) ? (((unsigned)__double2hiint(dg) & 0x7fffffffu) < small_hi || small_hi == 0u && dg == 0.0)
-                                : (((unsigned)__double2hiint(l) & 0x7fffffffu) > 0x40000000u);
-         if (!__any_sync(0xffffffffu, bad)) {
-            const double aqq = dg;                     // meaningful on lane q
+         const unsigned qh = (unsigned)__double2hiint(aqq), lh = (unsigned)__double2hiint(l) & 0x7fffffffu;
+         const bool badq = prm.posdef ? ((qh >> 31) != 0u || (qh & 0x7fffffffu) < 0x00100000u) : ((qh & 0x7fffffffu) < small_hi_pos);
+         const bool badl = !prm.posdef && lh > 0x40000000u;
+         const bool anyb = __any_sync(0xffffffffu, badq || badl);
+         TK(3);
+         if (!anyb) {
             alive = alive2;
             dg -= l * ldr;
             const int qn = next_q(alive);              // overlaps the update below
+            TK(4);
             rdg = 1.0 / dg;
-            sLc[lane + np * LDS] = l;
-            const double2* ldv = reinterpret_cast<const double2*>(srow);
+            const double2* v2 = reinterpret_cast<const double2*>(sv + cbase);
 #pragma unroll
-            for (int c2 = 0; c2 < NB / 2; ++c2) {
-               const double2 v = ldv[c2];
-               a[2 * c2] -= l * v.x;
-               a[2 * c2 + 1] -= l * v.y;
+            for (int j2 = 0; j2 < 4; ++j2) {
+               const double2 v = v2[j2];
+               a[2 * j2] -= l * v.x;
+               a[2 * j2 + 1] -= l * v.y;
             }
-            if (lane == q) { spord[np] = q; sptype[np] = 0; sd[2 * np] = d11; sd[2 * np + 1] = 0.0; sdd[2 * np] = aqq; sdd[2 * np + 1] = 0.0; }
+            if (wq == 0) sLc[lane + np * LDS] = l;
+            if (rec) { spord[np] = q; sd[2 * np] = d11; sdd[2 * np] = aqq; }
             np += 1;
             q = qn;
+            TK(5);
+            bar128();                                   // sv is rewritten by the next step
+            TK(6);
             continue;
          }
          if (prm.posdef) return SSIDS_ERROR_NOT_POS_DEF;
-         __syncwarp();   // srow is rewritten below
       }
       // ---- general step: complete pivoting (block_ldlt.hxx:290-414)
       int q1, q2 = -1, m1, t1;
@@ -136,44 +170,46 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], double dg, int wj, c
          // largest |a(r,c)| over the alive rows / columns, compared on the high word of the double
          // (sign cleared, 15 mantissa bits, the low 5 bits carry 31-col); ties -> smallest column,
          // then smallest row
-         unsigned kb[NB];
+         unsigned kb = 0u;
 #pragma unroll
-         for (int c = 0; c < NB; ++c)
-            kb[c] = ((alive >> c) & 1u) ? ((((unsigned)__double2hiint(a[c])) & 0x7fffffe0u) | (unsigned)(31 - c)) : 0u;
-#pragma unroll
-         for (int st = NB / 2; st > 0; st >>= 1)
-#pragma unroll
-            for (int c = 0; c < st; ++c) kb[c] = max(kb[c], kb[c + st]);
-         const unsigned bk = rowalive ? kb[0] : 0u;
+         for (int j = 0; j < 8; ++j) {
+            const int c = cbase + j;
+            const unsigned k = ((alive >> c) & 1u) ? ((((unsigned)__double2hiint(a[j])) & 0x7fffffe0u) | (unsigned)(31 - c)) : 0u;
+            kb = max(kb, k);
+         }
+         const unsigned bk = rowalive ? kb : 0u;
          const int bc = 31 - (int)(bk & 31u);
-         const unsigned mk = __reduce_max_sync(0xffffffffu, bk & ~31u);
+         const unsigned wmk = __reduce_max_sync(0xffffffffu, bk & ~31u);
+         if (lane == 0) skey[wq] = wmk;
+         bar128();
+         const unsigned mk = max(max(skey[0], skey[1]), max(skey[2], skey[3]));
          if ((mk >> 20) == 0u) {
             if (!prm.action) return SSIDS_ERROR_SINGULAR;
-            warp_zero_pivots(alive, np, lane, sLc, sd, sdd, spord, sptype);
+            zero_pivots();
             break;
          }
          const int lo = min(lane, bc), hi = max(lane, bc);
          const unsigned idx = (rowalive && (bk & ~31u) == mk) ? (unsigned)(lo * 32 + hi) : 0xffffu;
-         const unsigned mi = __reduce_min_sync(0xffffffffu, idx);
+         const unsigned wmi = __reduce_min_sync(0xffffffffu, idx);
+         if (lane == 0) skey[4 + wq] = wmi;
+         bar128();
+         const unsigned mi = min(min(skey[4], skey[5]), min(skey[6], skey[7]));
          m1 = (int)(mi >> 5);
          t1 = (int)(mi & 31u);
          q1 = m1;
       }
-      // rows m1 and t1 of the current Schur complement -> shared
-      if (lane == m1 || lane == t1) {
-         double2* dst = reinterpret_cast<double2*>(srow + (lane == m1 ? 0 : NB));
-#pragma unroll
-         for (int c2 = 0; c2 < NB / 2; ++c2) dst[c2] = make_double2(a[2 * c2], a[2 * c2 + 1]);
-      }
-      __syncwarp();
-      a11 = srow[m1];
+      // columns m1 and t1 of the current Schur complement -> shared
+      if (wq == (m1 >> 3)) sv[lane] = sel8(a, m1 & 7);
+      if (wq == (t1 >> 3)) sv[NB + lane] = sel8(a, t1 & 7);
+      bar128();
+      a11 = sv[m1];
       int voff = 0;
-      a21 = srow[t1];
-      a22 = srow[NB + t1];
+      a21 = sv[t1];
+      a22 = sv[NB + t1];
       if (fabs(a21) < prm.small_) {
          // the largest entry is below `small`: all remaining pivots are zero pivots
          if (!prm.action) return SSIDS_ERROR_SINGULAR;
-         warp_zero_pivots(alive, np, lane, sLc, sd, sdd, spord, sptype);
+         zero_pivots();
          break;
       }
       if (t1 == m1) {
@@ -197,36 +233,35 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], double dg, int wj, c
       if (q2 < 0) {
          alive &= ~(1u << q1);
          const bool upd = (alive >> lane) & 1u;
-         const double ldr = upd ? srow[voff + lane] : 0.0;
+         const double ldr = upd ? sv[voff + lane] : 0.0;
          const double l = ldr * d11;
-         sLc[lane + np * LDS] = l;
-         const double2* ldv = reinterpret_cast<const double2*>(srow + voff);
+         if (wq == 0) sLc[lane + np * LDS] = l;
+         const double2* v2 = reinterpret_cast<const double2*>(sv + voff + cbase);
 #pragma unroll
-         for (int c2 = 0; c2 < NB / 2; ++c2) {
-            const double2 v = ldv[c2];
-            a[2 * c2] -= l * v.x;
-            a[2 * c2 + 1] -= l * v.y;
+         for (int j2 = 0; j2 < 4; ++j2) {
+            const double2 v = v2[j2];
+            a[2 * j2] -= l * v.x;
+            a[2 * j2 + 1] -= l * v.y;
          }
          dg -= l * ldr;
-         if (lane == 0) { spord[np] = q1; sptype[np] = 0; sd[2 * np] = d11; sd[2 * np + 1] = 0.0; sdd[2 * np] = a11; sdd[2 * np + 1] = 0.0; }
+         if (rec) { spord[np] = q1; sptype[np] = 0; sd[2 * np] = d11; sd[2 * np + 1] = 0.0; sdd[2 * np] = a11; sdd[2 * np + 1] = 0.0; }
          np += 1;
       } else {
          alive &= ~((1u << q1) | (1u << q2));
          const bool upd = (alive >> lane) & 1u;
-         const double w1 = upd ? srow[lane] : 0.0, w2 = upd ? srow[NB + lane] : 0.0;
+         const double w1 = upd ? sv[lane] : 0.0, w2 = upd ? sv[NB + lane] : 0.0;
          const double l1 = d11 * w1 + d21 * w2, l2 = d21 * w1 + d22 * w2;
-         sLc[lane + np * LDS] = l1;
-         sLc[lane + (np + 1) * LDS] = l2;
-         const double2* ldv1 = reinterpret_cast<const double2*>(srow);
-         const double2* ldv2 = reinterpret_cast<const double2*>(srow + NB);
+         if (wq == 0) { sLc[lane + np * LDS] = l1; sLc[lane + (np + 1) * LDS] = l2; }
+         const double2* v1p = reinterpret_cast<const double2*>(sv + cbase);
+         const double2* v2p = reinterpret_cast<const double2*>(sv + NB + cbase);
 #pragma unroll
-         for (int c2 = 0; c2 < NB / 2; ++c2) {
-            const double2 v1 = ldv1[c2], v2 = ldv2[c2];
-            a[2 * c2] -= l1 * v1.x + l2 * v2.x;
-            a[2 * c2 + 1] -= l1 * v1.y + l2 * v2.y;
+         for (int j2 = 0; j2 < 4; ++j2) {
+            const double2 v1 = v1p[j2], v2 = v2p[j2];
+            a[2 * j2] -= l1 * v1.x + l2 * v2.x;
+            a[2 * j2 + 1] -= l1 * v1.y + l2 * v2.y;
          }
          dg -= l1 * w1 + l2 * w2;
-         if (lane == 0) {
+         if (rec) {
             spord[np] = q1; spord[np + 1] = q2;
             sptype[np] = 1; sptype[np + 1] = 2;
             sd[2 * np] = d11; sd[2 * np + 1] = d21; sd[2 * np + 2] = DINF; sd[2 * np + 3] = d22;
@@ -236,20 +271,20 @@ __device__ __forceinline__ int warp_ldlt32(double (&a)[NB], double dg, int wj, c
       }
       rdg = 1.0 / dg;
       q = next_q(alive);
+      bar128();                                         // sv is rewritten by the next step
    }
+   if (prm.debug && lane == 0 && wq == 0 && blockIdx.x == 0) printf("[pivot4] np=%d sel+sts %lld bar %lld lds+shfl+test+vote %lld dg+redux %lld rcp+update+book %lld bar %lld\n", np, tk[1], tk[2], tk[3], tk[4], tk[5], tk[6]);
+#undef TK
    return 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// K1: factorise the next diagonal block (<= PB columns) of a front in shared memory
-// ------------------------------------------------------------------------------------------
 constexpr int LDBB = NB + 4;       // k-major 32-column operand, = 4 mod 16: conflict-free MMA fragments
 __host__ __device__ inline size_t block_smem_bytes(int wcap) {
    // sA wcap x (wcap+4) | sX, sXa NB x XLD each (only when the block has more than one sub-panel; sLc
    // aliases sXa) | sLj NB x NB | sInv NB x LDBB | srow | sdk, sdd | ints
    const size_t xbuf = wcap > NB ? 2 * (size_t)NB * XLD : (size_t)NB * LDS;
    return sizeof(double) * ((size_t)wcap * (wcap + 4) + xbuf + NB * NB + NB * LDBB + 2 * NB + 2 + 2 * (2 * PB + 2)) +
-          sizeof(int) * (2 * PB + 2 * NB + 8);
+          sizeof(int) * (2 * PB + 2 * NB + 16);
 }
 
 __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only, int wcap) {
@@ -300,8 +335,6 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
    const size_t ldl = f.ldl;
    const int wc = f.wc;
    double* const fL = f.L;
-   double* const fWld = f.Wld;
-   double* const L11g = f.dbuf;
    double* const A0g = f.dbuf + (size_t)PB * wc;
    double* const dkg = f.dbuf + 2 * (size_t)PB * wc;
    double* const Linvg = dkg + 2 * PB + 2;
@@ -335,21 +368,25 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
    for (int c0 = 0; c0 < w; c0 += NB) {
       const int wj = min(NB, w - c0), r1 = c0 + NB;
       const int nr = max(0, w - r1);            // rows of the block below the sub-panel
-      // a. pivoting on the diagonal sub-block (warp 0)
-      if (warp == 0) {
-         double a[NB];
+      // a. pivoting on the diagonal sub-block (warps 0-3)
+      if (warp < 4) {
+         double a[8];
 #pragma unroll
-         for (int c = 0; c < NB; ++c) {
+         for (int j = 0; j < 8; ++j) {
+            const int c = 8 * warp + j;
             double v = 0.0;
             if (c < wj && lane < wj) v = (c <= lane) ? sA[(c0 + lane) + (c0 + c) * sld] : sA[(c0 + c) + (c0 + lane) * sld];
-            a[c] = v;
+            a[j] = v;
          }
          const double dg = lane < wj ? sA[(c0 + lane) + (c0 + lane) * sld] : 1.0;
-         const int err = warp_ldlt32(a, dg, wj, prm, lane, srow, sLc, sdk + 2 * c0, sdd + 2 * c0, spord, sptj);
-         __syncwarp();
-         const bool mv = lane < wj && spord[lane] != lane;
-         const unsigned pm = __ballot_sync(0xffffffffu, mv);
-         if (lane == 0) { smisc[0] = err; smisc[1] = wj; smisc[2] = pm != 0u; }
+         const int err = ldlt32_4w(a, dg, wj, prm, lane, warp, srow, reinterpret_cast<unsigned*>(smisc + 8), sLc,
+                                   sdk + 2 * c0, sdd + 2 * c0, spord, sptj);
+         bar128();
+         if (warp == 0) {
+            const bool mv = lane < wj && spord[lane] != lane;
+            const unsigned pm = __ballot_sync(0xffffffffu, mv);
+            if (lane == 0) { smisc[0] = err; smisc[1] = wj; smisc[2] = pm != 0u; }
+         }
       }
       __syncthreads();
       if (c0 == 0) B200_TICK();   // 2: first sub-panel pivoted
@@ -518,24 +555,12 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
    __syncthreads();
    B200_TICK();      // all sub-panels
 
-   // ---- publish: L11 (unit lower, pivot order), L11*D into Wld, D^{-1}, pivot lists
+   // ---- publish: L11 (unit lower, pivot order) straight into the front, D^{-1}, pivot lists.  The
+   // original block stays in A0 for the columns k_commit may have to restore.
    {
-      const int wr = (w + NB - 1) & ~(NB - 1);
-      for (int k = warp; k < wr; k += 8) {
-         const int pt = k < w ? sptype[k] : 0;
-         const double dd0 = sdd[2 * (k < w ? k : 0)], dd1 = sdd[2 * (k < w ? k : 0) + 1];
-         const int kn = pt == 1 ? k + 1 : (pt == 2 ? k - 1 : k);   // partner column of a 2x2
-         for (int i = lane; i < wr; i += 32) {
-            double lv = 0.0;
-            if (i < w && k < w) lv = i > k ? sA[i + k * sld] : (i == k ? 1.0 : 0.0);
-            L11g[i + (size_t)k * PB] = lv;
-            if (i > k && i < w) {
-               double x = lv * dd0;
-               if (pt != 0) x += sA[i + kn * sld] * dd1;
-               fWld[(size_t)k * ldl + done + i] = x;
-            }
-         }
-      }
+      double* Lb = fL + (size_t)done * ldl + done;
+      for (int k = warp; k < w; k += 8)
+         for (int i = k + lane; i < w; i += 32) Lb[(size_t)k * ldl + i] = i == k ? 1.0 : sA[i + k * sld];
       for (int i = tid; i < 2 * w + 2; i += 256) dkg[i] = i < 2 * w ? sdk[i] : 0.0;
       if (tid < w) { ibuf[tid] = slperm[tid]; ibuf[PB + tid] = sptype[tid]; }
       if (tid < 4) {
@@ -602,13 +627,15 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, in
          const bool ok = k < w && r0 + rr < m;
          cp_async8(Xs + k * LDX + rr, ok ? Lp + (size_t)(done + slperm[k]) * ldl + r0 + rr : Lp, ok);
       }
-      const double* L11 = f.dbuf;
+      // L11 blocks below the diagonal blocks come from the front itself (k_block wrote them in place)
+      const double* L11 = Lp + (size_t)done * ldl + done;
       for (int j = 1; j < nb; ++j)
          for (int i = 0; i < j; ++i) {
             double* dst = Bl + (size_t)(j * (j - 1) / 2 + i) * NB * LDBB;
-            for (int e = tid; e < NB * NB / 2; e += 256) {
-               const int k = e >> 4, c = (e & 15) * 2;
-               cp_async16(dst + k * LDBB + c, L11 + (size_t)(i * NB + k) * PB + j * NB + c, 16);
+            for (int e = tid; e < NB * NB; e += 256) {
+               const int k = e >> 5, c = e & 31;
+               const bool ok = i * NB + k < w && j * NB + c < w;
+               cp_async8(dst + k * LDBB + c, ok ? L11 + (size_t)(i * NB + k) * ldl + j * NB + c : L11, ok);
             }
          }
       const double* Linv = f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2;
@@ -716,18 +743,41 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
    const size_t ldl = f.ldl;
    const int y = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    if (y == 0) {
-      const double* L11 = f.dbuf;
-      const double* A0 = f.dbuf + (size_t)PB * f.wc;
-      for (int k = warp; k < w; k += 8) {
-         const int pk = lperm[k];
-         for (int i = k + lane; i < w; i += 32) {
-            double v;
-            if (k < nelim) v = L11[i + (size_t)k * PB];
-            else { const int pi = lperm[i]; v = A0[max(pi, pk) + (size_t)min(pi, pk) * PB]; }
-            f.L[(size_t)(done + k) * ldl + done + i] = v;
+      const double* dk = f.dbuf + 2 * (size_t)PB * f.wc;
+      if (nelim < w) {
+         // failed columns get their original values back (block part from A0 in pivot order; CopyBackup,
+         // ldlt_app.cxx:423) ...
+         const double* A0 = f.dbuf + (size_t)PB * f.wc;
+         for (int k = nelim + warp; k < w; k += 8) {
+            const int pk = lperm[k];
+            for (int i = k + lane; i < w; i += 32) {
+               const int pi = lperm[i];
+               f.L[(size_t)(done + k) * ldl + done + i] = A0[max(pi, pk) + (size_t)min(pi, pk) * PB];
+            }
+         }
+         // ... and the trailing update needs X = L D for their rows (calcLD, calc_ld.hxx:42-118)
+         const int* ptype = f.ibuf + PB;
+         for (int k = warp; k < nelim; k += 8) {
+            const int pt = ptype[k];
+            double d0, d1;          // X(i,k) = L(i,k) d0 + L(i,partner) d1
+            int kn = k;
+            if (pt == 0) {
+               d0 = dk[2 * k] != 0.0 ? 1.0 / dk[2 * k] : 0.0; d1 = 0.0;
+            } else {
+               const int kf = pt == 1 ? k : k - 1;
+               const double i11 = dk[2 * kf], i21 = dk[2 * kf + 1], i22 = dk[2 * kf + 3];
+               const double det = i11 * i22 - i21 * i21;
+               d0 = (pt == 1 ? i22 : i11) / det;
+               d1 = -i21 / det;
+               kn = pt == 1 ? k + 1 : k - 1;
+            }
+            for (int i = nelim + lane; i < w; i += 32) {
+               double x = f.L[(size_t)(done + k) * ldl + done + i] * d0;
+               if (pt != 0) x += f.L[(size_t)(done + kn) * ldl + done + i] * d1;
+               f.Wld[(size_t)k * ldl + done + i] = x;
+            }
          }
       }
-      const double* dk = f.dbuf + 2 * (size_t)PB * f.wc;
       for (int k = tid; k < nelim; k += 256) {
          f.D[2 * (done + k)] = dk[2 * k];
          f.D[2 * (done + k) + 1] = dk[2 * k + 1];
@@ -741,17 +791,25 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
       }
    } else if (y <= ncolchunks) {
       if (!f.ibuf[2 * PB]) return;
-      // one warp per column, 8 columns per warp
+      // rows [done, done+w) of 8 finished columns per warp follow the pivot order: all loads, then all stores
+      const int cb = (y - 1) * 64 + warp * 8;
+      if (cb >= done) return;
+      int lp[PB / 32];
+#pragma unroll
+      for (int q = 0; q < PB / 32; ++q) { const int i = lane + 32 * q; lp[q] = i < w ? lperm[i] : 0; }
+      double tmp[8][PB / 32];
+#pragma unroll
       for (int s = 0; s < 8; ++s) {
-         const int c = (y - 1) * 64 + warp * 8 + s;
-         if (c >= done) return;
-         double* col = f.L + (size_t)c * ldl + done;
-         double tmp[PB / 32];
+         const double* col = f.L + (size_t)(cb + s) * ldl + done;
 #pragma unroll
-         for (int q = 0; q < PB / 32; ++q) { const int i = lane + 32 * q; tmp[q] = i < w ? col[lperm[i]] : 0.0; }
-         __syncwarp();
+         for (int q = 0; q < PB / 32; ++q) tmp[s][q] = (cb + s < done && lane + 32 * q < w) ? col[lp[q]] : 0.0;
+      }
+      __syncwarp();
 #pragma unroll
-         for (int q = 0; q < PB / 32; ++q) { const int i = lane + 32 * q; if (i < w) col[i] = tmp[q]; }
+      for (int s = 0; s < 8; ++s) {
+         double* col = f.L + (size_t)(cb + s) * ldl + done;
+#pragma unroll
+         for (int q = 0; q < PB / 32; ++q) if (cb + s < done && lane + 32 * q < w) col[lane + 32 * q] = tmp[s][q];
       }
    } else {
       if (nelim == w) return;
