@@ -308,7 +308,11 @@ def run_ours(args):
             "e2e": {"value": world * flops / ef / 1e12, "unit": UNIT, "h2d_bytes_per_step": int(8 * prob["val"].size + 8 * n),
                     "d2h_bytes_per_step": int(8 * n), "factor_ms": ef * 1e3, "solve_ms": es * 1e3},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the largest k_update launch (ncu --set full,
+                         # profiles/r1_ncu_k_update.txt; 302 MB algorithmic bytes for that launch); not re-measured here
+                         "traffic": 249744640 if args.grid == 64 else None,
+                         "traffic_note": "one ncu capture of the largest launch (t=6016, kc=128), not an average over launches",
                          "kernel": "k_update (trailing Schur update, FP64)",
                          "peak_source": "measured here: cuBLAS Dgemm 4096^3 via torch.matmul(float64), best of 5 (MEASURED_PEAKS.json has no FP64 entry)",
                          "share_of_factor_time": upd_secs / (tf_prof * args.steps) if tf_prof > 0 else None,
