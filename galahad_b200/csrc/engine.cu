@@ -42,7 +42,8 @@ struct FrontDev {
    double* D;
    int* perm;
    int* orig;      // orig[r] = local index variable r had when the front was assembled (r < n)
-   double* Wld;    // ldl x wc  L*D of the current block (front-row indexed)
+   double* Wld;    // ldl x wc  L*D of the current block (front-row indexed); blocks alternate between Wld and Wld2
+   double* Wld2;   //           so that the bulk update of block b can run beside the factorisation of block b+1
    double* Wo;     // ldl x wc  permuted original columns of the block (restore on failure)
    double* dbuf;   // L11[PB*wc] | A0[PB*wc] | dk[2*PB+2] | Linv[NB*wc] (inverses of the 32x32 diagonal blocks of L11)
    int* ibuf;      // lperm[PB] | ptype[PB] | permuted
@@ -57,6 +58,9 @@ struct FrontDev {
    int state;           // 0 absent on this rank, 2 factorised here, 3 imported from another rank (child data only)
    int active;          // 1 while this front is being assembled / factorised by the current call
    int part_kind;       // 0 leaf part, 1 root part of the subtree partition (multi-GPU solve phases)
+   int stall;           // look-ahead schedule: a failed pivot was seen, the front waits for the synchronous retry rounds
+   int urec[2][4];      // per block parity: {first pivot column k0, accepted pivots kc, end of the strip columns, -}
+   int pad4[2];         // written by k_commit, read by the trailing updates of that block
 };
 
 struct SlotStatic {
@@ -435,10 +439,10 @@ __global__ void k_build_masks(const FrontDev* fr, int nslots, char* mine, char* 
 // ------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int block_wc(int n) { return std::max(NB, (std::min(n, PB) + NB - 1) / NB * NB); }
-// doubles of block workspace of a front: Wld | Wo | L11 | A0 | dk | Linv | ibuf
+// doubles of block workspace of a front: Wld | Wld2 | Wo | L11 | A0 | dk | Linv | ibuf
 static inline size_t front_ws_doubles(size_t ldl, int n) {
    const size_t wc = (size_t)block_wc(n);
-   return align_up(2 * ldl * wc + 2 * (size_t)PB * wc + 2 * PB + 2 + (size_t)NB * wc + (2 * PB + 8) / 2, 32) + 128;
+   return align_up(3 * ldl * wc + 2 * (size_t)PB * wc + 2 * PB + 2 + (size_t)NB * wc + (2 * PB + 8) / 2, 32) + 128;
 }
 static inline int size_class(int m) { return m <= 64 ? 0 : m <= 256 ? 1 : m <= 1024 ? 2 : m <= 4096 ? 3 : 4; }
 
@@ -693,6 +697,9 @@ class Numeric {
    static constexpr int NAUX = 4;
    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+   // look-ahead: bulk-update stream and events per chunk stream (0: st, 1..NAUX: aux[g-1])
+   cudaStream_t bulk[NAUX + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+   cudaEvent_t ev_commit[NAUX + 1][2] = {}, ev_bulk[NAUX + 1][2] = {};
    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
    int cuda_err = 0;
    int64_t launches = 0;
@@ -713,6 +720,10 @@ class Numeric {
       if (st) cudaStreamDestroy(st);
       for (int g = 0; g < NAUX; ++g) { if (aux[g]) cudaStreamDestroy(aux[g]); if (ev_join[g]) cudaEventDestroy(ev_join[g]); }
       if (ev_fork) cudaEventDestroy(ev_fork);
+      for (int g = 0; g <= NAUX; ++g) {
+         if (bulk[g]) cudaStreamDestroy(bulk[g]);
+         for (int q = 0; q < 2; ++q) { if (ev_commit[g][q]) cudaEventDestroy(ev_commit[g][q]); if (ev_bulk[g][q]) cudaEventDestroy(ev_bulk[g][q]); }
+      }
       if (ev0) cudaEventDestroy(ev0);
       if (ev1) cudaEventDestroy(ev1);
       if (ev2) cudaEventDestroy(ev2);
@@ -758,6 +769,13 @@ int Numeric::init() {
       CU(cudaEventCreateWithFlags(&ev_join[g], cudaEventDisableTiming));
    }
    CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+   for (int g = 0; g <= NAUX; ++g) {
+      CU(cudaStreamCreateWithFlags(&bulk[g], cudaStreamNonBlocking));
+      for (int q = 0; q < 2; ++q) {
+         CU(cudaEventCreateWithFlags(&ev_commit[g][q], cudaEventDisableTiming));
+         CU(cudaEventCreateWithFlags(&ev_bulk[g][q], cudaEventDisableTiming));
+      }
+   }
    CU(cudaEventCreate(&ev0));
    CU(cudaEventCreate(&ev1));
    CU(cudaEventCreate(&ev2));
@@ -838,6 +856,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    // synchronises the stream)
    const bool trace = getenv("B200LDLT_TRACE") != nullptr;
    const int upd_share = getenv("B200LDLT_UPD_SHARE") ? atoi(getenv("B200LDLT_UPD_SHARE")) : 296;
+   const bool lookahead = !(getenv("B200LDLT_LOOKAHEAD") && atoi(getenv("B200LDLT_LOOKAHEAD")) == 0);
    const int max_groups = getenv("B200LDLT_GROUPS") ? std::max(1, std::min((int)NAUX, atoi(getenv("B200LDLT_GROUPS")))) : (int)NAUX;
    auto trace_fronts = [&](const char* what, int slot_first, int count) {
       std::vector<FrontDev> tmp(count);
@@ -915,8 +934,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             f.perm = Pb + oP; f.orig = f.perm + align_up((size_t)f.n + 1, 32); oP += 2 * align_up((size_t)f.n + 1, 32);
             double* wp = Wb + oW;
             oW += front_ws_doubles(f.ldl, f.n);
-            f.Wld = wp; f.Wo = wp + (size_t)f.ldl * f.wc;
-            f.dbuf = wp + 2 * (size_t)f.ldl * f.wc;
+            f.Wld = wp; f.Wld2 = wp + (size_t)f.ldl * f.wc; f.Wo = wp + 2 * (size_t)f.ldl * f.wc;
+            f.dbuf = wp + 3 * (size_t)f.ldl * f.wc;
             f.ibuf = (int*)(f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2 + (size_t)NB * f.wc);
          }
       }
@@ -1002,7 +1021,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          };
          auto prof_end = [&]() { cudaEventRecord(prof_ev[prof_used + 1], st); prof_used += 2; };   // profile mode is single-stream
          // one chunk = a contiguous slot range of one size class, processed block by block on stream sx
-         auto run_chunk = [&](int j0, int j1, cudaStream_t sx, bool single) -> int {
+         auto run_chunk = [&](int j0, int j1, cudaStream_t sx, bool single, int sidx) -> int {
             int maxm = 0, maxn = 0;
             for (int q = j0; q < j1; ++q)
                if (active[order[q]]) { maxm = std::max(maxm, hfr[order[q]].m); maxn = std::max(maxn, hfr[order[q]].n); }
@@ -1058,21 +1077,27 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                for (int ob = 0; ob <= nouter; ++ob) map_off[ob] += (int)updmap_used;
                updmap_used += hmap.size();
             }
+            // look-ahead: the trailing update of block b is split into the strip that the next block needs
+            // (on this stream) and the bulk (on the chunk's second stream, beside the factorisation of block
+            // b+1).  Worth it for large fronts with several blocks; profile / trace runs keep one stream.
+            const bool la = lookahead && !o.profile && !trace && nouter >= 2 && maxm >= 1024;
+            int nbulk = 0;
             for (int ob = 0; ob < nouter; ++ob) {
                const int na = map_na[ob];   // slots [b0, b0+na) cover every front that still has a block number ob
                if (na == 0) break;
+               const int par = ob & 1;
                int maxw = 0;
                for (int q = 0; q < na; ++q) if (active[order[j0 + q]]) maxw = std::max(maxw, std::min(PB, hfr[order[j0 + q]].n - ob * PB));
                const int wcap = (maxw + NB - 1) / NB * NB;
                // blocks shortened by failed pivots leave `done` behind ob*PB, so the row grid covers the
                // whole front; CTAs above the block exit at once
                const int yapply = std::max(1, (maxm + AR - 1) / AR);
-               k_block<<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap);
-               k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, wcap);
-               k_commit<<<dim3(na, ycommit), 256, 0, sx>>>(d_fr, lst, b0, ncolchunks);
+               k_block<<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
+               k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, wcap, par);
+               k_commit<<<dim3(na, ycommit), 256, 0, sx>>>(d_fr, lst, b0, ncolchunks, par);
                launches += 3;
-               {
-                  const int nct = (map_off[ob + 1] - map_off[ob]) / 3;
+               const int nct = (map_off[ob + 1] - map_off[ob]) / 3;
+               if (!la) {
                   if (o.profile) {
                      for (int q = 0; q < na; ++q) {
                         const FrontDev& ff = hfr[order[j0 + q]];
@@ -1082,13 +1107,27 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                      }
                      prof_begin();
                   }
-                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob]);
+                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 0);
                   if (o.profile) prof_end();
                   ++launches;
+               } else {
+                  CU(cudaEventRecord(ev_commit[sidx][par], sx));
+                  CU(cudaStreamWaitEvent(bulk[sidx], ev_commit[sidx][par], 0));
+                  k_update<<<nct, 256, UPD_SMEM, bulk[sidx]>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 2);
+                  CU(cudaEventRecord(ev_bulk[sidx][par], bulk[sidx]));
+                  ++nbulk;
+                  // the strip overlaps the region of the previous block's bulk update
+                  if (ob > 0) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][par ^ 1], 0));
+                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 1);
+                  launches += 2;
                }
                if (trace) trace_fronts("block", b0, na);
             }
-            k_block<<<j1 - j0, 256, block_smem_bytes(NB), sx>>>(d_fr, lst, b0, prm, 1, NB);
+            if (nbulk > 0) {   // the closing step may move columns: every bulk update has to be finished
+               CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][0], 0));
+               if (nbulk > 1) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][1], 0));
+            }
+            k_block<<<j1 - j0, 256, block_smem_bytes(NB), sx>>>(d_fr, lst, b0, prm, 1, NB, 0, 0);
             ++launches;
             return 0;
          };
@@ -1107,7 +1146,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             int G = 1;
             if (!o.profile && !trace && nact >= 2 && nact <= 128 && c >= 2) G = std::min(nact, max_groups);
             if (G == 1) {
-               int rc2 = run_chunk(i0, i1, st, true);
+               int rc2 = run_chunk(i0, i1, st, true, 0);
                if (rc2) return stats.flag = rc2;
             } else {
                if (!forked) { CU(cudaEventRecord(ev_fork, st)); forked = true; }
@@ -1123,7 +1162,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   if (g2 == G - 1) j1 = i1;
                   if (j1 > j0) {
                      CU(cudaStreamWaitEvent(aux[g2], ev_fork, 0));
-                     int rc2 = run_chunk(j0, j1, aux[g2], false);
+                     int rc2 = run_chunk(j0, j1, aux[g2], false, g2 + 1);
                      if (rc2) return stats.flag = rc2;
                      CU(cudaEventRecord(ev_join[g2], aux[g2]));
                      CU(cudaStreamWaitEvent(st, ev_join[g2], 0));
@@ -1164,12 +1203,12 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * nt, cudaMemcpyHostToDevice, st));
          const int ncolchunks = (maxn + 63) / 64;
          const int wcap = (std::min(maxn, PB) + NB - 1) / NB * NB;
-         k_block<<<nt, 256, block_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, 0, wcap);
-         k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap);
-         k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks);
-         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, nullptr);
+         k_block<<<nt, 256, block_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, 0, wcap, 0, 0);
+         k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap, 0);
+         k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks, 0);
+         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, nullptr, 0, 0);
          if (trace) for (int s : tpp_list) trace_fronts("retry", s, 1);
-         k_block<<<nt, 256, block_smem_bytes(NB), st>>>(d_fr, d_list, 0, prm, 1, NB);
+         k_block<<<nt, 256, block_smem_bytes(NB), st>>>(d_fr, d_list, 0, prm, 1, NB, 0, 0);
          launches += 5;
          if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
          if (flag < 0) break;

@@ -287,9 +287,16 @@ __host__ __device__ inline size_t block_smem_bytes(int wcap) {
           sizeof(int) * (2 * PB + 2 * NB + 16);
 }
 
-__global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only, int wcap) {
+__global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only, int wcap,
+                                               int par, int la) {
    FrontDev& f = fr[front_slot(list, slot0)];
    if (f.flag < 0) return;
+   // look-ahead schedule: a front that saw a failed pivot waits for the synchronous retry rounds, because
+   // parking failed columns moves entries that a concurrent bulk update may be working on
+   if (f.stall && la) {
+      if (threadIdx.x == 0) f.urec[par][1] = 0;   // this parity's record belongs to a block that is already applied
+      return;
+   }
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int g = lane >> 2, t4 = lane & 3;
    extern __shared__ __align__(16) double smem[];
@@ -319,12 +326,17 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
    if (w > 0) {
       const int nelim = compute_nelim(f.fail, w, f.p2mask);
       const int nfail = w - nelim;
-      done += nelim;
       if (prm.posdef && nfail > 0) {
          __syncthreads();
          if (tid == 0) { f.flag = SSIDS_ERROR_NOT_POS_DEF; f.w = 0; }
          return;
       }
+      if (nfail > 0 && la) {
+         __syncthreads();
+         if (tid == 0) { f.stall = 1; f.urec[par][1] = 0; }
+         return;
+      }
+      done += nelim;
       for (int q = 0; q < nfail; ++q) {
          const int a = done + q, b = gend - 1 - q;
          if (a < b) block_sym_swap(f, a, b);
@@ -342,6 +354,8 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
    __syncthreads();
    w = finish_only ? 0 : max(0, min(wcap, gend - done));   // wcap <= PB: the launch's shared-memory capacity
    if (tid == 0) {
+      f.stall = 0;
+      f.urec[par][1] = 0;            // no trailing update for this parity until k_commit says so
       f.done = done; f.gend = gend; f.w = w; f.fail = w; f.nelim = done;
       f.p2mask[0] = f.p2mask[1] = f.p2mask[2] = f.p2mask[3] = 0u;
    }
@@ -594,10 +608,11 @@ __host__ __device__ inline size_t apply_smem_bytes(int wcap) {
           sizeof(int) * 2 * PB;
 }
 
-__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap) {
+__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap, int par) {
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
-   if (w == 0 || f.flag < 0) return;
+   if (w == 0 || f.flag < 0 || f.stall) return;
+   double* const Wldp = par ? f.Wld2 : f.Wld;
    const int done = f.done, m = f.m;
    const int r0 = done + w + blockIdx.y * AR;
    if (r0 >= m) return;
@@ -718,7 +733,7 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, in
                }
                if (!prm.posdef && !(fabs(l) <= prm.lim)) myfail = min(myfail, kk);
                Lp[(size_t)(done + kk) * ldl + r] = l;
-               f.Wld[(size_t)kk * ldl + r] = xv;
+               Wldp[(size_t)kk * ldl + r] = xv;
             }
          }
       }
@@ -733,16 +748,19 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, in
 // finished columns whose rows [done, done+w) follow the pivot order, then chunks of 256 rows
 // restoring failed columns.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, int slot0, int ncolchunks) {
+__global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, int slot0, int ncolchunks, int par) {
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
-   if (w == 0 || f.flag < 0) return;
+   if (w == 0 || f.flag < 0 || f.stall) return;
    const int done = f.done, m = f.m;
    const int* lperm = f.ibuf;
    const int nelim = compute_nelim(f.fail, w, f.p2mask);
    const size_t ldl = f.ldl;
    const int y = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    if (y == 0) {
+      // what the trailing updates of this block need: first pivot column, accepted pivots, end of the strip
+      if (tid == 0) { f.urec[par][0] = done; f.urec[par][2] = min(m, done + w + PB); f.urec[par][1] = nelim; }
+      double* const Wldp = par ? f.Wld2 : f.Wld;
       const double* dk = f.dbuf + 2 * (size_t)PB * f.wc;
       if (nelim < w) {
          // failed columns get their original values back (block part from A0 in pivot order; CopyBackup,
@@ -774,7 +792,7 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
             for (int i = nelim + lane; i < w; i += 32) {
                double x = f.L[(size_t)(done + k) * ldl + done + i] * d0;
                if (pt != 0) x += f.L[(size_t)(done + kn) * ldl + done + i] * d1;
-               f.Wld[(size_t)k * ldl + done + i] = x;
+               Wldp[(size_t)k * ldl + done + i] = x;
             }
          }
       }
@@ -830,19 +848,22 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
 // strength-reduced addresses, and tile coordinates advance incrementally.
 // Work distribution: with `map` (one int3 per CTA: front offset, part, parts) CTAs are dealt to the fronts
 // of the launch in proportion to their tile counts; without it the grid is (fronts, parts).
-__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0, const int* __restrict__ map) {
+// mode 0: the whole region; 1: only the strip (column tiles that start before urec[2], i.e. the next
+// block's columns and the failed columns of this one); 2: everything else (look-ahead schedule).
+__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0, const int* __restrict__ map,
+                                                   int par, int mode) {
    int fq, part, nparts;
    if (map) { fq = map[3 * blockIdx.x]; part = map[3 * blockIdx.x + 1]; nparts = map[3 * blockIdx.x + 2]; }
    else { fq = blockIdx.x; part = blockIdx.y; nparts = gridDim.y; }
    const FrontDev& f = fr[list ? list[fq] : slot0 + fq];
-   const int w = f.w;
-   if (f.flag < 0 || w == 0) return;
-   // pivots accepted in the current block; the region starts right behind them, so columns of the
-   // block that failed (restored by k_commit) receive the update as well
-   const int kc = compute_nelim(f.fail, w, f.p2mask);
+   if (f.flag < 0) return;
+   // pivots accepted in the block (recorded by k_commit); the region starts right behind them, so columns
+   // of the block that failed (restored by k_commit) receive the update as well
+   const int kc = f.urec[par][1];
    const int m = f.m;
-   const int k0 = f.done, cbeg = f.done + kc, cend = m;
+   const int k0 = f.urec[par][0], cbeg = k0 + kc, cend = m;
    if (kc <= 0 || cbeg >= cend) return;
+   const int tjs = (f.urec[par][2] - cbeg + TN - 1) / TN;   // column tiles [0, tjs) form the strip
    const int kofs = 0;
    const int ntr = (m - cbeg + TM - 1) / TM;
    const int ntc = (cend - cbeg + TN - 1) / TN;
@@ -857,7 +878,7 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    double* const Lp = f.L;
    double* const Cp = f.C;
    const double* Abase = Lp + (size_t)k0 * ldl;
-   const double* Bbase = f.Wld + (size_t)kofs * ldl;
+   const double* Bbase = (par ? f.Wld2 : f.Wld) + (size_t)kofs * ldl;
    const bool vec16 = (cbeg & 1) == 0;      // 16-byte cp.async needs even row offsets (ldl is even)
    const int nchunk = (kc + BK - 1) / BK;
    // tile (ti,tj) touches the lower triangle iff tj <= 2*ti+1 (TM = 2*TN, shared origin cbeg);
@@ -865,8 +886,12 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    // NEXT tile is requested while the last chunk of the current one is multiplied, and its C tile
    // is pulled towards L2.
    auto normalise = [&](int& ti, int& tj) -> bool {
-      while (ti < ntr) { const int wd = min(ntc, 2 * ti + 2); if (tj < wd) break; tj -= wd; ++ti; }
-      return ti < ntr;
+      for (;;) {
+         while (ti < ntr) { const int wd = min(ntc, 2 * ti + 2); if (tj < wd) break; tj -= wd; ++ti; }
+         if (ti >= ntr) return false;
+         if (mode == 0 || (mode == 1) == (tj < tjs)) return true;
+         tj += nparts;            // not this launch's tile: take the next one of the walk
+      }
    };
    auto load_stage = [&](int rbase, int cbase, bool full, int chunk, int buf) {
       const int kb = chunk * BK;
