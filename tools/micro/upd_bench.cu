@@ -1,0 +1,259 @@
+// Trailing-update kernel experiments outside the engine: C(lower, t x t) -= A(t x kc) B(t x kc)^T in FP64
+// on the tensor pipe.  Variant 0 = the engine's shape (128x64 tiles, 2 CTAs/SM, 2-stage cp.async, two
+// barriers per k-chunk); variant 1 = 128x128 tiles, 1 CTA/SM, 3-stage ring, one barrier per chunk.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o upd_bench upd_bench.cu && ./upd_bench [t] [kc]
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(double* s, const double* g, int bytes) {
+   unsigned a = (unsigned)__cvta_generic_to_shared(s);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a), "l"(g), "r"(bytes));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+constexpr int BK = 32;
+
+// ---------------------------------------------------------------- variant 0
+namespace v0 {
+constexpr int TM = 128, TN = 64, LDA = TM + 4, LDB = TN + 4;
+constexpr int SMEM = 2 * BK * (LDA + LDB) * 8;
+__global__ void __launch_bounds__(256, 2) k(const double* __restrict__ A, const double* __restrict__ B, double* C, int t, int ld, int kc, int mode) {
+   extern __shared__ double smem[];
+   double* As = smem; double* Bs = smem + 2 * BK * LDA;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wr = warp & 3, wc = warp >> 2, g = lane >> 2, t4 = lane & 3;
+   const int ntr = t / TM, ntc = t / TN, nchunk = kc / BK;
+   int ti = 0, tj = blockIdx.x;
+   auto norm = [&](int& a, int& b) { while (a < ntr) { int wd = min(ntc, 2 * a + 2); if (b < wd) break; b -= wd; ++a; } return a < ntr; };
+   if (!norm(ti, tj)) return;
+   auto load = [&](int rb, int cb, int ch, int buf) {
+      if (mode & 2) { cp_commit(); return; }
+      const int kb = ch * BK;
+      const double* pa = A + (size_t)(kb + (tid >> 6)) * ld + rb + (tid & 63) * 2;
+      double* sa = As + buf * BK * LDA + (tid >> 6) * LDA + (tid & 63) * 2;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cp_async16(sa + q * 4 * LDA, pa + (size_t)q * 4 * ld, 16);
+      const double* pb = B + (size_t)(kb + (tid >> 5)) * ld + cb + (tid & 31) * 2;
+      double* sb = Bs + buf * BK * LDB + (tid >> 5) * LDB + (tid & 31) * 2;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cp_async16(sb + q * 8 * LDB, pb + (size_t)q * 8 * ld, 16);
+      cp_commit();
+   };
+   int buf = 0;
+   load(ti * TM, tj * TN, 0, 0);
+   for (;;) {
+      const int rb = ti * TM, cb = tj * TN;
+      int nti = ti, ntj = tj + gridDim.x;
+      const bool has_next = norm(nti, ntj);
+      double acc[4][4][2];
+      const int r0 = rb + wr * 32 + g, c0 = cb + wc * 32 + 2 * t4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+         for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][j][h] = (mode & 9) ? 0.0 : ((mode & 4) ? C[((size_t)ti * ntc + tj) * (TM * TN) + (size_t)(c0 - cb + j * 8 + h) * TM + (r0 - rb + i * 8)] : C[(size_t)(c0 + j * 8 + h) * ld + r0 + i * 8]);
+      if (mode & 8) {
+         const double* pp = C + (size_t)(cb + (tid >> 2)) * ld + rb + (tid & 3) * 32;
+         asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+         asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 16));
+      }
+      for (int ch = 0; ch < nchunk; ++ch) {
+         if (ch + 1 < nchunk) { load(rb, cb, ch + 1, buf ^ 1); cp_wait<1>(); }
+         else if (has_next) { load(nti * TM, ntj * TN, 0, buf ^ 1); cp_wait<1>(); }
+         else cp_wait<0>();
+         __syncthreads();
+         const double* as = As + buf * BK * LDA + wr * 32 + g + t4 * LDA;
+         const double* bs = Bs + buf * BK * LDB + wc * 32 + g + t4 * LDB;
+         double af[2][4], bf[2][4];
+#pragma unroll
+         for (int i = 0; i < 4; ++i) { af[0][i] = as[i * 8]; bf[0][i] = bs[i * 8]; }
+#pragma unroll
+         for (int ks = 0; ks < BK; ks += 4) {
+            const int cur = (ks >> 2) & 1, nxt = cur ^ 1;
+            if (ks + 4 < BK) {
+#pragma unroll
+               for (int i = 0; i < 4; ++i) { af[nxt][i] = as[(ks + 4) * LDA + i * 8]; bf[nxt][i] = bs[(ks + 4) * LDB + i * 8]; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+               for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], -bf[cur][j]);
+         }
+         __syncthreads();
+         buf ^= 1;
+      }
+      if (mode & 8) {
+         double cv[4][4][2];
+#pragma unroll
+         for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+               for (int i = 0; i < 4; ++i) cv[i][j][h] = C[(size_t)(c0 + j * 8 + h) * ld + r0 + i * 8];
+#pragma unroll
+         for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+               for (int i = 0; i < 4; ++i) acc[i][j][h] += cv[i][j][h];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+         for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (!(mode & 1) || acc[i][j][h] == 12345.678) { if (mode & 4) C[((size_t)ti * ntc + tj) * (TM * TN) + (size_t)(c0 - cb + j * 8 + h) * TM + (r0 - rb + i * 8)] = acc[i][j][h]; else C[(size_t)(c0 + j * 8 + h) * ld + r0 + i * 8] = acc[i][j][h]; }
+      if (!has_next) break;
+      ti = nti; tj = ntj;
+   }
+}
+}  // namespace v0
+
+// ---------------------------------------------------------------- variant 1
+namespace v1 {
+constexpr int TM = 128, TN = 128, LDA = TM + 4, LDB = TN + 4, NST = 3;
+constexpr int SMEM = NST * BK * (LDA + LDB) * 8;
+// 8 warps as 2 (rows) x 4 (cols): warp tile 64 x 32 = 8 x 4 MMA tiles
+__global__ void __launch_bounds__(256, 1) k(const double* __restrict__ A, const double* __restrict__ B, double* C, int t, int ld, int kc, int mode) {
+   extern __shared__ double smem[];
+   double* As = smem; double* Bs = smem + NST * BK * LDA;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wr = warp & 1, wc = warp >> 1, g = lane >> 2, t4 = lane & 3;
+   const int nt = t / TM, nchunk = kc / BK;
+   const int ntiles = nt * (nt + 1) / 2;
+   auto tile_of = [&](int idx, int& ti, int& tj) {
+      int r = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+      while (r * (r + 1) / 2 > idx) --r;
+      while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+      ti = r; tj = idx - r * (r + 1) / 2;
+   };
+   auto load = [&](int rb, int cb, int ch, int st) {
+      if (mode & 2) return;
+      const int kb = ch * BK;
+      const double* pa = A + (size_t)(kb + (tid >> 6)) * ld + rb + (tid & 63) * 2;
+      double* sa = As + st * BK * LDA + (tid >> 6) * LDA + (tid & 63) * 2;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cp_async16(sa + q * 4 * LDA, pa + (size_t)q * 4 * ld, 16);
+      const double* pb = B + (size_t)(kb + (tid >> 6)) * ld + cb + (tid & 63) * 2;
+      double* sb = Bs + st * BK * LDB + (tid >> 6) * LDB + (tid & 63) * 2;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cp_async16(sb + q * 4 * LDB, pb + (size_t)q * 4 * ld, 16);
+   };
+   // the CTA's chunk stream: tiles blockIdx.x, +gridDim.x, ... each nchunk chunks; the producer runs NST-1 ahead
+   const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+   const int total = my_tiles * nchunk;
+   if (total == 0) return;
+   int p_idx = 0;   // next chunk to request
+   auto produce = [&]() {
+      if (p_idx < total) {
+         const int tl = p_idx / nchunk, ch = p_idx - tl * nchunk;
+         int ti, tj;
+         tile_of(blockIdx.x + tl * gridDim.x, ti, tj);
+         load(ti * TM, tj * TN, ch, p_idx % NST);
+      }
+      cp_commit();
+      ++p_idx;
+   };
+   for (int s = 0; s < NST - 1; ++s) produce();
+   int c_idx = 0;
+   for (int tl = 0; tl < my_tiles; ++tl) {
+      int ti, tj;
+      tile_of(blockIdx.x + tl * gridDim.x, ti, tj);
+      const int rb = ti * TM, cb = tj * TN;
+      double acc[8][4][2];
+      const int r0 = rb + wr * 64 + g, c0 = cb + wc * 32 + 2 * t4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+         for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i][j][h] = (mode & 1) ? 0.0 : C[(size_t)(c0 + j * 8 + h) * ld + r0 + i * 8];
+      if (tl + 1 < my_tiles) {   // next C tile towards L2
+         int nti, ntj;
+         tile_of(blockIdx.x + (tl + 1) * gridDim.x, nti, ntj);
+         const double* pp = C + (size_t)(ntj * TN + (tid >> 1)) * ld + nti * TM + (tid & 1) * 64;
+#pragma unroll
+         for (int q = 0; q < 4; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 16 * q));
+      }
+      for (int ch = 0; ch < nchunk; ++ch, ++c_idx) {
+         cp_wait<NST - 2>();
+         __syncthreads();          // chunk c_idx has landed for everybody; the stage of chunk c_idx-1 is free
+         produce();
+         const int st = c_idx % NST;
+         const double* as = As + st * BK * LDA + wr * 64 + g + t4 * LDA;
+         const double* bs = Bs + st * BK * LDB + wc * 32 + g + t4 * LDB;
+#pragma unroll
+         for (int ks = 0; ks < BK; ks += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = as[ks * LDA + i * 8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = -bs[ks * LDB + j * 8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+               for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+         }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+         for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (!(mode & 1) || acc[i][j][h] == 12345.678) C[(size_t)(c0 + j * 8 + h) * ld + r0 + i * 8] = acc[i][j][h];
+   }
+}
+}  // namespace v1
+
+int main(int argc, char** argv) {
+   const int t = argc > 1 ? atoi(argv[1]) : 6016, kc = argc > 2 ? atoi(argv[2]) : 128;
+   const int ld = t;
+   double *A, *B, *C0, *C1;
+   cudaMalloc(&A, (size_t)ld * kc * 8); cudaMalloc(&B, (size_t)ld * kc * 8);
+   cudaMalloc(&C0, (size_t)ld * t * 8); cudaMalloc(&C1, (size_t)ld * t * 8);
+   std::vector<double> h((size_t)ld * kc);
+   srand(1);
+   for (auto& v : h) v = (rand() % 2001 - 1000) * 1e-3;
+   cudaMemcpy(A, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+   for (auto& v : h) v = (rand() % 2001 - 1000) * 1e-3;
+   cudaMemcpy(B, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+   cudaMemset(C0, 0, (size_t)ld * t * 8); cudaMemset(C1, 0, (size_t)ld * t * 8);
+   cudaFuncSetAttribute(v0::k, cudaFuncAttributeMaxDynamicSharedMemorySize, v0::SMEM);
+   cudaFuncSetAttribute(v1::k, cudaFuncAttributeMaxDynamicSharedMemorySize, v1::SMEM);
+   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+   const double flops = (double)kc * t * (double)(t + 1);
+   for (int mode : {0, 8, 1})
+   for (int variant = 0; variant < 2; ++variant) {
+      for (int grid : {148, 296}) {
+         if (variant == 0 && grid == 148) continue;
+         if (variant == 1) continue;
+         float best = 1e30f;
+         for (int rep = 0; rep < 6; ++rep) {
+            cudaEventRecord(e0);
+            if (variant == 0) v0::k<<<grid, 256, v0::SMEM>>>(A, B, C0, t, ld, kc, mode);
+            else v1::k<<<grid, 256, v1::SMEM>>>(A, B, C1, t, ld, kc, mode);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            best = ms < best ? ms : best;
+         }
+         printf("mode %d (1: no C traffic, 2: no operand loads) variant %d grid %d: %.1f us  %.2f TF/s  (%s)\n", mode, variant, grid, best * 1e3, flops / (best * 1e-3) / 1e12, cudaGetErrorString(cudaGetLastError()));
+      }
+   }
+   // both variants ran 6 reps x (4 / 2 grids): compare C0/24 with C1/12 on a sample
+   std::vector<double> c0(1 << 16), c1(1 << 16);
+   double md = 0, mx = 0;
+   for (int col : {0, 63, 64, 1000, t - 129, t - 1}) {
+      const int rows = std::min(t - col, 1 << 16);
+      cudaMemcpy(c0.data(), C0 + (size_t)col * ld + col, rows * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(c1.data(), C1 + (size_t)col * ld + col, rows * 8, cudaMemcpyDeviceToHost);
+      for (int i = 0; i < rows; ++i) { md = fmax(md, fabs(c0[i] / 24.0 - c1[i] / 12.0)); mx = fmax(mx, fabs(c0[i] / 24.0)); }
+   }
+   printf("max |C0/24 - C1/12| = %.3e (max |C| %.3e)\n", md, mx);
+   return 0;
+}
