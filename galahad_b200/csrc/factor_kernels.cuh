@@ -287,8 +287,11 @@ __host__ __device__ inline size_t block_smem_bytes(int wcap) {
           sizeof(int) * (2 * PB + 2 * NB + 16);
 }
 
-__global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only, int wcap,
-                                               int par, int la) {
+// SMALL: blocks of at most one sub-panel (fronts with <= 32 candidate columns, the bulk of the tree): no
+// in-block solve / update code, half the registers, two CTAs per SM.
+template <bool SMALL>
+__global__ void __launch_bounds__(256, SMALL ? 2 : 1) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only,
+                                                              int wcap, int par, int la) {
    FrontDev& f = fr[front_slot(list, slot0)];
    if (f.flag < 0) return;
    // look-ahead schedule: a front that saw a failed pivot waits for the synchronous retry rounds, because
@@ -412,8 +415,8 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
       anymoved |= moved ? 1u : 0u;
       // b. rows of the sub-block in the earlier columns of the block follow the pivot order; L_jj
       {
-         double tmp[(PB - NB) / 8];
-         if (moved) {
+         double tmp[SMALL ? 1 : (PB - NB) / 8];
+         if (!SMALL && moved) {
 #pragma unroll
             for (int s = 0; s < (PB - NB) / 8; ++s) {
                const int c = warp + 8 * s;
@@ -428,7 +431,7 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
             if (lane < wj && k < wj) lv[s] = lane > k ? sLc[spord[lane] + k * LDS] : (lane == k ? 1.0 : 0.0);
          }
          __syncthreads();          // sLc (aliased by sXa) and the old rows have been read
-         if (moved) {
+         if (!SMALL && moved) {
 #pragma unroll
             for (int s = 0; s < (PB - NB) / 8; ++s) {
                const int c = warp + 8 * s;
@@ -474,9 +477,10 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
             s2[i2] = v;
          }
       }
-      if (r1 >= w) break;
+      if (SMALL || r1 >= w) break;
       __syncthreads();
       if (c0 == 0) B200_TICK();   // 4: inverse
+      if constexpr (!SMALL) {
       // c. rows below: X = A inv(L_jj)^T on the tensor pipe.  Warp = column tile ct (8 columns) x
       //    every second row tile; inv(L_jj)(c,k) = 0 for k > c bounds the k loop.
       {
@@ -565,6 +569,7 @@ __global__ void __launch_bounds__(256) k_block(FrontDev* fr, const int* list, in
       }
       __syncthreads();
       if (c0 == 0) B200_TICK();   // 6: phase e
+      }
    }
    __syncthreads();
    B200_TICK();      // all sub-panels
