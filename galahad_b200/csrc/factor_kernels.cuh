@@ -67,6 +67,16 @@ __device__ __forceinline__ void warp_zero_pivots(unsigned& alive, int& np, int l
    }
 }
 
+// reciprocal without the special-case branches of the IEEE division: MUFU seed + three Newton steps
+// (1-2 ulp; the value is stored as D^{-1} and used consistently, so the factorisation stays exact for it)
+__device__ __forceinline__ double fast_rcp(double x) {
+   double r;
+   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+   r = fma(fma(-x, r, 1.0), r, r);
+   r = fma(fma(-x, r, 1.0), r, r);
+   r = fma(fma(-x, r, 1.0), r, r);
+   return r;
+}
 __device__ __forceinline__ void bar128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ double sel8(const double (&a)[8], int i) {
    const double s0 = (i & 1) ? a[1] : a[0], s1 = (i & 1) ? a[3] : a[2], s2 = (i & 1) ? a[5] : a[4], s3 = (i & 1) ? a[7] : a[6];
@@ -88,7 +98,7 @@ __device__ __forceinline__ double sel8(const double (&a)[8], int i) {
 // multiplier of original row r for pivot k.  Returns 0 or an SSIDS error flag (uniform).
 // sv: 2*NB + 2 doubles (two broadcast columns, reciprocal and value of the pivot); skey: 8 ints.
 __device__ __forceinline__ int ldlt32_4w(double (&a)[8], double dg, int wj, const Params& prm, int lane, int wq,
-                                         double* sv, unsigned* skey, double* sLc, double* sd, double* sdd,
+                                         double* svbase, unsigned* skey, double* sLc, double* sd, double* sdd,
                                          int* spord, int* sptype) {
    unsigned alive = (wj == NB) ? 0xffffffffu : ((1u << wj) - 1u);
    int np = 0;
@@ -117,7 +127,12 @@ __device__ __forceinline__ int ldlt32_4w(double (&a)[8], double dg, int wj, cons
 #define TK(i) do { if (prm.debug) { long long t_ = clock64(); if (i > 0) tk[i] += t_ - tlast; tlast = t_; } } while (0)
    int q = next_q(alive);
    bar128();
+   int it = 0;
    while (alive) {
+      // the broadcast buffers alternate between steps: the barrier after this step's write also orders the
+      // reads of the step before the previous one, so no barrier is needed at the end of a step
+      double* const sv = svbase + (it & 1) * (2 * NB);
+      ++it;
       const bool rowalive = (alive >> lane) & 1u;
       // ---- fast step
       {
@@ -144,7 +159,7 @@ __device__ __forceinline__ int ldlt32_4w(double (&a)[8], double dg, int wj, cons
             dg -= l * ldr;
             const int qn = next_q(alive);              // overlaps the update below
             TK(4);
-            rdg = 1.0 / dg;
+            rdg = fast_rcp(dg);
             const double2* v2 = reinterpret_cast<const double2*>(sv + cbase);
 #pragma unroll
             for (int j2 = 0; j2 < 4; ++j2) {
@@ -157,8 +172,6 @@ __device__ __forceinline__ int ldlt32_4w(double (&a)[8], double dg, int wj, cons
             np += 1;
             q = qn;
             TK(5);
-            bar128();                                   // sv is rewritten by the next step
-            TK(6);
             continue;
          }
          if (prm.posdef) return SSIDS_ERROR_NOT_POS_DEF;
@@ -271,7 +284,6 @@ __device__ __forceinline__ int ldlt32_4w(double (&a)[8], double dg, int wj, cons
       }
       rdg = 1.0 / dg;
       q = next_q(alive);
-      bar128();                                         // sv is rewritten by the next step
    }
    if (prm.debug && lane == 0 && wq == 0 && blockIdx.x == 0) printf("[pivot4] np=%d sel+sts %lld bar %lld lds+shfl+test+vote %lld dg+redux %lld rcp+update+book %lld bar %lld\n", np, tk[1], tk[2], tk[3], tk[4], tk[5], tk[6]);
 #undef TK
@@ -283,7 +295,7 @@ __host__ __device__ inline size_t block_smem_bytes(int wcap) {
    // sA wcap x (wcap+4) | sX, sXa NB x XLD each (only when the block has more than one sub-panel; sLc
    // aliases sXa) | sLj NB x NB | sInv NB x LDBB | srow | sdk, sdd | ints
    const size_t xbuf = wcap > NB ? 2 * (size_t)NB * XLD : (size_t)NB * LDS;
-   return sizeof(double) * ((size_t)wcap * (wcap + 4) + xbuf + NB * NB + NB * LDBB + 2 * NB + 2 + 2 * (2 * PB + 2)) +
+   return sizeof(double) * ((size_t)wcap * (wcap + 4) + xbuf + NB * NB + NB * LDBB + 4 * NB + 2 + 2 * (2 * PB + 2)) +
           sizeof(int) * (2 * PB + 2 * NB + 16);
 }
 
@@ -293,10 +305,15 @@ template <bool SMALL>
 __global__ void __launch_bounds__(256, SMALL ? 2 : 1) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only,
                                                               int wcap, int par, int la) {
    FrontDev& f = fr[front_slot(list, slot0)];
-   if (f.flag < 0) return;
+   // the front record is read through shared memory: one round trip instead of a chain of dependent loads
+   __shared__ FrontDev sf;
+   static_assert(sizeof(FrontDev) % 8 == 0, "FrontDev is copied in 8-byte words");
+   if (threadIdx.x < sizeof(FrontDev) / 8) reinterpret_cast<double*>(&sf)[threadIdx.x] = reinterpret_cast<const double*>(&f)[threadIdx.x];
+   __syncthreads();
+   if (sf.flag < 0) return;
    // look-ahead schedule: a front that saw a failed pivot waits for the synchronous retry rounds, because
    // parking failed columns moves entries that a concurrent bulk update may be working on
-   if (f.stall && la) {
+   if (sf.stall && la) {
       if (threadIdx.x == 0) f.urec[par][1] = 0;   // this parity's record belongs to a block that is already applied
       return;
    }
@@ -311,7 +328,7 @@ __global__ void __launch_bounds__(256, SMALL ? 2 : 1) k_block(FrontDev* fr, cons
    double* sLj = sXa + (wcap > NB ? NB * XLD : NB * LDS);   // L_jj in pivot order, sLj[i + k*NB]
    double* sInv = sLj + NB * NB;             // sInv[k*LDBB + c] = inv(L_jj)(c,k)
    double* srow = sInv + NB * LDBB;
-   double* sdk = srow + 2 * NB + 2;          // D^{-1} of the block (SSIDS format)
+   double* sdk = srow + 4 * NB + 2;          // D^{-1} of the block (SSIDS format)
    double* sdd = sdk + 2 * PB + 2;           // D of the block: diagonal, off-diagonal
    int* slperm = reinterpret_cast<int*>(sdd + 2 * PB + 2);
    int* sptype = slperm + PB;
@@ -325,9 +342,9 @@ __global__ void __launch_bounds__(256, SMALL ? 2 : 1) k_block(FrontDev* fr, cons
 #define B200_TICK() do { if (dbg && ntq < 16) tq[ntq++] = clock64(); } while (0)
    B200_TICK();
    // ---- close the previous block
-   int done = f.done, gend = f.gend, w = f.w;
+   int done = sf.done, gend = sf.gend, w = sf.w;
    if (w > 0) {
-      const int nelim = compute_nelim(f.fail, w, f.p2mask);
+      const int nelim = compute_nelim(sf.fail, w, sf.p2mask);
       const int nfail = w - nelim;
       if (prm.posdef && nfail > 0) {
          __syncthreads();
@@ -347,13 +364,13 @@ __global__ void __launch_bounds__(256, SMALL ? 2 : 1) k_block(FrontDev* fr, cons
       gend -= nfail;
    }
    // everything the rest of the kernel needs from the front record (the stores below may alias it)
-   const size_t ldl = f.ldl;
-   const int wc = f.wc;
-   double* const fL = f.L;
-   double* const A0g = f.dbuf + (size_t)PB * wc;
-   double* const dkg = f.dbuf + 2 * (size_t)PB * wc;
+   const size_t ldl = sf.ldl;
+   const int wc = sf.wc;
+   double* const fL = sf.L;
+   double* const A0g = sf.dbuf + (size_t)PB * wc;
+   double* const dkg = sf.dbuf + 2 * (size_t)PB * wc;
    double* const Linvg = dkg + 2 * PB + 2;
-   int* const ibuf = f.ibuf;
+   int* const ibuf = sf.ibuf;
    __syncthreads();
    w = finish_only ? 0 : max(0, min(wcap, gend - done));   // wcap <= PB: the launch's shared-memory capacity
    if (tid == 0) {
