@@ -760,8 +760,9 @@ int Numeric::init() {
    if (d_fr) return 0;
    CU(cudaSetDevice(P->device));
    CU(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM));
-   CU(cudaFuncSetAttribute(k_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(PB)));
-   CU(cudaFuncSetAttribute(k_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(NB)));
+   CU(cudaFuncSetAttribute(k_block<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(PB)));
+   CU(cudaFuncSetAttribute(k_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(2 * NB)));
+   CU(cudaFuncSetAttribute(k_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(NB)));
    CU(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes(PB)));
    const int nn = std::max(P->nnodes, 1);
    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -1093,8 +1094,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                // blocks shortened by failed pivots leave `done` behind ob*PB, so the row grid covers the
                // whole front; CTAs above the block exit at once
                const int yapply = std::max(1, (maxm + AR - 1) / AR);
-               if (wcap == NB) k_block<true><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
-               else k_block<false><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
+               if (wcap == NB) k_block<0><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
+               else if (wcap == 2 * NB) k_block<1><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
+               else k_block<2><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
                k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, wcap, par);
                k_commit<<<dim3(na, ycommit), 256, 0, sx>>>(d_fr, lst, b0, ncolchunks, par);
                launches += 3;
@@ -1129,7 +1131,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][0], 0));
                if (nbulk > 1) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][1], 0));
             }
-            k_block<true><<<j1 - j0, 256, block_smem_bytes(NB), sx>>>(d_fr, lst, b0, prm, 1, NB, 0, 0);
+            k_block<0><<<j1 - j0, 256, block_smem_bytes(NB), sx>>>(d_fr, lst, b0, prm, 1, NB, 0, 0);
             ++launches;
             return 0;
          };
@@ -1205,12 +1207,12 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          CU(cudaMemcpyAsync(d_list, pin_i, sizeof(int) * nt, cudaMemcpyHostToDevice, st));
          const int ncolchunks = (maxn + 63) / 64;
          const int wcap = (std::min(maxn, PB) + NB - 1) / NB * NB;
-         k_block<false><<<nt, 256, block_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, 0, wcap, 0, 0);
+         k_block<2><<<nt, 256, block_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, 0, wcap, 0, 0);
          k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap, 0);
          k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks, 0);
          k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, nullptr, 0, 0);
          if (trace) for (int s : tpp_list) trace_fronts("retry", s, 1);
-         k_block<true><<<nt, 256, block_smem_bytes(NB), st>>>(d_fr, d_list, 0, prm, 1, NB, 0, 0);
+         k_block<0><<<nt, 256, block_smem_bytes(NB), st>>>(d_fr, d_list, 0, prm, 1, NB, 0, 0);
          launches += 5;
          if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
          if (flag < 0) break;

@@ -299,11 +299,13 @@ __host__ __device__ inline size_t block_smem_bytes(int wcap) {
           sizeof(int) * (2 * PB + 2 * NB + 16);
 }
 
-// SMALL: blocks of at most one sub-panel (fronts with <= 32 candidate columns, the bulk of the tree): no
-// in-block solve / update code, half the registers, two CTAs per SM.
-template <bool SMALL>
-__global__ void __launch_bounds__(256, SMALL ? 2 : 1) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only,
+// KIND 0: blocks of at most one sub-panel (fronts with <= 32 candidate columns, the bulk of the tree): no
+// in-block solve / update code, half the registers, two CTAs per SM.  KIND 1: two sub-panels, register
+// budget of two CTAs per SM (the many 33..64-column fronts of banded / KKT problems).
+template <int KIND>      // 0: blocks of <= 32 columns, 1: <= 64 columns (both two CTAs per SM), 2: up to 128 columns
+__global__ void __launch_bounds__(256, KIND < 2 ? 2 : 1) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only,
                                                               int wcap, int par, int la) {
+   constexpr bool SMALL = KIND == 0;
    FrontDev& f = fr[front_slot(list, slot0)];
    // the front record is read through shared memory: one round trip instead of a chain of dependent loads
    __shared__ FrontDev sf;
@@ -432,10 +434,10 @@ __global__ void __launch_bounds__(256, SMALL ? 2 : 1) k_block(FrontDev* fr, cons
       anymoved |= moved ? 1u : 0u;
       // b. rows of the sub-block in the earlier columns of the block follow the pivot order; L_jj
       {
-         double tmp[SMALL ? 1 : (PB - NB) / 8];
+         double tmp[KIND == 0 ? 1 : (KIND == 1 ? NB / 8 : (PB - NB) / 8)];
          if (!SMALL && moved) {
 #pragma unroll
-            for (int s = 0; s < (PB - NB) / 8; ++s) {
+            for (int s = 0; s < (int)(sizeof(tmp) / sizeof(double)); ++s) {
                const int c = warp + 8 * s;
                tmp[s] = (c < c0 && lane < wj) ? sA[(c0 + spord[lane]) + c * sld] : 0.0;
             }
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(256, SMALL ? 2 : 1) k_block(FrontDev* fr, cons
          __syncthreads();          // sLc (aliased by sXa) and the old rows have been read
          if (!SMALL && moved) {
 #pragma unroll
-            for (int s = 0; s < (PB - NB) / 8; ++s) {
+            for (int s = 0; s < (int)(sizeof(tmp) / sizeof(double)); ++s) {
                const int c = warp + 8 * s;
                if (c < c0 && lane < wj) sA[(c0 + lane) + c * sld] = tmp[s];
             }
