@@ -496,6 +496,7 @@ class Plan {
    int *d_child_idx = nullptr, *d_rlist = nullptr, *d_rel = nullptr, *d_order = nullptr;
    int *d_aslot = nullptr, *d_asrc = nullptr, *d_acol = nullptr, *d_arow = nullptr;
    int64_t est_factor_doubles = 0, est_c_doubles[2] = {0, 0}, est_ws_doubles = 0;
+   std::vector<int64_t> lvl_L_doubles, lvl_C_doubles;   // per level, without delays (same rounding as the numeric phase)
    ~Plan() {
       cudaSetDevice(device);
       cudaFree(d_ss); cudaFree(d_child_idx); cudaFree(d_rlist); cudaFree(d_rel); cudaFree(d_order);
@@ -643,6 +644,16 @@ Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
          ws += (int64_t)front_ws_doubles(align_up(st.nrow, 2), st.ncol);
       }
       P->est_c_doubles[l & 1] = std::max(P->est_c_doubles[l & 1], c);
+      {
+         int64_t tl = 0, tc = 0;
+         for (int s = P->lvl_ptr[l]; s < P->lvl_ptr[l + 1]; ++s) {
+            const SlotStatic& st2 = P->hss[s];
+            tl += (int64_t)align_up((size_t)align_up(st2.nrow, 2) * st2.ncol, 32);
+            tc += (int64_t)align_up((size_t)align_up(st2.nrow - st2.ncol, 2) * (st2.nrow - st2.ncol), 32);
+         }
+         P->lvl_L_doubles.push_back(tl);
+         P->lvl_C_doubles.push_back(tc);
+      }
       P->est_ws_doubles = std::max(P->est_ws_doubles, ws);
    }
    std::vector<int> order(sym.order);
@@ -697,6 +708,11 @@ class Numeric {
    static constexpr int NAUX = 4;
    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+   // zero-fill of the next level's L and C regions on a side stream while this level is factorised
+   cudaStream_t zs = nullptr;
+   cudaEvent_t ev_ea = nullptr, ev_zero = nullptr;
+   char *prez_c = nullptr, *prez_l = nullptr;
+   size_t prez_c_bytes = 0, prez_l_bytes = 0;
    // look-ahead: bulk-update stream and events per chunk stream (0: st, 1..NAUX: aux[g-1])
    cudaStream_t bulk[NAUX + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
    cudaEvent_t ev_commit[NAUX + 1][2] = {}, ev_bulk[NAUX + 1][2] = {};
@@ -720,6 +736,9 @@ class Numeric {
       if (st) cudaStreamDestroy(st);
       for (int g = 0; g < NAUX; ++g) { if (aux[g]) cudaStreamDestroy(aux[g]); if (ev_join[g]) cudaEventDestroy(ev_join[g]); }
       if (ev_fork) cudaEventDestroy(ev_fork);
+      if (zs) cudaStreamDestroy(zs);
+      if (ev_ea) cudaEventDestroy(ev_ea);
+      if (ev_zero) cudaEventDestroy(ev_zero);
       for (int g = 0; g <= NAUX; ++g) {
          if (bulk[g]) cudaStreamDestroy(bulk[g]);
          for (int q = 0; q < 2; ++q) { if (ev_commit[g][q]) cudaEventDestroy(ev_commit[g][q]); if (ev_bulk[g][q]) cudaEventDestroy(ev_bulk[g][q]); }
@@ -771,6 +790,9 @@ int Numeric::init() {
       CU(cudaEventCreateWithFlags(&ev_join[g], cudaEventDisableTiming));
    }
    CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+   CU(cudaStreamCreateWithFlags(&zs, cudaStreamNonBlocking));
+   CU(cudaEventCreateWithFlags(&ev_ea, cudaEventDisableTiming));
+   CU(cudaEventCreateWithFlags(&ev_zero, cudaEventDisableTiming));
    for (int g = 0; g <= NAUX; ++g) {
       CU(cudaStreamCreateWithFlags(&bulk[g], cudaStreamNonBlocking));
       for (int q = 0; q < 2; ++q) {
@@ -871,6 +893,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    std::vector<int> lvl_list, tpp_list;
    std::vector<int64_t> tileptr;
    size_t updmap_used = 0;
+   prez_c = prez_l = nullptr;
    const bool lvl_times = getenv("B200LDLT_LEVELTIMES") != nullptr;   // wall time per level (each level ends with a sync)
    for (int l = 0; l < P->nlevels && flag >= 0; ++l) {
       const int s0 = P->lvl_ptr[l], s1 = P->lvl_ptr[l + 1], ns = s1 - s0;
@@ -943,8 +966,16 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       }
       memcpy(pin_fr + s0, hfr.data() + s0, sizeof(FrontDev) * ns);
       CU(cudaMemcpyAsync(d_fr + s0, pin_fr + s0, sizeof(FrontDev) * ns, cudaMemcpyHostToDevice, st));
-      CU(cudaMemsetAsync(Lb, 0, totL * 8, st));
-      if (totC) CU(cudaMemsetAsync(Cb, 0, totC * 8, st));
+      {
+         // what the previous level's side stream has already zeroed (sizes without delays) is skipped
+         size_t zl = 0, zc = 0;
+         if (prez_l || prez_c) CU(cudaStreamWaitEvent(st, ev_zero, 0));
+         if (prez_l && prez_l == (char*)Lb) zl = std::min(prez_l_bytes, totL * 8);
+         if (prez_c && prez_c == (char*)Cb) zc = std::min(prez_c_bytes, totC * 8);
+         prez_l = prez_c = nullptr;
+         if (totL * 8 > zl) CU(cudaMemsetAsync((char*)Lb + zl, 0, totL * 8 - zl, st));
+         if (totC * 8 > zc) CU(cudaMemsetAsync((char*)Cb + zc, 0, totC * 8 - zc, st));
+      }
       CU(cudaMemsetAsync(Db, 0, totD * 8, st));
       const int cb = P->hss[s0].child_begin, ce = P->hss[s1 - 1].child_end;
       if (ce > cb)
@@ -1005,6 +1036,23 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             ++launches;
          }
          // the staging regions stay untouched until the level's closing synchronisation (collect)
+      }
+      // The children's contribution blocks (the other arena) are dead once extend-add has run: zero the next
+      // level's C region there, and its L region behind this level's, beside the factorisation kernels.
+      if (phase == 0 && l + 1 < P->nlevels && !trace) {
+         Arena& na2 = car[(l + 1) & 1];
+         const size_t cbytes = (size_t)P->lvl_C_doubles[l + 1] * 8, lbytes = (size_t)P->lvl_L_doubles[l + 1] * 8;
+         CU(cudaEventRecord(ev_ea, st));
+         CU(cudaStreamWaitEvent(zs, ev_ea, 0));
+         if (cbytes > 0 && !na2.chunks.empty() && cbytes <= na2.chunks[0].size) {
+            prez_c = na2.chunks[0].p; prez_c_bytes = cbytes;
+            CU(cudaMemsetAsync(prez_c, 0, cbytes, zs));
+         }
+         if (lbytes > 0 && fac.cur < fac.chunks.size() && fac.off + align_up(lbytes, 256) <= fac.chunks[fac.cur].size) {
+            prez_l = fac.chunks[fac.cur].p + fac.off; prez_l_bytes = lbytes;
+            CU(cudaMemsetAsync(prez_l, 0, lbytes, zs));
+         }
+         CU(cudaEventRecord(ev_zero, zs));
       }
       // factor: fronts bucketed by size class, sorted by candidate count (descending) inside.
       // Each bucket runs rounds of blocks (PB columns, four launches each); the

@@ -203,3 +203,31 @@ def backward_error(prob, x, b):
     r = A @ x - b
     an = abs(A).sum(axis=1).max()
     return float(np.abs(r).max() / (an * np.abs(x).max() + np.abs(b).max()))
+
+
+def dense_front_problem(n, kind, seed=SEED):
+    """A dense symmetric matrix factorised as ONE front (identity order).  kinds: 'spd', 'indef' (random),
+    'zdiag' (zero diagonal: 2x2 pivots everywhere), 'kkt' (zero (2,2) block), 'small' (badly scaled).
+    Returns (A, problem dict); the expected inertia comes from the eigenvalues."""
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(-1, 1, (n, n))
+    A = (A + A.T) / 2
+    if kind == "zdiag":
+        np.fill_diagonal(A, 0.0)
+    elif kind == "kkt":
+        k = n // 3
+        A[n - k:, n - k:] = 0.0
+        A[:n - k, :n - k] += np.eye(n - k) * 2
+    elif kind == "spd":
+        A = A @ A.T + n * np.eye(n)
+    elif kind == "small":
+        A[:, : n // 2] *= 1e-3
+        A[: n // 2, :] *= 1e-3
+    il = np.tril_indices(n)
+    order = np.lexsort((il[0], il[1]))           # column-major lower triangle
+    row, col = il[0][order], il[1][order]
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(col, minlength=n))]).astype(np.int64)
+    val = A[row, col].copy()
+    neg = int((np.linalg.eigvalsh(A) < 0).sum())
+    return A, dict(n=n, ptr=ptr, row=row.astype(np.int32), val=val, order=np.arange(n, dtype=np.int32),
+                   inertia=(n - neg, neg, 0), name=f"dense_{kind}_{n}")

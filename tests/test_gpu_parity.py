@@ -132,6 +132,26 @@ def test_medium_grid_properties():
         assert P.backward_error(prob, x, b) <= 1e-14
 
 
+def test_dense_fronts_with_failed_pivots():
+    """One dense front per matrix: zero-diagonal / KKT-like matrices force 2x2 pivots, failed columns
+    (a-posteriori test), shortened blocks, TPP and the retry rounds; orders above 1024 run under the
+    look-ahead schedule (a failed pivot stalls the front until the synchronous retry rounds).  Inertia
+    against the eigenvalues (exact), solutions by backward error."""
+    for kind, n in (("zdiag", 142), ("kkt", 517), ("indef", 1300), ("zdiag", 2100), ("spd", 1100)):
+        A, prob = P.dense_front_problem(n, kind, seed=n)
+        s, flag = gpu_factor(prob)
+        assert flag >= 0, (kind, n, flag)
+        assert s.inform.num_neg == prob["inertia"][1], (kind, n)
+        b = A @ np.ones(n)
+        f, x = s.solve(b)
+        be = np.abs(A @ x - b).max() / (np.abs(A).sum(1).max() * np.abs(x).max() + np.abs(b).max())
+        assert f == 0 and be <= 1e-13, (kind, n, be)
+        if kind == "spd":
+            s2, flag2 = gpu_factor(prob, posdef=True)
+            f, x2 = s2.solve(b)
+            assert flag2 == 0 and np.abs(x2 - x).max() <= 1e-10 * np.abs(x).max()
+
+
 @pytest.mark.parametrize("nranks", [2, 4])
 def test_tree_parallel_ranks_emulated(nranks):
     """The multi-rank path (subtree partition, packed boundary fronts, phased solve) with every
