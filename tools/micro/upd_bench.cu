@@ -324,9 +324,9 @@ int main(int argc, char** argv) {
    cudaFuncSetAttribute(v2::k, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM);
    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
    const double flops = (double)kc * t * (double)(t + 1);
-   for (int mode : {0, 16, 32, 1})
+   for (int mode : {0})
    for (int variant : {0}) {
-      for (int grid : {296}) {
+      for (int grid : {296, 592}) {
          float best = 1e30f;
          for (int rep = 0; rep < 6; ++rep) {
             cudaEventRecord(e0);
