@@ -424,6 +424,12 @@ __global__ void k_stats(const FrontDev* fr, int nslots, int* counters) {
 
 #include "solve_kernels.cuh"
 
+static inline size_t step_smem_fwd(int kbc) { return (size_t)(kbc * (kbc + 1) + kbc + 256) * 8; }
+static inline int step_grid_y(int rows, int rc, int slots, int fronts) {
+   return std::max(1, std::min((rows + rc - 1) / rc, slots / std::max(1, fronts)));
+}
+static inline size_t step_smem_bwd(int kbc) { return (size_t)(kbc * (kbc + 1) + std::max(kbc, SE / kbc) + 32) * 8; }
+
 // multi-GPU: which pivots did this rank eliminate, and which of them in the root part
 __global__ void k_build_masks(const FrontDev* fr, int nslots, char* mine, char* root) {
    const int lane = threadIdx.x & 31;
@@ -689,8 +695,9 @@ class Numeric {
    static constexpr size_t UPDMAP_CAP = (size_t)3 << 20;   // ints
    int64_t* d_xw_off = nullptr;
    int64_t* d_part_off = nullptr;
+   int* d_ticket = nullptr;         // per slot: arrival counter of the backward step's CTAs (left at zero by the last one)
    int* d_slist = nullptr;
-   std::vector<int> slist, lvl_steps, lvl_maxm;
+   std::vector<int> slist, lvl_steps, lvl_maxm, lvl_maxne;
    std::vector<std::vector<int>> lvl_nact, lvl_actm;
    int64_t part_total = 0;
    double* d_part = nullptr;
@@ -728,7 +735,7 @@ class Numeric {
       cudaSetDevice(P->device);
       fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release(); bar.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
-      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
+      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
       if (pin_updmap) cudaFreeHost(pin_updmap);
@@ -783,6 +790,8 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(2 * NB)));
    CU(cudaFuncSetAttribute(k_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(NB)));
    CU(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes(PB)));
+   CU(cudaFuncSetAttribute(k_fwd_step<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd(128)));
+   CU(cudaFuncSetAttribute(k_bwd_step<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    const int nn = std::max(P->nnodes, 1);
    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
    for (int g = 0; g < NAUX; ++g) {
@@ -817,6 +826,8 @@ int Numeric::init() {
    CU(cudaMallocHost(&pin_updmap, sizeof(int) * UPDMAP_CAP));
    CU(cudaMalloc(&d_xw_off, sizeof(int64_t) * (nn + 1)));
    CU(cudaMalloc(&d_part_off, sizeof(int64_t) * (nn + 1)));
+   CU(cudaMalloc(&d_ticket, sizeof(int) * (nn + 1)));
+   CU(cudaMemset(d_ticket, 0, sizeof(int) * (nn + 1)));
    CU(cudaMalloc(&d_slist, sizeof(int) * nn));
    CU(cudaMalloc(&d_val, sizeof(double) * std::max<int64_t>(P->sym->nz, 1)));
    child_doff.assign(P->child_idx.size(), 0);
@@ -928,7 +939,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          f.done = 0; f.gend = f.n; f.w = 0; f.fail = 0; f.nelim = 0; f.flag = 0; f.wc = block_wc(f.n);
          f.state = 2; f.active = 1; f.part_kind = part_kind[s];
          totL += align_up((size_t)f.ldl * f.n, 32);
-         if (!boundary[s]) totC += align_up((size_t)f.ldc * (f.m - f.n), 32);
+         if (!boundary[s]) totC += align_up((size_t)f.ldc * (f.m - f.n) + 1, 32);
          totD += align_up(2 * (size_t)f.n + 2, 32);
          totP += 2 * align_up((size_t)f.n + 1, 32);
          totW += front_ws_doubles(f.ldl, f.n);
@@ -948,12 +959,15 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             f.L = Lb + oL; oL += align_up((size_t)f.ldl * f.n, 32);
             if (boundary[s]) {
                // the contribution block crosses a part boundary: it must outlive the level arenas
-               size_t cb = align_up((size_t)f.ldc * (f.m - f.n), 32) * 8;
+               size_t cb = align_up((size_t)f.ldc * (f.m - f.n) + 1, 32) * 8;
                f.C = (double*)bar.alloc(cb);
                if (!f.C) { stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_ALLOCATION; }
                CU(cudaMemsetAsync(f.C, 0, cb, st));
+               f.C += f.n & 1;
             } else {
-               f.C = Cb + oC; oC += align_up((size_t)f.ldc * (f.m - f.n), 32);
+               // C(r, c) sits at f.C + (c - n) ldc + (r - n): shifted by one double when n is odd, so that even rows r
+               // are 16-byte aligned in C exactly as they are in L (k_update's paired accesses)
+               f.C = Cb + oC + (f.n & 1); oC += align_up((size_t)f.ldc * (f.m - f.n) + 1, 32);
             }
             f.D = Db + oD; oD += align_up(2 * (size_t)f.n + 2, 32);
             f.perm = Pb + oP; f.orig = f.perm + align_up((size_t)f.n + 1, 32); oP += 2 * align_up((size_t)f.n + 1, 32);
@@ -1334,13 +1348,14 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       CU(cudaMemcpy(d_xw_off, off.data(), sizeof(int64_t) * (nn + 1), cudaMemcpyHostToDevice));
       // partial-dot workspace of the backward solve: (row chunks + 1) x KB per front
       std::vector<int64_t> poff(nn + 1, 0);
-      for (int s = 0; s < nn; ++s) poff[s + 1] = poff[s] + (int64_t)((hfr[s].m + RD - 1) / RD + 1) * KB;
+      for (int s = 0; s < nn; ++s) poff[s + 1] = poff[s] + (int64_t)((hfr[s].m + 63) / 64 + 1) * KB;   // chunks of >= SE / KB = 64 rows
       part_total = poff[nn];
       CU(cudaMemcpy(d_part_off, poff.data(), sizeof(int64_t) * (nn + 1), cudaMemcpyHostToDevice));
       // per level: fronts sorted by eliminated columns (descending) so that the fronts active in
       // column block `step` form a prefix
       slist.assign(nn, 0);
       lvl_steps.assign(P->nlevels, 0);
+      lvl_maxne.assign(P->nlevels, 0);
       lvl_nact.assign(P->nlevels, std::vector<int>());
       lvl_actm.assign(P->nlevels, std::vector<int>());
       for (int l = 0; l < P->nlevels; ++l) {
@@ -1354,6 +1369,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          auto ne_of = [&](int s) { return hfr[s].state == 2 ? hfr[s].nelim : 0; };
          const int steps = a1 > a0 ? (ne_of(slist[a0]) + KB - 1) / KB : 0;
          lvl_steps[l] = steps;
+         lvl_maxne[l] = a1 > a0 ? ne_of(slist[a0]) : 0;
          lvl_nact[l].assign(steps, 0);
          lvl_actm[l].assign(steps, 0);
          for (int st2 = 0; st2 < steps; ++st2) {
@@ -1415,12 +1431,15 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
       for (int sp = 0; sp < lvl_steps[l]; ++sp) {
          const int na = lvl_nact[l][sp];
          if (na == 0) break;
-         k_fwd_tri<<<na, 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, sp, kind);
-         const int rows = lvl_actm[l][sp] - sp * KB - 1;
-         if (rows > 0) { k_fwd_upd<<<dim3(na, (rows + RC - 1) / RC), 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, sp, kind); ++nlaunch; }
+         const int kbmax = std::min(KB, lvl_maxne[l] - sp * KB);
+         const int rows = std::max(0, lvl_actm[l][sp] - sp * KB - 1);
+         // one wave of CTAs: a front's row chunks are dealt to at most `slots / fronts` CTAs
+         if (kbmax <= 32) k_fwd_step<32><<<dim3(na, step_grid_y(rows, SE / 32, 2 * 148, na)), 256, step_smem_fwd(32), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, sp, kind);
+         else if (kbmax <= 64) k_fwd_step<64><<<dim3(na, step_grid_y(rows, SE / 64, 2 * 148, na)), 256, step_smem_fwd(64), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, sp, kind);
+         else k_fwd_step<128><<<dim3(na, step_grid_y(rows, SE / 128, 148, na)), 256, step_smem_fwd(128), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, sp, kind);
          ++nlaunch;
       }
-      k_fwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xw, d_xp, s0, posdef ? 1 : 0, kind);
+      k_fwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xa, d_xp, s0, posdef ? 1 : 0, kind);
       ++nlaunch;
    }
 }
@@ -1433,9 +1452,11 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
       for (int sp = lvl_steps[l] - 1; sp >= 0; --sp) {
          const int na = lvl_nact[l][sp];
          if (na == 0) continue;
-         const int rows = lvl_actm[l][sp] - sp * KB - 1;
-         if (rows > 0) { k_bwd_dots<<<dim3(na, (rows + RD - 1) / RD), 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, sp, kind); ++nlaunch; }
-         k_bwd_tri<<<na, 256, 0, st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, sp, kind);
+         const int kbmax = std::min(KB, lvl_maxne[l] - sp * KB);
+         const int rows = std::max(0, lvl_actm[l][sp] - sp * KB - 1);
+         if (kbmax <= 32) k_bwd_step<32><<<dim3(na, step_grid_y(rows, SE / 32, 3 * 148, na)), 256, step_smem_bwd(32), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, sp, kind);
+         else if (kbmax <= 64) k_bwd_step<64><<<dim3(na, step_grid_y(rows, SE / 64, 3 * 148, na)), 256, step_smem_bwd(64), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, sp, kind);
+         else k_bwd_step<128><<<dim3(na, step_grid_y(rows, SE / 128, 148, na)), 256, step_smem_bwd(128), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, sp, kind);
          ++nlaunch;
       }
       k_bwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xw, d_xp, s0, kind);

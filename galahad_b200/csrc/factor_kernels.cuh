@@ -981,32 +981,36 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
       const bool has_next = normalise(nti, ntj);
       const int nrbase = cbeg + nti * TM, ncbase = cbeg + ntj * TN;
       double acc[4][4][2];
-      // accumulators start as the C tile; the product is subtracted by feeding -B to the MMA
-      const int r0 = rbase + wr * 32 + g, c0 = cbase + wc * 32 + 2 * t4;
+      // accumulators start as the C tile; the product is subtracted by feeding -B to the MMA.  The MMA computes
+      // the TRANSPOSE of the tile (B-operand rows are the tile's columns), so that a thread's two accumulator
+      // elements are two consecutive rows of one column: one 16-byte access instead of two 8-byte ones.
+      // acc[i][j][h] = C(r0 + 8 i + h, c0 + 8 j)
+      const int r0 = rbase + wr * 32 + 2 * t4, c0 = cbase + wc * 32 + g;
       if (full && below) {
 #pragma unroll
-         for (int j = 0; j < 4; ++j)
+         for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j * 8;
+            const double* colp = (c < fn) ? (Lp + (size_t)c * ldl + r0) : (Cp + (size_t)(c - fn) * ldc + (r0 - fn));
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-               const int c = c0 + j * 8 + h;
-               const double* colp = (c < fn) ? (Lp + (size_t)c * ldl + r0) : (Cp + (size_t)(c - fn) * ldc + (r0 - fn));
-#pragma unroll
-               for (int i = 0; i < 4; ++i) acc[i][j][h] = colp[i * 8];
+            for (int i = 0; i < 4; ++i) {
+               const double2 v = *reinterpret_cast<const double2*>(colp + i * 8);
+               acc[i][j][0] = v.x; acc[i][j][1] = v.y;
             }
+         }
       } else {
 #pragma unroll
-         for (int j = 0; j < 4; ++j)
+         for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j * 8;
+            const bool cv = c < cend;
+            const double* colp = (c < fn) ? (Lp + (size_t)c * ldl) : (Cp + (size_t)(c - fn) * ldc - fn);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-               const int c = c0 + j * 8 + h;
-               const bool cv = c < cend;
-               const double* colp = (c < fn) ? (Lp + (size_t)c * ldl) : (Cp + (size_t)(c - fn) * ldc - fn);
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-               for (int i = 0; i < 4; ++i) {
-                  const int r = r0 + i * 8;
+               for (int h = 0; h < 2; ++h) {
+                  const int r = r0 + i * 8 + h;
                   acc[i][j][h] = (cv && r < m && r >= c) ? colp[r] : 0.0;
                }
-            }
+         }
       }
       for (int ch = 0; ch < nchunk; ++ch) {
          if (ch + 1 < nchunk) {
@@ -1046,7 +1050,7 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-               for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], -bf[cur][j]);
+               for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], -bf[cur][j], af[cur][i]);
          }
          __syncthreads();
          buf ^= 1;
@@ -1054,28 +1058,26 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
       // epilogue: store only
       if (full && below) {
 #pragma unroll
-         for (int j = 0; j < 4; ++j)
+         for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j * 8;
+            double* colp = (c < fn) ? (Lp + (size_t)c * ldl + r0) : (Cp + (size_t)(c - fn) * ldc + (r0 - fn));
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-               const int c = c0 + j * 8 + h;
-               double* colp = (c < fn) ? (Lp + (size_t)c * ldl + r0) : (Cp + (size_t)(c - fn) * ldc + (r0 - fn));
-#pragma unroll
-               for (int i = 0; i < 4; ++i) colp[i * 8] = acc[i][j][h];
-            }
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<double2*>(colp + i * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+         }
       } else {
 #pragma unroll
-         for (int j = 0; j < 4; ++j)
+         for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j * 8;
+            if (c >= cend) continue;
+            double* colp = (c < fn) ? (Lp + (size_t)c * ldl) : (Cp + (size_t)(c - fn) * ldc - fn);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-               const int c = c0 + j * 8 + h;
-               if (c >= cend) continue;
-               double* colp = (c < fn) ? (Lp + (size_t)c * ldl) : (Cp + (size_t)(c - fn) * ldc - fn);
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-               for (int i = 0; i < 4; ++i) {
-                  const int r = r0 + i * 8;
+               for (int h = 0; h < 2; ++h) {
+                  const int r = r0 + i * 8 + h;
                   if (r < m && r >= c) colp[r] = acc[i][j][h];
                }
-            }
+         }
       }
       if (!has_next) break;
       ti = nti; tj = ntj;

@@ -2,16 +2,22 @@
 //
 // Reference behaviour: NumericSubtree.hxx:280-400 (gather, trsv/gemv per node, scatter) and
 // ldlt_app.cxx:2537-2588.  Here every level of the (fused) assembly tree is processed by batched
-// kernels; a front's L is walked in column blocks of KB: a single CTA solves the KB x KB triangle,
-// then all rows below are updated (forward) / reduced (backward) by many CTAs, so the big fronts
-// stream L at HBM speed instead of through one SM.  No atomics: children's contributions are
-// gathered by the parent in child order, partial dot products are summed in chunk order, so a
-// solve is bit-reproducible.
+// kernels; a front's L is walked in column blocks of KB, ONE launch per block and direction:
+//   forward  (k_fwd_step): every CTA of a front stages the block's KB x KB triangle in shared memory and
+//            solves it (redundantly: the result is needed by all of them and there is no inter-CTA wait),
+//            then applies the block's columns to its own chunk of the rows below, whose entries of L it
+//            requested before touching the triangle;
+//   backward (k_bwd_step): every CTA forms the partial dot products of its chunk of rows with the block's
+//            columns; the CTA that finishes last (ticket counter) sums the partials in chunk order and solves
+//            the transposed triangle.
+// Everything here is bound by memory latency, not bandwidth (ncu launch list, profiles/r1_notes.md part 3):
+// each thread therefore has all of its loads (32 per thread) in flight at once, and dependent work runs from
+// shared memory.  No floating-point atomics: children's contributions are gathered by the parent in child
+// order and partial dot products are summed in chunk order, so a solve is bit-reproducible.
 #pragma once
 
-constexpr int KB = 256;      // solve column block
-constexpr int RC = 64;       // rows per CTA in the forward update
-constexpr int RD = 128;      // rows per CTA in the backward dot products
+constexpr int KB = 128;      // solve column block
+constexpr int SE = 8192;     // entries of L per CTA in the update / dot phases: rows x block columns, 32 per thread
 
 __device__ __forceinline__ int row_gidx(const FrontDev& f, const int* rl, int r) {
    return r < f.n ? f.perm[r] : rl[f.ncol + (r - f.n)];
@@ -77,91 +83,146 @@ __global__ void __launch_bounds__(256) k_fwd_gather(const FrontDev* __restrict__
    }
 }
 
-// solve the KB x KB unit-lower triangle of block `step`; one CTA per front
-__global__ void __launch_bounds__(256) k_fwd_tri(const FrontDev* __restrict__ fr, const int* __restrict__ list,
-                                                 const int64_t* __restrict__ xw_off, double* XW, int step, int kind) {
-   const int s = list[blockIdx.x];
-   const FrontDev& f = fr[s];
-   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
-   const int ne = f.nelim, k0 = step * KB;
-   if (k0 >= ne) return;
-   const int kb = min(KB, ne - k0);
-   double* xw = XW + xw_off[s];
-   const size_t ldl = f.ldl;
-   const double* __restrict__ L = f.L;
-   __shared__ double ys[KB];
-   for (int i = threadIdx.x; i < kb; i += 256) ys[i] = xw[k0 + i];
-   __syncthreads();
+// stage the lower triangle of L(k0:k0+kb, k0:k0+kb) in shared memory (column-major, leading dimension sld)
+__device__ __forceinline__ void stage_triangle(double* S, int sld, const double* __restrict__ Lb, size_t ldl, int kb) {
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   for (int c = wid; c < kb; c += 8)
+      for (int r = (c & ~31) + lane; r < kb; r += 32) cp_async8(S + c * sld + r, Lb + (size_t)c * ldl + r, true);
+   cp_async_commit();
+}
+
+// xs(0:kb) <- L^{-1} xs, L unit lower triangular in shared memory; 32 x 32 sub-triangles by one warp with the
+// row in registers and the solution passed by shuffles, the rows below them by all threads
+__device__ __forceinline__ void smem_solve_lower(const double* S, int sld, int kb, double* xs) {
    const int lane = threadIdx.x & 31;
    for (int s0 = 0; s0 < kb; s0 += 32) {
       const int sb = min(32, kb - s0);
       if (threadIdx.x < 32) {
-         // lane i holds row i of the 32x32 sub-triangle in registers
          double lrow[32];
-         const double* Lb = L + (size_t)(k0 + s0) * ldl + k0 + s0 + lane;
+         const double* Sb = S + s0 * sld + s0 + lane;
 #pragma unroll
-         for (int j = 0; j < 32; ++j) lrow[j] = (j < lane && lane < sb) ? Lb[(size_t)j * ldl] : 0.0;
-         double xi = lane < sb ? ys[s0 + lane] : 0.0;
+         for (int j = 0; j < 32; ++j) lrow[j] = (j < lane && lane < sb) ? Sb[j * sld] : 0.0;
+         double xi = lane < sb ? xs[s0 + lane] : 0.0;
 #pragma unroll
          for (int j = 0; j < 32; ++j) {
-            double yj = __shfl_sync(0xffffffffu, xi, j);
+            const double yj = __shfl_sync(0xffffffffu, xi, j);
             xi -= lrow[j] * yj;
          }
-         if (lane < sb) ys[s0 + lane] = xi;
+         if (lane < sb) xs[s0 + lane] = xi;
       }
       __syncthreads();
-      // rows of this KB block below the sub-block
       const int r = s0 + sb + threadIdx.x;
       if (r < kb) {
-         const double* Lr = L + (size_t)(k0 + s0) * ldl + k0 + r;
-         double acc = 0.0;
+         const double* Sr = S + s0 * sld + r;
+         double a0 = 0.0, a1 = 0.0;
 #pragma unroll 8
-         for (int j = 0; j < sb; ++j) acc += Lr[(size_t)j * ldl] * ys[s0 + j];
-         ys[r] -= acc;
+         for (int j = 0; j < sb; j += 2) { a0 += Sr[j * sld] * xs[s0 + j]; if (j + 1 < sb) a1 += Sr[(j + 1) * sld] * xs[s0 + j + 1]; }
+         xs[r] -= a0 + a1;
       }
       __syncthreads();
    }
-   for (int i = threadIdx.x; i < kb; i += 256) xw[k0 + i] = ys[i];
 }
 
-// xw(r) -= L(r, block) y(block) for the rows below block `step`; RC rows per CTA, 4 threads per row
-__global__ void __launch_bounds__(256) k_fwd_upd(const FrontDev* __restrict__ fr, const int* __restrict__ list,
-                                                 const int64_t* __restrict__ xw_off, double* XW, int step, int kind) {
+// xs(0:kb) <- L^{-T} xs, sub-blocks last to first; dots = 32 doubles of scratch
+__device__ __forceinline__ void smem_solve_lower_t(const double* S, int sld, int kb, double* xs, double* dots) {
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const int nsb = (kb + 31) / 32;
+   for (int sbi = nsb - 1; sbi >= 0; --sbi) {
+      const int s0 = sbi * 32, sb = min(32, kb - s0);
+      // the rows of the block already solved: columns s0..s0+sb, rows s0+sb..kb (contiguous down a column)
+      for (int j = wid; j < sb; j += 8) {
+         const double* col = S + (s0 + j) * sld;
+         double acc = 0.0;
+         for (int r = s0 + sb + lane; r < kb; r += 32) acc += col[r] * xs[r];
+#pragma unroll
+         for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+         if (lane == 0) dots[j] = acc;
+      }
+      __syncthreads();
+      if (threadIdx.x < 32) {
+         // lane i holds column i of the sub-triangle (rows below the diagonal) = row i of L^T
+         double lcol[32];
+         const double* Sb = S + (s0 + lane) * sld + s0;
+#pragma unroll
+         for (int j = 0; j < 32; ++j) lcol[j] = (j > lane && j < sb && lane < sb) ? Sb[j] : 0.0;
+         double v = lane < sb ? xs[s0 + lane] - dots[lane] : 0.0;
+#pragma unroll
+         for (int j = 31; j >= 0; --j) {
+            const double xj = __shfl_sync(0xffffffffu, v, j);
+            v -= lcol[j] * xj;
+         }
+         if (lane < sb) xs[s0 + lane] = v;
+      }
+      __syncthreads();
+   }
+}
+
+// Forward step for column block `step` of every front of the launch.  KBC = 32 / 64 / 128 bounds the block
+// width of the launch; a CTA covers RC = SE / KBC rows below the block, NG = 256 / RC threads per row.
+// The solved block goes to XY (the front's slice of the gather accumulators, dead by now), never back into
+// xw: a CTA scheduled late must still find the unsolved right-hand side there.
+template <int KBC>
+__global__ void __launch_bounds__(256, KBC <= 64 ? 2 : 1) k_fwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
+                                                  const int64_t* __restrict__ xw_off, double* XW, double* XY, int step, int kind) {
+   constexpr int RC = SE / KBC, NG = 256 / RC, SLD = KBC + 1;
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
    if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const int ne = f.nelim, k0 = step * KB;
    if (k0 >= ne) return;
-   const int kb = min(KB, ne - k0);
-   const int r0 = k0 + kb + blockIdx.y * RC;
-   if (r0 >= f.m) return;
+   const int kb = min(KB, ne - k0), m = f.m;
+   const int nchunk = (m - (k0 + kb) + RC - 1) / RC;      // chunks of RC rows below the block; CTA y takes y, y + gridDim.y, ...
+   if (blockIdx.y > 0 && (int)blockIdx.y >= nchunk) return;
+   extern __shared__ double sm[];
+   double* S = sm;                    // KBC x SLD
+   double* xs = sm + KBC * SLD;       // KBC
+   double* red = xs + KBC;            // 256
    double* xw = XW + xw_off[s];
-   __shared__ double ys[KB];
-   __shared__ double part[4][RC];
-   for (int i = threadIdx.x; i < kb; i += 256) ys[i] = xw[k0 + i];
+   const size_t ldl = f.ldl;
+   const double* __restrict__ Lb = f.L + (size_t)k0 * ldl + k0;
+   stage_triangle(S, SLD, Lb, ldl, kb);
+   // this CTA's part of the rows below: thread (row rl, column group g) holds 32 entries of L
+   const int rl = threadIdx.x & (RC - 1), g = threadIdx.x / RC;
+   const double* __restrict__ Lg = f.L + (size_t)(k0 + g * (KBC / NG)) * ldl;
+   double lreg[KBC / NG];
+   int r = k0 + kb + blockIdx.y * RC + rl;
+#pragma unroll
+   for (int j = 0; j < KBC / NG; ++j) lreg[j] = (r < m && g * (KBC / NG) + j < kb) ? Lg[(size_t)j * ldl + r] : 0.0;
+   for (int i = threadIdx.x; i < KBC; i += 256) xs[i] = i < kb ? xw[k0 + i] : 0.0;
+   cp_async_wait<0>();
    __syncthreads();
-   const int rl = threadIdx.x & (RC - 1), q = threadIdx.x / RC;
-   const int r = r0 + rl;
-   double acc = 0.0;
-   if (r < f.m) {
-      const int j0 = q * (KB / 4), j1 = min(kb, j0 + KB / 4);
-      const double* __restrict__ Lr = f.L + (size_t)(k0 + j0) * f.ldl + r;
-      const size_t ldl = f.ldl;
-      int j = j0;
-      for (; j + 8 <= j1; j += 8) {
-         double v[8];
-#pragma unroll
-         for (int u = 0; u < 8; ++u) v[u] = Lr[(size_t)(j - j0 + u) * ldl];
-#pragma unroll
-         for (int u = 0; u < 8; ++u) acc += v[u] * ys[j + u];
-      }
-      for (; j < j1; ++j) acc += Lr[(size_t)(j - j0) * ldl] * ys[j];
+   smem_solve_lower(S, SLD, kb, xs);
+   if (blockIdx.y == 0) {
+      double* xy = XY + xw_off[s];
+      for (int i = threadIdx.x; i < kb; i += 256) xy[k0 + i] = xs[i];
    }
-   part[q][rl] = acc;
-   __syncthreads();
-   if (q == 0 && r < f.m) xw[r] -= (part[0][rl] + part[1][rl]) + (part[2][rl] + part[3][rl]);
+   double xg[KBC / NG];
+#pragma unroll
+   for (int j = 0; j < KBC / NG; ++j) xg[j] = xs[g * (KBC / NG) + j];
+   for (int ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < KBC / NG; ++j) acc += lreg[j] * xg[j];
+      const int rcur = r;
+      r += gridDim.y * RC;
+      if (ch + (int)gridDim.y < nchunk) {
+#pragma unroll
+         for (int j = 0; j < KBC / NG; ++j) lreg[j] = (r < m && g * (KBC / NG) + j < kb) ? Lg[(size_t)j * ldl + r] : 0.0;
+      }
+      if (NG > 1) {
+         __syncthreads();
+         red[threadIdx.x] = acc;
+         __syncthreads();
+         if (g == 0) {
+#pragma unroll
+            for (int q = 1; q < NG; ++q) acc += red[q * RC + rl];
+         }
+      }
+      if (g == 0 && rcur < m) xw[rcur] -= acc;
+   }
 }
 
+// XY: the solved blocks (k_fwd_step)
 __global__ void __launch_bounds__(256) k_fwd_store(const FrontDev* __restrict__ fr, const int64_t* __restrict__ xw_off,
                                                    const double* __restrict__ XW, double* x, int slot0, int posdef_scale, int kind) {
    const int s = slot0 + blockIdx.x;
@@ -223,95 +284,82 @@ __global__ void __launch_bounds__(256) k_bwd_gather(const FrontDev* __restrict__
    }
 }
 
-// partial dot products of the rows below block `step` with the block's columns:
-// PART[front][chunk][j] = sum_{r in chunk} L(r, k0+j) xw(r)
-__global__ void __launch_bounds__(256) k_bwd_dots(const FrontDev* __restrict__ fr, const int* __restrict__ list,
-                                                  const int64_t* __restrict__ xw_off, const double* __restrict__ XW,
-                                                  const int64_t* __restrict__ part_off, double* PART, int step, int kind) {
+// Backward step for column block `step`: PART[front][chunk][j] = sum_{r in chunk} L(r, k0+j) xw(r) by every CTA
+// (one warp per group of KBC / 8 columns, lanes down the rows), then the last CTA to arrive computes
+// x(block) = L(block,block)^{-T} (xw(block) - sum of the partials, in chunk order).
+template <int KBC>
+__global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
+                                                  const int64_t* __restrict__ xw_off, double* XW,
+                                                  const int64_t* __restrict__ part_off, double* PART, int* ticket, int step, int kind) {
+   constexpr int RD = SE / KBC, CW = KBC / 8, RL = RD / 32, SLD = KBC + 1;
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
    if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const int ne = f.nelim, k0 = step * KB;
    if (k0 >= ne) return;
-   const int kb = min(KB, ne - k0);
-   const int r0 = k0 + kb + blockIdx.y * RD;
-   if (r0 >= f.m) return;
-   const int r1 = min(f.m, r0 + RD);
-   const double* xw = XW + xw_off[s];
-   double* part = PART + part_off[s] + (size_t)blockIdx.y * KB;
-   __shared__ double xs[RD];
-   for (int i = threadIdx.x; i < RD; i += 256) xs[i] = (r0 + i < r1) ? xw[r0 + i] : 0.0;
-   __syncthreads();
-   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-   const size_t ldl = f.ldl;
-   for (int j = wid; j < kb; j += 8) {
-      const double* __restrict__ col = f.L + (size_t)(k0 + j) * ldl + r0;
-      double v[RD / 32];
-#pragma unroll
-      for (int u = 0; u < RD / 32; ++u) v[u] = (r0 + lane + 32 * u < r1) ? col[lane + 32 * u] : 0.0;
-      double acc = 0.0;
-#pragma unroll
-      for (int u = 0; u < RD / 32; ++u) acc += v[u] * xs[lane + 32 * u];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      if (lane == 0) part[j] = acc;
-   }
-}
-
-// x(block) = L(block,block)^{-T} (xw(block) - sum of partial dots); one CTA per front
-__global__ void __launch_bounds__(256) k_bwd_tri(const FrontDev* __restrict__ fr, const int* __restrict__ list,
-                                                 const int64_t* __restrict__ xw_off, double* XW,
-                                                 const int64_t* __restrict__ part_off, const double* __restrict__ PART, int step, int kind) {
-   const int s = list[blockIdx.x];
-   const FrontDev& f = fr[s];
-   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
-   const int ne = f.nelim, k0 = step * KB;
-   if (k0 >= ne) return;
-   const int kb = min(KB, ne - k0);
+   const int kb = min(KB, ne - k0), m = f.m;
+   const int nchunk = (m - (k0 + kb) + RD - 1) / RD;
+   if ((int)blockIdx.y >= max(nchunk, 1)) return;
+   extern __shared__ double sm[];
+   double* S = sm;                    // KBC x SLD
+   double* xs = sm + KBC * SLD;       // max(KBC, RD)
+   double* dots = xs + (KBC > RD ? KBC : RD);   // 32
+   __shared__ int is_last;
    double* xw = XW + xw_off[s];
-   const double* part = PART + part_off[s];
-   const int nchunk = (f.m - (k0 + kb) + RD - 1) / RD;
+   double* part = PART + part_off[s];
    const size_t ldl = f.ldl;
-   const double* __restrict__ L = f.L;
-   __shared__ double ys[KB];
-   for (int i = threadIdx.x; i < kb; i += 256) {
-      double v = xw[k0 + i];
-      for (int c = 0; c < nchunk; ++c) v -= part[(size_t)c * KB + i];
-      ys[i] = v;
-   }
-   __syncthreads();
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-   const int nsb = (kb + 31) / 32;
-   for (int sbi = nsb - 1; sbi >= 0; --sbi) {
-      const int s0 = sbi * 32, sb = min(32, kb - s0);
-      // subtract the already solved rows of this KB block: columns s0..s0+sb, rows s0+sb..kb
-      __shared__ double dots[32];
-      for (int j = wid; j < sb; j += 8) {
-         const double* col = L + (size_t)(k0 + s0 + j) * ldl + k0;
-         double acc = 0.0;
-         for (int r = s0 + sb + lane; r < kb; r += 32) acc += col[r] * ys[r];
+   if (nchunk > 0) {
+      const int nctas = min((int)gridDim.y, nchunk);      // CTA y takes chunks y, y + gridDim.y, ...
+      for (int ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
+         const int r0 = k0 + kb + ch * RD, r1 = min(m, r0 + RD);
+         double v[CW][RL];
 #pragma unroll
-         for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-         if (lane == 0) dots[j] = acc;
-      }
-      __syncthreads();
-      if (threadIdx.x < 32) {
-         // lane i holds column i of the sub-triangle (rows below the diagonal) = row i of L^T
-         double lcol[32];
-         const double* Lb = L + (size_t)(k0 + s0 + lane) * ldl + k0 + s0;
+         for (int c = 0; c < CW; ++c) {
+            const int j = wid * CW + c;
+            const double* __restrict__ col = f.L + (size_t)(k0 + j) * ldl + r0;
 #pragma unroll
-         for (int j = 0; j < 32; ++j) lcol[j] = (j > lane && j < sb && lane < sb) ? Lb[j] : 0.0;
-         double v = lane < sb ? ys[s0 + lane] - dots[lane] : 0.0;
-#pragma unroll
-         for (int j = 31; j >= 0; --j) {
-            double xj = __shfl_sync(0xffffffffu, v, j);
-            v -= lcol[j] * xj;
+            for (int u = 0; u < RL; ++u) v[c][u] = (j < kb && r0 + lane + 32 * u < r1) ? col[lane + 32 * u] : 0.0;
          }
-         if (lane < sb) ys[s0 + lane] = v;
+         __syncthreads();
+         for (int i = threadIdx.x; i < RD; i += 256) xs[i] = (r0 + i < r1) ? xw[r0 + i] : 0.0;
+         __syncthreads();
+         double* pc = part + (size_t)ch * KB;
+#pragma unroll
+         for (int c = 0; c < CW; ++c) {
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < RL; ++u) acc += v[c][u] * xs[lane + 32 * u];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0 && wid * CW + c < kb) pc[wid * CW + c] = acc;
+         }
       }
-      __syncthreads();
+      if (nctas > 1) {
+         __threadfence();
+         __syncthreads();
+         if (threadIdx.x == 0) {
+            const int t = atomicAdd(ticket + s, 1);
+            is_last = (t == nctas - 1);
+            if (is_last) ticket[s] = 0;       // ready for the next step
+         }
+         __syncthreads();
+         if (!is_last) return;
+         __threadfence();
+      } else {
+         __syncthreads();
+      }
    }
-   for (int i = threadIdx.x; i < kb; i += 256) xw[k0 + i] = ys[i];
+   stage_triangle(S, SLD, f.L + (size_t)k0 * ldl + k0, ldl, kb);
+   for (int i = threadIdx.x; i < kb; i += 256) {
+      double vv = xw[k0 + i];
+      for (int c = 0; c < nchunk; ++c) vv -= __ldcg(part + (size_t)c * KB + i);
+      xs[i] = vv;
+   }
+   cp_async_wait<0>();
+   __syncthreads();
+   smem_solve_lower_t(S, SLD, kb, xs, dots);
+   for (int i = threadIdx.x; i < kb; i += 256) xw[k0 + i] = xs[i];
 }
 
 __global__ void __launch_bounds__(256) k_bwd_store(const FrontDev* __restrict__ fr, const int64_t* __restrict__ xw_off,
