@@ -425,6 +425,7 @@ __global__ void k_stats(const FrontDev* fr, int nslots, int* counters) {
 #include "solve_kernels.cuh"
 
 static inline size_t step_smem_fwd(int kbc) { return (size_t)(kbc * (kbc + 1) + kbc + 256) * 8; }
+static inline size_t chain_smem() { return (size_t)(KB * (KB + 1) + KB + 2 * KB + 32) * 8; }
 static inline int step_grid_y(int rows, int rc, int slots, int fronts) {
    return std::max(1, std::min((rows + rc - 1) / rc, slots / std::max(1, fronts)));
 }
@@ -695,6 +696,18 @@ class Numeric {
    static constexpr size_t UPDMAP_CAP = (size_t)3 << 20;   // ints
    int64_t* d_xw_off = nullptr;
    int64_t* d_part_off = nullptr;
+   // chain kernels (solve_kernels.cuh): role tables per level and direction, block flags, ticket counters
+   int2* d_roles = nullptr;
+   size_t roles_cap = 0;
+   int* d_flag_off = nullptr;
+   int* d_flags = nullptr;
+   size_t flags_cap = 0;
+   unsigned long long* d_chain_counter = nullptr;   // [2 * nlevels]
+   int* d_chain_err = nullptr;
+   int solve_epoch = 0;
+   std::vector<int64_t> roles_fwd_off, roles_bwd_off;
+   std::vector<int> roles_fwd_n, roles_bwd_n;
+   bool use_chain = !(getenv("B200LDLT_CHAIN") && atoi(getenv("B200LDLT_CHAIN")) == 0);
    int* d_ticket = nullptr;         // per slot: arrival counter of the backward step's CTAs (left at zero by the last one)
    int* d_slist = nullptr;
    std::vector<int> slist, lvl_steps, lvl_maxm, lvl_maxne;
@@ -735,7 +748,7 @@ class Numeric {
       cudaSetDevice(P->device);
       fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release(); bar.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
-      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
+      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_flag_off); cudaFree(d_flags); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
       if (pin_updmap) cudaFreeHost(pin_updmap);
@@ -791,6 +804,8 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(NB)));
    CU(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes(PB)));
    CU(cudaFuncSetAttribute(k_fwd_step<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd(128)));
+   CU(cudaFuncSetAttribute(k_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem()));
+   CU(cudaFuncSetAttribute(k_bwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem()));
    CU(cudaFuncSetAttribute(k_bwd_step<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    const int nn = std::max(P->nnodes, 1);
    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -827,6 +842,10 @@ int Numeric::init() {
    CU(cudaMalloc(&d_xw_off, sizeof(int64_t) * (nn + 1)));
    CU(cudaMalloc(&d_part_off, sizeof(int64_t) * (nn + 1)));
    CU(cudaMalloc(&d_ticket, sizeof(int) * (nn + 1)));
+   CU(cudaMalloc(&d_flag_off, sizeof(int) * (nn + 1)));
+   CU(cudaMalloc(&d_chain_counter, sizeof(unsigned long long) * 2 * (P->nlevels + 1)));
+   CU(cudaMalloc(&d_chain_err, sizeof(int)));
+   CU(cudaMemset(d_chain_err, 0, sizeof(int)));
    CU(cudaMemset(d_ticket, 0, sizeof(int) * (nn + 1)));
    CU(cudaMalloc(&d_slist, sizeof(int) * nn));
    CU(cudaMalloc(&d_val, sizeof(double) * std::max<int64_t>(P->sym->nz, 1)));
@@ -1380,6 +1399,51 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          }
       }
       if (nn > 0) CU(cudaMemcpy(d_slist, slist.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
+      // chain kernels for the levels that hold fronts of more than KB eliminated columns
+      {
+         std::vector<int> foff(nn + 1, 0);
+         for (int s = 0; s < nn; ++s) foff[s + 1] = foff[s] + ((hfr[s].state == 2 ? hfr[s].nelim : 0) + KB - 1) / KB;
+         std::vector<int2> roles;
+         roles_fwd_off.assign(P->nlevels, 0); roles_bwd_off.assign(P->nlevels, 0);
+         roles_fwd_n.assign(P->nlevels, 0); roles_bwd_n.assign(P->nlevels, 0);
+         for (int l = 0; l < P->nlevels; ++l) {
+            if (!use_chain || lvl_maxne[l] <= KB) continue;
+            const int a0 = P->lvl_ptr[l], a1 = P->lvl_ptr[l + 1];
+            auto ne_of = [&](int s) { return hfr[s].state == 2 ? hfr[s].nelim : 0; };
+            int maxr = 0;
+            for (int s = a0; s < a1; ++s)
+               if (ne_of(s) > 0) maxr = std::max(maxr, (ne_of(s) + KB - 1) / KB + (hfr[s].m - ne_of(s) + CH - 1) / CH);
+            roles_fwd_off[l] = (int64_t)roles.size();
+            for (int i = 0; i < maxr; ++i)
+               for (int q = a0; q < a1; ++q) {
+                  const int s = slist[q], ne = ne_of(s);
+                  if (ne > 0 && i < (ne + KB - 1) / KB + (hfr[s].m - ne + CH - 1) / CH) roles.push_back(make_int2(s, i));
+               }
+            roles_fwd_n[l] = (int)(roles.size() - roles_fwd_off[l]);
+            roles_bwd_off[l] = (int64_t)roles.size();
+            for (int i = 0; i < maxr; ++i)
+               for (int q = a0; q < a1; ++q) {
+                  const int s = slist[q], nb = (ne_of(s) + KB - 1) / KB;
+                  if (i < nb) roles.push_back(make_int2(s, nb - 1 - i));
+               }
+            roles_bwd_n[l] = (int)(roles.size() - roles_bwd_off[l]);
+         }
+         if (roles_cap < roles.size() + 1) {
+            cudaFree(d_roles); d_roles = nullptr;
+            CU(cudaMalloc(&d_roles, sizeof(int2) * (roles.size() + 1)));
+            roles_cap = roles.size() + 1;
+         }
+         if (flags_cap < (size_t)foff[nn] + 1) {
+            cudaFree(d_flags); d_flags = nullptr;
+            CU(cudaMalloc(&d_flags, sizeof(int) * ((size_t)foff[nn] + 1)));
+            flags_cap = (size_t)foff[nn] + 1;
+         }
+         if (!roles.empty()) CU(cudaMemcpy(d_roles, roles.data(), sizeof(int2) * roles.size(), cudaMemcpyHostToDevice));
+         CU(cudaMemcpy(d_flag_off, foff.data(), sizeof(int) * (nn + 1), cudaMemcpyHostToDevice));
+         CU(cudaMemset(d_flags, 0, sizeof(int) * flags_cap));
+         CU(cudaMemset(d_chain_counter, 0, sizeof(unsigned long long) * 2 * (P->nlevels + 1)));
+         solve_epoch = 0;
+      }
       // child delay offsets must describe the final state for the solve
       if (!child_doff.empty())
          CU(cudaMemcpy(d_child_doff, child_doff.data(), sizeof(int) * child_doff.size(), cudaMemcpyHostToDevice));
@@ -1423,11 +1487,17 @@ int Numeric::solve_prepare() {
 
 // forward sweep over the fronts of `kind` (-1: all)
 void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
+   const int epoch = ++solve_epoch;
    double* d_xa = d_xw + xw_cap / 2;
    for (int l = 0; l < P->nlevels; ++l) {
       const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
       k_fwd_gather<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xa, d_xp, s0, kind);
       ++nlaunch;
+      if (roles_fwd_n[l] > 0) {
+         k_fwd_chain<<<roles_fwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_fwd_off[l], roles_fwd_n[l], d_chain_counter + 2 * l, d_xw_off,
+                                                               d_xw, d_xa, d_flag_off, d_flags, epoch, kind, d_chain_err);
+         ++nlaunch;
+      } else
       for (int sp = 0; sp < lvl_steps[l]; ++sp) {
          const int na = lvl_nact[l][sp];
          if (na == 0) break;
@@ -1445,10 +1515,16 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
 }
 
 void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
+   const int epoch = ++solve_epoch;
    for (int l = P->nlevels - 1; l >= 0; --l) {
       const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
       k_bwd_gather<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_rlist, d_xw_off, d_xw, d_xp, s0, diag ? 1 : 0, posdef ? 1 : 0, kind);
       ++nlaunch;
+      if (roles_bwd_n[l] > 0) {
+         k_bwd_chain<<<roles_bwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_bwd_off[l], roles_bwd_n[l], d_chain_counter + 2 * l + 1, d_xw_off,
+                                                               d_xw, d_flag_off, d_flags, epoch, kind, d_chain_err);
+         ++nlaunch;
+      } else
       for (int sp = lvl_steps[l] - 1; sp >= 0; --sp) {
          const int na = lvl_nact[l][sp];
          if (na == 0) continue;
@@ -1494,10 +1570,16 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
       if (!on_device) CU(cudaMemcpyAsync(xj, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
    }
    CU(cudaEventRecord(ev1, st));
+   pin_i[pin_i_cap - 1] = 0;
+   CU(cudaMemcpyAsync(pin_i + pin_i_cap - 1, d_chain_err, sizeof(int), cudaMemcpyDeviceToHost, st));
    CU(cudaStreamSynchronize(st));
    {
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) { cuda_err = (int)e; return SSIDS_ERROR_CUDA_UNKNOWN; }
+   }
+   if (pin_i[pin_i_cap - 1] != 0) {   // a chain kernel gave up waiting for a block (solve_kernels.cuh): never expected
+      CU(cudaMemset(d_chain_err, 0, sizeof(int)));
+      return SSIDS_ERROR_CUDA_UNKNOWN;
    }
    float ms = 0;
    cudaEventElapsedTime(&ms, ev0, ev1);

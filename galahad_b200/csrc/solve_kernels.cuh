@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(256) k_fwd_gather(const FrontDev* __restrict__
 
 // stage the lower triangle of L(k0:k0+kb, k0:k0+kb) in shared memory (column-major, leading dimension sld)
 __device__ __forceinline__ void stage_triangle(double* S, int sld, const double* __restrict__ Lb, size_t ldl, int kb) {
-   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-   for (int c = wid; c < kb; c += 8)
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+   for (int c = wid; c < kb; c += nw)
       for (int r = (c & ~31) + lane; r < kb; r += 32) cp_async8(S + c * sld + r, Lb + (size_t)c * ldl + r, true);
    cp_async_commit();
 }
@@ -130,7 +130,7 @@ __device__ __forceinline__ void smem_solve_lower_t(const double* S, int sld, int
    for (int sbi = nsb - 1; sbi >= 0; --sbi) {
       const int s0 = sbi * 32, sb = min(32, kb - s0);
       // the rows of the block already solved: columns s0..s0+sb, rows s0+sb..kb (contiguous down a column)
-      for (int j = wid; j < sb; j += 8) {
+      for (int j = wid; j < sb; j += (int)(blockDim.x >> 5)) {
          const double* col = S + (s0 + j) * sld;
          double acc = 0.0;
          for (int r = s0 + sb + lane; r < kb; r += 32) acc += col[r] * xs[r];
@@ -220,6 +220,178 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 2 : 1) k_fwd_step(const Front
       }
       if (g == 0 && rcur < m) xw[rcur] -= acc;
    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Chain kernels: ONE launch per level and direction for levels that hold fronts of more than KB eliminated
+// columns.  A front's work is cut into roles, dealt to CTAs through a ticket counter in an order in which a
+// role only ever waits for roles with smaller tickets (so a waiting CTA can never keep its producer off the
+// GPU):
+//   forward : role c < nb owns block row c of the front: it streams L(c, b) for b < c as the solved blocks y_b
+//             are published (one flag per block, holding the epoch of the sweep), then solves its own triangle
+//             from shared memory and publishes y_c; roles >= nb take 128 rows each of the part below the pivots;
+//   backward: role c owns block column c: dot products with the rows below the pivots (known), then with the
+//             blocks b > c as their solutions appear, last first; then the transposed triangle.
+// The entries of L needed next are always requested BEFORE the flag they depend on is polled, so that the chain
+// between two consecutive blocks is: flag -> 64 FMAs per thread from registers -> reduction -> triangle.
+// A lost producer cannot hang the GPU: a poll gives up after ~2 s and raises *err.
+constexpr int CH = 128;      // rows of a role = block width
+
+__device__ __forceinline__ void chain_wait(const int* flag, int epoch, int* err) {
+   if ((threadIdx.x & 31) == 0 && *((volatile const int*)flag) != epoch && *((volatile int*)err) == 0) {
+      const long long t0 = clock64();
+      while (*((volatile const int*)flag) != epoch) {
+         if (clock64() - t0 > 2000000000LL) { *err = 1; break; }
+      }
+   }
+   __syncwarp();
+   __threadfence();
+}
+__device__ __forceinline__ void chain_publish(int* flag, int epoch) {
+   __threadfence();
+   __syncthreads();
+   if (threadIdx.x == 0) *((volatile int*)flag) = epoch;
+}
+
+__global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
+                                                      unsigned long long* counter, const int64_t* __restrict__ xw_off, double* XW,
+                                                      double* XY, const int* __restrict__ flag_off, int* flags, int epoch, int kind, int* err) {
+   constexpr int SLD = KB + 1;
+   __shared__ int2 role;
+   if (threadIdx.x == 0) role = roles[(int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles)];
+   __syncthreads();
+   const int s = role.x, idx = role.y;
+   const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
+   const int ne = f.nelim, m = f.m, nb = (ne + KB - 1) / KB;
+   const bool owner = idx < nb;
+   const int rbase = owner ? idx * KB : ne + (idx - nb) * CH;
+   const int rend = min(owner ? ne : m, rbase + CH);
+   const int nblk = owner ? idx : nb;
+   extern __shared__ double sm[];
+   double* S = sm;                    // KB x SLD
+   double* xs = sm + KB * SLD;        // KB
+   double* red = xs + KB;             // 2 x CH
+   double* xw = XW + xw_off[s];
+   double* xy = XY + xw_off[s];
+   int* fl = flags + flag_off[s];
+   const size_t ldl = f.ldl;
+   if (owner) stage_triangle(S, SLD, f.L + (size_t)rbase * ldl + rbase, ldl, rend - rbase);
+   const int i = threadIdx.x & (CH - 1), g = threadIdx.x >> 7;      // row of the role, column quarter pair
+   const bool rv = rbase + i < rend;
+   const double* __restrict__ Lr = f.L + rbase + i;
+   double la[32], lb[32], acc = 0.0;
+   // half h of block b: columns KB b + 64 h + 32 g + j
+   auto load_half = [&](double (&buf)[32], int b, int h) {
+      const int c0 = KB * b + 64 * h + 32 * g;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) buf[j] = (rv && c0 + j < ne) ? Lr[(size_t)(c0 + j) * ldl] : 0.0;
+   };
+   auto use_half = [&](const double (&buf)[32], int b, int h) {
+      const int c0 = KB * b + 64 * h + 32 * g;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc += buf[j] * (c0 + j < ne ? __ldcg(xy + c0 + j) : 0.0);
+   };
+   if (nblk > 0) load_half(la, 0, 0);
+   for (int b = 0; b < nblk; ++b) {
+      load_half(lb, b, 1);
+      chain_wait(fl + b, epoch, err);
+      use_half(la, b, 0);
+      if (b + 1 < nblk) load_half(la, b + 1, 0);
+      use_half(lb, b, 1);
+   }
+   red[g * CH + i] = acc;
+   __syncthreads();
+   if (!owner) {
+      if (g == 0 && rv) xw[rbase + i] -= red[i] + red[CH + i];
+      return;
+   }
+   const int kb = rend - rbase;
+   if (g == 0) xs[i] = rv ? xw[rbase + i] - (red[i] + red[CH + i]) : 0.0;
+   cp_async_wait<0>();
+   __syncthreads();
+   smem_solve_lower(S, SLD, kb, xs);
+   if (threadIdx.x < kb) xy[rbase + threadIdx.x] = xs[threadIdx.x];
+   chain_publish(fl + idx, epoch);
+}
+
+__global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
+                                                      unsigned long long* counter, const int64_t* __restrict__ xw_off, double* XW,
+                                                      const int* __restrict__ flag_off, int* flags, int epoch, int kind, int* err) {
+   constexpr int SLD = KB + 1;
+   __shared__ int2 role;
+   if (threadIdx.x == 0) role = roles[(int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles)];
+   __syncthreads();
+   const int s = role.x, c = role.y;
+   const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
+   const int ne = f.nelim, m = f.m, nb = (ne + KB - 1) / KB;
+   const int cbase = c * KB, kb = min(KB, ne - cbase);
+   const int ntail = (m - ne + CH - 1) / CH;
+   extern __shared__ double sm[];
+   double* S = sm;                    // KB x SLD
+   double* xs = sm + KB * SLD;        // KB
+   double* dots = xs + KB;            // KB + 32
+   double* xw = XW + xw_off[s];
+   int* fl = flags + flag_off[s];
+   const size_t ldl = f.ldl;
+   stage_triangle(S, SLD, f.L + (size_t)cbase * ldl + cbase, ldl, kb);
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   // warp wid takes columns cbase + 16 wid + q; a half chunk is 64 rows: two loads per lane and column
+   const double* __restrict__ Lc = f.L + (size_t)(cbase + 16 * wid) * ldl + lane;
+   double va[16][2], vb[16][2], acc[16];
+#pragma unroll
+   for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+   // half chunk hh: chunks 0..ntail-1 are the rows below the pivots, then the blocks nb-1, nb-2, ..., c+1
+   auto rows_of = [&](int hh, int& r0, int& r1, int& b) {
+      const int q = hh >> 1;
+      int rb, rl;
+      if (q < ntail) { rb = ne + CH * q; rl = m; b = -1; }
+      else { b = nb - 1 - (q - ntail); rb = KB * b; rl = ne; }
+      r0 = rb + 64 * (hh & 1);
+      r1 = min(rl, rb + CH);
+   };
+   auto load_half = [&](double (&buf)[16][2], int hh) {
+      int r0, r1, b;
+      rows_of(hh, r0, r1, b);
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+#pragma unroll
+         for (int u = 0; u < 2; ++u)
+            buf[q][u] = (16 * wid + q < kb && r0 + lane + 32 * u < r1) ? Lc[(size_t)q * ldl + r0 + 32 * u] : 0.0;
+   };
+   auto use_half = [&](const double (&buf)[16][2], int hh) {
+      int r0, r1, b;
+      rows_of(hh, r0, r1, b);
+      if (b >= 0 && (hh & 1) == 0) chain_wait(fl + b, epoch, err);
+      double xv[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) xv[u] = (r0 + lane + 32 * u < r1) ? __ldcg(xw + r0 + lane + 32 * u) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[q] += buf[q][0] * xv[0] + buf[q][1] * xv[1];
+   };
+   const int H = 2 * (ntail + nb - 1 - c);
+   if (H > 0) load_half(va, 0);
+   for (int hh = 0; hh < H; hh += 2) {
+      load_half(vb, hh + 1);
+      use_half(va, hh);
+      if (hh + 2 < H) load_half(va, hh + 2);
+      use_half(vb, hh + 1);
+   }
+#pragma unroll
+   for (int q = 0; q < 16; ++q) {
+      double a = acc[q];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (lane == 0) dots[32 + 16 * wid + q] = a;
+   }
+   __syncthreads();
+   if (threadIdx.x < KB) xs[threadIdx.x] = threadIdx.x < kb ? xw[cbase + threadIdx.x] - dots[32 + threadIdx.x] : 0.0;
+   cp_async_wait<0>();
+   __syncthreads();
+   smem_solve_lower_t(S, SLD, kb, xs, dots);
+   if (threadIdx.x < kb) xw[cbase + threadIdx.x] = xs[threadIdx.x];
+   chain_publish(fl + c, epoch);
 }
 
 // XY: the solved blocks (k_fwd_step)
