@@ -707,6 +707,7 @@ class Numeric {
    int solve_epoch = 0;
    std::vector<int64_t> roles_fwd_off, roles_bwd_off;
    std::vector<int> roles_fwd_n, roles_bwd_n;
+   bool use_fused = !(getenv("B200LDLT_FUSED") && atoi(getenv("B200LDLT_FUSED")) == 0);
    bool use_chain = !(getenv("B200LDLT_CHAIN") && atoi(getenv("B200LDLT_CHAIN")) == 0);
    int* d_ticket = nullptr;         // per slot: arrival counter of the backward step's CTAs (left at zero by the last one)
    int* d_slist = nullptr;
@@ -803,10 +804,12 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(2 * NB)));
    CU(cudaFuncSetAttribute(k_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(NB)));
    CU(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes(PB)));
-   CU(cudaFuncSetAttribute(k_fwd_step<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd(128)));
+   CU(cudaFuncSetAttribute(k_fwd_step<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd(128)));
+   CU(cudaFuncSetAttribute(k_fwd_step<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd(128)));
    CU(cudaFuncSetAttribute(k_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem()));
    CU(cudaFuncSetAttribute(k_bwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem()));
-   CU(cudaFuncSetAttribute(k_bwd_step<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
+   CU(cudaFuncSetAttribute(k_bwd_step<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
+   CU(cudaFuncSetAttribute(k_bwd_step<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    const int nn = std::max(P->nnodes, 1);
    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
    for (int g = 0; g < NAUX; ++g) {
@@ -1375,6 +1378,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       slist.assign(nn, 0);
       lvl_steps.assign(P->nlevels, 0);
       lvl_maxne.assign(P->nlevels, 0);
+      lvl_maxm.assign(P->nlevels, 0);
       lvl_nact.assign(P->nlevels, std::vector<int>());
       lvl_actm.assign(P->nlevels, std::vector<int>());
       for (int l = 0; l < P->nlevels; ++l) {
@@ -1389,6 +1393,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          const int steps = a1 > a0 ? (ne_of(slist[a0]) + KB - 1) / KB : 0;
          lvl_steps[l] = steps;
          lvl_maxne[l] = a1 > a0 ? ne_of(slist[a0]) : 0;
+         for (int s = a0; s < a1; ++s) if (hfr[s].state == 2) lvl_maxm[l] = std::max(lvl_maxm[l], hfr[s].m);
          lvl_nact[l].assign(steps, 0);
          lvl_actm[l].assign(steps, 0);
          for (int st2 = 0; st2 < steps; ++st2) {
@@ -1485,13 +1490,39 @@ int Numeric::solve_prepare() {
    return 0;
 }
 
+// launch helpers: instantiation by the widest block of the launch
+template <bool FUSED>
+static void launch_fwd_step(int kbmax, dim3 grid, cudaStream_t st, const FrontDev* fr, const int* list, const int64_t* xw_off, double* xw,
+                            double* xy, int sp, int kind, const GatherArgs& ga) {
+   if (kbmax <= 32) k_fwd_step<32, FUSED><<<grid, 256, step_smem_fwd(32), st>>>(fr, list, xw_off, xw, xy, sp, kind, ga);
+   else if (kbmax <= 64) k_fwd_step<64, FUSED><<<grid, 256, step_smem_fwd(64), st>>>(fr, list, xw_off, xw, xy, sp, kind, ga);
+   else k_fwd_step<128, FUSED><<<grid, 256, step_smem_fwd(128), st>>>(fr, list, xw_off, xw, xy, sp, kind, ga);
+}
+template <bool FUSED>
+static void launch_bwd_step(int kbmax, dim3 grid, cudaStream_t st, const FrontDev* fr, const int* list, const int64_t* xw_off, double* xw,
+                            const int64_t* part_off, double* part, int* ticket, int sp, int kind, const GatherArgs& ga) {
+   if (kbmax <= 32) k_bwd_step<32, FUSED><<<grid, 256, step_smem_bwd(32), st>>>(fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
+   else if (kbmax <= 64) k_bwd_step<64, FUSED><<<grid, 256, step_smem_bwd(64), st>>>(fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
+   else k_bwd_step<128, FUSED><<<grid, 256, step_smem_bwd(128), st>>>(fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
+}
+static inline int step_slots(int kbmax, bool bwd) { return kbmax <= 64 ? (bwd ? 3 : 2) * 148 : 148; }
+
 // forward sweep over the fronts of `kind` (-1: all)
 void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
    const int epoch = ++solve_epoch;
    double* d_xa = d_xw + xw_cap / 2;
+   GatherArgs ga{P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, P->d_rlist, d_xp, posdef ? 1 : 0, 0};
    for (int l = 0; l < P->nlevels; ++l) {
       const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
-      k_fwd_gather<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xa, d_xp, s0, kind);
+      if (ns == 0) continue;
+      const int kb0 = std::min(KB, lvl_maxne[l]), rows0 = lvl_steps[l] > 0 ? std::max(0, lvl_actm[l][0] - 1) : 0;
+      if (use_fused && lvl_steps[l] == 1 && step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, false), ns) == 1) {
+         // every front of the level is one block and one CTA: gather, solve, update and store in one launch
+         launch_fwd_step<true>(kb0, dim3(ns, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, 0, kind, ga);
+         ++nlaunch;
+         continue;
+      }
+      k_fwd_gather<<<ns, lvl_maxm[l] > 1024 ? 1024 : 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xa, d_xp, s0, kind);
       ++nlaunch;
       if (roles_fwd_n[l] > 0) {
          k_fwd_chain<<<roles_fwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_fwd_off[l], roles_fwd_n[l], d_chain_counter + 2 * l, d_xw_off,
@@ -1504,9 +1535,8 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
          const int kbmax = std::min(KB, lvl_maxne[l] - sp * KB);
          const int rows = std::max(0, lvl_actm[l][sp] - sp * KB - 1);
          // one wave of CTAs: a front's row chunks are dealt to at most `slots / fronts` CTAs
-         if (kbmax <= 32) k_fwd_step<32><<<dim3(na, step_grid_y(rows, SE / 32, 2 * 148, na)), 256, step_smem_fwd(32), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, sp, kind);
-         else if (kbmax <= 64) k_fwd_step<64><<<dim3(na, step_grid_y(rows, SE / 64, 2 * 148, na)), 256, step_smem_fwd(64), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, sp, kind);
-         else k_fwd_step<128><<<dim3(na, step_grid_y(rows, SE / 128, 148, na)), 256, step_smem_fwd(128), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, sp, kind);
+         const int rc = SE / (kbmax <= 32 ? 32 : kbmax <= 64 ? 64 : 128);
+         launch_fwd_step<false>(kbmax, dim3(na, step_grid_y(rows, rc, step_slots(kbmax, false), na)), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, sp, kind, ga);
          ++nlaunch;
       }
       k_fwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xa, d_xp, s0, posdef ? 1 : 0, kind);
@@ -1516,10 +1546,21 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
 
 void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
    const int epoch = ++solve_epoch;
+   GatherArgs ga{P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, P->d_rlist, d_xp, posdef ? 1 : 0, diag ? 1 : 0};
    for (int l = P->nlevels - 1; l >= 0; --l) {
       const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
-      k_bwd_gather<<<ns, 256, 0, st>>>(d_fr, P->d_ss, P->d_rlist, d_xw_off, d_xw, d_xp, s0, diag ? 1 : 0, posdef ? 1 : 0, kind);
-      ++nlaunch;
+      if (ns == 0) continue;
+      const int kb0 = std::min(KB, lvl_maxne[l]), rows0 = lvl_steps[l] > 0 ? std::max(0, lvl_actm[l][0] - 1) : 0;
+      if (use_fused && lvl_steps[l] == 1 && step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, true), ns) == 1) {
+         launch_bwd_step<true>(kb0, dim3(lvl_nact[l][0], 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga);
+         ++nlaunch;
+         continue;
+      }
+      {
+         const int gy = std::max(1, std::min((lvl_maxm[l] + 255) / 256, 592 / ns));
+         k_bwd_gather<<<dim3(ns, gy), 256, 0, st>>>(d_fr, P->d_ss, P->d_rlist, d_xw_off, d_xw, d_xp, s0, diag ? 1 : 0, posdef ? 1 : 0, kind);
+         ++nlaunch;
+      }
       if (roles_bwd_n[l] > 0) {
          k_bwd_chain<<<roles_bwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_bwd_off[l], roles_bwd_n[l], d_chain_counter + 2 * l + 1, d_xw_off,
                                                                d_xw, d_flag_off, d_flags, epoch, kind, d_chain_err);
@@ -1530,9 +1571,9 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
          if (na == 0) continue;
          const int kbmax = std::min(KB, lvl_maxne[l] - sp * KB);
          const int rows = std::max(0, lvl_actm[l][sp] - sp * KB - 1);
-         if (kbmax <= 32) k_bwd_step<32><<<dim3(na, step_grid_y(rows, SE / 32, 3 * 148, na)), 256, step_smem_bwd(32), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, sp, kind);
-         else if (kbmax <= 64) k_bwd_step<64><<<dim3(na, step_grid_y(rows, SE / 64, 3 * 148, na)), 256, step_smem_bwd(64), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, sp, kind);
-         else k_bwd_step<128><<<dim3(na, step_grid_y(rows, SE / 128, 148, na)), 256, step_smem_bwd(128), st>>>(d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, sp, kind);
+         const int rd = SE / (kbmax <= 32 ? 32 : kbmax <= 64 ? 64 : 128);
+         launch_bwd_step<false>(kbmax, dim3(na, step_grid_y(rows, rd, step_slots(kbmax, true), na)), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part,
+                                d_ticket, sp, kind, ga);
          ++nlaunch;
       }
       k_bwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xw, d_xp, s0, kind);

@@ -45,13 +45,11 @@ __global__ void k_merge_masked(double* __restrict__ xp, const double* __restrict
 }
 
 // xw = [b(pivot rows); 0] + sum over children (in child order) of their update vectors
-__global__ void __launch_bounds__(256) k_fwd_gather(const FrontDev* __restrict__ fr, const SlotStatic* __restrict__ ss,
-                                                    const int* __restrict__ child_idx, const int* __restrict__ child_doff,
-                                                    const int* __restrict__ rel, const int64_t* __restrict__ xw_off,
-                                                    double* XW, double* XA, const double* __restrict__ x, int slot0, int kind) {
-   const int s = slot0 + blockIdx.x;
+__device__ __forceinline__ void fwd_gather_front(const FrontDev* __restrict__ fr, const SlotStatic* __restrict__ ss,
+                                                 const int* __restrict__ child_idx, const int* __restrict__ child_doff,
+                                                 const int* __restrict__ rel, const int64_t* __restrict__ xw_off,
+                                                 double* XW, double* XA, const double* __restrict__ x, int s) {
    const FrontDev& f = fr[s];
-   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const SlotStatic st = ss[s];
    double* xw = XW + xw_off[s];
    double* acc = XA + xw_off[s];   // indexed by the parent's ASSEMBLY order
@@ -81,6 +79,16 @@ __global__ void __launch_bounds__(256) k_fwd_gather(const FrontDev* __restrict__
       if (has_children) v += acc[r < f.n ? f.orig[r] : r];
       xw[r] = v;
    }
+}
+
+__global__ void __launch_bounds__(1024) k_fwd_gather(const FrontDev* __restrict__ fr, const SlotStatic* __restrict__ ss,
+                                                     const int* __restrict__ child_idx, const int* __restrict__ child_doff,
+                                                     const int* __restrict__ rel, const int64_t* __restrict__ xw_off,
+                                                     double* XW, double* XA, const double* __restrict__ x, int slot0, int kind) {
+   const int s = slot0 + blockIdx.x;
+   const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
+   fwd_gather_front(fr, ss, child_idx, child_doff, rel, xw_off, XW, XA, x, s);
 }
 
 // stage the lower triangle of L(k0:k0+kb, k0:k0+kb) in shared memory (column-major, leading dimension sld)
@@ -161,14 +169,21 @@ __device__ __forceinline__ void smem_solve_lower_t(const double* S, int sld, int
 // width of the launch; a CTA covers RC = SE / KBC rows below the block, NG = 256 / RC threads per row.
 // The solved block goes to XY (the front's slice of the gather accumulators, dead by now), never back into
 // xw: a CTA scheduled late must still find the unsolved right-hand side there.
-template <int KBC>
+// FUSED (levels whose fronts have one block and one CTA each): the CTA also gathers the children's update vectors
+// first and scatters the solved pivots into x afterwards, i.e. the whole level is this one launch.
+struct GatherArgs {
+   const SlotStatic* ss; const int* child_idx; const int* child_doff; const int* rel; const int* rlist;
+   double* x; int posdef_scale, do_diag;
+};
+template <int KBC, bool FUSED>
 __global__ void __launch_bounds__(256, KBC <= 64 ? 2 : 1) k_fwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
-                                                  const int64_t* __restrict__ xw_off, double* XW, double* XY, int step, int kind) {
+                                                  const int64_t* __restrict__ xw_off, double* XW, double* XY, int step, int kind, GatherArgs ga) {
    constexpr int RC = SE / KBC, NG = 256 / RC, SLD = KBC + 1;
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
    if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const int ne = f.nelim, k0 = step * KB;
+   if (FUSED && ne == 0) { fwd_gather_front(fr, ga.ss, ga.child_idx, ga.child_doff, ga.rel, xw_off, XW, XY, ga.x, s); return; }
    if (k0 >= ne) return;
    const int kb = min(KB, ne - k0), m = f.m;
    const int nchunk = (m - (k0 + kb) + RC - 1) / RC;      // chunks of RC rows below the block; CTA y takes y, y + gridDim.y, ...
@@ -188,11 +203,17 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 2 : 1) k_fwd_step(const Front
    int r = k0 + kb + blockIdx.y * RC + rl;
 #pragma unroll
    for (int j = 0; j < KBC / NG; ++j) lreg[j] = (r < m && g * (KBC / NG) + j < kb) ? Lg[(size_t)j * ldl + r] : 0.0;
+   if (FUSED) {      // the triangle and this thread's entries of L are on their way meanwhile
+      fwd_gather_front(fr, ga.ss, ga.child_idx, ga.child_doff, ga.rel, xw_off, XW, XY, ga.x, s);
+      __syncthreads();
+   }
    for (int i = threadIdx.x; i < KBC; i += 256) xs[i] = i < kb ? xw[k0 + i] : 0.0;
    cp_async_wait<0>();
    __syncthreads();
    smem_solve_lower(S, SLD, kb, xs);
-   if (blockIdx.y == 0) {
+   if (FUSED) {
+      for (int i = threadIdx.x; i < kb; i += 256) ga.x[f.perm[i]] = ga.posdef_scale ? xs[i] * sqrt(f.D[2 * i]) : xs[i];
+   } else if (blockIdx.y == 0) {
       double* xy = XY + xw_off[s];
       for (int i = threadIdx.x; i < kb; i += 256) xy[k0 + i] = xs[i];
    }
@@ -429,17 +450,10 @@ __global__ void k_solve_diag(const FrontDev* __restrict__ fr, double* x, int nsl
 }
 
 // backward: xw(r >= ne) = x(ancestors), xw(r < ne) = D^{-1} y (or sqrt scaling for posdef)
-__global__ void __launch_bounds__(256) k_bwd_gather(const FrontDev* __restrict__ fr, const SlotStatic* __restrict__ ss,
-                                                    const int* __restrict__ rlist, const int64_t* __restrict__ xw_off,
-                                                    double* XW, const double* __restrict__ x, int slot0, int do_diag,
-                                                    int posdef_scale, int kind) {
-   const int s = slot0 + blockIdx.x;
-   const FrontDev& f = fr[s];
-   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
-   const int* rl = rlist + ss[s].rl_off;
-   double* xw = XW + xw_off[s];
+__device__ __forceinline__ void bwd_gather_front(const FrontDev& f, const int* __restrict__ rl, double* xw, const double* __restrict__ x,
+                                                 int do_diag, int posdef_scale, int rfirst, int rstride) {
    const int m = f.m, ne = f.nelim;
-   for (int r = threadIdx.x; r < m; r += blockDim.x) {
+   for (int r = rfirst; r < m; r += rstride) {
       double v;
       if (r >= ne) v = x[row_gidx(f, rl, r)];
       else {
@@ -455,14 +469,25 @@ __global__ void __launch_bounds__(256) k_bwd_gather(const FrontDev* __restrict__
       xw[r] = v;
    }
 }
+// grid (fronts of the level, row chunks)
+__global__ void __launch_bounds__(256) k_bwd_gather(const FrontDev* __restrict__ fr, const SlotStatic* __restrict__ ss,
+                                                    const int* __restrict__ rlist, const int64_t* __restrict__ xw_off,
+                                                    double* XW, const double* __restrict__ x, int slot0, int do_diag,
+                                                    int posdef_scale, int kind) {
+   const int s = slot0 + blockIdx.x;
+   const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
+   bwd_gather_front(f, rlist + ss[s].rl_off, XW + xw_off[s], x, do_diag, posdef_scale, blockIdx.y * blockDim.x + threadIdx.x,
+                    gridDim.y * blockDim.x);
+}
 
 // Backward step for column block `step`: PART[front][chunk][j] = sum_{r in chunk} L(r, k0+j) xw(r) by every CTA
 // (one warp per group of KBC / 8 columns, lanes down the rows), then the last CTA to arrive computes
 // x(block) = L(block,block)^{-T} (xw(block) - sum of the partials, in chunk order).
-template <int KBC>
+template <int KBC, bool FUSED>
 __global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
                                                   const int64_t* __restrict__ xw_off, double* XW,
-                                                  const int64_t* __restrict__ part_off, double* PART, int* ticket, int step, int kind) {
+                                                  const int64_t* __restrict__ part_off, double* PART, int* ticket, int step, int kind, GatherArgs ga) {
    constexpr int RD = SE / KBC, CW = KBC / 8, RL = RD / 32, SLD = KBC + 1;
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
@@ -481,6 +506,10 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const Front
    double* part = PART + part_off[s];
    const size_t ldl = f.ldl;
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   if (FUSED) {
+      bwd_gather_front(f, ga.rlist + ga.ss[s].rl_off, xw, ga.x, ga.do_diag, ga.posdef_scale, threadIdx.x, 256);
+      __syncthreads();
+   }
    if (nchunk > 0) {
       const int nctas = min((int)gridDim.y, nchunk);      // CTA y takes chunks y, y + gridDim.y, ...
       for (int ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
@@ -531,7 +560,8 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const Front
    cp_async_wait<0>();
    __syncthreads();
    smem_solve_lower_t(S, SLD, kb, xs, dots);
-   for (int i = threadIdx.x; i < kb; i += 256) xw[k0 + i] = xs[i];
+   if (FUSED) { for (int i = threadIdx.x; i < kb; i += 256) ga.x[f.perm[i]] = xs[i]; }
+   else for (int i = threadIdx.x; i < kb; i += 256) xw[k0 + i] = xs[i];
 }
 
 __global__ void __launch_bounds__(256) k_bwd_store(const FrontDev* __restrict__ fr, const int64_t* __restrict__ xw_off,
