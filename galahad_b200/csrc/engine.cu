@@ -699,12 +699,11 @@ class Numeric {
    // chain kernels (solve_kernels.cuh): role tables per level and direction, block flags, ticket counters
    int2* d_roles = nullptr;
    size_t roles_cap = 0;
-   int* d_flag_off = nullptr;
-   int* d_flags = nullptr;
-   size_t flags_cap = 0;
+   double* d_cy = nullptr;          // blocks published by the chain kernels of the running sweep (indexed like d_xw)
+   size_t cy_cap = 0;
+   bool have_chain = false;
    unsigned long long* d_chain_counter = nullptr;   // [2 * nlevels]
    int* d_chain_err = nullptr;
-   int solve_epoch = 0;
    std::vector<int64_t> roles_fwd_off, roles_bwd_off;
    std::vector<int> roles_fwd_n, roles_bwd_n;
    bool use_fused = !(getenv("B200LDLT_FUSED") && atoi(getenv("B200LDLT_FUSED")) == 0);
@@ -749,7 +748,7 @@ class Numeric {
       cudaSetDevice(P->device);
       fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release(); bar.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
-      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_flag_off); cudaFree(d_flags); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
+      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
       if (pin_updmap) cudaFreeHost(pin_updmap);
@@ -845,7 +844,6 @@ int Numeric::init() {
    CU(cudaMalloc(&d_xw_off, sizeof(int64_t) * (nn + 1)));
    CU(cudaMalloc(&d_part_off, sizeof(int64_t) * (nn + 1)));
    CU(cudaMalloc(&d_ticket, sizeof(int) * (nn + 1)));
-   CU(cudaMalloc(&d_flag_off, sizeof(int) * (nn + 1)));
    CU(cudaMalloc(&d_chain_counter, sizeof(unsigned long long) * 2 * (P->nlevels + 1)));
    CU(cudaMalloc(&d_chain_err, sizeof(int)));
    CU(cudaMemset(d_chain_err, 0, sizeof(int)));
@@ -1406,8 +1404,6 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       if (nn > 0) CU(cudaMemcpy(d_slist, slist.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
       // chain kernels for the levels that hold fronts of more than KB eliminated columns
       {
-         std::vector<int> foff(nn + 1, 0);
-         for (int s = 0; s < nn; ++s) foff[s + 1] = foff[s] + ((hfr[s].state == 2 ? hfr[s].nelim : 0) + KB - 1) / KB;
          std::vector<int2> roles;
          roles_fwd_off.assign(P->nlevels, 0); roles_bwd_off.assign(P->nlevels, 0);
          roles_fwd_n.assign(P->nlevels, 0); roles_bwd_n.assign(P->nlevels, 0);
@@ -1438,16 +1434,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             CU(cudaMalloc(&d_roles, sizeof(int2) * (roles.size() + 1)));
             roles_cap = roles.size() + 1;
          }
-         if (flags_cap < (size_t)foff[nn] + 1) {
-            cudaFree(d_flags); d_flags = nullptr;
-            CU(cudaMalloc(&d_flags, sizeof(int) * ((size_t)foff[nn] + 1)));
-            flags_cap = (size_t)foff[nn] + 1;
-         }
          if (!roles.empty()) CU(cudaMemcpy(d_roles, roles.data(), sizeof(int2) * roles.size(), cudaMemcpyHostToDevice));
-         CU(cudaMemcpy(d_flag_off, foff.data(), sizeof(int) * (nn + 1), cudaMemcpyHostToDevice));
-         CU(cudaMemset(d_flags, 0, sizeof(int) * flags_cap));
          CU(cudaMemset(d_chain_counter, 0, sizeof(unsigned long long) * 2 * (P->nlevels + 1)));
-         solve_epoch = 0;
+         have_chain = !roles.empty();
       }
       // child delay offsets must describe the final state for the solve
       if (!child_doff.empty())
@@ -1481,6 +1470,12 @@ int Numeric::solve_prepare() {
       CU(cudaMalloc(&d_xw, 2 * ((size_t)xw_total + 2) * 8));
       xw_cap = 2 * ((size_t)xw_total + 2);
    }
+   if (have_chain && cy_cap < (size_t)xw_total + 2) {
+      cudaFree(d_cy);
+      d_cy = nullptr;
+      CU(cudaMalloc(&d_cy, ((size_t)xw_total + 2) * 8));
+      cy_cap = (size_t)xw_total + 2;
+   }
    if (part_cap < (size_t)part_total + 2) {
       cudaFree(d_part);
       d_part = nullptr;
@@ -1509,7 +1504,7 @@ static inline int step_slots(int kbmax, bool bwd) { return kbmax <= 64 ? (bwd ? 
 
 // forward sweep over the fronts of `kind` (-1: all)
 void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
-   const int epoch = ++solve_epoch;
+   if (have_chain) cudaMemsetAsync(d_cy, 0xff, (size_t)xw_total * 8, st);   // nothing published yet (CY_EMPTY)
    double* d_xa = d_xw + xw_cap / 2;
    GatherArgs ga{P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, P->d_rlist, d_xp, posdef ? 1 : 0, 0};
    for (int l = 0; l < P->nlevels; ++l) {
@@ -1526,7 +1521,7 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
       ++nlaunch;
       if (roles_fwd_n[l] > 0) {
          k_fwd_chain<<<roles_fwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_fwd_off[l], roles_fwd_n[l], d_chain_counter + 2 * l, d_xw_off,
-                                                               d_xw, d_xa, d_flag_off, d_flags, epoch, kind, d_chain_err);
+                                                               d_xw, d_xa, d_cy, kind, d_chain_err);
          ++nlaunch;
       } else
       for (int sp = 0; sp < lvl_steps[l]; ++sp) {
@@ -1545,7 +1540,7 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
 }
 
 void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
-   const int epoch = ++solve_epoch;
+   if (have_chain) cudaMemsetAsync(d_cy, 0xff, (size_t)xw_total * 8, st);
    GatherArgs ga{P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, P->d_rlist, d_xp, posdef ? 1 : 0, diag ? 1 : 0};
    for (int l = P->nlevels - 1; l >= 0; --l) {
       const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
@@ -1563,7 +1558,7 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
       }
       if (roles_bwd_n[l] > 0) {
          k_bwd_chain<<<roles_bwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_bwd_off[l], roles_bwd_n[l], d_chain_counter + 2 * l + 1, d_xw_off,
-                                                               d_xw, d_flag_off, d_flags, epoch, kind, d_chain_err);
+                                                               d_xw, d_cy, kind, d_chain_err);
          ++nlaunch;
       } else
       for (int sp = lvl_steps[l] - 1; sp >= 0; --sp) {

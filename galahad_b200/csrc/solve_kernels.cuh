@@ -249,34 +249,45 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 2 : 1) k_fwd_step(const Front
 // role only ever waits for roles with smaller tickets (so a waiting CTA can never keep its producer off the
 // GPU):
 //   forward : role c < nb owns block row c of the front: it streams L(c, b) for b < c as the solved blocks y_b
-//             are published (one flag per block, holding the epoch of the sweep), then solves its own triangle
-//             from shared memory and publishes y_c; roles >= nb take 128 rows each of the part below the pivots;
+//             are published, then solves its own triangle from shared memory and publishes y_c; roles >= nb take
+//             128 rows each of the part below the pivots;
 //   backward: role c owns block column c: dot products with the rows below the pivots (known), then with the
 //             blocks b > c as their solutions appear, last first; then the transposed triangle.
-// The entries of L needed next are always requested BEFORE the flag they depend on is polled, so that the chain
-// between two consecutive blocks is: flag -> 64 FMAs per thread from registers -> reduction -> triangle.
-// A lost producer cannot hang the GPU: a poll gives up after ~2 s and raises *err.
+// The entries of L needed next are always requested BEFORE the block they multiply is polled, so that the chain
+// between two consecutive blocks is: values arrive -> 64 FMAs per thread from registers -> reduction -> triangle.
+// A lost producer cannot hang the GPU: a poll gives up after ~1 s and raises *err.
 constexpr int CH = 128;      // rows of a role = block width
 
-__device__ __forceinline__ void chain_wait(const int* flag, int epoch, int* err) {
-   if ((threadIdx.x & 31) == 0 && *((volatile const int*)flag) != epoch && *((volatile int*)err) == 0) {
-      const long long t0 = clock64();
-      while (*((volatile const int*)flag) != epoch) {
-         if (clock64() - t0 > 2000000000LL) { *err = 1; break; }
-      }
-   }
-   __syncwarp();
-   __threadfence();
+// Solved blocks travel between the CTAs of a launch through CY, a vector the host fills with the bit pattern
+// CY_EMPTY (all ones, a NaN no computation produces: the publisher canonicalises) before each sweep.  The
+// consumer polls the values themselves: 8-byte stores are atomic, so no flag and no fence are needed, and the
+// chain saves one L2 round trip per block.
+constexpr unsigned long long CY_EMPTY = 0xffffffffffffffffULL;
+__device__ __forceinline__ double cy_load(const double* p) {
+   return __longlong_as_double(*((volatile const long long*)p));
 }
-__device__ __forceinline__ void chain_publish(int* flag, int epoch) {
-   __threadfence();
-   __syncthreads();
-   if (threadIdx.x == 0) *((volatile int*)flag) = epoch;
+__device__ __forceinline__ bool cy_empty(double v) { return (unsigned long long)__double_as_longlong(v) == CY_EMPTY; }
+__device__ __forceinline__ void cy_store(double* p, double v) {
+   if (cy_empty(v)) v = __longlong_as_double(0x7ff8000000000000LL);
+   *((volatile double*)p) = v;
+}
+// spin until buf[0..N) (values this thread needs, at stride `stride` from p) are all published
+template <int N>
+__device__ __forceinline__ void cy_wait(double (&buf)[N], const double* p, int stride, int nvalid, int* err) {
+   long long t0 = 0;
+   for (;;) {
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < N; ++j) { buf[j] = j * stride < nvalid ? cy_load(p + j * stride) : 0.0; ok = ok && !cy_empty(buf[j]); }
+      if (ok) break;
+      if (t0 == 0) { if (*((volatile int*)err)) break; t0 = clock64(); }
+      else if (clock64() - t0 > 2000000000LL) { *err = 1; break; }
+   }
 }
 
 __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
                                                       unsigned long long* counter, const int64_t* __restrict__ xw_off, double* XW,
-                                                      double* XY, const int* __restrict__ flag_off, int* flags, int epoch, int kind, int* err) {
+                                                      double* XY, double* CY, int kind, int* err) {
    constexpr int SLD = KB + 1;
    __shared__ int2 role;
    if (threadIdx.x == 0) role = roles[(int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles)];
@@ -294,14 +305,14 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
    double* xs = sm + KB * SLD;        // KB
    double* red = xs + KB;             // 2 x CH
    double* xw = XW + xw_off[s];
-   double* xy = XY + xw_off[s];
-   int* fl = flags + flag_off[s];
+   const double* cy = CY + xw_off[s];
    const size_t ldl = f.ldl;
    if (owner) stage_triangle(S, SLD, f.L + (size_t)rbase * ldl + rbase, ldl, rend - rbase);
-   const int i = threadIdx.x & (CH - 1), g = threadIdx.x >> 7;      // row of the role, column quarter pair
+   const int i = threadIdx.x & (CH - 1), g = threadIdx.x >> 7;      // row of the role, column half of a half block
    const bool rv = rbase + i < rend;
+   const double x0 = (g == 0 && rv) ? xw[rbase + i] : 0.0;
    const double* __restrict__ Lr = f.L + rbase + i;
-   double la[32], lb[32], acc = 0.0;
+   double la[32], lb[32], yv[32], acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
    // half h of block b: columns KB b + 64 h + 32 g + j
    auto load_half = [&](double (&buf)[32], int b, int h) {
       const int c0 = KB * b + 64 * h + 32 * g;
@@ -310,35 +321,39 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
    };
    auto use_half = [&](const double (&buf)[32], int b, int h) {
       const int c0 = KB * b + 64 * h + 32 * g;
+      cy_wait(yv, cy + c0, 1, ne - c0, err);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc += buf[j] * (c0 + j < ne ? __ldcg(xy + c0 + j) : 0.0);
+      for (int j = 0; j < 32; j += 4) {
+         acc0 += buf[j] * yv[j]; acc1 += buf[j + 1] * yv[j + 1]; acc2 += buf[j + 2] * yv[j + 2]; acc3 += buf[j + 3] * yv[j + 3];
+      }
    };
    if (nblk > 0) load_half(la, 0, 0);
    for (int b = 0; b < nblk; ++b) {
       load_half(lb, b, 1);
-      chain_wait(fl + b, epoch, err);
       use_half(la, b, 0);
       if (b + 1 < nblk) load_half(la, b + 1, 0);
       use_half(lb, b, 1);
    }
-   red[g * CH + i] = acc;
+   red[g * CH + i] = (acc0 + acc1) + (acc2 + acc3);
    __syncthreads();
    if (!owner) {
-      if (g == 0 && rv) xw[rbase + i] -= red[i] + red[CH + i];
+      if (g == 0 && rv) xw[rbase + i] = x0 - (red[i] + red[CH + i]);
       return;
    }
    const int kb = rend - rbase;
-   if (g == 0) xs[i] = rv ? xw[rbase + i] - (red[i] + red[CH + i]) : 0.0;
+   if (g == 0) xs[i] = rv ? x0 - (red[i] + red[CH + i]) : 0.0;
    cp_async_wait<0>();
    __syncthreads();
    smem_solve_lower(S, SLD, kb, xs);
-   if (threadIdx.x < kb) xy[rbase + threadIdx.x] = xs[threadIdx.x];
-   chain_publish(fl + idx, epoch);
+   if (threadIdx.x < kb) {
+      cy_store(CY + xw_off[s] + rbase + threadIdx.x, xs[threadIdx.x]);
+      XY[xw_off[s] + rbase + threadIdx.x] = xs[threadIdx.x];
+   }
 }
 
 __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
                                                       unsigned long long* counter, const int64_t* __restrict__ xw_off, double* XW,
-                                                      const int* __restrict__ flag_off, int* flags, int epoch, int kind, int* err) {
+                                                      double* CY, int kind, int* err) {
    constexpr int SLD = KB + 1;
    __shared__ int2 role;
    if (threadIdx.x == 0) role = roles[(int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles)];
@@ -352,12 +367,13 @@ __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict
    extern __shared__ double sm[];
    double* S = sm;                    // KB x SLD
    double* xs = sm + KB * SLD;        // KB
-   double* dots = xs + KB;            // KB + 32
+   double* dots = xs + KB;            // 32 + KB
    double* xw = XW + xw_off[s];
-   int* fl = flags + flag_off[s];
+   const double* cy = CY + xw_off[s];
    const size_t ldl = f.ldl;
    stage_triangle(S, SLD, f.L + (size_t)cbase * ldl + cbase, ldl, kb);
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const double x0 = threadIdx.x < kb ? xw[cbase + threadIdx.x] : 0.0;
    // warp wid takes columns cbase + 16 wid + q; a half chunk is 64 rows: two loads per lane and column
    const double* __restrict__ Lc = f.L + (size_t)(cbase + 16 * wid) * ldl + lane;
    double va[16][2], vb[16][2], acc[16];
@@ -384,10 +400,12 @@ __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict
    auto use_half = [&](const double (&buf)[16][2], int hh) {
       int r0, r1, b;
       rows_of(hh, r0, r1, b);
-      if (b >= 0 && (hh & 1) == 0) chain_wait(fl + b, epoch, err);
       double xv[2];
+      if (b >= 0) cy_wait(xv, cy + r0 + lane, 32, r1 - (r0 + lane), err);          // a block solved by this launch
+      else {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) xv[u] = (r0 + lane + 32 * u < r1) ? __ldcg(xw + r0 + lane + 32 * u) : 0.0;
+         for (int u = 0; u < 2; ++u) xv[u] = (r0 + lane + 32 * u < r1) ? xw[r0 + lane + 32 * u] : 0.0;
+      }
 #pragma unroll
       for (int q = 0; q < 16; ++q) acc[q] += buf[q][0] * xv[0] + buf[q][1] * xv[1];
    };
@@ -407,12 +425,14 @@ __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict
       if (lane == 0) dots[32 + 16 * wid + q] = a;
    }
    __syncthreads();
-   if (threadIdx.x < KB) xs[threadIdx.x] = threadIdx.x < kb ? xw[cbase + threadIdx.x] - dots[32 + threadIdx.x] : 0.0;
+   if (threadIdx.x < KB) xs[threadIdx.x] = threadIdx.x < kb ? x0 - dots[32 + threadIdx.x] : 0.0;
    cp_async_wait<0>();
    __syncthreads();
    smem_solve_lower_t(S, SLD, kb, xs, dots);
-   if (threadIdx.x < kb) xw[cbase + threadIdx.x] = xs[threadIdx.x];
-   chain_publish(fl + c, epoch);
+   if (threadIdx.x < kb) {
+      cy_store(CY + xw_off[s] + cbase + threadIdx.x, xs[threadIdx.x]);
+      xw[cbase + threadIdx.x] = xs[threadIdx.x];
+   }
 }
 
 // XY: the solved blocks (k_fwd_step)
