@@ -15,6 +15,7 @@
 // Data layout in HBM: per front, L is m x n column-major (ld = m rounded
 // up to 2), D^{-1} is 2n doubles in SSIDS's format (ldlt_app.cxx:324-329), perm is n ints, the
 // contribution block C is (m-n)^2 column-major and lives one level (ping-pong arenas).
+#include <cuda.h>            // types and prototypes only: the driver entry points are looked up at run time
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -735,6 +736,11 @@ class Numeric {
    size_t prez_c_bytes = 0, prez_l_bytes = 0;
    // look-ahead: bulk-update stream and events per chunk stream (0: st, 1..NAUX: aux[g-1])
    cudaStream_t bulk[NAUX + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+   // SM partition (green context): the bulk updates run on all SMs but `reserve_sms`, so that the next block's
+   // factorisation kernel (one CTA that needs a whole SM's shared memory) always finds a free SM
+   CUgreenCtx gctx_bulk = nullptr;
+   int reserve_sms = 0, bulk_sms = 148;
+   int make_bulk_partition(int want);
    cudaEvent_t ev_commit[NAUX + 1][2] = {}, ev_bulk[NAUX + 1][2] = {};
    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
    int cuda_err = 0;
@@ -762,6 +768,13 @@ class Numeric {
       for (int g = 0; g <= NAUX; ++g) {
          if (bulk[g]) cudaStreamDestroy(bulk[g]);
          for (int q = 0; q < 2; ++q) { if (ev_commit[g][q]) cudaEventDestroy(ev_commit[g][q]); if (ev_bulk[g][q]) cudaEventDestroy(ev_bulk[g][q]); }
+      }
+      if (gctx_bulk) {
+         typedef CUresult (*fn_gd)(CUgreenCtx);
+         fn_gd f_gd = nullptr;
+         cudaDriverEntryPointQueryResult qr;
+         if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", (void**)&f_gd, cudaEnableDefault, &qr) == cudaSuccess && f_gd) f_gd(gctx_bulk);
+         gctx_bulk = nullptr;
       }
       if (ev0) cudaEventDestroy(ev0);
       if (ev1) cudaEventDestroy(ev1);
@@ -795,6 +808,40 @@ class Numeric {
       }                                                                \
    } while (0)
 
+// Split the device's SMs into `want` reserved SMs and the rest; the rest becomes a green context whose streams
+// carry the bulk trailing updates.  Any failure leaves the ordinary streams in place (a scheduling aid, not a
+// different code path).  Driver entry points come from cudaGetDriverEntryPoint: no link against libcuda.
+int Numeric::make_bulk_partition(int want) {
+   typedef CUresult (*fn_dget)(CUdevice*, int);
+   typedef CUresult (*fn_res)(CUdevice, CUdevResource*, CUdevResourceType);
+   typedef CUresult (*fn_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+   typedef CUresult (*fn_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+   typedef CUresult (*fn_gctx)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+   fn_dget f_dget = nullptr; fn_res f_res = nullptr; fn_split f_split = nullptr; fn_desc f_desc = nullptr; fn_gctx f_gctx = nullptr;
+   cudaDriverEntryPointQueryResult qr;
+   cudaFree(0);   // the primary context exists from here on
+   if (cudaGetDriverEntryPoint("cuDeviceGet", (void**)&f_dget, cudaEnableDefault, &qr) != cudaSuccess || !f_dget) return -1;
+   if (cudaGetDriverEntryPoint("cuDeviceGetDevResource", (void**)&f_res, cudaEnableDefault, &qr) != cudaSuccess || !f_res) return -1;
+   if (cudaGetDriverEntryPoint("cuDevSmResourceSplitByCount", (void**)&f_split, cudaEnableDefault, &qr) != cudaSuccess || !f_split) return -1;
+   if (cudaGetDriverEntryPoint("cuDevResourceGenerateDesc", (void**)&f_desc, cudaEnableDefault, &qr) != cudaSuccess || !f_desc) return -1;
+   if (cudaGetDriverEntryPoint("cuGreenCtxCreate", (void**)&f_gctx, cudaEnableDefault, &qr) != cudaSuccess || !f_gctx) return -1;
+   CUdevice dev;
+   if (f_dget(&dev, P->device) != CUDA_SUCCESS) return -1;
+   CUdevResource all, grp, rem;
+   if (f_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return -1;
+   unsigned int ng = 1;
+   if (f_split(&grp, &ng, &all, &rem, 0, (unsigned)want) != CUDA_SUCCESS || ng < 1 || rem.sm.smCount < 32) return -1;
+   CUdevResourceDesc desc;
+   if (f_desc(&desc, &rem, 1) != CUDA_SUCCESS) return -1;
+   CUgreenCtx g = nullptr;
+   if (f_gctx(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS || !g) return -1;
+   gctx_bulk = g;
+   reserve_sms = (int)grp.sm.smCount;
+   bulk_sms = (int)rem.sm.smCount;
+   if (getenv("B200LDLT_VERBOSE")) fprintf(stderr, "[b200ldlt] SM partition: %d reserved, %d for bulk updates\n", reserve_sms, bulk_sms);
+   return 0;
+}
+
 int Numeric::init() {
    if (d_fr) return 0;
    CU(cudaSetDevice(P->device));
@@ -810,6 +857,13 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_bwd_step<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    CU(cudaFuncSetAttribute(k_bwd_step<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    const int nn = std::max(P->nnodes, 1);
+   {
+      const int want = getenv("B200LDLT_RESERVE_SMS") ? atoi(getenv("B200LDLT_RESERVE_SMS")) : 8;
+      if (want > 0) {
+         const int prc = make_bulk_partition(want);
+         if (prc && getenv("B200LDLT_VERBOSE")) fprintf(stderr, "[b200ldlt] SM partition not available (%s)\n", cudaGetErrorString(cudaGetLastError()));
+      }
+   }
    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
    for (int g = 0; g < NAUX; ++g) {
       CU(cudaStreamCreateWithFlags(&aux[g], cudaStreamNonBlocking));
@@ -820,7 +874,15 @@ int Numeric::init() {
    CU(cudaEventCreateWithFlags(&ev_ea, cudaEventDisableTiming));
    CU(cudaEventCreateWithFlags(&ev_zero, cudaEventDisableTiming));
    for (int g = 0; g <= NAUX; ++g) {
-      CU(cudaStreamCreateWithFlags(&bulk[g], cudaStreamNonBlocking));
+      if (gctx_bulk) {
+         typedef CUresult (*fn_sc)(CUstream*, CUgreenCtx, unsigned int, int);
+         fn_sc f_sc = nullptr;
+         cudaDriverEntryPointQueryResult qr;
+         if (cudaGetDriverEntryPoint("cuGreenCtxStreamCreate", (void**)&f_sc, cudaEnableDefault, &qr) != cudaSuccess || !f_sc ||
+             f_sc((CUstream*)&bulk[g], gctx_bulk, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS)
+            bulk[g] = nullptr;
+      }
+      if (!bulk[g]) CU(cudaStreamCreateWithFlags(&bulk[g], cudaStreamNonBlocking));
       for (int q = 0; q < 2; ++q) {
          CU(cudaEventCreateWithFlags(&ev_commit[g][q], cudaEventDisableTiming));
          CU(cudaEventCreateWithFlags(&ev_bulk[g][q], cudaEventDisableTiming));
@@ -1115,6 +1177,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             const int ncolchunks = (maxn + 63) / 64;
             const int ycommit = 1 + ncolchunks + (maxm + 255) / 256;
             const int nouter = (maxn + PB - 1) / PB;
+            const bool la_chunk = lookahead && !o.profile && !trace && nouter >= 2 && maxm >= 1024;
             // trailing-update work maps of this bucket: CTAs in proportion to the fronts' tile counts
             // (shapes without failed pivots; every front of the launch keeps at least one CTA, so a
             // front that lags behind is still updated correctly, only slower)
@@ -1141,7 +1204,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   }
                   // chunks that share the GPU with other streams keep to about half of the CTA slots, so that
                   // another chunk's block factorisation finds a free SM while this update runs
-                  const int64_t target = std::min<int64_t>(std::max<int64_t>(total, 1), single ? 2 * 296 : upd_share);
+                  const int64_t target = std::min<int64_t>(std::max<int64_t>(total, 1), (single ? 2 : 1) * (la_chunk ? 2 * bulk_sms : upd_share));
                   for (int q = 0; q < na; ++q) {
                      int parts = total > 0 ? (int)((tl[q] * target + total / 2) / total) : 1;
                      parts = std::max(1, (int)std::min<int64_t>(parts, std::max<int64_t>(tl[q], 1)));
@@ -1164,7 +1227,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             // look-ahead: the trailing update of block b is split into the strip that the next block needs
             // (on this stream) and the bulk (on the chunk's second stream, beside the factorisation of block
             // b+1).  Worth it for large fronts with several blocks; profile / trace runs keep one stream.
-            const bool la = lookahead && !o.profile && !trace && nouter >= 2 && maxm >= 1024;
+            const bool la = la_chunk;
             int nbulk = 0;
             for (int ob = 0; ob < nouter; ++ob) {
                const int na = map_na[ob];   // slots [b0, b0+na) cover every front that still has a block number ob

@@ -169,3 +169,50 @@ def test_tree_parallel_ranks_emulated(nranks):
         assert P.backward_error(prob, x, b) <= max(1e-14, 10 * P.backward_error(prob, xr, b))
         assert np.abs(x - xr).max() <= 1e-10 * max(1.0, np.abs(xr).max())
         er.free()
+
+
+def test_solve_block_boundaries_and_partial_jobs():
+    """The solve kernels at their seams: fronts of exactly / just below / just above one and several
+    128-column blocks (fused single-block launch, step kernels, chain kernels with a partial last block),
+    all jobs of datatypes.f90:62-66 on a multi-block front, and bit-reproducibility of repeated solves
+    (the chain kernels' CTAs arrive in any order, the summation orders are fixed)."""
+    for n in (31, 32, 33, 127, 128, 129, 255, 256, 257, 384, 700):
+        A, prob = P.dense_front_problem(n, "spd" if n % 2 else "indef", seed=1000 + n)
+        s, flag = gpu_factor(prob)
+        assert flag >= 0 and s.inform.num_neg == prob["inertia"][1], n
+        b = A @ np.linspace(-1.0, 1.0, n)
+        f, x = s.solve(b)
+        be = np.abs(A @ x - b).max() / (np.abs(A).sum(1).max() * np.abs(x).max() + np.abs(b).max())
+        assert f == 0 and be <= 1e-13, (n, be)
+        f, x2 = s.solve(b)
+        assert np.array_equal(x, x2), n
+        f, y = s.solve(b, job=1)
+        f, z = s.solve(y, job=4)
+        assert np.abs(z - x).max() <= 1e-11 * max(1, np.abs(x).max()), n
+        f, y2 = s.solve(y, job=2)
+        f, z2 = s.solve(y2, job=3)
+        assert np.abs(z2 - x).max() <= 1e-11 * max(1, np.abs(x).max()), n
+        # several right-hand sides are solved column by column: same bits as one at a time
+        B = np.stack([b, 2 * b - 1.0, np.ones(n)], axis=1)
+        f, X = s.solve(B)
+        assert np.array_equal(X[:, 0], x), n
+        f, x3 = s.solve(np.ones(n))
+        assert np.array_equal(X[:, 2], x3), n
+
+
+def test_c2_full_size_properties():
+    """BASELINE configs[1] at full size (64^3 7-point Laplacian, n = 262 144): size-independent properties --
+    SPD so no negative pivots and no delays, the posdef and the pivoted path agree, backward error <= 1e-14,
+    solves reproducible to the bit."""
+    prob = P.laplace_problem(64)
+    s, flag = gpu_factor(prob)
+    assert flag == 0 and s.inform.num_neg == 0 and s.inform.num_delay == 0
+    xs, b = rhs_for(prob)
+    f, x = s.solve(b)
+    assert f == 0 and P.backward_error(prob, x, b) <= 1e-14
+    f, x2 = s.solve(b)
+    assert np.array_equal(x, x2)
+    s2, flag2 = gpu_factor(prob, posdef=True)
+    f, xp = s2.solve(b)
+    assert flag2 == 0 and P.backward_error(prob, xp, b) <= 1e-14
+    assert np.abs(xp - x).max() <= 1e-10 * np.abs(x).max()
