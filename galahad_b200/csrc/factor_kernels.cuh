@@ -977,6 +977,8 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
       const int rbase = cbeg + ti * TM, cbase = cbeg + tj * TN;
       const bool full = (rbase + TM <= m) && (cbase + TN <= cend) && vec16;
       const bool below = cbase + TN - 1 <= rbase;     // tile entirely below the diagonal
+      // a warp whose 32 x 32 part of a diagonal tile lies strictly above the diagonal has nothing to compute
+      const bool above = rbase + wr * 32 + 31 < cbase + wc * 32;
       int nti = ti, ntj = tj + nparts;
       const bool has_next = normalise(nti, ntj);
       const int nrbase = cbeg + nti * TM, ncbase = cbeg + ntj * TN;
@@ -1035,6 +1037,7 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
          const double* as = As + buf * BK * LDA + wr * 32 + g + t4 * LDA;
          const double* bs = Bs + buf * BK * LDB + wc * 32 + g + t4 * LDB;
          double af[2][4], bf[2][4];
+         if (!above) {
 #pragma unroll
          for (int i = 0; i < 4; ++i) { af[0][i] = as[i * 8]; bf[0][i] = bs[i * 8]; }
 #pragma unroll
@@ -1051,6 +1054,7 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], -bf[cur][j], af[cur][i]);
+         }
          }
          __syncthreads();
          buf ^= 1;
