@@ -384,11 +384,12 @@ def run_tree_parallel(args, prob, torch, dist, rank, world, local):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.grid), "num_flops": flops, "num_factor": nfact,
-                       "parallelism": f"tree-parallel over {world} GPUs: {len(ds.boundaries)} leaf subtrees, root part on rank 0, "
-                                      f"{ds.bytes_moved / 1e6:.1f} MB of contribution blocks over NCCL per factorisation",
+                       "parallelism": f"tree-parallel over {world} GPUs: proportional mapping, {ds.nstages} stages, "
+                                      f"{sum(1 for st in ds.boundaries for (_, a, c) in st if a != c)} boundary fronts moved between ranks "
+                                      f"({ds.bytes_moved / 1e6:.1f} MB through rank 0 per factorisation)",
                        "l2": "256 MB buffer written between iterations; factor working set >> L2",
-                       "timing": "max over ranks of the wall time of factor (H2D of val, leaves, exchange, root) between device synchronisations"},
-            "factor_ms": tf * 1e3, "solve_ms": ts * 1e3, "leaves_ms": ds.t_leaves * 1e3, "root_ms": ds.t_root * 1e3,
+                       "timing": "max over ranks of the wall time of factor (H2D of val, the stages and the exchanges between them) between device synchronisations"},
+            "factor_ms": tf * 1e3, "solve_ms": ts * 1e3, "stage_ms_rank0": [round(v * 1e3, 3) for v in ds.t_stage],
             "backward_error": P.backward_error(prob, x, b), "num_neg": ds.num_neg,
             "gpu_launches": int(ds.s.inform.reserved[0]) * args.steps,
             "e2e": {"value": flops / tf / 1e12, "unit": UNIT, "h2d_bytes_per_step": int(world * 8 * prob["val"].size + world * 8 * n),

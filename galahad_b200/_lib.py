@@ -66,9 +66,10 @@ SYMBOLS = [
     "b200ldlt_default_options", "b200ldlt_analyse", "b200ldlt_analyse_ptr64", "b200ldlt_factor",
     "b200ldlt_factor_device", "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_enquire_indef",
     "b200ldlt_enquire_posdef", "b200ldlt_alter", "b200ldlt_free_fkeep", "b200ldlt_free",
-    "b200ldlt_akeep_sizes", "b200ldlt_akeep_get", "b200ldlt_partition", "b200ldlt_part_info",
+    "b200ldlt_akeep_sizes", "b200ldlt_akeep_get", "b200ldlt_partition", "b200ldlt_part_info", "b200ldlt_map_info",
     "b200ldlt_node_info", "b200ldlt_node_copy", "b200ldlt_version", "b200ldlt_ntree_sizes", "b200ldlt_ntree_get",
-    "b200ldlt_dist_init", "b200ldlt_dist_factor", "b200ldlt_dist_nboundary", "b200ldlt_dist_boundary",
+    "b200ldlt_dist_init", "b200ldlt_dist_factor", "b200ldlt_dist_nstages", "b200ldlt_dist_nboundary", "b200ldlt_dist_boundary",
+    "b200ldlt_dist_xp_get_stage", "b200ldlt_dist_xp_merge_stage",
     "b200ldlt_dist_contrib_bytes", "b200ldlt_dist_contrib_pack", "b200ldlt_dist_contrib_unpack",
     "b200ldlt_dist_xtail_bytes", "b200ldlt_dist_xtail_pack", "b200ldlt_dist_xtail_unpack", "b200ldlt_dist_solve",
     "b200ldlt_dist_xp", "b200ldlt_dist_xp_get",
@@ -109,7 +110,10 @@ def lib():
     L.b200ldlt_dist_init.argtypes = [vp, vpp, C.c_int, C.c_int, op, fp]
     L.b200ldlt_dist_factor.argtypes = [vp, vp, C.c_int, C.c_int, dp, op, fp]
     L.b200ldlt_dist_nboundary.argtypes = [vp]
-    L.b200ldlt_dist_boundary.argtypes = [vp, C.c_int, ip, ip]
+    L.b200ldlt_dist_boundary.argtypes = [vp, C.c_int, ip, ip, ip, ip]
+    L.b200ldlt_dist_nstages.argtypes = [vp]
+    L.b200ldlt_dist_xp_get_stage.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.b200ldlt_dist_xp_merge_stage.argtypes = [vp, C.c_int, vp, C.c_int]
     L.b200ldlt_dist_contrib_bytes.argtypes = [vp, C.c_int]
     L.b200ldlt_dist_contrib_bytes.restype = C.c_int64
     L.b200ldlt_dist_contrib_pack.argtypes = [vp, C.c_int, vp]
@@ -123,6 +127,7 @@ def lib():
     L.b200ldlt_dist_xp.restype = C.c_void_p
     L.b200ldlt_dist_xp_get.argtypes = [vp, vp, C.c_int]
     L.b200ldlt_partition.argtypes = [vp, C.c_int]
+    L.b200ldlt_map_info.argtypes = [vp, C.c_int, ip, ip]
     L.b200ldlt_part_info.argtypes = [vp, C.c_int, ip, ip, ip, ip, lp]
     L.b200ldlt_node_info.argtypes = [vp, C.c_int, ip, ip, ip]
     L.b200ldlt_node_copy.argtypes = [vp, C.c_int, dp, dp, ip]

@@ -530,6 +530,72 @@ void find_subtree_partition(Symbolic& sym, int ndev, double max_load_inbalance, 
    if (nn == 0) { sym.nparts = 1; sym.part = {0, 0}; sym.exec_loc = {-1}; }
 }
 
+
+void proportional_mapping(Symbolic& sym, int ndev) {
+   const int nn = sym.nnodes;
+   if (ndev < 1) ndev = 1;
+   sym.map_owner.assign(std::max(nn, 1), 0);
+   sym.map_stage.assign(std::max(nn, 1), 0);
+   sym.nstages = 1;
+   if (nn == 0) return;
+   std::vector<int64_t> flops(nn + 1, 0);
+   std::vector<int> size(nn + 1, 0);
+   for (int node = 0; node < nn; ++node) {
+      int64_t m = sym.rptr[node + 1] - sym.rptr[node], nc = sym.sptr[node + 1] - sym.sptr[node];
+      for (int64_t j = m - nc + 1; j <= m; ++j) flops[node] += j * j;   // compute_flops, anal.f90:205-224
+      size[node] += 1;
+      flops[sym.sparent[node]] += flops[node];
+      size[sym.sparent[node]] += size[node];
+   }
+   std::vector<std::vector<int>> children(nn + 1);
+   for (int node = 0; node < nn; ++node) children[sym.sparent[node]].push_back(node);
+   std::vector<char> upper(nn + 1, 0);
+   struct Item { int node, r0, g; };
+   std::vector<Item> stack;
+   stack.push_back({nn, 0, ndev});           // the virtual root holds the forest
+   while (!stack.empty()) {
+      const Item it = stack.back();
+      stack.pop_back();
+      if (it.g <= 1 && it.node < nn) {         // one device left: the whole subtree is a leaf part of it
+         for (int q = it.node - size[it.node] + 1; q <= it.node; ++q) sym.map_owner[q] = it.r0;
+         continue;
+      }
+      if (it.node < nn) { sym.map_owner[it.node] = it.r0; upper[it.node] = 1; }
+      std::vector<int> kids = children[it.node];
+      std::stable_sort(kids.begin(), kids.end(), [&](int a, int b) { return flops[a] > flops[b]; });
+      int64_t W = 0;
+      for (int c : kids) W += flops[c];
+      // devices per child: rounded share, the largest child first; leftovers go to the largest children
+      std::vector<int> alloc(kids.size(), 0);
+      int left = it.g;
+      for (size_t i = 0; i < kids.size() && left > 0; ++i) {
+         const double share = W > 0 ? (double)it.g * (double)flops[kids[i]] / (double)W : 0.0;
+         int a = (int)(share + 0.5);
+         if (i == 0) a = std::max(a, 1);
+         a = std::min(a, left);
+         alloc[i] = a;
+         left -= a;
+      }
+      for (size_t i = 0; i < kids.size() && left > 0; ++i)
+         if (alloc[i] > 0) { ++alloc[i]; --left; }
+      int r = it.r0;
+      for (size_t i = 0; i < kids.size(); ++i) {
+         if (alloc[i] > 0) { stack.push_back({kids[i], r, alloc[i]}); r += alloc[i]; }
+         else stack.push_back({kids[i], it.r0, 1});      // too small for a device of its own: stays with the owner
+      }
+   }
+   // stages, children before parents (postorder numbering)
+   int mx = 0;
+   for (int node = 0; node < nn; ++node) {
+      int st = 0;
+      for (int c : children[node]) st = std::max(st, sym.map_stage[c] + (sym.map_owner[c] != sym.map_owner[node] ? 1 : 0));
+      sym.map_stage[node] = st;
+      mx = std::max(mx, st);
+   }
+   (void)upper;
+   sym.nstages = mx + 1;
+}
+
 }  // namespace b200
 
 namespace b200 {

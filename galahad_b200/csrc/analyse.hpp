@@ -37,6 +37,11 @@ struct Symbolic {
    std::vector<int> contrib_ptr;   // nparts+1
    std::vector<int> contrib_idx;   // contributing parts
    std::vector<int> contrib_dest;  // destination node of each contribution
+   // proportional mapping of the whole tree onto `ndev` devices (proportional_mapping): owner and stage of
+   // every node.  A node's stage is larger than the stage of every child owned by another device, so stage k
+   // can be factorised everywhere once the boundary fronts of the stages < k have been exchanged.
+   std::vector<int> map_owner, map_stage;
+   int nstages = 1;
 };
 
 enum : int {
@@ -67,6 +72,12 @@ enum : int {
 // Lower-triangular CSC pattern (ptr/row, 0-based) + user order (order[i] = position, 0-based).
 // Returns sym.flag.  nemin < 1 selects the reference default (32).
 int analyse(int n, const int64_t* ptr, const int* row, const int* order, int nemin, Symbolic& sym);
+
+// Proportional mapping (the multi-level generalisation of the subtree partition: SURVEY section 8e): the root
+// gets all devices, the devices of a node are split among its children in proportion to their subtree flops,
+// a subtree that is left with one device is a leaf part of that device; a node is owned by the first device of
+// its range.  Fills map_owner / map_stage / nstages.
+void proportional_mapping(Symbolic& sym, int ndev);
 
 // Partition the assembly tree into `ndev` leaf parts + one root part following
 // anal.f90:284-459 with a GPU-only topology of `ndev` equal devices.

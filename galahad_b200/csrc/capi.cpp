@@ -345,7 +345,17 @@ int b200ldlt_partition(void* akeep, int nranks) {
    if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
    Akeep* ak = static_cast<Akeep*>(akeep);
    find_subtree_partition(ak->nsym, nranks, 1.2, 0);   // on the engine's (fused) tree
+   proportional_mapping(ak->nsym, nranks);
    return ak->nsym.nparts;
+}
+
+int b200ldlt_map_info(void* akeep, int node, int* owner, int* stage) {
+   if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   const Symbolic& s = static_cast<Akeep*>(akeep)->nsym;
+   if (node < 0 || node >= s.nnodes || (int)s.map_owner.size() < s.nnodes) return SSIDS_ERROR_CALL_SEQUENCE;
+   if (owner) *owner = s.map_owner[node];
+   if (stage) *stage = s.map_stage[node];
+   return 0;
 }
 
 int b200ldlt_part_info(void* akeep, int part, int* first_node, int* last_node, int* owner,
@@ -377,7 +387,8 @@ int b200ldlt_dist_init(void* akeep, void** fkeep, int rank, int nranks, const b2
    if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
    Akeep* ak = static_cast<Akeep*>(akeep);
    *inf = ak->inf_analyse;
-   find_subtree_partition(ak->nsym, nranks, 1.2, 0);
+   find_subtree_partition(ak->nsym, nranks, 1.2, 0);   // reported through part_info (SSIDS's single-level view)
+   proportional_mapping(ak->nsym, nranks);             // what the engine executes
    inf->nparts = ak->nsym.nparts;
    if (ensure_plan(ak, opt->device)) { inf->cuda_error = ak->plan_cuda_error; return inf->flag = SSIDS_ERROR_CUDA_UNKNOWN; }
    if (*fkeep) b200ldlt_free_fkeep(fkeep);
@@ -412,25 +423,38 @@ int b200ldlt_dist_factor(void* akeep, void* fkeep, int phase, int posdef, const 
    return inf->flag = flag;
 }
 
-// boundary fronts: roots of leaf parts whose parent lies in the root part
+// stages of the proportional mapping, and its boundary fronts: nodes whose parent is factorised in a later
+// stage; (node, owner of the node, owner of its parent, stage of the node)
+int b200ldlt_dist_nstages(void* akeep) {
+   if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
+   return static_cast<Akeep*>(akeep)->nsym.nstages;
+}
 int b200ldlt_dist_nboundary(void* akeep) {
    if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
    const Symbolic& s = static_cast<Akeep*>(akeep)->nsym;
+   if ((int)s.map_stage.size() < s.nnodes) return 0;
    int c = 0;
-   for (int p = 0; p < s.nparts; ++p) {
-      int last = s.part[p + 1] - 1;
-      if (s.exec_loc[p] >= 0 && last >= 0 && s.sparent[last] < s.nnodes) ++c;
+   for (int node = 0; node < s.nnodes; ++node) {
+      const int par = s.sparent[node];
+      if (par < s.nnodes && s.map_stage[par] > s.map_stage[node]) ++c;
    }
    return c;
 }
-int b200ldlt_dist_boundary(void* akeep, int i, int* node, int* owner) {
+int b200ldlt_dist_boundary(void* akeep, int i, int* node_out, int* src, int* dst, int* stage) {
    if (!akeep) return SSIDS_ERROR_CALL_SEQUENCE;
    const Symbolic& s = static_cast<Akeep*>(akeep)->nsym;
+   if ((int)s.map_stage.size() < s.nnodes) return SSIDS_ERROR_CALL_SEQUENCE;
    int c = 0;
-   for (int p = 0; p < s.nparts; ++p) {
-      int last = s.part[p + 1] - 1;
-      if (s.exec_loc[p] >= 0 && last >= 0 && s.sparent[last] < s.nnodes) {
-         if (c == i) { *node = last; *owner = s.exec_loc[p]; return 0; }
+   for (int node = 0; node < s.nnodes; ++node) {
+      const int par = s.sparent[node];
+      if (par < s.nnodes && s.map_stage[par] > s.map_stage[node]) {
+         if (c == i) {
+            if (node_out) *node_out = node;
+            if (src) *src = s.map_owner[node];
+            if (dst) *dst = s.map_owner[par];
+            if (stage) *stage = s.map_stage[node];
+            return 0;
+         }
          ++c;
       }
    }
@@ -449,6 +473,8 @@ int b200ldlt_dist_solve(void* fkeep, int step, double* d_x, const double* d_src)
 }
 void* b200ldlt_dist_xp(void* fkeep) { return numeric_xp(static_cast<Fkeep*>(fkeep)->num); }
 int b200ldlt_dist_xp_get(void* fkeep, void* d_dst, int n) { return numeric_xp_get(static_cast<Fkeep*>(fkeep)->num, d_dst, n); }
+int b200ldlt_dist_xp_get_stage(void* fkeep, int stage, void* d_dst, int n) { return numeric_xp_get_stage(static_cast<Fkeep*>(fkeep)->num, stage, d_dst, n); }
+int b200ldlt_dist_xp_merge_stage(void* fkeep, int stage, const void* d_src, int n) { return numeric_xp_merge_stage(static_cast<Fkeep*>(fkeep)->num, stage, d_src, n); }
 
 // per-node results (parity tests compare these with the oracle's)
 int b200ldlt_node_info(void* fkeep, int node, int* m, int* n, int* nelim) {

@@ -58,7 +58,7 @@ struct FrontDev {
    unsigned p2mask[4];  // bit k set: column k of the current block is the second column of a 2x2 pivot
    int state;           // 0 absent on this rank, 2 factorised here, 3 imported from another rank (child data only)
    int active;          // 1 while this front is being assembled / factorised by the current call
-   int part_kind;       // 0 leaf part, 1 root part of the subtree partition (multi-GPU solve phases)
+   int part_kind;       // stage of the front in the proportional mapping (multi-GPU factor / solve phases); 0 on one GPU
    int stall;           // look-ahead schedule: a failed pivot was seen, the front waits for the synchronous retry rounds
    int urec[2][4];      // per block parity: {first pivot column k0, accepted pivots kc, end of the strip columns, -}
    int pad4[2];         // written by k_commit, read by the trailing updates of that block
@@ -432,14 +432,29 @@ static inline int step_grid_y(int rows, int rc, int slots, int fronts) {
 }
 static inline size_t step_smem_bwd(int kbc) { return (size_t)(kbc * (kbc + 1) + std::max(kbc, SE / kbc) + 32) * 8; }
 
-// multi-GPU: which pivots did this rank eliminate, and which of them in the root part
-__global__ void k_build_masks(const FrontDev* fr, int nslots, char* mine, char* root) {
+// multi-GPU: which pivots did this rank eliminate, and in which stage
+__global__ void k_build_masks(const FrontDev* fr, int nslots, char* mine, char* stage) {
    const int lane = threadIdx.x & 31;
    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
    if (s >= nslots) return;
    const FrontDev& f = fr[s];
    if (f.state != 2) return;
-   for (int k = lane; k < f.nelim; k += 32) { mine[f.perm[k]] = 1; root[f.perm[k]] = f.part_kind == 1; }
+   for (int k = lane; k < f.nelim; k += 32) { mine[f.perm[k]] = 1; stage[f.perm[k]] = (char)f.part_kind; }
+}
+// dst[0..n) = the entries of xp this rank produced in `stage`, zero elsewhere; dst[n..2n) = 1 where produced.
+// Both halves are summed over the ranks; k_merge_stage then takes the entries some rank produced.
+__global__ void k_get_stage(double* __restrict__ dst, const double* __restrict__ xp, const char* __restrict__ mine,
+                            const char* __restrict__ stage, int st, int n) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) {
+      const bool p = mine[i] && stage[i] == st;
+      dst[i] = p ? xp[i] : 0.0;
+      dst[n + i] = p ? 1.0 : 0.0;
+   }
+}
+__global__ void k_merge_stage(double* __restrict__ xp, const double* __restrict__ src, int n) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && src[n + i] != 0.0) xp[i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -781,11 +796,15 @@ class Numeric {
       if (ev2) cudaEventDestroy(ev2);
    }
    int init();
+   int nstages = 1;
    int factor(const double* val, bool on_device, const FactorOptions& o, FactorStats& stats, int phase = 0);
    int set_partition(int rank, int nr);
    int finish_factor(FactorStats& stats, int flag);
    int solve(int job, int nrhs, double* x, int ldx, bool on_device, double* seconds, int64_t* nl);
    int solve_prepare();
+   int build_solve_tables();
+   bool tables_dirty = true;
+   std::vector<int> child_doff_final;
    void sweep_fwd(int kind, int64_t& nlaunch);
    void sweep_bwd(int kind, bool diag, int64_t& nlaunch);
    int64_t contrib_bytes(int node) const;
@@ -912,6 +931,7 @@ int Numeric::init() {
    CU(cudaMemset(d_ticket, 0, sizeof(int) * (nn + 1)));
    CU(cudaMalloc(&d_slist, sizeof(int) * nn));
    CU(cudaMalloc(&d_val, sizeof(double) * std::max<int64_t>(P->sym->nz, 1)));
+   CU(cudaDeviceSynchronize());   // the null-stream memsets above are not ordered with the non-blocking streams
    child_doff.assign(P->child_idx.size(), 0);
    hfr.assign(nn, FrontDev());
    fac.err = dar.err = par.err = car[0].err = car[1].err = war.err = bar.err = &cuda_err;
@@ -948,18 +968,17 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    car[0].reserve((size_t)(P->est_c_doubles[0] * mult) * 8 + (1 << 16));
    car[1].reserve((size_t)(P->est_c_doubles[1] * mult) * 8 + (1 << 16));
    war.reserve((size_t)(P->est_ws_doubles * mult) * 8 + (1 << 16));
-   if (phase != 2) CU(cudaMemsetAsync(d_fr, 0, sizeof(FrontDev) * std::max(nn, 1), st));
-   // phase 0: everything (single GPU).  phase 1: the leaf parts this rank owns.  phase 2: the root
-   // part (its owner only), on top of what phase 1 and the imports left in place.
-   if (phase != 2) { fac.reset(); dar.reset(); par.reset(); bar.reset(); }
+   if (phase <= 1) CU(cudaMemsetAsync(d_fr, 0, sizeof(FrontDev) * std::max(nn, 1), st));
+   // phase 0: everything (single GPU).  phase k >= 1: this rank's fronts of stage k-1 of the proportional
+   // mapping, on top of what the earlier phases and the imports left in place.
+   if (phase <= 1) { fac.reset(); dar.reset(); par.reset(); bar.reset(); }
    for (int s = 0; s < nn; ++s) {
-      const bool mine_leaf = owner[s] == my_rank, root_part = owner[s] < 0;
-      active[s] = phase == 0 ? 1 : phase == 1 ? (mine_leaf ? 1 : 0) : (root_part && my_rank == 0 ? 1 : 0);
-      if (phase != 2) { hfr[s] = FrontDev(); }
+      active[s] = phase == 0 ? 1 : ((owner[s] == my_rank && part_kind[s] == phase - 1) ? 1 : 0);
+      if (phase <= 1) { hfr[s] = FrontDev(); }
    }
 
    CU(cudaEventRecord(ev0, st));
-   if (phase == 2) {
+   if (phase >= 2) {
       // values are already resident from phase 1
    } else if (on_device) {
       CU(cudaMemcpyAsync(d_val, val, sizeof(double) * sym.nz, cudaMemcpyDeviceToDevice, st));
@@ -1423,8 +1442,25 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    stats.num_two = pin_i[1];
    stats.num_zero = pin_i[2];
    if (stats.num_zero > 0) flag = SSIDS_WARNING_FACT_SINGULAR;
-   // solve work-vector offsets
-   {
+   tables_dirty = true;      // solve offsets, level lists and chain roles are rebuilt by the next solve
+   child_doff_final = child_doff;
+   if (d_mine_mask && nn > 0) {
+      CU(cudaMemsetAsync(d_mine_mask, 0, std::max(sym.n, 1), st));   // on st: the null stream is not ordered with it
+      CU(cudaMemsetAsync(d_root_mask, 0, std::max(sym.n, 1), st));
+      k_build_masks<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, nn, d_mine_mask, d_root_mask);
+      CU(cudaStreamSynchronize(st));
+   }
+   have = true;
+   last = stats;
+   last.flag = flag;
+   return stats.flag = flag;
+}
+
+// Solve tables (work-vector offsets, per-level front lists, chain roles): host work that depends on the pivot
+// counts of the finished factorisation; built by the first solve after a factorisation, not inside its timing.
+int Numeric::build_solve_tables() {
+   const int nn = P->nnodes;
+   const std::vector<int>& child_doff = child_doff_final;
       std::vector<int64_t> off(nn + 1, 0);
       for (int s = 0; s < nn; ++s) off[s + 1] = off[s] + align_up(hfr[s].m, 2);
       xw_total = off[nn];
@@ -1498,27 +1534,19 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             roles_cap = roles.size() + 1;
          }
          if (!roles.empty()) CU(cudaMemcpy(d_roles, roles.data(), sizeof(int2) * roles.size(), cudaMemcpyHostToDevice));
-         CU(cudaMemset(d_chain_counter, 0, sizeof(unsigned long long) * 2 * (P->nlevels + 1)));
+         CU(cudaMemsetAsync(d_chain_counter, 0, sizeof(unsigned long long) * 2 * (P->nlevels + 1), st));
          have_chain = !roles.empty();
       }
       // child delay offsets must describe the final state for the solve
       if (!child_doff.empty())
          CU(cudaMemcpy(d_child_doff, child_doff.data(), sizeof(int) * child_doff.size(), cudaMemcpyHostToDevice));
-   }
-   if (d_mine_mask && nn > 0) {
-      CU(cudaMemset(d_mine_mask, 0, std::max(sym.n, 1)));
-      CU(cudaMemset(d_root_mask, 0, std::max(sym.n, 1)));
-      k_build_masks<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, nn, d_mine_mask, d_root_mask);
-      CU(cudaStreamSynchronize(st));
-   }
-   have = true;
-   last = stats;
-   last.flag = flag;
-   return stats.flag = flag;
+   tables_dirty = false;
+   return 0;
 }
 
 int Numeric::solve_prepare() {
    const int n = P->sym->n;
+   if (tables_dirty) { int rc = build_solve_tables(); if (rc) return rc; }
    size_t need = (size_t)std::max(n, 1);
    if (x_cap < need) {
       cudaFree(d_x); cudaFree(d_xp);
@@ -1677,7 +1705,7 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
       if (e != cudaSuccess) { cuda_err = (int)e; return SSIDS_ERROR_CUDA_UNKNOWN; }
    }
    if (pin_i[pin_i_cap - 1] != 0) {   // a chain kernel gave up waiting for a block (solve_kernels.cuh): never expected
-      CU(cudaMemset(d_chain_err, 0, sizeof(int)));
+      CU(cudaMemsetAsync(d_chain_err, 0, sizeof(int), st));
       return SSIDS_ERROR_CUDA_UNKNOWN;
    }
    float ms = 0;
@@ -1698,29 +1726,25 @@ int Numeric::set_partition(int rank, int nr) {
    const int nn = P->nnodes;
    my_rank = rank;
    nranks = nr;
-   std::vector<int> node_owner(nn, -1);
-   for (int p = 0; p < sym.nparts; ++p)
-      for (int node = sym.part[p]; node < sym.part[p + 1]; ++node) node_owner[node] = sym.exec_loc[p];
-   std::vector<char> root_mask(std::max(sym.n, 1), 0), mine_mask(std::max(sym.n, 1), 0);
+   nstages = std::max(1, sym.nstages);
+   if ((int)sym.map_owner.size() < nn || (int)sym.map_stage.size() < nn) return SSIDS_ERROR_CALL_SEQUENCE;
    for (int node = 0; node < nn; ++node) {
       const int s = P->node_slot[node];
-      owner[s] = node_owner[node];
-      part_kind[s] = node_owner[node] < 0 ? 1 : 0;
+      owner[s] = sym.map_owner[node];
+      part_kind[s] = sym.map_stage[node];
       const int par = sym.sparent[node];
-      boundary[s] = (par < nn && node_owner[node] >= 0 && node_owner[par] < 0) ? 1 : 0;
-      const bool mine = node_owner[node] == rank || (node_owner[node] < 0 && rank == 0);
-      for (int piv = sym.sptr[node]; piv < sym.sptr[node + 1]; ++piv) {
-         root_mask[piv] = node_owner[node] < 0;
-         mine_mask[piv] = mine;
-      }
+      // the parent is factorised by a later call: the contribution block must outlive the level arenas
+      boundary[s] = (par < nn && sym.map_stage[par] > sym.map_stage[node]) ? 1 : 0;
    }
-   // delayed pivots cross part boundaries with their columns; the masks above are by ORIGINAL
-   // supernode, which is exact when nothing is delayed across a boundary (checked at import)
+   // which pivots this rank eliminated, and in which stage, is recorded after each factorisation phase
+   // (k_build_masks): delayed pivots move to the front that finally eliminates them
    cudaFree(d_root_mask); cudaFree(d_mine_mask);
-   CU(cudaMalloc(&d_root_mask, root_mask.size()));
-   CU(cudaMalloc(&d_mine_mask, mine_mask.size()));
-   CU(cudaMemcpy(d_root_mask, root_mask.data(), root_mask.size(), cudaMemcpyHostToDevice));
-   CU(cudaMemcpy(d_mine_mask, mine_mask.data(), mine_mask.size(), cudaMemcpyHostToDevice));
+   d_root_mask = d_mine_mask = nullptr;
+   CU(cudaMalloc(&d_root_mask, std::max(sym.n, 1)));
+   CU(cudaMalloc(&d_mine_mask, std::max(sym.n, 1)));
+   CU(cudaMemsetAsync(d_root_mask, 0, std::max(sym.n, 1), st));
+   CU(cudaMemsetAsync(d_mine_mask, 0, std::max(sym.n, 1), st));
+   CU(cudaStreamSynchronize(st));
    return 0;
 }
 
@@ -1816,17 +1840,17 @@ int Numeric::dist_solve(int step, double* d_xio, const double* src) {
    int64_t nl = 0;
    int rc = solve_prepare();
    if (rc) return rc;
-   if (step == 1) {
+   (void)src;
+   if (step == 1) {                                   // right-hand side into pivot order
       k_permute_in<<<nb, 256, 0, st>>>(d_xio, d_xp, P->d_order, n);
-      sweep_fwd(0, nl);
-   } else if (step == 2) {
-      sweep_fwd(1, nl);
-      sweep_bwd(1, !posdef, nl);
-   } else if (step == 3) {
-      if (src) k_merge_masked<<<nb, 256, 0, st>>>(d_xp, src, d_mine_mask, n);
-      sweep_bwd(0, !posdef, nl);
-   } else if (step == 4) {
-      k_permute_out_masked<<<nb, 256, 0, st>>>(d_xio, d_xp, P->d_order, d_mine_mask, n);
+   } else if (step >= 100 && step < 200) {            // forward sweep over this rank's fronts of stage step - 100
+      sweep_fwd(step - 100, nl);
+   } else if (step >= 200 && step < 300) {            // diagonal + backward sweep of stage step - 200
+      sweep_bwd(step - 200, !posdef, nl);
+   } else if (step == 4) {                            // the whole solution in the caller's order
+      k_permute_out<<<nb, 256, 0, st>>>(d_xio, d_xp, P->d_order, n);
+   } else {
+      return SSIDS_ERROR_JOB_OOR;
    }
    CU(cudaStreamSynchronize(st));
    cudaError_t e = cudaGetLastError();
@@ -1849,6 +1873,19 @@ int numeric_xtail_pack(Numeric* n, int node, void* dst) { return n->xtail_pack(n
 int numeric_xtail_unpack(Numeric* n, int node, const void* src) { return n->xtail_unpack(node, (const char*)src); }
 int numeric_dist_solve(Numeric* n, int step, double* d_x, const double* src) { return n->dist_solve(step, d_x, src); }
 double* numeric_xp(Numeric* n) { return n->d_xp; }
+int numeric_xp_get_stage(Numeric* N, int stage, void* d_dst, int n) {
+   cudaSetDevice(N->P->device);
+   if (!N->d_mine_mask || !N->d_xp) return SSIDS_ERROR_CALL_SEQUENCE;
+   k_get_stage<<<(n + 255) / 256, 256, 0, N->st>>>((double*)d_dst, N->d_xp, N->d_mine_mask, N->d_root_mask, stage, n);
+   return cudaStreamSynchronize(N->st) == cudaSuccess ? 0 : SSIDS_ERROR_CUDA_UNKNOWN;
+}
+int numeric_xp_merge_stage(Numeric* N, int stage, const void* d_src, int n) {
+   (void)stage;
+   cudaSetDevice(N->P->device);
+   if (!N->d_xp) return SSIDS_ERROR_CALL_SEQUENCE;
+   k_merge_stage<<<(n + 255) / 256, 256, 0, N->st>>>(N->d_xp, (const double*)d_src, n);
+   return cudaStreamSynchronize(N->st) == cudaSuccess ? 0 : SSIDS_ERROR_CUDA_UNKNOWN;
+}
 int numeric_xp_get(Numeric* N, void* d_dst, int n) {
    cudaSetDevice(N->P->device);
    return cudaMemcpy(d_dst, N->d_xp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice) == cudaSuccess ? 0 : SSIDS_ERROR_CUDA_UNKNOWN;

@@ -63,6 +63,8 @@ int numeric_xtail_unpack(Numeric*, int node, const void* d_src);
 int numeric_dist_solve(Numeric*, int step, double* d_x, const double* d_src);
 double* numeric_xp(Numeric*);
 int numeric_xp_get(Numeric*, void* d_dst, int n);
+int numeric_xp_get_stage(Numeric*, int stage, void* d_dst, int n);
+int numeric_xp_merge_stage(Numeric*, int stage, const void* d_src, int n);
 
 // debugging / parity: per-node results copied to the host
 int numeric_node_info(Numeric*, int node, int* m, int* n, int* nelim);

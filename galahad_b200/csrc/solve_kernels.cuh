@@ -32,18 +32,6 @@ __global__ void k_permute_out(double* __restrict__ x, const double* __restrict__
    if (i < n && order[i] >= 0) x[i] = xp[order[i]];
 }
 
-// multi-GPU: keep only the entries this rank produced (mask[p] != 0 for its pivots), zero elsewhere
-__global__ void k_permute_out_masked(double* __restrict__ x, const double* __restrict__ xp, const int* __restrict__ order,
-                                     const char* __restrict__ mask, int n) {
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n) x[i] = (order[i] >= 0 && mask[order[i]]) ? xp[order[i]] : 0.0;
-}
-// multi-GPU: take the root part's solution entries from the owner's pivot-order vector
-__global__ void k_merge_masked(double* __restrict__ xp, const double* __restrict__ src, const char* __restrict__ mine, int n) {
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n && !mine[i]) xp[i] = src[i];   // everything this rank did not eliminate itself (its ancestors are among them)
-}
-
 // xw = [b(pivot rows); 0] + sum over children (in child order) of their update vectors
 __device__ __forceinline__ void fwd_gather_front(const FrontDev* __restrict__ fr, const SlotStatic* __restrict__ ss,
                                                  const int* __restrict__ child_idx, const int* __restrict__ child_doff,

@@ -1,11 +1,12 @@
 """Tree-parallel SLS factor/solve across the GPUs of one node, one process per GPU.
 
-The assembly tree is cut into leaf subtrees (one owner rank each) and a root part (rank 0), as
-SSIDS's find_subtree_partition does for its NUMA regions / GPUs (src/ssids/anal.f90:284-459).
-There is exactly one exchange step per phase and it is point to point: the packed boundary
-fronts (contribution block + delayed columns, the wire format of contrib_type,
-src/ssids/contrib.f90:19-33) travel to the root owner with torch.distributed send/recv -- NCCL
-over NVLink on GPUs; the CPU tests drive the same schedule over gloo with a mock engine.
+The assembly tree is mapped onto the ranks by proportional mapping (csrc/analyse.cpp), the multi-level
+generalisation of SSIDS's find_subtree_partition (src/ssids/anal.f90:284-459): leaf subtrees go to single
+ranks, the fronts above them to the first rank of the group that shares their subtree, and stages are
+numbered so that stage k only needs fronts of earlier stages from other ranks.  After every stage the
+packed boundary fronts (contribution block + delayed columns, the wire format of contrib_type,
+src/ssids/contrib.f90:19-33) travel point to point to the owner of their parent with torch.distributed
+send/recv -- NCCL over NVLink on GPUs; the CPU tests drive the same schedule over gloo with a mock engine.
 """
 import ctypes as C
 
@@ -14,30 +15,37 @@ import torch
 import torch.distributed as dist
 
 
-def exchange_to_root(items, rank, nbytes_fn, pack_fn, unpack_fn, device, root=0):
-    """items: list of (key, owner).  Owners != root send key's packed bytes to root; root unpacks.
-    nbytes_fn(key) -> int (owner side), pack_fn(key, uint8 tensor), unpack_fn(key, uint8 tensor)."""
+def exchange(items, rank, nbytes_fn, pack_fn, unpack_fn, device):
+    """items: list of (key, src_rank, dst_rank), the same list in the same order on every rank.  src packs
+    key's bytes and sends them to dst, dst unpacks; pairs that do not involve this rank are skipped.
+    nbytes_fn(key) -> int (src side), pack_fn(key, uint8 tensor), unpack_fn(key, uint8 tensor, nbytes).
+    Returns the bytes this rank sent or received."""
     moved = 0
-    for key, owner in items:
-        if owner == root:
+    for key, src, dst in items:
+        if src == dst:
             continue
-        if rank == owner:
+        if rank == src:
             nb = int(nbytes_fn(key))
-            dist.send(torch.tensor([nb], dtype=torch.int64, device=device), dst=root)
+            dist.send(torch.tensor([nb], dtype=torch.int64, device=device), dst=dst)
             buf = torch.empty(max(nb, 1), dtype=torch.uint8, device=device)
             pack_fn(key, buf)
-            dist.send(buf, dst=root)
+            dist.send(buf, dst=dst)
             moved += nb
-        elif rank == root:
+        elif rank == dst:
             sz = torch.zeros(1, dtype=torch.int64, device=device)
-            dist.recv(sz, src=owner)
+            dist.recv(sz, src=src)
             nb = int(sz.item())
             buf = torch.empty(max(nb, 1), dtype=torch.uint8, device=device)
-            dist.recv(buf, src=owner)
+            dist.recv(buf, src=src)
             torch.cuda.synchronize(device) if buf.is_cuda else None   # NCCL is async; the engine reads on its own stream
             unpack_fn(key, buf, nb)
             moved += nb
     return moved
+
+
+def exchange_to_root(items, rank, nbytes_fn, pack_fn, unpack_fn, device, root=0):
+    """The single-level special case: items (key, owner) all travel to `root`."""
+    return exchange([(k, o, root) for k, o in items], rank, nbytes_fn, pack_fn, unpack_fn, device)
 
 
 class DistSolver:
@@ -53,6 +61,7 @@ class DistSolver:
         self.s = Solver(device=self.dev_index, **opts)
         self.boundaries = []
         self.bytes_moved = 0
+        self.debug = False
 
     def analyse(self, n, ptr, row, order):
         flag = self.s.analyse(n, ptr, row, order)
@@ -60,34 +69,34 @@ class DistSolver:
         s = self.s
         f = s.L.b200ldlt_dist_init(s.akeep, C.byref(s.fkeep), self.rank, self.world, C.byref(s.opt), C.byref(s.inform))
         assert f >= 0, f"dist_init flag {f}"
-        nb = s.L.b200ldlt_dist_nboundary(s.akeep)
-        self.boundaries = []
-        for i in range(nb):
-            node, owner = C.c_int(), C.c_int()
-            s.L.b200ldlt_dist_boundary(s.akeep, i, C.byref(node), C.byref(owner))
-            self.boundaries.append((node.value, owner.value))
+        self.nstages = s.L.b200ldlt_dist_nstages(s.akeep)
+        self.boundaries = [[] for _ in range(self.nstages)]      # per stage: (node, src rank, dst rank)
+        for i in range(s.L.b200ldlt_dist_nboundary(s.akeep)):
+            node, src, dst, stage = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            s.L.b200ldlt_dist_boundary(s.akeep, i, C.byref(node), C.byref(src), C.byref(dst), C.byref(stage))
+            self.boundaries[stage.value].append((node.value, src.value, dst.value))
         return flag
 
     def factor(self, val, posdef=False):
         s = self.s
         val = np.ascontiguousarray(val, np.float64)
         vp = val.ctypes.data_as(C.POINTER(C.c_double))
-        f1 = s.L.b200ldlt_dist_factor(s.akeep, s.fkeep, 1, int(posdef), vp, C.byref(s.opt), C.byref(s.inform))
-        t1 = s.inform.time_factor
-        stats = np.array([s.inform.num_neg, s.inform.num_two, s.inform.num_delay, 0, min(f1, 0)], dtype=np.int64)
-        self.bytes_moved = exchange_to_root(
-            self.boundaries, self.rank,
-            lambda node: s.L.b200ldlt_dist_contrib_bytes(s.fkeep, node),
-            lambda node, buf: s.L.b200ldlt_dist_contrib_pack(s.fkeep, node, C.c_void_p(buf.data_ptr())),
-            lambda node, buf, nb: s.L.b200ldlt_dist_contrib_unpack(s.fkeep, node, C.c_void_p(buf.data_ptr()), nb),
-            self.device)
-        t2 = 0.0
-        if self.rank == 0:
-            f2 = s.L.b200ldlt_dist_factor(s.akeep, s.fkeep, 2, int(posdef), vp, C.byref(s.opt), C.byref(s.inform))
-            t2 = s.inform.time_factor
-            # after phase 2 the counters cover every front factorised on rank 0 (leaves + root part)
-            stats = np.array([s.inform.num_neg, s.inform.num_two, s.inform.num_delay, 0, min(f1, f2, 0)], dtype=np.int64)
-        self.t_leaves, self.t_root = t1, t2
+        self.bytes_moved = 0
+        self.t_stage = []
+        worst = 0
+        for k in range(self.nstages):
+            f = s.L.b200ldlt_dist_factor(s.akeep, s.fkeep, k + 1, int(posdef), vp, C.byref(s.opt), C.byref(s.inform))
+            worst = min(worst, f)
+            self.t_stage.append(s.inform.time_factor)
+            self.bytes_moved += exchange(
+                self.boundaries[k], self.rank,
+                lambda node: s.L.b200ldlt_dist_contrib_bytes(s.fkeep, node),
+                lambda node, buf: s.L.b200ldlt_dist_contrib_pack(s.fkeep, node, C.c_void_p(buf.data_ptr())),
+                lambda node, buf, nb: s.L.b200ldlt_dist_contrib_unpack(s.fkeep, node, C.c_void_p(buf.data_ptr()), nb),
+                self.device)
+        self.t_leaves, self.t_root = self.t_stage[0], float(sum(self.t_stage[1:]))
+        # after its last phase a rank's counters cover every front it factorised
+        stats = np.array([s.inform.num_neg, s.inform.num_two, s.inform.num_delay, 0, worst], dtype=np.int64)
         t = torch.from_numpy(stats).to(self.device)
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -97,30 +106,35 @@ class DistSolver:
 
     def solve(self, b):
         s = self.s
+        n = self.n
         x = torch.from_numpy(np.ascontiguousarray(b, np.float64)).to(self.device)
         torch.cuda.synchronize(self.device)
         f = s.L.b200ldlt_dist_solve(s.fkeep, 1, C.c_void_p(x.data_ptr()), None)
         assert f >= 0, f
-        exchange_to_root(
-            self.boundaries, self.rank,
-            lambda node: s.L.b200ldlt_dist_xtail_bytes(s.fkeep, node),
-            lambda node, buf: s.L.b200ldlt_dist_xtail_pack(s.fkeep, node, C.c_void_p(buf.data_ptr())),
-            lambda node, buf, nb: s.L.b200ldlt_dist_xtail_unpack(s.fkeep, node, C.c_void_p(buf.data_ptr())),
-            self.device)
-        xp = torch.zeros(self.n, dtype=torch.float64, device=self.device)
-        if self.rank == 0:
-            f = s.L.b200ldlt_dist_solve(s.fkeep, 2, C.c_void_p(x.data_ptr()), None)
+        for k in range(self.nstages):
+            f = s.L.b200ldlt_dist_solve(s.fkeep, 100 + k, C.c_void_p(x.data_ptr()), None)
             assert f >= 0, f
-            torch.cuda.synchronize(self.device)
-            s.L.b200ldlt_dist_xp_get(s.fkeep, C.c_void_p(xp.data_ptr()), self.n)
-        if self.world > 1:
-            dist.broadcast(xp, src=0)
-            torch.cuda.synchronize(self.device)
-        src = None if self.rank == 0 else C.c_void_p(xp.data_ptr())
-        f = s.L.b200ldlt_dist_solve(s.fkeep, 3, C.c_void_p(x.data_ptr()), src)
-        assert f >= 0, f
+            exchange(
+                self.boundaries[k], self.rank,
+                lambda node: s.L.b200ldlt_dist_xtail_bytes(s.fkeep, node),
+                lambda node, buf: s.L.b200ldlt_dist_xtail_pack(s.fkeep, node, C.c_void_p(buf.data_ptr())),
+                lambda node, buf, nb: s.L.b200ldlt_dist_xtail_unpack(s.fkeep, node, C.c_void_p(buf.data_ptr())),
+                self.device)
+        part = torch.empty(2 * n, dtype=torch.float64, device=self.device)
+        for k in range(self.nstages - 1, -1, -1):
+            f = s.L.b200ldlt_dist_solve(s.fkeep, 200 + k, C.c_void_p(x.data_ptr()), None)
+            assert f >= 0, f
+            if self.world > 1:
+                # the solution entries of stage k, from whoever produced them, to everybody
+                assert s.L.b200ldlt_dist_xp_get_stage(s.fkeep, k, C.c_void_p(part.data_ptr()), n) == 0
+                dist.all_reduce(part, op=dist.ReduceOp.SUM)
+                torch.cuda.synchronize(self.device)
+                assert s.L.b200ldlt_dist_xp_merge_stage(s.fkeep, k, C.c_void_p(part.data_ptr()), n) == 0
+                if self.debug:
+                    xpv = torch.empty(n, dtype=torch.float64, device=self.device)
+                    s.L.b200ldlt_dist_xp_get(s.fkeep, C.c_void_p(xpv.data_ptr()), n)
+                    print(f"[rank {self.rank}] bwd stage {k}: flagged {int(part[n:].sum().item())} sum|val| {part[:n].abs().sum().item():.6e} "
+                          f"sum|xp| {xpv.abs().sum().item():.6e}", flush=True)
         f = s.L.b200ldlt_dist_solve(s.fkeep, 4, C.c_void_p(x.data_ptr()), None)
         assert f >= 0, f
-        if self.world > 1:
-            dist.all_reduce(x, op=dist.ReduceOp.SUM)
         return x.cpu().numpy()

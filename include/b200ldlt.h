@@ -156,24 +156,31 @@ int b200ldlt_ntree_get(void *akeep, int array_base, int *sptr, int *sparent, int
 /* Partition the assembly tree into leaf subtrees for `nranks` devices + a root part
  * (after find_subtree_partition, anal.f90:284-459).  Returns the number of parts. */
 int b200ldlt_partition(void *akeep, int nranks);
+/* proportional mapping computed by the same call: owner rank and stage of a node of the engine tree */
+int b200ldlt_map_info(void *akeep, int node, int *owner, int *stage);
 int b200ldlt_part_info(void *akeep, int part, int *first_node, int *last_node, int *owner,
                        int *dest_node, int64_t *flops);
 
-/* Tree-parallel execution, one process per GPU.  The subtree partition assigns
- * leaf subtrees to ranks and the rest of the tree (the root part) to rank 0.  Sequence per rank:
- *   dist_init -> dist_factor(phase 1: my leaf parts) -> for every boundary front: owner packs,
- *   the host side ships the packed block to rank 0 (NCCL), rank 0 unpacks -> rank 0:
- *   dist_factor(phase 2: root part).  Solve: dist_solve step 1 (all ranks), x tails of the boundary
- *   fronts to rank 0, step 2 (rank 0), broadcast of rank 0's pivot-order vector (dist_xp),
- *   step 3 (all ranks), step 4 + sum over ranks.
- * The packed boundary block is the wire format of SSIDS's contrib_type (src/ssids/contrib.f90:19-33):
- * dimensions, delayed pivot list, delayed columns, dense lower contribution block. */
+/* Tree-parallel execution, one process per GPU.  dist_init maps the assembly tree
+ * onto the ranks (proportional mapping: a node's ranks are split among its children by subtree flops; a
+ * subtree left with one rank is a leaf part; a node belongs to the first rank of its range) and numbers
+ * stages so that stage k only needs fronts of earlier stages from other ranks.
+ *   factor: for k = 0 .. nstages-1: dist_factor(phase k+1: my fronts of stage k), then every boundary
+ *           front of stage k whose parent lives elsewhere is packed by its owner (contrib_bytes /
+ *           contrib_pack), moved by the host (NCCL send/recv) and imported by the parent's owner
+ *           (contrib_unpack);
+ *   solve:  dist_solve(1) (all ranks: b in pivot order); for k ascending: dist_solve(100+k) (forward
+ *           sweep of stage k), x tails of its boundary fronts to the parents' owners (xtail_*); for k
+ *           descending: dist_solve(200+k) (diagonal + backward sweep), then the solution entries of stage k
+ *           are summed over the ranks (xp_get_stage -> all-reduce -> xp_merge_stage); dist_solve(4) returns
+ *           the whole solution in the caller's order on every rank. */
 int b200ldlt_dist_init(void *akeep, void **fkeep, int rank, int nranks, const b200ldlt_options *opt,
                        b200ldlt_inform *inf);
 int b200ldlt_dist_factor(void *akeep, void *fkeep, int phase, int posdef, const double *val,
                          const b200ldlt_options *opt, b200ldlt_inform *inf);
+int b200ldlt_dist_nstages(void *akeep);
 int b200ldlt_dist_nboundary(void *akeep);
-int b200ldlt_dist_boundary(void *akeep, int i, int *node, int *owner);
+int b200ldlt_dist_boundary(void *akeep, int i, int *node, int *src_rank, int *dst_rank, int *stage);
 int64_t b200ldlt_dist_contrib_bytes(void *fkeep, int node);
 int b200ldlt_dist_contrib_pack(void *fkeep, int node, void *d_dst);
 int b200ldlt_dist_contrib_unpack(void *fkeep, int node, const void *d_src, int64_t bytes);
@@ -183,6 +190,9 @@ int b200ldlt_dist_xtail_unpack(void *fkeep, int node, const void *d_src);
 int b200ldlt_dist_solve(void *fkeep, int step, double *d_x, const double *d_src);
 void *b200ldlt_dist_xp(void *fkeep);
 int b200ldlt_dist_xp_get(void *fkeep, void *d_dst, int n);   /* copy the pivot-order vector (device to device) */
+/* entries of the pivot-order vector this rank produced in `stage` (zero elsewhere) / take the entries of `stage` from d_src */
+int b200ldlt_dist_xp_get_stage(void *fkeep, int stage, void *d_dst, int n);
+int b200ldlt_dist_xp_merge_stage(void *fkeep, int stage, const void *d_src, int n);
 
 /* ---- per-front results, for parity checks against the oracle ---------------------------------- */
 int b200ldlt_node_info(void *fkeep, int node, int *m, int *n, int *nelim);

@@ -61,16 +61,39 @@ def test_partition_invariants():
             assert busy.size >= 2
             total = loads.sum() + sum(fl for a, b, o, d, fl in parts if o < 0)
             assert loads.max() + (total - loads.sum()) < total   # estimated makespan beats one device
-        # boundary list = roots of leaf parts with a parent
+        # proportional mapping (what the engine executes): owners, stages, boundary list
+        own, stg = np.zeros(nn, int), np.zeros(nn, int)
+        for node in range(nn):
+            o, t = C.c_int(), C.c_int()
+            assert s.L.b200ldlt_map_info(s.akeep, node, C.byref(o), C.byref(t)) == 0
+            own[node], stg[node] = o.value, t.value
+        assert own.min() >= 0 and own.max() < nranks and stg.min() == 0
+        assert len(set(own.tolist())) == min(nranks, 8)          # a 16^3 ND tree has work for 8 devices
+        nb_expected = 0
+        for node in range(nn):
+            p_ = par[node]
+            if p_ >= nn:
+                continue
+            # a parent never runs before its children; children on other ranks are exchanged first
+            assert stg[p_] >= stg[node]
+            if own[p_] != own[node]:
+                assert stg[p_] > stg[node]
+            nb_expected += stg[p_] > stg[node]
+        assert s.L.b200ldlt_dist_nstages(s.akeep) == stg.max() + 1
+        assert (stg.max() == 0) == (nranks == 1)
         nb = s.L.b200ldlt_dist_nboundary(s.akeep)
-        assert nb == sum(1 for a, b, o, d, fl in parts if o >= 0 and d >= 0)
+        assert nb == nb_expected
+        for i in range(nb):
+            a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            assert s.L.b200ldlt_dist_boundary(s.akeep, i, C.byref(a), C.byref(b), C.byref(c), C.byref(d)) == 0
+            assert own[a.value] == b.value and own[par[a.value]] == c.value and stg[a.value] == d.value
 
 
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from galahad_b200.dist import exchange_to_root
+    from galahad_b200.dist import exchange, exchange_to_root
     items = [(10, 1), (11, 0), (12, 1), (13, 1)]            # (key, owner)
     payload = {k: np.arange(k * 3, dtype=np.uint8) for k, _ in items}
     got = {}
@@ -89,6 +112,13 @@ def _worker(rank, world, port, q):
         ok = sorted(got) == [10, 12, 13] and all((got[k] == payload[k]).all() for k in got) and moved == 30 + 36 + 39
     else:
         ok = moved == 30 + 36 + 39 and not got
+    # general form: (key, src, dst) pairs, both directions
+    got2 = {}
+    items2 = [(20, 0, 1), (21, 1, 0), (22, 1, 1), (23, 0, 1)]
+    payload.update({k: np.arange(k * 2, dtype=np.uint8) for k, _, _ in items2})
+    moved2 = exchange(items2, rank, nbytes, pack, lambda k, buf, nb: got2.__setitem__(k, buf[:nb].numpy().copy()), torch.device("cpu"))
+    want = [21] if rank == 0 else [20, 23]
+    ok = ok and sorted(got2) == want and all((got2[k] == payload[k]).all() for k in got2) and moved2 == 40 + 42 + 46
     t = torch.tensor([1 if ok else 0])
     dist.all_reduce(t)
     if rank == 0:

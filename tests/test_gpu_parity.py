@@ -152,10 +152,10 @@ def test_dense_fronts_with_failed_pivots():
             assert flag2 == 0 and np.abs(x2 - x).max() <= 1e-10 * np.abs(x).max()
 
 
-@pytest.mark.parametrize("nranks", [2, 4])
+@pytest.mark.parametrize("nranks", [2, 3, 4, 8])
 def test_tree_parallel_ranks_emulated(nranks):
-    """The multi-rank path (subtree partition, packed boundary fronts, phased solve) with every
-    rank emulated as its own fkeep on this GPU: must reproduce the single-GPU result exactly."""
+    """The multi-rank path (proportional mapping, staged factorisation with packed boundary fronts, staged
+    solve) with every rank emulated as its own fkeep on this GPU: must reproduce the single-GPU result."""
     from galahad_b200.dist_emulate import EmulatedRanks
     for prob in (P.laplace_problem(12), P.kkt_grid_problem(10, dlo=1e-10), P.random_sym_problem(400, 0.01, "indef", seed=5)):
         xs, b = rhs_for(prob)

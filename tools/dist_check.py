@@ -14,6 +14,7 @@ grid = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 kind = sys.argv[2] if len(sys.argv) > 2 else "lap"
 prob = P.laplace_problem(grid) if kind == "lap" else P.kkt_grid_problem(grid)
 ds = DistSolver()
+ds.debug = bool(os.environ.get('B200LDLT_DIST_DEBUG'))
 ds.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"])
 rng = np.random.default_rng(1); xs = rng.uniform(-1, 1, prob["n"])
 b = P.full_from_lower(prob["n"], prob["ptr"], prob["row"], prob["val"]) @ xs
@@ -22,8 +23,7 @@ for rep in range(3):
     if dist.is_initialized(): dist.barrier()
     t0 = time.time(); flag = ds.factor(prob["val"]); torch.cuda.synchronize(); tf = time.time() - t0
     t0 = time.time(); x = ds.solve(b); ts = time.time() - t0
-    if rank == 0:
-        print(f"[{ds.world} ranks] {prob['name']} flag {flag} neg {ds.num_neg} (expect {prob['inertia'][1]}) delay {ds.num_delay} "
-              f"boundaries {len(ds.boundaries)} moved {ds.bytes_moved/1e6:.1f} MB factor wall {tf*1e3:.1f} ms "
-              f"(leaves {ds.t_leaves*1e3:.1f} + root {ds.t_root*1e3:.1f}) solve wall {ts*1e3:.1f} ms berr {P.backward_error(prob, x, b):.2e}", flush=True)
+    print(f"[rank {rank} of {ds.world}] rep {rep} {prob['name']} flag {flag} neg {ds.num_neg} (expect {prob['inertia'][1]}) delay {ds.num_delay} "
+          f"stages {ds.nstages} moved {ds.bytes_moved/1e6:.1f} MB factor wall {tf*1e3:.1f} ms "
+          f"(stages {[round(v*1e3,1) for v in ds.t_stage]}) solve wall {ts*1e3:.1f} ms berr {P.backward_error(prob, x, b):.2e} sum|x| {np.abs(x).sum():.6e}", flush=True)
 if dist.is_initialized(): dist.destroy_process_group()
