@@ -4,6 +4,6 @@ timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 tail -3 gpurun_out/s3_bench_n$N.err | cut -c1-400
 python - <<PY
 import json
-d=json.load(open('gpurun_out/s3_bench_n$N.json'))
+d=json.loads([l for l in open("gpurun_out/s3_bench_n$N.json") if l.startswith("{")][-1])
 print({k:d[k] for k in ('value','n_gpus','factor_ms','solve_ms','stage_ms_rank0','backward_error','num_neg')}, d['config']['parallelism'])
 PY
