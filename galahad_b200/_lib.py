@@ -64,7 +64,7 @@ class Inform(C.Structure):
 # every symbol include/b200ldlt.h declares (tests check the library exports each of them)
 SYMBOLS = [
     "b200ldlt_default_options", "b200ldlt_analyse", "b200ldlt_analyse_ptr64", "b200ldlt_factor",
-    "b200ldlt_factor_device", "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_enquire_indef",
+    "b200ldlt_factor_device", "b200ldlt_set_value_map", "b200ldlt_factor_mapped", "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_enquire_indef",
     "b200ldlt_enquire_posdef", "b200ldlt_alter", "b200ldlt_free_fkeep", "b200ldlt_free",
     "b200ldlt_akeep_sizes", "b200ldlt_akeep_get", "b200ldlt_partition", "b200ldlt_part_info", "b200ldlt_map_info",
     "b200ldlt_node_info", "b200ldlt_node_copy", "b200ldlt_version", "b200ldlt_ntree_sizes", "b200ldlt_ntree_get",
@@ -96,6 +96,8 @@ def lib():
     L.b200ldlt_analyse_ptr64.argtypes = [vpp, C.c_int, lp, ip, ip, op, fp]
     L.b200ldlt_factor.argtypes = [vp, vpp, C.c_int, dp, op, fp]
     L.b200ldlt_factor_device.argtypes = [vp, vpp, C.c_int, vp, op, fp]
+    L.b200ldlt_set_value_map.argtypes = [vp, vpp, C.c_int, ip, op, fp]
+    L.b200ldlt_factor_mapped.argtypes = [vp, vpp, C.c_int, C.c_int, dp, op, fp]
     L.b200ldlt_solve.argtypes = [vp, vp, C.c_int, C.c_int, dp, C.c_int, op, fp]
     L.b200ldlt_solve_device.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, op, fp]
     L.b200ldlt_enquire_indef.argtypes = [vp, vp, ip, dp, op, fp]
@@ -208,6 +210,19 @@ class Solver:
         val = np.ascontiguousarray(val, dtype=np.float64)
         return self.L.b200ldlt_factor(self.akeep, C.byref(self.fkeep), int(posdef), as_ptr(val, C.c_double),
                                       C.byref(self.opt), C.byref(self.inform))
+
+    def set_value_map(self, maps):
+        """maps: SLS's MAPS (1-based signed positions, sls.f90:8409-8578) for the caller's entries."""
+        maps = np.ascontiguousarray(maps, dtype=np.int32)
+        self._map_ne = maps.size
+        return self.L.b200ldlt_set_value_map(self.akeep, C.byref(self.fkeep), maps.size, as_ptr(maps, C.c_int),
+                                             C.byref(self.opt), C.byref(self.inform))
+
+    def factor_mapped(self, user_val, posdef=False):
+        user_val = np.ascontiguousarray(user_val, dtype=np.float64)
+        assert user_val.size == self._map_ne
+        return self.L.b200ldlt_factor_mapped(self.akeep, C.byref(self.fkeep), int(posdef), user_val.size,
+                                             as_ptr(user_val, C.c_double), C.byref(self.opt), C.byref(self.inform))
 
     def factor_device(self, d_ptr, posdef=False):
         return self.L.b200ldlt_factor_device(self.akeep, C.byref(self.fkeep), int(posdef), C.c_void_p(d_ptr),

@@ -146,13 +146,8 @@ int b200ldlt_analyse(void** akeep, int n, const int* ptr, const int* row, int* o
    return b200ldlt_analyse_ptr64(akeep, n, p64.data(), row, order, opt, inf);
 }
 
-static int factor_common(void* akeep, void** fkeep, int posdef, const double* val, bool on_device,
-                         const b200ldlt_options* opt, b200ldlt_inform* inf) {
-   if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
-   Akeep* ak = static_cast<Akeep*>(akeep);
-   *inf = ak->inf_analyse;
-   inf->time_analyse = 0;
-   if (ak->sym.n > 0 && !val) return inf->flag = SSIDS_ERROR_VAL;
+// plan and numeric handle for this akeep (created on first use)
+static int ensure_fkeep(Akeep* ak, void** fkeep, const b200ldlt_options* opt, b200ldlt_inform* inf) {
    if (ensure_plan(ak, opt->device)) {
       inf->cuda_error = ak->plan_cuda_error;
       return inf->flag = SSIDS_ERROR_CUDA_UNKNOWN;
@@ -166,8 +161,23 @@ static int factor_common(void* akeep, void** fkeep, int posdef, const double* va
       fk->num = numeric_create(ak->plan);
       *fkeep = fk;
    }
+   return 0;
+}
+
+// mapped_ne >= 0: `val` holds the caller's mapped_ne values in input order, gathered on the device through the
+// value map (b200ldlt_set_value_map)
+static int factor_common(void* akeep, void** fkeep, int posdef, const double* val, bool on_device,
+                         const b200ldlt_options* opt, b200ldlt_inform* inf, int mapped_ne = -1) {
+   if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   *inf = ak->inf_analyse;
+   inf->time_analyse = 0;
+   if (ak->sym.n > 0 && !val) return inf->flag = SSIDS_ERROR_VAL;
+   if (int rc = ensure_fkeep(ak, fkeep, opt, inf)) return rc;
+   Fkeep* fk = static_cast<Fkeep*>(*fkeep);
    FactorStats st;
-   int flag = numeric_factor(fk->num, val, on_device, to_engine(opt, posdef), st);
+   int flag = mapped_ne >= 0 ? numeric_factor_mapped(fk->num, mapped_ne, val, to_engine(opt, posdef), st)
+                             : numeric_factor(fk->num, val, on_device, to_engine(opt, posdef), st);
    inf->cuda_error = st.cuda_error;
    inf->num_delay = st.num_delay;
    inf->num_neg = st.num_neg;
@@ -196,6 +206,20 @@ int b200ldlt_factor(void* akeep, void** fkeep, int posdef, const double* val,
 int b200ldlt_factor_device(void* akeep, void** fkeep, int posdef, const double* d_val,
                            const b200ldlt_options* opt, b200ldlt_inform* inf) {
    return factor_common(akeep, fkeep, posdef, d_val, true, opt, inf);
+}
+
+int b200ldlt_set_value_map(void* akeep, void** fkeep, int ne, const int* maps, const b200ldlt_options* opt,
+                           b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !opt || !inf || ne < 0 || (ne > 0 && !maps)) return SSIDS_ERROR_CALL_SEQUENCE;
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   *inf = ak->inf_analyse;
+   if (int rc = ensure_fkeep(ak, fkeep, opt, inf)) return rc;
+   return inf->flag = numeric_set_value_map(static_cast<Fkeep*>(*fkeep)->num, ne, maps);
+}
+int b200ldlt_factor_mapped(void* akeep, void** fkeep, int posdef, int ne, const double* user_val,
+                           const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   if (ne < 0) return SSIDS_ERROR_CALL_SEQUENCE;
+   return factor_common(akeep, fkeep, posdef, user_val, false, opt, inf, ne);
 }
 
 static int solve_common(void* akeep, void* fkeep, int job, int nrhs, double* x, int ldx, bool on_device,

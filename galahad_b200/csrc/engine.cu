@@ -432,6 +432,24 @@ static inline int step_grid_y(int rows, int rc, int slots, int fronts) {
 }
 static inline size_t step_smem_bwd(int kbc) { return (size_t)(kbc * (kbc + 1) + std::max(kbc, SE / kbc) + 32) * 8; }
 
+// SLS value gather on the device (SLS_factorize, sls.f90:4106-4147): VAL(MAPS(l)) = val(l) for the first entry of
+// every position, duplicates added in input order, positions without an entry (missing diagonals) stay zero.
+// set_*: the (source, destination) pairs with MAPS > 0; dup_*: per destination with duplicates, its sources in
+// input order (one thread each: the summation order is the reference's).
+__global__ void k_gather_set(double* __restrict__ val, const double* __restrict__ uval, const int* __restrict__ src,
+                             const int* __restrict__ dst, int nset) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < nset) val[dst[i]] = uval[src[i]];
+}
+__global__ void k_gather_dup(double* __restrict__ val, const double* __restrict__ uval, const int* __restrict__ dup_dst,
+                             const int* __restrict__ dup_ptr, const int* __restrict__ dup_src, int ndup) {
+   int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= ndup) return;
+   double acc = val[dup_dst[t]];
+   for (int q = dup_ptr[t]; q < dup_ptr[t + 1]; ++q) acc += uval[dup_src[q]];
+   val[dup_dst[t]] = acc;
+}
+
 // multi-GPU: which pivots did this rank eliminate, and in which stage
 __global__ void k_build_masks(const FrontDev* fr, int nslots, char* mine, char* stage) {
    const int lane = threadIdx.x & 31;
@@ -733,6 +751,12 @@ class Numeric {
    size_t part_cap = 0;
    std::vector<int> child_doff;
    double* d_val = nullptr;
+   // SLS value map (set_value_map): device copies and the user's values of the current factorisation
+   double* d_uval = nullptr;
+   int *d_vm_src = nullptr, *d_vm_dst = nullptr, *d_vm_dup_dst = nullptr, *d_vm_dup_ptr = nullptr, *d_vm_dup_src = nullptr;
+   int vm_ne = 0, vm_nset = 0, vm_ndup = 0;
+   int set_value_map(int ne, const int* maps);
+   int gather_values(int ne, const double* uval);
    double *d_x = nullptr, *d_xp = nullptr, *d_xw = nullptr;
    size_t x_cap = 0, xw_cap = 0;
    int64_t xw_total = 0;
@@ -769,7 +793,7 @@ class Numeric {
       cudaSetDevice(P->device);
       fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release(); bar.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
-      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
+      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_uval); cudaFree(d_vm_src); cudaFree(d_vm_dst); cudaFree(d_vm_dup_dst); cudaFree(d_vm_dup_ptr); cudaFree(d_vm_dup_src); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
       if (pin_updmap) cudaFreeHost(pin_updmap);
@@ -981,7 +1005,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    if (phase >= 2) {
       // values are already resident from phase 1
    } else if (on_device) {
-      CU(cudaMemcpyAsync(d_val, val, sizeof(double) * sym.nz, cudaMemcpyDeviceToDevice, st));
+      if (val != d_val) CU(cudaMemcpyAsync(d_val, val, sizeof(double) * sym.nz, cudaMemcpyDeviceToDevice, st));
    } else {
       CU(cudaMemcpyAsync(d_val, val, sizeof(double) * sym.nz, cudaMemcpyHostToDevice, st));
    }
@@ -1891,6 +1915,65 @@ int numeric_xp_get(Numeric* N, void* d_dst, int n) {
    return cudaMemcpy(d_dst, N->d_xp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice) == cudaSuccess ? 0 : SSIDS_ERROR_CUDA_UNKNOWN;
 }
 void numeric_destroy(Numeric* n) { delete n; }
+int Numeric::set_value_map(int ne, const int* maps) {
+   int rc = init();
+   if (rc) return rc;
+   CU(cudaSetDevice(P->device));
+   const int64_t nz = P->sym->nz;
+   std::vector<int> src, dst;
+   std::vector<std::vector<int>> dups;        // per destination, in input order
+   std::vector<int> dup_of(std::max<int64_t>(nz, 1), -1), dup_dst;
+   for (int l = 0; l < ne; ++l) {
+      const int k = maps[l];
+      if (k > 0) { if (k > nz) return SSIDS_ERROR_VAL; src.push_back(l); dst.push_back(k - 1); }
+      else if (k < 0) {
+         const int t = -k - 1;
+         if (t >= nz) return SSIDS_ERROR_VAL;
+         if (dup_of[t] < 0) { dup_of[t] = (int)dups.size(); dups.emplace_back(); dup_dst.push_back(t); }
+         dups[dup_of[t]].push_back(l);
+      }
+   }
+   std::vector<int> dptr(dups.size() + 1, 0), dsrc;
+   for (size_t t = 0; t < dups.size(); ++t) { dptr[t + 1] = dptr[t] + (int)dups[t].size(); dsrc.insert(dsrc.end(), dups[t].begin(), dups[t].end()); }
+   cudaFree(d_uval); cudaFree(d_vm_src); cudaFree(d_vm_dst); cudaFree(d_vm_dup_dst); cudaFree(d_vm_dup_ptr); cudaFree(d_vm_dup_src);
+   d_uval = nullptr; d_vm_src = d_vm_dst = d_vm_dup_dst = d_vm_dup_ptr = d_vm_dup_src = nullptr;
+   vm_ne = ne; vm_nset = (int)src.size(); vm_ndup = (int)dups.size();
+   CU(cudaMalloc(&d_uval, sizeof(double) * std::max(ne, 1)));
+   CU(cudaMalloc(&d_vm_src, sizeof(int) * std::max<size_t>(src.size(), 1)));
+   CU(cudaMalloc(&d_vm_dst, sizeof(int) * std::max<size_t>(dst.size(), 1)));
+   CU(cudaMalloc(&d_vm_dup_dst, sizeof(int) * std::max<size_t>(dup_dst.size(), 1)));
+   CU(cudaMalloc(&d_vm_dup_ptr, sizeof(int) * dptr.size()));
+   CU(cudaMalloc(&d_vm_dup_src, sizeof(int) * std::max<size_t>(dsrc.size(), 1)));
+   if (!src.empty()) {
+      CU(cudaMemcpy(d_vm_src, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(d_vm_dst, dst.data(), sizeof(int) * dst.size(), cudaMemcpyHostToDevice));
+   }
+   if (!dup_dst.empty()) {
+      CU(cudaMemcpy(d_vm_dup_dst, dup_dst.data(), sizeof(int) * dup_dst.size(), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(d_vm_dup_src, dsrc.data(), sizeof(int) * dsrc.size(), cudaMemcpyHostToDevice));
+   }
+   CU(cudaMemcpy(d_vm_dup_ptr, dptr.data(), sizeof(int) * dptr.size(), cudaMemcpyHostToDevice));
+   return 0;
+}
+
+// user's values (host, ne of them) -> d_val through the value map; the factorisation then runs on d_val in place
+int Numeric::gather_values(int ne, const double* uval) {
+   if (!d_uval || ne != vm_ne) return SSIDS_ERROR_CALL_SEQUENCE;
+   CU(cudaSetDevice(P->device));
+   const int64_t nz = P->sym->nz;
+   if (ne > 0) CU(cudaMemcpyAsync(d_uval, uval, sizeof(double) * ne, cudaMemcpyHostToDevice, st));
+   if (nz > 0) CU(cudaMemsetAsync(d_val, 0, sizeof(double) * nz, st));
+   if (vm_nset > 0) k_gather_set<<<(vm_nset + 255) / 256, 256, 0, st>>>(d_val, d_uval, d_vm_src, d_vm_dst, vm_nset);
+   if (vm_ndup > 0) k_gather_dup<<<(vm_ndup + 255) / 256, 256, 0, st>>>(d_val, d_uval, d_vm_dup_dst, d_vm_dup_ptr, d_vm_dup_src, vm_ndup);
+   return 0;
+}
+
+int numeric_set_value_map(Numeric* n, int ne, const int* maps) { return n->set_value_map(ne, maps); }
+int numeric_factor_mapped(Numeric* n, int ne, const double* uval, const FactorOptions& o, FactorStats& s) {
+   int rc = n->gather_values(ne, uval);
+   if (rc) return s.flag = rc;
+   return n->factor(n->d_val, true, o, s);
+}
 int numeric_factor(Numeric* n, const double* val, bool on_device, const FactorOptions& o, FactorStats& s) {
    int rc = n->factor(val, on_device, o, s);
    s.cuda_error = n->cuda_err;

@@ -40,6 +40,8 @@ int plan_device(const Plan*);
 
 Numeric* numeric_create(Plan*);
 void numeric_destroy(Numeric*);
+int numeric_set_value_map(Numeric*, int ne, const int* maps);
+int numeric_factor_mapped(Numeric*, int ne, const double* uval, const FactorOptions&, FactorStats&);
 int numeric_factor(Numeric*, const double* val, bool val_on_device, const FactorOptions&,
                    FactorStats&);
 // x(ldx,nrhs) indexed by ORIGINAL variable; job 0..4

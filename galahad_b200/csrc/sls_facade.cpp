@@ -33,7 +33,7 @@ struct SlsData {
    std::vector<double> val;
    void* akeep = nullptr;
    void* fkeep = nullptr;
-   bool analysed = false, factorized = false, must_be_definite = false;
+   bool analysed = false, factorized = false, must_be_definite = false, map_set = false;
 };
 
 double now() {
@@ -239,6 +239,7 @@ void sls_analyse_matrix_perm(sls_control_type* control, void** data, int* status
    inf.duplicates = dup; inf.out_of_range = oor; inf.upper = up; inf.missing_diagonals = md; inf.entries = ents;
    inf.real_size_factors = inf.integer_size_factors = -1;   // SSIDS leaves them unset too (sbls.f90:4132)
    d->analysed = inf.status == GALAHAD_OK;
+   d->map_set = false;          // new MAPS: uploaded again by the next factorize
    d->factorized = false;
    inf.time.clock_analyse = now() - t0;
    inf.time.analyse_external = si.time_analyse;
@@ -264,19 +265,20 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
    (void)ne;
    double t0 = now();
    const int n = d->n;
-   d->uval.assign(val, val + d->ne);
-   // value gather (sls.f90:4106-4147): diagonals zeroed first, duplicates summed
-   for (int i = 1; i <= n; ++i) d->val[d->ptr[i - 1] - 1] = 0.0;
-   for (int l = 0; l < d->ne; ++l) {
-      int k = d->maps[l];
-      if (k > 0) d->val[k - 1] = val[l];
-      else if (k < 0) d->val[-k - 1] += val[l];
-   }
+   (void)n;
+   d->uval.assign(val, val + d->ne);          // kept for the residuals of the refinement loop
    // pivot_control 2/3 -> must_be_definite -> Cholesky path (sls.f90:2227-2228, 4282)
    const int posdef = (d->control.pivot_control == 2 || d->control.pivot_control == 3) ? 1 : 0;
    b200ldlt_options o = to_solver(d->control);
    b200ldlt_inform si;
-   b200ldlt_factor(d->akeep, &d->fkeep, posdef, d->val.data(), &o, &si);
+   // value gather (sls.f90:4106-4147: diagonals zeroed first, duplicates summed) on the device, through the MAPS
+   // uploaded once per analyse
+   if (!d->map_set) {
+      int mf = b200ldlt_set_value_map(d->akeep, &d->fkeep, d->ne, d->maps.data(), &o, &si);
+      d->map_set = mf >= 0;
+   }
+   if (d->map_set) b200ldlt_factor_mapped(d->akeep, &d->fkeep, posdef, d->ne, val, &o, &si);
+   // (set_value_map only fails without a CUDA device; si then carries -51 and there is no other path)
    int dup = inf.duplicates, oor = inf.out_of_range, up = inf.upper, md = inf.missing_diagonals, ents = inf.entries;
    sls_time_type tm = inf.time;
    from_solver(inf, si);

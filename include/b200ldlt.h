@@ -119,6 +119,16 @@ int b200ldlt_factor(void *akeep, void **fkeep, int posdef, const double *val,
 int b200ldlt_factor_device(void *akeep, void **fkeep, int posdef, const double *d_val,
                            const b200ldlt_options *opt, b200ldlt_inform *inf);
 
+/* SLS's value gather on the device (replaces the loop of SLS_factorize, sls.f90:4106-4147, that fills
+ * data%matrix%VAL from the caller's values through data%MAPS).  set_value_map: once per analyse, `maps[l]` as
+ * SLS_coord_to_sorted_csr leaves it (1-based: > 0 position of entry l, < 0 add to position -maps[l], 0 out of
+ * range; sls.f90:8409-8578).  factor_mapped: `user_val[ne]` in the caller's order (host); positions without an
+ * entry (missing diagonals) are zero, duplicates are summed in input order. */
+int b200ldlt_set_value_map(void *akeep, void **fkeep, int ne, const int *maps, const b200ldlt_options *opt,
+                           b200ldlt_inform *inf);
+int b200ldlt_factor_mapped(void *akeep, void **fkeep, int posdef, int ne, const double *user_val,
+                           const b200ldlt_options *opt, b200ldlt_inform *inf);
+
 /* Solve with nrhs right-hand sides held by columns in HOST x(ldx,nrhs), overwritten by the solution.
  * job as B200LDLT_JOB_*. */
 int b200ldlt_solve(void *akeep, void *fkeep, int job, int nrhs, double *x, int ldx,

@@ -216,3 +216,56 @@ def test_c2_full_size_properties():
     f, xp = s2.solve(b)
     assert flag2 == 0 and P.backward_error(prob, xp, b) <= 1e-14
     assert np.abs(xp - x).max() <= 1e-10 * np.abs(x).max()
+
+
+def test_value_gather_on_device_matches_host_gather():
+    """SLS's value gather (sls.f90:4106-4147) done on the device through the MAPS of
+    SLS_coord_to_sorted_csr: entries in arbitrary order, duplicates (up to four per position, summed in input
+    order), out-of-range entries (map 0) and positions without an entry (zero).  Must give the bits of the
+    host-side gather followed by b200ldlt_factor."""
+    rng = np.random.default_rng(77)
+    prob = P.kkt_grid_problem(8)
+    n, ptr, row, val = prob["n"], prob["ptr"], prob["row"], prob["val"]
+    nz = val.size
+    # user entries: every position once (shuffled), some split into 2-4 duplicates, a few out-of-range ones
+    pos = rng.permutation(nz)
+    pos = pos[rng.random(nz) > 0.02]                              # 2 % of the positions get no entry at all
+    dup = np.concatenate([rng.choice(pos, nz // 10), rng.choice(pos, nz // 30), rng.choice(pos[:50], 100)])
+    entries = np.concatenate([pos, dup])
+    rng.shuffle(entries)
+    uval = rng.uniform(-1, 1, entries.size)
+    # the diagonal stays dominant enough for a stable factorisation
+    diag = ptr[:-1]
+    seen = np.zeros(nz, bool)
+    maps = np.zeros(entries.size + 7, np.int32)
+    for l, p in enumerate(entries):
+        maps[l] = (p + 1) if not seen[p] else -(p + 1)
+        seen[p] = True
+    user = np.concatenate([uval, rng.uniform(-1, 1, 7)])          # the last seven are out of range: map 0
+    is_diag = np.isin(entries, diag)
+    user[:entries.size][is_diag] = np.abs(user[:entries.size][is_diag]) + 8.0
+    host = np.zeros(nz)
+    for l in range(entries.size):                                  # the reference's loop
+        k = maps[l]
+        if k > 0:
+            host[k - 1] = user[l]
+        elif k < 0:
+            host[-k - 1] += user[l]
+    s1 = Solver()
+    assert s1.analyse(n, ptr, row, prob["order"]) >= 0
+    assert s1.factor(host) >= 0
+    s2 = Solver()
+    assert s2.analyse(n, ptr, row, prob["order"]) >= 0
+    assert s2.set_value_map(maps) == 0
+    assert s2.factor_mapped(user) >= 0
+    assert (s1.inform.num_neg, s1.inform.num_two, s1.inform.num_delay) == (s2.inform.num_neg, s2.inform.num_two, s2.inform.num_delay)
+    b = rng.uniform(-1, 1, n)
+    f1, x1 = s1.solve(b)
+    f2, x2 = s2.solve(b)
+    assert f1 == 0 and f2 == 0 and np.array_equal(x1, x2)
+    # a second factorisation with new values reuses the uploaded map
+    user2 = user.copy()
+    user2[:entries.size][is_diag] += 1.0
+    assert s2.factor_mapped(user2) >= 0
+    f3, x3 = s2.solve(b)
+    assert f3 == 0 and not np.array_equal(x3, x2)
