@@ -216,6 +216,25 @@ int b200ldlt_set_value_map(void* akeep, void** fkeep, int ne, const int* maps, c
    if (int rc = ensure_fkeep(ak, fkeep, opt, inf)) return rc;
    return inf->flag = numeric_set_value_map(static_cast<Fkeep*>(*fkeep)->num, ne, maps);
 }
+int b200ldlt_set_user_matrix(void* akeep, void** fkeep, int ne, const int* row, const int* col,
+                             const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !opt || !inf || ne < 0 || (ne > 0 && (!row || !col))) return SSIDS_ERROR_CALL_SEQUENCE;
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   *inf = ak->inf_analyse;
+   if (int rc = ensure_fkeep(ak, fkeep, opt, inf)) return rc;
+   return inf->flag = numeric_set_user_matrix(static_cast<Fkeep*>(*fkeep)->num, ne, row, col);
+}
+int b200ldlt_solve_refined(void* akeep, void* fkeep, double* x, int max_refinements, double stop_absolute,
+                           double stop_relative, int* refinements, const b200ldlt_options*, b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !inf || !x) return SSIDS_ERROR_CALL_SEQUENCE;
+   Fkeep* fk = static_cast<Fkeep*>(fkeep);
+   if (fk->ak != akeep || !fk->num || !numeric_has_factors(fk->num)) return inf->flag = SSIDS_ERROR_CALL_SEQUENCE;
+   if (fk->ak->sym.n == 0) { if (refinements) *refinements = 0; return inf->flag = 0; }
+   double secs = 0;
+   int flag = numeric_solve_refined(fk->num, x, std::max(max_refinements, 0), stop_absolute, stop_relative, refinements, &secs);
+   inf->time_solve = secs;
+   return inf->flag = flag;
+}
 int b200ldlt_factor_mapped(void* akeep, void** fkeep, int posdef, int ne, const double* user_val,
                            const b200ldlt_options* opt, b200ldlt_inform* inf) {
    if (ne < 0) return SSIDS_ERROR_CALL_SEQUENCE;

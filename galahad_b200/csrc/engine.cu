@@ -450,6 +450,31 @@ __global__ void k_gather_dup(double* __restrict__ val, const double* __restrict_
    val[dup_dst[t]] = acc;
 }
 
+// Iterative refinement on the device (SLS_solve_ir, sls.f90:4751-4947).  The residual uses the caller's entries
+// (coordinates + the values of the latest factor_mapped), row by row in input order, without contraction into
+// FMAs: the same sequence of operations as the reference's loop over the entries.
+__global__ void k_residual(double* __restrict__ r, const double* __restrict__ b, const double* __restrict__ x,
+                           const double* __restrict__ uval, const int* __restrict__ rptr, const int* __restrict__ rent,
+                           const int* __restrict__ rcol, int n) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   double acc = b[i];
+   for (int q = rptr[i]; q < rptr[i + 1]; ++q) acc = __dsub_rn(acc, __dmul_rn(uval[rent[q]], x[rcol[q]]));
+   r[i] = acc;
+}
+__global__ void k_axpy1(double* __restrict__ x, const double* __restrict__ r, int n) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) x[i] += r[i];
+}
+// max |v_i| into *out (non-negative doubles order like their bit patterns)
+__global__ void k_maxabs(const double* __restrict__ v, int n, unsigned long long* out) {
+   double m = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmax(m, fabs(v[i]));
+#pragma unroll
+   for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+   if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
 // multi-GPU: which pivots did this rank eliminate, and in which stage
 __global__ void k_build_masks(const FrontDev* fr, int nslots, char* mine, char* stage) {
    const int lane = threadIdx.x & 31;
@@ -756,6 +781,13 @@ class Numeric {
    int *d_vm_src = nullptr, *d_vm_dst = nullptr, *d_vm_dup_dst = nullptr, *d_vm_dup_ptr = nullptr, *d_vm_dup_src = nullptr;
    int vm_ne = 0, vm_nset = 0, vm_ndup = 0;
    int set_value_map(int ne, const int* maps);
+   // refinement: the caller's entries by row (set_user_matrix), work vectors
+   int *d_um_rptr = nullptr, *d_um_rent = nullptr, *d_um_rcol = nullptr;
+   double *d_rb = nullptr, *d_rx = nullptr, *d_rr = nullptr;
+   unsigned long long* d_rnorm = nullptr;
+   int um_ne = -1;
+   int set_user_matrix(int ne, const int* row, const int* col);
+   int solve_refined(double* x, int max_ref, double stop_abs, double stop_rel, int* nref, double* seconds);
    int gather_values(int ne, const double* uval);
    double *d_x = nullptr, *d_xp = nullptr, *d_xw = nullptr;
    size_t x_cap = 0, xw_cap = 0;
@@ -793,7 +825,8 @@ class Numeric {
       cudaSetDevice(P->device);
       fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release(); bar.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
-      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_part); cudaFree(d_val); cudaFree(d_uval); cudaFree(d_vm_src); cudaFree(d_vm_dst); cudaFree(d_vm_dup_dst); cudaFree(d_vm_dup_ptr); cudaFree(d_vm_dup_src); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
+      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_um_rptr); cudaFree(d_um_rent); cudaFree(d_um_rcol); cudaFree(d_rb); cudaFree(d_rx); cudaFree(d_rr); cudaFree(d_rnorm);
+      cudaFree(d_part); cudaFree(d_val); cudaFree(d_uval); cudaFree(d_vm_src); cudaFree(d_vm_dst); cudaFree(d_vm_dup_dst); cudaFree(d_vm_dup_ptr); cudaFree(d_vm_dup_src); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
       if (pin_updmap) cudaFreeHost(pin_updmap);
@@ -1968,6 +2001,89 @@ int Numeric::gather_values(int ne, const double* uval) {
    return 0;
 }
 
+int Numeric::set_user_matrix(int ne, const int* row, const int* col) {
+   int rc = init();
+   if (rc) return rc;
+   CU(cudaSetDevice(P->device));
+   const int n = P->sym->n;
+   std::vector<int> rptr(n + 2, 0);
+   for (int l = 0; l < ne; ++l) {
+      const int i = row[l], j = col[l];
+      if (std::min(i, j) < 1 || std::max(i, j) > n) continue;
+      ++rptr[i + 1];
+      if (i != j) ++rptr[j + 1];
+   }
+   for (int i = 0; i <= n; ++i) rptr[i + 1] += rptr[i];
+   std::vector<int> rent(std::max(rptr[n + 1], 1)), rcol(std::max(rptr[n + 1], 1)), fill(rptr.begin() + 1, rptr.end());
+   for (int l = 0; l < ne; ++l) {          // input order within every row: the order of the reference's loop
+      const int i = row[l], j = col[l];
+      if (std::min(i, j) < 1 || std::max(i, j) > n) continue;
+      rent[fill[i - 1]] = l; rcol[fill[i - 1]++] = j - 1;
+      if (i != j) { rent[fill[j - 1]] = l; rcol[fill[j - 1]++] = i - 1; }
+   }
+   cudaFree(d_um_rptr); cudaFree(d_um_rent); cudaFree(d_um_rcol); cudaFree(d_rb); cudaFree(d_rx); cudaFree(d_rr); cudaFree(d_rnorm);
+   d_um_rptr = d_um_rent = d_um_rcol = nullptr; d_rb = d_rx = d_rr = nullptr; d_rnorm = nullptr;
+   CU(cudaMalloc(&d_um_rptr, sizeof(int) * (n + 1)));
+   CU(cudaMalloc(&d_um_rent, sizeof(int) * rent.size()));
+   CU(cudaMalloc(&d_um_rcol, sizeof(int) * rcol.size()));
+   CU(cudaMalloc(&d_rb, sizeof(double) * std::max(n, 1)));
+   CU(cudaMalloc(&d_rx, sizeof(double) * std::max(n, 1)));
+   CU(cudaMalloc(&d_rr, sizeof(double) * std::max(n, 1)));
+   CU(cudaMalloc(&d_rnorm, sizeof(unsigned long long)));
+   CU(cudaMemcpy(d_um_rptr, rptr.data() + 1, sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+   CU(cudaMemcpy(d_um_rent, rent.data(), sizeof(int) * rent.size(), cudaMemcpyHostToDevice));
+   CU(cudaMemcpy(d_um_rcol, rcol.data(), sizeof(int) * rcol.size(), cudaMemcpyHostToDevice));
+   um_ne = ne;
+   return 0;
+}
+
+// x: b on entry, the refined solution on return (host).  x_0 = 0, r_0 = b; repeat { solve A dx = r; x += dx; r = b - A x }
+// until max |r_i| < max(stop_abs, stop_rel max |b_i|) or max_ref refinements (sls.f90:4806-4945)
+int Numeric::solve_refined(double* x, int max_ref, double stop_abs, double stop_rel, int* nref, double* seconds) {
+   if (!have) return SSIDS_ERROR_CALL_SEQUENCE;
+   if (um_ne < 0 || um_ne != vm_ne || !d_uval) return SSIDS_ERROR_CALL_SEQUENCE;   // needs set_user_matrix + factor_mapped
+   CU(cudaSetDevice(P->device));
+   const int n = P->sym->n, nb = (n + 255) / 256;
+   double bnorm = 0.0;
+   for (int i = 0; i < n; ++i) bnorm = std::max(bnorm, std::fabs(x[i]));
+   const double stop = std::max(stop_abs, stop_rel * bnorm);
+   CU(cudaMemcpyAsync(d_rb, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(d_rr, d_rb, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+   CU(cudaMemsetAsync(d_rx, 0, sizeof(double) * n, st));
+   CU(cudaStreamSynchronize(st));
+   double total = 0.0;
+   int it = 0, flag = 0;
+   for (it = 0; it <= max_ref; ++it) {
+      double secs = 0.0;
+      int64_t nl = 0;
+      flag = solve(0, 1, d_rr, n, true, &secs, &nl);
+      total += secs;
+      if (flag < 0) break;
+      k_axpy1<<<nb, 256, 0, st>>>(d_rx, d_rr, n);
+      if (it == max_ref) break;
+      k_residual<<<nb, 256, 0, st>>>(d_rr, d_rb, d_rx, d_uval, d_um_rptr, d_um_rent, d_um_rcol, n);
+      CU(cudaMemsetAsync(d_rnorm, 0, sizeof(unsigned long long), st));
+      k_maxabs<<<148, 256, 0, st>>>(d_rr, n, d_rnorm);
+      unsigned long long bits = 0;
+      CU(cudaMemcpyAsync(&bits, d_rnorm, sizeof(bits), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      double rn;
+      std::memcpy(&rn, &bits, sizeof(rn));
+      if (rn < stop) break;
+   }
+   if (nref) *nref = std::min(it, max_ref);
+   if (flag >= 0) {
+      CU(cudaMemcpyAsync(x, d_rx, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+   }
+   if (seconds) *seconds = total;
+   return flag;
+}
+
+int numeric_set_user_matrix(Numeric* n, int ne, const int* row, const int* col) { return n->set_user_matrix(ne, row, col); }
+int numeric_solve_refined(Numeric* n, double* x, int max_ref, double stop_abs, double stop_rel, int* nref, double* seconds) {
+   return n->solve_refined(x, max_ref, stop_abs, stop_rel, nref, seconds);
+}
 int numeric_set_value_map(Numeric* n, int ne, const int* maps) { return n->set_value_map(ne, maps); }
 int numeric_factor_mapped(Numeric* n, int ne, const double* uval, const FactorOptions& o, FactorStats& s) {
    int rc = n->gather_values(ne, uval);

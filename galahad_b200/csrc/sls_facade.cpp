@@ -27,8 +27,7 @@ struct SlsData {
    sls_inform_type inform;
    int n = 0, ne = 0;          // user's matrix
    int type = 0;               // 0 coordinate, 1 sparse_by_rows, 2 dense
-   std::vector<int> urow, ucol;   // user's entries as 1-based coordinates (kept for refinement)
-   std::vector<double> uval;
+   std::vector<int> urow, ucol;   // user's entries as 1-based coordinates (uploaded for the residuals of the refinement loop)
    std::vector<int> maps, ptr, col, order;   // 1-based, as data%MAPS, data%matrix%PTR/COL, data%ORDER
    std::vector<double> val;
    void* akeep = nullptr;
@@ -266,7 +265,6 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
    double t0 = now();
    const int n = d->n;
    (void)n;
-   d->uval.assign(val, val + d->ne);          // kept for the residuals of the refinement loop
    // pivot_control 2/3 -> must_be_definite -> Cholesky path (sls.f90:2227-2228, 4282)
    const int posdef = (d->control.pivot_control == 2 || d->control.pivot_control == 3) ? 1 : 0;
    b200ldlt_options o = to_solver(d->control);
@@ -275,6 +273,7 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
    // uploaded once per analyse
    if (!d->map_set) {
       int mf = b200ldlt_set_value_map(d->akeep, &d->fkeep, d->ne, d->maps.data(), &o, &si);
+      if (mf >= 0) mf = b200ldlt_set_user_matrix(d->akeep, &d->fkeep, d->ne, d->urow.data(), d->ucol.data(), &o, &si);
       d->map_set = mf >= 0;
    }
    if (d->map_set) b200ldlt_factor_mapped(d->akeep, &d->fkeep, posdef, d->ne, val, &o, &si);
@@ -313,33 +312,16 @@ void sls_solve_system(void** data, int* status, int n, double sol[]) {
    if (d->control.max_iterative_refinements <= 0) {
       flag = solver_solve(d, 0, sol);
    } else {
-      // SLS_solve_ir (sls.f90:4751-4947): x = 0; r = b; repeat { solve A dx = r; x += dx; r = b - A x }
-      std::vector<double> b(sol, sol + n), x(n, 0.0), r(sol, sol + n);
-      double bnorm = 0;
-      for (int i = 0; i < n; ++i) bnorm = std::max(bnorm, std::fabs(b[i]));
-      const double stop = std::max(d->control.acceptable_residual_absolute, d->control.acceptable_residual_relative * bnorm);
-      flag = 0;
-      for (int it = 0; it <= d->control.max_iterative_refinements; ++it) {
-         inf.iterative_refinements = it;
-         flag = solver_solve(d, 0, r.data());
-         if (flag < 0) break;
-         for (int i = 0; i < n; ++i) x[i] += r[i];
-         if (it < d->control.max_iterative_refinements) {
-            r = b;
-            for (int l = 0; l < d->ne; ++l) {
-               int i = d->urow[l], j = d->ucol[l];
-               if (std::min(i, j) >= 1 && std::max(i, j) <= n) {
-                  double v = d->uval[l];
-                  r[i - 1] -= v * x[j - 1];
-                  if (i != j) r[j - 1] -= v * x[i - 1];
-               }
-            }
-            double rn = 0;
-            for (int i = 0; i < n; ++i) rn = std::max(rn, std::fabs(r[i]));
-            if (rn < stop) break;
-         }
-      }
-      std::copy(x.begin(), x.end(), sol);
+      // SLS_solve_ir (sls.f90:4751-4947): x = 0; r = b; repeat { solve A dx = r; x += dx; r = b - A x }, on the
+      // device: b goes up once, x comes back once, the residual uses the entries uploaded by factorize
+      b200ldlt_options o = to_solver(d->control);
+      b200ldlt_inform si;
+      int nref = 0;
+      flag = b200ldlt_solve_refined(d->akeep, d->fkeep, sol, d->control.max_iterative_refinements,
+                                    d->control.acceptable_residual_absolute, d->control.acceptable_residual_relative, &nref, &o, &si);
+      inf.iterative_refinements = nref;
+      d->inform.b200ldlt_inform.time_solve = si.time_solve;
+      d->inform.time.solve_external += si.time_solve;
    }
    inf.status = flag >= 0 ? GALAHAD_OK : (flag == -11 ? GALAHAD_ERROR_PERMUTATION : GALAHAD_ERROR_TECHNICAL);
    inf.time.clock_solve = now() - t0;

@@ -129,6 +129,16 @@ int b200ldlt_set_value_map(void *akeep, void **fkeep, int ne, const int *maps, c
 int b200ldlt_factor_mapped(void *akeep, void **fkeep, int posdef, int ne, const double *user_val,
                            const b200ldlt_options *opt, b200ldlt_inform *inf);
 
+/* Iterative refinement on the device (the loop of SLS_solve_ir, sls.f90:4751-4947): x_0 = 0, r_0 = b; repeat
+ * { solve A dx = r; x += dx; r = b - A x } until max|r_i| < max(stop_absolute, stop_relative max|b_i|) or
+ * max_refinements.  The residual uses the caller's own entries: set_user_matrix (once per analyse; 1-based
+ * coordinates exactly as given to SLS, out-of-range entries ignored, duplicates kept) and the values of the
+ * latest b200ldlt_factor_mapped.  x: b on entry, the solution on return (host). */
+int b200ldlt_set_user_matrix(void *akeep, void **fkeep, int ne, const int *row, const int *col,
+                             const b200ldlt_options *opt, b200ldlt_inform *inf);
+int b200ldlt_solve_refined(void *akeep, void *fkeep, double *x, int max_refinements, double stop_absolute,
+                           double stop_relative, int *refinements, const b200ldlt_options *opt, b200ldlt_inform *inf);
+
 /* Solve with nrhs right-hand sides held by columns in HOST x(ldx,nrhs), overwritten by the solution.
  * job as B200LDLT_JOB_*. */
 int b200ldlt_solve(void *akeep, void *fkeep, int job, int nrhs, double *x, int ldx,

@@ -139,3 +139,61 @@ def test_kkt_through_sls_with_nd_order():
     b = P.full_from_lower(n, prob["ptr"], prob["row"], prob["val"]) @ xs
     st, x = s.solve_system(b)
     assert P.backward_error(prob, x, b) <= 1e-14
+
+
+@pytest.mark.gpu
+def test_iterative_refinement_on_device():
+    """SLS_solve_ir (sls.f90:4751-4947) runs on the device: same iterates as the loop written out with
+    unrefined solves and a residual over the caller's entries (here with duplicates and a relaxed pivot
+    threshold so that refinement has something to do), iteration count reported, early stop honoured."""
+    prob = P.kkt_grid_problem(8, dlo=1e-10)
+    n = prob["n"]
+    colidx = np.repeat(np.arange(n), np.diff(prob["ptr"]))
+    rng = np.random.default_rng(11)
+    # split a tenth of the entries into two duplicates each
+    row, col, val = prob["row"].copy(), colidx.copy(), prob["val"].copy()
+    pick = rng.choice(row.size, row.size // 10, replace=False)
+    row = np.concatenate([row, row[pick]]); col = np.concatenate([col, col[pick]])
+    half = val[pick] * rng.uniform(0.2, 0.8, pick.size)
+    val[pick] -= half
+    val = np.concatenate([val, half])
+    q = rng.permutation(row.size)
+    row, col, val = row[q], col[q], val[q]
+    A = P.full_from_lower(n, prob["ptr"], prob["row"], prob["val"])
+    b = A @ rng.uniform(-1, 1, n)
+
+    def residual(x):                      # the reference's loop over the entries, in input order
+        r = b.copy()
+        for l in range(row.size):
+            i, j, v = row[l], col[l], val[l]
+            r[i] -= v * x[j]
+            if i != j:
+                r[j] -= v * x[i]
+        return r
+
+    s = SLS()
+    s.control.f_indexing = False
+    s.control.relative_pivot_tolerance = 1e-8
+    assert s.analyse_matrix(n, "coordinate", row.size, row, col, perm=prob["order"]) == 0
+    assert s.factorize_matrix(val) == 0
+    st, x0 = s.solve_system(b)                                     # no refinement
+    # two refinements written out with plain solves
+    x = x0.copy()
+    for _ in range(2):
+        st, dx = s.solve_system(residual(x))
+        x = x + dx
+    s.control.max_iterative_refinements = 2
+    s.control.acceptable_residual_relative = 0.0
+    s.control.acceptable_residual_absolute = 0.0
+    s.reset_control()
+    st, xr = s.solve_system(b)
+    assert st == 0 and s.information().iterative_refinements == 2
+    assert np.abs(xr - x).max() <= 1e-13 * max(1.0, np.abs(x).max())
+    assert np.abs(residual(xr)).max() <= np.abs(residual(x0)).max()
+    # a generous tolerance stops after the first solve
+    s.control.acceptable_residual_relative = 1.0
+    s.reset_control()
+    st, x1 = s.solve_system(b)
+    assert st == 0 and s.information().iterative_refinements == 0
+    assert np.array_equal(x1, x0)
+    s.terminate()
