@@ -6,6 +6,7 @@
 #include "analyse.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <limits>
 
@@ -530,6 +531,31 @@ void find_subtree_partition(Symbolic& sym, int ndev, double max_load_inbalance, 
    if (nn == 0) { sym.nparts = 1; sym.part = {0, 0}; sym.exec_loc = {-1}; }
 }
 
+
+int equilib_scale_sym(int n, const int64_t* ptr, const int* row, const double* val, double* scaling,
+                      int max_iterations, float tol) {
+   std::vector<double> maxentry(std::max(n, 1));
+   for (int i = 0; i < n; ++i) scaling[i] = 1.0;
+   int itr = 1;
+   for (; itr <= max_iterations; ++itr) {
+      // maximum entry in each row and column; the matrix is symmetric but only half of it is held
+      std::fill(maxentry.begin(), maxentry.end(), 0.0);
+      for (int c = 0; c < n; ++c)
+         for (int64_t j = ptr[c]; j < ptr[c + 1]; ++j) {
+            const int r = row[j];
+            const double v = std::fabs(scaling[r] * val[j] * scaling[c]);
+            maxentry[r] = std::max(maxentry[r], v);
+            maxentry[c] = std::max(maxentry[c], v);
+         }
+      // update the scaling (empty columns keep theirs)
+      for (int i = 0; i < n; ++i) if (maxentry[i] > 0) scaling[i] = scaling[i] / std::sqrt(maxentry[i]);
+      double worst = 0.0;
+      for (int i = 0; i < n; ++i) worst = std::max(worst, std::fabs(1 - maxentry[i]));
+      if (n > 0 && worst < (double)tol) break;
+      if (n == 0) break;
+   }
+   return itr - 1;      // inform%iterations
+}
 
 void proportional_mapping(Symbolic& sym, int ndev) {
    const int nn = sym.nnodes;

@@ -73,6 +73,13 @@ enum : int {
 // Returns sym.flag.  nemin < 1 selects the reference default (32).
 int analyse(int n, const int64_t* ptr, const int* row, const int* order, int nemin, Symbolic& sym);
 
+// Symmetric infinity-norm equilibration (options%scaling = 4 of SSIDS): restatement of inf_norm_equilib_sym,
+// src/spral/scaling.f90:480-521 (Algorithm 1 of Knight, Ruiz & Ucar), with the reference's defaults
+// max_iterations = 10, tol = 1e-8 (a default REAL there, hence the float).  ptr/row: lower triangle by columns,
+// 0-based.  Same operations in the same order; max is order-independent, so the result is the reference's bits.
+int equilib_scale_sym(int n, const int64_t* ptr, const int* row, const double* val, double* scaling,
+                      int max_iterations = 10, float tol = 1e-8f);
+
 // Proportional mapping (the multi-level generalisation of the subtree partition: SURVEY section 8e): the root
 // gets all devices, the devices of a node are split among its children in proportion to their subtree flops,
 // a subtree that is left with one device is a leaf part of that device; a node is owned by the first device of

@@ -216,6 +216,36 @@ int b200ldlt_set_value_map(void* akeep, void** fkeep, int ne, const int* maps, c
    if (int rc = ensure_fkeep(ak, fkeep, opt, inf)) return rc;
    return inf->flag = numeric_set_value_map(static_cast<Fkeep*>(*fkeep)->num, ne, maps);
 }
+// ssids_factor with its optional SCALE argument and options%scaling (ssids.f90:900-1030)
+int b200ldlt_factor_scaled(void* akeep, void** fkeep, int posdef, const double* val, double* scale,
+                           const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   *inf = ak->inf_analyse;
+   const int sc = opt->reserved[2];
+   if (sc >= 1 && sc <= 3) return inf->flag = SSIDS_ERROR_UNIMPLEMENTED;   // Hungarian / auction / matching-order scalings
+   if (ak->sym.n > 0 && !val) return inf->flag = SSIDS_ERROR_VAL;
+   if (int rc = ensure_fkeep(ak, fkeep, opt, inf)) return rc;
+   Fkeep* fk = static_cast<Fkeep*>(*fkeep);
+   const int n = ak->sym.n;
+   int rc = 0;
+   if (sc >= 4) {                       // norm equilibration, computed here, returned in `scale` if given
+      std::vector<double> s(std::max(n, 1));
+      equilib_scale_sym(n, ak->sym.ptr.data(), ak->sym.row.data(), val, s.data());
+      if (scale) std::copy(s.begin(), s.begin() + n, scale);
+      rc = numeric_set_scaling(fk->num, s.data());
+   } else {
+      rc = numeric_set_scaling(fk->num, scale);   // user-supplied (original variable order) or none
+   }
+   if (rc) return inf->flag = rc;
+   return factor_common(akeep, fkeep, posdef, val, false, opt, inf);
+}
+int b200ldlt_equilib_scale(int n, const int64_t* ptr, const int* row, const double* val, double* scaling, int* iterations) {
+   if (n < 0 || !ptr || (n > 0 && (!row || !val || !scaling))) return SSIDS_ERROR_CALL_SEQUENCE;
+   const int it = equilib_scale_sym(n, ptr, row, val, scaling);
+   if (iterations) *iterations = it;
+   return 0;
+}
 int b200ldlt_set_user_matrix(void* akeep, void** fkeep, int ne, const int* row, const int* col,
                              const b200ldlt_options* opt, b200ldlt_inform* inf) {
    if (!akeep || !fkeep || !opt || !inf || ne < 0 || (ne > 0 && (!row || !col))) return SSIDS_ERROR_CALL_SEQUENCE;

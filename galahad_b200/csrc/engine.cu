@@ -450,6 +450,13 @@ __global__ void k_gather_dup(double* __restrict__ val, const double* __restrict_
    val[dup_dst[t]] = acc;
 }
 
+// a_ij <- s_i a_ij s_j on the values of the lower triangle (add_a_block with scaling, assemble.hxx:54-66)
+__global__ void k_scale_values(double* __restrict__ val, const int* __restrict__ rowi, const int* __restrict__ coli,
+                               const double* __restrict__ scale, int64_t nz) {
+   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (k < nz) val[k] = __dmul_rn(__dmul_rn(scale[rowi[k]], val[k]), scale[coli[k]]);
+}
+
 // Iterative refinement on the device (SLS_solve_ir, sls.f90:4751-4947).  The residual uses the caller's entries
 // (coordinates + the values of the latest factor_mapped), row by row in input order, without contraction into
 // FMAs: the same sequence of operations as the reference's loop over the entries.
@@ -781,6 +788,11 @@ class Numeric {
    int *d_vm_src = nullptr, *d_vm_dst = nullptr, *d_vm_dup_dst = nullptr, *d_vm_dup_ptr = nullptr, *d_vm_dup_src = nullptr;
    int vm_ne = 0, vm_nset = 0, vm_ndup = 0;
    int set_value_map(int ne, const int* maps);
+   // scaling of the factorisation (variable order), the A pattern as (row, column) per entry
+   double* d_scale = nullptr;
+   int *d_a_rowi = nullptr, *d_a_coli = nullptr;
+   bool scaled = false;
+   int set_scaling(const double* scale);
    // refinement: the caller's entries by row (set_user_matrix), work vectors
    int *d_um_rptr = nullptr, *d_um_rent = nullptr, *d_um_rcol = nullptr;
    double *d_rb = nullptr, *d_rx = nullptr, *d_rr = nullptr;
@@ -825,7 +837,7 @@ class Numeric {
       cudaSetDevice(P->device);
       fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release(); bar.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
-      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_um_rptr); cudaFree(d_um_rent); cudaFree(d_um_rcol); cudaFree(d_rb); cudaFree(d_rx); cudaFree(d_rr); cudaFree(d_rnorm);
+      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_scale); cudaFree(d_a_rowi); cudaFree(d_a_coli); cudaFree(d_um_rptr); cudaFree(d_um_rent); cudaFree(d_um_rcol); cudaFree(d_rb); cudaFree(d_rx); cudaFree(d_rr); cudaFree(d_rnorm);
       cudaFree(d_part); cudaFree(d_val); cudaFree(d_uval); cudaFree(d_vm_src); cudaFree(d_vm_dst); cudaFree(d_vm_dup_dst); cudaFree(d_vm_dup_ptr); cudaFree(d_vm_dup_src); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
@@ -1041,6 +1053,10 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       if (val != d_val) CU(cudaMemcpyAsync(d_val, val, sizeof(double) * sym.nz, cudaMemcpyDeviceToDevice, st));
    } else {
       CU(cudaMemcpyAsync(d_val, val, sizeof(double) * sym.nz, cudaMemcpyHostToDevice, st));
+   }
+   if (phase <= 1 && scaled && sym.nz > 0) {
+      k_scale_values<<<(unsigned)((sym.nz + 255) / 256), 256, 0, st>>>(d_val, d_a_rowi, d_a_coli, d_scale, sym.nz);
+      ++launches;
    }
    CU(cudaEventRecord(ev1, st));
 
@@ -1742,7 +1758,7 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
       double* dx = d_x;
       if (on_device) dx = xj;
       else CU(cudaMemcpyAsync(d_x, xj, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-      if (n > 0) { k_permute_in<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, n); ++nlaunch; }
+      if (n > 0) { k_permute_in<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, (scaled && (job == 0 || job == 1)) ? d_scale : nullptr, n); ++nlaunch; }
       const bool fwd = (job == 0 || job == 1), bwd = (job == 0 || job == 3 || job == 4);
       const bool diag = !posdef && (job == 0 || job == 2 || job == 4);
       // posdef: LL^T semantics with L_chol = L sqrt(D); sqrt(D^-1) is folded into each sweep so
@@ -1750,7 +1766,7 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
       if (fwd) sweep_fwd(-1, nlaunch);
       if (diag && !bwd && nn > 0) { k_solve_diag<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, d_xp, nn); ++nlaunch; }
       if (bwd) sweep_bwd(-1, diag, nlaunch);
-      if (n > 0) { k_permute_out<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, n); ++nlaunch; }
+      if (n > 0) { k_permute_out<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, (scaled && (job == 0 || job == 3 || job == 4)) ? d_scale : nullptr, n); ++nlaunch; }
       if (!on_device) CU(cudaMemcpyAsync(xj, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
    }
    CU(cudaEventRecord(ev1, st));
@@ -1899,13 +1915,13 @@ int Numeric::dist_solve(int step, double* d_xio, const double* src) {
    if (rc) return rc;
    (void)src;
    if (step == 1) {                                   // right-hand side into pivot order
-      k_permute_in<<<nb, 256, 0, st>>>(d_xio, d_xp, P->d_order, n);
+      k_permute_in<<<nb, 256, 0, st>>>(d_xio, d_xp, P->d_order, scaled ? d_scale : nullptr, n);
    } else if (step >= 100 && step < 200) {            // forward sweep over this rank's fronts of stage step - 100
       sweep_fwd(step - 100, nl);
    } else if (step >= 200 && step < 300) {            // diagonal + backward sweep of stage step - 200
       sweep_bwd(step - 200, !posdef, nl);
    } else if (step == 4) {                            // the whole solution in the caller's order
-      k_permute_out<<<nb, 256, 0, st>>>(d_xio, d_xp, P->d_order, n);
+      k_permute_out<<<nb, 256, 0, st>>>(d_xio, d_xp, P->d_order, scaled ? d_scale : nullptr, n);
    } else {
       return SSIDS_ERROR_JOB_OOR;
    }
@@ -2001,6 +2017,30 @@ int Numeric::gather_values(int ne, const double* uval) {
    return 0;
 }
 
+// scale: n factors in variable order for the next factorisations and their solves, or null for none
+int Numeric::set_scaling(const double* scale) {
+   int rc = init();
+   if (rc) return rc;
+   CU(cudaSetDevice(P->device));
+   const Symbolic& sym = *P->sym;
+   if (!scale) { scaled = false; return 0; }
+   if (!d_scale) CU(cudaMalloc(&d_scale, sizeof(double) * std::max(sym.n, 1)));
+   if (!d_a_rowi) {
+      std::vector<int> coli((size_t)std::max<int64_t>(sym.nz, 1));
+      for (int c = 0; c < sym.n; ++c)
+         for (int64_t j = sym.ptr[c]; j < sym.ptr[c + 1]; ++j) coli[j] = c;
+      CU(cudaMalloc(&d_a_rowi, sizeof(int) * std::max<int64_t>(sym.nz, 1)));
+      CU(cudaMalloc(&d_a_coli, sizeof(int) * std::max<int64_t>(sym.nz, 1)));
+      if (sym.nz > 0) {
+         CU(cudaMemcpy(d_a_rowi, sym.row.data(), sizeof(int) * sym.nz, cudaMemcpyHostToDevice));
+         CU(cudaMemcpy(d_a_coli, coli.data(), sizeof(int) * sym.nz, cudaMemcpyHostToDevice));
+      }
+   }
+   CU(cudaMemcpy(d_scale, scale, sizeof(double) * sym.n, cudaMemcpyHostToDevice));
+   scaled = true;
+   return 0;
+}
+
 int Numeric::set_user_matrix(int ne, const int* row, const int* col) {
    int rc = init();
    if (rc) return rc;
@@ -2080,6 +2120,7 @@ int Numeric::solve_refined(double* x, int max_ref, double stop_abs, double stop_
    return flag;
 }
 
+int numeric_set_scaling(Numeric* n, const double* scale) { return n->set_scaling(scale); }
 int numeric_set_user_matrix(Numeric* n, int ne, const int* row, const int* col) { return n->set_user_matrix(ne, row, col); }
 int numeric_solve_refined(Numeric* n, double* x, int max_ref, double stop_abs, double stop_rel, int* nref, double* seconds) {
    return n->solve_refined(x, max_ref, stop_abs, stop_rel, nref, seconds);

@@ -41,6 +41,7 @@ int plan_device(const Plan*);
 Numeric* numeric_create(Plan*);
 void numeric_destroy(Numeric*);
 int numeric_set_value_map(Numeric*, int ne, const int* maps);
+int numeric_set_scaling(Numeric*, const double* scale);
 int numeric_set_user_matrix(Numeric*, int ne, const int* row, const int* col);
 int numeric_solve_refined(Numeric*, double* x, int max_ref, double stop_abs, double stop_rel, int* nref, double* seconds);
 int numeric_factor_mapped(Numeric*, int ne, const double* uval, const FactorOptions&, FactorStats&);

@@ -23,13 +23,17 @@ __device__ __forceinline__ int row_gidx(const FrontDev& f, const int* rl, int r)
    return r < f.n ? f.perm[r] : rl[f.ncol + (r - f.n)];
 }
 
-__global__ void k_permute_in(const double* __restrict__ x, double* __restrict__ xp, const int* __restrict__ order, int n) {
+// scale: the factorisation's scaling in variable order or null (fkeep.F90:247-310: scaled on the way in for the
+// jobs that start with the forward sweep, on the way out for those that end with the backward sweep)
+__global__ void k_permute_in(const double* __restrict__ x, double* __restrict__ xp, const int* __restrict__ order,
+                             const double* __restrict__ scale, int n) {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n && order[i] >= 0) xp[order[i]] = x[i];
+   if (i < n && order[i] >= 0) xp[order[i]] = scale ? x[i] * scale[i] : x[i];
 }
-__global__ void k_permute_out(double* __restrict__ x, const double* __restrict__ xp, const int* __restrict__ order, int n) {
+__global__ void k_permute_out(double* __restrict__ x, const double* __restrict__ xp, const int* __restrict__ order,
+                              const double* __restrict__ scale, int n) {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n && order[i] >= 0) x[i] = xp[order[i]];
+   if (i < n && order[i] >= 0) x[i] = scale ? xp[order[i]] * scale[i] : xp[order[i]];
 }
 
 // xw = [b(pivot rows); 0] + sum over children (in child order) of their update vectors

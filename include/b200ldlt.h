@@ -65,7 +65,8 @@ typedef struct b200ldlt_options {
    int device;          /* CUDA device ordinal, -1: current device */
    int panel_width;     /* reserved; 0 = engine default */
    int reserved[7];     /* reserved[0] = 1: profile mode (CUDA events around every trailing update);
-                           reserved[1] = 1: do not fuse chains (engine tree == reference tree) */
+                           reserved[1] = 1: do not fuse chains (engine tree == reference tree);
+                           reserved[2]: ssids options%scaling for b200ldlt_factor_scaled */
 } b200ldlt_options;
 
 /* Inform: shaped like ssids_inform (src/ssids/inform.f90:17-49). */
@@ -128,6 +129,18 @@ int b200ldlt_set_value_map(void *akeep, void **fkeep, int ne, const int *maps, c
                            b200ldlt_inform *inf);
 int b200ldlt_factor_mapped(void *akeep, void **fkeep, int posdef, int ne, const double *user_val,
                            const b200ldlt_options *opt, b200ldlt_inform *inf);
+
+/* Factorisation with scaling: ssids_factor's optional SCALE argument and options%scaling (ssids.f90:900-1030),
+ * the option in opt->reserved[2]:  <= 0: `scale` (n factors, original variable order) is used if not NULL, else no
+ * scaling;  >= 4: symmetric infinity-norm equilibration (inf_norm_equilib_sym, src/spral/scaling.f90:480-521)
+ * computed from `val` and returned in `scale` if not NULL;  1..3 (Hungarian, auction, matching-order scalings): -98,
+ * not implemented.  The scaled matrix S A S is factorised; solves scale on the way in (jobs 0, 1) and on the way out
+ * (jobs 0, 3, 4) exactly as fkeep.F90:247-310.  A later b200ldlt_factor / _factor_mapped keeps the scaling that was
+ * set last; pass opt->reserved[2] = 0 and scale = NULL here to clear it.  `val` is a host pointer.
+ * b200ldlt_equilib_scale: the equilibration alone (0-based lower triangle by columns). */
+int b200ldlt_factor_scaled(void *akeep, void **fkeep, int posdef, const double *val, double *scale,
+                           const b200ldlt_options *opt, b200ldlt_inform *inf);
+int b200ldlt_equilib_scale(int n, const int64_t *ptr, const int *row, const double *val, double *scaling, int *iterations);
 
 /* Iterative refinement on the device (the loop of SLS_solve_ir, sls.f90:4751-4947): x_0 = 0, r_0 = b; repeat
  * { solve A dx = r; x += dx; r = b - A x } until max|r_i| < max(stop_absolute, stop_relative max|b_i|) or

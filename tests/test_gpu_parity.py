@@ -269,3 +269,44 @@ def test_value_gather_on_device_matches_host_gather():
     assert s2.factor_mapped(user2) >= 0
     f3, x3 = s2.solve(b)
     assert f3 == 0 and not np.array_equal(x3, x2)
+
+
+def test_scaled_factorisation():
+    """ssids_factor's SCALE argument and options%scaling = 4 (ssids.f90:900-1030, fkeep.F90:247-310): a
+    symmetrically mis-scaled KKT matrix factorised with user-supplied factors that undo the damage gives the
+    pivot sequence statistics of the well-scaled matrix and solves the mis-scaled system; equilibration gives
+    a clean factorisation too; partial solves compose; scalings 1-3 are reported as not implemented."""
+    rng = np.random.default_rng(21)
+    prob = P.kkt_grid_problem(8)
+    n, ptr, row = prob["n"], prob["ptr"], prob["row"]
+    col = np.repeat(np.arange(n), np.diff(ptr))
+    d = 10.0 ** rng.uniform(-5, 5, n)
+    bad = dict(prob, val=prob["val"] * d[row] * d[col])                 # D A D
+    A = P.full_from_lower(n, ptr, row, bad["val"])
+    xs = rng.uniform(-1, 1, n)
+    b = A @ xs
+    good, flag = gpu_factor(prob)
+    # user-supplied scaling 1/d: the engine factorises exactly the well-scaled matrix again (up to rounding of d * (1/d))
+    s = Solver()
+    assert s.analyse(n, ptr, row, prob["order"]) >= 0
+    flag, sc = s.factor_scaled(bad["val"], scale=1.0 / d)
+    assert flag >= 0
+    assert (s.inform.num_neg, s.inform.num_delay) == (good.inform.num_neg, good.inform.num_delay)
+    f, x = s.solve(b)
+    assert f == 0 and P.backward_error(bad, x, b) <= 1e-14
+    f, y = s.solve(b, job=1)
+    f, z = s.solve(y, job=4)
+    assert np.abs(z - x).max() <= 1e-12 * np.abs(x).max()
+    # equilibration computed by the library, returned to the caller
+    flag, sc = s.factor_scaled(bad["val"], scaling=4)
+    assert flag >= 0 and sc is not None and sc.min() > 0 and s.inform.num_neg == prob["inertia"][1]
+    f, x4 = s.solve(b)
+    assert f == 0 and P.backward_error(bad, x4, b) <= 1e-14
+    flag, _ = s.factor_scaled(bad["val"], scaling=2)
+    assert flag == -98
+    # clearing the scaling restores the plain path
+    flag, _ = s.factor_scaled(prob["val"], scaling=0)
+    b0 = P.full_from_lower(n, ptr, row, prob["val"]) @ xs
+    f, x0 = s.solve(b0)
+    fg, xg = good.solve(b0)
+    assert flag >= 0 and np.array_equal(x0, xg)

@@ -94,3 +94,53 @@ def test_singular_matrix_is_flagged():
     assert st["flag"] == 7 and st["num_zero"] == 1          # SSIDS_WARNING_FACT_SINGULAR
     st = Oracle(sym, 3, small=1e-14, action=False).factor(val, False)
     assert st["flag"] == -5                                 # SSIDS_ERROR_SINGULAR
+
+
+def _equilib_numpy(n, ptr, row, val, max_iterations=10, tol=np.float32(1e-8)):
+    """Independent restatement of inf_norm_equilib_sym (src/spral/scaling.f90:480-521), vectorised: the
+    per-row maxima are order-independent, every other operation is elementwise, so the bits must agree."""
+    col = np.repeat(np.arange(n), np.diff(ptr))
+    s = np.ones(n)
+    it = 0
+    for it in range(1, max_iterations + 1):
+        v = np.abs(s[row] * val * s[col])
+        m = np.zeros(n)
+        np.maximum.at(m, row, v)
+        np.maximum.at(m, col, v)
+        nzr = m > 0
+        s[nzr] = s[nzr] / np.sqrt(m[nzr])
+        if np.abs(1 - m).max() < float(tol):
+            break
+    else:
+        it = max_iterations + 1
+    return s, it - 1
+
+
+def test_equilibration_scaling_matches_restatement():
+    """options%scaling = 4: the C++ restatement behind b200ldlt_factor_scaled against the numpy one, bit for
+    bit, on badly scaled KKT matrices; and the property the algorithm is for: every row of |S A S| has
+    infinity norm 1 to the tolerance once it has converged."""
+    import ctypes as C
+    from galahad_b200 import _lib
+    from galahad_b200 import problems as P
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    for prob in (P.kkt_grid_problem(6, dlo=1e-10), P.random_sym_problem(300, 0.02, "indef", seed=9)):
+        n, ptr, row = prob["n"], np.asarray(prob["ptr"], np.int64), np.asarray(prob["row"], np.int32)
+        d = 10.0 ** rng.uniform(-6, 6, n)                      # destroy the scaling symmetrically
+        col = np.repeat(np.arange(n), np.diff(ptr))
+        val = prob["val"] * d[row] * d[col]
+        s = np.zeros(n)
+        it = C.c_int()
+        assert L.b200ldlt_equilib_scale(n, ptr.ctypes.data_as(C.POINTER(C.c_int64)), row.ctypes.data_as(C.POINTER(C.c_int)),
+                                        val.ctypes.data_as(C.POINTER(C.c_double)), s.ctypes.data_as(C.POINTER(C.c_double)),
+                                        C.byref(it)) == 0
+        s_np, it_np = _equilib_numpy(n, ptr, row, val)
+        assert it.value == it_np and np.array_equal(s, s_np)
+        # more iterations: converged scaling equilibrates the rows
+        s2, it2 = _equilib_numpy(n, ptr, row, val, max_iterations=200)
+        v = np.abs(s2[row] * val * s2[col])
+        m = np.zeros(n)
+        np.maximum.at(m, row, v)
+        np.maximum.at(m, col, v)
+        assert it2 < 200 and np.abs(1 - m).max() < 1e-6
