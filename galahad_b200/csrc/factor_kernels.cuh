@@ -887,10 +887,14 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    const int m = f.m;
    const int k0 = f.urec[par][0], cbeg = k0 + kc, cend = m;
    if (kc <= 0 || cbeg >= cend) return;
-   const int tjs = (f.urec[par][2] - cbeg + TN - 1) / TN;   // column tiles [0, tjs) form the strip
+   // The tile grid starts at the even index org <= cbeg: every row offset of the operands and of C is then a
+   // multiple of 16 bytes (ldl, ldc are even, C is shifted by n & 1), so all operand loads are 16-byte copies.
+   // When cbeg is odd the grid has one extra leading row and column, masked in the first row / column of tiles.
+   const int org = cbeg & ~1;
+   const int tjs = (f.urec[par][2] - org + TN - 1) / TN;   // column tiles [0, tjs) form the strip
    const int kofs = 0;
-   const int ntr = (m - cbeg + TM - 1) / TM;
-   const int ntc = (cend - cbeg + TN - 1) / TN;
+   const int ntr = (m - org + TM - 1) / TM;
+   const int ntc = (cend - org + TN - 1) / TN;
    extern __shared__ double smem[];
    double* As = smem;                       // [2][BK][LDA]
    double* Bs = smem + 2 * BK * LDA;        // [2][BK][LDB]
@@ -903,7 +907,8 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    double* const Cp = f.C;
    const double* Abase = Lp + (size_t)k0 * ldl;
    const double* Bbase = (par ? f.Wld2 : f.Wld) + (size_t)kofs * ldl;
-   const bool vec16 = (cbeg & 1) == 0;      // 16-byte cp.async needs even row offsets (ldl is even)
+   const bool vec16 = true;
+   const int rclamp = (int)ldl - 2;         // last even row index inside a column of L / Wld
    const int nchunk = (kc + BK - 1) / BK;
    // tile (ti,tj) touches the lower triangle iff tj <= 2*ti+1 (TM = 2*TN, shared origin cbeg);
    // tiles are numbered row by row; a CTA walks its tiles incrementally.  The first k-chunk of the
@@ -933,35 +938,23 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
          const size_t stb = 8 * ldl;
 #pragma unroll
          for (int q = 0; q < 4; ++q) cp_async16(sb_ + q * 8 * LDB, pb + q * stb, 16);
-      } else if (vec16) {
+      } else {
+         // edge tiles and short k-chunks: the same 16-byte copies with the row index clamped into the column
+         // (rows / columns beyond the front are never stored, and every output element only sees its own row of
+         // A and its own column of B); k-rows beyond kc are zero-filled
 #pragma unroll
          for (int q = 0; q < 8; ++q) {
             const int e = q * 256 + tid, kk = e >> 6, rr = (e & 63) * 2;
-            const int ra = rbase + rr;
-            const int nb = (kb + kk < kc) ? (ra + 1 < m ? 16 : (ra < m ? 8 : 0)) : 0;
+            const int ra = min(rbase + rr, rclamp);
+            const int nb = (kb + kk < kc) ? 16 : 0;
             cp_async16(as + kk * LDA + rr, nb ? Abase + (size_t)(kb + kk) * ldl + ra : Abase, nb);
          }
 #pragma unroll
          for (int q = 0; q < 4; ++q) {
             const int e = q * 256 + tid, kk = e >> 5, rr = (e & 31) * 2;
-            const int cb = cbase + rr;
-            const int nb = (kb + kk < kc) ? (cb + 1 < cend ? 16 : (cb < cend ? 8 : 0)) : 0;
+            const int cb = min(cbase + rr, rclamp);
+            const int nb = (kb + kk < kc) ? 16 : 0;
             cp_async16(bs + kk * LDB + rr, nb ? Bbase + (size_t)(kb + kk) * ldl + cb : Bbase, nb);
-         }
-      } else {
-#pragma unroll
-         for (int q = 0; q < 16; ++q) {
-            const int e = q * 256 + tid, kk = e >> 7, rr = e & 127;
-            const int ra = rbase + rr;
-            const bool ok = kb + kk < kc && ra < m;
-            cp_async8(as + kk * LDA + rr, ok ? Abase + (size_t)(kb + kk) * ldl + ra : Abase, ok);
-         }
-#pragma unroll
-         for (int q = 0; q < 8; ++q) {
-            const int e = q * 256 + tid, kk = e >> 6, rr = e & 63;
-            const int cb = cbase + rr;
-            const bool ok = kb + kk < kc && cb < cend;
-            cp_async8(bs + kk * LDB + rr, ok ? Bbase + (size_t)(kb + kk) * ldl + cb : Bbase, ok);
          }
       }
       cp_async_commit();
@@ -970,18 +963,19 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    if (!normalise(ti, tj)) return;
    int buf = 0;
    {
-      const int rbase = cbeg + ti * TM, cbase = cbeg + tj * TN;
+      const int rbase = org + ti * TM, cbase = org + tj * TN;
       load_stage(rbase, cbase, (rbase + TM <= m) && (cbase + TN <= cend) && vec16, 0, 0);
    }
    for (;;) {
-      const int rbase = cbeg + ti * TM, cbase = cbeg + tj * TN;
-      const bool full = (rbase + TM <= m) && (cbase + TN <= cend) && vec16;
+      const int rbase = org + ti * TM, cbase = org + tj * TN;
+      const bool fullg = (rbase + TM <= m) && (cbase + TN <= cend);      // geometry: operand loads
+      const bool full = fullg && rbase >= cbeg && cbase >= cbeg;         // and no masked leading row / column
       const bool below = cbase + TN - 1 <= rbase;     // tile entirely below the diagonal
       // a warp whose 32 x 32 part of a diagonal tile lies strictly above the diagonal has nothing to compute
       const bool above = rbase + wr * 32 + 31 < cbase + wc * 32;
       int nti = ti, ntj = tj + nparts;
       const bool has_next = normalise(nti, ntj);
-      const int nrbase = cbeg + nti * TM, ncbase = cbeg + ntj * TN;
+      const int nrbase = org + nti * TM, ncbase = org + ntj * TN;
       double acc[4][4][2];
       // accumulators start as the C tile; the product is subtracted by feeding -B to the MMA.  The MMA computes
       // the TRANSPOSE of the tile (B-operand rows are the tile's columns), so that a thread's two accumulator
@@ -1003,7 +997,7 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
 #pragma unroll
          for (int j = 0; j < 4; ++j) {
             const int c = c0 + j * 8;
-            const bool cv = c < cend;
+            const bool cv = c < cend && c >= cbeg;
             const double* colp = (c < fn) ? (Lp + (size_t)c * ldl) : (Cp + (size_t)(c - fn) * ldc - fn);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1016,7 +1010,7 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
       }
       for (int ch = 0; ch < nchunk; ++ch) {
          if (ch + 1 < nchunk) {
-            load_stage(rbase, cbase, full, ch + 1, buf ^ 1);
+            load_stage(rbase, cbase, fullg, ch + 1, buf ^ 1);
             cp_async_wait<1>();
          } else if (has_next) {
             load_stage(nrbase, ncbase, (nrbase + TM <= m) && (ncbase + TN <= cend) && vec16, 0, buf ^ 1);
@@ -1072,7 +1066,7 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
 #pragma unroll
          for (int j = 0; j < 4; ++j) {
             const int c = c0 + j * 8;
-            if (c >= cend) continue;
+            if (c >= cend || c < cbeg) continue;
             double* colp = (c < fn) ? (Lp + (size_t)c * ldl) : (Cp + (size_t)(c - fn) * ldc - fn);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
