@@ -971,8 +971,8 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
       const bool fullg = (rbase + TM <= m) && (cbase + TN <= cend);      // geometry: operand loads
       const bool full = fullg && rbase >= cbeg && cbase >= cbeg;         // and no masked leading row / column
       const bool below = cbase + TN - 1 <= rbase;     // tile entirely below the diagonal
-      // a warp whose 32 x 32 part of a diagonal tile lies strictly above the diagonal has nothing to compute
-      const bool above = rbase + wr * 32 + 31 < cbase + wc * 32;
+      // a warp whose 32 x 32 part of the tile lies strictly above the diagonal or outside the front has nothing to compute
+      const bool above = rbase + wr * 32 + 31 < cbase + wc * 32 || rbase + wr * 32 >= m || cbase + wc * 32 >= cend;   // or outside the front
       int nti = ti, ntj = tj + nparts;
       const bool has_next = normalise(nti, ntj);
       const int nrbase = org + nti * TM, ncbase = org + ntj * TN;
