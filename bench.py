@@ -391,7 +391,7 @@ def run_tree_parallel(args, prob, torch, dist, rank, world, local):
                        "timing": "max over ranks of the wall time of factor (H2D of val, the stages and the exchanges between them) between device synchronisations"},
             "factor_ms": tf * 1e3, "solve_ms": ts * 1e3, "stage_ms_rank0": [round(v * 1e3, 3) for v in ds.t_stage],
             "backward_error": P.backward_error(prob, x, b), "num_neg": ds.num_neg,
-            "gpu_launches": int(ds.s.inform.reserved[0]) * args.steps,
+            "gpu_launches": int(ds.launches) * args.steps,   # rank 0, all stages
             "e2e": {"value": flops / tf / 1e12, "unit": UNIT, "h2d_bytes_per_step": int(world * 8 * prob["val"].size + world * 8 * n),
                     "d2h_bytes_per_step": int(8 * n), "factor_ms": tf * 1e3, "solve_ms": ts * 1e3},
             "roofline": {"bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,

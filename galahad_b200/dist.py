@@ -83,11 +83,13 @@ class DistSolver:
         vp = val.ctypes.data_as(C.POINTER(C.c_double))
         self.bytes_moved = 0
         self.t_stage = []
+        self.launches = 0
         worst = 0
         for k in range(self.nstages):
             f = s.L.b200ldlt_dist_factor(s.akeep, s.fkeep, k + 1, int(posdef), vp, C.byref(s.opt), C.byref(s.inform))
             worst = min(worst, f)
             self.t_stage.append(s.inform.time_factor)
+            self.launches += int(s.inform.reserved[0])
             self.bytes_moved += exchange(
                 self.boundaries[k], self.rank,
                 lambda node: s.L.b200ldlt_dist_contrib_bytes(s.fkeep, node),

@@ -29,7 +29,7 @@ def test_partition_invariants():
     assert s.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"]) == 0
     nt = s.numeric_tree()
     nn, par = nt["nnodes"], nt["sparent"]
-    for nranks in (1, 2, 4, 8):
+    for nranks in (1, 2, 3, 4, 5, 8):
         parts = parts_of(s, nranks)
         # contiguous cover of all nodes
         assert parts[0][0] == 0 and parts[-1][1] == nn - 1
@@ -68,7 +68,7 @@ def test_partition_invariants():
             assert s.L.b200ldlt_map_info(s.akeep, node, C.byref(o), C.byref(t)) == 0
             own[node], stg[node] = o.value, t.value
         assert own.min() >= 0 and own.max() < nranks and stg.min() == 0
-        assert len(set(own.tolist())) == min(nranks, 8)          # a 16^3 ND tree has work for 8 devices
+        assert len(set(own.tolist())) == nranks                  # a 16^3 ND tree has work for 8 devices
         nb_expected = 0
         for node in range(nn):
             p_ = par[node]
