@@ -1066,6 +1066,12 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    const bool trace = getenv("B200LDLT_TRACE") != nullptr;
    const int upd_share = getenv("B200LDLT_UPD_SHARE") ? atoi(getenv("B200LDLT_UPD_SHARE")) : 296;
    const bool lookahead = !(getenv("B200LDLT_LOOKAHEAD") && atoi(getenv("B200LDLT_LOOKAHEAD")) == 0);
+   // rank-2PB trailing updates in the look-ahead chunks (k_update, pair mode)
+   const bool pairing_on = !(getenv("B200LDLT_PAIR") && atoi(getenv("B200LDLT_PAIR")) == 0);
+   // worth it where the bulk update dwarfs the panel chain (it gives up the overlap of the next block's factorisation
+   // with the bulk update): fronts of at least this many rows
+   const int pair_min_m = getenv("B200LDLT_PAIR_MINM") ? atoi(getenv("B200LDLT_PAIR_MINM")) : 8192;
+   const bool pair_dbg = getenv("B200LDLT_PAIR") && atoi(getenv("B200LDLT_PAIR")) == 2;
    const int max_groups = getenv("B200LDLT_GROUPS") ? std::max(1, std::min((int)NAUX, atoi(getenv("B200LDLT_GROUPS")))) : (int)NAUX;
    auto trace_fronts = [&](const char* what, int slot_first, int count) {
       std::vector<FrontDev> tmp(count);
@@ -1320,6 +1326,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             // (on this stream) and the bulk (on the chunk's second stream, beside the factorisation of block
             // b+1).  Worth it for large fronts with several blocks; profile / trace runs keep one stream.
             const bool la = la_chunk;
+            const bool pairing = pairing_on && la && maxm >= pair_min_m;
             int nbulk = 0;
             for (int ob = 0; ob < nouter; ++ob) {
                const int na = map_na[ob];   // slots [b0, b0+na) cover every front that still has a block number ob
@@ -1331,6 +1338,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                // blocks shortened by failed pivots leave `done` behind ob*PB, so the row grid covers the
                // whole front; CTAs above the block exit at once
                const int yapply = std::max(1, (maxm + AR - 1) / AR);
+               // pair updates read both X buffers and the even block's record: the next even block may only start
+               // once the pair's bulk update is done
+               if (la && pairing && par == 0 && ob >= 2) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][1], 0));
                if (wcap == NB) k_block<0><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
                else if (wcap == 2 * NB) k_block<1><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
                else k_block<2><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
@@ -1348,18 +1358,23 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                      }
                      prof_begin();
                   }
-                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 0);
+                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 0, 0, 0);
                   if (o.profile) prof_end();
                   ++launches;
                } else {
+                  if (pair_dbg && par == 1) {   // debugging aid (B200LDLT_PAIR=2): the deferred bulk as a launch of its own
+                     if (ob > 0) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][0], 0));
+                     k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], 0, 2, 0, 0);
+                     ++launches;
+                  }
                   CU(cudaEventRecord(ev_commit[sidx][par], sx));
                   CU(cudaStreamWaitEvent(bulk[sidx], ev_commit[sidx][par], 0));
-                  k_update<<<nct, 256, UPD_SMEM, bulk[sidx]>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 2);
+                  k_update<<<nct, 256, UPD_SMEM, bulk[sidx]>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 2, (pairing && !(pair_dbg && par == 1)) ? 1 : 0, (ob + 1) * PB);
                   CU(cudaEventRecord(ev_bulk[sidx][par], bulk[sidx]));
                   ++nbulk;
                   // the strip overlaps the region of the previous block's bulk update
                   if (ob > 0) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][par ^ 1], 0));
-                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 1);
+                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 1, (pairing && !(pair_dbg && par == 1)) ? 1 : 0, (ob + 1) * PB);
                   launches += 2;
                }
                if (trace) trace_fronts("block", b0, na);
@@ -1447,7 +1462,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          k_block<2><<<nt, 256, block_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, 0, wcap, 0, 0);
          k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap, 0);
          k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks, 0);
-         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, nullptr, 0, 0);
+         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, nullptr, 0, 0, 0, 0);
          if (trace) for (int s : tpp_list) trace_fronts("retry", s, 1);
          k_block<0><<<nt, 256, block_smem_bytes(NB), st>>>(d_fr, d_list, 0, prm, 1, NB, 0, 0);
          launches += 5;

@@ -874,8 +874,15 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
 // of the launch in proportion to their tile counts; without it the grid is (fronts, parts).
 // mode 0: the whole region; 1: only the strip (column tiles that start before urec[2], i.e. the next
 // block's columns and the failed columns of this one); 2: everything else (look-ahead schedule).
+// pair != 0 (look-ahead chunks): updates of rank 2 PB.  The bulk update of an even block that has a partner (the front
+// has columns beyond next_col) is deferred; the odd block's strip and bulk then apply BOTH blocks at once,
+// k = [k0 - PB, k0 + kc), the B operand from Wld for the even and Wld2 for the odd block, so that C is read and
+// written once per 2 PB pivots.  The PB columns behind the even block (the odd block's failed columns and, if the odd
+// block is short, the columns after it) already have the even block's update from its strip: they see zeros in the
+// even block's part of B.  If the odd block accepted nothing (the front stalled
+// on a failed pivot of the even block), its bulk launch flushes the even block's deferred bulk instead.
 __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0, const int* __restrict__ map,
-                                                   int par, int mode) {
+                                                   int par, int mode, int pair, int next_col) {
    int fq, part, nparts;
    if (map) { fq = map[3 * blockIdx.x]; part = map[3 * blockIdx.x + 1]; nparts = map[3 * blockIdx.x + 2]; }
    else { fq = blockIdx.x; part = blockIdx.y; nparts = gridDim.y; }
@@ -883,15 +890,28 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    if (f.flag < 0) return;
    // pivots accepted in the block (recorded by k_commit); the region starts right behind them, so columns
    // of the block that failed (restored by k_commit) receive the update as well
-   const int kc = f.urec[par][1];
+   int rp = par;              // parity of the record / X buffer of a single-block update
+   int kce = 0, colsplit = 0; // pair update: pivots of the even block in the k range, end of the even block's strip
+   if (pair) {
+      if (par == 0) {
+         if (mode == 2 && f.n > next_col) return;          // deferred to the partner
+      } else if (f.urec[1][1] <= 0) {
+         if (mode != 2) return;
+         rp = 0;                                            // flush the even block's bulk
+      } else {
+         kce = PB;
+         colsplit = f.urec[1][0] + PB;      // the even block's strip went PB columns past its own block
+      }
+   }
+   const int kc = kce + f.urec[rp][1];
    const int m = f.m;
-   const int k0 = f.urec[par][0], cbeg = k0 + kc, cend = m;
+   const int k0 = f.urec[rp][0] - kce, cbeg = k0 + kc, cend = m;
    if (kc <= 0 || cbeg >= cend) return;
    // The tile grid starts at the even index org <= cbeg: every row offset of the operands and of C is then a
    // multiple of 16 bytes (ldl, ldc are even, C is shifted by n & 1), so all operand loads are 16-byte copies.
    // When cbeg is odd the grid has one extra leading row and column, masked in the first row / column of tiles.
    const int org = cbeg & ~1;
-   const int tjs = (f.urec[par][2] - org + TN - 1) / TN;   // column tiles [0, tjs) form the strip
+   const int tjs = (f.urec[rp][2] - org + TN - 1) / TN;   // column tiles [0, tjs) form the strip
    const int kofs = 0;
    const int ntr = (m - org + TM - 1) / TM;
    const int ntc = (cend - org + TN - 1) / TN;
@@ -906,7 +926,8 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    double* const Lp = f.L;
    double* const Cp = f.C;
    const double* Abase = Lp + (size_t)k0 * ldl;
-   const double* Bbase = (par ? f.Wld2 : f.Wld) + (size_t)kofs * ldl;
+   const double* Bbase = (rp ? f.Wld2 : f.Wld) + (size_t)kofs * ldl;   // single: the block's X; pair: the odd block's
+   const double* Bev = f.Wld;                                          // pair: the even block's X
    const bool vec16 = true;
    const int rclamp = (int)ldl - 2;         // last even row index inside a column of L / Wld
    const int nchunk = (kc + BK - 1) / BK;
@@ -926,14 +947,18 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
       const int kb = chunk * BK;
       double* as = As + buf * BK * LDA;
       double* bs = Bs + buf * BK * LDB;
-      if (full && kb + BK <= kc) {
+      const bool epart = kb < kce;                          // chunk of the even block's pivots (PB is a multiple of BK)
+      const double* Bsrc = epart ? Bev + (size_t)kb * ldl : Bbase + (size_t)(kb - kce) * ldl;
+      const int klim = kc - kb;                             // valid k rows of the chunk
+      const bool split = epart && cbase < colsplit;         // tile holds columns that must not see the even block
+      if (full && klim >= BK && !split) {
          // thread -> (k row = q*4 + tid/64, piece (tid%64)*2) for A; (q*8 + tid/32, (tid%32)*2) for B
          const double* pa = Abase + (size_t)(kb + (tid >> 6)) * ldl + rbase + (tid & 63) * 2;
          double* sa_ = as + (tid >> 6) * LDA + (tid & 63) * 2;
          const size_t sta = 4 * ldl;
 #pragma unroll
          for (int q = 0; q < 8; ++q) cp_async16(sa_ + q * 4 * LDA, pa + q * sta, 16);
-         const double* pb = Bbase + (size_t)(kb + (tid >> 5)) * ldl + cbase + (tid & 31) * 2;
+         const double* pb = Bsrc + (size_t)(tid >> 5) * ldl + cbase + (tid & 31) * 2;
          double* sb_ = bs + (tid >> 5) * LDB + (tid & 31) * 2;
          const size_t stb = 8 * ldl;
 #pragma unroll
@@ -946,15 +971,26 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
          for (int q = 0; q < 8; ++q) {
             const int e = q * 256 + tid, kk = e >> 6, rr = (e & 63) * 2;
             const int ra = min(rbase + rr, rclamp);
-            const int nb = (kb + kk < kc) ? 16 : 0;
+            const int nb = (kk < klim) ? 16 : 0;
             cp_async16(as + kk * LDA + rr, nb ? Abase + (size_t)(kb + kk) * ldl + ra : Abase, nb);
          }
+         if (!split) {
 #pragma unroll
-         for (int q = 0; q < 4; ++q) {
-            const int e = q * 256 + tid, kk = e >> 5, rr = (e & 31) * 2;
-            const int cb = min(cbase + rr, rclamp);
-            const int nb = (kb + kk < kc) ? 16 : 0;
-            cp_async16(bs + kk * LDB + rr, nb ? Bbase + (size_t)(kb + kk) * ldl + cb : Bbase, nb);
+            for (int q = 0; q < 4; ++q) {
+               const int e = q * 256 + tid, kk = e >> 5, rr = (e & 31) * 2;
+               const int cb = min(cbase + rr, rclamp);
+               const int nb = (kk < klim) ? 16 : 0;
+               cp_async16(bs + kk * LDB + rr, nb ? Bsrc + (size_t)kk * ldl + cb : Bsrc, nb);
+            }
+         } else {
+            // column by column: zeros for the odd block's failed columns (c < colsplit)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+               const int e = q * 256 + tid, kk = e >> 6, cc = e & 63;
+               const int cb = cbase + cc;
+               const bool ok = kk < klim && cb >= colsplit;
+               cp_async8(bs + kk * LDB + cc, ok ? Bsrc + (size_t)kk * ldl + min(cb, rclamp + 1) : Bsrc, ok);
+            }
          }
       }
       cp_async_commit();

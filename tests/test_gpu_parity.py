@@ -310,3 +310,63 @@ def test_scaled_factorisation():
     f, x0 = s.solve(b0)
     fg, xg = good.solve(b0)
     assert flag >= 0 and np.array_equal(x0, xg)
+
+
+def _arms_problem(arms, ns, kind, seed=3):
+    """Dense arms of different widths joined by a dense separator: one level of fronts with m > n and different
+    block counts, then the separator front."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n = sum(arms) + ns
+    A = np.zeros((n, n))
+
+    def sym(k):
+        M = rng.uniform(-1, 1, (k, k))
+        return (M + M.T) / 2
+    o = 0
+    for a in arms:
+        A[o:o + a, o:o + a] = sym(a)
+        A[n - ns:, o:o + a] = rng.uniform(-1, 1, (ns, a))
+        o += a
+    A[n - ns:, n - ns:] = sym(ns)
+    A = np.tril(A)
+    A = A + np.tril(A, -1).T
+    if kind == "spd":
+        A += n * np.eye(n)
+    nn, ptr, row, val = P.lower_csc(sp.csc_matrix(A))
+    neg = int((np.linalg.eigvalsh(A) < 0).sum())
+    return A, dict(n=n, ptr=ptr, row=row, val=val, order=np.arange(n, dtype=np.int32), inertia=(n - neg, neg, 0))
+
+
+def test_rank_256_updates(monkeypatch):
+    """The look-ahead schedule with paired blocks (k_update pair mode: the even block's bulk update deferred and
+    applied together with the odd block's, B200LDLT_PAIR_MINM lowers the front size from which it is used):
+    fronts with a short last block, several fronts of different block counts in one launch, failed pivots in
+    either block of a pair (stall + flush), and a sparse problem; against the eigenvalues / the unpaired run."""
+    monkeypatch.setenv("B200LDLT_PAIR_MINM", "0")
+    for arms, ns, kind in (((300, 200, 520), 900, "spd"), ((300,), 800, "indef"), ((520, 300), 1000, "indef"),
+                           ((129, 257), 1000, "spd"), ((640,), 1100, "indef")):
+        A, prob = _arms_problem(arms, ns, kind)
+        s, flag = gpu_factor(prob)
+        assert flag >= 0 and s.inform.num_neg == prob["inertia"][1], (arms, kind)
+        b = A @ np.ones(prob["n"])
+        f, x = s.solve(b)
+        be = np.abs(A @ x - b).max() / (np.abs(A).sum(1).max() * np.abs(x).max() + np.abs(b).max())
+        assert f == 0 and be <= 1e-13, (arms, kind, be)
+    for kind, n in (("indef", 1300), ("zdiag", 2100), ("kkt", 1500)):
+        A, prob = P.dense_front_problem(n, kind, seed=n)
+        s, flag = gpu_factor(prob)
+        assert flag >= 0 and s.inform.num_neg == prob["inertia"][1], (kind, n)
+        b = A @ np.ones(n)
+        f, x = s.solve(b)
+        be = np.abs(A @ x - b).max() / (np.abs(A).sum(1).max() * np.abs(x).max() + np.abs(b).max())
+        assert f == 0 and be <= 1e-13, (kind, n, be)
+    prob = P.laplace_problem(32)
+    xs, b = rhs_for(prob)
+    s, flag = gpu_factor(prob)
+    f, x = s.solve(b)
+    assert flag == 0 and P.backward_error(prob, x, b) <= 1e-14
+    monkeypatch.setenv("B200LDLT_PAIR", "0")
+    s0, flag0 = gpu_factor(prob)
+    f, x0 = s0.solve(b)
+    assert np.abs(x - x0).max() <= 1e-12 * np.abs(x0).max()

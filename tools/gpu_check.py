@@ -95,6 +95,8 @@ if __name__ == "__main__":
         allok &= check(P.kkt_grid_problem(24), detail=False, use_ref=True)
         allok &= check(P.qpband_problem(100000), detail=False, use_ref=True)
         allok &= check(P.laplace_problem(24, stencil=27), detail=False, use_ref=True)
+    elif which == "lap32":
+        allok &= check(P.laplace_problem(32))
     elif which == "c2":
         allok &= check(P.laplace_problem(64), detail=False)
         allok &= check(P.laplace_problem(64), posdef=True, detail=False)
