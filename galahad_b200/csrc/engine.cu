@@ -45,6 +45,7 @@ struct FrontDev {
    int* orig;      // orig[r] = local index variable r had when the front was assembled (r < n)
    double* Wld;    // ldl x wc  L*D of the current block (front-row indexed); blocks alternate between Wld and Wld2
    double* Wld2;   //           so that the bulk update of block b can run beside the factorisation of block b+1
+   double* Wld3;   //           third buffer: paired (rank 2 PB) updates read two of them while the next block writes the third
    double* Wo;     // ldl x wc  permuted original columns of the block (restore on failure)
    double* dbuf;   // L11[PB*wc] | A0[PB*wc] | dk[2*PB+2] | Linv[NB*wc] (inverses of the 32x32 diagonal blocks of L11)
    int* ibuf;      // lperm[PB] | ptype[PB] | permuted
@@ -512,10 +513,10 @@ __global__ void k_merge_stage(double* __restrict__ xp, const double* __restrict_
 // ------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int block_wc(int n) { return std::max(NB, (std::min(n, PB) + NB - 1) / NB * NB); }
-// doubles of block workspace of a front: Wld | Wld2 | Wo | L11 | A0 | dk | Linv | ibuf
+// doubles of block workspace of a front: Wld | Wld2 | Wld3 | Wo | L11 | A0 | dk | Linv | ibuf
 static inline size_t front_ws_doubles(size_t ldl, int n) {
    const size_t wc = (size_t)block_wc(n);
-   return align_up(3 * ldl * wc + 2 * (size_t)PB * wc + 2 * PB + 2 + (size_t)NB * wc + (2 * PB + 8) / 2, 32) + 128;
+   return align_up(4 * ldl * wc + 2 * (size_t)PB * wc + 2 * PB + 2 + (size_t)NB * wc + (2 * PB + 8) / 2, 32) + 128;
 }
 static inline int size_class(int m) { return m <= 64 ? 0 : m <= 256 ? 1 : m <= 1024 ? 2 : m <= 4096 ? 3 : 4; }
 
@@ -1153,8 +1154,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             f.perm = Pb + oP; f.orig = f.perm + align_up((size_t)f.n + 1, 32); oP += 2 * align_up((size_t)f.n + 1, 32);
             double* wp = Wb + oW;
             oW += front_ws_doubles(f.ldl, f.n);
-            f.Wld = wp; f.Wld2 = wp + (size_t)f.ldl * f.wc; f.Wo = wp + 2 * (size_t)f.ldl * f.wc;
-            f.dbuf = wp + 3 * (size_t)f.ldl * f.wc;
+            f.Wld = wp; f.Wld2 = wp + (size_t)f.ldl * f.wc; f.Wld3 = wp + 2 * (size_t)f.ldl * f.wc; f.Wo = wp + 3 * (size_t)f.ldl * f.wc;
+            f.dbuf = wp + 4 * (size_t)f.ldl * f.wc;
             f.ibuf = (int*)(f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2 + (size_t)NB * f.wc);
          }
       }
@@ -1338,14 +1339,13 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                // blocks shortened by failed pivots leave `done` behind ob*PB, so the row grid covers the
                // whole front; CTAs above the block exit at once
                const int yapply = std::max(1, (maxm + AR - 1) / AR);
-               // pair updates read both X buffers and the even block's record: the next even block may only start
-               // once the pair's bulk update is done
-               if (la && pairing && par == 0 && ob >= 2) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][1], 0));
+               // X buffer of this block: paired updates read two buffers while the next block writes the third
+               const int xb = pairing ? ob % 3 : par;
                if (wcap == NB) k_block<0><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
                else if (wcap == 2 * NB) k_block<1><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
                else k_block<2><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
-               k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, wcap, par);
-               k_commit<<<dim3(na, ycommit), 256, 0, sx>>>(d_fr, lst, b0, ncolchunks, par);
+               k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, wcap, xb);
+               k_commit<<<dim3(na, ycommit), 256, 0, sx>>>(d_fr, lst, b0, ncolchunks, par, xb);
                launches += 3;
                const int nct = (map_off[ob + 1] - map_off[ob]) / 3;
                if (!la) {
@@ -1358,23 +1358,23 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                      }
                      prof_begin();
                   }
-                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 0, 0, 0);
+                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 0, 0, 0, xb);
                   if (o.profile) prof_end();
                   ++launches;
                } else {
                   if (pair_dbg && par == 1) {   // debugging aid (B200LDLT_PAIR=2): the deferred bulk as a launch of its own
                      if (ob > 0) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][0], 0));
-                     k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], 0, 2, 0, 0);
+                     k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], 0, 2, 0, 0, (xb + 2) % 3);
                      ++launches;
                   }
                   CU(cudaEventRecord(ev_commit[sidx][par], sx));
                   CU(cudaStreamWaitEvent(bulk[sidx], ev_commit[sidx][par], 0));
-                  k_update<<<nct, 256, UPD_SMEM, bulk[sidx]>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 2, (pairing && !(pair_dbg && par == 1)) ? 1 : 0, (ob + 1) * PB);
+                  k_update<<<nct, 256, UPD_SMEM, bulk[sidx]>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 2, (pairing && !(pair_dbg && par == 1)) ? 1 : 0, (ob + 1) * PB, xb);
                   CU(cudaEventRecord(ev_bulk[sidx][par], bulk[sidx]));
                   ++nbulk;
                   // the strip overlaps the region of the previous block's bulk update
                   if (ob > 0) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][par ^ 1], 0));
-                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 1, (pairing && !(pair_dbg && par == 1)) ? 1 : 0, (ob + 1) * PB);
+                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 1, (pairing && !(pair_dbg && par == 1)) ? 1 : 0, (ob + 1) * PB, xb);
                   launches += 2;
                }
                if (trace) trace_fronts("block", b0, na);
@@ -1461,8 +1461,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          const int wcap = (std::min(maxn, PB) + NB - 1) / NB * NB;
          k_block<2><<<nt, 256, block_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, 0, wcap, 0, 0);
          k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap, 0);
-         k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks, 0);
-         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, nullptr, 0, 0, 0, 0);
+         k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks, 0, 0);
+         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, nullptr, 0, 0, 0, 0, 0);
          if (trace) for (int s : tpp_list) trace_fronts("retry", s, 1);
          k_block<0><<<nt, 256, block_smem_bytes(NB), st>>>(d_fr, d_list, 0, prm, 1, NB, 0, 0);
          launches += 5;

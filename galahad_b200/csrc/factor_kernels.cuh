@@ -624,6 +624,8 @@ __global__ void __launch_bounds__(256, KIND < 2 ? 2 : 1) k_block(FrontDev* fr, c
 //    X_j = Y inv(L_jj)^T                      DMMA with the explicit 32x32 inverses from k_block
 //    L_j = X_j D^{-1} (in place), X_j kept in Wld, a-posteriori test |l| <= 1/u
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double* xbuf(const FrontDev& f, int xb) { return xb == 0 ? f.Wld : (xb == 1 ? f.Wld2 : f.Wld3); }
+
 constexpr int AR = 64;             // rows per CTA in k_apply
 constexpr int LDX = AR + 4;        // k-major smem leading dimension, = 4 mod 16: conflict-free fragments
 __host__ __device__ inline size_t apply_smem_bytes(int wcap) {
@@ -632,11 +634,11 @@ __host__ __device__ inline size_t apply_smem_bytes(int wcap) {
           sizeof(int) * 2 * PB;
 }
 
-__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap, int par) {
+__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap, int xb) {
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0 || f.stall) return;
-   double* const Wldp = par ? f.Wld2 : f.Wld;
+   double* const Wldp = xbuf(f, xb);
    const int done = f.done, m = f.m;
    const int r0 = done + w + blockIdx.y * AR;
    if (r0 >= m) return;
@@ -772,7 +774,7 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, in
 // finished columns whose rows [done, done+w) follow the pivot order, then chunks of 256 rows
 // restoring failed columns.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, int slot0, int ncolchunks, int par) {
+__global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, int slot0, int ncolchunks, int par, int xb) {
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0 || f.stall) return;
@@ -784,7 +786,7 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
    if (y == 0) {
       // what the trailing updates of this block need: first pivot column, accepted pivots, end of the strip
       if (tid == 0) { f.urec[par][0] = done; f.urec[par][2] = min(m, done + w + PB); f.urec[par][1] = nelim; }
-      double* const Wldp = par ? f.Wld2 : f.Wld;
+      double* const Wldp = xbuf(f, xb);
       const double* dk = f.dbuf + 2 * (size_t)PB * f.wc;
       if (nelim < w) {
          // failed columns get their original values back (block part from A0 in pivot order; CopyBackup,
@@ -882,7 +884,7 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
 // even block's part of B.  If the odd block accepted nothing (the front stalled
 // on a failed pivot of the even block), its bulk launch flushes the even block's deferred bulk instead.
 __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0, const int* __restrict__ map,
-                                                   int par, int mode, int pair, int next_col) {
+                                                   int par, int mode_in, int pair, int next_col, int xb) {
    int fq, part, nparts;
    if (map) { fq = map[3 * blockIdx.x]; part = map[3 * blockIdx.x + 1]; nparts = map[3 * blockIdx.x + 2]; }
    else { fq = blockIdx.x; part = blockIdx.y; nparts = gridDim.y; }
@@ -890,14 +892,19 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    if (f.flag < 0) return;
    // pivots accepted in the block (recorded by k_commit); the region starts right behind them, so columns
    // of the block that failed (restored by k_commit) receive the update as well
-   int rp = par;              // parity of the record / X buffer of a single-block update
+   int rp = par;              // parity of the record of a single-block update
+   int mode = mode_in;
    int kce = 0, colsplit = 0; // pair update: pivots of the even block in the k range, end of the even block's strip
    if (pair) {
       if (par == 0) {
          if (mode == 2 && f.n > next_col) return;          // deferred to the partner
       } else if (f.urec[1][1] <= 0) {
-         if (mode != 2) return;
-         rp = 0;                                            // flush the even block's bulk
+         // flush the even block's deferred bulk; in the STRIP launch, i.e. on the chunk's own stream before the next
+         // block's kernels (which reset the even record)
+         if (mode != 1) return;
+         rp = 0;
+         mode = 2;
+         xb = (xb + 2) % 3;
       } else {
          kce = PB;
          colsplit = f.urec[1][0] + PB;      // the even block's strip went PB columns past its own block
@@ -926,8 +933,8 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    double* const Lp = f.L;
    double* const Cp = f.C;
    const double* Abase = Lp + (size_t)k0 * ldl;
-   const double* Bbase = (rp ? f.Wld2 : f.Wld) + (size_t)kofs * ldl;   // single: the block's X; pair: the odd block's
-   const double* Bev = f.Wld;                                          // pair: the even block's X
+   const double* Bbase = xbuf(f, xb) + (size_t)kofs * ldl;   // single: the block's X; pair: the odd block's
+   const double* Bev = xbuf(f, (xb + 2) % 3);                 // pair: the even block's X (the buffer before in the rotation)
    const bool vec16 = true;
    const int rclamp = (int)ldl - 2;         // last even row index inside a column of L / Wld
    const int nchunk = (kc + BK - 1) / BK;
