@@ -1700,9 +1700,10 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
       ++nlaunch;
       if (roles_fwd_n[l] > 0) {
          k_fwd_chain<<<roles_fwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_fwd_off[l], roles_fwd_n[l], d_chain_counter + 2 * l, d_xw_off,
-                                                               d_xw, d_xa, d_cy, kind, d_chain_err);
+                                                               d_xw, d_cy, d_xp, posdef ? 1 : 0, kind, d_chain_err);
          ++nlaunch;
-      } else
+         continue;      // the owners stored their pivots themselves
+      }
       for (int sp = 0; sp < lvl_steps[l]; ++sp) {
          const int na = lvl_nact[l][sp];
          if (na == 0) break;
@@ -1737,9 +1738,10 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
       }
       if (roles_bwd_n[l] > 0) {
          k_bwd_chain<<<roles_bwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_bwd_off[l], roles_bwd_n[l], d_chain_counter + 2 * l + 1, d_xw_off,
-                                                               d_xw, d_cy, kind, d_chain_err);
+                                                               d_xw, d_cy, d_xp, kind, d_chain_err);
          ++nlaunch;
-      } else
+         continue;
+      }
       for (int sp = lvl_steps[l] - 1; sp >= 0; --sp) {
          const int na = lvl_nact[l][sp];
          if (na == 0) continue;

@@ -279,7 +279,7 @@ __device__ __forceinline__ void cy_wait(double (&buf)[N], const double* p, int s
 
 __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
                                                       unsigned long long* counter, const int64_t* __restrict__ xw_off, double* XW,
-                                                      double* XY, double* CY, int kind, int* err) {
+                                                      double* CY, double* x, int posdef_scale, int kind, int* err) {
    constexpr int SLD = KB + 1;
    __shared__ int2 role;
    if (threadIdx.x == 0) role = roles[(int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles)];
@@ -338,14 +338,16 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
    __syncthreads();
    smem_solve_lower(S, SLD, kb, xs);
    if (threadIdx.x < kb) {
-      cy_store(CY + xw_off[s] + rbase + threadIdx.x, xs[threadIdx.x]);
-      XY[xw_off[s] + rbase + threadIdx.x] = xs[threadIdx.x];
+      const double v = xs[threadIdx.x];
+      cy_store(CY + xw_off[s] + rbase + threadIdx.x, v);
+      // the solved pivots go straight into x (L_chol = L sqrt(D) for posdef; D is stored inverted)
+      x[f.perm[rbase + threadIdx.x]] = posdef_scale ? v * sqrt(f.D[2 * (rbase + threadIdx.x)]) : v;
    }
 }
 
 __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
                                                       unsigned long long* counter, const int64_t* __restrict__ xw_off, double* XW,
-                                                      double* CY, int kind, int* err) {
+                                                      double* CY, double* x, int kind, int* err) {
    constexpr int SLD = KB + 1;
    __shared__ int2 role;
    if (threadIdx.x == 0) role = roles[(int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles)];
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict
    smem_solve_lower_t(S, SLD, kb, xs, dots);
    if (threadIdx.x < kb) {
       cy_store(CY + xw_off[s] + cbase + threadIdx.x, xs[threadIdx.x]);
-      xw[cbase + threadIdx.x] = xs[threadIdx.x];
+      x[f.perm[cbase + threadIdx.x]] = xs[threadIdx.x];
    }
 }
 
