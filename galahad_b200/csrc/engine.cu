@@ -947,7 +947,14 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_bwd_step<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    const int nn = std::max(P->nnodes, 1);
    {
-      const int want = getenv("B200LDLT_RESERVE_SMS") ? atoi(getenv("B200LDLT_RESERVE_SMS")) : 8;
+      // Nsight Compute cannot profile kernels launched into a green context ("Failed to prepare kernel for
+      // profiling"): under an injected profiler (ncu sets NV_COMPUTE_PROFILER_PERFWORKS_DIR and
+      // NVIDIA_PROCESS_INJECTION_* in the target, other tools CUDA_INJECTION64_PATH) the partition is off unless asked
+      // for explicitly
+      const bool injected = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
+                            getenv("NVIDIA_PROCESS_INJECTION_CRASH_REPORTING") != nullptr ||
+                            getenv("CUDA_INJECTION64_PATH") != nullptr;
+      const int want = getenv("B200LDLT_RESERVE_SMS") ? atoi(getenv("B200LDLT_RESERVE_SMS")) : (injected ? 0 : 8);
       if (want > 0) {
          const int prc = make_bulk_partition(want);
          if (prc && getenv("B200LDLT_VERBOSE")) fprintf(stderr, "[b200ldlt] SM partition not available (%s)\n", cudaGetErrorString(cudaGetLastError()));
