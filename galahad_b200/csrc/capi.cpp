@@ -2,6 +2,7 @@
 // shifts, handle ownership, flag bookkeeping.  Mirrors the call-sequence checks of
 // src/ssids/ssids.f90 (analyse :148, factor :770/:821-827, solve :1139/:1155-1195,
 // enquire :1255/:1299, alter :1347, free :1388).
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -18,7 +19,11 @@ using namespace b200;
 
 namespace {
 
+// An Akeep is shared between the caller's handle and every Fkeep created from it (the Numeric keeps pointers into
+// its Plan): the last owner destroys it.  Re-analysing into a live handle or freeing akeep before fkeep therefore
+// never leaves a Numeric with a dangling Plan.
 struct Akeep {
+   std::atomic<int> refs{1};
    Symbolic sym;      // the reference's assembly tree (what SLS reports)
    Symbolic nsym;     // the engine's tree: chains fused (analyse.cpp fuse_chains)
    Plan* plan = nullptr;
@@ -32,6 +37,14 @@ struct Fkeep {
    Akeep* ak = nullptr;
    Numeric* num = nullptr;
 };
+
+void akeep_release(Akeep* ak) {
+   if (!ak) return;
+   if (ak->refs.fetch_sub(1) == 1) {
+      if (ak->plan) plan_destroy(ak->plan);
+      delete ak;
+   }
+}
 
 void clear_inform(b200ldlt_inform* inf) {
    if (inf) std::memset(inf, 0, sizeof(*inf));
@@ -127,10 +140,7 @@ int b200ldlt_analyse_ptr64(void** akeep, int n, const int64_t* ptr, const int* r
    inf->nparts = 1;
    inf->time_analyse = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
    ak->inf_analyse = *inf;
-   if (*akeep) {
-      void* none = nullptr;
-      b200ldlt_free(akeep, &none);
-   }
+   if (*akeep) akeep_release(static_cast<Akeep*>(*akeep));   // an fkeep made from it keeps it alive until it is freed
    *akeep = ak;
    return flag;
 }
@@ -158,6 +168,7 @@ static int ensure_fkeep(Akeep* ak, void** fkeep, const b200ldlt_options* opt, b2
       fk = new (std::nothrow) Fkeep();
       if (!fk) return inf->flag = SSIDS_ERROR_ALLOCATION;
       fk->ak = ak;
+      ak->refs.fetch_add(1);
       fk->num = numeric_create(ak->plan);
       *fkeep = fk;
    }
@@ -245,6 +256,15 @@ int b200ldlt_equilib_scale(int n, const int64_t* ptr, const int* row, const doub
    const int it = equilib_scale_sym(n, ptr, row, val, scaling);
    if (iterations) *iterations = it;
    return 0;
+}
+int b200ldlt_set_scaling(void* akeep, void** fkeep, const double* scale, const b200ldlt_options* opt,
+                         b200ldlt_inform* inf) {
+   if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
+   Akeep* ak = static_cast<Akeep*>(akeep);
+   *inf = ak->inf_analyse;
+   if (!scale && !*fkeep) return inf->flag = 0;          // nothing to clear
+   if (int rc = ensure_fkeep(ak, fkeep, opt, inf)) return rc;
+   return inf->flag = numeric_set_scaling(static_cast<Fkeep*>(*fkeep)->num, scale);
 }
 int b200ldlt_set_user_matrix(void* akeep, void** fkeep, int ne, const int* row, const int* col,
                              const b200ldlt_options* opt, b200ldlt_inform* inf) {
@@ -350,7 +370,8 @@ int b200ldlt_alter(void* akeep, void* fkeep, const double* d, b200ldlt_inform* i
 int b200ldlt_free_fkeep(void** fkeep) {
    if (!fkeep || !*fkeep) return 0;
    Fkeep* fk = static_cast<Fkeep*>(*fkeep);
-   if (fk->num) numeric_destroy(fk->num);
+   if (fk->num) numeric_destroy(fk->num);   // before the Plan it points into
+   akeep_release(fk->ak);
    delete fk;
    *fkeep = nullptr;
    return 0;
@@ -359,9 +380,7 @@ int b200ldlt_free_fkeep(void** fkeep) {
 int b200ldlt_free(void** akeep, void** fkeep) {
    if (fkeep) b200ldlt_free_fkeep(fkeep);
    if (akeep && *akeep) {
-      Akeep* ak = static_cast<Akeep*>(*akeep);
-      if (ak->plan) plan_destroy(ak->plan);
-      delete ak;
+      akeep_release(static_cast<Akeep*>(*akeep));
       *akeep = nullptr;
    }
    return 0;
@@ -468,6 +487,7 @@ int b200ldlt_dist_init(void* akeep, void** fkeep, int rank, int nranks, const b2
    Fkeep* fk = new (std::nothrow) Fkeep();
    if (!fk) return inf->flag = SSIDS_ERROR_ALLOCATION;
    fk->ak = ak;
+   ak->refs.fetch_add(1);
    fk->num = numeric_create(ak->plan);
    *fkeep = fk;
    return inf->flag = numeric_set_partition(fk->num, rank, nranks);

@@ -15,7 +15,6 @@
 // Data layout in HBM: per front, L is m x n column-major (ld = m rounded
 // up to 2), D^{-1} is 2n doubles in SSIDS's format (ldlt_app.cxx:324-329), perm is n ints, the
 // contribution block C is (m-n)^2 column-major and lives one level (ping-pong arenas).
-#include <cuda.h>            // types and prototypes only: the driver entry points are looked up at run time
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -24,6 +23,7 @@
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "engine.hpp"
@@ -43,9 +43,8 @@ struct FrontDev {
    double* D;
    int* perm;
    int* orig;      // orig[r] = local index variable r had when the front was assembled (r < n)
-   double* Wld;    // ldl x wc  L*D of the current block (front-row indexed); blocks alternate between Wld and Wld2
-   double* Wld2;   //           so that the bulk update of block b can run beside the factorisation of block b+1
-   double* Wld3;   //           third buffer: paired (rank 2 PB) updates read two of them while the next block writes the third
+   double* Wld;    // ldl x xw  X = L*D of the pivots (front-row indexed): a ring over the pivot index, pivot p of the front
+                   //           lives in column p mod xw, so that a trailing update of any rank reads one contiguous pivot range
    double* Wo;     // ldl x wc  permuted original columns of the block (restore on failure)
    double* dbuf;   // L11[PB*wc] | A0[PB*wc] | dk[2*PB+2] | Linv[NB*wc] (inverses of the 32x32 diagonal blocks of L11)
    int* ibuf;      // lperm[PB] | ptype[PB] | permuted
@@ -62,7 +61,12 @@ struct FrontDev {
    int part_kind;       // stage of the front in the proportional mapping (multi-GPU factor / solve phases); 0 on one GPU
    int stall;           // look-ahead schedule: a failed pivot was seen, the front waits for the synchronous retry rounds
    int urec[2][4];      // per block parity: {first pivot column k0, accepted pivots kc, end of the strip columns, -}
-   int pad4[2];         // written by k_commit, read by the trailing updates of that block
+                        // written by k_commit, read by the trailing updates of that block
+   int xw;              // columns of the X ring
+   int gk0;             // deferred (rank G*PB) updates: first pivot of the current group of blocks
+   int brec[2][6];      // per group parity: {first pivot, end pivot, first column, end of the next group's columns, tag, -}:
+                        // the group's trailing update, written by k_commit of the group's last block
+   int pend[4];         // {first pivot, end pivot, first column, flag}: deferred update not yet owed by a bulk launch
 };
 
 struct SlotStatic {
@@ -196,7 +200,9 @@ __device__ void block_sym_swap(const FrontDev& f, int a, int b) {
    __syncthreads();
 }
 
+__device__ int g_upd_debug = 0;     // B200LDLT_DEBUG_UPD=1: k_commit and k_upd3 print what they record / apply (diagnostic)
 #include "factor_kernels.cuh"
+#include "upd_kernels.cuh"
 constexpr int UPD_SMEM = 2 * BK * (LDA + LDB) * (int)sizeof(double);
 
 // ------------------------------------------------------------------------------------------
@@ -477,7 +483,12 @@ __global__ void k_axpy1(double* __restrict__ x, const double* __restrict__ r, in
 // max |v_i| into *out (non-negative doubles order like their bit patterns)
 __global__ void k_maxabs(const double* __restrict__ v, int n, unsigned long long* out) {
    double m = 0.0;
-   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmax(m, fabs(v[i]));
+   // fmax drops NaN: a non-finite entry must not read as a small residual (the refinement loop would report a NaN
+   // solution as converged), so it counts as +inf
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const double a = fabs(v[i]);
+      m = fmax(m, a <= 1.7976931348623157e308 ? a : DINF);
+   }
 #pragma unroll
    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
@@ -513,10 +524,14 @@ __global__ void k_merge_stage(double* __restrict__ xp, const double* __restrict_
 // ------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int block_wc(int n) { return std::max(NB, (std::min(n, PB) + NB - 1) / NB * NB); }
-// doubles of block workspace of a front: Wld | Wld2 | Wld3 | Wo | L11 | A0 | dk | Linv | ibuf
+// columns of a front's X ring: every pivot its own column up to 2 * GMAX blocks, where a group's deferred update reads
+// one half while the next group's blocks write the other
+constexpr int GMAX = 4;          // blocks per deferred trailing update (rank GMAX * PB)
+static inline int ring_cols(int n) { return n <= PB ? block_wc(n) : std::min((n + PB - 1) / PB * PB, 2 * GMAX * PB); }
+// doubles of block workspace of a front: X ring | Wo | L11 | A0 | dk | Linv | ibuf
 static inline size_t front_ws_doubles(size_t ldl, int n) {
    const size_t wc = (size_t)block_wc(n);
-   return align_up(4 * ldl * wc + 2 * (size_t)PB * wc + 2 * PB + 2 + (size_t)NB * wc + (2 * PB + 8) / 2, 32) + 128;
+   return align_up(ldl * ((size_t)ring_cols(n) + wc) + 2 * (size_t)PB * wc + 2 * PB + 2 + (size_t)NB * wc + (2 * PB + 8) / 2, 32) + 128;
 }
 static inline int size_class(int m) { return m <= 64 ? 0 : m <= 256 ? 1 : m <= 1024 ? 2 : m <= 4096 ? 3 : 4; }
 
@@ -754,6 +769,7 @@ class Numeric {
    bool posdef = false, have = false;
    std::vector<FrontDev> hfr;
    FrontDev* d_fr = nullptr;
+   bool inited = false, init_failed = false;   // init() ran to its end / stopped at a failed allocation
    FrontDev* pin_fr = nullptr;       // pinned staging, nslots entries
    int* pin_i = nullptr;             // pinned ints: collect + lists staging
    size_t pin_i_cap = 0;
@@ -820,11 +836,6 @@ class Numeric {
    size_t prez_c_bytes = 0, prez_l_bytes = 0;
    // look-ahead: bulk-update stream and events per chunk stream (0: st, 1..NAUX: aux[g-1])
    cudaStream_t bulk[NAUX + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-   // SM partition (green context): the bulk updates run on all SMs but `reserve_sms`, so that the next block's
-   // factorisation kernel (one CTA that needs a whole SM's shared memory) always finds a free SM
-   CUgreenCtx gctx_bulk = nullptr;
-   int reserve_sms = 0, bulk_sms = 148;
-   int make_bulk_partition(int want);
    cudaEvent_t ev_commit[NAUX + 1][2] = {}, ev_bulk[NAUX + 1][2] = {};
    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
    int cuda_err = 0;
@@ -853,13 +864,6 @@ class Numeric {
       for (int g = 0; g <= NAUX; ++g) {
          if (bulk[g]) cudaStreamDestroy(bulk[g]);
          for (int q = 0; q < 2; ++q) { if (ev_commit[g][q]) cudaEventDestroy(ev_commit[g][q]); if (ev_bulk[g][q]) cudaEventDestroy(ev_bulk[g][q]); }
-      }
-      if (gctx_bulk) {
-         typedef CUresult (*fn_gd)(CUgreenCtx);
-         fn_gd f_gd = nullptr;
-         cudaDriverEntryPointQueryResult qr;
-         if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", (void**)&f_gd, cudaEnableDefault, &qr) == cudaSuccess && f_gd) f_gd(gctx_bulk);
-         gctx_bulk = nullptr;
       }
       if (ev0) cudaEventDestroy(ev0);
       if (ev1) cudaEventDestroy(ev1);
@@ -897,44 +901,14 @@ class Numeric {
       }                                                                \
    } while (0)
 
-// Split the device's SMs into `want` reserved SMs and the rest; the rest becomes a green context whose streams
-// carry the bulk trailing updates.  Any failure leaves the ordinary streams in place (a scheduling aid, not a
-// different code path).  Driver entry points come from cudaGetDriverEntryPoint: no link against libcuda.
-int Numeric::make_bulk_partition(int want) {
-   typedef CUresult (*fn_dget)(CUdevice*, int);
-   typedef CUresult (*fn_res)(CUdevice, CUdevResource*, CUdevResourceType);
-   typedef CUresult (*fn_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
-   typedef CUresult (*fn_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
-   typedef CUresult (*fn_gctx)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
-   fn_dget f_dget = nullptr; fn_res f_res = nullptr; fn_split f_split = nullptr; fn_desc f_desc = nullptr; fn_gctx f_gctx = nullptr;
-   cudaDriverEntryPointQueryResult qr;
-   cudaFree(0);   // the primary context exists from here on
-   if (cudaGetDriverEntryPoint("cuDeviceGet", (void**)&f_dget, cudaEnableDefault, &qr) != cudaSuccess || !f_dget) return -1;
-   if (cudaGetDriverEntryPoint("cuDeviceGetDevResource", (void**)&f_res, cudaEnableDefault, &qr) != cudaSuccess || !f_res) return -1;
-   if (cudaGetDriverEntryPoint("cuDevSmResourceSplitByCount", (void**)&f_split, cudaEnableDefault, &qr) != cudaSuccess || !f_split) return -1;
-   if (cudaGetDriverEntryPoint("cuDevResourceGenerateDesc", (void**)&f_desc, cudaEnableDefault, &qr) != cudaSuccess || !f_desc) return -1;
-   if (cudaGetDriverEntryPoint("cuGreenCtxCreate", (void**)&f_gctx, cudaEnableDefault, &qr) != cudaSuccess || !f_gctx) return -1;
-   CUdevice dev;
-   if (f_dget(&dev, P->device) != CUDA_SUCCESS) return -1;
-   CUdevResource all, grp, rem;
-   if (f_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return -1;
-   unsigned int ng = 1;
-   if (f_split(&grp, &ng, &all, &rem, 0, (unsigned)want) != CUDA_SUCCESS || ng < 1 || rem.sm.smCount < 32) return -1;
-   CUdevResourceDesc desc;
-   if (f_desc(&desc, &rem, 1) != CUDA_SUCCESS) return -1;
-   CUgreenCtx g = nullptr;
-   if (f_gctx(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS || !g) return -1;
-   gctx_bulk = g;
-   reserve_sms = (int)grp.sm.smCount;
-   bulk_sms = (int)rem.sm.smCount;
-   if (getenv("B200LDLT_VERBOSE")) fprintf(stderr, "[b200ldlt] SM partition: %d reserved, %d for bulk updates\n", reserve_sms, bulk_sms);
-   return 0;
-}
-
 int Numeric::init() {
-   if (d_fr) return 0;
+   if (inited) return 0;
+   if (init_failed) return SSIDS_ERROR_ALLOCATION;   // a half-built handle is never used: free it and start again
+   init_failed = true;                               // cleared by the last line; any CU() failure below leaves it set
    CU(cudaSetDevice(P->device));
    CU(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM));
+   CU(cudaFuncSetAttribute(k_upd3, cudaFuncAttributeMaxDynamicSharedMemorySize, upd3::SMEM));
+   { const int dbg = getenv("B200LDLT_DEBUG_UPD") ? 1 : 0; CU(cudaMemcpyToSymbol(g_upd_debug, &dbg, sizeof(int))); }
    CU(cudaFuncSetAttribute(k_block<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(PB)));
    CU(cudaFuncSetAttribute(k_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(2 * NB)));
    CU(cudaFuncSetAttribute(k_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(NB)));
@@ -946,20 +920,6 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_bwd_step<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    CU(cudaFuncSetAttribute(k_bwd_step<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    const int nn = std::max(P->nnodes, 1);
-   {
-      // Nsight Compute cannot profile kernels launched into a green context ("Failed to prepare kernel for
-      // profiling"): under an injected profiler (ncu sets NV_COMPUTE_PROFILER_PERFWORKS_DIR and
-      // NVIDIA_PROCESS_INJECTION_* in the target, other tools CUDA_INJECTION64_PATH) the partition is off unless asked
-      // for explicitly
-      const bool injected = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
-                            getenv("NVIDIA_PROCESS_INJECTION_CRASH_REPORTING") != nullptr ||
-                            getenv("CUDA_INJECTION64_PATH") != nullptr;
-      const int want = getenv("B200LDLT_RESERVE_SMS") ? atoi(getenv("B200LDLT_RESERVE_SMS")) : (injected ? 0 : 8);
-      if (want > 0) {
-         const int prc = make_bulk_partition(want);
-         if (prc && getenv("B200LDLT_VERBOSE")) fprintf(stderr, "[b200ldlt] SM partition not available (%s)\n", cudaGetErrorString(cudaGetLastError()));
-      }
-   }
    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
    for (int g = 0; g < NAUX; ++g) {
       CU(cudaStreamCreateWithFlags(&aux[g], cudaStreamNonBlocking));
@@ -970,14 +930,6 @@ int Numeric::init() {
    CU(cudaEventCreateWithFlags(&ev_ea, cudaEventDisableTiming));
    CU(cudaEventCreateWithFlags(&ev_zero, cudaEventDisableTiming));
    for (int g = 0; g <= NAUX; ++g) {
-      if (gctx_bulk) {
-         typedef CUresult (*fn_sc)(CUstream*, CUgreenCtx, unsigned int, int);
-         fn_sc f_sc = nullptr;
-         cudaDriverEntryPointQueryResult qr;
-         if (cudaGetDriverEntryPoint("cuGreenCtxStreamCreate", (void**)&f_sc, cudaEnableDefault, &qr) != cudaSuccess || !f_sc ||
-             f_sc((CUstream*)&bulk[g], gctx_bulk, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS)
-            bulk[g] = nullptr;
-      }
       if (!bulk[g]) CU(cudaStreamCreateWithFlags(&bulk[g], cudaStreamNonBlocking));
       for (int q = 0; q < 2; ++q) {
          CU(cudaEventCreateWithFlags(&ev_commit[g][q], cudaEventDisableTiming));
@@ -1016,6 +968,8 @@ int Numeric::init() {
    boundary.assign(nn, 0);
    part_kind.assign(nn, 0);
    owner.assign(nn, 0);
+   init_failed = false;
+   inited = true;
    return 0;
 }
 
@@ -1074,12 +1028,10 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    const bool trace = getenv("B200LDLT_TRACE") != nullptr;
    const int upd_share = getenv("B200LDLT_UPD_SHARE") ? atoi(getenv("B200LDLT_UPD_SHARE")) : 296;
    const bool lookahead = !(getenv("B200LDLT_LOOKAHEAD") && atoi(getenv("B200LDLT_LOOKAHEAD")) == 0);
-   // rank-2PB trailing updates in the look-ahead chunks (k_update, pair mode)
-   const bool pairing_on = !(getenv("B200LDLT_PAIR") && atoi(getenv("B200LDLT_PAIR")) == 0);
-   // worth it where the bulk update dwarfs the panel chain (it gives up the overlap of the next block's factorisation
-   // with the bulk update): fronts of at least this many rows
-   const int pair_min_m = getenv("B200LDLT_PAIR_MINM") ? atoi(getenv("B200LDLT_PAIR_MINM")) : 8192;
-   const bool pair_dbg = getenv("B200LDLT_PAIR") && atoi(getenv("B200LDLT_PAIR")) == 2;
+   // large fronts: trailing updates through k_upd3, deferred over defer_g blocks for fronts of defer_min_m rows and more
+   const bool use_upd3 = !(getenv("B200LDLT_UPD3") && atoi(getenv("B200LDLT_UPD3")) == 0);
+   const int defer_g = getenv("B200LDLT_DEFER") ? std::max(1, atoi(getenv("B200LDLT_DEFER"))) : 4;
+   const int defer_min_m = getenv("B200LDLT_DEFER_MINM") ? atoi(getenv("B200LDLT_DEFER_MINM")) : 2048;
    const int max_groups = getenv("B200LDLT_GROUPS") ? std::max(1, std::min((int)NAUX, atoi(getenv("B200LDLT_GROUPS")))) : (int)NAUX;
    auto trace_fronts = [&](const char* what, int slot_first, int count) {
       std::vector<FrontDev> tmp(count);
@@ -1094,6 +1046,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    size_t updmap_used = 0;
    prez_c = prez_l = nullptr;
    const bool lvl_times = getenv("B200LDLT_LEVELTIMES") != nullptr;   // wall time per level (each level ends with a sync)
+   const bool timeline = getenv("B200LDLT_TIMELINE") != nullptr;
+   std::vector<cudaEvent_t> tl_ev;
+   std::vector<std::string> tl_name;
    for (int l = 0; l < P->nlevels && flag >= 0; ++l) {
       const int s0 = P->lvl_ptr[l], s1 = P->lvl_ptr[l + 1], ns = s1 - s0;
       const auto lvl_t0 = std::chrono::steady_clock::now();
@@ -1161,8 +1116,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             f.perm = Pb + oP; f.orig = f.perm + align_up((size_t)f.n + 1, 32); oP += 2 * align_up((size_t)f.n + 1, 32);
             double* wp = Wb + oW;
             oW += front_ws_doubles(f.ldl, f.n);
-            f.Wld = wp; f.Wld2 = wp + (size_t)f.ldl * f.wc; f.Wld3 = wp + 2 * (size_t)f.ldl * f.wc; f.Wo = wp + 3 * (size_t)f.ldl * f.wc;
-            f.dbuf = wp + 4 * (size_t)f.ldl * f.wc;
+            f.xw = ring_cols(f.n);
+            f.Wld = wp; f.Wo = wp + (size_t)f.ldl * f.xw;
+            f.dbuf = f.Wo + (size_t)f.ldl * f.wc;
             f.ibuf = (int*)(f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2 + (size_t)NB * f.wc);
          }
       }
@@ -1272,6 +1228,17 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             cudaEventRecord(prof_ev[prof_used], st);
          };
          auto prof_end = [&]() { cudaEventRecord(prof_ev[prof_used + 1], st); prof_used += 2; };   // profile mode is single-stream
+         // B200LDLT_TIMELINE=1: an event after every launch of the large-front chunks, printed per level (diagnostic)
+         auto mark = [&](cudaStream_t sm, const char* what, int a, int b) {
+            if (!timeline) return;
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, sm);
+            tl_ev.push_back(e);
+            char buf[64];
+            snprintf(buf, sizeof buf, "%s %s %d %d", sm == st ? "main" : "side", what, a, b);
+            tl_name.push_back(buf);
+         };
          // one chunk = a contiguous slot range of one size class, processed block by block on stream sx
          auto run_chunk = [&](int j0, int j1, cudaStream_t sx, bool single, int sidx) -> int {
             int maxm = 0, maxn = 0;
@@ -1283,40 +1250,88 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             const int ncolchunks = (maxn + 63) / 64;
             const int ycommit = 1 + ncolchunks + (maxm + 255) / 256;
             const int nouter = (maxn + PB - 1) / PB;
-            const bool la_chunk = lookahead && !o.profile && !trace && nouter >= 2 && maxm >= 1024;
-            // trailing-update work maps of this bucket: CTAs in proportion to the fronts' tile counts
-            // (shapes without failed pivots; every front of the launch keeps at least one CTA, so a
-            // front that lags behind is still updated correctly, only slower)
-            std::vector<int> map_off(nouter + 1, 0), map_na(nouter, 0);
+            // Large fronts (size class >= 3) take their trailing updates through k_upd3; with several blocks per front
+            // the schedule looks ahead: the part of an update the next block needs runs on this stream, the rest in slices
+            // on the chunk's second stream beside the next blocks' factorisation kernels (k_block: one CTA per front).
+            const bool big = single && cls(order[j0]) >= 3 && use_upd3;
+            const bool la = big && lookahead && !o.profile && !trace && nouter >= 2;
+            // blocks per trailing update of the columns behind the group (rank G * PB): C is read and written once per G blocks
+            const int G = (big && nouter >= 2 && maxm >= defer_min_m) ? std::max(1, std::min(defer_g, (int)GMAX)) : 1;
+            const int ngroups = (nouter + G - 1) / G;
+            auto nblocks_of = [&](const FrontDev& ff) { return (ff.n + PB - 1) / PB; };
+            // work maps: CTAs in proportion to the fronts' tile counts (shapes without failed pivots; every front of
+            // a launch keeps at least one CTA, so a front that lags behind is still updated correctly, only slower)
+            std::vector<int> map_off(nouter + 1, 0), map_na(nouter, 0);            // k_update / strips, per block
+            std::vector<int> bmap_off(ngroups + 1, 0);                              // k_upd3 bulk, per group
+            std::vector<int64_t> gtiles(ngroups, 0);
             {
                std::vector<int> hmap;
                std::vector<int64_t> tl;
+               auto deal = [&](int na, int64_t total, int64_t target) {
+                  for (int q = 0; q < na; ++q) {
+                     int parts = total > 0 ? (int)((tl[q] * target + total / 2) / total) : 1;
+                     parts = std::max(1, (int)std::min<int64_t>(parts, std::max<int64_t>(tl[q], 1)));
+                     // a front without work in the static picture may have some after a failed pivot (a shortened
+                     // block leaves columns of its group behind): a few CTAs that normally exit at once
+                     if (big && tl[q] == 0) parts = 4;
+                     for (int pp = 0; pp < parts; ++pp) { hmap.push_back(q); hmap.push_back(pp); hmap.push_back(parts); }
+                  }
+               };
                for (int ob = 0; ob < nouter; ++ob) {
                   int na = 0;
-                  for (int q = j0; q < j1; ++q) if (active[order[q]] && (hfr[order[q]].n + PB - 1) / PB > ob) na = q - j0 + 1;
+                  for (int q = j0; q < j1; ++q) if (active[order[q]] && nblocks_of(hfr[order[q]]) > ob) na = q - j0 + 1;
                   map_na[ob] = na;
                   tl.assign(na, 0);
                   int64_t total = 0;
+                  const int g = ob / G;
                   for (int q = 0; q < na; ++q) {
                      const FrontDev& ff = hfr[order[j0 + q]];
-                     if (!active[order[j0 + q]]) continue;
-                     const int t = ff.m - std::min(ff.n, (ob + 1) * PB);
-                     if (t <= 0 || ff.n <= ob * PB) continue;
-                     const int ntr = (t + TM - 1) / TM, ntc = (t + TN - 1) / TN;
+                     if (!active[order[j0 + q]] || ff.n <= ob * PB) continue;
+                     const int kend = std::min(ff.n, (ob + 1) * PB);
                      int64_t cnt = 0;
-                     for (int ti = 0; ti < ntr; ++ti) cnt += std::min(ntc, 2 * ti + 2);
+                     if (!big) {
+                        const int t = ff.m - kend;
+                        if (t <= 0) continue;
+                        const int ntr = (t + TM - 1) / TM, ntc = (t + TN - 1) / TN;
+                        for (int ti = 0; ti < ntr; ++ti) cnt += std::min(ntc, 2 * ti + 2);
+                     } else if (G > 1) {
+                        // the block's own update: the columns behind it up to the end of the group
+                        const int c1 = std::min(ff.m, std::max(kend, (g + 1) * G * PB));
+                        const int org = kend & ~1;
+                        if (c1 > kend) cnt = upd3::tiles_upto((c1 - org + upd3::UTN - 1) / upd3::UTN, (ff.m - org + upd3::UTM - 1) / upd3::UTM);
+                     }
                      tl[q] = cnt;
                      total += cnt;
                   }
                   // chunks that share the GPU with other streams keep to about half of the CTA slots, so that
                   // another chunk's block factorisation finds a free SM while this update runs
-                  const int64_t target = std::min<int64_t>(std::max<int64_t>(total, 1), (single ? 2 : 1) * (la_chunk ? 2 * bulk_sms : upd_share));
-                  for (int q = 0; q < na; ++q) {
-                     int parts = total > 0 ? (int)((tl[q] * target + total / 2) / total) : 1;
-                     parts = std::max(1, (int)std::min<int64_t>(parts, std::max<int64_t>(tl[q], 1)));
-                     for (int pp = 0; pp < parts; ++pp) { hmap.push_back(q); hmap.push_back(pp); hmap.push_back(parts); }
-                  }
+                  const int64_t target = big ? 148 : std::min<int64_t>(std::max<int64_t>(total, 1), (single ? 2 : 1) * upd_share);
+                  if (!big || G > 1) deal(na, total, std::min<int64_t>(target, std::max<int64_t>(total, 1)));
                   map_off[ob + 1] = (int)hmap.size();
+               }
+               if (big) {
+                  for (int g = 0; g < ngroups; ++g) {
+                     const int na = map_na[g * G];
+                     tl.assign(na, 0);
+                     int64_t total = 0;
+                     for (int q = 0; q < na; ++q) {
+                        const FrontDev& ff = hfr[order[j0 + q]];
+                        if (!active[order[j0 + q]] || ff.n <= g * G * PB) continue;
+                        const int kend = std::min(ff.n, (g + 1) * G * PB);
+                        const int c1 = G == 1 ? kend : std::min(ff.m, std::max(kend, (g + 1) * G * PB));
+                        if (c1 >= ff.m) continue;
+                        const int ntr = (ff.m - (c1 & ~1) + upd3::UTM - 1) / upd3::UTM;
+                        tl[q] = upd3::tiles_upto(ntr, ntr);
+                        total += tl[q];
+                     }
+                     gtiles[g] = total;
+                     // the SMs of the next blocks' k_block CTAs (one per front) stay free
+                     const int nkb = g + 1 < ngroups ? map_na[(g + 1) * G] : 0;
+                     const int64_t target = std::max(64, 148 - std::min(nkb, 84));
+                     deal(na, total, std::min<int64_t>(target, std::max<int64_t>(total, 1)));
+                     bmap_off[g + 1] = (int)hmap.size();
+                  }
+                  for (int g = 0; g <= ngroups; ++g) if (bmap_off[g] < map_off[nouter]) bmap_off[g] = map_off[nouter];
                }
                if (updmap_used + hmap.size() > UPDMAP_CAP) {   // staging in use by earlier copies: drain first
                   CU(cudaStreamSynchronize(st));
@@ -1328,67 +1343,127 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                if (!hmap.empty())
                   CU(cudaMemcpyAsync(d_updmap + updmap_used, pin_updmap + updmap_used, sizeof(int) * hmap.size(), cudaMemcpyHostToDevice, sx));
                for (int ob = 0; ob <= nouter; ++ob) map_off[ob] += (int)updmap_used;
+               for (int g = 0; g <= ngroups; ++g) bmap_off[g] += (int)updmap_used;
                updmap_used += hmap.size();
             }
-            // look-ahead: the trailing update of block b is split into the strip that the next block needs
-            // (on this stream) and the bulk (on the chunk's second stream, beside the factorisation of block
-            // b+1).  Worth it for large fronts with several blocks; profile / trace runs keep one stream.
-            const bool la = la_chunk;
-            const bool pairing = pairing_on && la && maxm >= pair_min_m;
-            int nbulk = 0;
+            // profile mode (bench roofline): every trailing-update launch between two events, its algorithmic flops
+            auto prof_region = [&](int ob0, int ob1, bool strip_only, bool bulk_only) {
+               // flops of the launch that applies the pivots of blocks [ob0, ob1] of every front to its region
+               const int g = ob0 / G;
+               for (int q = j0; q < j1; ++q) {
+                  const FrontDev& ff = hfr[order[q]];
+                  if (!active[order[q]] || ff.n <= ob0 * PB) continue;
+                  const double ka = ob0 * PB, kb = std::min<double>(ff.n, (ob1 + 1) * PB);
+                  const double c1 = G == 1 ? kb : std::min<double>(ff.m, std::max<double>(kb, (g + 1) * G * PB));
+                  double ca, cb;
+                  if (strip_only) { ca = kb; cb = c1; }
+                  else if (bulk_only) { ca = c1; cb = ff.m; }
+                  else { ca = kb; cb = ff.m; }
+                  if (cb > ca && kb > ka) prof_flops += (kb - ka) * (cb - ca) * (2.0 * ff.m - ca - cb + 1.0);
+               }
+            };
+            int slices_left = 0, slice_ns = 1, slice_tag = 0, slice_z = 0, slice_g = 0;   // window slices of the previous group's update
             for (int ob = 0; ob < nouter; ++ob) {
                const int na = map_na[ob];   // slots [b0, b0+na) cover every front that still has a block number ob
                if (na == 0) break;
                const int par = ob & 1;
+               const int g = ob / G, gpos = ob % G;
+               const bool glast = gpos == G - 1 || ob == nouter - 1;
                int maxw = 0;
                for (int q = 0; q < na; ++q) if (active[order[j0 + q]]) maxw = std::max(maxw, std::min(PB, hfr[order[j0 + q]].n - ob * PB));
                const int wcap = (maxw + NB - 1) / NB * NB;
                // blocks shortened by failed pivots leave `done` behind ob*PB, so the row grid covers the
                // whole front; CTAs above the block exit at once
                const int yapply = std::max(1, (maxm + AR - 1) / AR);
-               // X buffer of this block: paired updates read two buffers while the next block writes the third
-               const int xb = pairing ? ob % 3 : par;
-               if (wcap == NB) k_block<0><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
-               else if (wcap == 2 * NB) k_block<1><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
-               else k_block<2><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, la ? 1 : 0);
-               k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, wcap, xb);
-               k_commit<<<dim3(na, ycommit), 256, 0, sx>>>(d_fr, lst, b0, ncolchunks, par, xb);
+               bool slice_running = false;
+               if (slices_left > 0) {
+                  // one slice of the previous group's update beside this block's factorisation
+                  const int s = slice_ns - slices_left;      // 1 .. ns-1
+                  const int nct = (bmap_off[slice_g + 1] - bmap_off[slice_g]) / 3;
+                  if (nct > 0) {
+                     CU(cudaEventRecord(ev_commit[sidx][0], sx));
+                     CU(cudaStreamWaitEvent(bulk[sidx], ev_commit[sidx][0], 0));
+                     k_upd3<<<nct, upd3::THREADS, upd3::SMEM, bulk[sidx]>>>(d_fr, lst, b0, d_updmap + bmap_off[slice_g], 1, slice_g & 1, slice_tag,
+                                                                            s - 1, s, slice_ns - 1, slice_z);
+                     CU(cudaEventRecord(ev_bulk[sidx][0], bulk[sidx]));
+                     mark(bulk[sidx], "slice", ob, s);
+                     ++launches;
+                     slice_running = true;
+                  }
+                  --slices_left;
+               }
+               // a front that sees a failed pivot stalls (instead of parking the failed columns at once) whenever other
+               // work on it may be outstanding: a concurrent slice, or the deferred update of its group
+               const int stall_on_fail = (la || G > 1) ? 1 : 0;
+               if (wcap == NB) k_block<0><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, stall_on_fail);
+               else if (wcap == 2 * NB) k_block<1><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, stall_on_fail);
+               else k_block<2><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, stall_on_fail);
+               if (big) mark(sx, "block", ob, na);
+               if (slice_running) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][0], 0));
+               k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, wcap);
+               if (big) mark(sx, "apply", ob, yapply);
+               k_commit<<<dim3(na, ycommit), 256, 0, sx>>>(d_fr, lst, b0, ncolchunks, par, gpos, G, g + 1);
+               if (big) mark(sx, "commit", ob, 0);
                launches += 3;
                const int nct = (map_off[ob + 1] - map_off[ob]) / 3;
-               if (!la) {
-                  if (o.profile) {
-                     for (int q = 0; q < na; ++q) {
-                        const FrontDev& ff = hfr[order[j0 + q]];
-                        if (!active[order[j0 + q]]) continue;
-                        double je = std::min<double>(ff.n, (ob + 1) * PB), kc2 = je - ob * PB, tt = ff.m - je;
-                        if (kc2 > 0 && tt > 0) prof_flops += kc2 * tt * (tt + 1);
-                     }
-                     prof_begin();
-                  }
-                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 0, 0, 0, xb);
+               if (!big) {
+                  if (o.profile) { prof_region(ob, ob, false, false); prof_begin(); }
+                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par);
                   if (o.profile) prof_end();
                   ++launches;
                } else {
-                  if (pair_dbg && par == 1) {   // debugging aid (B200LDLT_PAIR=2): the deferred bulk as a launch of its own
-                     if (ob > 0) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][0], 0));
-                     k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], 0, 2, 0, 0, (xb + 2) % 3);
+                  if (G > 1 && nct > 0) {
+                     if (o.profile) { prof_region(ob, ob, true, false); prof_begin(); }
+                     k_upd3<<<nct, upd3::THREADS, upd3::SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], 0, par, 0, 0, 0, 1, 0);
+                     mark(sx, "strip", ob, nct);
+                     if (o.profile) prof_end();
                      ++launches;
                   }
-                  CU(cudaEventRecord(ev_commit[sidx][par], sx));
-                  CU(cudaStreamWaitEvent(bulk[sidx], ev_commit[sidx][par], 0));
-                  k_update<<<nct, 256, UPD_SMEM, bulk[sidx]>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 2, (pairing && !(pair_dbg && par == 1)) ? 1 : 0, (ob + 1) * PB, xb);
-                  CU(cudaEventRecord(ev_bulk[sidx][par], bulk[sidx]));
-                  ++nbulk;
-                  // the strip overlaps the region of the previous block's bulk update
-                  if (ob > 0) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][par ^ 1], 0));
-                  k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par, 1, (pairing && !(pair_dbg && par == 1)) ? 1 : 0, (ob + 1) * PB, xb);
-                  launches += 2;
+                  if (glast) {
+                     const int nctb = (bmap_off[g + 1] - bmap_off[g]) / 3;
+                     // slices beside the next group's blocks, as many tiles as fit behind their k_block launches
+                     const int nnext = (la && ob + 1 < nouter) ? std::min(G, nouter - (ob + 1)) : 0;
+                     int z = 256;
+                     if (nnext > 0 && nctb > 0 && gtiles[g] > 0) {
+                        const double tile_us = 20.0 * G;                         // 128 x 128 x (G PB) at the kernel's rate
+                        const int per_window = std::max(1, (int)(66.0 / tile_us));
+                        const double cap = (double)nnext * nctb * per_window;
+                        z = (int)std::ceil(256.0 * std::max(0.0, 1.0 - cap / (double)gtiles[g]));
+                        z = std::max(0, std::min(256, z));
+                     }
+                     if (nctb > 0) {
+                        if (o.profile) { prof_region(g * G, ob, false, true); prof_begin(); }
+                        k_upd3<<<nctb, upd3::THREADS, upd3::SMEM, sx>>>(d_fr, lst, b0, d_updmap + bmap_off[g], 1, g & 1, g + 1, -1, 0, 1, z);
+                        mark(sx, "slice0", ob, z);
+                        if (o.profile) prof_end();
+                        ++launches;
+                     }
+                     if (nnext > 0 && z < 256) { slices_left = nnext; slice_ns = nnext + 1; slice_tag = g + 1; slice_z = z; slice_g = g; }
+                     else if (nnext > 0 && nctb > 0) {
+                        // everything already ran in slice 0 (bound0 = T whenever z = 256): nothing left for the windows
+                        slices_left = 0;
+                     }
+                  }
                }
                if (trace) trace_fronts("block", b0, na);
             }
-            if (nbulk > 0) {   // the closing step may move columns: every bulk update has to be finished
-               CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][0], 0));
-               if (nbulk > 1) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][1], 0));
+            if (big && G > 1) {
+               // what stalled fronts still owe (deferred pivots of an unfinished group)
+               int nf = 0;
+               std::vector<int> fm;
+               int nfl = 0;
+               for (int q = j0; q < j1; ++q) if (active[order[q]] && nblocks_of(hfr[order[q]]) >= 2) ++nfl;
+               const int fparts = std::max(1, 148 / std::max(nfl, 1));
+               for (int q = j0; q < j1; ++q)
+                  if (active[order[q]] && nblocks_of(hfr[order[q]]) >= 2)
+                     for (int pp = 0; pp < fparts; ++pp) { fm.push_back(q - j0); fm.push_back(pp); fm.push_back(fparts); ++nf; }
+               if (nf > 0 && updmap_used + fm.size() <= UPDMAP_CAP) {
+                  memcpy(pin_updmap + updmap_used, fm.data(), sizeof(int) * fm.size());
+                  CU(cudaMemcpyAsync(d_updmap + updmap_used, pin_updmap + updmap_used, sizeof(int) * fm.size(), cudaMemcpyHostToDevice, sx));
+                  k_upd3<<<nf, upd3::THREADS, upd3::SMEM, sx>>>(d_fr, lst, b0, d_updmap + updmap_used, 2, 0, 0, 0, 0, 1, 0);
+                  updmap_used += fm.size();
+                  ++launches;
+               } else if (nf > 0) return SSIDS_ERROR_ALLOCATION;
             }
             k_block<0><<<j1 - j0, 256, block_smem_bytes(NB), sx>>>(d_fr, lst, b0, prm, 1, NB, 0, 0);
             ++launches;
@@ -1407,7 +1482,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             // a few large fronts: split them over streams so that one group's block factorisation
             // overlaps another group's trailing update
             int G = 1;
-            if (!o.profile && !trace && nact >= 2 && nact <= 128 && c >= 2) G = std::min(nact, max_groups);
+            if (!o.profile && !trace && nact >= 2 && nact <= 128 && (c == 2 || (c > 2 && !use_upd3))) G = std::min(nact, max_groups);
             if (G == 1) {
                int rc2 = run_chunk(i0, i1, st, true, 0);
                if (rc2) return stats.flag = rc2;
@@ -1467,9 +1542,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          const int ncolchunks = (maxn + 63) / 64;
          const int wcap = (std::min(maxn, PB) + NB - 1) / NB * NB;
          k_block<2><<<nt, 256, block_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, 0, wcap, 0, 0);
-         k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap, 0);
-         k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks, 0, 0);
-         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, nullptr, 0, 0, 0, 0, 0);
+         k_apply<<<dim3(nt, std::max(1, (maxm + AR - 1) / AR)), 256, apply_smem_bytes(wcap), st>>>(d_fr, d_list, 0, prm, wcap);
+         k_commit<<<dim3(nt, 1 + ncolchunks + (maxm + 255) / 256), 256, 0, st>>>(d_fr, d_list, 0, ncolchunks, 0, 0, 1, 0);
+         k_update<<<dim3(nt, 148), 256, UPD_SMEM, st>>>(d_fr, d_list, 0, nullptr, 0);
          if (trace) for (int s : tpp_list) trace_fronts("retry", s, 1);
          k_block<0><<<nt, 256, block_smem_bytes(NB), st>>>(d_fr, d_list, 0, prm, 1, NB, 0, 0);
          launches += 5;
@@ -1496,6 +1571,19 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       }
       if (flag < 0) break;
       for (int s = s0; s < s1; ++s) if (active[s]) { num_delay += hfr[s].n - hfr[s].nelim; hfr[s].active = 0; }
+      if (timeline && !tl_ev.empty()) {
+         cudaDeviceSynchronize();
+         float prev_main = 0, prev_side = 0;
+         for (size_t q = 0; q < tl_ev.size(); ++q) {
+            float t = 0;
+            cudaEventElapsedTime(&t, tl_ev[0], tl_ev[q]);
+            const bool side = tl_name[q][0] == 's';
+            fprintf(stderr, "[timeline] L%d %8.1f us (+%7.1f) %s\n", l, t * 1e3, (t - (side ? prev_side : prev_main)) * 1e3, tl_name[q].c_str());
+            (side ? prev_side : prev_main) = t;
+         }
+         for (cudaEvent_t e : tl_ev) cudaEventDestroy(e);
+         tl_ev.clear(); tl_name.clear();
+      }
       if (lvl_times)
          fprintf(stderr, "[b200ldlt] level %d fronts %d launches %lld wall %.3f ms\n", l, ns, (long long)(launches - lvl_l0),
                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - lvl_t0).count());

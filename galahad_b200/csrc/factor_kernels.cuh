@@ -624,7 +624,6 @@ __global__ void __launch_bounds__(256, KIND < 2 ? 2 : 1) k_block(FrontDev* fr, c
 //    X_j = Y inv(L_jj)^T                      DMMA with the explicit 32x32 inverses from k_block
 //    L_j = X_j D^{-1} (in place), X_j kept in Wld, a-posteriori test |l| <= 1/u
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double* xbuf(const FrontDev& f, int xb) { return xb == 0 ? f.Wld : (xb == 1 ? f.Wld2 : f.Wld3); }
 
 constexpr int AR = 64;             // rows per CTA in k_apply
 constexpr int LDX = AR + 4;        // k-major smem leading dimension, = 4 mod 16: conflict-free fragments
@@ -634,11 +633,12 @@ __host__ __device__ inline size_t apply_smem_bytes(int wcap) {
           sizeof(int) * 2 * PB;
 }
 
-__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap, int xb) {
+__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap) {
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0 || f.stall) return;
-   double* const Wldp = xbuf(f, xb);
+   double* const Wldp = f.Wld;     // X ring: pivot p of the front in column p mod xw
+   const int xw = f.xw;
    const int done = f.done, m = f.m;
    const int r0 = done + w + blockIdx.y * AR;
    if (r0 >= m) return;
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, in
                }
                if (!prm.posdef && !(fabs(l) <= prm.lim)) myfail = min(myfail, kk);
                Lp[(size_t)(done + kk) * ldl + r] = l;
-               Wldp[(size_t)kk * ldl + r] = xv;
+               Wldp[(size_t)((done + kk) % xw) * ldl + r] = xv;
             }
          }
       }
@@ -774,7 +774,12 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, in
 // finished columns whose rows [done, done+w) follow the pivot order, then chunks of 256 rows
 // restoring failed columns.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, int slot0, int ncolchunks, int par, int xb) {
+// Update records (thread 0 of the first CTA).  urec[par]: this block's pivots and the end of its strip.  With deferred
+// updates (G > 1 blocks per group, look-ahead chunks) the block's own update stops at the end of the group's columns and
+// the columns behind them wait for the group's last block, whose record brec[gpar] covers the pivots of the whole group;
+// until then `pend` says what is owed (a front that stalls on a failed pivot is paid by the chunk's closing flush).
+__global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, int slot0, int ncolchunks, int par, int gpos, int G,
+                                                int gtag) {
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0 || f.stall) return;
@@ -785,8 +790,29 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
    const int y = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    if (y == 0) {
       // what the trailing updates of this block need: first pivot column, accepted pivots, end of the strip
-      if (tid == 0) { f.urec[par][0] = done; f.urec[par][2] = min(m, done + w + PB); f.urec[par][1] = nelim; }
-      double* const Wldp = xbuf(f, xb);
+      if (tid == 0) {
+         const int kend = done + nelim;
+         const int gk0 = gpos == 0 ? done : f.gk0;
+         if (gpos == 0) f.gk0 = done;
+         const bool last = gpos == G - 1 || done + w >= f.gend;       // no further block of this group for this front
+         // G == 1: one region behind the accepted pivots (failed columns included), whose first columns -- the next
+         // block's -- form the part the next block waits for
+         const int c1 = G == 1 ? kend : min(m, max(done + w, gk0 + G * PB));
+         const int gse = G == 1 ? min(m, done + w + PB) : min(m, c1 + G * PB);
+         f.urec[par][0] = done; f.urec[par][2] = c1; f.urec[par][1] = nelim;
+         if (g_upd_debug)
+            printf("[k_commit] front %d m %d n %d done %d w %d nelim %d gend %d gpos %d G %d tag %d gk0 %d c1 %d last %d\n", f.slot, m, f.n, done, w,
+                   nelim, f.gend, gpos, G, gtag, gk0, c1, (int)last);
+         if (last) {
+            const int gp = (gtag - 1) & 1;
+            f.brec[gp][0] = gk0; f.brec[gp][1] = kend; f.brec[gp][2] = c1; f.brec[gp][3] = gse; f.brec[gp][4] = gtag;
+            f.pend[3] = 0;
+         } else {
+            f.pend[0] = gk0; f.pend[1] = kend; f.pend[2] = c1; f.pend[3] = 1;
+         }
+      }
+      double* const Wldp = f.Wld;
+      const int xw = f.xw;
       const double* dk = f.dbuf + 2 * (size_t)PB * f.wc;
       if (nelim < w) {
          // failed columns get their original values back (block part from A0 in pivot order; CopyBackup,
@@ -818,7 +844,7 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
             for (int i = nelim + lane; i < w; i += 32) {
                double x = f.L[(size_t)(done + k) * ldl + done + i] * d0;
                if (pt != 0) x += f.L[(size_t)(done + kn) * ldl + done + i] * d1;
-               Wldp[(size_t)k * ldl + done + i] = x;
+               Wldp[(size_t)((done + k) % xw) * ldl + done + i] = x;
             }
          }
       }
@@ -864,27 +890,17 @@ __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, i
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: FP64 tensor-core Schur update.  C(r,c) -= sum_k A(r,k) B(c,k) over the lower triangle of
-// the region cols [cbeg, cend), rows >= col, with A = L(:, k0:k0+kc) and B = Wld(:, kofs:kofs+kc).
-// CTA = 256 threads = 8 warps (4 x 2); CTA tile 128 x 128; warp tile 32 x 64 = 4 x 8 m8n8k4 MMAs.
-// ------------------------------------------------------------------------------------------
+// K4: FP64 tensor-core Schur update of the small and medium fronts (and of the synchronous retry rounds):
+// C(r,c) -= sum_k A(r,k) B(c,k) over the lower triangle of the columns behind the accepted pivots of the block
+// urec[par], with A = L(:, k0:k0+kc) and B = the pivots' columns of the X ring.  The large fronts of the look-ahead
+// chunks go through k_upd3 (upd_kernels.cuh).
 // CTA = 256 threads = 8 warps (4 x 2); CTA tile 128 x 64; warp tile 32 x 32 = 4 x 4 m8n8k4 MMAs;
 // two CTAs per SM.  ncu (profiles/r1_notes.md) showed the kernel bound by per-warp instruction
 // issue around the MMAs, so interior tiles take a path without bounds predicates and with
 // strength-reduced addresses, and tile coordinates advance incrementally.
 // Work distribution: with `map` (one int3 per CTA: front offset, part, parts) CTAs are dealt to the fronts
 // of the launch in proportion to their tile counts; without it the grid is (fronts, parts).
-// mode 0: the whole region; 1: only the strip (column tiles that start before urec[2], i.e. the next
-// block's columns and the failed columns of this one); 2: everything else (look-ahead schedule).
-// pair != 0 (look-ahead chunks): updates of rank 2 PB.  The bulk update of an even block that has a partner (the front
-// has columns beyond next_col) is deferred; the odd block's strip and bulk then apply BOTH blocks at once,
-// k = [k0 - PB, k0 + kc), the B operand from Wld for the even and Wld2 for the odd block, so that C is read and
-// written once per 2 PB pivots.  The PB columns behind the even block (the odd block's failed columns and, if the odd
-// block is short, the columns after it) already have the even block's update from its strip: they see zeros in the
-// even block's part of B.  If the odd block accepted nothing (the front stalled
-// on a failed pivot of the even block), its bulk launch flushes the even block's deferred bulk instead.
-__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0, const int* __restrict__ map,
-                                                   int par, int mode_in, int pair, int next_col, int xb) {
+__global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list, int slot0, const int* __restrict__ map, int par) {
    int fq, part, nparts;
    if (map) { fq = map[3 * blockIdx.x]; part = map[3 * blockIdx.x + 1]; nparts = map[3 * blockIdx.x + 2]; }
    else { fq = blockIdx.x; part = blockIdx.y; nparts = gridDim.y; }
@@ -892,34 +908,14 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    if (f.flag < 0) return;
    // pivots accepted in the block (recorded by k_commit); the region starts right behind them, so columns
    // of the block that failed (restored by k_commit) receive the update as well
-   int rp = par;              // parity of the record of a single-block update
-   int mode = mode_in;
-   int kce = 0, colsplit = 0; // pair update: pivots of the even block in the k range, end of the even block's strip
-   if (pair) {
-      if (par == 0) {
-         if (mode == 2 && f.n > next_col) return;          // deferred to the partner
-      } else if (f.urec[1][1] <= 0) {
-         // flush the even block's deferred bulk; in the STRIP launch, i.e. on the chunk's own stream before the next
-         // block's kernels (which reset the even record)
-         if (mode != 1) return;
-         rp = 0;
-         mode = 2;
-         xb = (xb + 2) % 3;
-      } else {
-         kce = PB;
-         colsplit = f.urec[1][0] + PB;      // the even block's strip went PB columns past its own block
-      }
-   }
-   const int kc = kce + f.urec[rp][1];
+   const int kc = f.urec[par][1];
    const int m = f.m;
-   const int k0 = f.urec[rp][0] - kce, cbeg = k0 + kc, cend = m;
+   const int k0 = f.urec[par][0], cbeg = k0 + kc, cend = m;
    if (kc <= 0 || cbeg >= cend) return;
    // The tile grid starts at the even index org <= cbeg: every row offset of the operands and of C is then a
    // multiple of 16 bytes (ldl, ldc are even, C is shifted by n & 1), so all operand loads are 16-byte copies.
    // When cbeg is odd the grid has one extra leading row and column, masked in the first row / column of tiles.
    const int org = cbeg & ~1;
-   const int tjs = (f.urec[rp][2] - org + TN - 1) / TN;   // column tiles [0, tjs) form the strip
-   const int kofs = 0;
    const int ntr = (m - org + TM - 1) / TM;
    const int ntc = (cend - org + TN - 1) / TN;
    extern __shared__ double smem[];
@@ -929,47 +925,38 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
    const int wr = warp & 3, wc = warp >> 2;  // 4 x 2 warps; warp tile origin: rows wr*32, cols wc*32
    const int g = lane >> 2, t4 = lane & 3;
    const size_t ldl = f.ldl;
-   const int fn = f.n, ldc = f.ldc;
+   const int fn = f.n, ldc = f.ldc, xw = f.xw;
    double* const Lp = f.L;
    double* const Cp = f.C;
    const double* Abase = Lp + (size_t)k0 * ldl;
-   const double* Bbase = xbuf(f, xb) + (size_t)kofs * ldl;   // single: the block's X; pair: the odd block's
-   const double* Bev = xbuf(f, (xb + 2) % 3);                 // pair: the even block's X (the buffer before in the rotation)
+   const double* const Xp = f.Wld;          // pivot p in column p mod xw
    const bool vec16 = true;
-   const int rclamp = (int)ldl - 2;         // last even row index inside a column of L / Wld
+   const int rclamp = (int)ldl - 2;         // last even row index inside a column of L / X
    const int nchunk = (kc + BK - 1) / BK;
    // tile (ti,tj) touches the lower triangle iff tj <= 2*ti+1 (TM = 2*TN, shared origin cbeg);
    // tiles are numbered row by row; a CTA walks its tiles incrementally.  The first k-chunk of the
    // NEXT tile is requested while the last chunk of the current one is multiplied, and its C tile
    // is pulled towards L2.
    auto normalise = [&](int& ti, int& tj) -> bool {
-      for (;;) {
-         while (ti < ntr) { const int wd = min(ntc, 2 * ti + 2); if (tj < wd) break; tj -= wd; ++ti; }
-         if (ti >= ntr) return false;
-         if (mode == 0 || (mode == 1) == (tj < tjs)) return true;
-         tj += nparts;            // not this launch's tile: take the next one of the walk
-      }
+      while (ti < ntr) { const int wd = min(ntc, 2 * ti + 2); if (tj < wd) break; tj -= wd; ++ti; }
+      return ti < ntr;
    };
    auto load_stage = [&](int rbase, int cbase, bool full, int chunk, int buf) {
       const int kb = chunk * BK;
       double* as = As + buf * BK * LDA;
       double* bs = Bs + buf * BK * LDB;
-      const bool epart = kb < kce;                          // chunk of the even block's pivots (PB is a multiple of BK)
-      const double* Bsrc = epart ? Bev + (size_t)kb * ldl : Bbase + (size_t)(kb - kce) * ldl;
       const int klim = kc - kb;                             // valid k rows of the chunk
-      const bool split = epart && cbase < colsplit;         // tile holds columns that must not see the even block
-      if (full && klim >= BK && !split) {
+      if (full && klim >= BK) {
          // thread -> (k row = q*4 + tid/64, piece (tid%64)*2) for A; (q*8 + tid/32, (tid%32)*2) for B
          const double* pa = Abase + (size_t)(kb + (tid >> 6)) * ldl + rbase + (tid & 63) * 2;
          double* sa_ = as + (tid >> 6) * LDA + (tid & 63) * 2;
          const size_t sta = 4 * ldl;
 #pragma unroll
          for (int q = 0; q < 8; ++q) cp_async16(sa_ + q * 4 * LDA, pa + q * sta, 16);
-         const double* pb = Bsrc + (size_t)(tid >> 5) * ldl + cbase + (tid & 31) * 2;
          double* sb_ = bs + (tid >> 5) * LDB + (tid & 31) * 2;
-         const size_t stb = 8 * ldl;
+         const int kr = k0 + kb + (tid >> 5), cc = cbase + (tid & 31) * 2;
 #pragma unroll
-         for (int q = 0; q < 4; ++q) cp_async16(sb_ + q * 8 * LDB, pb + q * stb, 16);
+         for (int q = 0; q < 4; ++q) cp_async16(sb_ + q * 8 * LDB, Xp + (size_t)((kr + q * 8) % xw) * ldl + cc, 16);
       } else {
          // edge tiles and short k-chunks: the same 16-byte copies with the row index clamped into the column
          // (rows / columns beyond the front are never stored, and every output element only sees its own row of
@@ -981,23 +968,12 @@ __global__ void __launch_bounds__(256, 2) k_update(FrontDev* fr, const int* list
             const int nb = (kk < klim) ? 16 : 0;
             cp_async16(as + kk * LDA + rr, nb ? Abase + (size_t)(kb + kk) * ldl + ra : Abase, nb);
          }
-         if (!split) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-               const int e = q * 256 + tid, kk = e >> 5, rr = (e & 31) * 2;
-               const int cb = min(cbase + rr, rclamp);
-               const int nb = (kk < klim) ? 16 : 0;
-               cp_async16(bs + kk * LDB + rr, nb ? Bsrc + (size_t)kk * ldl + cb : Bsrc, nb);
-            }
-         } else {
-            // column by column: zeros for the odd block's failed columns (c < colsplit)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-               const int e = q * 256 + tid, kk = e >> 6, cc = e & 63;
-               const int cb = cbase + cc;
-               const bool ok = kk < klim && cb >= colsplit;
-               cp_async8(bs + kk * LDB + cc, ok ? Bsrc + (size_t)kk * ldl + min(cb, rclamp + 1) : Bsrc, ok);
-            }
+         for (int q = 0; q < 4; ++q) {
+            const int e = q * 256 + tid, kk = e >> 5, rr = (e & 31) * 2;
+            const int cb = min(cbase + rr, rclamp);
+            const int nb = (kk < klim) ? 16 : 0;
+            cp_async16(bs + kk * LDB + rr, nb ? Xp + (size_t)((k0 + kb + kk) % xw) * ldl + cb : Xp, nb);
          }
       }
       cp_async_commit();

@@ -32,7 +32,7 @@ struct SlsData {
    std::vector<double> val;
    void* akeep = nullptr;
    void* fkeep = nullptr;
-   bool analysed = false, factorized = false, must_be_definite = false, map_set = false;
+   bool analysed = false, factorized = false, must_be_definite = false, map_set = false, scale_set = false;
 };
 
 double now() {
@@ -197,7 +197,7 @@ void sls_analyse_matrix_perm(sls_control_type* control, void** data, int* status
    }
    d->n = n;
    d->type = ty == "coordinate" ? 0 : ty == "sparse_by_rows" ? 1 : 2;
-   d->must_be_definite = false;
+   d->must_be_definite = control->pivot_control == 2 || control->pivot_control == 3;   // sls.f90:2227-2228
    // user's lower triangle as 1-based coordinates (sls.f90:2869-2909)
    d->urow.clear(); d->ucol.clear();
    if (d->type == 0) {
@@ -218,6 +218,11 @@ void sls_analyse_matrix_perm(sls_control_type* control, void** data, int* status
    inf.entries = d->ne;
    sls_coord_to_sorted_csr(n, d->ne, d->urow.data(), d->ucol.data(), d->maps.data(), d->ptr.data(), &inf.duplicates,
                            &inf.out_of_range, &inf.upper, &inf.missing_diagonals);
+   if (d->must_be_definite && inf.missing_diagonals > 0) {   // sls.f90:2326-2329, 2739-2742
+      d->analysed = false;
+      *status = inf.status = GALAHAD_ERROR_INERTIA;
+      return;
+   }
    const int nz = d->ptr[n] - 1;
    d->col.assign(nz, 0);
    d->val.assign(nz, 0.0);
@@ -239,6 +244,7 @@ void sls_analyse_matrix_perm(sls_control_type* control, void** data, int* status
    inf.real_size_factors = inf.integer_size_factors = -1;   // SSIDS leaves them unset too (sbls.f90:4132)
    d->analysed = inf.status == GALAHAD_OK;
    d->map_set = false;          // new MAPS: uploaded again by the next factorize
+   d->scale_set = false;
    d->factorized = false;
    inf.time.clock_analyse = now() - t0;
    inf.time.analyse_external = si.time_analyse;
@@ -264,7 +270,6 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
    (void)ne;
    double t0 = now();
    const int n = d->n;
-   (void)n;
    // pivot_control 2/3 -> must_be_definite -> Cholesky path (sls.f90:2227-2228, 4282)
    const int posdef = (d->control.pivot_control == 2 || d->control.pivot_control == 3) ? 1 : 0;
    b200ldlt_options o = to_solver(d->control);
@@ -276,6 +281,35 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
       if (mf >= 0) mf = b200ldlt_set_user_matrix(d->akeep, &d->fkeep, d->ne, d->urow.data(), d->ucol.data(), &o, &si);
       d->map_set = mf >= 0;
    }
+   // control%scaling (sls.f90:3558, 3766-3860, 1405-1413).  3: SLS computes symmetric infinity-norm equilibration factors
+   // itself (MC77 with job 0 there, an HSL stub in a stock build) and factorises S A S: here the factors come from
+   // the engine's equilibration (b200ldlt_equilib_scale, the restatement of spral/scaling.f90 inf_norm_equilib_sym --
+   // the same Ruiz iteration MC77 runs in that norm), computed from the gathered values.  1 (MC64), 2 (MC77 one-norm)
+   // and -1, -2, -3 (SSIDS's Hungarian / auction / matching-order scalings) have no implementation behind them.
+   const int sc = d->control.scaling;
+   if (sc != 0 && sc != 3) {
+      *status = inf.status = GALAHAD_UNAVAILABLE_OPTION;
+      d->factorized = false;
+      return;
+   }
+   if (d->map_set && sc == 3) {
+      const int nz = d->ptr[n] - 1;
+      std::vector<double> hv(nz, 0.0), sf(n, 1.0);
+      for (int l = 0; l < d->ne; ++l) {          // the gather of sls.f90:4106-4147 on the host, for the factors only
+         const int k = d->maps[l];
+         if (k > 0) hv[k - 1] += val[l]; else if (k < 0) hv[-k - 1] += val[l];
+      }
+      std::vector<int64_t> p0(n + 1);
+      std::vector<int> r0(nz);
+      for (int i = 0; i <= n; ++i) p0[i] = d->ptr[i] - 1;
+      for (int k = 0; k < nz; ++k) r0[k] = d->col[k] - 1;
+      b200ldlt_equilib_scale(n, p0.data(), r0.data(), hv.data(), sf.data(), nullptr);
+      if (b200ldlt_set_scaling(d->akeep, &d->fkeep, sf.data(), &o, &si) < 0) d->map_set = false;
+      d->scale_set = d->map_set;
+   } else if (d->map_set && d->scale_set) {
+      b200ldlt_set_scaling(d->akeep, &d->fkeep, nullptr, &o, &si);
+      d->scale_set = false;
+   }
    if (d->map_set) b200ldlt_factor_mapped(d->akeep, &d->fkeep, posdef, d->ne, val, &o, &si);
    // (set_value_map only fails without a CUDA device; si then carries -51 and there is no other path)
    int dup = inf.duplicates, oor = inf.out_of_range, up = inf.upper, md = inf.missing_diagonals, ents = inf.entries;
@@ -284,7 +318,8 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
    inf.duplicates = dup; inf.out_of_range = oor; inf.upper = up; inf.missing_diagonals = md; inf.entries = ents;
    inf.time = tm;
    inf.num_zero = d->n - si.matrix_rank;
-   if (si.flag == -6) inf.status = GALAHAD_ERROR_INERTIA;   // not positive definite where required (sls.h status -20)
+   // (a matrix that is not positive definite where that was required, SSIDS flag -6, reads GALAHAD_ERROR_RESTRICTIONS
+   // through the table above exactly as SLS_copy_inform_from_ssids has it, sls.f90:1768-1769)
    inf.real_size_factors = inf.integer_size_factors = -1;
    d->factorized = inf.status == GALAHAD_OK;
    inf.time.clock_factorize = now() - t0;

@@ -141,6 +141,11 @@ int b200ldlt_factor_mapped(void *akeep, void **fkeep, int posdef, int ne, const 
 int b200ldlt_factor_scaled(void *akeep, void **fkeep, int posdef, const double *val, double *scale,
                            const b200ldlt_options *opt, b200ldlt_inform *inf);
 int b200ldlt_equilib_scale(int n, const int64_t *ptr, const int *row, const double *val, double *scaling, int *iterations);
+/* The scaling alone: `scale` (n factors, original variable order, host) applies to every later factorisation of this
+ * fkeep and to its solves, NULL clears it.  What the SLS layer uses when it computes the factors itself
+ * (data%SCALE with explicit_scaling, sls.f90:3558) and the values arrive through b200ldlt_factor_mapped. */
+int b200ldlt_set_scaling(void *akeep, void **fkeep, const double *scale, const b200ldlt_options *opt,
+                         b200ldlt_inform *inf);
 
 /* Iterative refinement on the device (the loop of SLS_solve_ir, sls.f90:4751-4947): x_0 = 0, r_0 = b; repeat
  * { solve A dx = r; x += dx; r = b - A x } until max|r_i| < max(stop_absolute, stop_relative max|b_i|) or

@@ -338,14 +338,17 @@ def _arms_problem(arms, ns, kind, seed=3):
     return A, dict(n=n, ptr=ptr, row=row, val=val, order=np.arange(n, dtype=np.int32), inertia=(n - neg, neg, 0))
 
 
-def test_rank_256_updates(monkeypatch):
-    """The look-ahead schedule with paired blocks (k_update pair mode: the even block's bulk update deferred and
-    applied together with the odd block's, B200LDLT_PAIR_MINM lowers the front size from which it is used):
-    fronts with a short last block, several fronts of different block counts in one launch, failed pivots in
-    either block of a pair (stall + flush), and a sparse problem; against the eigenvalues / the unpaired run."""
-    monkeypatch.setenv("B200LDLT_PAIR_MINM", "0")
+@pytest.mark.parametrize("defer", [4, 2, 3])
+def test_deferred_updates(monkeypatch, defer):
+    """The look-ahead schedule of the large fronts (k_upd3): the columns behind a group of `defer` blocks get the
+    group's pivots in one trailing update of rank defer * 128, cut into a part on the critical path and slices beside
+    the next blocks (B200LDLT_DEFER_MINM lowers the front size from which groups are used).  Fronts with a short last
+    block, several fronts of different block counts in one launch, failed pivots anywhere in a group (stall + closing
+    flush), and a sparse problem; against the eigenvalues / the run without groups."""
+    monkeypatch.setenv("B200LDLT_DEFER_MINM", "0")
+    monkeypatch.setenv("B200LDLT_DEFER", str(defer))
     for arms, ns, kind in (((300, 200, 520), 900, "spd"), ((300,), 800, "indef"), ((520, 300), 1000, "indef"),
-                           ((129, 257), 1000, "spd"), ((640,), 1100, "indef")):
+                           ((129, 257), 1000, "spd"), ((640,), 1100, "indef"), ((1100, 700), 1300, "spd")):
         A, prob = _arms_problem(arms, ns, kind)
         s, flag = gpu_factor(prob)
         assert flag >= 0 and s.inform.num_neg == prob["inertia"][1], (arms, kind)
@@ -366,7 +369,30 @@ def test_rank_256_updates(monkeypatch):
     s, flag = gpu_factor(prob)
     f, x = s.solve(b)
     assert flag == 0 and P.backward_error(prob, x, b) <= 1e-14
-    monkeypatch.setenv("B200LDLT_PAIR", "0")
+    monkeypatch.setenv("B200LDLT_DEFER", "1")
     s0, flag0 = gpu_factor(prob)
     f, x0 = s0.solve(b)
     assert np.abs(x - x0).max() <= 1e-12 * np.abs(x0).max()
+    monkeypatch.setenv("B200LDLT_UPD3", "0")       # the small-front kernel on every front
+    s1, flag1 = gpu_factor(prob)
+    f, x1 = s1.solve(b)
+    assert flag1 == 0 and np.abs(x - x1).max() <= 1e-12 * np.abs(x1).max()
+
+
+def test_reanalyse_on_a_live_handle():
+    """analyse, factor, analyse, factor on one Solver: the fkeep made from the first akeep outlives it until the next
+    factorisation replaces it (the akeep is shared with its fkeeps); freeing akeep before fkeep is legal as well."""
+    p1, p2 = P.laplace_problem(6), P.kkt_grid_problem(6)
+    s = Solver()
+    for prob in (p1, p2, p1):
+        assert s.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"]) >= 0
+        assert s.factor(prob["val"]) >= 0
+        xs, b = rhs_for(prob)
+        f, x = s.solve(b)
+        assert f >= 0 and P.backward_error(prob, x, b) <= 1e-14 and s.inform.num_neg == prob["inertia"][1]
+    import ctypes as C
+    none = C.c_void_p()
+    s.L.b200ldlt_free(C.byref(s.akeep), C.byref(none))       # akeep first ...
+    assert not s.akeep.value
+    s.L.b200ldlt_free_fkeep(C.byref(s.fkeep))                # ... its fkeep afterwards
+    assert not s.fkeep.value

@@ -106,7 +106,9 @@ def test_provided_order_and_definite_path():
     s = SLS()
     s.control.pivot_control = 2                                      # indefinite matrix on the definite path
     s.analyse_matrix(N, "coordinate", 7, ROW, COL)
-    assert s.factorize_matrix(VAL) == -20                            # sls.h: "not positive definite" status
+    # SSIDS flag -6 (not positive definite) goes through SLS_copy_inform_from_ssids, which files it under
+    # GALAHAD_error_restrictions = -3 (sls.f90:1768-1769); the facade follows the reference's table
+    assert s.factorize_matrix(VAL) == -3
 
 
 @pytest.mark.gpu
