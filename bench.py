@@ -9,9 +9,12 @@ A step = one numeric factorization + one solve (1 RHS) of the same matrix (analy
 interior-point callers do).  `value` = num_flops / mean factorize time with A's values resident in
 HBM (num_flops = the reference's own count, core_analyse.f90:880-892); `solve_ms` rides along.
 `e2e` = the same through the host-buffer C-ABI calls (H2D of val and b, D2H of x inside the timed
-region).  N > 1: ONE factorisation of the same matrix, tree-parallel over the ranks (leaf subtrees
-per GPU, contribution blocks shipped to the root owner with NCCL), i.e.
-strong scaling.
+region).  N > 1: ONE factorisation of one matrix, tree-parallel over the ranks (subtrees per GPU,
+contribution blocks shipped to the owner of the parent front with NCCL).  The
+default is WEAK scaling: the grid grows with N so that the factorisation's flops per GPU stay those of
+C2 (64^3 at N = 1; 72^3, 80^3, 90^3 at N = 2, 4, 8: 2.02, 3.83, 7.86 times the flops) -- a 35 ms
+problem cannot occupy eight GPUs, the large problems the partition exists for can.  `--scaling strong`
+keeps the 64^3 matrix at every N.
 `--impl reference` times the reference's own C++ SSIDS CPU engine (oracle/_ref) on the host cores.
 """
 import argparse
@@ -27,8 +30,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_upd3 launch from an ncu --set full capture (profiles/); filled in
+# from the capture of the current build, None until then
+UPD3_TRAFFIC = {"bytes": None, "note": "no ncu capture of this build yet"}
+
 METRIC = "sls_factorize_fp64_tflops"
 UNIT = "TFLOP/s"
+
+
+# weak scaling: grid with N times the factorisation flops of 64^3 (flops ~ g^6; engine-tree counts 8.875e11, 1.681e12,
+# 3.452e12 against 4.391e11)
+WEAK_GRID = {1: 64, 2: 72, 4: 80, 8: 90}
+
+
+def grid_for(args):
+    if args.grid:
+        return args.grid
+    if args.scaling == "strong" or args.gpus <= 1:
+        return 64
+    return WEAK_GRID.get(args.gpus, int(round(64 * args.gpus ** (1.0 / 6.0))))
 
 
 def make_problem(grid):
@@ -37,7 +57,8 @@ def make_problem(grid):
 
 
 def workload_name(grid):
-    return f"C2: 3-D 7-point Laplacian {grid}^3 (n={grid ** 3}), geometric ND order, SLS pivot_control=1 (LDL^T, u=0.01), factor + 1-RHS solve"
+    tag = "C2" if grid == 64 else "C2 scaled to N GPUs (flops per GPU as 64^3)"
+    return f"{tag}: 3-D 7-point Laplacian {grid}^3 (n={grid ** 3}), geometric ND order, SLS pivot_control=1 (LDL^T, u=0.01), factor + 1-RHS solve"
 
 
 class ClockSampler:
@@ -141,7 +162,7 @@ def run_reference(args):
     total_steps = args.steps + args.warmup
     grid = args.grid
     est_rate = 0.0045e12 * min(cores, 32)
-    for g in (args.grid, 56, 48, 40, 32, 24):
+    for g in (args.grid, 80, 72, 64, 56, 48, 40, 32, 24):
         if g > args.grid:
             continue
         grid = g
@@ -169,7 +190,7 @@ def run_reference(args):
     sample = f"full factor+solve of the {grid}^3 grid ({flops:.3e} flops) per step, {len(tf)} steps"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": (mf + ms) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": (mf + ms) * 1e3, "higher_is_better": True, "scaling": args.scaling_kind,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.grid), "sample_grid": grid, "threads": ref.nthreads()},
         "factor_ms": mf * 1e3, "solve_ms": ms * 1e3,
@@ -262,7 +283,7 @@ def run_ours(args):
     launches = int(np.sum([r[2] for r in res]))
     # roofline pass: the same K steps with CUDA events around every launch of the dominant kernel
     # (profile mode keeps the factorisation on one stream so that a launch is timed alone)
-    s.opt.reserved[0] = 1
+    s.opt.reserved[0] = 2
     step_device()
     barrier()
     resp = [step_device() for _ in range(args.steps)]
@@ -296,7 +317,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling_kind, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.grid), "num_flops": flops, "num_factor": nfact,
                        "parallelism": "1 GPU",
                        "l2": "256 MB buffer written between iterations; factor working set >> L2",
@@ -309,14 +330,13 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(8 * n), "factor_ms": ef * 1e3, "solve_ms": es * 1e3},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the largest k_update launch (ncu --set full,
-                         # profiles/r1_ncu_k_update.txt; 302 MB algorithmic bytes for that launch); not re-measured here
-                         "traffic": 249744640 if args.grid == 64 else None,
-                         "traffic_note": "one ncu capture of the largest launch (t=6016, kc=128), not an average over launches",
-                         "kernel": "k_update (trailing Schur update, FP64)",
+                         "traffic": UPD3_TRAFFIC.get("bytes") if args.grid == 64 else None,
+                         "traffic_note": UPD3_TRAFFIC.get("note"),
+                         "kernel": "k_upd3 (trailing Schur update of the large fronts, FP64 DMMA)",
                          "peak_source": "measured here: cuBLAS Dgemm 4096^3 via torch.matmul(float64), best of 5 (MEASURED_PEAKS.json has no FP64 entry)",
                          "share_of_factor_time": upd_secs / (tf_prof * args.steps) if tf_prof > 0 else None,
-                         "measured": "second pass of the same K steps with CUDA events around every k_update launch on the engine stream (single-stream mode, factor_ms %.2f)" % (tf_prof * 1e3)},
+                         "launches_per_step": int(s.inform.reserved[2]),
+                         "measured": "second pass of the same K steps with CUDA events around every k_upd3 launch on the engine stream (no look-ahead: each launch timed alone, factor_ms %.2f)" % (tf_prof * 1e3)},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
@@ -382,7 +402,7 @@ def run_tree_parallel(args, prob, torch, dist, rank, world, local):
         line = {
             "metric": METRIC, "value": flops / tf / 1e12, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling_kind, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.grid), "num_flops": flops, "num_factor": nfact,
                        "parallelism": f"tree-parallel over {world} GPUs: proportional mapping, {ds.nstages} stages, "
                                       f"{sum(1 for st in ds.boundaries for (_, a, c) in st if a != c)} boundary fronts moved between ranks "
@@ -428,9 +448,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200ldlt")
-    ap.add_argument("--grid", type=int, default=64)
+    ap.add_argument("--grid", type=int, default=0, help="grid size (default: 64 at N = 1, scaled with N otherwise)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = flops per GPU as C2 (default), strong = the 64^3 matrix at every N")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    args.scaling_kind = args.scaling if args.gpus > 1 else "weak"
+    args.grid = grid_for(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

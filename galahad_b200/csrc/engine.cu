@@ -1374,7 +1374,14 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                const int wcap = (maxw + NB - 1) / NB * NB;
                // blocks shortened by failed pivots leave `done` behind ob*PB, so the row grid covers the
                // whole front; CTAs above the block exit at once
-               const int yapply = std::max(1, (maxm + AR - 1) / AR);
+               // k_apply: about two CTAs per SM over the fronts of the launch, each walking its share of the row tiles
+               int yapply = std::max(1, (maxm + AR - 1) / AR);
+               {
+                  const int ntile_max = yapply;
+                  yapply = std::max(1, std::min(ntile_max, 296 / std::max(na, 1)));
+                  const int rounds = (ntile_max + yapply - 1) / yapply;
+                  yapply = (ntile_max + rounds - 1) / rounds;
+               }
                bool slice_running = false;
                if (slices_left > 0) {
                   // one slice of the previous group's update beside this block's factorisation
@@ -1407,9 +1414,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                launches += 3;
                const int nct = (map_off[ob + 1] - map_off[ob]) / 3;
                if (!big) {
-                  if (o.profile) { prof_region(ob, ob, false, false); prof_begin(); }
+                  if (o.profile == 1) { prof_region(ob, ob, false, false); prof_begin(); }
                   k_update<<<nct, 256, UPD_SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], par);
-                  if (o.profile) prof_end();
+                  if (o.profile == 1) prof_end();
                   ++launches;
                } else {
                   if (G > 1 && nct > 0) {
@@ -2037,9 +2044,15 @@ int Numeric::dist_solve(int step, double* d_xio, const double* src) {
    } else {
       return SSIDS_ERROR_JOB_OOR;
    }
+   pin_i[pin_i_cap - 1] = 0;
+   CU(cudaMemcpyAsync(pin_i + pin_i_cap - 1, d_chain_err, sizeof(int), cudaMemcpyDeviceToHost, st));
    CU(cudaStreamSynchronize(st));
    cudaError_t e = cudaGetLastError();
    if (e != cudaSuccess) { cuda_err = (int)e; return SSIDS_ERROR_CUDA_UNKNOWN; }
+   if (pin_i[pin_i_cap - 1] != 0) {   // a chain kernel gave up waiting for a block, as in Numeric::solve
+      CU(cudaMemsetAsync(d_chain_err, 0, sizeof(int), st));
+      return SSIDS_ERROR_CUDA_UNKNOWN;
+   }
    return 0;
 }
 

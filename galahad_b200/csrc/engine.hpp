@@ -14,7 +14,8 @@ struct FactorOptions {
    double small_ = 1e-20;
    double multiplier = 1.1;
    int print_level = -1;
-   int profile = 0;     // 1: bracket every trailing-update launch with CUDA events (bench roofline)
+   int profile = 0;     // bench roofline: CUDA events around every trailing-update launch (1), or around the launches of
+                        // the large-front kernel k_upd3 only (2); single stream, no look-ahead
 };
 
 struct FactorStats {

@@ -628,27 +628,24 @@ __global__ void __launch_bounds__(256, KIND < 2 ? 2 : 1) k_block(FrontDev* fr, c
 constexpr int AR = 64;             // rows per CTA in k_apply
 constexpr int LDX = AR + 4;        // k-major smem leading dimension, = 4 mod 16: conflict-free fragments
 __host__ __device__ inline size_t apply_smem_bytes(int wcap) {
-   const int nb = wcap / NB;
-   return sizeof(double) * ((size_t)wcap * LDX + NB * LDX + (size_t)(nb * (nb - 1) / 2 + nb) * NB * LDBB + 2 * PB + 2) +
-          sizeof(int) * 2 * PB;
+   return sizeof(double) * ((size_t)wcap * LDX + NB * LDX + 2 * PB + 2) + sizeof(int) * 2 * PB;
 }
 
-__global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap) {
+__global__ void __launch_bounds__(256, 2) k_apply(FrontDev* fr, const int* list, int slot0, Params prm, int wcap) {
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0 || f.stall) return;
    double* const Wldp = f.Wld;     // X ring: pivot p of the front in column p mod xw
    const int xw = f.xw;
    const int done = f.done, m = f.m;
-   const int r0 = done + w + blockIdx.y * AR;
-   if (r0 >= m) return;
+   // a CTA walks row tiles blockIdx.y, blockIdx.y + gridDim.y, ...: the L11 blocks and inverses are staged once, the next
+   // tile's rows are pulled towards L2 while the current tile is solved
+   const int ntile = (m - (done + w) + AR - 1) / AR;
+   if ((int)blockIdx.y >= ntile) return;
    extern __shared__ __align__(16) double smem[];
-   const int nbc = wcap / NB;
    double* Xs = smem;                                    // Xs[k*LDX + r]: A, then X, k < wcap
    double* Ys = Xs + (size_t)wcap * LDX;                 // Ys[k*LDX + r], k < NB
-   double* Bl = Ys + NB * LDX;                           // strictly lower blocks (j,i): [k*LDBB + c] = L11(32j+c, 32i+k)
-   double* Bi = Bl + (size_t)(nbc * (nbc - 1) / 2) * NB * LDBB;   // [j][k*LDBB + c] = inv(L_jj)(c,k)
-   double* sdk = Bi + (size_t)nbc * NB * LDBB;
+   double* sdk = Ys + NB * LDX;
    int* slperm = reinterpret_cast<int*>(sdk + 2 * PB + 2);
    int* sptype = slperm + PB;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -661,43 +658,43 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, in
    __syncthreads();
    const size_t ldl = f.ldl;
    double* const Lp = f.L;
+   const double* const L11 = Lp + (size_t)done * ldl + done;
+   const double* const Linv = f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2;
+   double* const Wo = f.Wo;
+   int myfail = w;
+   for (int tile = blockIdx.y; tile < ntile; tile += gridDim.y) {
+   const int r0 = done + w + tile * AR;
+   if (tile != (int)blockIdx.y) __syncthreads();      // the previous tile's last pass still reads Xs
    {
-      // A tile (8-byte copies: the row offset may be odd), L11 blocks and inverses (16-byte copies)
+      // A tile (8-byte copies: the row offset may be odd)
       for (int e = tid; e < wr * AR; e += 256) {
          const int k = e >> 6, rr = e & (AR - 1);
          const bool ok = k < w && r0 + rr < m;
          cp_async8(Xs + k * LDX + rr, ok ? Lp + (size_t)(done + slperm[k]) * ldl + r0 + rr : Lp, ok);
       }
-      // L11 blocks below the diagonal blocks come from the front itself (k_block wrote them in place)
-      const double* L11 = Lp + (size_t)done * ldl + done;
-      for (int j = 1; j < nb; ++j)
-         for (int i = 0; i < j; ++i) {
-            double* dst = Bl + (size_t)(j * (j - 1) / 2 + i) * NB * LDBB;
-            for (int e = tid; e < NB * NB; e += 256) {
-               const int k = e >> 5, c = e & 31;
-               const bool ok = i * NB + k < w && j * NB + c < w;
-               cp_async8(dst + k * LDBB + c, ok ? L11 + (size_t)(i * NB + k) * ldl + j * NB + c : L11, ok);
-            }
+      if (tile + (int)gridDim.y < ntile) {
+         // the next tile of this CTA towards L2: 64 rows of a column are 4 or 5 lines of 128 bytes
+         const int rn = r0 + (int)gridDim.y * AR;
+         for (int e = tid; e < w * 5; e += 256) {
+            const int k = e / 5, q = e - k * 5;
+            const int rr = min(rn + q * 16, m - 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Lp + (size_t)(done + slperm[k]) * ldl + rr));
          }
-      const double* Linv = f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2;
-      for (int e = tid; e < nb * NB * NB / 2; e += 256) {
-         const int j = e >> 9, k = (e >> 4) & 31, c = (e & 15) * 2;
-         cp_async16(Bi + (size_t)j * NB * LDBB + k * LDBB + c, Linv + (size_t)j * NB * NB + k * NB + c, 16);
       }
       cp_async_commit();
       cp_async_wait<0>();
    }
    __syncthreads();
-   // keep the permuted originals for the restore path
+   // keep the permuted originals for the restore path (the pointer is read once: a store through it could alias the
+   // front record, and the reload after every store would serialise the loop on L2 round trips)
    for (int e = tid; e < w * AR; e += 256) {
       const int k = e >> 6, rr = e & (AR - 1);
-      if (r0 + rr < m) f.Wo[(size_t)k * ldl + r0 + rr] = Xs[k * LDX + rr];
+      if (r0 + rr < m) Wo[(size_t)k * ldl + r0 + rr] = Xs[k * LDX + rr];
    }
    const int rg = warp & 1, cg = warp >> 1;      // warp tile: rows rg*32..+31, columns cg*8..+7 of the stage
    const int g = lane >> 2, t4 = lane & 3;
    const int srow_ = tid & (AR - 1), skq = tid >> 6;   // scaling pass: row, group of 8 columns
    const bool rv = r0 + srow_ < m;
-   int myfail = w;
    for (int j = 0; j < nb; ++j) {
       const int c0 = j * NB;
       double acc[4][2];
@@ -705,14 +702,34 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, in
       for (int i4 = 0; i4 < 4; ++i4)
 #pragma unroll
          for (int h = 0; h < 2; ++h) acc[i4][h] = Xs[(c0 + cg * 8 + 2 * t4 + h) * LDX + rg * 32 + i4 * 8 + g];
-      for (int i = 0; i < j; ++i) {
-         const double* as = Xs + (i * NB + t4) * LDX + rg * 32 + g;
-         const double* bs = Bl + (size_t)(j * (j - 1) / 2 + i) * NB * LDBB + t4 * LDBB + cg * 8 + g;
+      // The B operands -- this warp's 8 columns of the L11 blocks (j, i), i < j, which k_block wrote into the front in
+      // place, and of inv(L_jj) -- come straight from global memory as MMA fragments (one double per lane and k-step;
+      // every CTA of the front reads the same few KB, L1 / L2 hits): no shared-memory copy, two CTAs per SM
+      const int bc = j * NB + cg * 8 + g;               // column of the block row j this lane feeds
+      const double* const lrow = L11 + bc;
+      double binv[NB / 4], bl[2][NB / 4];
+      // block (j, 0) and the inverse are requested before anything else of the stage, block (j, i + 1) while block
+      // (j, i) is multiplied: the L2 round trips overlap the MMAs
+      if (j > 0) {
 #pragma unroll
-         for (int ks = 0; ks < NB; ks += 4) {
-            const double b = -bs[ks * LDBB];
+         for (int q = 0; q < NB / 4; ++q) bl[0][q] = bc < w ? __ldg(lrow + (size_t)(q * 4 + t4) * ldl) : 0.0;
+      }
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) dmma(acc[i4][0], acc[i4][1], as[ks * LDX + i4 * 8], b);
+      for (int q = 0; q < NB / 4; ++q) binv[q] = __ldg(Linv + (size_t)j * NB * NB + (q * 4 + t4) * NB + cg * 8 + g);
+#pragma unroll
+      for (int i = 0; i < PB / NB - 1; ++i) {
+         if (i < j) {
+            if (i + 1 < j) {
+#pragma unroll
+               for (int q = 0; q < NB / 4; ++q) bl[(i + 1) & 1][q] = bc < w ? __ldg(lrow + (size_t)((i + 1) * NB + q * 4 + t4) * ldl) : 0.0;
+            }
+            const double* as = Xs + (i * NB + t4) * LDX + rg * 32 + g;
+#pragma unroll
+            for (int ks = 0; ks < NB; ks += 4) {
+               const double b = -bl[i & 1][ks >> 2];
+#pragma unroll
+               for (int i4 = 0; i4 < 4; ++i4) dmma(acc[i4][0], acc[i4][1], as[ks * LDX + i4 * 8], b);
+            }
          }
       }
 #pragma unroll
@@ -725,12 +742,13 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, in
       for (int i4 = 0; i4 < 4; ++i4) x[i4][0] = x[i4][1] = 0.0;
       {
          const double* as = Ys + t4 * LDX + rg * 32 + g;
-         const double* bs = Bi + (size_t)j * NB * LDBB + t4 * LDBB + cg * 8 + g;
          const int kend = 8 * (cg + 1);            // inv(L_jj)(c,k) = 0 for k > c
-         for (int ks = 0; ks < kend; ks += 4) {
-            const double b = bs[ks * LDBB];
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) dmma(x[i4][0], x[i4][1], as[ks * LDX + i4 * 8], b);
+         for (int ks = 0; ks < NB; ks += 4) {
+            if (ks < kend) {
+#pragma unroll
+               for (int i4 = 0; i4 < 4; ++i4) dmma(x[i4][0], x[i4][1], as[ks * LDX + i4 * 8], binv[ks >> 2]);
+            }
          }
       }
 #pragma unroll
@@ -764,6 +782,7 @@ __global__ void __launch_bounds__(256) k_apply(FrontDev* fr, const int* list, in
          }
       }
    }
+   }   // row tiles
 #pragma unroll
    for (int off = 16; off > 0; off >>= 1) myfail = min(myfail, __shfl_xor_sync(0xffffffffu, myfail, off));
    if (lane == 0 && myfail < w) atomicMin(&f.fail, myfail);

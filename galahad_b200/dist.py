@@ -67,6 +67,7 @@ class DistSolver:
         flag = self.s.analyse(n, ptr, row, order)
         self.n = n
         s = self.s
+        self.rank_struct = int(s.inform.matrix_rank)
         f = s.L.b200ldlt_dist_init(s.akeep, C.byref(s.fkeep), self.rank, self.world, C.byref(s.opt), C.byref(s.inform))
         assert f >= 0, f"dist_init flag {f}"
         self.nstages = s.L.b200ldlt_dist_nstages(s.akeep)
@@ -77,19 +78,33 @@ class DistSolver:
             self.boundaries[stage.value].append((node.value, src.value, dst.value))
         return flag
 
+    def _agree(self, flag):
+        """The smallest flag over the ranks (errors are negative): every rank takes the same decision."""
+        if self.world == 1:
+            return int(flag)
+        t = torch.tensor([int(flag)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item())
+
     def factor(self, val, posdef=False):
+        """Returns the SSIDS flag of the factorisation: the most severe error of any rank (MIN over the ranks),
+        else the largest warning (MAX).  An error in a stage stops every rank before the exchange of that stage."""
         s = self.s
         val = np.ascontiguousarray(val, np.float64)
         vp = val.ctypes.data_as(C.POINTER(C.c_double))
         self.bytes_moved = 0
         self.t_stage = []
         self.launches = 0
-        worst = 0
+        warn = 0
         for k in range(self.nstages):
             f = s.L.b200ldlt_dist_factor(s.akeep, s.fkeep, k + 1, int(posdef), vp, C.byref(s.opt), C.byref(s.inform))
-            worst = min(worst, f)
             self.t_stage.append(s.inform.time_factor)
             self.launches += int(s.inform.reserved[0])
+            worst = self._agree(min(f, 0))
+            if worst < 0:
+                self.num_neg = self.num_two = self.num_delay = self.num_zero = 0
+                return worst
+            warn = max(warn, f)
             self.bytes_moved += exchange(
                 self.boundaries[k], self.rank,
                 lambda node: s.L.b200ldlt_dist_contrib_bytes(s.fkeep, node),
@@ -97,14 +112,22 @@ class DistSolver:
                 lambda node, buf, nb: s.L.b200ldlt_dist_contrib_unpack(s.fkeep, node, C.c_void_p(buf.data_ptr()), nb),
                 self.device)
         self.t_leaves, self.t_root = self.t_stage[0], float(sum(self.t_stage[1:]))
-        # after its last phase a rank's counters cover every front it factorised
-        stats = np.array([s.inform.num_neg, s.inform.num_two, s.inform.num_delay, 0, worst], dtype=np.int64)
+        # after its last phase a rank's counters cover every front it factorised; zero pivots are the difference between
+        # the structural rank of the analysis and the rank the engine reports
+        nzero = int(self.rank_struct - s.inform.matrix_rank)
+        stats = np.array([s.inform.num_neg, s.inform.num_two, s.inform.num_delay, nzero], dtype=np.int64)
         t = torch.from_numpy(stats).to(self.device)
+        w = torch.tensor([int(warn)], dtype=torch.int64, device=self.device)
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
         tot = t.cpu().numpy()
-        self.num_neg, self.num_two, self.num_delay = int(tot[0]), int(tot[1]), int(tot[2])
-        return int(tot[4])
+        self.num_neg, self.num_two, self.num_delay, self.num_zero = int(tot[0]), int(tot[1]), int(tot[2]), int(tot[3])
+        self.matrix_rank = int(self.rank_struct - self.num_zero)
+        warn = int(w.item())
+        if self.num_zero > 0:
+            warn = max(warn, 7)          # SSIDS_WARNING_FACT_SINGULAR (datatypes.f90:56), whoever found the zero pivots
+        return warn
 
     def solve(self, b):
         s = self.s
@@ -114,8 +137,9 @@ class DistSolver:
         f = s.L.b200ldlt_dist_solve(s.fkeep, 1, C.c_void_p(x.data_ptr()), None)
         assert f >= 0, f
         for k in range(self.nstages):
-            f = s.L.b200ldlt_dist_solve(s.fkeep, 100 + k, C.c_void_p(x.data_ptr()), None)
-            assert f >= 0, f
+            f = self._agree(s.L.b200ldlt_dist_solve(s.fkeep, 100 + k, C.c_void_p(x.data_ptr()), None))
+            if f < 0:
+                raise RuntimeError(f"distributed forward solve failed in stage {k} on some rank: flag {f}")
             exchange(
                 self.boundaries[k], self.rank,
                 lambda node: s.L.b200ldlt_dist_xtail_bytes(s.fkeep, node),
@@ -124,8 +148,9 @@ class DistSolver:
                 self.device)
         part = torch.empty(2 * n, dtype=torch.float64, device=self.device)
         for k in range(self.nstages - 1, -1, -1):
-            f = s.L.b200ldlt_dist_solve(s.fkeep, 200 + k, C.c_void_p(x.data_ptr()), None)
-            assert f >= 0, f
+            f = self._agree(s.L.b200ldlt_dist_solve(s.fkeep, 200 + k, C.c_void_p(x.data_ptr()), None))
+            if f < 0:
+                raise RuntimeError(f"distributed backward solve failed in stage {k} on some rank: flag {f}")
             if self.world > 1:
                 # the solution entries of stage k, from whoever produced them, to everybody
                 assert s.L.b200ldlt_dist_xp_get_stage(s.fkeep, k, C.c_void_p(part.data_ptr()), n) == 0

@@ -64,7 +64,8 @@ typedef struct b200ldlt_options {
    double multiplier;   /* factor-storage slack for delayed pivots (>= 1.0) */
    int device;          /* CUDA device ordinal, -1: current device */
    int panel_width;     /* reserved; 0 = engine default */
-   int reserved[7];     /* reserved[0] = 1: profile mode (CUDA events around every trailing update);
+   int reserved[7];     /* reserved[0] = 1: profile mode (CUDA events around every trailing update), 2: around the
+                           launches of the large-front update kernel only;
                            reserved[1] = 1: do not fuse chains (engine tree == reference tree);
                            reserved[2]: ssids options%scaling for b200ldlt_factor_scaled */
 } b200ldlt_options;
