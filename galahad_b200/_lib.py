@@ -63,7 +63,7 @@ class Inform(C.Structure):
 
 # every symbol include/b200ldlt.h declares (tests check the library exports each of them)
 SYMBOLS = [
-    "b200ldlt_default_options", "b200ldlt_analyse", "b200ldlt_analyse_ptr64", "b200ldlt_factor",
+    "b200ldlt_default_options", "b200ldlt_order", "b200ldlt_analyse", "b200ldlt_analyse_ptr64", "b200ldlt_factor",
     "b200ldlt_factor_device", "b200ldlt_set_value_map", "b200ldlt_factor_mapped", "b200ldlt_set_user_matrix", "b200ldlt_solve_refined", "b200ldlt_factor_scaled", "b200ldlt_equilib_scale", "b200ldlt_set_scaling", "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_enquire_indef",
     "b200ldlt_enquire_posdef", "b200ldlt_alter", "b200ldlt_free_fkeep", "b200ldlt_free",
     "b200ldlt_akeep_sizes", "b200ldlt_akeep_get", "b200ldlt_partition", "b200ldlt_part_info", "b200ldlt_map_info",
@@ -92,6 +92,7 @@ def lib():
     op, fp = C.POINTER(Options), C.POINTER(Inform)
     L.b200ldlt_default_options.argtypes = [op]
     L.b200ldlt_default_options.restype = None
+    L.b200ldlt_order.argtypes = [C.c_int, lp, ip, C.c_int, ip, op]
     L.b200ldlt_analyse.argtypes = [vpp, C.c_int, ip, ip, ip, op, fp]
     L.b200ldlt_analyse_ptr64.argtypes = [vpp, C.c_int, lp, ip, ip, op, fp]
     L.b200ldlt_factor.argtypes = [vp, vpp, C.c_int, dp, op, fp]

@@ -80,6 +80,11 @@ int analyse(int n, const int64_t* ptr, const int* row, const int* order, int nem
 int equilib_scale_sym(int n, const int64_t* ptr, const int* row, const double* val, double* scaling,
                       int max_iterations = 10, float tol = 1e-8f);
 
+// Fill-reducing orderings (ordering.cpp): approximate minimum degree, and nested dissection from level structures with
+// minimum-degree leaves.  Lower triangle by columns, 0-based; order[i] = pivot position of variable i.  0 or an SSIDS flag.
+int amd_order(int n, const int64_t* ptr, const int* row, int* order);
+int nd_order(int n, const int64_t* ptr, const int* row, int* order, int leaf_size = 200);
+
 // Proportional mapping (the multi-level generalisation of the subtree partition: SURVEY section 8e): the root
 // gets all devices, the devices of a node are split among its children in proportion to their subtree flops,
 // a subtree that is left with one device is a leaf part of that device; a node is owned by the first device of

@@ -145,6 +145,29 @@ int b200ldlt_analyse_ptr64(void** akeep, int n, const int64_t* ptr, const int* r
    return flag;
 }
 
+int b200ldlt_order(int n, const int64_t* ptr, const int* row, int kind, int* order, const b200ldlt_options* opt) {
+   if (n < 0) return SSIDS_ERROR_A_N_OOR;
+   if (n == 0) return 0;
+   if (!ptr || !row || !order || !opt) return SSIDS_ERROR_A_PTR;
+   const int base = opt->array_base ? 1 : 0;
+   try {
+      const int64_t nz = ptr[n] - base;
+      std::vector<int64_t> p0(n + 1);
+      std::vector<int> r0((size_t)std::max<int64_t>(nz, 0));
+      for (int i = 0; i <= n; ++i) p0[i] = ptr[i] - base;
+      for (int64_t k = 0; k < nz; ++k) r0[k] = row[k] - base;
+      int rc;
+      if (kind == 1) rc = amd_order(n, p0.data(), r0.data(), order);
+      else if (kind == 3) rc = nd_order(n, p0.data(), r0.data(), order);
+      else return SSIDS_ERROR_UNIMPLEMENTED;
+      if (rc < 0) return rc;
+      if (base) for (int i = 0; i < n; ++i) order[i] += 1;
+      return 0;
+   } catch (const std::bad_alloc&) {
+      return SSIDS_ERROR_ALLOCATION;
+   }
+}
+
 int b200ldlt_analyse(void** akeep, int n, const int* ptr, const int* row, int* order,
                      const b200ldlt_options* opt, b200ldlt_inform* inf) {
    if (n < 0 || !ptr) {

@@ -231,10 +231,29 @@ void sls_analyse_matrix_perm(sls_control_type* control, void** data, int* status
       int k = d->maps[l];
       if (k > 0) d->col[k - 1] = std::max(d->urow[l], d->ucol[l]);
    }
-   // the order (sls.f90:2962-2968): PERM if present, else the identity
-   d->order.assign(n, 0);
-   for (int i = 0; i < n; ++i) d->order[i] = perm ? perm[i] - base + 1 : i + 1;
+   // The order.  PERM if present (sls.f90:2962-2968).  Otherwise control%ordering decides (sls.f90:2262-2268, 2395-2412,
+   // 3134-3140): >= 0 is MC68's menu -- 0, 1 and anything above 6 approximate minimum degree, 2 minimum degree, 3 nested
+   // dissection, 4 (indefinite 1x1 / 2x2 ordering), 5 and 6 (MC61 profile / band) have nothing behind them here; < 0 asks the
+   // solver for its own, which for this solver, as for SSIDS with METIS, is nested dissection.  The orderings are this
+   // library's (ordering.cpp): the reference's come from packages outside its tree, no permutation is pinned.
    b200ldlt_options o = to_solver(d->control);
+   d->order.assign(n, 0);
+   if (perm) {
+      for (int i = 0; i < n; ++i) d->order[i] = perm[i] - base + 1;
+   } else {
+      const int oc = d->control.ordering;
+      int kind;
+      if (oc == -1 || oc == 3) kind = 3;
+      else if (oc < 0 || oc == 4 || oc == 5 || oc == 6) kind = 0;
+      else kind = 1;
+      std::vector<int64_t> p64(d->ptr.begin(), d->ptr.end());
+      const int rc = kind ? b200ldlt_order(n, p64.data(), d->col.data(), kind, d->order.data(), &o) : GALAHAD_UNAVAILABLE_OPTION;
+      if (rc < 0) {
+         d->analysed = false;
+         *status = inf.status = rc == GALAHAD_UNAVAILABLE_OPTION ? GALAHAD_UNAVAILABLE_OPTION : GALAHAD_ERROR_TECHNICAL;
+         return;
+      }
+   }
    b200ldlt_inform si;
    if (d->akeep) b200ldlt_free(&d->akeep, &d->fkeep);
    b200ldlt_analyse(&d->akeep, n, d->ptr.data(), d->col.data(), d->order.data(), &o, &si);

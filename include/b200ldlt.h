@@ -108,6 +108,12 @@ void b200ldlt_default_options(b200ldlt_options *opt);
 int b200ldlt_analyse(void **akeep, int n, const int *ptr, const int *row, int *order,
                      const b200ldlt_options *opt, b200ldlt_inform *inf);
 
+/* Fill-reducing orderings computed on the host, for callers that pass no order of their own (what SLS_analyse gets from
+ * MC68 / METIS, sls.f90:2395-2470 and ssids.f90 options%ordering = 1; stubs in a stock build of the reference).
+ * kind 1: approximate minimum degree; kind 3: nested dissection (level-structure separators, minimum-degree leaves).
+ * ptr / row as for b200ldlt_analyse_ptr64 (base from opt->array_base); order[n] out, same base. */
+int b200ldlt_order(int n, const int64_t *ptr, const int *row, int kind, int *order, const b200ldlt_options *opt);
+
 /* 64-bit ptr variant (ssids.f90:148 analyse_double takes int64 ptr). */
 int b200ldlt_analyse_ptr64(void **akeep, int n, const int64_t *ptr, const int *row, int *order,
                            const b200ldlt_options *opt, b200ldlt_inform *inf);
