@@ -522,6 +522,19 @@ __global__ void k_merge_stage(double* __restrict__ xp, const double* __restrict_
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// Launch as a programmatic dependent of the previous kernel in the stream (pdl_enter in the kernel): the grid is resident
+// and past its launch latency when its predecessor completes.
+template <typename... KArgs, typename... Args>
+static inline void launch_dep(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+   cudaLaunchConfig_t cfg = {};
+   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+   cudaLaunchAttribute at[1];
+   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+   at[0].val.programmaticStreamSerializationAllowed = 1;
+   cfg.attrs = at;
+   cfg.numAttrs = pdl ? 1 : 0;
+   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int block_wc(int n) { return std::max(NB, (std::min(n, PB) + NB - 1) / NB * NB); }
 // columns of a front's X ring: every pivot its own column up to 2 * GMAX blocks, where a group's deferred update reads
@@ -1030,6 +1043,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    const bool lookahead = !(getenv("B200LDLT_LOOKAHEAD") && atoi(getenv("B200LDLT_LOOKAHEAD")) == 0);
    // large fronts: trailing updates through k_upd3, deferred over defer_g blocks for fronts of defer_min_m rows and more
    const bool use_upd3 = !(getenv("B200LDLT_UPD3") && atoi(getenv("B200LDLT_UPD3")) == 0);
+   const bool use_pdl = !(getenv("B200LDLT_PDL") && atoi(getenv("B200LDLT_PDL")) == 0);
+   const int upd3_min_m = getenv("B200LDLT_UPD3_MINM") ? atoi(getenv("B200LDLT_UPD3_MINM")) : 1800;
    const int defer_g = getenv("B200LDLT_DEFER") ? std::max(1, atoi(getenv("B200LDLT_DEFER"))) : 4;
    const int defer_min_m = getenv("B200LDLT_DEFER_MINM") ? atoi(getenv("B200LDLT_DEFER_MINM")) : 2048;
    const int max_groups = getenv("B200LDLT_GROUPS") ? std::max(1, std::min((int)NAUX, atoi(getenv("B200LDLT_GROUPS")))) : (int)NAUX;
@@ -1253,7 +1268,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             // Large fronts (size class >= 3) take their trailing updates through k_upd3; with several blocks per front
             // the schedule looks ahead: the part of an update the next block needs runs on this stream, the rest in slices
             // on the chunk's second stream beside the next blocks' factorisation kernels (k_block: one CTA per front).
-            const bool big = single && cls(order[j0]) >= 3 && use_upd3;
+            const bool big = single && cls(order[j0]) >= 3 && use_upd3 && maxm >= upd3_min_m;
             const bool la = big && lookahead && !o.profile && !trace && nouter >= 2;
             // blocks per trailing update of the columns behind the group (rank G * PB): C is read and written once per G blocks
             const int G = (big && nouter >= 2 && maxm >= defer_min_m) ? std::max(1, std::min(defer_g, (int)GMAX)) : 1;
@@ -1409,7 +1424,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                if (slice_running) CU(cudaStreamWaitEvent(sx, ev_bulk[sidx][0], 0));
                k_apply<<<dim3(na, yapply), 256, apply_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, wcap);
                if (big) mark(sx, "apply", ob, yapply);
-               k_commit<<<dim3(na, ycommit), 256, 0, sx>>>(d_fr, lst, b0, ncolchunks, par, gpos, G, g + 1);
+               launch_dep(use_pdl && !timeline, k_commit, dim3(na, ycommit), dim3(256), 0, sx, d_fr, lst, b0, ncolchunks, par, gpos, G, g + 1);
                if (big) mark(sx, "commit", ob, 0);
                launches += 3;
                const int nct = (map_off[ob + 1] - map_off[ob]) / 3;
@@ -1421,7 +1436,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                } else {
                   if (G > 1 && nct > 0) {
                      if (o.profile) { prof_region(ob, ob, true, false); prof_begin(); }
-                     k_upd3<<<nct, upd3::THREADS, upd3::SMEM, sx>>>(d_fr, lst, b0, d_updmap + map_off[ob], 0, par, 0, 0, 0, 1, 0);
+                     launch_dep(use_pdl && !timeline && !o.profile, k_upd3, dim3(nct), dim3(upd3::THREADS), upd3::SMEM, sx, d_fr, lst, b0,
+                                (const int*)(d_updmap + map_off[ob]), 0, par, 0, 0, 0, 1, 0);
                      mark(sx, "strip", ob, nct);
                      if (o.profile) prof_end();
                      ++launches;
@@ -1440,7 +1456,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                      }
                      if (nctb > 0) {
                         if (o.profile) { prof_region(g * G, ob, false, true); prof_begin(); }
-                        k_upd3<<<nctb, upd3::THREADS, upd3::SMEM, sx>>>(d_fr, lst, b0, d_updmap + bmap_off[g], 1, g & 1, g + 1, -1, 0, 1, z);
+                        launch_dep(use_pdl && !timeline && !o.profile, k_upd3, dim3(nctb), dim3(upd3::THREADS), upd3::SMEM, sx, d_fr, lst, b0,
+                                   (const int*)(d_updmap + bmap_off[g]), 1, g & 1, g + 1, -1, 0, 1, z);
                         mark(sx, "slice0", ob, z);
                         if (o.profile) prof_end();
                         ++launches;
@@ -1489,7 +1506,12 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             // a few large fronts: split them over streams so that one group's block factorisation
             // overlaps another group's trailing update
             int G = 1;
-            if (!o.profile && !trace && nact >= 2 && nact <= 128 && (c == 2 || (c > 2 && !use_upd3))) G = std::min(nact, max_groups);
+            // classes of many medium fronts: stream groups and the small-front kernel (one group's block factorisation
+            // beside another's update); classes with fronts of upd3_min_m rows and more: one chunk, k_upd3
+            int cls_maxm = 0;
+            for (int q = i0; q < i1; ++q) if (active[order[q]]) cls_maxm = std::max(cls_maxm, hfr[order[q]].m);
+            const bool cls_big = c >= 3 && use_upd3 && cls_maxm >= upd3_min_m;
+            if (!o.profile && !trace && nact >= 2 && nact <= 128 && c >= 2 && !cls_big) G = std::min(nact, max_groups);
             if (G == 1) {
                int rc2 = run_chunk(i0, i1, st, true, 0);
                if (rc2) return stats.flag = rc2;

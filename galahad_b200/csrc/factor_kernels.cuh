@@ -302,6 +302,14 @@ __host__ __device__ inline size_t block_smem_bytes(int wcap) {
 // KIND 0: blocks of at most one sub-panel (fronts with <= 32 candidate columns, the bulk of the tree): no
 // in-block solve / update code, half the registers, two CTAs per SM.  KIND 1: two sub-panels, register
 // budget of two CTAs per SM (the many 33..64-column fronts of banded / KKT problems).
+// Programmatic dependent launch: a kernel launched with the stream-serialisation attribute becomes resident while its
+// predecessor in the stream is still running and waits here for it to complete (memory included); it lets its own
+// successor do the same at once.  Without the attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_enter() {
+   asm volatile("griddepcontrol.wait;" ::: "memory");
+   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 template <int KIND>      // 0: blocks of <= 32 columns, 1: <= 64 columns (both two CTAs per SM), 2: up to 128 columns
 __global__ void __launch_bounds__(256, KIND < 2 ? 2 : 1) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only,
                                                               int wcap, int par, int la) {
@@ -799,6 +807,7 @@ __global__ void __launch_bounds__(256, 2) k_apply(FrontDev* fr, const int* list,
 // until then `pend` says what is owed (a front that stalls on a failed pivot is paid by the chunk's closing flush).
 __global__ void __launch_bounds__(256) k_commit(FrontDev* fr, const int* list, int slot0, int ncolchunks, int par, int gpos, int G,
                                                 int gtag) {
+   pdl_enter();
    FrontDev& f = fr[front_slot(list, slot0)];
    const int w = f.w;
    if (w == 0 || f.flag < 0 || f.stall) return;

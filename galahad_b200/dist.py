@@ -15,31 +15,56 @@ import torch
 import torch.distributed as dist
 
 
+_bufs = {}
+
+
+def _buffer(tag, nbytes, device):
+    """A reusable byte buffer per (tag, device): the exchange of every factorisation moves the same fronts."""
+    key = (tag, str(device))
+    buf = _bufs.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.1), 1), dtype=torch.uint8, device=device)
+        _bufs[key] = buf
+    return buf[:max(nbytes, 1)]
+
+
 def exchange(items, rank, nbytes_fn, pack_fn, unpack_fn, device):
     """items: list of (key, src_rank, dst_rank), the same list in the same order on every rank.  src packs
     key's bytes and sends them to dst, dst unpacks; pairs that do not involve this rank are skipped.
     nbytes_fn(key) -> int (src side), pack_fn(key, uint8 tensor), unpack_fn(key, uint8 tensor, nbytes).
-    Returns the bytes this rank sent or received."""
-    moved = 0
-    for key, src, dst in items:
-        if src == dst:
-            continue
+    The sizes of all items travel in one all-reduce (every item has exactly one source), then all transfers of the
+    step are posted together (batched point-to-point operations: they share the links instead of queueing behind
+    each other).  Returns the bytes this rank sent or received."""
+    moving = [(key, src, dst) for key, src, dst in items if src != dst]
+    if not moving:
+        return 0
+    sizes = torch.zeros(len(moving), dtype=torch.int64, device=device)
+    for j, (key, src, dst) in enumerate(moving):
         if rank == src:
-            nb = int(nbytes_fn(key))
-            dist.send(torch.tensor([nb], dtype=torch.int64, device=device), dst=dst)
-            buf = torch.empty(max(nb, 1), dtype=torch.uint8, device=device)
+            sizes[j] = int(nbytes_fn(key))
+    dist.all_reduce(sizes, op=dist.ReduceOp.SUM)
+    sz = [int(v) for v in sizes.cpu().tolist()]
+    ops, incoming, moved = [], [], 0
+    for j, (key, src, dst) in enumerate(moving):
+        if rank == src:
+            buf = _buffer(("send", j), sz[j], device)
             pack_fn(key, buf)
-            dist.send(buf, dst=dst)
-            moved += nb
+            ops.append(dist.P2POp(dist.isend, buf, dst))
+            moved += sz[j]
         elif rank == dst:
-            sz = torch.zeros(1, dtype=torch.int64, device=device)
-            dist.recv(sz, src=src)
-            nb = int(sz.item())
-            buf = torch.empty(max(nb, 1), dtype=torch.uint8, device=device)
-            dist.recv(buf, src=src)
-            torch.cuda.synchronize(device) if buf.is_cuda else None   # NCCL is async; the engine reads on its own stream
-            unpack_fn(key, buf, nb)
-            moved += nb
+            buf = _buffer(("recv", j), sz[j], device)
+            ops.append(dist.P2POp(dist.irecv, buf, src))
+            incoming.append((key, buf, sz[j]))
+            moved += sz[j]
+    if ops:
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize(device)      # the engine packed on its own stream
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize(device)      # NCCL is asynchronous; the engine reads on its own stream
+    for key, buf, nb in incoming:
+        unpack_fn(key, buf, nb)
     return moved
 
 
