@@ -67,6 +67,7 @@ struct FrontDev {
    int brec[2][6];      // per group parity: {first pivot, end pivot, first column, end of the next group's columns, tag, -}:
                         // the group's trailing update, written by k_commit of the group's last block
    int pend[4];         // {first pivot, end pivot, first column, flag}: deferred update not yet owed by a bulk launch
+   int fused;           // 1: assembled and factorised by k_front (front_kernels.cuh); the general kernels of the level pass it by
 };
 
 struct SlotStatic {
@@ -107,7 +108,7 @@ __global__ void k_setup(FrontDev* fr, const SlotStatic* ss, const int* child_idx
    int s = slot0 + blockIdx.x;
    if (s >= slot0 + nslots) return;
    FrontDev& f = fr[s];
-   if (!f.active) return;
+   if (!f.active || f.fused) return;
    const SlotStatic st = ss[s];
    for (int j = threadIdx.x; j < st.ncol; j += blockDim.x) f.perm[j] = st.first_piv + j;
    for (int j = threadIdx.x; j < f.n; j += blockDim.x) f.orig[j] = j;
@@ -124,7 +125,7 @@ __global__ void k_scatter_a(const FrontDev* fr, const int* aslot, const int* asr
    int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (e >= e1) return;
    const FrontDev& f = fr[aslot[e]];
-   if (!f.active) return;
+   if (!f.active || f.fused) return;
    int r = arow[e], c = acol[e];
    if (r >= f.ncol) r += f.ndelay_in;
    f.L[(size_t)c * f.ldl + r] = val[asrc[e]];
@@ -203,6 +204,7 @@ __device__ void block_sym_swap(const FrontDev& f, int a, int b) {
 __device__ int g_upd_debug = 0;     // B200LDLT_DEBUG_UPD=1: k_commit and k_upd3 print what they record / apply (diagnostic)
 #include "factor_kernels.cuh"
 #include "upd_kernels.cuh"
+#include "front_kernels.cuh"
 constexpr int UPD_SMEM = 2 * BK * (LDA + LDB) * (int)sizeof(double);
 
 // ------------------------------------------------------------------------------------------
@@ -597,12 +599,13 @@ class Plan {
    SlotStatic* d_ss = nullptr;
    int *d_child_idx = nullptr, *d_rlist = nullptr, *d_rel = nullptr, *d_order = nullptr;
    int *d_aslot = nullptr, *d_asrc = nullptr, *d_acol = nullptr, *d_arow = nullptr;
+   int64_t* d_aptr = nullptr;        // per slot: its range of the A scatter map (k_front)
    int64_t est_factor_doubles = 0, est_c_doubles[2] = {0, 0}, est_ws_doubles = 0;
    std::vector<int64_t> lvl_L_doubles, lvl_C_doubles;   // per level, without delays (same rounding as the numeric phase)
    ~Plan() {
       cudaSetDevice(device);
       cudaFree(d_ss); cudaFree(d_child_idx); cudaFree(d_rlist); cudaFree(d_rel); cudaFree(d_order);
-      cudaFree(d_aslot); cudaFree(d_asrc); cudaFree(d_acol); cudaFree(d_arow);
+      cudaFree(d_aslot); cudaFree(d_asrc); cudaFree(d_acol); cudaFree(d_arow); cudaFree(d_aptr);
    }
 };
 
@@ -715,6 +718,7 @@ Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
    // A scatter map, grouped by level
    int64_t na = sym.nptr[nn];
    std::vector<int> aslot(na), asrc(na), acol(na), arow(na);
+   std::vector<int64_t> aptr(nn + 1, 0);
    P->lvl_a_ptr.assign(P->nlevels + 1, 0);
    {
       int64_t o = 0;
@@ -723,6 +727,7 @@ Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
          for (int s = P->lvl_ptr[l]; s < P->lvl_ptr[l + 1]; ++s) {
             int i = P->slot_node[s];
             int64_t blkm = sym.rptr[i + 1] - sym.rptr[i];
+            aptr[s] = o;
             for (int64_t e2 = sym.nptr[i]; e2 < sym.nptr[i + 1]; ++e2) {
                int64_t dest = sym.nlist[2 * e2 + 1];
                aslot[o] = s;
@@ -734,6 +739,7 @@ Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
          }
       }
       P->lvl_a_ptr[P->nlevels] = o;
+      aptr[nn] = o;
    }
    // size estimates without delays
    for (int l = 0; l < P->nlevels; ++l) {
@@ -763,7 +769,7 @@ Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
              upload(&P->d_rlist, sym.rlist) == cudaSuccess && upload(&P->d_rel, rel) == cudaSuccess &&
              upload(&P->d_order, order) == cudaSuccess && upload(&P->d_aslot, aslot) == cudaSuccess &&
              upload(&P->d_asrc, asrc) == cudaSuccess && upload(&P->d_acol, acol) == cudaSuccess &&
-             upload(&P->d_arow, arow) == cudaSuccess;
+             upload(&P->d_arow, arow) == cudaSuccess && upload(&P->d_aptr, aptr) == cudaSuccess;
    if (!ok) {
       *cuda_error = (int)cudaGetLastError();
       if (*cuda_error == 0) *cuda_error = (int)cudaErrorMemoryAllocation;
@@ -836,6 +842,8 @@ class Numeric {
    int64_t xw_total = 0;
    Arena fac, dar, par, car[2], war, bar;   // bar: contribution blocks that cross a part boundary + imports
    std::vector<char> active, boundary;
+   std::vector<char> live;                 // per slot, during a level: active and not taken by k_front
+   int *d_flist = nullptr, *pin_flist = nullptr;   // fronts of a level taken by k_front: [n <= 32 | n <= 64]
    std::vector<int> part_kind, owner;      // per slot; owner -1 = root part
    int my_rank = 0, nranks = 1;
    cudaStream_t st = nullptr;
@@ -867,6 +875,8 @@ class Numeric {
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
       if (pin_updmap) cudaFreeHost(pin_updmap);
+      if (pin_flist) cudaFreeHost(pin_flist);
+      cudaFree(d_flist);
       cudaFree(d_updmap);
       if (st) cudaStreamDestroy(st);
       for (int g = 0; g < NAUX; ++g) { if (aux[g]) cudaStreamDestroy(aux[g]); if (ev_join[g]) cudaEventDestroy(ev_join[g]); }
@@ -926,6 +936,8 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(2 * NB)));
    CU(cudaFuncSetAttribute(k_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(NB)));
    CU(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes(PB)));
+   CU(cudaFuncSetAttribute(k_front<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ffront::SMEM_CAP));
+   CU(cudaFuncSetAttribute(k_front<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ffront::SMEM_CAP));
    CU(cudaFuncSetAttribute(k_fwd_step<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd(128)));
    CU(cudaFuncSetAttribute(k_fwd_step<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd(128)));
    CU(cudaFuncSetAttribute(k_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem()));
@@ -972,12 +984,15 @@ int Numeric::init() {
    CU(cudaMemset(d_chain_err, 0, sizeof(int)));
    CU(cudaMemset(d_ticket, 0, sizeof(int) * (nn + 1)));
    CU(cudaMalloc(&d_slist, sizeof(int) * nn));
+   CU(cudaMalloc(&d_flist, sizeof(int) * nn));
+   CU(cudaMallocHost(&pin_flist, sizeof(int) * nn));
    CU(cudaMalloc(&d_val, sizeof(double) * std::max<int64_t>(P->sym->nz, 1)));
    CU(cudaDeviceSynchronize());   // the null-stream memsets above are not ordered with the non-blocking streams
    child_doff.assign(P->child_idx.size(), 0);
    hfr.assign(nn, FrontDev());
    fac.err = dar.err = par.err = car[0].err = car[1].err = war.err = bar.err = &cuda_err;
    active.assign(nn, 1);
+   live.assign(nn, 1);
    boundary.assign(nn, 0);
    part_kind.assign(nn, 0);
    owner.assign(nn, 0);
@@ -1044,6 +1059,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    // large fronts: trailing updates through k_upd3, deferred over defer_g blocks for fronts of defer_min_m rows and more
    const bool use_upd3 = !(getenv("B200LDLT_UPD3") && atoi(getenv("B200LDLT_UPD3")) == 0);
    const bool use_pdl = !(getenv("B200LDLT_PDL") && atoi(getenv("B200LDLT_PDL")) == 0);
+   // small fronts (at most 64 candidate columns, panel in shared memory) in one launch per level (front_kernels.cuh)
+   const bool use_front = !(getenv("B200LDLT_FRONT") && atoi(getenv("B200LDLT_FRONT")) == 0);
    const int upd3_min_m = getenv("B200LDLT_UPD3_MINM") ? atoi(getenv("B200LDLT_UPD3_MINM")) : 1800;
    const int defer_g = getenv("B200LDLT_DEFER") ? std::max(1, atoi(getenv("B200LDLT_DEFER"))) : 4;
    const int defer_min_m = getenv("B200LDLT_DEFER_MINM") ? atoi(getenv("B200LDLT_DEFER_MINM")) : 2048;
@@ -1074,6 +1091,10 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       updmap_used = 0;   // the previous level ended with a stream synchronisation
       // sizes with delays
       size_t totL = 0, totC = 0, totD = 0, totP = 0, totW = 0;
+      std::vector<int> flist[2];
+      size_t fsmem[2] = {0, 0};
+      int ngeneral = 0;
+      for (int s = s0; s < s1; ++s) live[s] = 0;
       int nactive_lvl = 0;
       for (int s = s0; s < s1; ++s) nactive_lvl += active[s];
       if (nactive_lvl == 0) continue;
@@ -1096,6 +1117,17 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          f.ldc = (int)align_up(f.m - f.n, 2);
          f.done = 0; f.gend = f.n; f.w = 0; f.fail = 0; f.nelim = 0; f.flag = 0; f.wc = block_wc(f.n);
          f.state = 2; f.active = 1; f.part_kind = part_kind[s];
+         {
+            const int nchs = ss.child_end - ss.child_begin;
+            if (use_front && f.n <= ffront::MAXN && nchs <= ffront::MAXCH && ffront::smem_bytes(f.m, f.n, nchs) <= ffront::SMEM_CAP) {
+               f.fused = 1;
+               const int np = f.n <= NB ? 0 : 1;
+               flist[np].push_back(s);
+               fsmem[np] = std::max(fsmem[np], ffront::smem_bytes(f.m, f.n, nchs));
+            }
+            live[s] = f.fused ? 0 : 1;
+            if (!f.fused) ++ngeneral;
+         }
          totL += align_up((size_t)f.ldl * f.n, 32);
          if (!boundary[s]) totC += align_up((size_t)f.ldc * (f.m - f.n) + 1, 32);
          totD += align_up(2 * (size_t)f.n + 2, 32);
@@ -1153,9 +1185,27 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       const int cb = P->hss[s0].child_begin, ce = P->hss[s1 - 1].child_end;
       if (ce > cb)
          CU(cudaMemcpyAsync(d_child_doff + cb, child_doff.data() + cb, sizeof(int) * (ce - cb), cudaMemcpyHostToDevice, st));
-      k_setup<<<ns, 128, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, s0, ns);
-      ++launches;
-      {
+      if (!flist[0].empty() || !flist[1].empty()) {
+         const int n0 = (int)flist[0].size(), n1 = (int)flist[1].size();
+         if (n0) memcpy(pin_flist + s0, flist[0].data(), sizeof(int) * n0);
+         if (n1) memcpy(pin_flist + s0 + n0, flist[1].data(), sizeof(int) * n1);
+         CU(cudaMemcpyAsync(d_flist + s0, pin_flist + s0, sizeof(int) * (n0 + n1), cudaMemcpyHostToDevice, st));
+         if (n0) {
+            k_front<1><<<n0, ffront::THREADS, fsmem[0], st>>>(d_fr, P->d_ss, d_flist + s0, P->d_child_idx, d_child_doff, P->d_rel, P->d_aptr,
+                                                             P->d_asrc, P->d_acol, P->d_arow, d_val, prm);
+            ++launches;
+         }
+         if (n1) {
+            k_front<2><<<n1, ffront::THREADS, fsmem[1], st>>>(d_fr, P->d_ss, d_flist + s0 + n0, P->d_child_idx, d_child_doff, P->d_rel, P->d_aptr,
+                                                             P->d_asrc, P->d_acol, P->d_arow, d_val, prm);
+            ++launches;
+         }
+      }
+      if (ngeneral > 0) {
+         k_setup<<<ns, 128, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, s0, ns);
+         ++launches;
+      }
+      if (ngeneral > 0) {
          int64_t e0 = P->lvl_a_ptr[l], e1 = P->lvl_a_ptr[l + 1];
          if (e1 > e0) {
             k_scatter_a<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, st>>>(d_fr, P->d_aslot, P->d_asrc, P->d_acol, P->d_arow, d_val, e0, e1);
@@ -1166,7 +1216,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       // so each ordinal gets its own region of the pinned buffer.
       {
          int maxc = 0;
-         for (int s = s0; s < s1; ++s) if (active[s]) maxc = std::max(maxc, P->hss[s].child_end - P->hss[s].child_begin);
+         for (int s = s0; s < s1; ++s) if (live[s]) maxc = std::max(maxc, P->hss[s].child_end - P->hss[s].child_begin);
          size_t pin_off = 0;
          for (int k = 0; k < maxc; ++k) {
             lvl_list.clear();
@@ -1174,7 +1224,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             tileptr.clear();
             tileptr.push_back(0);
             for (int s = s0; s < s1; ++s) {
-               if (!active[s]) continue;
+               if (!live[s]) continue;
                const SlotStatic& ss = P->hss[s];
                if (ss.child_end - ss.child_begin <= k) continue;
                int cs = P->child_idx[ss.child_begin + k];
@@ -1258,7 +1308,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          auto run_chunk = [&](int j0, int j1, cudaStream_t sx, bool single, int sidx) -> int {
             int maxm = 0, maxn = 0;
             for (int q = j0; q < j1; ++q)
-               if (active[order[q]]) { maxm = std::max(maxm, hfr[order[q]].m); maxn = std::max(maxn, hfr[order[q]].n); }
+               if (live[order[q]]) { maxm = std::max(maxm, hfr[order[q]].m); maxn = std::max(maxn, hfr[order[q]].n); }
             if (maxm == 0) return 0;
             const int* lst = nullptr;
             const int b0 = s0 + j0;   // first slot of the bucket
@@ -1294,14 +1344,14 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                };
                for (int ob = 0; ob < nouter; ++ob) {
                   int na = 0;
-                  for (int q = j0; q < j1; ++q) if (active[order[q]] && nblocks_of(hfr[order[q]]) > ob) na = q - j0 + 1;
+                  for (int q = j0; q < j1; ++q) if (live[order[q]] && nblocks_of(hfr[order[q]]) > ob) na = q - j0 + 1;
                   map_na[ob] = na;
                   tl.assign(na, 0);
                   int64_t total = 0;
                   const int g = ob / G;
                   for (int q = 0; q < na; ++q) {
                      const FrontDev& ff = hfr[order[j0 + q]];
-                     if (!active[order[j0 + q]] || ff.n <= ob * PB) continue;
+                     if (!live[order[j0 + q]] || ff.n <= ob * PB) continue;
                      const int kend = std::min(ff.n, (ob + 1) * PB);
                      int64_t cnt = 0;
                      if (!big) {
@@ -1331,7 +1381,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                      int64_t total = 0;
                      for (int q = 0; q < na; ++q) {
                         const FrontDev& ff = hfr[order[j0 + q]];
-                        if (!active[order[j0 + q]] || ff.n <= g * G * PB) continue;
+                        if (!live[order[j0 + q]] || ff.n <= g * G * PB) continue;
                         const int kend = std::min(ff.n, (g + 1) * G * PB);
                         const int c1 = G == 1 ? kend : std::min(ff.m, std::max(kend, (g + 1) * G * PB));
                         if (c1 >= ff.m) continue;
@@ -1367,7 +1417,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                const int g = ob0 / G;
                for (int q = j0; q < j1; ++q) {
                   const FrontDev& ff = hfr[order[q]];
-                  if (!active[order[q]] || ff.n <= ob0 * PB) continue;
+                  if (!live[order[q]] || ff.n <= ob0 * PB) continue;
                   const double ka = ob0 * PB, kb = std::min<double>(ff.n, (ob1 + 1) * PB);
                   const double c1 = G == 1 ? kb : std::min<double>(ff.m, std::max<double>(kb, (g + 1) * G * PB));
                   double ca, cb;
@@ -1385,7 +1435,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                const int g = ob / G, gpos = ob % G;
                const bool glast = gpos == G - 1 || ob == nouter - 1;
                int maxw = 0;
-               for (int q = 0; q < na; ++q) if (active[order[j0 + q]]) maxw = std::max(maxw, std::min(PB, hfr[order[j0 + q]].n - ob * PB));
+               for (int q = 0; q < na; ++q) if (live[order[j0 + q]]) maxw = std::max(maxw, std::min(PB, hfr[order[j0 + q]].n - ob * PB));
                const int wcap = (maxw + NB - 1) / NB * NB;
                // blocks shortened by failed pivots leave `done` behind ob*PB, so the row grid covers the
                // whole front; CTAs above the block exit at once
@@ -1416,7 +1466,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                }
                // a front that sees a failed pivot stalls (instead of parking the failed columns at once) whenever other
                // work on it may be outstanding: a concurrent slice, or the deferred update of its group
-               const int stall_on_fail = (la || G > 1) ? 1 : 0;
+               const int stall_on_fail = ((la || G > 1) ? 1 : 0) | 2;     // bit 1: fronts of k_front are passed by
                if (wcap == NB) k_block<0><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, stall_on_fail);
                else if (wcap == 2 * NB) k_block<1><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, stall_on_fail);
                else k_block<2><<<na, 256, block_smem_bytes(wcap), sx>>>(d_fr, lst, b0, prm, 0, wcap, par, stall_on_fail);
@@ -1476,10 +1526,10 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                int nf = 0;
                std::vector<int> fm;
                int nfl = 0;
-               for (int q = j0; q < j1; ++q) if (active[order[q]] && nblocks_of(hfr[order[q]]) >= 2) ++nfl;
+               for (int q = j0; q < j1; ++q) if (live[order[q]] && nblocks_of(hfr[order[q]]) >= 2) ++nfl;
                const int fparts = std::max(1, 148 / std::max(nfl, 1));
                for (int q = j0; q < j1; ++q)
-                  if (active[order[q]] && nblocks_of(hfr[order[q]]) >= 2)
+                  if (live[order[q]] && nblocks_of(hfr[order[q]]) >= 2)
                      for (int pp = 0; pp < fparts; ++pp) { fm.push_back(q - j0); fm.push_back(pp); fm.push_back(fparts); ++nf; }
                if (nf > 0 && updmap_used + fm.size() <= UPDMAP_CAP) {
                   memcpy(pin_updmap + updmap_used, fm.data(), sizeof(int) * fm.size());
@@ -1489,7 +1539,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   ++launches;
                } else if (nf > 0) return SSIDS_ERROR_ALLOCATION;
             }
-            k_block<0><<<j1 - j0, 256, block_smem_bytes(NB), sx>>>(d_fr, lst, b0, prm, 1, NB, 0, 0);
+            k_block<0><<<j1 - j0, 256, block_smem_bytes(NB), sx>>>(d_fr, lst, b0, prm, 1, NB, 0, 2);
             ++launches;
             return 0;
          };
@@ -1500,7 +1550,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             int nact = 0;
             double work = 0;
             while (i1 < ns && cls(order[i1]) == c) {
-               if (active[order[i1]]) { ++nact; work += (double)hfr[order[i1]].n * hfr[order[i1]].m * hfr[order[i1]].m; }
+               if (live[order[i1]]) { ++nact; work += (double)hfr[order[i1]].n * hfr[order[i1]].m * hfr[order[i1]].m; }
                ++i1;
             }
             // a few large fronts: split them over streams so that one group's block factorisation
@@ -1509,7 +1559,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             // classes of many medium fronts: stream groups and the small-front kernel (one group's block factorisation
             // beside another's update); classes with fronts of upd3_min_m rows and more: one chunk, k_upd3
             int cls_maxm = 0;
-            for (int q = i0; q < i1; ++q) if (active[order[q]]) cls_maxm = std::max(cls_maxm, hfr[order[q]].m);
+            for (int q = i0; q < i1; ++q) if (live[order[q]]) cls_maxm = std::max(cls_maxm, hfr[order[q]].m);
             const bool cls_big = c >= 3 && use_upd3 && cls_maxm >= upd3_min_m;
             if (!o.profile && !trace && nact >= 2 && nact <= 128 && c >= 2 && !cls_big) G = std::min(nact, max_groups);
             if (G == 1) {
@@ -1523,7 +1573,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   int j1 = j0;
                   const double goal = work * (g2 + 1) / G;
                   while (j1 < i1 && (acc < goal || g2 == G - 1)) {
-                     if (active[order[j1]]) acc += (double)hfr[order[j1]].n * hfr[order[j1]].m * hfr[order[j1]].m;
+                     if (live[order[j1]]) acc += (double)hfr[order[j1]].n * hfr[order[j1]].m * hfr[order[j1]].m;
                      ++j1;
                   }
                   if (g2 == G - 1) j1 = i1;

@@ -321,9 +321,11 @@ __global__ void __launch_bounds__(256, KIND < 2 ? 2 : 1) k_block(FrontDev* fr, c
    if (threadIdx.x < sizeof(FrontDev) / 8) reinterpret_cast<double*>(&sf)[threadIdx.x] = reinterpret_cast<const double*>(&f)[threadIdx.x];
    __syncthreads();
    if (sf.flag < 0) return;
-   // look-ahead schedule: a front that saw a failed pivot waits for the synchronous retry rounds, because
+   // la bit 1: the front belongs to k_front on this pass (a front it rolled back waits for the retry rounds)
+   if (sf.fused && (la & 2)) return;
+   // look-ahead schedule (la bit 0): a front that saw a failed pivot waits for the synchronous retry rounds, because
    // parking failed columns moves entries that a concurrent bulk update may be working on
-   if (sf.stall && la) {
+   if (sf.stall && (la & 1)) {
       if (threadIdx.x == 0) f.urec[par][1] = 0;   // this parity's record belongs to a block that is already applied
       return;
    }
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(256, KIND < 2 ? 2 : 1) k_block(FrontDev* fr, c
          if (tid == 0) { f.flag = SSIDS_ERROR_NOT_POS_DEF; f.w = 0; }
          return;
       }
-      if (nfail > 0 && la) {
+      if (nfail > 0 && (la & 1)) {
          __syncthreads();
          if (tid == 0) { f.stall = 1; f.urec[par][1] = 0; }
          return;
