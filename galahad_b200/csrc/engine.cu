@@ -74,6 +74,7 @@ struct SlotStatic {
    int ncol, nrow, parent, first_piv;   // parent slot, -1 for roots
    int64_t rl_off, rel_off;
    int child_begin, child_end;
+   int npm, pad_;                       // npm: rows below the pivots that are candidate columns of the parent (rel < parent's ncol)
 };
 
 struct Params {
@@ -711,7 +712,9 @@ Plan* plan_create(const Symbolic& sym, int device, int* cuda_error) {
             int c = P->slot_node[P->child_idx[ci]];
             int cn = sym.sptr[c + 1] - sym.sptr[c];
             int64_t o = rel_off[c];
-            for (int64_t j = sym.rptr[c] + cn; j < sym.rptr[c + 1]; ++j) rel[o++] = map[sym.rlist[j]];
+            int npm = 0;
+            for (int64_t j = sym.rptr[c] + cn; j < sym.rptr[c + 1]; ++j) { rel[o++] = map[sym.rlist[j]]; if (map[sym.rlist[j]] < st.ncol) ++npm; }
+            P->hss[P->child_idx[ci]].npm = npm;
          }
       }
    }
@@ -843,6 +846,7 @@ class Numeric {
    Arena fac, dar, par, car[2], war, bar;   // bar: contribution blocks that cross a part boundary + imports
    std::vector<char> active, boundary;
    std::vector<char> live;                 // per slot, during a level: active and not taken by k_front
+   std::vector<char> lvl_fusable;          // per level: every front fits k_front when no column is delayed into it
    int *d_flist = nullptr, *pin_flist = nullptr;   // fronts of a level taken by k_front: [n <= 32 | n <= 64]
    std::vector<int> part_kind, owner;      // per slot; owner -1 = root part
    int my_rank = 0, nranks = 1;
@@ -936,8 +940,10 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(2 * NB)));
    CU(cudaFuncSetAttribute(k_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(NB)));
    CU(cudaFuncSetAttribute(k_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem_bytes(PB)));
-   CU(cudaFuncSetAttribute(k_front<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ffront::SMEM_CAP));
-   CU(cudaFuncSetAttribute(k_front<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ffront::SMEM_CAP));
+   CU(cudaFuncSetAttribute(k_front<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ffront::SMEM_CAP));
+   CU(cudaFuncSetAttribute(k_front<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ffront::SMEM_CAP));
+   CU(cudaFuncSetAttribute(k_front<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ffront::SMEM_CAP));
+   CU(cudaFuncSetAttribute(k_front<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ffront::SMEM_CAP));
    CU(cudaFuncSetAttribute(k_fwd_step<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd(128)));
    CU(cudaFuncSetAttribute(k_fwd_step<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd(128)));
    CU(cudaFuncSetAttribute(k_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem()));
@@ -996,6 +1002,16 @@ int Numeric::init() {
    boundary.assign(nn, 0);
    part_kind.assign(nn, 0);
    owner.assign(nn, 0);
+   lvl_fusable.assign(P->nlevels + 1, 0);
+   for (int l = 0; l < P->nlevels; ++l) {
+      bool all = true;
+      for (int s = P->lvl_ptr[l]; s < P->lvl_ptr[l + 1] && all; ++s) {
+         const SlotStatic& ss = P->hss[s];
+         const int nchs = ss.child_end - ss.child_begin;
+         all = ss.ncol <= ffront::MAXN && nchs <= ffront::MAXCH && ffront::smem_bytes(ss.nrow, ss.ncol, nchs) <= ffront::SMEM_CAP;
+      }
+      lvl_fusable[l] = all ? 1 : 0;
+   }
    init_failed = false;
    inited = true;
    return 0;
@@ -1061,6 +1077,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    const bool use_pdl = !(getenv("B200LDLT_PDL") && atoi(getenv("B200LDLT_PDL")) == 0);
    // small fronts (at most 64 candidate columns, panel in shared memory) in one launch per level (front_kernels.cuh)
    const bool use_front = !(getenv("B200LDLT_FRONT") && atoi(getenv("B200LDLT_FRONT")) == 0);
+   const int front_small_m = getenv("B200LDLT_FRONT_SMALLM") ? atoi(getenv("B200LDLT_FRONT_SMALLM")) : 96;
    const int upd3_min_m = getenv("B200LDLT_UPD3_MINM") ? atoi(getenv("B200LDLT_UPD3_MINM")) : 1800;
    const int defer_g = getenv("B200LDLT_DEFER") ? std::max(1, atoi(getenv("B200LDLT_DEFER"))) : 4;
    const int defer_min_m = getenv("B200LDLT_DEFER_MINM") ? atoi(getenv("B200LDLT_DEFER_MINM")) : 2048;
@@ -1091,8 +1108,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       updmap_used = 0;   // the previous level ended with a stream synchronisation
       // sizes with delays
       size_t totL = 0, totC = 0, totD = 0, totP = 0, totW = 0;
-      std::vector<int> flist[2];
-      size_t fsmem[2] = {0, 0};
+      std::vector<int> flist[4];
+      size_t fsmem[4] = {0, 0, 0, 0};
       int ngeneral = 0;
       for (int s = s0; s < s1; ++s) live[s] = 0;
       int nactive_lvl = 0;
@@ -1121,7 +1138,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             const int nchs = ss.child_end - ss.child_begin;
             if (use_front && f.n <= ffront::MAXN && nchs <= ffront::MAXCH && ffront::smem_bytes(f.m, f.n, nchs) <= ffront::SMEM_CAP) {
                f.fused = 1;
-               const int np = f.n <= NB ? 0 : 1;
+               // buckets: one or two panels x four warps (fronts of at most front_small_m rows) or eight
+               const int np = (f.n <= NB ? 0 : 1) + (f.m <= front_small_m ? 2 : 0);
                flist[np].push_back(s);
                fsmem[np] = std::max(fsmem[np], ffront::smem_bytes(f.m, f.n, nchs));
             }
@@ -1178,27 +1196,35 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          if (prez_l && prez_l == (char*)Lb) zl = std::min(prez_l_bytes, totL * 8);
          if (prez_c && prez_c == (char*)Cb) zc = std::min(prez_c_bytes, totC * 8);
          prez_l = prez_c = nullptr;
-         if (totL * 8 > zl) CU(cudaMemsetAsync((char*)Lb + zl, 0, totL * 8 - zl, st));
-         if (totC * 8 > zc) CU(cudaMemsetAsync((char*)Cb + zc, 0, totC * 8 - zc, st));
+         // k_front writes every entry of its fronts' L and of the lower triangle of their contribution blocks: a level
+         // it takes whole needs no zero-fill
+         if (ngeneral > 0 && totL * 8 > zl) CU(cudaMemsetAsync((char*)Lb + zl, 0, totL * 8 - zl, st));
+         if (ngeneral > 0 && totC * 8 > zc) CU(cudaMemsetAsync((char*)Cb + zc, 0, totC * 8 - zc, st));
       }
       CU(cudaMemsetAsync(Db, 0, totD * 8, st));
       const int cb = P->hss[s0].child_begin, ce = P->hss[s1 - 1].child_end;
       if (ce > cb)
          CU(cudaMemcpyAsync(d_child_doff + cb, child_doff.data() + cb, sizeof(int) * (ce - cb), cudaMemcpyHostToDevice, st));
-      if (!flist[0].empty() || !flist[1].empty()) {
-         const int n0 = (int)flist[0].size(), n1 = (int)flist[1].size();
-         if (n0) memcpy(pin_flist + s0, flist[0].data(), sizeof(int) * n0);
-         if (n1) memcpy(pin_flist + s0 + n0, flist[1].data(), sizeof(int) * n1);
-         CU(cudaMemcpyAsync(d_flist + s0, pin_flist + s0, sizeof(int) * (n0 + n1), cudaMemcpyHostToDevice, st));
-         if (n0) {
-            k_front<1><<<n0, ffront::THREADS, fsmem[0], st>>>(d_fr, P->d_ss, d_flist + s0, P->d_child_idx, d_child_doff, P->d_rel, P->d_aptr,
-                                                             P->d_asrc, P->d_acol, P->d_arow, d_val, prm);
-            ++launches;
+      {
+         int nf = 0;
+         for (int b = 0; b < 4; ++b) {
+            if (!flist[b].empty()) memcpy(pin_flist + s0 + nf, flist[b].data(), sizeof(int) * flist[b].size());
+            nf += (int)flist[b].size();
          }
-         if (n1) {
-            k_front<2><<<n1, ffront::THREADS, fsmem[1], st>>>(d_fr, P->d_ss, d_flist + s0 + n0, P->d_child_idx, d_child_doff, P->d_rel, P->d_aptr,
-                                                             P->d_asrc, P->d_acol, P->d_arow, d_val, prm);
+         if (nf > 0) CU(cudaMemcpyAsync(d_flist + s0, pin_flist + s0, sizeof(int) * nf, cudaMemcpyHostToDevice, st));
+         int off = 0;
+         for (int b = 0; b < 4; ++b) {
+            const int nb = (int)flist[b].size();
+            if (nb == 0) continue;
+            const int* lst = d_flist + s0 + off;
+#define B200_FRONT_ARGS d_fr, P->d_ss, lst, P->d_child_idx, d_child_doff, P->d_rel, P->d_aptr, P->d_asrc, P->d_acol, P->d_arow, d_val, prm
+            if (b == 0) k_front<1, 8><<<nb, 256, fsmem[b], st>>>(B200_FRONT_ARGS);
+            else if (b == 1) k_front<2, 8><<<nb, 256, fsmem[b], st>>>(B200_FRONT_ARGS);
+            else if (b == 2) k_front<1, 4><<<nb, 128, fsmem[b], st>>>(B200_FRONT_ARGS);
+            else k_front<2, 4><<<nb, 128, fsmem[b], st>>>(B200_FRONT_ARGS);
+#undef B200_FRONT_ARGS
             ++launches;
+            off += nb;
          }
       }
       if (ngeneral > 0) {
@@ -1262,7 +1288,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
       }
       // The children's contribution blocks (the other arena) are dead once extend-add has run: zero the next
       // level's C region there, and its L region behind this level's, beside the factorisation kernels.
-      if (phase == 0 && l + 1 < P->nlevels && !trace) {
+      if (phase == 0 && l + 1 < P->nlevels && !trace && !(use_front && lvl_fusable[l + 1])) {
          Arena& na2 = car[(l + 1) & 1];
          const size_t cbytes = (size_t)P->lvl_C_doubles[l + 1] * 8, lbytes = (size_t)P->lvl_L_doubles[l + 1] * 8;
          CU(cudaEventRecord(ev_ea, st));
