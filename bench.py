@@ -32,7 +32,11 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_upd3 launch from an ncu --set full capture (profiles/); filled in
 # from the capture of the current build, None until then
-UPD3_TRAFFIC = {"bytes": None, "note": "no ncu capture of this build yet"}
+UPD3_TRAFFIC = {"bytes": 2453002600,
+                "note": "dram__bytes_read.sum + dram__bytes_write.sum of the longest k_upd3 launch of C2 (1.71 ms, rank-512 deferred update of a "
+                        "level's fronts, ncu --set full, profiles/r2_ncu_k_upd3.txt): 2.09 GB read + 0.36 GB written for about 0.8 GB of "
+                        "algorithmic bytes -- the operands of all fronts of the launch (about 200 MB) do not stay in L2 beside the C stream; the "
+                        "launch is compute-bound all the same (DMMA pipe 88 % active, 1.4 TB/s of DRAM traffic); one launch, not an average"}
 
 METRIC = "sls_factorize_fp64_tflops"
 UNIT = "TFLOP/s"
@@ -54,6 +58,11 @@ def grid_for(args):
 def make_problem(grid):
     from galahad_b200 import problems as P
     return P.laplace_problem(grid)
+
+
+def config_for(grid, flops, nfact):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    return {"workload": workload_name(grid), "num_flops": flops, "num_factor": nfact}
 
 
 def workload_name(grid):
@@ -173,6 +182,15 @@ def run_reference(args):
     s = Solver()
     s.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"])
     flops = float(s.inform.num_flops)
+    cfg_flops, cfg_nfact = flops, int(s.inform.num_factor)
+    if grid != args.grid:
+        # the config names the full workload; the timed sample is the smaller grid
+        s2 = Solver()
+        p2 = make_problem(args.grid)
+        s2.analyse(p2["n"], p2["ptr"], p2["row"], p2["order"])
+        cfg_flops, cfg_nfact = float(s2.inform.num_flops), int(s2.inform.num_factor)
+        s2.free()
+        del p2
     sym = s.symbolic()
     ref = refssids.RefSSIDS(sym, prob["n"], u=0.01, small=1e-20)
     rng = np.random.default_rng(20261018)
@@ -192,7 +210,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": (mf + ms) * 1e3, "higher_is_better": True, "scaling": args.scaling_kind,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.grid), "sample_grid": grid, "threads": ref.nthreads()},
+        "config": config_for(args.grid, cfg_flops, cfg_nfact),
+        "sample_grid": grid, "threads": ref.nthreads(),
         "factor_ms": mf * 1e3, "solve_ms": ms * 1e3,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.nthreads(), "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -244,10 +263,10 @@ def run_ours(args):
         assert f >= 0, f"factor flag {f}"
         tf = s.inform.time_factor_device
         nl = s.inform.reserved[0]
-        uf, us = s.inform.upd_flops, s.inform.upd_seconds
+        uf, us, ul = s.inform.upd_flops, s.inform.upd_seconds, s.inform.reserved[2]
         f = s.solve_device(d_x.data_ptr(), 1, n)
         assert f >= 0, f"solve flag {f}"
-        return tf, s.inform.time_solve, nl + s.inform.reserved[1], uf, us
+        return tf, s.inform.time_solve, nl + s.inform.reserved[1], uf, us, ul
 
     def step_host():
         import ctypes as C
@@ -318,10 +337,10 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling_kind, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.grid), "num_flops": flops, "num_factor": nfact,
-                       "parallelism": "1 GPU",
-                       "l2": "256 MB buffer written between iterations; factor working set >> L2",
-                       "timing": "value = flops / mean CUDA-event time of the numeric factorization (engine stream, val resident); ms_per_step = CUDA events around the K steps / K"},
+            "config": config_for(args.grid, flops, nfact),
+            "notes": {"parallelism": "1 GPU",
+                      "l2": "256 MB buffer written between iterations; factor working set >> L2",
+                      "timing": "value = flops / mean CUDA-event time of the numeric factorization (engine stream, val resident); ms_per_step = CUDA events around the K steps / K"},
             "factor_ms": tf * 1e3, "solve_ms": ts * 1e3,
             "solve_gbs": (2 * 8 * nfact + 2 * 8 * n) / ts / 1e9,
             "backward_error": berr,
@@ -335,12 +354,17 @@ def run_ours(args):
                          "kernel": "k_upd3 (trailing Schur update of the large fronts, FP64 DMMA)",
                          "peak_source": "measured here: cuBLAS Dgemm 4096^3 via torch.matmul(float64), best of 5 (MEASURED_PEAKS.json has no FP64 entry)",
                          "share_of_factor_time": upd_secs / (tf_prof * args.steps) if tf_prof > 0 else None,
-                         "launches_per_step": int(s.inform.reserved[2]),
+                         "launches_per_step": int(resp[-1][5]),
                          "measured": "second pass of the same K steps with CUDA events around every k_upd3 launch on the engine stream (no look-ahead: each launch timed alone, factor_ms %.2f)" % (tf_prof * 1e3)},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(prob, s, flops)
+        if world == 1 and not args.no_kkt:
+            s.free()
+            del d_val, flush
+            torch.cuda.empty_cache()
+            line["kkt_c3"] = kkt_c3(torch, peak)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -403,12 +427,12 @@ def run_tree_parallel(args, prob, torch, dist, rank, world, local):
             "metric": METRIC, "value": flops / tf / 1e12, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling_kind, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.grid), "num_flops": flops, "num_factor": nfact,
-                       "parallelism": f"tree-parallel over {world} GPUs: proportional mapping, {ds.nstages} stages, "
-                                      f"{sum(1 for st in ds.boundaries for (_, a, c) in st if a != c)} boundary fronts moved between ranks "
-                                      f"({ds.bytes_moved / 1e6:.1f} MB through rank 0 per factorisation)",
-                       "l2": "256 MB buffer written between iterations; factor working set >> L2",
-                       "timing": "max over ranks of the wall time of factor (H2D of val, the stages and the exchanges between them) between device synchronisations"},
+            "config": config_for(args.grid, flops, nfact),
+            "notes": {"parallelism": f"tree-parallel over {world} GPUs: proportional mapping, {ds.nstages} stages, "
+                                     f"{sum(1 for st in ds.boundaries for (_, a, c) in st if a != c)} boundary fronts moved between ranks "
+                                     f"({ds.bytes_moved / 1e6:.1f} MB through rank 0 per factorisation)",
+                      "l2": "256 MB buffer written between iterations; factor working set >> L2",
+                      "timing": "max over ranks of the wall time of factor (H2D of val, the stages and the exchanges between them) between device synchronisations"},
             "factor_ms": tf * 1e3, "solve_ms": ts * 1e3, "stage_ms_rank0": [round(v * 1e3, 3) for v in ds.t_stage],
             "backward_error": P.backward_error(prob, x, b), "num_neg": ds.num_neg,
             "gpu_launches": int(ds.launches) * args.steps,   # rank 0, all stages
@@ -421,6 +445,43 @@ def run_tree_parallel(args, prob, torch, dist, rank, world, local):
         print(json.dumps(line))
     dist.destroy_process_group()
     return 0
+
+
+def kkt_c3(torch, peak):
+    """BASELINE config C3 beside the headline: the indefinite KKT matrix [H A^T; A -D] of a 110^3 grid QP (n = 1,996,500,
+    1.04e14 flops), where the trailing updates, not the panel chain, bound the factorisation.  One warm-up and one timed
+    factorisation + solve (CUDA events on the engine stream, values resident); inertia checked against (n, m, 0)."""
+    try:
+        from galahad_b200 import problems as P
+        from galahad_b200._lib import Solver
+        prob = P.kkt_grid_problem(110)
+        s = Solver()
+        s.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"])
+        flops = float(s.inform.num_flops)
+        d_val = torch.from_numpy(prob["val"]).cuda()
+        rng = np.random.default_rng(20261018)
+        b = rng.uniform(-1, 1, prob["n"])
+        d_x = torch.from_numpy(b).cuda()
+        tf = 0.0
+        for _ in range(2):
+            torch.cuda.synchronize()
+            f = s.factor_device(d_val.data_ptr(), False)
+            assert f >= 0, f
+            tf = s.inform.time_factor_device
+        neg = int(s.inform.num_neg)
+        f = s.solve_device(d_x.data_ptr(), 1, prob["n"])
+        assert f >= 0, f
+        ts = s.inform.time_solve
+        berr = P.backward_error(prob, d_x.cpu().numpy(), b)
+        out = {"workload": "C3: KKT [H A^T; A -D] of a 110^3 grid QP (n=%d), ND order, pivot_control=1" % prob["n"],
+               "num_flops": flops, "factor_ms": tf * 1e3, "tflops": flops / tf / 1e12, "frac_of_fp64_peak": flops / tf / 1e12 / peak,
+               "solve_ms": ts * 1e3, "solve_gbs": (2 * 8 * int(s.inform.num_factor)) / ts / 1e9,
+               "num_neg": neg, "num_neg_expected": int(prob["inertia"][1]), "num_delay": int(s.inform.num_delay),
+               "backward_error": berr, "steps": 1, "warmup": 1}
+        s.free()
+        return out
+    except Exception as e:   # the headline line must survive a failure of the secondary measurement
+        return {"unavailable": repr(e)}
 
 
 def cpu_baseline(prob, s, flops):
@@ -452,6 +513,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = flops per GPU as C2 (default), strong = the 64^3 matrix at every N")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-kkt", action="store_true", help="skip the secondary C3 (KKT) measurement")
     args = ap.parse_args()
     args.scaling_kind = args.scaling if args.gpus > 1 else "weak"
     args.grid = grid_for(args)

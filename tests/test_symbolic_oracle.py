@@ -1,0 +1,129 @@
+"""Symbolic analysis: the C++ product path (csrc/analyse.cpp, through the C ABI) against the
+independent Python restatement of the reference's Fortran (oracle/symbolic_oracle.py), entry by entry: final pivot order,
+inverse permutation, supernode partition, assembly tree, sorted row lists, the A -> L map, num_factor, num_flops.
+Integer work: the bar is bit-exact.  The committed digests (tests/golden/symbolic_digests.json, written by
+tests/golden/make_symbolic_golden.py) pin both against silent drift."""
+import hashlib
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from galahad_b200 import problems as P
+from galahad_b200._lib import Solver
+from oracle import symbolic_oracle as SO
+from util import bcsstk01_problem, golden, golden_cases, kat_problem
+
+
+def pattern_problem(A, order=None):
+    n = A.shape[0]
+    N, ptr, row, val = P.lower_csc(sp.csc_matrix(A))
+    return dict(n=N, ptr=ptr, row=row, val=val, order=np.arange(n, dtype=np.int32) if order is None else order)
+
+
+def cases():
+    out = []
+    for which in ("indef", "spd"):
+        for order in ("identity", "reverse"):
+            out.append((f"kat_{which}_{order}", kat_problem(which, order)[0], 32))
+    out.append(("bcsstk01_identity", bcsstk01_problem("identity"), 32))
+    out.append(("bcsstk01_reverse", bcsstk01_problem("reverse"), 32))
+    for name, prob, _ in golden_cases():
+        if not name.endswith("_pd") and "it3" not in name:
+            out.append((name, prob, 32))
+    out.append(("lap7_12_nemin1", P.laplace_problem(12), 1))
+    out.append(("lap7_12_nemin8", P.laplace_problem(12), 8))
+    out.append(("kkt7_10_nemin4", P.kkt_grid_problem(10), 4))
+    n = 41                                   # arrow: a root with 40 children (merge-sort path of find_supernodes)
+    A = np.eye(n) * 4
+    A[n - 1, :] = 1
+    A[:, n - 1] = 1
+    out.append(("arrow_nemin1", pattern_problem(A), 1))
+    out.append(("arrow_nemin32", pattern_problem(A), 32))
+    rng = np.random.default_rng(5)
+    for t, nemin in enumerate((1, 4, 16, 32)):
+        n = 200
+        M = sp.random(n, n, density=0.01, random_state=int(rng.integers(1 << 30)), format="csc")
+        M = M + M.T + sp.eye(n) * 3
+        out.append((f"sprand_{t}_nemin{nemin}", pattern_problem(M.toarray(), rng.permutation(n).astype(np.int32)), nemin))
+    # structurally singular: variables 3 and 6 have no entry at all (null roots of find_postorder)
+    ptr = np.array([0, 2, 3, 5, 5, 6, 8, 8, 9], np.int64)
+    row = np.array([0, 1, 1, 2, 4, 4, 5, 7, 7], np.int32)
+    out.append(("null_columns", dict(n=8, ptr=ptr, row=row, val=np.ones(9), order=np.arange(8, dtype=np.int32)), 32))
+    return out
+
+
+def product_arrays(prob, nemin):
+    s = Solver()
+    s.opt.nemin = nemin
+    flag = s.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"])
+    assert flag >= 0
+    sym = s.symbolic(base=1)
+    nl = sym["nlist"].reshape(-1, 2)
+    return dict(flag=flag, nnodes=sym["nnodes"], order=s.order + 1, invp=sym["invp"], sptr=sym["sptr"], sparent=sym["sparent"],
+                rptr=sym["rptr"], rlist=sym["rlist"], nptr=sym["nptr"], nlist1=nl[:, 0], nlist2=nl[:, 1],
+                num_factor=int(s.inform.num_factor), num_flops=int(s.inform.num_flops))
+
+
+def oracle_arrays(prob, nemin):
+    o = SO.analyse(prob["n"], prob["ptr"], prob["row"], prob["order"], nemin)
+    nn = o["nnodes"]
+    return dict(flag=o["flag"], nnodes=nn, order=o["order"][1:], invp=o["invp"][1:], sptr=o["sptr"][1:nn + 2], sparent=o["sparent"][1:nn + 1],
+                rptr=o["rptr"][1:nn + 2], rlist=o["rlist"][1:], nptr=o["nptr"][1:nn + 2], nlist1=o["nlist1"][1:], nlist2=o["nlist2"][1:],
+                num_factor=o["num_factor"], num_flops=o["num_flops"])
+
+
+KEYS = ("order", "invp", "sptr", "sparent", "rptr", "rlist", "nptr", "nlist1", "nlist2")
+
+
+def digest(arrs):
+    h = hashlib.sha256()
+    for k in KEYS:
+        h.update(np.asarray(arrs[k], dtype=np.int64).tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("name,prob,nemin", cases(), ids=[c[0] for c in cases()])
+def test_product_matches_symbolic_oracle(name, prob, nemin):
+    a = product_arrays(prob, nemin)
+    b = oracle_arrays(prob, nemin)
+    assert a["nnodes"] == b["nnodes"]
+    assert a["num_factor"] == b["num_factor"] and a["num_flops"] == b["num_flops"]
+    for k in KEYS:
+        assert np.array_equal(np.asarray(a[k], dtype=np.int64), np.asarray(b[k], dtype=np.int64)), (name, k)
+    g = golden("symbolic_digests.json")[name]
+    assert g["nnodes"] == a["nnodes"] and g["num_factor"] == a["num_factor"] and g["num_flops"] == a["num_flops"]
+    assert g["sha256"] == digest(a)
+
+
+def test_invalid_order_is_rejected():
+    # check_order, anal.f90:147-197: duplicates and out-of-range entries are SSIDS_ERROR_ORDER (-8)
+    prob = P.laplace_problem(4)
+    bad = prob["order"].copy()
+    bad[3] = bad[5]
+    assert SO.analyse(prob["n"], prob["ptr"], prob["row"], bad)["flag"] == -8
+    s = Solver()
+    assert s.analyse(prob["n"], prob["ptr"], prob["row"], bad) == -8
+
+
+def test_structural_invariants_on_a_larger_grid():
+    # sizes beyond what the pure-Python oracle is run on: properties that hold for any valid output
+    prob = P.laplace_problem(24)
+    a = product_arrays(prob, 32)
+    nn = a["nnodes"]
+    sptr, sparent, rptr, rlist = a["sptr"], a["sparent"], a["rptr"], a["rlist"]
+    assert sptr[0] == 1 and sptr[nn] == prob["n"] + 1 and np.all(np.diff(sptr) >= 1)
+    assert np.all(sparent > np.arange(1, nn + 1))                       # postordered: parent after child
+    assert sorted(a["order"].tolist()) == list(range(1, prob["n"] + 1))
+    for i in range(nn):
+        r = rlist[rptr[i] - 1: rptr[i + 1] - 1]
+        assert np.all(np.diff(r) > 0)                                   # ascending, no duplicates
+        nc = sptr[i + 1] - sptr[i]
+        assert np.array_equal(r[:nc], np.arange(sptr[i], sptr[i + 1]))  # pivots first
+        p = sparent[i]
+        if p <= nn:                                                     # rows below the pivots appear in the parent
+            rp = rlist[rptr[p - 1] - 1: rptr[p] - 1]
+            assert np.isin(r[nc:], rp).all()
+    m = np.diff(rptr) - np.diff(sptr)
+    k = np.diff(sptr)
+    assert a["num_factor"] == int((k * (k + 1) // 2 + k * m).sum())
