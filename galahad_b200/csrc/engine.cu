@@ -934,7 +934,8 @@ int Numeric::init() {
    init_failed = true;                               // cleared by the last line; any CU() failure below leaves it set
    CU(cudaSetDevice(P->device));
    CU(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM));
-   CU(cudaFuncSetAttribute(k_upd3, cudaFuncAttributeMaxDynamicSharedMemorySize, upd3::SMEM));
+   CU(cudaFuncSetAttribute(kt_upd3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd3::SMEM));
+   CU(cudaFuncSetAttribute(kt_upd3<upd3::STM>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd3::Shape<upd3::STM>::SMEM));
    { const int dbg = getenv("B200LDLT_DEBUG_UPD") ? 1 : 0; CU(cudaMemcpyToSymbol(g_upd_debug, &dbg, sizeof(int))); }
    CU(cudaFuncSetAttribute(k_block<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(PB)));
    CU(cudaFuncSetAttribute(k_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes(2 * NB)));
@@ -1077,6 +1078,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    const bool use_pdl = !(getenv("B200LDLT_PDL") && atoi(getenv("B200LDLT_PDL")) == 0);
    // small fronts (at most 64 candidate columns, panel in shared memory) in one launch per level (front_kernels.cuh)
    const bool use_front = !(getenv("B200LDLT_FRONT") && atoi(getenv("B200LDLT_FRONT")) == 0);
+   // the launches on a front's critical path (strips, the next group's columns of a deferred update) in 64 x 64 tiles
+   const bool small_strips = !(getenv("B200LDLT_SMALL_STRIPS") && atoi(getenv("B200LDLT_SMALL_STRIPS")) == 0);
+   const int small_strip_tiles = getenv("B200LDLT_SMALL_STRIP_TILES") ? atoi(getenv("B200LDLT_SMALL_STRIP_TILES")) : 148;
    const int front_small_m = getenv("B200LDLT_FRONT_SMALLM") ? atoi(getenv("B200LDLT_FRONT_SMALLM")) : 96;
    const int upd3_min_m = getenv("B200LDLT_UPD3_MINM") ? atoi(getenv("B200LDLT_UPD3_MINM")) : 1800;
    const int defer_g = getenv("B200LDLT_DEFER") ? std::max(1, atoi(getenv("B200LDLT_DEFER"))) : 4;
@@ -1354,6 +1358,10 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             // a launch keeps at least one CTA, so a front that lags behind is still updated correctly, only slower)
             std::vector<int> map_off(nouter + 1, 0), map_na(nouter, 0);            // k_update / strips, per block
             std::vector<int> bmap_off(ngroups + 1, 0);                              // k_upd3 bulk, per group
+            std::vector<int> gmap_off(ngroups + 1, 0);                              // the next group's columns of a group's update (GSTRIP)
+            // tile size of the launches on the critical path, per block / group: 64 when the launch would be less than one
+            // wave of 128 x 128 tiles (then a tile's latency, not the throughput, is what the next block waits for)
+            std::vector<int> strip_tile(nouter, 128), gstrip_on(ngroups, 0);
             std::vector<int64_t> gtiles(ngroups, 0);
             {
                std::vector<int> hmap;
@@ -1375,6 +1383,20 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   tl.assign(na, 0);
                   int64_t total = 0;
                   const int g = ob / G;
+                  int stile = 128;
+                  if (big && G > 1 && small_strips) {
+                     int64_t t128 = 0;
+                     for (int q = 0; q < na; ++q) {
+                        const FrontDev& ff = hfr[order[j0 + q]];
+                        if (!live[order[j0 + q]] || ff.n <= ob * PB) continue;
+                        const int kend = std::min(ff.n, (ob + 1) * PB);
+                        const int c1 = std::min(ff.m, std::max(kend, (g + 1) * G * PB));
+                        const int org = kend & ~1;
+                        if (c1 > kend) t128 += upd3::tiles_upto((c1 - org + 127) / 128, (ff.m - org + 127) / 128);
+                     }
+                     if (t128 < small_strip_tiles) stile = upd3::STM;
+                  }
+                  strip_tile[ob] = stile;
                   for (int q = 0; q < na; ++q) {
                      const FrontDev& ff = hfr[order[j0 + q]];
                      if (!live[order[j0 + q]] || ff.n <= ob * PB) continue;
@@ -1389,14 +1411,14 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                         // the block's own update: the columns behind it up to the end of the group
                         const int c1 = std::min(ff.m, std::max(kend, (g + 1) * G * PB));
                         const int org = kend & ~1;
-                        if (c1 > kend) cnt = upd3::tiles_upto((c1 - org + upd3::UTN - 1) / upd3::UTN, (ff.m - org + upd3::UTM - 1) / upd3::UTM);
+                        if (c1 > kend) cnt = upd3::tiles_upto((c1 - org + stile - 1) / stile, (ff.m - org + stile - 1) / stile);
                      }
                      tl[q] = cnt;
                      total += cnt;
                   }
                   // chunks that share the GPU with other streams keep to about half of the CTA slots, so that
                   // another chunk's block factorisation finds a free SM while this update runs
-                  const int64_t target = big ? 148 : std::min<int64_t>(std::max<int64_t>(total, 1), (single ? 2 : 1) * upd_share);
+                  const int64_t target = big ? (stile == 128 ? 148 : 296) : std::min<int64_t>(std::max<int64_t>(total, 1), (single ? 2 : 1) * upd_share);
                   if (!big || G > 1) deal(na, total, std::min<int64_t>(target, std::max<int64_t>(total, 1)));
                   map_off[ob + 1] = (int)hmap.size();
                }
@@ -1423,6 +1445,33 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                      bmap_off[g + 1] = (int)hmap.size();
                   }
                   for (int g = 0; g <= ngroups; ++g) if (bmap_off[g] < map_off[nouter]) bmap_off[g] = map_off[nouter];
+                  gmap_off[0] = (int)hmap.size();
+                  for (int g = 0; g < ngroups; ++g) {
+                     if (small_strips && g + 1 < ngroups) {
+                        const int na = map_na[g * G];
+                        const int stile = upd3::STM;
+                        tl.assign(na, 0);
+                        int64_t total = 0, t128 = 0;
+                        for (int q = 0; q < na; ++q) {
+                           const FrontDev& ff = hfr[order[j0 + q]];
+                           if (!live[order[j0 + q]] || ff.n <= g * G * PB) continue;
+                           const int kend = std::min(ff.n, (g + 1) * G * PB);
+                           const int c1 = G == 1 ? kend : std::min(ff.m, std::max(kend, (g + 1) * G * PB));
+                           if (c1 >= ff.m) continue;
+                           const int gse = G == 1 ? std::min(ff.m, kend + PB) : std::min(ff.m, c1 + G * PB);
+                           const int org = c1 & ~1;
+                           const int cb = std::min(ff.m, org + (gse - org + 127) / 128 * 128);
+                           tl[q] = upd3::tiles_upto((cb - org + stile - 1) / stile, (ff.m - org + stile - 1) / stile);
+                           total += tl[q];
+                           t128 += upd3::tiles_upto((cb - org + 127) / 128, (ff.m - org + 127) / 128);
+                        }
+                        if (t128 < small_strip_tiles) {
+                           gstrip_on[g] = 1;
+                           deal(na, total, std::min<int64_t>(296, std::max<int64_t>(total, 1)));
+                        }
+                     }
+                     gmap_off[g + 1] = (int)hmap.size();
+                  }
                }
                if (updmap_used + hmap.size() > UPDMAP_CAP) {   // staging in use by earlier copies: drain first
                   CU(cudaStreamSynchronize(st));
@@ -1435,6 +1484,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   CU(cudaMemcpyAsync(d_updmap + updmap_used, pin_updmap + updmap_used, sizeof(int) * hmap.size(), cudaMemcpyHostToDevice, sx));
                for (int ob = 0; ob <= nouter; ++ob) map_off[ob] += (int)updmap_used;
                for (int g = 0; g <= ngroups; ++g) bmap_off[g] += (int)updmap_used;
+               for (int g = 0; g <= ngroups; ++g) gmap_off[g] += (int)updmap_used;
                updmap_used += hmap.size();
             }
             // profile mode (bench roofline): every trailing-update launch between two events, its algorithmic flops
@@ -1481,7 +1531,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   if (nct > 0) {
                      CU(cudaEventRecord(ev_commit[sidx][0], sx));
                      CU(cudaStreamWaitEvent(bulk[sidx], ev_commit[sidx][0], 0));
-                     k_upd3<<<nct, upd3::THREADS, upd3::SMEM, bulk[sidx]>>>(d_fr, lst, b0, d_updmap + bmap_off[slice_g], 1, slice_g & 1, slice_tag,
+                     kt_upd3<128><<<nct, upd3::THREADS, upd3::SMEM, bulk[sidx]>>>(d_fr, lst, b0, d_updmap + bmap_off[slice_g], 1, slice_g & 1, slice_tag,
                                                                             s - 1, s, slice_ns - 1, slice_z);
                      CU(cudaEventRecord(ev_bulk[sidx][0], bulk[sidx]));
                      mark(bulk[sidx], "slice", ob, s);
@@ -1512,8 +1562,12 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                } else {
                   if (G > 1 && nct > 0) {
                      if (o.profile) { prof_region(ob, ob, true, false); prof_begin(); }
-                     launch_dep(use_pdl && !timeline && !o.profile, k_upd3, dim3(nct), dim3(upd3::THREADS), upd3::SMEM, sx, d_fr, lst, b0,
-                                (const int*)(d_updmap + map_off[ob]), 0, par, 0, 0, 0, 1, 0);
+                     if (strip_tile[ob] == upd3::STM)
+                        launch_dep(use_pdl && !timeline && !o.profile, kt_upd3<upd3::STM>, dim3(nct), dim3(upd3::THREADS), upd3::Shape<upd3::STM>::SMEM, sx,
+                                   d_fr, lst, b0, (const int*)(d_updmap + map_off[ob]), 0, par, 0, 0, 0, 1, 0);
+                     else
+                        launch_dep(use_pdl && !timeline && !o.profile, kt_upd3<128>, dim3(nct), dim3(upd3::THREADS), upd3::SMEM, sx, d_fr, lst, b0,
+                                   (const int*)(d_updmap + map_off[ob]), 0, par, 0, 0, 0, 1, 0);
                      mark(sx, "strip", ob, nct);
                      if (o.profile) prof_end();
                      ++launches;
@@ -1530,10 +1584,19 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                         z = (int)std::ceil(256.0 * std::max(0.0, 1.0 - cap / (double)gtiles[g]));
                         z = std::max(0, std::min(256, z));
                      }
+                     const int nctg = (gmap_off[g + 1] - gmap_off[g]) / 3;
                      if (nctb > 0) {
                         if (o.profile) { prof_region(g * G, ob, false, true); prof_begin(); }
-                        launch_dep(use_pdl && !timeline && !o.profile, k_upd3, dim3(nctb), dim3(upd3::THREADS), upd3::SMEM, sx, d_fr, lst, b0,
-                                   (const int*)(d_updmap + bmap_off[g]), 1, g & 1, g + 1, -1, 0, 1, z);
+                        if (nctg > 0) {
+                           // the next group's columns first, in small tiles; the bulk launches start behind them (sa = -2)
+                           launch_dep(use_pdl && !timeline && !o.profile, kt_upd3<upd3::STM>, dim3(nctg), dim3(upd3::THREADS), upd3::Shape<upd3::STM>::SMEM, sx,
+                                      d_fr, lst, b0, (const int*)(d_updmap + gmap_off[g]), 3, g & 1, g + 1, 0, 0, 1, 0);
+                           mark(sx, "gstrip", ob, nctg);
+                           ++launches;
+                        }
+                        if (nctg == 0 || z > 0)
+                        launch_dep(use_pdl && !timeline && !o.profile, kt_upd3<128>, dim3(nctb), dim3(upd3::THREADS), upd3::SMEM, sx, d_fr, lst, b0,
+                                   (const int*)(d_updmap + bmap_off[g]), 1, g & 1, g + 1, nctg > 0 ? -2 : -1, 0, 1, z);
                         mark(sx, "slice0", ob, z);
                         if (o.profile) prof_end();
                         ++launches;
@@ -1560,7 +1623,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                if (nf > 0 && updmap_used + fm.size() <= UPDMAP_CAP) {
                   memcpy(pin_updmap + updmap_used, fm.data(), sizeof(int) * fm.size());
                   CU(cudaMemcpyAsync(d_updmap + updmap_used, pin_updmap + updmap_used, sizeof(int) * fm.size(), cudaMemcpyHostToDevice, sx));
-                  k_upd3<<<nf, upd3::THREADS, upd3::SMEM, sx>>>(d_fr, lst, b0, d_updmap + updmap_used, 2, 0, 0, 0, 0, 1, 0);
+                  kt_upd3<128><<<nf, upd3::THREADS, upd3::SMEM, sx>>>(d_fr, lst, b0, d_updmap + updmap_used, 2, 0, 0, 0, 0, 1, 0);
                   updmap_used += fm.size();
                   ++launches;
                } else if (nf > 0) return SSIDS_ERROR_ALLOCATION;

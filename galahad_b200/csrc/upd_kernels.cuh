@@ -33,6 +33,16 @@ constexpr int ULDA = UTM + 4, ULDB = UTN + 4;
 constexpr int USTAGE = UBK * (ULDA + ULDB);                       // doubles
 constexpr int SMEM = UNST * USTAGE * 8 + 2 * UNST * 8 + 64;      // bytes
 constexpr int THREADS = 288;
+// The launches on a front's critical path (a block's strip, the next group's columns of a deferred update) are a few
+// dozen 128 x 128 tiles: one tile per CTA at the rate of ONE SM (18 us per 128 pivots).  They take 64 x 64 tiles instead
+// (kt_upd3<64>): four times the CTAs, two per SM.
+constexpr int STM = 64;
+template <int TM> struct Shape {
+   static constexpr int TN = TM, LDA = TM + 4, LDB = TM + 4;
+   static constexpr int STAGE = UBK * (LDA + LDB);
+   static constexpr int SMEM = UNST * STAGE * 8 + 2 * UNST * 8 + 64;
+   static constexpr int RI = TM / 16, CJ = TM / 32;     // 8 x 8 MMA tiles per warp: rows, columns (warps 2 x 4)
+};
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
@@ -100,9 +110,12 @@ __host__ __device__ __forceinline__ long long tiles_upto(int ncols, int ntr) {  
 
 }  // namespace upd3
 
-__global__ void __launch_bounds__(upd3::THREADS, 1) k_upd3(FrontDev* fr, const int* list, int slot0, const int* __restrict__ map,
-                                                          int kind, int par, int tag, int sa, int sb, int sc, int z) {
+template <int TM>
+__global__ void __launch_bounds__(upd3::THREADS, TM == 128 ? 1 : 2) kt_upd3(FrontDev* fr, const int* list, int slot0, const int* __restrict__ map,
+                                                                          int kind, int par, int tag, int sa, int sb, int sc, int z) {
    using namespace upd3;
+   using SH = Shape<TM>;
+   constexpr int UTM = TM, UTN = TM, ULDA = SH::LDA, ULDB = SH::LDB, USTAGE = SH::STAGE, RI = SH::RI, CJ = SH::CJ;
    pdl_enter();
    const int fq = map[3 * blockIdx.x], part = map[3 * blockIdx.x + 1], nparts = map[3 * blockIdx.x + 2];
    const FrontDev& f = fr[list ? list[fq] : slot0 + fq];
@@ -113,9 +126,15 @@ __global__ void __launch_bounds__(upd3::THREADS, 1) k_upd3(FrontDev* fr, const i
    if (kind == 0) {
       ka = f.urec[par][0]; kb = ka + f.urec[par][1]; ca = kb; cb = f.urec[par][2]; gse = cb;
       if (f.urec[par][1] <= 0) return;
-   } else if (kind == 1) {
+   } else if (kind == 1 || kind == 3) {
       if (f.brec[par][4] != tag) return;              // this group never reached the front (or it stalled before)
       ka = f.brec[par][0]; kb = f.brec[par][1]; ca = f.brec[par][2]; cb = m; gse = f.brec[par][3];
+      if (kind == 3) {
+         // GSTRIP: the part of the group's update the next group's blocks wait for -- the 128-wide tile columns (BULK's
+         // numbering) that hold the columns up to gse; BULK launches with sa == -2 start behind them
+         const int org128 = ca & ~1;
+         cb = min(m, org128 + (max(gse, ca) - org128 + upd3::UTN - 1) / upd3::UTN * upd3::UTN);
+      }
    } else {
       if (!f.pend[3]) return;
       ka = f.pend[0]; kb = f.pend[1]; ca = f.pend[2]; cb = m; gse = m;
@@ -129,7 +148,7 @@ __global__ void __launch_bounds__(upd3::THREADS, 1) k_upd3(FrontDev* fr, const i
    if (kind == 1) {
       const int ngs = (int)tiles_upto((max(gse, ca) - org + UTN - 1) / UTN, ntr);
       const int bound0 = min(T, max(ngs, (int)(((long long)T * z + 255) >> 8)));
-      if (sa < 0) hi = bound0;
+      if (sa < 0) { hi = bound0; if (sa == -2) lo = min(ngs, bound0); }
       else {
          const long long R = T - bound0;
          lo = bound0 + (int)(R * sa / sc);
@@ -175,8 +194,8 @@ __global__ void __launch_bounds__(upd3::THREADS, 1) k_upd3(FrontDev* fr, const i
          if (tl + 1 < my_tiles) {
             // its C tile towards L2: 128 columns x 8 lines of 128 B
             const int nrb = org + nti * UTM, ncb = org + ntj * UTN;
-            for (int q = lane; q < UTN * 8; q += 32) {
-               const int c = ncb + (q >> 3), r = nrb + (q & 7) * 16;
+            for (int q = lane; q < UTN * (UTM / 16); q += 32) {
+               const int c = ncb + q / (UTM / 16), r = nrb + (q % (UTM / 16)) * 16;
                if (c < cb && r < m && r + 15 >= c) {
                   const double* pp = (c < fn) ? (Lp + (size_t)c * ldl + r) : (Cp + (size_t)(c - fn) * ldc + (r - fn));
                   asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
@@ -215,7 +234,7 @@ __global__ void __launch_bounds__(upd3::THREADS, 1) k_upd3(FrontDev* fr, const i
       return;
    }
 
-   // ------------------------------------------------------------------- consumers: 2 x 4 warps, warp tile 64 x 32
+   // ------------------------------------------------------------------- consumers: 2 x 4 warps, warp tile TM/2 x TN/4
    const int wr = warp & 1, wc = warp >> 1, g = lane >> 2, t4 = lane & 3;
    const unsigned long long pol_stream = policy_evict_first();
    int it = 0;
@@ -225,32 +244,32 @@ __global__ void __launch_bounds__(upd3::THREADS, 1) k_upd3(FrontDev* fr, const i
       const int rb = org + ti * UTM, cbase = org + tj * UTN;
       // accumulators hold the transposed tile: acc[i][j][h] = C(r0 + 8 i + h, c0 + 8 j), so that a thread's pair is two
       // consecutive rows of one column (16-byte accesses)
-      const int r0 = rb + wr * 64 + 2 * t4, c0 = cbase + wc * 32 + g;
-      const int wrow = rb + wr * 64, wcol = cbase + wc * 32;
+      const int r0 = rb + wr * (UTM / 2) + 2 * t4, c0 = cbase + wc * (UTN / 4) + g;
+      const int wrow = rb + wr * (UTM / 2), wcol = cbase + wc * (UTN / 4);
       // nothing to compute for a warp whose part lies strictly above the diagonal or outside the region
-      const bool idle = wrow + 63 < wcol || wrow >= m || wcol >= cb || wcol + 31 < ca;
+      const bool idle = wrow + UTM / 2 - 1 < wcol || wrow >= m || wcol >= cb || wcol + UTN / 4 - 1 < ca;
       const bool interior = ti > tj && rb + UTM <= m && cbase + UTN <= cb && cbase >= ca;
-      double acc[8][4][2];
+      double acc[RI][CJ][2];
       if (!idle) {
          if (interior) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < CJ; ++j) {
                const int c = c0 + j * 8;
                const double* colp = (c < fn) ? (Lp + (size_t)c * ldl + r0) : (Cp + (size_t)(c - fn) * ldc + (r0 - fn));
 #pragma unroll
-               for (int i = 0; i < 8; ++i) {
+               for (int i = 0; i < RI; ++i) {
                   const double2 v = ld_c2(colp + i * 8, pol_stream);
                   acc[i][j][0] = v.x; acc[i][j][1] = v.y;
                }
             }
          } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < CJ; ++j) {
                const int c = c0 + j * 8;
                const bool cv = c < cb && c >= ca;
                const double* colp = (c < fn) ? (Lp + (size_t)c * ldl) : (Cp + (size_t)(c - fn) * ldc - fn);
 #pragma unroll
-               for (int i = 0; i < 8; ++i)
+               for (int i = 0; i < RI; ++i)
 #pragma unroll
                   for (int h = 0; h < 2; ++h) {
                      const int r = r0 + i * 8 + h;
@@ -264,42 +283,42 @@ __global__ void __launch_bounds__(upd3::THREADS, 1) k_upd3(FrontDev* fr, const i
          const unsigned ph = (unsigned)(it / UNST) & 1u;
          mbar_wait(full + s, ph);
          if (!idle) {
-            const double* as = smem + s * USTAGE + wr * 64 + g + t4 * ULDA;
-            const double* bs = smem + s * USTAGE + UBK * ULDA + wc * 32 + g + t4 * ULDB;
+            const double* as = smem + s * USTAGE + wr * (UTM / 2) + g + t4 * ULDA;
+            const double* bs = smem + s * USTAGE + UBK * ULDA + wc * (UTN / 4) + g + t4 * ULDB;
             const int nk4 = (min(UBK, kc - ch * UBK) + 3) >> 2;
             if (nk4 == UBK / 4) {
-               double af[2][8], bf[2][4];
+               double af[2][RI], bf[2][CJ];
 #pragma unroll
-               for (int i = 0; i < 8; ++i) af[0][i] = as[i * 8];
+               for (int i = 0; i < RI; ++i) af[0][i] = as[i * 8];
 #pragma unroll
-               for (int j = 0; j < 4; ++j) bf[0][j] = bs[j * 8];
+               for (int j = 0; j < CJ; ++j) bf[0][j] = bs[j * 8];
 #pragma unroll
                for (int ks = 0; ks < UBK / 4; ++ks) {
                   const int cur = ks & 1, nxt = cur ^ 1;
                   if (ks + 1 < UBK / 4) {
 #pragma unroll
-                     for (int i = 0; i < 8; ++i) af[nxt][i] = as[(ks + 1) * 4 * ULDA + i * 8];
+                     for (int i = 0; i < RI; ++i) af[nxt][i] = as[(ks + 1) * 4 * ULDA + i * 8];
 #pragma unroll
-                     for (int j = 0; j < 4; ++j) bf[nxt][j] = bs[(ks + 1) * 4 * ULDB + j * 8];
+                     for (int j = 0; j < CJ; ++j) bf[nxt][j] = bs[(ks + 1) * 4 * ULDB + j * 8];
                   }
 #pragma unroll
-                  for (int i = 0; i < 8; ++i)
+                  for (int i = 0; i < RI; ++i)
 #pragma unroll
-                     for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], -bf[cur][j], af[cur][i]);
+                     for (int j = 0; j < CJ; ++j) dmma(acc[i][j][0], acc[i][j][1], -bf[cur][j], af[cur][i]);
                }
             } else {
                // short last chunk of the pivot range
 #pragma unroll 1
                for (int ks = 0; ks < nk4; ++ks) {
-                  double af[8], bf[4];
+                  double af[RI], bf[CJ];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) af[i] = as[ks * 4 * ULDA + i * 8];
+                  for (int i = 0; i < RI; ++i) af[i] = as[ks * 4 * ULDA + i * 8];
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) bf[j] = -bs[ks * 4 * ULDB + j * 8];
+                  for (int j = 0; j < CJ; ++j) bf[j] = -bs[ks * 4 * ULDB + j * 8];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i)
+                  for (int i = 0; i < RI; ++i)
 #pragma unroll
-                     for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+                     for (int j = 0; j < CJ; ++j) dmma(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
                }
             }
          }
@@ -309,20 +328,20 @@ __global__ void __launch_bounds__(upd3::THREADS, 1) k_upd3(FrontDev* fr, const i
       if (!idle) {
          if (interior) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < CJ; ++j) {
                const int c = c0 + j * 8;
                double* colp = (c < fn) ? (Lp + (size_t)c * ldl + r0) : (Cp + (size_t)(c - fn) * ldc + (r0 - fn));
 #pragma unroll
-               for (int i = 0; i < 8; ++i) st_c2(colp + i * 8, acc[i][j][0], acc[i][j][1], pol_stream);
+               for (int i = 0; i < RI; ++i) st_c2(colp + i * 8, acc[i][j][0], acc[i][j][1], pol_stream);
             }
          } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < CJ; ++j) {
                const int c = c0 + j * 8;
                if (c >= cb || c < ca) continue;
                double* colp = (c < fn) ? (Lp + (size_t)c * ldl) : (Cp + (size_t)(c - fn) * ldc - fn);
 #pragma unroll
-               for (int i = 0; i < 8; ++i)
+               for (int i = 0; i < RI; ++i)
 #pragma unroll
                   for (int h = 0; h < 2; ++h) {
                      const int r = r0 + i * 8 + h;
