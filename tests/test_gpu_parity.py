@@ -396,3 +396,62 @@ def test_reanalyse_on_a_live_handle():
     assert not s.akeep.value
     s.L.b200ldlt_free_fkeep(C.byref(s.fkeep))                # ... its fkeep afterwards
     assert not s.fkeep.value
+
+
+def _nodes(prob, posdef=False):
+    s, flag = gpu_factor(prob, posdef)
+    nn = s.numeric_tree()["nnodes"]
+    return s, flag, [s.node(i) for i in range(nn)]
+
+
+@pytest.mark.parametrize("case", ["lap7_16", "kkt7_12_hard", "qpband_20000", "rand_indef", "dense_kkt_64", "dense_zdiag_40"])
+def test_small_fronts_in_one_launch(monkeypatch, case):
+    """k_front (fronts of at most 64 candidate columns assembled, factorised and their contribution block formed by one
+    CTA, front_kernels.cuh) against the general path (B200LDLT_FRONT=0) on the same matrix: same inertia, delays and
+    pivot counts; fronts of at most 32 columns whose subtree has no wider front are equal to the bit (same operations in
+    the same order); the rest agree to rounding; fronts with a failed pivot are rolled back and refactorised by the
+    general path's retry rounds (rand_indef, dense_*: delays and 2x2 pivots)."""
+    prob = {"lap7_16": lambda: P.laplace_problem(16), "kkt7_12_hard": lambda: P.kkt_grid_problem(12, dlo=1e-10),
+            "qpband_20000": lambda: P.qpband_problem(20000), "rand_indef": lambda: P.random_sym_problem(2000, 0.004, "indef", seed=5),
+            "dense_kkt_64": lambda: P.dense_front_problem(64, "kkt")[1], "dense_zdiag_40": lambda: P.dense_front_problem(40, "zdiag")[1]}[case]()
+    monkeypatch.setenv("B200LDLT_FRONT", "0")
+    s0, f0, n0 = _nodes(prob)
+    monkeypatch.setenv("B200LDLT_FRONT", "1")
+    s1, f1, n1 = _nodes(prob)
+    assert f0 == f1 and f1 >= 0
+    assert (s0.inform.num_neg, s0.inform.num_delay, s0.inform.num_two) == (s1.inform.num_neg, s1.inform.num_delay, s1.inform.num_two)
+    if prob.get("inertia") is not None:
+        assert s1.inform.num_neg == prob["inertia"][1]
+    assert s1.inform.reserved[0] < s0.inform.reserved[0] or case.startswith("dense") or case == "rand_indef"   # fewer launches
+    nbit = 0
+    for a, b in zip(n0, n1):
+        assert (a["m"], a["n"], a["nelim"]) == (b["m"], b["n"], b["nelim"])
+        assert np.array_equal(a["perm"], b["perm"])
+        if np.array_equal(a["L"], b["L"]) and np.array_equal(a["d"], b["d"]):
+            nbit += 1
+        else:
+            scale = max(1.0, float(np.abs(a["L"]).max()))
+            assert np.abs(a["L"] - b["L"]).max() <= 1e-9 * scale
+    if case == "lap7_16":
+        assert nbit >= len(n0) // 2          # the chains of 32-column fronts at the bottom of the tree
+    xs, b = rhs_for(prob)
+    f, x0 = s0.solve(b)
+    f, x1 = s1.solve(b)
+    assert P.backward_error(prob, x1, b) <= max(1e-14, 10 * P.backward_error(prob, x0, b))
+
+
+def test_c4_qpband_full_size_properties():
+    """BASELINE configs[3] at full size (QPBAND, N = 10^6: 45 330 fronts of at most 49 rows, all through k_front):
+    inertia (N, N/2, 0) exact, no delays, backward error, and a refactorisation with new barrier diagonals on the same
+    handle (the interior-point loop's pattern)."""
+    prob = P.qpband_problem(1000000)
+    s, flag = gpu_factor(prob)
+    assert flag == 0 and s.inform.num_neg == prob["inertia"][1] and s.inform.num_delay == 0
+    xs, b = rhs_for(prob)
+    f, x = s.solve(b)
+    assert f == 0 and P.backward_error(prob, x, b) <= 1e-14
+    prob2 = P.qpband_problem(1000000, it=7)
+    assert s.factor(prob2["val"]) == 0 and s.inform.num_neg == prob2["inertia"][1]
+    xs, b2 = rhs_for(prob2)
+    f, x2 = s.solve(b2)
+    assert f == 0 and P.backward_error(prob2, x2, b2) <= 1e-14
