@@ -1050,7 +1050,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    if (phase <= 1) { fac.reset(); dar.reset(); par.reset(); bar.reset(); }
    for (int s = 0; s < nn; ++s) {
       active[s] = phase == 0 ? 1 : ((owner[s] == my_rank && part_kind[s] == phase - 1) ? 1 : 0);
-      if (phase <= 1) { hfr[s] = FrontDev(); }
+      // phase 0 overwrites every record at its level (children before parents); the staged phases need the fronts of
+      // other ranks and later stages empty
+      if (phase == 1) { hfr[s] = FrontDev(); }
    }
 
    CU(cudaEventRecord(ev0, st));
@@ -1191,6 +1193,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             f.ibuf = (int*)(f.dbuf + 2 * (size_t)PB * f.wc + 2 * PB + 2 + (size_t)NB * f.wc);
          }
       }
+      const auto lvl_t1 = std::chrono::steady_clock::now();
       memcpy(pin_fr + s0, hfr.data() + s0, sizeof(FrontDev) * ns);
       CU(cudaMemcpyAsync(d_fr + s0, pin_fr + s0, sizeof(FrontDev) * ns, cudaMemcpyHostToDevice, st));
       {
@@ -1697,7 +1700,9 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          }
          return 0;
       };
+      const auto lvl_t2 = std::chrono::steady_clock::now();
       if (collect()) { cuda_err = (int)cudaGetLastError(); stats.cuda_error = cuda_err; return stats.flag = SSIDS_ERROR_CUDA_UNKNOWN; }
+      const auto lvl_t3 = std::chrono::steady_clock::now();
       if (flag < 0) break;
       for (int round = 0; round < 1000; ++round) {
          tpp_list.clear();
@@ -1753,8 +1758,10 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
          tl_ev.clear(); tl_name.clear();
       }
       if (lvl_times)
-         fprintf(stderr, "[b200ldlt] level %d fronts %d launches %lld wall %.3f ms\n", l, ns, (long long)(launches - lvl_l0),
-                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - lvl_t0).count());
+         fprintf(stderr, "[b200ldlt] level %d fronts %d launches %lld wall %.3f ms  (host: sizes %.3f, enqueue %.3f, wait %.3f)\n", l, ns,
+                 (long long)(launches - lvl_l0), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - lvl_t0).count(),
+                 std::chrono::duration<double, std::milli>(lvl_t1 - lvl_t0).count(), std::chrono::duration<double, std::milli>(lvl_t2 - lvl_t1).count(),
+                 std::chrono::duration<double, std::milli>(lvl_t3 - lvl_t2).count());
    }
    if (flag >= 0) {
       CU(cudaMemsetAsync(d_counters, 0, sizeof(int) * 8, st));
