@@ -436,7 +436,7 @@ __global__ void k_stats(const FrontDev* fr, int nslots, int* counters) {
 #include "solve_kernels.cuh"
 
 static inline size_t step_smem_fwd(int kbc) { return (size_t)(kbc * (kbc + 1) + kbc + 256) * 8; }
-static inline size_t chain_smem() { return (size_t)(KB * (KB + 1) + KB + 2 * KB + 32) * 8; }
+static inline size_t chain_smem() { return (size_t)(KB * (KB + 1) + KB + 2 * KB + 32 + 2 * KB + 4 * 32 * ILD + 32) * 8; }
 static inline int step_grid_y(int rows, int rc, int slots, int fronts) {
    return std::max(1, std::min((rows + rc - 1) / rc, slots / std::max(1, fronts)));
 }
@@ -813,6 +813,8 @@ class Numeric {
    std::vector<int> roles_fwd_n, roles_bwd_n;
    bool use_fused = !(getenv("B200LDLT_FUSED") && atoi(getenv("B200LDLT_FUSED")) == 0);
    bool use_chain = !(getenv("B200LDLT_CHAIN") && atoi(getenv("B200LDLT_CHAIN")) == 0);
+   // chain kernels: 32 x 32 diagonal sub-triangles through explicit inverses formed while a role waits (solve_kernels.cuh)
+   bool use_solve_inv = !(getenv("B200LDLT_SOLVE_INV") && atoi(getenv("B200LDLT_SOLVE_INV")) == 0);
    int* d_ticket = nullptr;         // per slot: arrival counter of the backward step's CTAs (left at zero by the last one)
    int* d_slist = nullptr;
    std::vector<int> slist, lvl_steps, lvl_maxm, lvl_maxne;
@@ -1970,7 +1972,7 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
       ++nlaunch;
       if (roles_fwd_n[l] > 0) {
          k_fwd_chain<<<roles_fwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_fwd_off[l], roles_fwd_n[l], d_chain_counter + 2 * l, d_xw_off,
-                                                               d_xw, d_cy, d_xp, posdef ? 1 : 0, kind, d_chain_err);
+                                                               d_xw, d_cy, d_xp, posdef ? 1 : 0, kind, d_chain_err, use_solve_inv ? 1 : 0);
          ++nlaunch;
          continue;      // the owners stored their pivots themselves
       }
@@ -2008,7 +2010,7 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
       }
       if (roles_bwd_n[l] > 0) {
          k_bwd_chain<<<roles_bwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_bwd_off[l], roles_bwd_n[l], d_chain_counter + 2 * l + 1, d_xw_off,
-                                                               d_xw, d_cy, d_xp, kind, d_chain_err);
+                                                               d_xw, d_cy, d_xp, kind, d_chain_err, use_solve_inv ? 1 : 0);
          ++nlaunch;
          continue;
       }

@@ -157,6 +157,128 @@ __device__ __forceinline__ void smem_solve_lower_t(const double* S, int sld, int
    }
 }
 
+// ---- chain kernels: the 32 x 32 diagonal sub-triangles through explicit inverses.  A chain role stages its triangle long
+// before the block it depends on is published, so it inverts the sub-triangles while it waits (warp w: sub-triangle w,
+// lane c: column c of the inverse by forward substitution on e_c); the solve on the chain is then four 32 x 32
+// matrix-vector products instead of 128 dependent substitution steps.  A sub-triangle whose inverse has an entry above
+// INV_MAX in modulus keeps the substitution (flag 0): the inverse is only used where it is as harmless as the
+// substitution itself (multipliers of well-conditioned blocks); results stay bit-reproducible run to run.
+constexpr int ILD = 33;
+constexpr double INV_MAX = 8.0;
+__device__ __forceinline__ void smem_invert_subtriangles(const double* S, int sld, int kb, double* Inv, int* iflag) {
+   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   if (w < 4 && 32 * w < kb) {
+      const int s0 = 32 * w, sb = min(32, kb - s0);
+      double z[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) z[i] = (i == lane) ? 1.0 : 0.0;
+      const double* T = S + s0 * sld + s0;
+#pragma unroll
+      for (int k = 0; k < 31; ++k) {
+         const double zk = z[k];
+         const double* col = T + k * sld;
+#pragma unroll
+         for (int i = k + 1; i < 32; ++i) z[i] -= zk * ((i < sb && k < sb) ? col[i] : 0.0);
+      }
+      double mx = 0.0;
+      double* dst = Inv + w * 32 * ILD + lane;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { dst[i * ILD] = z[i]; mx = fmax(mx, fabs(z[i])); }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      if (lane == 0) iflag[w] = (mx <= INV_MAX) ? 1 : 0;
+   }
+}
+
+// smem_solve_lower with the sub-triangles through their inverses where iflag allows
+__device__ __forceinline__ void smem_solve_lower_inv(const double* S, int sld, int kb, double* xs, const double* Inv, const int* iflag) {
+   const int lane = threadIdx.x & 31;
+   for (int s0 = 0; s0 < kb; s0 += 32) {
+      const int sb = min(32, kb - s0);
+      if (threadIdx.x < 32) {
+         if (iflag[s0 >> 5]) {
+            const double* Ir = Inv + (s0 >> 5) * 32 * ILD + lane * ILD;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+               a0 += Ir[j] * xs[s0 + j]; a1 += Ir[j + 1] * xs[s0 + j + 1]; a2 += Ir[j + 2] * xs[s0 + j + 2]; a3 += Ir[j + 3] * xs[s0 + j + 3];
+            }
+            __syncwarp();
+            if (lane < sb) xs[s0 + lane] = (a0 + a1) + (a2 + a3);
+         } else {
+            double lrow[32];
+            const double* Sb = S + s0 * sld + s0 + lane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) lrow[j] = (j < lane && lane < sb) ? Sb[j * sld] : 0.0;
+            double xi = lane < sb ? xs[s0 + lane] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+               const double yj = __shfl_sync(0xffffffffu, xi, j);
+               xi -= lrow[j] * yj;
+            }
+            if (lane < sb) xs[s0 + lane] = xi;
+         }
+      }
+      __syncthreads();
+      const int r = s0 + sb + threadIdx.x;
+      if (r < kb) {
+         const double* Sr = S + s0 * sld + r;
+         double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+         for (int j = 0; j < sb; j += 2) { a0 += Sr[j * sld] * xs[s0 + j]; if (j + 1 < sb) a1 += Sr[(j + 1) * sld] * xs[s0 + j + 1]; }
+         xs[r] -= a0 + a1;
+      }
+      __syncthreads();
+   }
+}
+
+// smem_solve_lower_t with the sub-triangles through their (transposed) inverses where iflag allows
+__device__ __forceinline__ void smem_solve_lower_t_inv(const double* S, int sld, int kb, double* xs, double* dots, const double* Inv,
+                                                       const int* iflag) {
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const int nsb = (kb + 31) / 32;
+   for (int sbi = nsb - 1; sbi >= 0; --sbi) {
+      const int s0 = sbi * 32, sb = min(32, kb - s0);
+      for (int j = wid; j < sb; j += (int)(blockDim.x >> 5)) {
+         const double* col = S + (s0 + j) * sld;
+         double acc = 0.0;
+         for (int r = s0 + sb + lane; r < kb; r += 32) acc += col[r] * xs[r];
+#pragma unroll
+         for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+         if (lane == 0) dots[j] = acc;
+      }
+      __syncthreads();
+      if (threadIdx.x < 32) {
+         if (iflag[sbi]) {
+            // x_i = sum_{j >= i} inv(j, i) (b_j - dots_j): column i of the inverse, conflict-free down the rows
+            const double* Ic = Inv + sbi * 32 * ILD + lane;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+               const double v0 = j < sb ? xs[s0 + j] - dots[j] : 0.0, v1 = j + 1 < sb ? xs[s0 + j + 1] - dots[j + 1] : 0.0;
+               const double v2 = j + 2 < sb ? xs[s0 + j + 2] - dots[j + 2] : 0.0, v3 = j + 3 < sb ? xs[s0 + j + 3] - dots[j + 3] : 0.0;
+               a0 += Ic[j * ILD] * v0; a1 += Ic[(j + 1) * ILD] * v1; a2 += Ic[(j + 2) * ILD] * v2; a3 += Ic[(j + 3) * ILD] * v3;
+            }
+            __syncwarp();
+            if (lane < sb) xs[s0 + lane] = (a0 + a1) + (a2 + a3);
+         } else {
+            double lcol[32];
+            const double* Sb = S + (s0 + lane) * sld + s0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) lcol[j] = (j > lane && j < sb && lane < sb) ? Sb[j] : 0.0;
+            double v = lane < sb ? xs[s0 + lane] - dots[lane] : 0.0;
+#pragma unroll
+            for (int j = 31; j >= 0; --j) {
+               const double xj = __shfl_sync(0xffffffffu, v, j);
+               v -= lcol[j] * xj;
+            }
+            if (lane < sb) xs[s0 + lane] = v;
+         }
+      }
+      __syncthreads();
+   }
+}
+
 // Forward step for column block `step` of every front of the launch.  KBC = 32 / 64 / 128 bounds the block
 // width of the launch; a CTA covers RC = SE / KBC rows below the block, NG = 256 / RC threads per row.
 // The solved block goes to XY (the front's slice of the gather accumulators, dead by now), never back into
@@ -279,9 +401,10 @@ __device__ __forceinline__ void cy_wait(double (&buf)[N], const double* p, int s
 
 __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
                                                       unsigned long long* counter, const int64_t* __restrict__ xw_off, double* XW,
-                                                      double* CY, double* x, int posdef_scale, int kind, int* err) {
+                                                      double* CY, double* x, int posdef_scale, int kind, int* err, int use_inv) {
    constexpr int SLD = KB + 1;
    __shared__ int2 role;
+   __shared__ int iflag[4];
    if (threadIdx.x == 0) role = roles[(int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles)];
    __syncthreads();
    const int s = role.x, idx = role.y;
@@ -296,6 +419,7 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
    double* S = sm;                    // KB x SLD
    double* xs = sm + KB * SLD;        // KB
    double* red = xs + KB;             // 2 x CH
+   double* Inv = red + 2 * CH + 32;   // 4 x 32 x ILD
    double* xw = XW + xw_off[s];
    const double* cy = CY + xw_off[s];
    const size_t ldl = f.ldl;
@@ -320,6 +444,12 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
       }
    };
    if (nblk > 0) load_half(la, 0, 0);
+   if (owner && use_inv) {
+      // the sub-triangles' inverses while the blocks this role depends on are being solved elsewhere
+      cp_async_wait<0>();
+      __syncthreads();
+      smem_invert_subtriangles(S, SLD, rend - rbase, Inv, iflag);
+   }
    for (int b = 0; b < nblk; ++b) {
       load_half(lb, b, 1);
       use_half(la, b, 0);
@@ -336,7 +466,8 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
    if (g == 0) xs[i] = rv ? x0 - (red[i] + red[CH + i]) : 0.0;
    cp_async_wait<0>();
    __syncthreads();
-   smem_solve_lower(S, SLD, kb, xs);
+   if (use_inv) smem_solve_lower_inv(S, SLD, kb, xs, Inv, iflag);
+   else smem_solve_lower(S, SLD, kb, xs);
    if (threadIdx.x < kb) {
       const double v = xs[threadIdx.x];
       cy_store(CY + xw_off[s] + rbase + threadIdx.x, v);
@@ -347,9 +478,10 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
 
 __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
                                                       unsigned long long* counter, const int64_t* __restrict__ xw_off, double* XW,
-                                                      double* CY, double* x, int kind, int* err) {
+                                                      double* CY, double* x, int kind, int* err, int use_inv) {
    constexpr int SLD = KB + 1;
    __shared__ int2 role;
+   __shared__ int iflag[4];
    if (threadIdx.x == 0) role = roles[(int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles)];
    __syncthreads();
    const int s = role.x, c = role.y;
@@ -362,6 +494,7 @@ __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict
    double* S = sm;                    // KB x SLD
    double* xs = sm + KB * SLD;        // KB
    double* dots = xs + KB;            // 32 + KB
+   double* Inv = dots + 32 + KB + 2 * KB;   // 4 x 32 x ILD (behind the forward kernel's layout: one size for both)
    double* xw = XW + xw_off[s];
    const double* cy = CY + xw_off[s];
    const size_t ldl = f.ldl;
@@ -405,6 +538,11 @@ __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict
    };
    const int H = 2 * (ntail + nb - 1 - c);
    if (H > 0) load_half(va, 0);
+   if (use_inv) {
+      cp_async_wait<0>();
+      __syncthreads();
+      smem_invert_subtriangles(S, SLD, kb, Inv, iflag);
+   }
    for (int hh = 0; hh < H; hh += 2) {
       load_half(vb, hh + 1);
       use_half(va, hh);
@@ -422,7 +560,8 @@ __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict
    if (threadIdx.x < KB) xs[threadIdx.x] = threadIdx.x < kb ? x0 - dots[32 + threadIdx.x] : 0.0;
    cp_async_wait<0>();
    __syncthreads();
-   smem_solve_lower_t(S, SLD, kb, xs, dots);
+   if (use_inv) smem_solve_lower_t_inv(S, SLD, kb, xs, dots, Inv, iflag);
+   else smem_solve_lower_t(S, SLD, kb, xs, dots);
    if (threadIdx.x < kb) {
       cy_store(CY + xw_off[s] + cbase + threadIdx.x, xs[threadIdx.x]);
       x[f.perm[cbase + threadIdx.x]] = xs[threadIdx.x];
