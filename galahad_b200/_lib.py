@@ -64,7 +64,7 @@ class Inform(C.Structure):
 # every symbol include/b200ldlt.h declares (tests check the library exports each of them)
 SYMBOLS = [
     "b200ldlt_default_options", "b200ldlt_order", "b200ldlt_analyse", "b200ldlt_analyse_ptr64", "b200ldlt_factor",
-    "b200ldlt_factor_device", "b200ldlt_set_value_map", "b200ldlt_factor_mapped", "b200ldlt_set_user_matrix", "b200ldlt_solve_refined", "b200ldlt_factor_scaled", "b200ldlt_equilib_scale", "b200ldlt_set_scaling", "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_enquire_indef",
+    "b200ldlt_factor_device", "b200ldlt_set_value_map", "b200ldlt_factor_mapped", "b200ldlt_factor_changed", "b200ldlt_set_user_matrix", "b200ldlt_solve_refined", "b200ldlt_factor_scaled", "b200ldlt_equilib_scale", "b200ldlt_set_scaling", "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_enquire_indef",
     "b200ldlt_enquire_posdef", "b200ldlt_alter", "b200ldlt_free_fkeep", "b200ldlt_free",
     "b200ldlt_akeep_sizes", "b200ldlt_akeep_get", "b200ldlt_partition", "b200ldlt_part_info", "b200ldlt_map_info",
     "b200ldlt_node_info", "b200ldlt_node_copy", "b200ldlt_version", "b200ldlt_ntree_sizes", "b200ldlt_ntree_get",
@@ -99,6 +99,7 @@ def lib():
     L.b200ldlt_factor_device.argtypes = [vp, vpp, C.c_int, vp, op, fp]
     L.b200ldlt_set_value_map.argtypes = [vp, vpp, C.c_int, ip, op, fp]
     L.b200ldlt_factor_mapped.argtypes = [vp, vpp, C.c_int, C.c_int, dp, op, fp]
+    L.b200ldlt_factor_changed.argtypes = [vp, vpp, C.c_int, C.c_int, ip, dp, op, fp]
     L.b200ldlt_set_user_matrix.argtypes = [vp, vpp, C.c_int, ip, ip, op, fp]
     L.b200ldlt_factor_scaled.argtypes = [vp, vpp, C.c_int, dp, dp, op, fp]
     L.b200ldlt_equilib_scale.argtypes = [C.c_int, lp, ip, dp, dp, ip]
@@ -229,6 +230,15 @@ class Solver:
         assert user_val.size == self._map_ne
         return self.L.b200ldlt_factor_mapped(self.akeep, C.byref(self.fkeep), int(posdef), user_val.size,
                                              as_ptr(user_val, C.c_double), C.byref(self.opt), C.byref(self.inform))
+
+    def factor_changed(self, which, new_val, posdef=False):
+        """Refactorise after entries `which` (positions in the caller's list given to factor_mapped, options%array_base)
+        took the values `new_val`; everything else stays as the latest factor_mapped left it on the device."""
+        which = np.ascontiguousarray(which, dtype=np.int32)
+        new_val = np.ascontiguousarray(new_val, dtype=np.float64)
+        assert which.size == new_val.size
+        return self.L.b200ldlt_factor_changed(self.akeep, C.byref(self.fkeep), int(posdef), which.size, as_ptr(which, C.c_int),
+                                              as_ptr(new_val, C.c_double), C.byref(self.opt), C.byref(self.inform))
 
     def factor_scaled(self, val, scale=None, scaling=0, posdef=False):
         """scaling: SSIDS options%scaling (0 with `scale` = user-supplied factors, 4 = equilibration).

@@ -201,17 +201,19 @@ static int ensure_fkeep(Akeep* ak, void** fkeep, const b200ldlt_options* opt, b2
 // mapped_ne >= 0: `val` holds the caller's mapped_ne values in input order, gathered on the device through the
 // value map (b200ldlt_set_value_map)
 static int factor_common(void* akeep, void** fkeep, int posdef, const double* val, bool on_device,
-                         const b200ldlt_options* opt, b200ldlt_inform* inf, int mapped_ne = -1) {
+                         const b200ldlt_options* opt, b200ldlt_inform* inf, int mapped_ne = -1, int nchg = -1,
+                         const int* which = nullptr) {
    if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
    Akeep* ak = static_cast<Akeep*>(akeep);
    *inf = ak->inf_analyse;
    inf->time_analyse = 0;
-   if (ak->sym.n > 0 && !val) return inf->flag = SSIDS_ERROR_VAL;
+   if (ak->sym.n > 0 && !val && nchg != 0) return inf->flag = SSIDS_ERROR_VAL;
    if (int rc = ensure_fkeep(ak, fkeep, opt, inf)) return rc;
    Fkeep* fk = static_cast<Fkeep*>(*fkeep);
    FactorStats st;
-   int flag = mapped_ne >= 0 ? numeric_factor_mapped(fk->num, mapped_ne, val, to_engine(opt, posdef), st)
-                             : numeric_factor(fk->num, val, on_device, to_engine(opt, posdef), st);
+   int flag = nchg >= 0      ? numeric_factor_changed(fk->num, nchg, which, val, to_engine(opt, posdef), st)
+              : mapped_ne >= 0 ? numeric_factor_mapped(fk->num, mapped_ne, val, to_engine(opt, posdef), st)
+                               : numeric_factor(fk->num, val, on_device, to_engine(opt, posdef), st);
    inf->cuda_error = st.cuda_error;
    inf->num_delay = st.num_delay;
    inf->num_neg = st.num_neg;
@@ -312,6 +314,19 @@ int b200ldlt_factor_mapped(void* akeep, void** fkeep, int posdef, int ne, const 
                            const b200ldlt_options* opt, b200ldlt_inform* inf) {
    if (ne < 0) return SSIDS_ERROR_CALL_SEQUENCE;
    return factor_common(akeep, fkeep, posdef, user_val, false, opt, inf, ne);
+}
+
+// Refactorisation after a few of the caller's entries changed (the interior-point loop: SBLS rebuilds K with new_h = new_a = 0
+// and only the barrier terms new, sbls.f90:143-153): the values of the latest b200ldlt_factor_mapped stay resident on the
+// device, `which[i]` (positions in the caller's entry list, options%array_base) take `new_val[i]`.
+int b200ldlt_factor_changed(void* akeep, void** fkeep, int posdef, int nchg, const int* which, const double* new_val,
+                            const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   if (nchg < 0 || (nchg > 0 && (!which || !new_val)) || !opt) return SSIDS_ERROR_CALL_SEQUENCE;
+   const int base = opt->array_base ? 1 : 0;
+   if (base == 0) return factor_common(akeep, fkeep, posdef, new_val, false, opt, inf, -1, nchg, which);
+   std::vector<int> w0(which, which + nchg);
+   for (int& v : w0) v -= base;
+   return factor_common(akeep, fkeep, posdef, new_val, false, opt, inf, -1, nchg, w0.data());
 }
 
 static int solve_common(void* akeep, void* fkeep, int job, int nrhs, double* x, int ldx, bool on_device,

@@ -460,6 +460,13 @@ __global__ void k_gather_dup(double* __restrict__ val, const double* __restrict_
    val[dup_dst[t]] = acc;
 }
 
+// changed entries of the caller's values: uval[which[i]] = newval[i] (SBLS's interior-point loop changes only the barrier
+// diagonal between two factorisations: sbls.f90:143-153 new_h / new_a / new_c)
+__global__ void k_update_user_values(double* __restrict__ uval, const int* __restrict__ which, const double* __restrict__ newval, int nchg) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < nchg) uval[which[i]] = newval[i];
+}
+
 // a_ij <- s_i a_ij s_j on the values of the lower triangle (add_a_block with scaling, assemble.hxx:54-66)
 __global__ void k_scale_values(double* __restrict__ val, const int* __restrict__ rowi, const int* __restrict__ coli,
                                const double* __restrict__ scale, int64_t nz) {
@@ -842,6 +849,11 @@ class Numeric {
    int set_user_matrix(int ne, const int* row, const int* col);
    int solve_refined(double* x, int max_ref, double stop_abs, double stop_rel, int* nref, double* seconds);
    int gather_values(int ne, const double* uval);
+   int update_values(int nchg, const int* which, const double* newval);
+   int *d_chg_idx = nullptr;
+   double* d_chg_val = nullptr;
+   size_t chg_cap = 0;
+   bool uval_valid = false;       // d_uval holds the values of a complete factor_mapped call
    double *d_x = nullptr, *d_xp = nullptr, *d_xw = nullptr;
    size_t x_cap = 0, xw_cap = 0;
    int64_t xw_total = 0;
@@ -877,6 +889,7 @@ class Numeric {
       fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release(); bar.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
       cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_scale); cudaFree(d_a_rowi); cudaFree(d_a_coli); cudaFree(d_um_rptr); cudaFree(d_um_rent); cudaFree(d_um_rcol); cudaFree(d_rb); cudaFree(d_rx); cudaFree(d_rr); cudaFree(d_rnorm);
+      cudaFree(d_chg_idx); cudaFree(d_chg_val);
       cudaFree(d_part); cudaFree(d_val); cudaFree(d_uval); cudaFree(d_vm_src); cudaFree(d_vm_dst); cudaFree(d_vm_dup_dst); cudaFree(d_vm_dup_ptr); cudaFree(d_vm_dup_src); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
       if (pin_i) cudaFreeHost(pin_i);
@@ -2282,6 +2295,7 @@ int Numeric::set_value_map(int ne, const int* maps) {
    cudaFree(d_uval); cudaFree(d_vm_src); cudaFree(d_vm_dst); cudaFree(d_vm_dup_dst); cudaFree(d_vm_dup_ptr); cudaFree(d_vm_dup_src);
    d_uval = nullptr; d_vm_src = d_vm_dst = d_vm_dup_dst = d_vm_dup_ptr = d_vm_dup_src = nullptr;
    vm_ne = ne; vm_nset = (int)src.size(); vm_ndup = (int)dups.size();
+   uval_valid = false;
    CU(cudaMalloc(&d_uval, sizeof(double) * std::max(ne, 1)));
    CU(cudaMalloc(&d_vm_src, sizeof(int) * std::max<size_t>(src.size(), 1)));
    CU(cudaMalloc(&d_vm_dst, sizeof(int) * std::max<size_t>(dst.size(), 1)));
@@ -2305,10 +2319,30 @@ int Numeric::gather_values(int ne, const double* uval) {
    if (!d_uval || ne != vm_ne) return SSIDS_ERROR_CALL_SEQUENCE;
    CU(cudaSetDevice(P->device));
    const int64_t nz = P->sym->nz;
-   if (ne > 0) CU(cudaMemcpyAsync(d_uval, uval, sizeof(double) * ne, cudaMemcpyHostToDevice, st));
+   if (ne > 0 && uval) CU(cudaMemcpyAsync(d_uval, uval, sizeof(double) * ne, cudaMemcpyHostToDevice, st));
+   if (uval) uval_valid = true;
    if (nz > 0) CU(cudaMemsetAsync(d_val, 0, sizeof(double) * nz, st));
    if (vm_nset > 0) k_gather_set<<<(vm_nset + 255) / 256, 256, 0, st>>>(d_val, d_uval, d_vm_src, d_vm_dst, vm_nset);
    if (vm_ndup > 0) k_gather_dup<<<(vm_ndup + 255) / 256, 256, 0, st>>>(d_val, d_uval, d_vm_dup_dst, d_vm_dup_ptr, d_vm_dup_src, vm_ndup);
+   return 0;
+}
+
+// nchg changed entries of the caller's values (0-based positions in the caller's arrays) into the resident copy
+int Numeric::update_values(int nchg, const int* which, const double* newval) {
+   if (!d_uval || !uval_valid) return SSIDS_ERROR_CALL_SEQUENCE;       // needs a complete factor_mapped first
+   if (nchg == 0) return 0;
+   for (int i = 0; i < nchg; ++i) if (which[i] < 0 || which[i] >= vm_ne) return SSIDS_ERROR_CALL_SEQUENCE;
+   CU(cudaSetDevice(P->device));
+   if (chg_cap < (size_t)nchg) {
+      cudaFree(d_chg_idx); cudaFree(d_chg_val);
+      d_chg_idx = nullptr; d_chg_val = nullptr; chg_cap = 0;
+      CU(cudaMalloc(&d_chg_idx, sizeof(int) * nchg));
+      CU(cudaMalloc(&d_chg_val, sizeof(double) * nchg));
+      chg_cap = (size_t)nchg;
+   }
+   CU(cudaMemcpyAsync(d_chg_idx, which, sizeof(int) * nchg, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(d_chg_val, newval, sizeof(double) * nchg, cudaMemcpyHostToDevice, st));
+   k_update_user_values<<<(nchg + 255) / 256, 256, 0, st>>>(d_uval, d_chg_idx, d_chg_val, nchg);
    return 0;
 }
 
@@ -2424,6 +2458,12 @@ int numeric_set_value_map(Numeric* n, int ne, const int* maps) { return n->set_v
 int numeric_factor_mapped(Numeric* n, int ne, const double* uval, const FactorOptions& o, FactorStats& s) {
    int rc = n->gather_values(ne, uval);
    if (rc) return s.flag = rc;
+   return n->factor(n->d_val, true, o, s);
+}
+int numeric_factor_changed(Numeric* n, int nchg, const int* which, const double* newval, const FactorOptions& o, FactorStats& s) {
+   int rc = n->update_values(nchg, which, newval);
+   if (rc == 0) rc = n->gather_values(n->vm_ne, nullptr);     // from the resident values
+   if (rc) { s = FactorStats(); return s.flag = rc; }
    return n->factor(n->d_val, true, o, s);
 }
 int numeric_factor(Numeric* n, const double* val, bool on_device, const FactorOptions& o, FactorStats& s) {

@@ -46,6 +46,7 @@ int numeric_set_scaling(Numeric*, const double* scale);
 int numeric_set_user_matrix(Numeric*, int ne, const int* row, const int* col);
 int numeric_solve_refined(Numeric*, double* x, int max_ref, double stop_abs, double stop_rel, int* nref, double* seconds);
 int numeric_factor_mapped(Numeric*, int ne, const double* uval, const FactorOptions&, FactorStats&);
+int numeric_factor_changed(Numeric*, int nchg, const int* which, const double* newval, const FactorOptions&, FactorStats&);
 int numeric_factor(Numeric*, const double* val, bool val_on_device, const FactorOptions&,
                    FactorStats&);
 // x(ldx,nrhs) indexed by ORIGINAL variable; job 0..4

@@ -134,6 +134,13 @@ int b200ldlt_factor_device(void *akeep, void **fkeep, int posdef, const double *
  * entry (missing diagonals) are zero, duplicates are summed in input order. */
 int b200ldlt_set_value_map(void *akeep, void **fkeep, int ne, const int *maps, const b200ldlt_options *opt,
                            b200ldlt_inform *inf);
+/* b200ldlt_factor_changed: refactorisation after a FEW of the caller's entries changed -- the interior-point loop, where
+ * SBLS rebuilds K every iteration although only the barrier terms are new (new_h = new_a = 0, sbls.f90:143-153).  The
+ * values of the latest b200ldlt_factor_mapped stay resident on the device; entry `which[i]` of the caller's list
+ * (options%array_base) takes `new_val[i]`, then gather + factorisation run as in factor_mapped: H2D traffic is 12 bytes
+ * per changed entry.  -1 (call sequence) without a previous complete factor_mapped on this fkeep. */
+int b200ldlt_factor_changed(void *akeep, void **fkeep, int posdef, int nchg, const int *which, const double *new_val,
+                            const b200ldlt_options *opt, b200ldlt_inform *inf);
 int b200ldlt_factor_mapped(void *akeep, void **fkeep, int posdef, int ne, const double *user_val,
                            const b200ldlt_options *opt, b200ldlt_inform *inf);
 

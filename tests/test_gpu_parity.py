@@ -269,6 +269,23 @@ def test_value_gather_on_device_matches_host_gather():
     assert s2.factor_mapped(user2) >= 0
     f3, x3 = s2.solve(b)
     assert f3 == 0 and not np.array_equal(x3, x2)
+    # b200ldlt_factor_changed: only the changed entries travel (the interior-point loop); the bits of a full factor_mapped
+    which = np.nonzero(np.concatenate([is_diag, np.zeros(7, bool)]))[0].astype(np.int32)
+    user3 = user2.copy()
+    user3[which] += 0.5
+    assert s2.factor_changed(which, user3[which]) >= 0
+    f4, x4 = s2.solve(b)
+    s3 = Solver()
+    assert s3.analyse(n, ptr, row, prob["order"]) >= 0
+    assert s3.set_value_map(maps) == 0
+    assert s3.factor_changed(which, user3[which]) == -1          # no complete factor_mapped on this handle yet
+    assert s3.factor_mapped(user3) >= 0
+    f5, x5 = s3.solve(b)
+    assert f4 == 0 and f5 == 0 and np.array_equal(x4, x5)
+    assert s2.factor_changed(np.array([user.size + 3], np.int32), np.array([1.0])) == -1     # position out of range
+    assert s2.factor_changed(np.zeros(0, np.int32), np.zeros(0)) >= 0                        # nothing changed: same factors
+    f6, x6 = s2.solve(b)
+    assert np.array_equal(x6, x4)
 
 
 def test_scaled_factorisation():
