@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200ldlt.so")
-SOURCES = ["engine.cu", "analyse.cpp", "ordering.cpp", "capi.cpp", "sls_facade.cpp"]
+SOURCES = ["engine.cu", "analyse.cpp", "ordering.cpp", "scaling.cpp", "capi.cpp", "sls_facade.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-shared",

@@ -80,6 +80,14 @@ int analyse(int n, const int64_t* ptr, const int* row, const int* order, int nem
 int equilib_scale_sym(int n, const int64_t* ptr, const int* row, const double* val, double* scaling,
                       int max_iterations = 10, float tol = 1e-8f);
 
+// Matching-based scaling by the Hungarian algorithm (options%scaling = 1 of SSIDS; scaling.cpp): restatement of
+// hungarian_scale_sym, src/spral/scaling.f90:134-170 with hungarian_wrapper / hungarian_match (MC64's algorithm).  Lower
+// triangle by columns, 0-based.  Returns 0, 1 (structurally singular, scaled by Duff and Pralet's correction because
+// scale_if_singular) or -2 (structurally singular and not scale_if_singular: scaling = 1).  match_out (optional, n): the
+// matching, 1-based, negative for the completion of the singular part; matched_out: its cardinality.
+int hungarian_scale_sym(int n, const int64_t* ptr, const int* row, const double* val, double* scaling, bool scale_if_singular,
+                        int* match_out = nullptr, int* matched_out = nullptr);
+
 // Fill-reducing orderings (ordering.cpp): approximate minimum degree, and nested dissection from level structures with
 // minimum-degree leaves.  Lower triangle by columns, 0-based; order[i] = pivot position of variable i.  0 or an SSIDS flag.
 int amd_order(int n, const int64_t* ptr, const int* row, int* order);

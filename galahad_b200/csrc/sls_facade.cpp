@@ -303,15 +303,17 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
    // control%scaling (sls.f90:3558, 3766-3860, 1405-1413).  3: SLS computes symmetric infinity-norm equilibration factors
    // itself (MC77 with job 0 there, an HSL stub in a stock build) and factorises S A S: here the factors come from
    // the engine's equilibration (b200ldlt_equilib_scale, the restatement of spral/scaling.f90 inf_norm_equilib_sym --
-   // the same Ruiz iteration MC77 runs in that norm), computed from the gathered values.  1 (MC64), 2 (MC77 one-norm)
-   // and -1, -2, -3 (SSIDS's Hungarian / auction / matching-order scalings) have no implementation behind them.
+   // the same Ruiz iteration MC77 runs in that norm), computed from the gathered values.  -1: SSIDS's own matching-based
+   // scaling by the Hungarian algorithm (options%scaling = 1, sls.f90:1405-1413 -> ssids.f90:928-960), the restatement
+   // of spral/scaling.f90 hungarian_scale_sym behind b200ldlt_hungarian_scale.  1 (MC64), 2 (MC77 one-norm) and -2, -3
+   // (SSIDS's auction / matching-order scalings) have no implementation behind them.
    const int sc = d->control.scaling;
-   if (sc != 0 && sc != 3) {
+   if (sc != 0 && sc != 3 && sc != -1) {
       *status = inf.status = GALAHAD_UNAVAILABLE_OPTION;
       d->factorized = false;
       return;
    }
-   if (d->map_set && sc == 3) {
+   if (d->map_set && (sc == 3 || sc == -1)) {
       const int nz = d->ptr[n] - 1;
       std::vector<double> hv(nz, 0.0), sf(n, 1.0);
       for (int l = 0; l < d->ne; ++l) {          // the gather of sls.f90:4106-4147 on the host, for the factors only
@@ -322,7 +324,16 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
       std::vector<int> r0(nz);
       for (int i = 0; i <= n; ++i) p0[i] = d->ptr[i] - 1;
       for (int k = 0; k < nz; ++k) r0[k] = d->col[k] - 1;
-      b200ldlt_equilib_scale(n, p0.data(), r0.data(), hv.data(), sf.data(), nullptr);
+      if (sc == 3) b200ldlt_equilib_scale(n, p0.data(), r0.data(), hv.data(), sf.data(), nullptr);
+      else {
+         // the facade holds the UPPER triangle by rows = the lower triangle by columns (sls.f90:8409-8578)
+         const int hf = b200ldlt_hungarian_scale(n, p0.data(), r0.data(), hv.data(), sf.data(), nullptr, nullptr, o.action);
+         if (hf == -2) {       // structurally singular and pivot_control = 3 (action = .false.): ssids.f90:946-949
+            *status = inf.status = GALAHAD_ERROR_RESTRICTIONS;  // SSIDS_ERROR_SINGULAR (-5) through SLS_copy_inform_from_ssids
+            d->factorized = false;
+            return;
+         }
+      }
       if (b200ldlt_set_scaling(d->akeep, &d->fkeep, sf.data(), &o, &si) < 0) d->map_set = false;
       d->scale_set = d->map_set;
    } else if (d->map_set && d->scale_set) {

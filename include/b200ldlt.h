@@ -147,14 +147,21 @@ int b200ldlt_factor_mapped(void *akeep, void **fkeep, int posdef, int ne, const 
 /* Factorisation with scaling: ssids_factor's optional SCALE argument and options%scaling (ssids.f90:900-1030),
  * the option in opt->reserved[2]:  <= 0: `scale` (n factors, original variable order) is used if not NULL, else no
  * scaling;  >= 4: symmetric infinity-norm equilibration (inf_norm_equilib_sym, src/spral/scaling.f90:480-521)
- * computed from `val` and returned in `scale` if not NULL;  1..3 (Hungarian, auction, matching-order scalings): -98,
- * not implemented.  The scaled matrix S A S is factorised; solves scale on the way in (jobs 0, 1) and on the way out
+ * computed from `val` and returned in `scale` if not NULL;  1: matching-based scaling by the Hungarian algorithm
+ * (hungarian_scale_sym, src/spral/scaling.f90:134-170, MC64's algorithm; ssids.f90:928-960), computed on the host from
+ * `val`, returned in `scale` if not NULL; a structurally singular matrix is scaled all the same when options%action is
+ * set and is SSIDS_ERROR_SINGULAR (-5) otherwise;  2, 3 (auction, matching-order scalings): -98, not implemented.  The scaled matrix S A S is factorised; solves scale on the way in (jobs 0, 1) and on the way out
  * (jobs 0, 3, 4) exactly as fkeep.F90:247-310.  A later b200ldlt_factor / _factor_mapped keeps the scaling that was
  * set last; pass opt->reserved[2] = 0 and scale = NULL here to clear it.  `val` is a host pointer.
  * b200ldlt_equilib_scale: the equilibration alone (0-based lower triangle by columns). */
 int b200ldlt_factor_scaled(void *akeep, void **fkeep, int posdef, const double *val, double *scale,
                            const b200ldlt_options *opt, b200ldlt_inform *inf);
 int b200ldlt_equilib_scale(int n, const int64_t *ptr, const int *row, const double *val, double *scaling, int *iterations);
+/* b200ldlt_hungarian_scale: the Hungarian scaling alone (0-based lower triangle by columns).  match (n, may be NULL):
+ * row i is matched to column match[i] (1-based; negative: completion of a structurally singular matrix); *matched: the
+ * cardinality of the matching.  Returns 0, 1 (singular, scaled because scale_if_singular) or -2 (singular, scaling = 1). */
+int b200ldlt_hungarian_scale(int n, const int64_t *ptr, const int *row, const double *val, double *scaling, int *match,
+                             int *matched, int scale_if_singular);
 /* The scaling alone: `scale` (n factors, original variable order, host) applies to every later factorisation of this
  * fkeep and to its solves, NULL clears it.  What the SLS layer uses when it computes the factors itself
  * (data%SCALE with explicit_scaling, sls.f90:3558) and the values arrive through b200ldlt_factor_mapped. */

@@ -319,6 +319,12 @@ def test_scaled_factorisation():
     assert flag >= 0 and sc is not None and sc.min() > 0 and s.inform.num_neg == prob["inertia"][1]
     f, x4 = s.solve(b)
     assert f == 0 and P.backward_error(bad, x4, b) <= 1e-14
+    # matching-based scaling by the Hungarian algorithm (options%scaling = 1): |s_i a_ij s_j| <= 1, clean factorisation
+    flag, sc1 = s.factor_scaled(bad["val"], scaling=1)
+    assert flag >= 0 and sc1 is not None and sc1.min() > 0 and s.inform.num_neg == prob["inertia"][1]
+    assert (np.abs(bad["val"]) * sc1[row] * sc1[col]).max() <= 1.0 + 1e-12
+    f, x1 = s.solve(b)
+    assert f == 0 and P.backward_error(bad, x1, b) <= 1e-14
     flag, _ = s.factor_scaled(bad["val"], scaling=2)
     assert flag == -98
     # clearing the scaling restores the plain path

@@ -199,3 +199,32 @@ def test_iterative_refinement_on_device():
     assert st == 0 and s.information().iterative_refinements == 0
     assert np.array_equal(x1, x0)
     s.terminate()
+
+
+@pytest.mark.gpu
+def test_matching_based_scaling_through_sls():
+    """control%scaling = -1 (SSIDS's Hungarian scaling, sls.f90:1405-1413): a symmetrically mis-scaled KKT matrix (scale
+    factors over sixteen orders of magnitude) factorises with the exact inertia and solves to backward error 1e-14;
+    -2 / -3 (auction, matching-order) stay GALAHAD_unavailable_option."""
+    prob = P.kkt_grid_problem(8)
+    n = prob["n"]
+    colidx = np.repeat(np.arange(n), np.diff(prob["ptr"]))
+    rng = np.random.default_rng(5)
+    d = 10.0 ** rng.uniform(-8, 8, n)
+    val = prob["val"] * d[prob["row"]] * d[colidx]
+    bad = dict(prob, val=val)
+    s = SLS()
+    s.control.f_indexing = False
+    s.control.scaling = -1
+    assert s.analyse_matrix(n, "coordinate", val.size, prob["row"], colidx, perm=prob["order"]) == 0
+    assert s.factorize_matrix(val) == 0
+    inf = s.information()
+    assert inf.negative_eigenvalues == prob["inertia"][1] and inf.rank == n
+    b = P.full_from_lower(n, prob["ptr"], prob["row"], val) @ rng.uniform(-1, 1, n)
+    st, x = s.solve_system(b)
+    assert st == 0 and P.backward_error(bad, x, b) <= 1e-14
+    s2 = SLS()
+    s2.control.f_indexing = False
+    s2.control.scaling = -2
+    assert s2.analyse_matrix(n, "coordinate", val.size, prob["row"], colidx, perm=prob["order"]) == 0
+    assert s2.factorize_matrix(val) == -29          # GALAHAD_unavailable_option
