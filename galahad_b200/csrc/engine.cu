@@ -504,6 +504,21 @@ __global__ void k_maxabs(const double* __restrict__ v, int n, unsigned long long
    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
 }
 
+// multi-GPU: the lower triangle of a contribution block (t columns, column j rows j..t-1) to / from a packed trapezoid:
+// half the bytes of the full square over NVLink
+__global__ void k_pack_lower(double* __restrict__ dst, const double* __restrict__ C, int ldc, int t) {
+   const int j = blockIdx.x;
+   const double* col = C + (size_t)j * ldc;
+   double* out = dst + ((size_t)j * t - (size_t)j * (j - 1) / 2) - j;       // out[r] for r >= j
+   for (int r = j + threadIdx.x; r < t; r += blockDim.x) out[r] = col[r];
+}
+__global__ void k_unpack_lower(double* __restrict__ C, const double* __restrict__ src, int ldc, int t) {
+   const int j = blockIdx.x;
+   double* col = C + (size_t)j * ldc;
+   const double* in = src + ((size_t)j * t - (size_t)j * (j - 1) / 2) - j;
+   for (int r = threadIdx.x; r < ldc; r += blockDim.x) col[r] = (r >= j && r < t) ? in[r] : 0.0;
+}
+
 // multi-GPU: which pivots did this rank eliminate, and in which stage
 __global__ void k_build_masks(const FrontDev* fr, int nslots, char* mine, char* stage) {
    const int lane = threadIdx.x & 31;
@@ -2125,10 +2140,13 @@ int Numeric::set_partition(int rank, int nr) {
 
 // packed boundary front: 8 x int64 header {m, n, nelim, ldl, ldc, 0,0,0} | perm[n-nelim] (padded to 8 B)
 // | L(:, nelim:n) (ldl x (n-nelim)) | C (ldc x (m-n))
+// wire format of a boundary front (contrib_type, contrib.f90:19-33): header | pivot indices of the delayed columns | the
+// delayed columns of L | the LOWER triangle of the contribution block, packed by columns
+static inline int64_t packed_lower(int64_t t) { return t * (t + 1) / 2; }
 int64_t Numeric::contrib_bytes(int node) const {
    const FrontDev& f = hfr[P->node_slot[node]];
    const int64_t nd = f.n - f.nelim;
-   return 64 + (int64_t)align_up(nd * 4, 8) + 8 * (int64_t)f.ldl * nd + 8 * (int64_t)f.ldc * (f.m - f.n);
+   return 64 + (int64_t)align_up(nd * 4, 8) + 8 * (int64_t)f.ldl * nd + 8 * packed_lower(f.m - f.n);
 }
 
 int Numeric::contrib_pack(int node, char* dst) {
@@ -2144,7 +2162,7 @@ int Numeric::contrib_pack(int node, char* dst) {
       CU(cudaMemcpyAsync(p, f.L + (size_t)f.nelim * f.ldl, 8 * (size_t)f.ldl * nd, cudaMemcpyDeviceToDevice, st));
       p += 8 * (size_t)f.ldl * nd;
    }
-   if (f.m > f.n) CU(cudaMemcpyAsync(p, f.C, 8 * (size_t)f.ldc * (f.m - f.n), cudaMemcpyDeviceToDevice, st));
+   if (f.m > f.n) k_pack_lower<<<f.m - f.n, 256, 0, st>>>((double*)p, f.C, f.ldc, f.m - f.n);
    CU(cudaStreamSynchronize(st));
    return 0;
 }
@@ -2161,12 +2179,13 @@ int Numeric::contrib_unpack(int node, const char* src, int64_t bytes) {
    f.ndelay_in = f.m - f.nrow;
    f.done = f.gend = f.nelim;
    f.state = 3; f.part_kind = 0;
-   const int64_t nd = f.n - f.nelim;
-   const int64_t need = 64 + (int64_t)align_up(nd * 4, 8) + 8 * (int64_t)f.ldl * nd + 8 * (int64_t)f.ldc * (f.m - f.n);
-   if (need != bytes) return SSIDS_ERROR_UNKNOWN;
-   char* buf = (char*)bar.alloc((size_t)bytes);
+   const int64_t nd = f.n - f.nelim, t = f.m - f.n;
+   const int64_t head = 64 + (int64_t)align_up(nd * 4, 8) + 8 * (int64_t)f.ldl * nd;
+   if (head + 8 * packed_lower(t) != bytes) return SSIDS_ERROR_UNKNOWN;
+   // header, pivot indices and delayed columns as they travelled; the contribution block expanded to its square
+   char* buf = (char*)bar.alloc((size_t)(head + 8 * (int64_t)f.ldc * t + 16));
    if (!buf) return SSIDS_ERROR_ALLOCATION;
-   CU(cudaMemcpyAsync(buf, src, (size_t)bytes, cudaMemcpyDeviceToDevice, st));
+   CU(cudaMemcpyAsync(buf, src, (size_t)head, cudaMemcpyDeviceToDevice, st));
    char* p = buf + 64;
    f.perm = (int*)p - f.nelim;                       // only perm[nelim..n) is ever read
    f.orig = nullptr;
@@ -2174,6 +2193,7 @@ int Numeric::contrib_unpack(int node, const char* src, int64_t bytes) {
    f.L = (double*)p - (size_t)f.nelim * f.ldl;      // only columns nelim..n are ever read
    p += 8 * (size_t)f.ldl * nd;
    f.C = (double*)p;
+   if (t > 0) k_unpack_lower<<<(unsigned)t, 256, 0, st>>>(f.C, (const double*)(src + head), f.ldc, (int)t);
    hfr[s] = f;
    CU(cudaMemcpyAsync(d_fr + s, &hfr[s], sizeof(FrontDev), cudaMemcpyHostToDevice, st));
    CU(cudaStreamSynchronize(st));
