@@ -1112,6 +1112,8 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    const bool use_front = !(getenv("B200LDLT_FRONT") && atoi(getenv("B200LDLT_FRONT")) == 0);
    // the launches on a front's critical path (strips, the next group's columns of a deferred update) in 64 x 64 tiles
    const bool small_strips = !(getenv("B200LDLT_SMALL_STRIPS") && atoi(getenv("B200LDLT_SMALL_STRIPS")) == 0);
+   const int big_groups = getenv("B200LDLT_BIG_GROUPS") ? atoi(getenv("B200LDLT_BIG_GROUPS")) : 1;
+   const int big_groups_minf = getenv("B200LDLT_BIG_GROUPS_MINF") ? atoi(getenv("B200LDLT_BIG_GROUPS_MINF")) : 4;
    const int small_strip_tiles = getenv("B200LDLT_SMALL_STRIP_TILES") ? atoi(getenv("B200LDLT_SMALL_STRIP_TILES")) : 148;
    const int front_small_m = getenv("B200LDLT_FRONT_SMALLM") ? atoi(getenv("B200LDLT_FRONT_SMALLM")) : 96;
    const int upd3_min_m = getenv("B200LDLT_UPD3_MINM") ? atoi(getenv("B200LDLT_UPD3_MINM")) : 1800;
@@ -1368,6 +1370,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             tl_name.push_back(buf);
          };
          // one chunk = a contiguous slot range of one size class, processed block by block on stream sx
+         int big_split = 1;      // chunks a class of large fronts is split into (they share the SMs)
          auto run_chunk = [&](int j0, int j1, cudaStream_t sx, bool single, int sidx) -> int {
             int maxm = 0, maxn = 0;
             for (int q = j0; q < j1; ++q)
@@ -1381,7 +1384,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             // Large fronts (size class >= 3) take their trailing updates through k_upd3; with several blocks per front
             // the schedule looks ahead: the part of an update the next block needs runs on this stream, the rest in slices
             // on the chunk's second stream beside the next blocks' factorisation kernels (k_block: one CTA per front).
-            const bool big = single && cls(order[j0]) >= 3 && use_upd3 && maxm >= upd3_min_m;
+            const bool big = (single || big_split > 1) && cls(order[j0]) >= 3 && use_upd3 && maxm >= upd3_min_m;
             const bool la = big && lookahead && !o.profile && !trace && nouter >= 2;
             // blocks per trailing update of the columns behind the group (rank G * PB): C is read and written once per G blocks
             const int G = (big && nouter >= 2 && maxm >= defer_min_m) ? std::max(1, std::min(defer_g, (int)GMAX)) : 1;
@@ -1451,7 +1454,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                   }
                   // chunks that share the GPU with other streams keep to about half of the CTA slots, so that
                   // another chunk's block factorisation finds a free SM while this update runs
-                  const int64_t target = big ? (stile == 128 ? 148 : 296) : std::min<int64_t>(std::max<int64_t>(total, 1), (single ? 2 : 1) * upd_share);
+                  const int64_t target = big ? (stile == 128 ? 148 : 296) / big_split : std::min<int64_t>(std::max<int64_t>(total, 1), (single ? 2 : 1) * upd_share);
                   if (!big || G > 1) deal(na, total, std::min<int64_t>(target, std::max<int64_t>(total, 1)));
                   map_off[ob + 1] = (int)hmap.size();
                }
@@ -1473,7 +1476,7 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
                      gtiles[g] = total;
                      // the SMs of the next blocks' k_block CTAs (one per front) stay free
                      const int nkb = g + 1 < ngroups ? map_na[(g + 1) * G] : 0;
-                     const int64_t target = std::max(64, 148 - std::min(nkb, 84));
+                     const int64_t target = std::max(64, 148 - std::min(nkb, 84)) / big_split;
                      deal(na, total, std::min<int64_t>(target, std::max<int64_t>(total, 1)));
                      bmap_off[g + 1] = (int)hmap.size();
                   }
@@ -1684,6 +1687,12 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
             for (int q = i0; q < i1; ++q) if (live[order[q]]) cls_maxm = std::max(cls_maxm, hfr[order[q]].m);
             const bool cls_big = c >= 3 && use_upd3 && cls_maxm >= upd3_min_m;
             if (!o.profile && !trace && nact >= 2 && nact <= 128 && c >= 2 && !cls_big) G = std::min(nact, max_groups);
+            // several large fronts: groups on separate streams as well, each with its own look-ahead schedule
+            big_split = 1;
+            if (!o.profile && !trace && !timeline && cls_big && big_groups > 1 && nact >= big_groups_minf) {
+               G = std::min({nact, big_groups, max_groups});
+               big_split = G;
+            }
             if (G == 1) {
                int rc2 = run_chunk(i0, i1, st, true, 0);
                if (rc2) return stats.flag = rc2;
