@@ -64,7 +64,7 @@ class Inform(C.Structure):
 # every symbol include/b200ldlt.h declares (tests check the library exports each of them)
 SYMBOLS = [
     "b200ldlt_default_options", "b200ldlt_order", "b200ldlt_analyse", "b200ldlt_analyse_ptr64", "b200ldlt_factor",
-    "b200ldlt_factor_device", "b200ldlt_set_value_map", "b200ldlt_factor_mapped", "b200ldlt_factor_changed", "b200ldlt_set_user_matrix", "b200ldlt_solve_refined", "b200ldlt_factor_scaled", "b200ldlt_equilib_scale", "b200ldlt_hungarian_scale", "b200ldlt_set_scaling", "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_enquire_indef",
+    "b200ldlt_factor_device", "b200ldlt_set_value_map", "b200ldlt_factor_mapped", "b200ldlt_factor_changed", "b200ldlt_set_user_matrix", "b200ldlt_solve_refined", "b200ldlt_factor_scaled", "b200ldlt_equilib_scale", "b200ldlt_hungarian_scale", "b200ldlt_auction_scale", "b200ldlt_set_scaling", "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_enquire_indef",
     "b200ldlt_enquire_posdef", "b200ldlt_alter", "b200ldlt_free_fkeep", "b200ldlt_free",
     "b200ldlt_akeep_sizes", "b200ldlt_akeep_get", "b200ldlt_partition", "b200ldlt_part_info", "b200ldlt_map_info",
     "b200ldlt_node_info", "b200ldlt_node_copy", "b200ldlt_version", "b200ldlt_ntree_sizes", "b200ldlt_ntree_get",
@@ -104,6 +104,7 @@ def lib():
     L.b200ldlt_factor_scaled.argtypes = [vp, vpp, C.c_int, dp, dp, op, fp]
     L.b200ldlt_equilib_scale.argtypes = [C.c_int, lp, ip, dp, dp, ip]
     L.b200ldlt_hungarian_scale.argtypes = [C.c_int, lp, ip, dp, dp, ip, ip, C.c_int]
+    L.b200ldlt_auction_scale.argtypes = [C.c_int, lp, ip, dp, dp, ip, ip, ip]
     L.b200ldlt_set_scaling.argtypes = [vp, vpp, dp, op, fp]
     L.b200ldlt_solve_refined.argtypes = [vp, vp, dp, C.c_int, C.c_double, C.c_double, ip, op, fp]
     L.b200ldlt_solve.argtypes = [vp, vp, C.c_int, C.c_int, dp, C.c_int, op, fp]
@@ -249,7 +250,7 @@ class Solver:
         sc = None
         if scale is not None:
             sc = np.array(scale, dtype=np.float64)
-        elif scaling >= 4 or scaling == 1:
+        elif scaling >= 4 or scaling in (1, 2):
             sc = np.zeros(max(self.n, 1))
         flag = self.L.b200ldlt_factor_scaled(self.akeep, C.byref(self.fkeep), int(posdef), as_ptr(val, C.c_double),
                                              None if sc is None else as_ptr(sc, C.c_double), C.byref(self.opt), C.byref(self.inform))

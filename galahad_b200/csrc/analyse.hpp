@@ -88,6 +88,12 @@ int equilib_scale_sym(int n, const int64_t* ptr, const int* row, const double* v
 int hungarian_scale_sym(int n, const int64_t* ptr, const int* row, const double* val, double* scaling, bool scale_if_singular,
                         int* match_out = nullptr, int* matched_out = nullptr);
 
+// Matching-based scaling by SPRAL's auction algorithm (options%scaling = 2): restatement of auction_scale_sym,
+// src/spral/scaling.f90:269-309 with auction_match / auction_match_core and the reference's default auction_options.
+// match_out (optional, n): row i is matched to column match[i] (1-based, 0 = unmatched).  Returns 0.
+int auction_scale_sym(int n, const int64_t* ptr, const int* row, const double* val, double* scaling, int* match_out = nullptr,
+                      int* matched_out = nullptr, int* iterations_out = nullptr);
+
 // Fill-reducing orderings (ordering.cpp): approximate minimum degree, and nested dissection from level structures with
 // minimum-degree leaves.  Lower triangle by columns, 0-based; order[i] = pivot position of variable i.  0 or an SSIDS flag.
 int amd_order(int n, const int64_t* ptr, const int* row, int* order);

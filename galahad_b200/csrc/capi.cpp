@@ -259,13 +259,18 @@ int b200ldlt_hungarian_scale(int n, const int64_t* ptr, const int* row, const do
    if (n < 0 || !ptr || !scaling || (n > 0 && ptr[n] > 0 && (!row || !val))) return SSIDS_ERROR_CALL_SEQUENCE;
    return hungarian_scale_sym(n, ptr, row, val, scaling, scale_if_singular != 0, match, matched);
 }
+int b200ldlt_auction_scale(int n, const int64_t* ptr, const int* row, const double* val, double* scaling, int* match,
+                           int* matched, int* iterations) {
+   if (n < 0 || !ptr || !scaling || (n > 0 && ptr[n] > 0 && (!row || !val))) return SSIDS_ERROR_CALL_SEQUENCE;
+   return auction_scale_sym(n, ptr, row, val, scaling, match, matched, iterations);
+}
 int b200ldlt_factor_scaled(void* akeep, void** fkeep, int posdef, const double* val, double* scale,
                            const b200ldlt_options* opt, b200ldlt_inform* inf) {
    if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
    Akeep* ak = static_cast<Akeep*>(akeep);
    *inf = ak->inf_analyse;
    const int sc = opt->reserved[2];
-   if (sc >= 2 && sc <= 3) return inf->flag = SSIDS_ERROR_UNIMPLEMENTED;   // auction / matching-order scalings
+   if (sc == 3) return inf->flag = SSIDS_ERROR_UNIMPLEMENTED;   // scaling from a matching-based ORDER (needs match_order_metis)
    if (ak->sym.n > 0 && !val) return inf->flag = SSIDS_ERROR_VAL;
    if (int rc = ensure_fkeep(ak, fkeep, opt, inf)) return rc;
    Fkeep* fk = static_cast<Fkeep*>(*fkeep);
@@ -275,6 +280,11 @@ int b200ldlt_factor_scaled(void* akeep, void** fkeep, int posdef, const double* 
       std::vector<double> s(std::max(n, 1));
       const int hf = hungarian_scale_sym(n, ak->sym.ptr.data(), ak->sym.row.data(), val, s.data(), opt->action != 0);
       if (hf == -2) return inf->flag = SSIDS_ERROR_SINGULAR;      // structurally singular and action = .false.
+      if (scale) std::copy(s.begin(), s.begin() + n, scale);
+      rc = numeric_set_scaling(fk->num, s.data());
+   } else if (sc == 2) {                // auction algorithm (ssids.f90:962-990), returned in `scale` if given
+      std::vector<double> s(std::max(n, 1));
+      auction_scale_sym(n, ak->sym.ptr.data(), ak->sym.row.data(), val, s.data());
       if (scale) std::copy(s.begin(), s.begin() + n, scale);
       rc = numeric_set_scaling(fk->num, s.data());
    } else if (sc >= 4) {                // norm equilibration, computed here, returned in `scale` if given

@@ -1,5 +1,6 @@
-// Matching-based scaling on the host (SSIDS options%scaling = 1, SLS scaling = -1): the Hungarian algorithm of MC64 as
-// SPRAL carries it.  Restatement of
+// Matching-based scalings on the host (SSIDS options%scaling = 1 / 2, SLS scaling = -1 / -2): the Hungarian algorithm of
+// MC64 as SPRAL carries it, and SPRAL's auction algorithm.  Restatement of
+//    auction_scale_sym / auction_match / auction_match_core   src/spral/scaling.f90:269-309, 1504-1609, 1351-1489
 //    hungarian_scale_sym / hungarian_wrapper        src/spral/scaling.f90:134-170, 597-801
 //    hungarian_init_heurisitic / hungarian_match    src/spral/scaling.f90:810-929, 938-1194
 //    heap_update / heap_pop / heap_delete           src/spral/scaling.f90:1203-1325
@@ -437,6 +438,130 @@ int hungarian_scale_sym(int n, const int64_t* ptr0, const int* row0, const doubl
    if (match_out) for (int i = 1; i <= n; ++i) match_out[i - 1] = match[i];
    if (matched_out) *matched_out = matched2;
    return flag;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Auction algorithm (options%scaling = 2): each unmatched column bids for its best row, prices (row duals) rise by the
+// margin over the second best plus eps; an approximate maximum-product matching in a bounded number of sweeps.
+// Options are the reference's defaults (auction_options, scaling.f90:33-38): max_iterations 30000, max_unchanged
+// (10, 100, 100), min_proportion (0.90, 0, 0), eps_initial 0.01 -- the last two are default REALs there, hence the floats.
+namespace {
+
+void auction_match_core(int m, int n, const std::vector<i64>& ptr, const std::vector<int>& row, const std::vector<double>& val,
+                        std::vector<int>& match, std::vector<double>& dualu, std::vector<double>& dualv, int& iterations,
+                        int& unmatchable) {
+   const int max_iterations = 30000;
+   const int max_unchanged[3] = {10, 100, 100};
+   const float min_proportion[3] = {0.90f, 0.0f, 0.0f};
+   const float eps_initial = 0.01f;
+   const double NEGH = -RINF;
+   std::vector<int> owner(m + 1, 0), next(n + 1, 0);
+   match.assign(n + 1, 0);
+   dualu.assign(m + 1, 0.0);
+   const int minmn = std::min(m, n);
+   int unmatched = minmn, prev = -1, nunchanged = 0, tail = n;
+   for (int i = 1; i <= n; ++i) next[i] = i;
+   double eps = (double)eps_initial;
+   unmatchable = 0;
+   int itr = 1;
+   for (; itr <= max_iterations; ++itr) {
+      if (unmatched == 0) break;
+      if (unmatched != prev) nunchanged = 0;
+      prev = unmatched;
+      nunchanged += 1;
+      const float frac = (float)(minmn - unmatched) / (float)minmn;
+      bool stop = false;
+      for (int k = 0; k < 3; ++k) if (nunchanged >= max_unchanged[k] && frac >= min_proportion[k]) stop = true;
+      if (stop) break;
+      eps = std::min(1.0, eps + 1.0 / (n + 1));
+      int insert = 0;
+      for (int cptr = 1; cptr <= tail; ++cptr) {
+         const int col = next[cptr];
+         if (match[col] != 0) continue;
+         if (ptr[col] == ptr[col + 1]) continue;
+         i64 j = ptr[col];
+         int bestr = row[j];
+         double bestu = val[j] - dualu[bestr], bestv = NEGH;
+         for (j = ptr[col] + 1; j < ptr[col + 1]; ++j) {
+            const double u = val[j] - dualu[row[j]];
+            if (u > bestu) { bestv = bestu; bestr = row[j]; bestu = u; }
+            else if (u > bestv) bestv = u;
+         }
+         if (bestv == NEGH) bestv = 0.0;
+         if (bestu > 0) {
+            dualu[bestr] = dualu[bestr] + bestu - bestv + eps;
+            dualv[col] = bestv - eps;
+            match[col] = bestr;
+            unmatched -= 1;
+            const int k = owner[bestr];
+            owner[bestr] = col;
+            if (k != 0) { match[k] = 0; unmatched += 1; insert += 1; next[insert] = k; }
+         } else {
+            match[col] = -1;
+            unmatched -= 1;
+            unmatchable += 1;
+         }
+      }
+      tail = insert;
+   }
+   iterations = itr - 1;
+   for (int j = 1; j <= n; ++j) if (match[j] == -1) match[j] = 0;
+}
+
+}  // namespace
+
+int auction_scale_sym(int n, const int64_t* ptr0, const int* row0, const double* val0, double* scaling, int* match_out,
+                      int* matched_out, int* iterations_out) {
+   const i64 nz = n > 0 ? ptr0[n] : 0;
+   std::vector<i64> ptr2(n + 2, 0);
+   std::vector<int> row2(2 * nz + 2, 0);
+   std::vector<double> val2(2 * nz + 2, 0.0);
+   i64 k = 1;
+   for (int i = 1; i <= n; ++i) {
+      ptr2[i] = k;
+      for (i64 j = ptr0[i - 1]; j < ptr0[i]; ++j) {
+         if (val0[j] == 0.0) continue;
+         row2[k] = row0[j] + 1;
+         val2[k] = std::log(std::fabs(val0[j]));
+         k += 1;
+      }
+   }
+   ptr2[n + 1] = k;
+   half_to_full(n, row2, ptr2, val2);
+   std::vector<double> cmax(n + 1, 0.0);
+   for (int i = 1; i <= n; ++i) {
+      if (ptr2[i + 1] <= ptr2[i]) { cmax[i] = 0.0; continue; }
+      double colmax = -RINF;
+      for (i64 j = ptr2[i]; j < ptr2[i + 1]; ++j) colmax = std::max(colmax, val2[j]);
+      cmax[i] = colmax;
+      for (i64 j = ptr2[i]; j < ptr2[i + 1]; ++j) val2[j] = colmax - val2[j];
+   }
+   const i64 nz2 = ptr2[n + 1] - 1;
+   double maxentry = -RINF;
+   for (i64 j = 1; j <= nz2; ++j) maxentry = std::max(maxentry, val2[j]);
+   maxentry = 2 * maxentry + 1;            // prefers matchings of high cardinality
+   for (i64 j = 1; j <= nz2; ++j) val2[j] = maxentry - val2[j];
+   std::vector<double> rscaling, cscaling(n + 1, 0.0);
+   for (int i = 1; i <= n; ++i) cscaling[i] = -cmax[i];
+   std::vector<int> cmatch;
+   int iterations = 0, unmatchable = 0;
+   auction_match_core(n, n, ptr2, row2, val2, cmatch, rscaling, cscaling, iterations, unmatchable);
+   int matched = 0;
+   for (int j = 1; j <= n; ++j) if (cmatch[j] != 0) ++matched;
+   for (int i = 1; i <= n; ++i) { rscaling[i] = -rscaling[i] + maxentry; cscaling[i] = -cscaling[i] - cmax[i]; }
+   if (match_out) {
+      for (int i = 0; i < n; ++i) match_out[i] = 0;
+      for (int j = 1; j <= n; ++j) if (cmatch[j] != 0) match_out[cmatch[j] - 1] = j;
+   }
+   // match_postproc, square
+   double rsum = 0.0, csum = 0.0;
+   for (int i = 1; i <= n; ++i) rsum += rscaling[i];
+   for (int i = 1; i <= n; ++i) csum += cscaling[i];
+   const double adjust = n > 0 ? (rsum / n - csum / n) / 2 : 0.0;
+   for (int i = 1; i <= n; ++i) scaling[i - 1] = std::exp(((rscaling[i] - adjust) + (cscaling[i] + adjust)) / 2);
+   if (matched_out) *matched_out = matched;
+   if (iterations_out) *iterations_out = iterations;
+   return 0;
 }
 
 }  // namespace b200

@@ -305,15 +305,16 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
    // the engine's equilibration (b200ldlt_equilib_scale, the restatement of spral/scaling.f90 inf_norm_equilib_sym --
    // the same Ruiz iteration MC77 runs in that norm), computed from the gathered values.  -1: SSIDS's own matching-based
    // scaling by the Hungarian algorithm (options%scaling = 1, sls.f90:1405-1413 -> ssids.f90:928-960), the restatement
-   // of spral/scaling.f90 hungarian_scale_sym behind b200ldlt_hungarian_scale.  1 (MC64), 2 (MC77 one-norm) and -2, -3
-   // (SSIDS's auction / matching-order scalings) have no implementation behind them.
+   // of spral/scaling.f90 hungarian_scale_sym behind b200ldlt_hungarian_scale; -2: SSIDS's auction scaling
+   // (options%scaling = 2, auction_scale_sym).  1 (MC64), 2 (MC77 one-norm) and -3 (scaling from SSIDS's matching-based
+   // order) have no implementation behind them.
    const int sc = d->control.scaling;
-   if (sc != 0 && sc != 3 && sc != -1) {
+   if (sc != 0 && sc != 3 && sc != -1 && sc != -2) {
       *status = inf.status = GALAHAD_UNAVAILABLE_OPTION;
       d->factorized = false;
       return;
    }
-   if (d->map_set && (sc == 3 || sc == -1)) {
+   if (d->map_set && (sc == 3 || sc == -1 || sc == -2)) {
       const int nz = d->ptr[n] - 1;
       std::vector<double> hv(nz, 0.0), sf(n, 1.0);
       for (int l = 0; l < d->ne; ++l) {          // the gather of sls.f90:4106-4147 on the host, for the factors only
@@ -325,6 +326,7 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
       for (int i = 0; i <= n; ++i) p0[i] = d->ptr[i] - 1;
       for (int k = 0; k < nz; ++k) r0[k] = d->col[k] - 1;
       if (sc == 3) b200ldlt_equilib_scale(n, p0.data(), r0.data(), hv.data(), sf.data(), nullptr);
+      else if (sc == -2) b200ldlt_auction_scale(n, p0.data(), r0.data(), hv.data(), sf.data(), nullptr, nullptr, nullptr);
       else {
          // the facade holds the UPPER triangle by rows = the lower triangle by columns (sls.f90:8409-8578)
          const int hf = b200ldlt_hungarian_scale(n, p0.data(), r0.data(), hv.data(), sf.data(), nullptr, nullptr, o.action);

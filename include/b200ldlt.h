@@ -150,7 +150,9 @@ int b200ldlt_factor_mapped(void *akeep, void **fkeep, int posdef, int ne, const 
  * computed from `val` and returned in `scale` if not NULL;  1: matching-based scaling by the Hungarian algorithm
  * (hungarian_scale_sym, src/spral/scaling.f90:134-170, MC64's algorithm; ssids.f90:928-960), computed on the host from
  * `val`, returned in `scale` if not NULL; a structurally singular matrix is scaled all the same when options%action is
- * set and is SSIDS_ERROR_SINGULAR (-5) otherwise;  2, 3 (auction, matching-order scalings): -98, not implemented.  The scaled matrix S A S is factorised; solves scale on the way in (jobs 0, 1) and on the way out
+ * set and is SSIDS_ERROR_SINGULAR (-5) otherwise;  2: matching-based scaling by SPRAL's auction algorithm
+ * (auction_scale_sym, scaling.f90:269-309, default auction_options; ssids.f90:962-990);  3 (scaling from a matching-based
+ * order, needs match_order_metis): -98, not implemented.  The scaled matrix S A S is factorised; solves scale on the way in (jobs 0, 1) and on the way out
  * (jobs 0, 3, 4) exactly as fkeep.F90:247-310.  A later b200ldlt_factor / _factor_mapped keeps the scaling that was
  * set last; pass opt->reserved[2] = 0 and scale = NULL here to clear it.  `val` is a host pointer.
  * b200ldlt_equilib_scale: the equilibration alone (0-based lower triangle by columns). */
@@ -162,6 +164,9 @@ int b200ldlt_equilib_scale(int n, const int64_t *ptr, const int *row, const doub
  * cardinality of the matching.  Returns 0, 1 (singular, scaled because scale_if_singular) or -2 (singular, scaling = 1). */
 int b200ldlt_hungarian_scale(int n, const int64_t *ptr, const int *row, const double *val, double *scaling, int *match,
                              int *matched, int scale_if_singular);
+/* b200ldlt_auction_scale: the auction scaling alone; match[i] = column matched to row i (1-based, 0 = unmatched). */
+int b200ldlt_auction_scale(int n, const int64_t *ptr, const int *row, const double *val, double *scaling, int *match,
+                           int *matched, int *iterations);
 /* The scaling alone: `scale` (n factors, original variable order, host) applies to every later factorisation of this
  * fkeep and to its solves, NULL clears it.  What the SLS layer uses when it computes the factors itself
  * (data%SCALE with explicit_scaling, sls.f90:3558) and the values arrive through b200ldlt_factor_mapped. */

@@ -2,6 +2,7 @@
 
     hungarian_scale_sym / hungarian_wrapper      src/spral/scaling.f90:134-170, 597-801
     hungarian_init_heurisitic / hungarian_match  src/spral/scaling.f90:810-929, 938-1194
+    auction_scale_sym / auction_match / _core    src/spral/scaling.f90:269-309, 1504-1609, 1351-1489
     heap_update / heap_pop / heap_delete         src/spral/scaling.f90:1203-1325
     match_postproc (square case)                 src/spral/scaling.f90:1611-1640
     half_to_full                                 src/spral/matrix_util.f90:3167-3302
@@ -497,3 +498,139 @@ def hungarian_scale_sym(n, ptr0, row0, val0, scale_if_singular=True):
     else:
         scaling = [math.exp((rscaling[i] + rscaling[i]) / 2) for i in range(1, n + 1)]
     return flag, scaling, match[1:n + 1], matched2
+
+
+def _f32(x):
+    import struct
+    return struct.unpack("f", struct.pack("f", x))[0]
+
+
+def auction_match_core(m, n, ptr, row, val, dualv, max_iterations=30000, max_unchanged=(10, 100, 100),
+                       min_proportion=(0.90, 0.0, 0.0), eps_initial=0.01):
+    """scaling.f90:1351-1489.  dualv: in/out (1-based list).  Returns (match, dualu, iterations, unmatchable)."""
+    NEGH = -RINF
+    owner = [0] * (m + 1)
+    nxt = list(range(n + 1))
+    match = [0] * (n + 1)
+    dualu = [0.0] * (m + 1)
+    minmn = min(m, n)
+    unmatched = minmn
+    prev = -1
+    nunchanged = 0
+    tail = n
+    eps = _f32(eps_initial)                      # a default REAL option assigned to a double
+    props = [_f32(p) for p in min_proportion]
+    unmatchable = 0
+    itr = 1
+    while itr <= max_iterations:
+        if unmatched == 0:
+            break
+        if unmatched != prev:
+            nunchanged = 0
+        prev = unmatched
+        nunchanged += 1
+        frac = _f32(_f32(float(minmn - unmatched)) / _f32(float(minmn)))     # single-precision quotient
+        if any(nunchanged >= max_unchanged[k] and frac >= props[k] for k in range(3)):
+            break
+        eps = min(1.0, eps + 1.0 / (n + 1))
+        insert = 0
+        for cptr in range(1, tail + 1):
+            col = nxt[cptr]
+            if match[col] != 0:
+                continue
+            if ptr[col] == ptr[col + 1]:
+                continue
+            j = ptr[col]
+            bestr = row[j]
+            bestu = val[j] - dualu[bestr]
+            bestv = NEGH
+            for j in range(ptr[col] + 1, ptr[col + 1]):
+                u = val[j] - dualu[row[j]]
+                if u > bestu:
+                    bestv = bestu
+                    bestr = row[j]
+                    bestu = u
+                elif u > bestv:
+                    bestv = u
+            if bestv == NEGH:
+                bestv = 0.0
+            if bestu > 0:
+                dualu[bestr] = dualu[bestr] + bestu - bestv + eps
+                dualv[col] = bestv - eps
+                match[col] = bestr
+                unmatched -= 1
+                k = owner[bestr]
+                owner[bestr] = col
+                if k != 0:
+                    match[k] = 0
+                    unmatched += 1
+                    insert += 1
+                    nxt[insert] = k
+            else:
+                match[col] = -1
+                unmatched -= 1
+                unmatchable += 1
+        tail = insert
+        itr += 1
+    iterations = itr - 1
+    for j in range(1, n + 1):
+        if match[j] == -1:
+            match[j] = 0
+    return match, dualu, iterations, unmatchable
+
+
+def auction_scale_sym(n, ptr0, row0, val0):
+    """auction_scale_sym + auction_match(expand = .true.) on a 0-based lower-CSC matrix with the reference's default
+    options.  Returns (scaling, match (1-based: row i matched to column match[i], 0 unmatched), matched, iterations)."""
+    ptr = [0] + [int(p) + 1 for p in ptr0]
+    row = [0] + [int(r) + 1 for r in row0]
+    val = [0.0] + [float(v) for v in val0]
+    ne = 2 * (ptr[n + 1] - 1)
+    ptr2 = [0] * (n + 2)
+    row2 = [0] * (ne + 1)
+    val2 = [0.0] * (ne + 1)
+    klong = 1
+    for i in range(1, n + 1):
+        ptr2[i] = klong
+        for jlong in range(ptr[i], ptr[i + 1]):
+            if val[jlong] == 0.0:
+                continue
+            row2[klong] = row[jlong]
+            val2[klong] = math.log(abs(val[jlong]))
+            klong += 1
+    ptr2[n + 1] = klong
+    half_to_full(n, row2, ptr2, val2)
+    cmax = [0.0] * (n + 1)
+    for i in range(1, n + 1):
+        if ptr2[i + 1] <= ptr2[i]:
+            cmax[i] = 0.0
+            continue
+        colmax = max(val2[ptr2[i]:ptr2[i + 1]])
+        cmax[i] = colmax
+        for k in range(ptr2[i], ptr2[i + 1]):
+            val2[k] = colmax - val2[k]
+    nz2 = ptr2[n + 1] - 1
+    maxentry = max(val2[1:nz2 + 1]) if nz2 > 0 else -RINF
+    maxentry = 2 * maxentry + 1
+    for k in range(1, nz2 + 1):
+        val2[k] = maxentry - val2[k]
+    cscaling = [0.0] + [-cmax[i] for i in range(1, n + 1)]
+    cmatch, rscaling, iterations, unmatchable = auction_match_core(n, n, ptr2, row2, val2, cscaling)
+    matched = sum(1 for j in range(1, n + 1) if cmatch[j] != 0)
+    for i in range(1, n + 1):
+        rscaling[i] = -rscaling[i] + maxentry
+        cscaling[i] = -cscaling[i] - cmax[i]
+    match = [0] * (n + 1)
+    for i in range(1, n + 1):
+        if cmatch[i] == 0:
+            continue
+        match[cmatch[i]] = i
+    rsum = 0.0
+    csum = 0.0
+    for i in range(1, n + 1):
+        rsum += rscaling[i]
+    for i in range(1, n + 1):
+        csum += cscaling[i]
+    adjust = (rsum / n - csum / n) / 2
+    scaling = [math.exp(((rscaling[i] - adjust) + (cscaling[i] + adjust)) / 2) for i in range(1, n + 1)]
+    return scaling, match[1:n + 1], matched, iterations

@@ -292,7 +292,8 @@ def test_scaled_factorisation():
     """ssids_factor's SCALE argument and options%scaling = 4 (ssids.f90:900-1030, fkeep.F90:247-310): a
     symmetrically mis-scaled KKT matrix factorised with user-supplied factors that undo the damage gives the
     pivot sequence statistics of the well-scaled matrix and solves the mis-scaled system; equilibration gives
-    a clean factorisation too; partial solves compose; scalings 1-3 are reported as not implemented."""
+    a clean factorisation too, as do the matching-based scalings 1 (Hungarian) and 2 (auction); partial solves compose;
+    scaling 3 (from a matching-based order) is reported as not implemented."""
     rng = np.random.default_rng(21)
     prob = P.kkt_grid_problem(8)
     n, ptr, row = prob["n"], prob["ptr"], prob["row"]
@@ -325,7 +326,13 @@ def test_scaled_factorisation():
     assert (np.abs(bad["val"]) * sc1[row] * sc1[col]).max() <= 1.0 + 1e-12
     f, x1 = s.solve(b)
     assert f == 0 and P.backward_error(bad, x1, b) <= 1e-14
-    flag, _ = s.factor_scaled(bad["val"], scaling=2)
+    # auction algorithm (options%scaling = 2): an approximate matching, entries of the scaled matrix bounded by e
+    flag, sc2 = s.factor_scaled(bad["val"], scaling=2)
+    assert flag >= 0 and sc2 is not None and sc2.min() > 0 and s.inform.num_neg == prob["inertia"][1]
+    assert (np.abs(bad["val"]) * sc2[row] * sc2[col]).max() <= np.e * (1 + 1e-12)
+    f, x2 = s.solve(b)
+    assert f == 0 and P.backward_error(bad, x2, b) <= 1e-14
+    flag, _ = s.factor_scaled(bad["val"], scaling=3)
     assert flag == -98
     # clearing the scaling restores the plain path
     flag, _ = s.factor_scaled(prob["val"], scaling=0)

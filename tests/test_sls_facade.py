@@ -205,7 +205,7 @@ def test_iterative_refinement_on_device():
 def test_matching_based_scaling_through_sls():
     """control%scaling = -1 (SSIDS's Hungarian scaling, sls.f90:1405-1413): a symmetrically mis-scaled KKT matrix (scale
     factors over sixteen orders of magnitude) factorises with the exact inertia and solves to backward error 1e-14;
-    -2 / -3 (auction, matching-order) stay GALAHAD_unavailable_option."""
+    -2 (auction) likewise; -3 (matching-order) stays GALAHAD_unavailable_option."""
     prob = P.kkt_grid_problem(8)
     n = prob["n"]
     colidx = np.repeat(np.arange(n), np.diff(prob["ptr"]))
@@ -223,8 +223,13 @@ def test_matching_based_scaling_through_sls():
     b = P.full_from_lower(n, prob["ptr"], prob["row"], val) @ rng.uniform(-1, 1, n)
     st, x = s.solve_system(b)
     assert st == 0 and P.backward_error(bad, x, b) <= 1e-14
-    s2 = SLS()
-    s2.control.f_indexing = False
-    s2.control.scaling = -2
-    assert s2.analyse_matrix(n, "coordinate", val.size, prob["row"], colidx, perm=prob["order"]) == 0
-    assert s2.factorize_matrix(val) == -29          # GALAHAD_unavailable_option
+    for sc, want in ((-2, 0), (-3, -29)):           # auction scaling; matching-order scaling: GALAHAD_unavailable_option
+        s2 = SLS()
+        s2.control.f_indexing = False
+        s2.control.scaling = sc
+        assert s2.analyse_matrix(n, "coordinate", val.size, prob["row"], colidx, perm=prob["order"]) == 0
+        assert s2.factorize_matrix(val) == want
+        if want == 0:
+            assert s2.information().negative_eigenvalues == prob["inertia"][1]
+            st, x2 = s2.solve_system(b)
+            assert st == 0 and P.backward_error(bad, x2, b) <= 1e-14
