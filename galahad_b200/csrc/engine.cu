@@ -1068,12 +1068,31 @@ int Numeric::factor(const double* val, bool on_device, const FactorOptions& o, F
    prm.posdef = posdef;
    { const char* tr = getenv("B200LDLT_TRACE"); prm.debug = tr && atoi(tr) >= 2; }
    double mult = std::max(o.multiplier, 1.0);
-   fac.reserve((size_t)(P->est_factor_doubles * mult) * 8 + (1 << 20));
+   // first reservations of the arenas (they grow on demand afterwards): the whole tree on one GPU, this rank's fronts
+   // only under a partition -- C5 on 8 GPUs ran rank 0 out of memory when every rank reserved the whole tree's 81 GB
+   int64_t estF = P->est_factor_doubles, estC[2] = {P->est_c_doubles[0], P->est_c_doubles[1]}, estW = P->est_ws_doubles;
+   if (phase >= 1 && nranks > 1) {
+      estF = 0; estC[0] = estC[1] = 0; estW = 0;
+      for (int l = 0; l < P->nlevels; ++l) {
+         int64_t c = 0, ws = 0;
+         for (int s = P->lvl_ptr[l]; s < P->lvl_ptr[l + 1]; ++s) {
+            if (owner[s] != my_rank) continue;
+            const SlotStatic& ss = P->hss[s];
+            const int64_t ldl = align_up(ss.nrow, 2), cm = ss.nrow - ss.ncol;
+            estF += ldl * ss.ncol + 32;
+            if (!boundary[s]) c += align_up(cm, 2) * cm + 32;
+            ws += (int64_t)front_ws_doubles(align_up(ss.nrow, 2), ss.ncol);
+         }
+         estC[l & 1] = std::max(estC[l & 1], c);
+         estW = std::max(estW, ws);
+      }
+   }
+   fac.reserve((size_t)(estF * mult) * 8 + (1 << 20));
    dar.reserve((size_t)(2.0 * sym.n * mult) * 8 + 64 * (size_t)nn + (1 << 16));
    par.reserve((size_t)(2.0 * sym.n * mult) * 4 + 512 * (size_t)nn + (1 << 16));
-   car[0].reserve((size_t)(P->est_c_doubles[0] * mult) * 8 + (1 << 16));
-   car[1].reserve((size_t)(P->est_c_doubles[1] * mult) * 8 + (1 << 16));
-   war.reserve((size_t)(P->est_ws_doubles * mult) * 8 + (1 << 16));
+   car[0].reserve((size_t)(estC[0] * mult) * 8 + (1 << 16));
+   car[1].reserve((size_t)(estC[1] * mult) * 8 + (1 << 16));
+   war.reserve((size_t)(estW * mult) * 8 + (1 << 16));
    if (phase <= 1) CU(cudaMemsetAsync(d_fr, 0, sizeof(FrontDev) * std::max(nn, 1), st));
    // phase 0: everything (single GPU).  phase k >= 1: this rank's fronts of stage k-1 of the proportional
    // mapping, on top of what the earlier phases and the imports left in place.
