@@ -591,19 +591,30 @@ void proportional_mapping(Symbolic& sym, int ndev) {
       std::stable_sort(kids.begin(), kids.end(), [&](int a, int b) { return flops[a] > flops[b]; });
       int64_t W = 0;
       for (int c : kids) W += flops[c];
-      // devices per child: rounded share, the largest child first; leftovers go to the largest children
+      // devices per child: the children whose share is at least half a device are candidates (largest first, at most
+      // g of them, the largest always); every candidate gets one device, the others go one at a time to the candidate
+      // with the largest flops per device -- the allocation that minimises the largest load per device.  (Rounded
+      // shares cascade badly down an unbalanced tree: the 27-point 160^3 grid on 8 devices left one device with 18 %
+      // of the flops and two with 2 % each.)
       std::vector<int> alloc(kids.size(), 0);
-      int left = it.g;
-      for (size_t i = 0; i < kids.size() && left > 0; ++i) {
-         const double share = W > 0 ? (double)it.g * (double)flops[kids[i]] / (double)W : 0.0;
-         int a = (int)(share + 0.5);
-         if (i == 0) a = std::max(a, 1);
-         a = std::min(a, left);
-         alloc[i] = a;
-         left -= a;
+      {
+         size_t ncand = 0;
+         for (size_t i = 0; i < kids.size() && (int)ncand < it.g; ++i) {
+            const double share = W > 0 ? (double)it.g * (double)flops[kids[i]] / (double)W : 0.0;
+            if (i == 0 || share >= 0.5) { alloc[i] = 1; ++ncand; } else break;      // kids are sorted: the rest is smaller
+         }
+         int left = ncand > 0 ? it.g - (int)ncand : 0;      // a leaf of the tree with several devices keeps them idle
+         while (left > 0) {
+            size_t best = 0;
+            double worst = -1.0;
+            for (size_t i = 0; i < ncand; ++i) {
+               const double load = (double)flops[kids[i]] / (double)alloc[i];
+               if (load > worst) { worst = load; best = i; }
+            }
+            ++alloc[best];
+            --left;
+         }
       }
-      for (size_t i = 0; i < kids.size() && left > 0; ++i)
-         if (alloc[i] > 0) { ++alloc[i]; --left; }
       int r = it.r0;
       for (size_t i = 0; i < kids.size(); ++i) {
          if (alloc[i] > 0) { stack.push_back({kids[i], r, alloc[i]}); r += alloc[i]; }
