@@ -63,7 +63,8 @@ class Inform(C.Structure):
 
 # every symbol include/b200ldlt.h declares (tests check the library exports each of them)
 SYMBOLS = [
-    "b200ldlt_default_options", "b200ldlt_order", "b200ldlt_analyse", "b200ldlt_analyse_ptr64", "b200ldlt_factor",
+    "b200ldlt_default_options", "b200ldlt_order", "b200ldlt_analyse", "b200ldlt_analyse_ptr64",
+    "b200ldlt_analyse_matched", "b200ldlt_match_order", "b200ldlt_factor",
     "b200ldlt_factor_device", "b200ldlt_set_value_map", "b200ldlt_factor_mapped", "b200ldlt_factor_changed", "b200ldlt_set_user_matrix", "b200ldlt_solve_refined", "b200ldlt_factor_scaled", "b200ldlt_equilib_scale", "b200ldlt_hungarian_scale", "b200ldlt_auction_scale", "b200ldlt_set_scaling", "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_enquire_indef",
     "b200ldlt_enquire_posdef", "b200ldlt_alter", "b200ldlt_free_fkeep", "b200ldlt_free",
     "b200ldlt_akeep_sizes", "b200ldlt_akeep_get", "b200ldlt_partition", "b200ldlt_part_info", "b200ldlt_map_info",
@@ -95,6 +96,8 @@ def lib():
     L.b200ldlt_order.argtypes = [C.c_int, lp, ip, C.c_int, ip, op]
     L.b200ldlt_analyse.argtypes = [vpp, C.c_int, ip, ip, ip, op, fp]
     L.b200ldlt_analyse_ptr64.argtypes = [vpp, C.c_int, lp, ip, ip, op, fp]
+    L.b200ldlt_analyse_matched.argtypes = [vpp, C.c_int, lp, ip, dp, ip, op, fp]
+    L.b200ldlt_match_order.argtypes = [C.c_int, lp, ip, dp, C.c_int, ip, dp, ip, ip, lp, ip]
     L.b200ldlt_factor.argtypes = [vp, vpp, C.c_int, dp, op, fp]
     L.b200ldlt_factor_device.argtypes = [vp, vpp, C.c_int, vp, op, fp]
     L.b200ldlt_set_value_map.argtypes = [vp, vpp, C.c_int, ip, op, fp]
@@ -184,6 +187,17 @@ class Solver:
                                              C.byref(self.opt), C.byref(self.inform))
         return flag
 
+    def analyse_matched(self, n, ptr, row, val):
+        """SSIDS options%ordering = 2: matching-based order from the values; its scaling is kept for factor_scaled(scaling=3)."""
+        ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        row = np.ascontiguousarray(row, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        self.order = np.zeros(max(int(n), 1), np.int32)[:int(n)]
+        self.n = int(n)
+        return self.L.b200ldlt_analyse_matched(C.byref(self.akeep), self.n, as_ptr(ptr, C.c_int64), as_ptr(row, C.c_int),
+                                               as_ptr(val, C.c_double), as_ptr(self.order, C.c_int),
+                                               C.byref(self.opt), C.byref(self.inform))
+
     def symbolic(self, base=0):
         nn, nr, nl = C.c_int(), C.c_int64(), C.c_int64()
         self.L.b200ldlt_akeep_sizes(self.akeep, C.byref(nn), C.byref(nr), C.byref(nl))
@@ -250,7 +264,7 @@ class Solver:
         sc = None
         if scale is not None:
             sc = np.array(scale, dtype=np.float64)
-        elif scaling >= 4 or scaling in (1, 2):
+        elif scaling >= 1:
             sc = np.zeros(max(self.n, 1))
         flag = self.L.b200ldlt_factor_scaled(self.akeep, C.byref(self.fkeep), int(posdef), as_ptr(val, C.c_double),
                                              None if sc is None else as_ptr(sc, C.c_double), C.byref(self.opt), C.byref(self.inform))

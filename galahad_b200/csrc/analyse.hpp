@@ -94,6 +94,15 @@ int hungarian_scale_sym(int n, const int64_t* ptr, const int* row, const double*
 int auction_scale_sym(int n, const int64_t* ptr, const int* row, const double* val, double* scaling, int* match_out = nullptr,
                       int* matched_out = nullptr, int* iterations_out = nullptr);
 
+// Matching-based ordering (options%ordering = 2 of SSIDS; scaling.cpp): restatement of match_order_metis,
+// src/spral/match_order.f90:135-208, with this library's orderings on the compressed graph (kind 1: minimum degree, else
+// nested dissection) where the reference calls METIS.  order[i] = pivot position of variable i (0-based), scale (n, may be
+// NULL) = the matching's scaling, pairs (n, may be NULL) = the matching split into singletons and pairs (1-based partner,
+// -1 singleton, -2 unmatched), cptr / crow (may be NULL) = lower triangle of the compressed pattern, 0-based.  Returns 0,
+// 1 (structurally singular) or an SSIDS error flag.
+int match_order(int n, const int64_t* ptr, const int* row, const double* val, int kind, int* order, double* scale,
+                int* pairs = nullptr, std::vector<int64_t>* cptr = nullptr, std::vector<int>* crow = nullptr);
+
 // Fill-reducing orderings (ordering.cpp): approximate minimum degree, and nested dissection from level structures with
 // minimum-degree leaves.  Lower triangle by columns, 0-based; order[i] = pivot position of variable i.  0 or an SSIDS flag.
 int amd_order(int n, const int64_t* ptr, const int* row, int* order);

@@ -31,6 +31,7 @@ struct Akeep {
    b200ldlt_inform inf_analyse;
    // partition
    std::vector<int64_t> part_flops;
+   std::vector<double> match_scale;   // scaling saved by a matching-based order (akeep%scaling, ssids.f90:283-286)
 };
 
 struct Fkeep {
@@ -264,13 +265,69 @@ int b200ldlt_auction_scale(int n, const int64_t* ptr, const int* row, const doub
    if (n < 0 || !ptr || !scaling || (n > 0 && ptr[n] > 0 && (!row || !val))) return SSIDS_ERROR_CALL_SEQUENCE;
    return auction_scale_sym(n, ptr, row, val, scaling, match, matched, iterations);
 }
+// 0-based entry points of the matching-based order alone (tests, callers with their own analyse)
+int b200ldlt_match_order(int n, const int64_t* ptr, const int* row, const double* val, int kind, int* order, double* scale,
+                         int* pairs, int* ncomp, int64_t* cptr, int* crow) {
+   if (n < 0 || !ptr || !order || (n > 0 && ptr[n] > 0 && (!row || !val))) return SSIDS_ERROR_CALL_SEQUENCE;
+   try {
+      std::vector<int64_t> cp;
+      std::vector<int> cr;
+      const int flag = match_order(n, ptr, row, val, kind, order, scale, pairs, &cp, &cr);
+      if (flag < 0) return flag;
+      if (ncomp) *ncomp = cp.empty() ? 0 : (int)cp.size() - 1;
+      if (cptr) std::copy(cp.begin(), cp.end(), cptr);
+      if (crow) std::copy(cr.begin(), cr.end(), crow);
+      return flag;
+   } catch (const std::bad_alloc&) {
+      return SSIDS_ERROR_ALLOCATION;
+   }
+}
+
+// ssids_analyse with options%ordering = 2 (ssids.f90:283-286, 321-358): the order comes from the matching on the values,
+// its scaling stays in akeep for options%scaling = 3.
+int b200ldlt_analyse_matched(void** akeep, int n, const int64_t* ptr, const int* row, const double* val, int* order,
+                             const b200ldlt_options* opt, b200ldlt_inform* inf) {
+   clear_inform(inf);
+   if (!akeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
+   if (n < 0) return inf->flag = SSIDS_ERROR_A_N_OOR;
+   if (n > 0 && (!ptr || !row || !order)) return inf->flag = SSIDS_ERROR_A_PTR;
+   if (n > 0 && !val) return inf->flag = SSIDS_ERROR_VAL;
+   const int base = opt->array_base ? 1 : 0;
+   if (n > 0 && ptr[0] != base) return inf->flag = SSIDS_ERROR_A_PTR;
+   for (int i = 0; i < n; ++i)
+      if (ptr[i + 1] < ptr[i]) return inf->flag = SSIDS_ERROR_A_PTR;
+   std::vector<double> sc(std::max(n, 1));
+   int mflag = 0;
+   try {
+      const int64_t nz = n > 0 ? ptr[n] - base : 0;
+      std::vector<int64_t> p0(n + 1);
+      std::vector<int> r0((size_t)nz), o0(std::max(n, 1));
+      for (int i = 0; i <= n; ++i) p0[i] = ptr[i] - base;
+      for (int64_t k = 0; k < nz; ++k) {
+         r0[k] = row[k] - base;
+         if (r0[k] < 0 || r0[k] >= n) return inf->flag = SSIDS_ERROR_A_ALL_OOR;
+      }
+      mflag = match_order(n, p0.data(), r0.data(), val, 3, o0.data(), sc.data());
+      if (mflag < 0) return inf->flag = mflag;
+      for (int i = 0; i < n; ++i) order[i] = o0[i] + base;
+   } catch (const std::bad_alloc&) {
+      return inf->flag = SSIDS_ERROR_ALLOCATION;
+   }
+   const int flag = b200ldlt_analyse_ptr64(akeep, n, ptr, row, order, opt, inf);
+   if (flag < 0) return flag;
+   Akeep* ak = static_cast<Akeep*>(*akeep);
+   ak->match_scale.assign(sc.begin(), sc.begin() + n);
+   if (mflag == 1) inf->flag = ak->inf_analyse.flag = SSIDS_WARNING_ANAL_SINGULAR;
+   return inf->flag;
+}
+
 int b200ldlt_factor_scaled(void* akeep, void** fkeep, int posdef, const double* val, double* scale,
                            const b200ldlt_options* opt, b200ldlt_inform* inf) {
    if (!akeep || !fkeep || !opt || !inf) return SSIDS_ERROR_CALL_SEQUENCE;
    Akeep* ak = static_cast<Akeep*>(akeep);
    *inf = ak->inf_analyse;
    const int sc = opt->reserved[2];
-   if (sc == 3) return inf->flag = SSIDS_ERROR_UNIMPLEMENTED;   // scaling from a matching-based ORDER (needs match_order_metis)
+   if (sc == 3 && (int)ak->match_scale.size() != ak->sym.n) return inf->flag = SSIDS_ERROR_NO_SAVED_SCALING;   // ssids.f90:990-995
    if (ak->sym.n > 0 && !val) return inf->flag = SSIDS_ERROR_VAL;
    if (int rc = ensure_fkeep(ak, fkeep, opt, inf)) return rc;
    Fkeep* fk = static_cast<Fkeep*>(*fkeep);
@@ -287,6 +344,9 @@ int b200ldlt_factor_scaled(void* akeep, void** fkeep, int posdef, const double* 
       auction_scale_sym(n, ak->sym.ptr.data(), ak->sym.row.data(), val, s.data());
       if (scale) std::copy(s.begin(), s.begin() + n, scale);
       rc = numeric_set_scaling(fk->num, s.data());
+   } else if (sc == 3) {                // saved by the matching-based order of the analyse phase (ssids.f90:990-998)
+      if (scale) std::copy(ak->match_scale.begin(), ak->match_scale.end(), scale);
+      rc = numeric_set_scaling(fk->num, n > 0 ? ak->match_scale.data() : nullptr);
    } else if (sc >= 4) {                // norm equilibration, computed here, returned in `scale` if given
       std::vector<double> s(std::max(n, 1));
       equilib_scale_sym(n, ak->sym.ptr.data(), ak->sym.row.data(), val, s.data());

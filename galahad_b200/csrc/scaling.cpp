@@ -441,6 +441,243 @@ int hungarian_scale_sym(int n, const int64_t* ptr0, const int* row0, const doubl
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Matching-based ordering (SSIDS options%ordering = 2): restatement of
+//    match_order_metis / mo_scale / mo_match / mo_split     src/spral/match_order.f90:135-208, 406-485, 495-629, 220-396
+//    expand_matrix                                           src/ssids/anal.f90:87-138
+// A maximum-product matching of |a_ij| (hungarian_match above) is broken into 1- and 2-cycles, matched pairs (i, j) are
+// merged into one vertex of a compressed graph, the compressed graph is ordered, and each pair takes two consecutive
+// places in the pivot order: the large off-diagonal a_ij is then at hand as a 2x2 pivot when the diagonals are small or
+// zero (KKT systems).  The duals of the matching give the scaling that SSIDS keeps for options%scaling = 3.  The
+// compressed graph is ordered by this library's nested dissection / minimum degree (ordering.cpp) where the reference
+// calls METIS, a package outside its tree.
+namespace {
+
+// lower triangle by columns (0-based in) -> both triangles, 1-based, entries of a column in the reference's order
+void expand_matrix(int n, const int64_t* ptr0, const int* row0, const double* val0, std::vector<i64>& aptr, std::vector<int>& arow,
+                   std::vector<double>& aval) {
+   const i64 nz = n > 0 ? ptr0[n] : 0;
+   aptr.assign(n + 2, 0);
+   arow.assign(2 * nz + 2, 0);
+   aval.assign(2 * nz + 2, 0.0);
+   for (int j = 1; j <= n; ++j)
+      for (i64 kk = ptr0[j - 1]; kk < ptr0[j]; ++kk) {
+         const int i = row0[kk] + 1;
+         aptr[i] += 1;
+         if (j == i) continue;
+         aptr[j] += 1;
+      }
+   for (int j = 2; j <= n; ++j) aptr[j] += aptr[j - 1];
+   aptr[n + 1] = aptr[n] + 1;
+   for (int j = 1; j <= n; ++j)
+      for (i64 kk = ptr0[j - 1]; kk < ptr0[j]; ++kk) {
+         const int i = row0[kk] + 1;
+         const double atemp = val0[kk];
+         const i64 ipos = aptr[i];
+         arow[ipos] = j;
+         aval[ipos] = atemp;
+         aptr[i] = ipos - 1;
+         if (j == i) continue;
+         const i64 jpos = aptr[j];
+         arow[jpos] = i;
+         aval[jpos] = atemp;
+         aptr[j] = jpos - 1;
+      }
+   for (int j = 1; j <= n; ++j) aptr[j] += 1;
+}
+
+// mo_match: matching and log-scaling of the full matrix of absolute values (explicit zeros gone); ptr2 / row2 / val2 are
+// overwritten.  Returns 0, or 1 when the matrix is structurally singular (unmatched rows: perm = -1, scale = -huge).
+int mo_match(int n, std::vector<int>& row2, std::vector<i64>& ptr2, std::vector<double>& val2, std::vector<double>& scale,
+             std::vector<int>& perm) {
+   std::vector<double> cmax(n + 1, 0.0);
+   for (int i = 1; i <= n; ++i) {
+      double colmax = 0.0;
+      for (i64 j = ptr2[i]; j < ptr2[i + 1]; ++j) colmax = std::max(colmax, val2[j]);
+      if (colmax != 0.0) colmax = std::log(colmax);
+      cmax[i] = colmax;
+   }
+   for (int i = 1; i <= n; ++i)
+      for (i64 j = ptr2[i]; j < ptr2[i + 1]; ++j) val2[j] = cmax[i] - std::log(val2[j]);
+   std::vector<int> cperm;
+   std::vector<double> du, dv;
+   int rank = 0;
+   hungarian_match(n, n, ptr2, row2, val2, cperm, rank, du, dv);
+   scale.assign(n + 1, 0.0);
+   perm.assign(n + 1, 0);
+   if (rank == n) {
+      for (int i = 1; i <= n; ++i) scale[i] = (du[i] + dv[i] - cmax[i]) / 2;
+      for (int i = 1; i <= n; ++i) perm[i] = cperm[i];
+      return 0;
+   }
+   // structurally singular: squeeze the unmatched rows and columns out, match what is left again
+   std::vector<int> old_to_new(n + 1, 0), new_to_old(n + 1, 0);
+   int k = 0;
+   for (int i = 1; i <= n; ++i) {
+      if (cperm[i] < 0) old_to_new[i] = -1;
+      else { k += 1; old_to_new[i] = k; new_to_old[k] = i; }
+   }
+   i64 nne = 0;
+   k = 0;
+   i64 j2 = 1;
+   ptr2[1] = 1;
+   for (int i = 1; i <= n; ++i) {
+      const i64 j1 = j2;
+      j2 = ptr2[i + 1];
+      if (cperm[i] < 0) continue;
+      k += 1;
+      for (i64 jl = j1; jl < j2; ++jl) {
+         const int jj = row2[jl];
+         if (cperm[jj] < 0) continue;
+         nne += 1;
+         row2[nne] = old_to_new[jj];
+         val2[nne] = val2[jl];
+      }
+      ptr2[k + 1] = nne + 1;
+   }
+   const int nn = k;
+   std::vector<int> cperm2;
+   int rank2 = 0;
+   hungarian_match(nn, nn, ptr2, row2, val2, cperm2, rank2, du, dv);
+   for (int i = 1; i <= n; ++i) {
+      const int j = old_to_new[i];
+      scale[i] = j < 0 ? -RINF : (du[j] + dv[j] - cmax[i]) / 2;
+   }
+   for (int i = 1; i <= n; ++i) perm[i] = -1;
+   for (int i = 1; i <= nn; ++i) perm[new_to_old[i]] = new_to_old[cperm2[i]];
+   return 1;
+}
+
+}  // namespace
+
+int match_order(int n, const int64_t* ptr0, const int* row0, const double* val0, int kind, int* order, double* scale_out,
+                int* pairs_out, std::vector<int64_t>* cptr_out, std::vector<int>* crow_out) {
+   if (n < 0) return SSIDS_ERROR_A_N_OOR;
+   if (n == 0) return 0;
+   std::vector<i64> aptr;
+   std::vector<int> arow;
+   std::vector<double> aval;
+   expand_matrix(n, ptr0, row0, val0, aptr, arow, aval);
+   // explicit zeros out, absolute values (match_order_metis; mo_scale repeats the squeeze on its own copy)
+   std::vector<i64> ptr2(n + 2, 0);
+   std::vector<int> row2(arow.size(), 0);
+   std::vector<double> val2(aval.size(), 0.0);
+   i64 k = 1;
+   for (int i = 1; i <= n; ++i) {
+      ptr2[i] = k;
+      for (i64 j = aptr[i]; j < aptr[i + 1]; ++j) {
+         if (aval[j] == 0.0) continue;
+         row2[k] = arow[j];
+         val2[k] = std::fabs(aval[j]);
+         k += 1;
+      }
+   }
+   ptr2[n + 1] = k;
+   std::vector<double> scale;
+   std::vector<int> cperm;
+   int flag;
+   {
+      std::vector<i64> p(ptr2);
+      std::vector<int> r(row2);
+      std::vector<double> v(val2);
+      flag = mo_match(n, r, p, v, scale, cperm);
+   }
+   // mo_split: cycles of the matching -> singletons and pairs
+   std::vector<int> iwork(n + 1, 0);
+   for (int i = 1; i <= n; ++i) {
+      if (iwork[i] != 0) continue;
+      int j = i;
+      for (;;) {
+         if (cperm[j] == -1) { iwork[j] = -2; break; }          // unmatched
+         if (cperm[j] == i) { iwork[j] = -1; break; }           // singleton, or the odd one of a cycle
+         const int jj = cperm[j];
+         iwork[j] = jj;
+         iwork[jj] = j;
+         j = cperm[jj];
+         if (j == i) break;
+      }
+   }
+   cperm = iwork;
+   std::vector<int> old_to_new(n + 1, 0), new_to_old(n + 1, 0);
+   int kc = 1;
+   for (int i = 1; i <= n; ++i) {
+      const int j = cperm[i];
+      if (j < i && j > 0) continue;
+      old_to_new[i] = kc;
+      new_to_old[kc] = i;                                        // the first of a pair
+      if (j > 0) old_to_new[j] = kc;
+      kc += 1;
+   }
+   const int ncomp_matched = kc - 1;
+   // pattern of the compressed matrix, then its lower triangle
+   std::vector<i64> ptr3(n + 2, 0);
+   std::vector<int> row3(row2.size(), 0);
+   std::fill(iwork.begin(), iwork.end(), 0);
+   ptr3[1] = 1;
+   int ncomp = 1;
+   i64 jj = 1;
+   for (int i = 1; i <= n; ++i) {
+      const int j = cperm[i];
+      if (j < i && j > 0) continue;
+      for (int pass = 0; pass < 2; ++pass) {
+         const int c = pass == 0 ? i : j;
+         if (c <= 0) continue;
+         for (i64 kl = ptr2[c]; kl < ptr2[c + 1]; ++kl) {
+            const int krow = old_to_new[row2[kl]];
+            if (iwork[krow] == i) continue;
+            if (krow > ncomp_matched) continue;
+            row3[jj] = krow;
+            jj += 1;
+            iwork[krow] = i;
+         }
+      }
+      ptr3[ncomp + 1] = jj;
+      ncomp += 1;
+   }
+   ncomp -= 1;
+   {
+      i64 out = 1, j1 = 1;
+      for (int i = 1; i <= ncomp; ++i) {
+         const i64 j2 = ptr3[i + 1];
+         for (i64 kk = j1; kk < j2; ++kk) {
+            const int krow = row3[kk];
+            if (krow < i) continue;
+            row3[out] = krow;
+            out += 1;
+         }
+         ptr3[i + 1] = out;
+         j1 = j2;
+      }
+   }
+   // order of the compressed matrix (0-based for the ordering routines)
+   std::vector<int64_t> cp(ncomp + 1);
+   std::vector<int> cr((size_t)(ptr3[ncomp + 1] - 1));
+   for (int i = 0; i <= ncomp; ++i) cp[i] = ptr3[i + 1] - 1;
+   for (size_t e = 0; e < cr.size(); ++e) cr[e] = row3[e + 1] - 1;
+   std::vector<int> cord(ncomp, 0);
+   const int orc = kind == 1 ? amd_order(ncomp, cp.data(), cr.data(), cord.data()) : nd_order(ncomp, cp.data(), cr.data(), cord.data());
+   if (orc < 0) return orc;
+   std::vector<int> inv(ncomp + 1, 0);
+   for (int i = 1; i <= ncomp; ++i) inv[cord[i - 1] + 1] = i;
+   int pos = 1;
+   for (int i = 1; i <= ncomp; ++i) {
+      int j = new_to_old[inv[i]];
+      order[j - 1] = pos - 1;
+      pos += 1;
+      if (cperm[j] > 0) {
+         j = cperm[j];
+         order[j - 1] = pos - 1;
+         pos += 1;
+      }
+   }
+   if (scale_out) for (int i = 1; i <= n; ++i) scale_out[i - 1] = std::exp(scale[i]);
+   if (pairs_out) for (int i = 1; i <= n; ++i) pairs_out[i - 1] = cperm[i];
+   if (cptr_out) *cptr_out = cp;
+   if (crow_out) *crow_out = cr;
+   return flag;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
 // Auction algorithm (options%scaling = 2): each unmatched column bids for its best row, prices (row duals) rise by the
 // margin over the second best plus eps; an approximate maximum-product matching in a bounded number of sweeps.
 // Options are the reference's defaults (auction_options, scaling.f90:33-38): max_iterations 30000, max_unchanged

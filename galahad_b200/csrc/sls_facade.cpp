@@ -233,7 +233,7 @@ void sls_analyse_matrix_perm(sls_control_type* control, void** data, int* status
    }
    // The order.  PERM if present (sls.f90:2962-2968).  Otherwise control%ordering decides (sls.f90:2262-2268, 2395-2412,
    // 3134-3140): >= 0 is MC68's menu -- 0, 1 and anything above 6 approximate minimum degree, 2 minimum degree, 3 nested
-   // dissection, 4 (indefinite 1x1 / 2x2 ordering), 5 and 6 (MC61 profile / band) have nothing behind them here; < 0 asks the
+   // dissection, 4 (indefinite 1x1 / 2x2 ordering), 5 and 6 (MC61 profile / band) have nothing behind them here; -1 asks the
    // solver for its own, which for this solver, as for SSIDS with METIS, is nested dissection.  The orderings are this
    // library's (ordering.cpp): the reference's come from packages outside its tree, no permutation is pinned.
    b200ldlt_options o = to_solver(d->control);
@@ -243,8 +243,20 @@ void sls_analyse_matrix_perm(sls_control_type* control, void** data, int* status
    } else {
       const int oc = d->control.ordering;
       int kind;
+      if (oc < -1) {
+         // SSIDS options%ordering = -oc.  2 is the matching-based order, which needs the values: SLS_analyse has none to
+         // pass (sls.f90:3134-3139), so the reference ends in SSIDS_ERROR_VAL (ssids.f90:230-238) and anything beyond in
+         // SSIDS_ERROR_ORDER (:222-227), mapped as every SSIDS flag is.  With values in hand the order is
+         // b200ldlt_analyse_matched's.
+         b200ldlt_inform e = {};
+         e.flag = oc == -2 ? -9 : -8;
+         from_solver(inf, e);
+         d->analysed = false;
+         *status = inf.status;
+         return;
+      }
       if (oc == -1 || oc == 3) kind = 3;
-      else if (oc < 0 || oc == 4 || oc == 5 || oc == 6) kind = 0;
+      else if (oc == 4 || oc == 5 || oc == 6) kind = 0;
       else kind = 1;
       std::vector<int64_t> p64(d->ptr.begin(), d->ptr.end());
       const int rc = kind ? b200ldlt_order(n, p64.data(), d->col.data(), kind, d->order.data(), &o) : GALAHAD_UNAVAILABLE_OPTION;
@@ -306,9 +318,16 @@ void sls_factorize_matrix(void** data, int* status, int ne, const double val[]) 
    // the same Ruiz iteration MC77 runs in that norm), computed from the gathered values.  -1: SSIDS's own matching-based
    // scaling by the Hungarian algorithm (options%scaling = 1, sls.f90:1405-1413 -> ssids.f90:928-960), the restatement
    // of spral/scaling.f90 hungarian_scale_sym behind b200ldlt_hungarian_scale; -2: SSIDS's auction scaling
-   // (options%scaling = 2, auction_scale_sym).  1 (MC64), 2 (MC77 one-norm) and -3 (scaling from SSIDS's matching-based
-   // order) have no implementation behind them.
+   // (options%scaling = 2, auction_scale_sym).  -3 (the scaling SSIDS saves with its matching-based order): that order
+   // cannot be had through SLS_analyse (no values, see above), so as in the reference nothing was saved:
+   // SSIDS_ERROR_NO_SAVED_SCALING (-15, ssids.f90:990-995) -> error_restrictions.  1 (MC64) and 2 (MC77 one-norm) have no
+   // implementation behind them.
    const int sc = d->control.scaling;
+   if (sc == -3) {
+      *status = inf.status = GALAHAD_ERROR_RESTRICTIONS;
+      d->factorized = false;
+      return;
+   }
    if (sc != 0 && sc != 3 && sc != -1 && sc != -2) {
       *status = inf.status = GALAHAD_UNAVAILABLE_OPTION;
       d->factorized = false;

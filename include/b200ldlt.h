@@ -114,6 +114,22 @@ int b200ldlt_analyse(void **akeep, int n, const int *ptr, const int *row, int *o
  * ptr / row as for b200ldlt_analyse_ptr64 (base from opt->array_base); order[n] out, same base. */
 int b200ldlt_order(int n, const int64_t *ptr, const int *row, int kind, int *order, const b200ldlt_options *opt);
 
+/* Matching-based ordering: ssids_analyse with options%ordering = 2 and VAL (ssids.f90:230-238, 321-358;
+ * match_order_metis, src/spral/match_order.f90:135-208).  A maximum-product matching of |a_ij| (the Hungarian algorithm
+ * of the scaling) is split into singletons and pairs, each pair becomes one vertex of a compressed graph, the compressed
+ * graph is ordered by nested dissection (this library's, where the reference calls METIS) and each pair takes two
+ * consecutive places of the pivot order; the matching's scaling is kept in akeep for b200ldlt_factor_scaled with
+ * scaling 3.  val[] aligned with ptr / row (host).  order[n]: out.  Flag 6 (SSIDS_WARNING_ANAL_SINGULAR) when the
+ * matrix is structurally singular, -9 (SSIDS_ERROR_VAL) without val.
+ * b200ldlt_match_order: the order alone on 0-based arrays; kind 1 orders the compressed graph by minimum degree, else
+ * nested dissection; every output but `order` may be NULL: scale[n]; pairs[n] = the split matching (1-based partner, -1
+ * singleton, -2 unmatched); *ncomp, cptr[ncomp+1], crow[] = lower triangle of the compressed pattern (at most n + 1 and
+ * 2 ptr[n] entries).  Returns 0, 1 (structurally singular) or an error flag. */
+int b200ldlt_analyse_matched(void **akeep, int n, const int64_t *ptr, const int *row, const double *val, int *order,
+                             const b200ldlt_options *opt, b200ldlt_inform *inf);
+int b200ldlt_match_order(int n, const int64_t *ptr, const int *row, const double *val, int kind, int *order, double *scale,
+                         int *pairs, int *ncomp, int64_t *cptr, int *crow);
+
 /* 64-bit ptr variant (ssids.f90:148 analyse_double takes int64 ptr). */
 int b200ldlt_analyse_ptr64(void **akeep, int n, const int64_t *ptr, const int *row, int *order,
                            const b200ldlt_options *opt, b200ldlt_inform *inf);
@@ -151,8 +167,8 @@ int b200ldlt_factor_mapped(void *akeep, void **fkeep, int posdef, int ne, const 
  * (hungarian_scale_sym, src/spral/scaling.f90:134-170, MC64's algorithm; ssids.f90:928-960), computed on the host from
  * `val`, returned in `scale` if not NULL; a structurally singular matrix is scaled all the same when options%action is
  * set and is SSIDS_ERROR_SINGULAR (-5) otherwise;  2: matching-based scaling by SPRAL's auction algorithm
- * (auction_scale_sym, scaling.f90:269-309, default auction_options; ssids.f90:962-990);  3 (scaling from a matching-based
- * order, needs match_order_metis): -98, not implemented.  The scaled matrix S A S is factorised; solves scale on the way in (jobs 0, 1) and on the way out
+ * (auction_scale_sym, scaling.f90:269-309, default auction_options; ssids.f90:962-990);  3: the scaling saved by
+ * b200ldlt_analyse_matched (ssids.f90:990-998), SSIDS_ERROR_NO_SAVED_SCALING (-15) after any other analyse.  The scaled matrix S A S is factorised; solves scale on the way in (jobs 0, 1) and on the way out
  * (jobs 0, 3, 4) exactly as fkeep.F90:247-310.  A later b200ldlt_factor / _factor_mapped keeps the scaling that was
  * set last; pass opt->reserved[2] = 0 and scale = NULL here to clear it.  `val` is a host pointer.
  * b200ldlt_equilib_scale: the equilibration alone (0-based lower triangle by columns). */

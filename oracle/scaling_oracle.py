@@ -6,6 +6,7 @@
     heap_update / heap_pop / heap_delete         src/spral/scaling.f90:1203-1325
     match_postproc (square case)                 src/spral/scaling.f90:1611-1640
     half_to_full                                 src/spral/matrix_util.f90:3167-3302
+    match_order_metis / mo_match / mo_split      src/spral/match_order.f90:135-208, 495-629, 220-396 (end of this file)
 
 (the algorithm of MC64: maximum-product matching by shortest augmenting paths on c_ij = max_i log|a_ij| - log|a_ij|; the
 scaling is exp((u_i + v_i - cmax_i) / 2)).  TEST INFRASTRUCTURE ONLY: tests/ compare the product's C++ implementation
@@ -634,3 +635,228 @@ def auction_scale_sym(n, ptr0, row0, val0):
     adjust = (rsum / n - csum / n) / 2
     scaling = [math.exp(((rscaling[i] - adjust) + (cscaling[i] + adjust)) / 2) for i in range(1, n + 1)]
     return scaling, match[1:n + 1], matched, iterations
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Matching-based ordering (SSIDS options%ordering = 2)
+#     match_order_metis / mo_scale / mo_match / mo_split   src/spral/match_order.f90:135-208, 406-485, 495-629, 220-396
+#     expand_matrix                                         src/ssids/anal.f90:87-138
+# The reference orders the compressed graph with METIS, which is not in its tree: `order_compressed` is passed in, and what
+# the tests pin bit for bit is everything around it (matching, split into singletons / pairs, compressed pattern, scaling,
+# expansion of the compressed order).
+
+
+def expand_matrix(n, ptr0, row0, val0):
+    """anal.f90:87-138.  0-based lower triangle by columns in; 1-based full matrix out (aptr has n + 2 entries)."""
+    nz = int(ptr0[n]) if n > 0 else 0
+    aptr = [0] * (n + 2)
+    arow = [0] * (2 * nz + 2)
+    aval = [0.0] * (2 * nz + 2)
+    for j in range(1, n + 1):
+        for kk in range(int(ptr0[j - 1]), int(ptr0[j])):
+            i = int(row0[kk]) + 1
+            aptr[i] += 1
+            if j == i:
+                continue
+            aptr[j] += 1
+    for j in range(2, n + 1):
+        aptr[j] = aptr[j - 1] + aptr[j]
+    aptr[n + 1] = aptr[n] + 1
+    for j in range(1, n + 1):
+        for kk in range(int(ptr0[j - 1]), int(ptr0[j])):
+            i = int(row0[kk]) + 1
+            atemp = float(val0[kk])
+            ipos = aptr[i]
+            arow[ipos] = j
+            aval[ipos] = atemp
+            aptr[i] = ipos - 1
+            if j == i:
+                continue
+            jpos = aptr[j]
+            arow[jpos] = i
+            aval[jpos] = atemp
+            aptr[j] = jpos - 1
+    for j in range(1, n + 1):
+        aptr[j] += 1
+    return aptr, arow, aval
+
+
+def mo_match(n, row2, ptr2, val2):
+    """match_order.f90:495-629.  val2 = absolute values, zeros removed; the three lists are overwritten.
+    Returns flag (0 / 1 = structurally singular), scale (log, 1-based), perm (1-based, -1 unmatched)."""
+    cmax = [0.0] * (n + 1)
+    for i in range(1, n + 1):
+        colmax = 0.0
+        for j in range(ptr2[i], ptr2[i + 1]):
+            if val2[j] > colmax:
+                colmax = val2[j]
+        if colmax != 0.0:
+            colmax = math.log(colmax)
+        cmax[i] = colmax
+    for i in range(1, n + 1):
+        for j in range(ptr2[i], ptr2[i + 1]):
+            val2[j] = cmax[i] - math.log(val2[j])
+    cperm, rank, du, dv = hungarian_match(n, n, ptr2, row2, val2)
+    scale = [0.0] * (n + 1)
+    if rank == n:
+        for i in range(1, n + 1):
+            scale[i] = (du[i] + dv[i] - cmax[i]) / 2
+        return 0, scale, list(cperm)
+    old_to_new = [0] * (n + 1)
+    new_to_old = [0] * (n + 1)
+    k = 0
+    for i in range(1, n + 1):
+        if cperm[i] < 0:
+            old_to_new[i] = -1
+        else:
+            k += 1
+            old_to_new[i] = k
+            new_to_old[k] = i
+    nne = 0
+    k = 0
+    ptr2[1] = 1
+    j2 = 1
+    for i in range(1, n + 1):
+        j1 = j2
+        j2 = ptr2[i + 1]
+        if cperm[i] < 0:
+            continue
+        k += 1
+        for jl in range(j1, j2):
+            jj = row2[jl]
+            if cperm[jj] < 0:
+                continue
+            nne += 1
+            row2[nne] = old_to_new[jj]
+            val2[nne] = val2[jl]
+        ptr2[k + 1] = nne + 1
+    nn = k
+    cperm2, rank2, du, dv = hungarian_match(nn, nn, ptr2, row2, val2)
+    for i in range(1, n + 1):
+        j = old_to_new[i]
+        scale[i] = -RINF if j < 0 else (du[j] + dv[j] - cmax[i]) / 2
+    perm = [-1] * (n + 1)
+    for i in range(1, nn + 1):
+        perm[new_to_old[i]] = new_to_old[cperm2[i]]
+    return 1, scale, perm
+
+
+def mo_split(n, row2, ptr2, cperm, order_compressed):
+    """match_order.f90:220-396.  Returns order (1-based positions, list of n + 1), the split matching, (ncomp, ptr3, row3)."""
+    iwork = [0] * (n + 1)
+    for i in range(1, n + 1):
+        if iwork[i] != 0:
+            continue
+        j = i
+        while True:
+            if cperm[j] == -1:
+                iwork[j] = -2
+                break
+            elif cperm[j] == i:
+                iwork[j] = -1
+                break
+            jj = cperm[j]
+            iwork[j] = jj
+            iwork[jj] = j
+            j = cperm[jj]
+            if j == i:
+                break
+    cperm = list(iwork)
+    old_to_new = [0] * (n + 1)
+    new_to_old = [0] * (n + 1)
+    k = 1
+    for i in range(1, n + 1):
+        j = cperm[i]
+        if j < i and j > 0:
+            continue
+        old_to_new[i] = k
+        new_to_old[k] = i
+        if j > 0:
+            old_to_new[j] = k
+        k += 1
+    ncomp_matched = k - 1
+    ne = ptr2[n + 1] - 1
+    ptr3 = [0] * (n + 2)
+    row3 = [0] * (ne + 2)
+    iwork = [0] * (n + 1)
+    ptr3[1] = 1
+    ncomp = 1
+    jj = 1
+    for i in range(1, n + 1):
+        j = cperm[i]
+        if j < i and j > 0:
+            continue
+        for kl in range(ptr2[i], ptr2[i + 1]):
+            krow = old_to_new[row2[kl]]
+            if iwork[krow] == i:
+                continue
+            if krow > ncomp_matched:
+                continue
+            row3[jj] = krow
+            jj += 1
+            iwork[krow] = i
+        if j > 0:
+            for kl in range(ptr2[j], ptr2[j + 1]):
+                krow = old_to_new[row2[kl]]
+                if iwork[krow] == i:
+                    continue
+                if krow > ncomp_matched:
+                    continue
+                row3[jj] = krow
+                jj += 1
+                iwork[krow] = i
+        ptr3[ncomp + 1] = jj
+        ncomp += 1
+    ncomp -= 1
+    ptr3[1] = 1
+    jj = 1
+    j1 = 1
+    for i in range(1, ncomp + 1):
+        j2 = ptr3[i + 1]
+        for k in range(j1, j2):
+            krow = row3[k]
+            if krow < i:
+                continue
+            row3[jj] = krow
+            jj += 1
+        ptr3[i + 1] = jj
+        j1 = j2
+    corder = order_compressed(ncomp, ptr3, row3)          # corder[i] = position of compressed vertex i, both 1-based
+    iw = [0] * (ncomp + 1)
+    for i in range(1, ncomp + 1):
+        iw[corder[i]] = i
+    order = [0] * (n + 1)
+    k = 1
+    for i in range(1, ncomp + 1):
+        j = new_to_old[iw[i]]
+        order[j] = k
+        k += 1
+        if cperm[j] > 0:
+            j = cperm[j]
+            order[j] = k
+            k += 1
+    return order, cperm, (ncomp, ptr3, row3)
+
+
+def match_order(n, ptr0, row0, val0, order_compressed):
+    """match_order_metis (match_order.f90:135-208) on the full matrix expand_matrix makes of the 0-based lower triangle.
+    Returns flag, order (0-based positions, n), scale (n), pairs (n; 1-based partner, -1 singleton, -2 unmatched) and the
+    compressed lower-triangular pattern (ncomp, ptr3, row3; 1-based lists)."""
+    aptr, arow, aval = expand_matrix(n, ptr0, row0, val0)
+    ptr2 = [0] * (n + 2)
+    row2 = [0] * len(arow)
+    val2 = [0.0] * len(aval)
+    k = 1
+    for i in range(1, n + 1):
+        ptr2[i] = k
+        for j in range(aptr[i], aptr[i + 1]):
+            if aval[j] == 0.0:
+                continue
+            row2[k] = arow[j]
+            val2[k] = abs(aval[j])
+            k += 1
+    ptr2[n + 1] = k
+    flag, scale, cperm = mo_match(n, list(row2), list(ptr2), list(val2))      # mo_scale works on its own copy
+    order, pairs, comp = mo_split(n, row2, ptr2, cperm, order_compressed)
+    sc = [math.exp(scale[i]) if scale[i] != -RINF else 0.0 for i in range(1, n + 1)]
+    return flag, [order[i] - 1 for i in range(1, n + 1)], sc, pairs[1:n + 1], comp

@@ -2,10 +2,13 @@
 seeded inputs.  Integer results (inertia, delays reported by both as they use the same schedule)
 are compared exactly; solutions by scaled backward error <= 1e-14 and agreement with the oracle's
 solution to 1e-10 x a condition allowance."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
 from galahad_b200 import problems as P
+from galahad_b200 import _lib
 from galahad_b200._lib import Solver
 from oracle.refssids import Oracle, permuted_solve
 from util import bcsstk01_problem, golden, golden_cases, kat_problem, rhs_for
@@ -293,7 +296,7 @@ def test_scaled_factorisation():
     symmetrically mis-scaled KKT matrix factorised with user-supplied factors that undo the damage gives the
     pivot sequence statistics of the well-scaled matrix and solves the mis-scaled system; equilibration gives
     a clean factorisation too, as do the matching-based scalings 1 (Hungarian) and 2 (auction); partial solves compose;
-    scaling 3 (from a matching-based order) is reported as not implemented."""
+    scaling 3 (saved by a matching-based order) after a plain analyse is SSIDS_ERROR_NO_SAVED_SCALING."""
     rng = np.random.default_rng(21)
     prob = P.kkt_grid_problem(8)
     n, ptr, row = prob["n"], prob["ptr"], prob["row"]
@@ -333,13 +336,63 @@ def test_scaled_factorisation():
     f, x2 = s.solve(b)
     assert f == 0 and P.backward_error(bad, x2, b) <= 1e-14
     flag, _ = s.factor_scaled(bad["val"], scaling=3)
-    assert flag == -98
+    assert flag == -15
     # clearing the scaling restores the plain path
     flag, _ = s.factor_scaled(prob["val"], scaling=0)
     b0 = P.full_from_lower(n, ptr, row, prob["val"]) @ xs
     f, x0 = s.solve(b0)
     fg, xg = good.solve(b0)
     assert flag >= 0 and np.array_equal(x0, xg)
+
+
+def test_matching_based_order_and_its_scaling():
+    """ssids_analyse with options%ordering = 2 and ssids_factor with options%scaling = 3 (ssids.f90:321-358, 990-998;
+    match_order.f90): a saddle-point matrix with a ZERO (2,2) block and tiny, badly scaled (1,1) diagonals.  Under a
+    fill-reducing order that knows nothing of the values many pivots fail their threshold test and are delayed; with
+    the matching-based order every constraint sits next to a variable it is matched with (a 2 x 2 pivot at hand) and the
+    matching's scaling makes those entries 1: far fewer delays, exact inertia (n_v, m, 0) and a solved system."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(17)
+    g = 10
+    nv = g ** 3
+    m = nv // 2
+    lap = P.laplace_problem(g)
+    Hl = sp.csc_matrix((lap["val"], lap["row"], lap["ptr"]), shape=(nv, nv))
+    H = (Hl + sp.tril(Hl, -1).T) * 1e-3 + sp.diags(10.0 ** rng.uniform(-8, -2, nv))
+    rows = np.repeat(np.arange(m), 2)
+    cols = np.stack([np.arange(m), np.arange(m) + m], 1).ravel()
+    J = sp.csr_matrix((10.0 ** rng.uniform(-2, 2, 2 * m), (rows, cols)), shape=(m, nv))
+    K = sp.bmat([[H, J.T], [J, None]], format="csc")
+    n, ptr, row, val = P.lower_csc(K)
+    prob = dict(n=n, ptr=ptr, row=row, val=val)
+    xs = rng.uniform(-1, 1, n)
+    b = K @ xs
+    # values-blind order: nested dissection of the pattern
+    L = _lib.lib()
+    plain = Solver()
+    o = np.zeros(n, np.int32)
+    assert L.b200ldlt_order(n, _lib.as_ptr(ptr.astype(np.int64), C.c_int64), _lib.as_ptr(row, C.c_int), 3, _lib.as_ptr(o, C.c_int),
+                            C.byref(plain.opt)) == 0
+    assert plain.analyse(n, ptr, row, o) >= 0
+    assert plain.factor(val) >= 0
+    d_plain = plain.inform.num_delay
+    assert (plain.inform.num_neg, plain.inform.matrix_rank) == (m, n)
+    # matching-based order + its scaling
+    s = Solver()
+    assert s.analyse_matched(n, ptr, row, val) == 0
+    assert sorted(s.order) == list(range(n))
+    flag, sc = s.factor_scaled(val, scaling=3)
+    assert flag >= 0 and sc is not None and sc.min() > 0
+    col = np.repeat(np.arange(n), np.diff(ptr))
+    assert (np.abs(val) * sc[row] * sc[col]).max() <= 1 + 1e-9
+    assert (s.inform.num_neg, s.inform.matrix_rank) == (m, n)
+    assert s.inform.num_delay * 4 <= max(d_plain, 4), (s.inform.num_delay, d_plain)
+    f, x = s.solve(b)
+    assert f == 0 and P.backward_error(prob, x, b) <= 1e-13
+    # the saved scaling belongs to the analyse: a new plain analyse forgets it
+    assert s.analyse(n, ptr, row, o) >= 0
+    flag, _ = s.factor_scaled(val, scaling=3)
+    assert flag == -15
 
 
 def _arms_problem(arms, ns, kind, seed=3):

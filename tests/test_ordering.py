@@ -77,7 +77,7 @@ def test_ordering_edge_cases():
 
 def test_sls_analyse_without_perm_uses_the_orderings():
     """control%ordering with no PERM: < 0 (the solver's own, the default -1) and 3 give nested dissection, 0 / 1 / 2 minimum
-    degree, 4 / 5 / 6 GALAHAD_unavailable_option; the order the solver reports is a permutation with less fill than the
+    degree, 4 / 5 / 6 GALAHAD_unavailable_option, -2 and below the reference's error codes; the order the solver reports is a permutation with less fill than the
     identity (sls.f90:2262-2268, 2395-2412)."""
     prob = P.laplace_problem(12)
     n = prob["n"]
@@ -93,8 +93,10 @@ def test_sls_analyse_without_perm_uses_the_orderings():
         seen[oc] = inf.entries_in_factors
         s.terminate()
     assert seen[-1] == seen[3] and seen[0] == seen[1] == seen[2] == seen[7]
-    for oc in (4, 5, 6, -2):
+    # -2 = SSIDS's matching-based order, for which SLS_analyse has no values to pass: SSIDS_ERROR_VAL -> error_restrictions;
+    # below that SSIDS_ERROR_ORDER -> error_inertia (the table of SLS_copy_inform_from_ssids, sls.f90:1766-1773)
+    for oc, want in ((4, -29), (5, -29), (6, -29), (-2, -3), (-3, -20)):
         s = SLS()
         s.control.ordering = oc
-        assert s.analyse_matrix(n, "coordinate", prob["row"].size, prob["row"], colidx) == -29, oc
+        assert s.analyse_matrix(n, "coordinate", prob["row"].size, prob["row"], colidx) == want, oc
         s.terminate()

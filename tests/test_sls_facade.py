@@ -223,7 +223,7 @@ def test_matching_based_scaling_through_sls():
     b = P.full_from_lower(n, prob["ptr"], prob["row"], val) @ rng.uniform(-1, 1, n)
     st, x = s.solve_system(b)
     assert st == 0 and P.backward_error(bad, x, b) <= 1e-14
-    for sc, want in ((-2, 0), (-3, -29)):           # auction scaling; matching-order scaling: GALAHAD_unavailable_option
+    for sc, want in ((-2, 0), (-3, -3)):            # auction scaling; matching-order scaling: nothing saved -> error_restrictions
         s2 = SLS()
         s2.control.f_indexing = False
         s2.control.scaling = sc
