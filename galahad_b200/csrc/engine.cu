@@ -436,7 +436,9 @@ __global__ void k_stats(const FrontDev* fr, int nslots, int* counters) {
 #include "solve_kernels.cuh"
 
 static inline size_t step_smem_fwd(int kbc) { return (size_t)(kbc * (kbc + 1) + kbc + 256) * 8; }
-static inline size_t chain_smem() { return (size_t)(KB * (KB + 1) + KB + 2 * KB + 32 + 2 * KB + 4 * 32 * ILD + 32) * 8; }
+static inline size_t chain_smem() {
+   return (size_t)(KB * (KB + 1) + KB + 2 * KB + 32 + 2 * KB + 4 * 32 * ILD + KB + 4 * KB + 32) * 8;
+}
 static inline int step_grid_y(int rows, int rc, int slots, int fronts) {
    return std::max(1, std::min((rows + rc - 1) / rc, slots / std::max(1, fronts)));
 }
@@ -831,12 +833,29 @@ class Numeric {
    bool have_chain = false;
    unsigned long long* d_chain_counter = nullptr;   // [2 * nlevels]
    int* d_chain_err = nullptr;
+   unsigned long long* d_chain_dbg = nullptr;       // B200LDLT_SOLVE_TRACE: four time stamps per chain role
+   // chain fronts: inverses of the 128 x 128 diagonal blocks (k_chain_inverses, once per factorisation) and the partial
+   // sums of the rows below the pivots for the backward sweep (k_bwd_tail)
+   double* d_minv = nullptr; size_t minv_cap = 0;   // blocks of KB x KB doubles
+   int* d_minv_off = nullptr;                       // per slot: first block, -1 = none
+   int* d_mflag = nullptr; size_t mflag_cap = 0;
+   int2* d_blist = nullptr;
+   bool have_minv = false;
+   double* d_tail = nullptr; size_t tail_cap = 0;
+   int64_t* d_tail_off = nullptr;                   // per slot: offset into d_tail, -1 = none
+   int4* d_troles = nullptr; size_t troles_cap = 0;
+   std::vector<int64_t> troles_off;
+   std::vector<int> troles_n;
+   bool have_tail = false;
+   void chain_trace(const char* what, int l, int nroles, int off);
    std::vector<int64_t> roles_fwd_off, roles_bwd_off;
    std::vector<int> roles_fwd_n, roles_bwd_n;
    bool use_fused = !(getenv("B200LDLT_FUSED") && atoi(getenv("B200LDLT_FUSED")) == 0);
    bool use_chain = !(getenv("B200LDLT_CHAIN") && atoi(getenv("B200LDLT_CHAIN")) == 0);
    // chain kernels: 32 x 32 diagonal sub-triangles through explicit inverses formed while a role waits (solve_kernels.cuh)
-   bool use_solve_inv = !(getenv("B200LDLT_SOLVE_INV") && atoi(getenv("B200LDLT_SOLVE_INV")) == 0);
+   // chain kernels of the solve: 0 substitution, 1 the 32 x 32 sub-triangles through their inverses, 2 the whole 128 x 128
+   // diagonal block through its inverse and one warp polling per 32 published values
+   int use_solve_inv = getenv("B200LDLT_SOLVE_INV") ? atoi(getenv("B200LDLT_SOLVE_INV")) : 2;
    int* d_ticket = nullptr;         // per slot: arrival counter of the backward step's CTAs (left at zero by the last one)
    int* d_slist = nullptr;
    std::vector<int> slist, lvl_steps, lvl_maxm, lvl_maxne;
@@ -903,7 +922,7 @@ class Numeric {
       cudaSetDevice(P->device);
       fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release(); bar.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
-      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_slist); cudaFree(d_scale); cudaFree(d_a_rowi); cudaFree(d_a_coli); cudaFree(d_um_rptr); cudaFree(d_um_rent); cudaFree(d_um_rcol); cudaFree(d_rb); cudaFree(d_rx); cudaFree(d_rr); cudaFree(d_rnorm);
+      cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_chain_dbg); cudaFree(d_minv); cudaFree(d_minv_off); cudaFree(d_mflag); cudaFree(d_blist); cudaFree(d_tail); cudaFree(d_tail_off); cudaFree(d_troles); cudaFree(d_slist); cudaFree(d_scale); cudaFree(d_a_rowi); cudaFree(d_a_coli); cudaFree(d_um_rptr); cudaFree(d_um_rent); cudaFree(d_um_rcol); cudaFree(d_rb); cudaFree(d_rx); cudaFree(d_rr); cudaFree(d_rnorm);
       cudaFree(d_chg_idx); cudaFree(d_chg_val);
       cudaFree(d_part); cudaFree(d_val); cudaFree(d_uval); cudaFree(d_vm_src); cudaFree(d_vm_dst); cudaFree(d_vm_dup_dst); cudaFree(d_vm_dup_ptr); cudaFree(d_vm_dup_src); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
       if (pin_fr) cudaFreeHost(pin_fr);
@@ -979,6 +998,7 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_fwd_step<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd(128)));
    CU(cudaFuncSetAttribute(k_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem()));
    CU(cudaFuncSetAttribute(k_bwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem()));
+   CU(cudaFuncSetAttribute(k_chain_inverses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_inv_smem()));
    CU(cudaFuncSetAttribute(k_bwd_step<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    CU(cudaFuncSetAttribute(k_bwd_step<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    const int nn = std::max(P->nnodes, 1);
@@ -1018,6 +1038,7 @@ int Numeric::init() {
    CU(cudaMalloc(&d_ticket, sizeof(int) * (nn + 1)));
    CU(cudaMalloc(&d_chain_counter, sizeof(unsigned long long) * 2 * (P->nlevels + 1)));
    CU(cudaMalloc(&d_chain_err, sizeof(int)));
+   if (getenv("B200LDLT_SOLVE_TRACE")) CU(cudaMalloc(&d_chain_dbg, sizeof(unsigned long long) * 16 * 4096));
    CU(cudaMemset(d_chain_err, 0, sizeof(int)));
    CU(cudaMemset(d_ticket, 0, sizeof(int) * (nn + 1)));
    CU(cudaMalloc(&d_slist, sizeof(int) * nn));
@@ -1952,6 +1973,73 @@ int Numeric::build_solve_tables() {
          if (!roles.empty()) CU(cudaMemcpy(d_roles, roles.data(), sizeof(int2) * roles.size(), cudaMemcpyHostToDevice));
          CU(cudaMemsetAsync(d_chain_counter, 0, sizeof(unsigned long long) * 2 * (P->nlevels + 1), st));
          have_chain = !roles.empty();
+         // the diagonal blocks' inverses and the tail chunks of the backward sweep for the same fronts
+         have_minv = have_tail = false;
+         troles_off.assign(P->nlevels, 0);
+         troles_n.assign(P->nlevels, 0);
+         if (have_chain && use_solve_inv > 1) {
+            std::vector<int2> blist;
+            std::vector<int> moff(std::max(nn, 1), -1);
+            std::vector<int64_t> toff(std::max(nn, 1), -1);
+            std::vector<int4> troles;
+            int64_t tail_total = 0;
+            for (int l = 0; l < P->nlevels; ++l) {
+               if (roles_fwd_n[l] == 0) continue;
+               troles_off[l] = (int64_t)troles.size();
+               for (int q = P->lvl_ptr[l]; q < P->lvl_ptr[l + 1]; ++q) {
+                  const int s = slist[q];
+                  const int ne = hfr[s].state == 2 ? hfr[s].nelim : 0;
+                  if (ne <= 0) continue;
+                  const int nb = (ne + KB - 1) / KB, ntc = (hfr[s].m - ne + TAIL_ROWS - 1) / TAIL_ROWS;
+                  moff[s] = (int)blist.size();
+                  for (int c = 0; c < nb; ++c) blist.push_back(make_int2(s, c));
+                  if (ntc > 0 && nb > 1) {
+                     toff[s] = tail_total;
+                     tail_total += (int64_t)ntc * nb * KB;
+                     for (int c = nb - 1; c >= 0; --c)
+                        for (int t = 0; t < ntc; ++t) troles.push_back(make_int4(s, c, t, 0));
+                  }
+               }
+               troles_n[l] = (int)(troles.size() - troles_off[l]);
+            }
+            const char* mb = getenv("B200LDLT_SOLVE_INV_MB");
+            const size_t budget = (size_t)(mb ? atoll(mb) : 4096) << 20;
+            if (!blist.empty() && blist.size() * KB * KB * 8 <= budget) {
+               if (!d_minv_off) CU(cudaMalloc(&d_minv_off, sizeof(int) * std::max(nn, 1)));
+               if (minv_cap < blist.size()) {
+                  cudaFree(d_minv); cudaFree(d_blist); d_minv = nullptr; d_blist = nullptr;
+                  if (cudaMalloc(&d_minv, blist.size() * KB * KB * 8) != cudaSuccess) { cudaGetLastError(); d_minv = nullptr; minv_cap = 0; }
+                  else { CU(cudaMalloc(&d_blist, sizeof(int2) * blist.size())); minv_cap = blist.size(); }
+               }
+               if (mflag_cap < blist.size()) {
+                  cudaFree(d_mflag); d_mflag = nullptr;
+                  CU(cudaMalloc(&d_mflag, sizeof(int) * blist.size()));
+                  mflag_cap = blist.size();
+               }
+               if (d_minv) {
+                  CU(cudaMemcpy(d_minv_off, moff.data(), sizeof(int) * std::max(nn, 1), cudaMemcpyHostToDevice));
+                  CU(cudaMemcpy(d_blist, blist.data(), sizeof(int2) * blist.size(), cudaMemcpyHostToDevice));
+                  k_chain_inverses<<<(int)blist.size(), 256, chain_inv_smem(), st>>>(d_fr, d_blist, d_minv, d_mflag);
+                  have_minv = true;
+               }
+            }
+            if (!troles.empty()) {
+               if (!d_tail_off) CU(cudaMalloc(&d_tail_off, sizeof(int64_t) * std::max(nn, 1)));
+               if (tail_cap < (size_t)tail_total) {
+                  cudaFree(d_tail); d_tail = nullptr;
+                  CU(cudaMalloc(&d_tail, sizeof(double) * (size_t)tail_total));
+                  tail_cap = (size_t)tail_total;
+               }
+               if (troles_cap < troles.size()) {
+                  cudaFree(d_troles); d_troles = nullptr;
+                  CU(cudaMalloc(&d_troles, sizeof(int4) * troles.size()));
+                  troles_cap = troles.size();
+               }
+               CU(cudaMemcpy(d_tail_off, toff.data(), sizeof(int64_t) * std::max(nn, 1), cudaMemcpyHostToDevice));
+               CU(cudaMemcpy(d_troles, troles.data(), sizeof(int4) * troles.size(), cudaMemcpyHostToDevice));
+               have_tail = true;
+            }
+         }
       }
       // child delay offsets must describe the final state for the solve
       if (!child_doff.empty())
@@ -1993,21 +2081,50 @@ int Numeric::solve_prepare() {
 }
 
 // launch helpers: instantiation by the widest block of the launch
+static inline bool solve_pdl() {
+   static const bool on = !(getenv("B200LDLT_SOLVE_PDL") && atoi(getenv("B200LDLT_SOLVE_PDL")) == 0);
+   return on;
+}
 template <bool FUSED>
 static void launch_fwd_step(int kbmax, dim3 grid, cudaStream_t st, const FrontDev* fr, const int* list, const int64_t* xw_off, double* xw,
                             double* xy, int sp, int kind, const GatherArgs& ga) {
-   if (kbmax <= 32) k_fwd_step<32, FUSED><<<grid, 256, step_smem_fwd(32), st>>>(fr, list, xw_off, xw, xy, sp, kind, ga);
-   else if (kbmax <= 64) k_fwd_step<64, FUSED><<<grid, 256, step_smem_fwd(64), st>>>(fr, list, xw_off, xw, xy, sp, kind, ga);
-   else k_fwd_step<128, FUSED><<<grid, 256, step_smem_fwd(128), st>>>(fr, list, xw_off, xw, xy, sp, kind, ga);
+   // levels of one launch each follow one another as programmatic dependents: the next level stages its L while this one runs
+   const bool dep = FUSED && solve_pdl();
+   if (kbmax <= 32) launch_dep(dep, k_fwd_step<32, FUSED>, grid, dim3(256), step_smem_fwd(32), st, fr, list, xw_off, xw, xy, sp, kind, ga);
+   else if (kbmax <= 64) launch_dep(dep, k_fwd_step<64, FUSED>, grid, dim3(256), step_smem_fwd(64), st, fr, list, xw_off, xw, xy, sp, kind, ga);
+   else launch_dep(dep, k_fwd_step<128, FUSED>, grid, dim3(256), step_smem_fwd(128), st, fr, list, xw_off, xw, xy, sp, kind, ga);
 }
 template <bool FUSED>
 static void launch_bwd_step(int kbmax, dim3 grid, cudaStream_t st, const FrontDev* fr, const int* list, const int64_t* xw_off, double* xw,
                             const int64_t* part_off, double* part, int* ticket, int sp, int kind, const GatherArgs& ga) {
-   if (kbmax <= 32) k_bwd_step<32, FUSED><<<grid, 256, step_smem_bwd(32), st>>>(fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
-   else if (kbmax <= 64) k_bwd_step<64, FUSED><<<grid, 256, step_smem_bwd(64), st>>>(fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
-   else k_bwd_step<128, FUSED><<<grid, 256, step_smem_bwd(128), st>>>(fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
+   const bool dep = FUSED && solve_pdl();
+   if (kbmax <= 32) launch_dep(dep, k_bwd_step<32, FUSED>, grid, dim3(256), step_smem_bwd(32), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
+   else if (kbmax <= 64) launch_dep(dep, k_bwd_step<64, FUSED>, grid, dim3(256), step_smem_bwd(64), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
+   else launch_dep(dep, k_bwd_step<128, FUSED>, grid, dim3(256), step_smem_bwd(128), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
 }
 static inline int step_slots(int kbmax, bool bwd) { return kbmax <= 64 ? (bwd ? 3 : 2) * 148 : 148; }
+
+// B200LDLT_SOLVE_TRACE: when each role of a chain launch started, had its inverses, saw its last dependency and published
+void Numeric::chain_trace(const char* what, int l, int nroles, int off) {
+   std::vector<unsigned long long> t(16 * (size_t)nroles);
+   std::vector<int2> rl(nroles);
+   cudaStreamSynchronize(st);
+   cudaMemcpy(t.data(), d_chain_dbg, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost);
+   cudaMemcpy(rl.data(), d_roles + off, sizeof(int2) * nroles, cudaMemcpyDeviceToHost);
+   unsigned long long t0 = ~0ULL, t3 = 0;
+   for (int i = 0; i < nroles; ++i) { t0 = std::min(t0, t[16 * i]); t3 = std::max(t3, t[16 * i + 3]); }
+   fprintf(stderr, "[b200ldlt] %s chain level %d: %d roles, %.1f us\n", what, l, nroles, (t3 - t0) * 1e-3);
+   if (nroles > 80) return;
+   const bool bwd = what[0] == 'b';
+   for (int i = 0; i < nroles; ++i) {
+      fprintf(stderr, "   cta %3d role (%d,%d): start %.1f inv %.1f deps %.1f done %.1f", i, rl[i].x, rl[i].y, (t[16 * i] - t0) * 1e-3,
+              (t[16 * i + 1] - t0) * 1e-3, (t[16 * i + 2] - t0) * 1e-3, (t[16 * i + 3] - t0) * 1e-3);
+      if (bwd) fprintf(stderr, "  reduced %.1f staged %.1f applied %.1f full %d", (t[16 * i + 4] - t0) * 1e-3, (t[16 * i + 5] - t0) * 1e-3,
+                       (t[16 * i + 6] - t0) * 1e-3, (int)t[16 * i + 7]);
+      if (bwd) { fprintf(stderr, "  warps"); for (int w = 0; w < 8; ++w) fprintf(stderr, " %.1f", (t[16 * i + 8 + w] - t0) * 1e-3); }
+      fprintf(stderr, "\n");
+   }
+}
 
 // forward sweep over the fronts of `kind` (-1: all)
 void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
@@ -2027,8 +2144,10 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
       k_fwd_gather<<<ns, lvl_maxm[l] > 1024 ? 1024 : 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xa, d_xp, s0, kind);
       ++nlaunch;
       if (roles_fwd_n[l] > 0) {
-         k_fwd_chain<<<roles_fwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_fwd_off[l], roles_fwd_n[l], d_chain_counter + 2 * l, d_xw_off,
-                                                               d_xw, d_cy, d_xp, posdef ? 1 : 0, kind, d_chain_err, use_solve_inv ? 1 : 0);
+         launch_dep(solve_pdl(), k_fwd_chain, dim3(roles_fwd_n[l]), dim3(256), chain_smem(), st, d_fr, d_roles + roles_fwd_off[l], roles_fwd_n[l],
+                    d_chain_counter + 2 * l, d_xw_off, d_xw, d_cy, d_xp, posdef ? 1 : 0, kind, d_chain_err, use_solve_inv,
+                    have_minv ? d_minv : nullptr, d_minv_off, d_mflag, d_chain_dbg);
+         if (d_chain_dbg) chain_trace("fwd", l, roles_fwd_n[l], roles_fwd_off[l]);
          ++nlaunch;
          continue;      // the owners stored their pivots themselves
       }
@@ -2065,8 +2184,14 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
          ++nlaunch;
       }
       if (roles_bwd_n[l] > 0) {
-         k_bwd_chain<<<roles_bwd_n[l], 256, chain_smem(), st>>>(d_fr, d_roles + roles_bwd_off[l], roles_bwd_n[l], d_chain_counter + 2 * l + 1, d_xw_off,
-                                                               d_xw, d_cy, d_xp, kind, d_chain_err, use_solve_inv ? 1 : 0);
+         if (have_tail && troles_n[l] > 0) {
+            k_bwd_tail<<<troles_n[l], 256, 0, st>>>(d_fr, d_troles + troles_off[l], d_xw_off, d_xw, d_tail, d_tail_off, kind);
+            ++nlaunch;
+         }
+         launch_dep(solve_pdl(), k_bwd_chain, dim3(roles_bwd_n[l]), dim3(256), chain_smem(), st, d_fr, d_roles + roles_bwd_off[l], roles_bwd_n[l],
+                    d_chain_counter + 2 * l + 1, d_xw_off, d_xw, d_cy, d_xp, kind, d_chain_err, use_solve_inv, have_minv ? d_minv : nullptr, d_minv_off,
+                    d_mflag, have_tail ? d_tail : nullptr, d_tail_off, d_chain_dbg);
+         if (d_chain_dbg) chain_trace("bwd", l, roles_bwd_n[l], roles_bwd_off[l]);
          ++nlaunch;
          continue;
       }

@@ -310,6 +310,11 @@ __device__ __forceinline__ void pdl_enter() {
    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// the two halves on their own (solve kernels): let the successor become resident at once, do everything that does not
+// depend on the predecessor (staging L), then wait
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int KIND>      // 0: blocks of <= 32 columns, 1: <= 64 columns (both two CTAs per SM), 2: up to 128 columns
 __global__ void __launch_bounds__(256, KIND < 2 ? 2 : 1) k_block(FrontDev* fr, const int* list, int slot0, Params prm, int finish_only,
                                                               int wcap, int par, int la) {

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(1024) k_fwd_gather(const FrontDev* __restrict_
                                                      const int* __restrict__ child_idx, const int* __restrict__ child_doff,
                                                      const int* __restrict__ rel, const int64_t* __restrict__ xw_off,
                                                      double* XW, double* XA, const double* __restrict__ x, int slot0, int kind) {
+   pdl_launch_dependents();
    const int s = slot0 + blockIdx.x;
    const FrontDev& f = fr[s];
    if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
@@ -279,6 +280,185 @@ __device__ __forceinline__ void smem_solve_lower_t_inv(const double* S, int sld,
    }
 }
 
+// ---- the whole 128 x 128 diagonal block through its inverse (chain kernels, use_inv = 2).  With the four sub-triangle
+// inverses in Inv, the blocks of M = inv(L_bb) below the diagonal replace those of L in S, block row by block row:
+//    T_j = sum_{k=j}^{i-1} L_ik M_kj,   M_ij = - M_ii T_j        (j < i; FP64 MMA, 8 x 8 tiles dealt to the warps)
+// Row i reads only L's blocks of row i and finished rows of M, so the update is in place.  The solve on the chain is then
+// ONE matrix-vector product (64 multiply-adds per thread, two threads per row) instead of four dependent sub-block steps.
+// Used only where it is harmless: every sub-triangle inverse within INV_MAX and every entry of M below the diagonal blocks
+// within INV_MAX_OFF; otherwise *flag128 = 0, the caller stages L again and keeps the sub-block path.
+constexpr int TLD = 33;
+constexpr double INV_MAX_OFF = 8.0;
+__device__ __forceinline__ void smem_invert_block128(double* S, int sld, const double* Inv, const int* iflag, double* T, int* flag128) {
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+   if (threadIdx.x == 0) *flag128 = (iflag[0] && iflag[1] && iflag[2] && iflag[3]) ? 1 : 0;
+   __syncthreads();
+   if (!*flag128) return;
+   double mx = 0.0;
+   for (int i = 1; i < 4; ++i) {
+      for (int tile = wid; tile < 16 * i; tile += 8) {
+         const int j = tile >> 4, tr = (tile >> 2) & 3, tc = tile & 3;
+         double c0 = 0.0, c1 = 0.0;
+         for (int k = j; k < i; ++k) {
+            const double* Lik = S + (size_t)(32 * k) * sld + 32 * i + 8 * tr + g;                   // (r, c) at c * sld + r
+            const double* Mkj = (k == j) ? Inv + j * 32 * ILD + 8 * tc + g                          // (r, c) at r * ILD + c
+                                         : S + (size_t)(32 * j + 8 * tc + g) * sld + 32 * k;
+            const int bstride = (k == j) ? ILD : 1;
+#pragma unroll
+            for (int ks = 0; ks < 32; ks += 4) dmma(c0, c1, Lik[(size_t)(ks + t4) * sld], Mkj[(ks + t4) * bstride]);
+         }
+         double* Tj = T + j * 32 * TLD + (8 * tr + g) * TLD + 8 * tc + 2 * t4;
+         Tj[0] = c0;
+         Tj[1] = c1;
+      }
+      __syncthreads();
+      for (int tile = wid; tile < 16 * i; tile += 8) {
+         const int j = tile >> 4, tr = (tile >> 2) & 3, tc = tile & 3;
+         double c0 = 0.0, c1 = 0.0;
+         const double* Mii = Inv + i * 32 * ILD + (8 * tr + g) * ILD;
+         const double* Tj = T + j * 32 * TLD + 8 * tc + g;
+#pragma unroll
+         for (int ks = 0; ks < 32; ks += 4) dmma(c0, c1, Mii[ks + t4], Tj[(ks + t4) * TLD]);
+         double* Mij = S + (size_t)(32 * j + 8 * tc + 2 * t4) * sld + 32 * i + 8 * tr + g;
+         Mij[0] = -c0;
+         Mij[sld] = -c1;
+         mx = fmax(mx, fmax(fabs(c0), fabs(c1)));
+         if (c0 != c0 || c1 != c1) mx = INFINITY;
+      }
+      __syncthreads();
+   }
+#pragma unroll
+   for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+   if (lane == 0 && !(mx <= INV_MAX_OFF)) *flag128 = 0;
+   __syncthreads();
+}
+
+// rows / columns kb..KB-1 of a short last block: zeros, so that the padded part of the inverse is the identity
+__device__ __forceinline__ void smem_pad_block128(double* S, int sld, int kb, double* Inv, int* iflag) {
+   for (int e = threadIdx.x; e < KB * KB; e += blockDim.x) {
+      const int c = e >> 7, r = e & (KB - 1);
+      if (r >= kb || c >= kb) S[c * sld + r] = 0.0;
+   }
+   // sub-triangles wholly behind kb are not visited by smem_invert_subtriangles
+   for (int w = (kb + 31) / 32; w < 4; ++w) {
+      for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) Inv[w * 32 * ILD + (e >> 5) * ILD + (e & 31)] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
+      if (threadIdx.x == 0) iflag[w] = 1;
+   }
+}
+
+// xs <- M xs (forward) with M = inv(L_bb) in S (block lower triangular, zeros above the diagonal of the diagonal blocks).
+// Thread (row r, half h) takes columns 16 h .. 16 h + 15 of every 32-block; part: 2 x KB doubles of scratch.
+__device__ __forceinline__ void smem_apply_inverse(const double* S, int sld, double* xs, double* part) {
+   const int r = threadIdx.x & (KB - 1), h = threadIdx.x >> 7, ib = r >> 5;
+   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+   for (int jb = 0; jb <= ib; ++jb) {
+      const double* Sr = S + (size_t)(32 * jb + 16 * h) * sld + r;
+      const double* xv = xs + 32 * jb + 16 * h;
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+         a0 += Sr[(size_t)c * sld] * xv[c]; a1 += Sr[(size_t)(c + 1) * sld] * xv[c + 1];
+         a2 += Sr[(size_t)(c + 2) * sld] * xv[c + 2]; a3 += Sr[(size_t)(c + 3) * sld] * xv[c + 3];
+      }
+   }
+   part[h * KB + r] = (a0 + a1) + (a2 + a3);
+   __syncthreads();
+   if (threadIdx.x < KB) xs[threadIdx.x] = part[threadIdx.x] + part[KB + threadIdx.x];
+}
+
+// xs <- M^T xs (backward): thread (column c, half h) takes rows 16 h .. 16 h + 15 of every 32-block at and below its own
+__device__ __forceinline__ void smem_apply_inverse_t(const double* S, int sld, double* xs, double* part) {
+   const int c = threadIdx.x & (KB - 1), h = threadIdx.x >> 7, cb = c >> 5;
+   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+   for (int ib = cb; ib < 4; ++ib) {
+      const double* Sc = S + (size_t)c * sld + 32 * ib + 16 * h;
+      const double* xv = xs + 32 * ib + 16 * h;
+#pragma unroll
+      for (int rr = 0; rr < 16; rr += 4) { a0 += Sc[rr] * xv[rr]; a1 += Sc[rr + 1] * xv[rr + 1]; a2 += Sc[rr + 2] * xv[rr + 2]; a3 += Sc[rr + 3] * xv[rr + 3]; }
+   }
+   part[h * KB + c] = (a0 + a1) + (a2 + a3);
+   __syncthreads();
+   if (threadIdx.x < KB) xs[threadIdx.x] = part[threadIdx.x] + part[KB + threadIdx.x];
+}
+
+// The inverses of the 128 x 128 diagonal blocks of the chain fronts, once per factorisation (first solve after it): one CTA
+// per block.  Minv: KB x KB doubles per block, column-major, block lower triangular with explicit zeros above the diagonal
+// of the 32 x 32 diagonal blocks (what stage_triangle copies); mflag = 0 where a bound failed (the chain keeps L there).
+__global__ void __launch_bounds__(256, 1) k_chain_inverses(const FrontDev* __restrict__ fr, const int2* __restrict__ blist, double* Minv,
+                                                           int* mflag) {
+   constexpr int SLD = KB + 1;
+   const int s = blist[blockIdx.x].x, c = blist[blockIdx.x].y;
+   const FrontDev& f = fr[s];
+   __shared__ int iflag[4];
+   __shared__ int flag128;
+   const int kb = f.state == 2 ? min(KB, f.nelim - c * KB) : 0;
+   if (kb <= 0) { if (threadIdx.x == 0) mflag[blockIdx.x] = 0; return; }
+   extern __shared__ double sm[];
+   double* S = sm;
+   double* Inv = S + KB * SLD;
+   double* T = Inv + 4 * 32 * ILD;
+   const size_t ldl = f.ldl;
+   stage_triangle(S, SLD, f.L + (size_t)(c * KB) * ldl + c * KB, ldl, kb);
+   cp_async_wait<0>();
+   __syncthreads();
+   if (kb < KB) { smem_pad_block128(S, SLD, kb, Inv, iflag); __syncthreads(); }
+   smem_invert_subtriangles(S, SLD, kb, Inv, iflag);
+   __syncthreads();
+   smem_invert_block128(S, SLD, Inv, iflag, T, &flag128);
+   if (threadIdx.x == 0) mflag[blockIdx.x] = flag128;
+   if (!flag128) return;
+   double* out = Minv + (size_t)blockIdx.x * KB * KB;
+   for (int e = threadIdx.x; e < KB * KB; e += blockDim.x) {
+      const int col = e >> 7, r = e & (KB - 1), cb = col >> 5, rb = r >> 5;
+      if (rb < cb) continue;
+      out[e] = rb == cb ? Inv[cb * 32 * ILD + (r & 31) * ILD + (col & 31)] : S[col * SLD + r];
+   }
+}
+static inline size_t chain_inv_smem() { return (size_t)(KB * (KB + 1) + 4 * 32 * ILD + 3 * 32 * TLD) * 8; }
+
+// Backward sweep, chain fronts: the rows below the pivots (the bulk of L's bytes in a front that is not a root) leave the
+// chain: CTA (front, column block c, chunk q of TAIL_ROWS rows) leaves sum_r L(r, col) x(r) over its rows for the 128
+// columns of the block in TAIL[tail_off + (q nb + c) KB + col]; the chain role subtracts the chunks in order.
+constexpr int TAIL_ROWS = 512;
+__global__ void __launch_bounds__(256) k_bwd_tail(const FrontDev* __restrict__ fr, const int4* __restrict__ troles, const int64_t* __restrict__ xw_off,
+                                                  const double* __restrict__ XW, double* TAIL, const int64_t* __restrict__ tail_off, int kind) {
+   pdl_launch_dependents();
+   const int4 tr = troles[blockIdx.x];
+   const int s = tr.x, c = tr.y, q = tr.z;
+   const FrontDev& f = fr[s];
+   if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
+   const int ne = f.nelim, m = f.m, nb = (ne + KB - 1) / KB;
+   const int cbase = c * KB, kb = min(KB, ne - cbase);
+   const int r0 = ne + q * TAIL_ROWS, r1 = min(m, r0 + TAIL_ROWS);
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const size_t ldl = f.ldl;
+   const double* __restrict__ xw = XW + xw_off[s];
+   const double* __restrict__ Lc = f.L + (size_t)(cbase + 16 * wid) * ldl;
+   double acc[16];
+#pragma unroll
+   for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+   for (int r = r0 + lane; r < r1; r += 64) {
+      const bool v1 = r + 32 < r1;
+      const double xa = xw[r], xb = v1 ? xw[r + 32] : 0.0;
+      double la[16], lb[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+         const bool cv = 16 * wid + j < kb;
+         la[j] = cv ? Lc[(size_t)j * ldl + r] : 0.0;
+         lb[j] = (cv && v1) ? Lc[(size_t)j * ldl + r + 32] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] += la[j] * xa + lb[j] * xb;
+   }
+   double* out = TAIL + tail_off[s] + ((size_t)q * nb + c) * KB + 16 * wid;
+#pragma unroll
+   for (int j = 0; j < 16; ++j) {
+      double a = acc[j];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (lane == 0) out[j] = a;
+   }
+}
+
 // Forward step for column block `step` of every front of the launch.  KBC = 32 / 64 / 128 bounds the block
 // width of the launch; a CTA covers RC = SE / KBC rows below the block, NG = 256 / RC threads per row.
 // The solved block goes to XY (the front's slice of the gather accumulators, dead by now), never back into
@@ -293,11 +473,12 @@ template <int KBC, bool FUSED>
 __global__ void __launch_bounds__(256, KBC <= 64 ? 2 : 1) k_fwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
                                                   const int64_t* __restrict__ xw_off, double* XW, double* XY, int step, int kind, GatherArgs ga) {
    constexpr int RC = SE / KBC, NG = 256 / RC, SLD = KBC + 1;
+   pdl_launch_dependents();
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
    if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const int ne = f.nelim, k0 = step * KB;
-   if (FUSED && ne == 0) { fwd_gather_front(fr, ga.ss, ga.child_idx, ga.child_doff, ga.rel, xw_off, XW, XY, ga.x, s); return; }
+   if (FUSED && ne == 0) { pdl_wait(); fwd_gather_front(fr, ga.ss, ga.child_idx, ga.child_doff, ga.rel, xw_off, XW, XY, ga.x, s); return; }
    if (k0 >= ne) return;
    const int kb = min(KB, ne - k0), m = f.m;
    const int nchunk = (m - (k0 + kb) + RC - 1) / RC;      // chunks of RC rows below the block; CTA y takes y, y + gridDim.y, ...
@@ -317,6 +498,7 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 2 : 1) k_fwd_step(const Front
    int r = k0 + kb + blockIdx.y * RC + rl;
 #pragma unroll
    for (int j = 0; j < KBC / NG; ++j) lreg[j] = (r < m && g * (KBC / NG) + j < kb) ? Lg[(size_t)j * ldl + r] : 0.0;
+   pdl_wait();       // the level before (a launch with programmatic serialisation starts while it is still running)
    if (FUSED) {      // the triangle and this thread's entries of L are on their way meanwhile
       fwd_gather_front(fr, ga.ss, ga.child_idx, ga.child_doff, ga.rel, xw_off, XW, XY, ga.x, s);
       __syncthreads();
@@ -399,13 +581,41 @@ __device__ __forceinline__ void cy_wait(double (&buf)[N], const double* p, int s
    }
 }
 
+// One warp polls 32 consecutive values (lane l: p[l]) with a single coalesced load per round and leaves them in shared
+// memory: the roles of a launch all wait for the same block, and 256 threads polling 32 values each from every CTA made
+// the few cache lines of CY the busiest spot of L2.
+__device__ __forceinline__ void cy_wait_warp(double* dst, const double* p, int nvalid, int* err) {
+   const int lane = threadIdx.x & 31;
+   long long t0 = 0;
+   double v;
+   for (;;) {
+      v = lane < nvalid ? cy_load(p + lane) : 0.0;
+      if (__all_sync(0xffffffffu, !cy_empty(v))) break;
+      if (t0 == 0) { if (*((volatile int*)err)) break; t0 = clock64(); }
+      else if (clock64() - t0 > 20000000000LL) { *err = 1; break; }
+   }
+   dst[lane] = v;
+}
+
+__device__ __forceinline__ unsigned long long chain_now() {
+   unsigned long long t;
+   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+   return t;
+}
+// dbg (B200LDLT_SOLVE_TRACE): per role {start, inverses done, last dependency arrived, published} in ns
+#define CHAIN_TICK(k) do { if (dbg && threadIdx.x == 0) dbg[16 * (size_t)ticket + (k)] = chain_now(); } while (0)
+
 __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
                                                       unsigned long long* counter, const int64_t* __restrict__ xw_off, double* XW,
-                                                      double* CY, double* x, int posdef_scale, int kind, int* err, int use_inv) {
+                                                      double* CY, double* x, int posdef_scale, int kind, int* err, int use_inv,
+                                                      const double* __restrict__ Minv, const int* __restrict__ minv_off,
+                                                      const int* __restrict__ mflag, unsigned long long* dbg) {
    constexpr int SLD = KB + 1;
    __shared__ int2 role;
    __shared__ int iflag[4];
-   if (threadIdx.x == 0) role = roles[(int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles)];
+   __shared__ int ticket;
+   pdl_launch_dependents();
+   if (threadIdx.x == 0) { ticket = (int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles); role = roles[ticket]; }
    __syncthreads();
    const int s = role.x, idx = role.y;
    const FrontDev& f = fr[s];
@@ -420,12 +630,21 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
    double* xs = sm + KB * SLD;        // KB
    double* red = xs + KB;             // 2 x CH
    double* Inv = red + 2 * CH + 32;   // 4 x 32 x ILD
+   double* ybuf = Inv + 4 * 32 * ILD + KB;  // 2 x KB: the published block, double buffered
+   double* part = ybuf + 2 * KB;            // 2 x KB
    double* xw = XW + xw_off[s];
    const double* cy = CY + xw_off[s];
    const size_t ldl = f.ldl;
-   if (owner) stage_triangle(S, SLD, f.L + (size_t)rbase * ldl + rbase, ldl, rend - rbase);
+   // the block's precomputed inverse (k_chain_inverses) where it exists and passed its bounds, else L itself
+   const int mq = (owner && use_inv > 1 && Minv != nullptr && minv_off[s] >= 0) ? minv_off[s] + idx : -1;
+   const bool full = mq >= 0 && mflag[mq] != 0;
+   if (owner) {
+      if (full) stage_triangle(S, SLD, Minv + (size_t)mq * KB * KB, KB, KB);
+      else stage_triangle(S, SLD, f.L + (size_t)rbase * ldl + rbase, ldl, rend - rbase);
+   }
    const int i = threadIdx.x & (CH - 1), g = threadIdx.x >> 7;      // row of the role, column half of a half block
    const bool rv = rbase + i < rend;
+   pdl_wait();       // the gather of this level
    const double x0 = (g == 0 && rv) ? xw[rbase + i] : 0.0;
    const double* __restrict__ Lr = f.L + rbase + i;
    double la[32], lb[32], yv[32], acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
@@ -443,19 +662,41 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
          acc0 += buf[j] * yv[j]; acc1 += buf[j + 1] * yv[j + 1]; acc2 += buf[j + 2] * yv[j + 2]; acc3 += buf[j + 3] * yv[j + 3];
       }
    };
+   CHAIN_TICK(0);
    if (nblk > 0) load_half(la, 0, 0);
-   if (owner && use_inv) {
+   if (owner && use_inv && !full) {
       // the sub-triangles' inverses while the blocks this role depends on are being solved elsewhere
       cp_async_wait<0>();
       __syncthreads();
       smem_invert_subtriangles(S, SLD, rend - rbase, Inv, iflag);
    }
-   for (int b = 0; b < nblk; ++b) {
-      load_half(lb, b, 1);
-      use_half(la, b, 0);
-      if (b + 1 < nblk) load_half(la, b + 1, 0);
-      use_half(lb, b, 1);
+   CHAIN_TICK(1);
+   if (use_inv > 1) {
+      const int wid = threadIdx.x >> 5;
+      for (int b = 0; b < nblk; ++b) {
+         load_half(lb, b, 1);
+         if (wid < 4) cy_wait_warp(ybuf + (b & 1) * KB + 32 * wid, cy + KB * b + 32 * wid, ne - (KB * b + 32 * wid), err);
+         __syncthreads();
+         const double* yb = ybuf + (b & 1) * KB + 32 * g;
+#pragma unroll
+         for (int j = 0; j < 32; j += 4) {
+            acc0 += la[j] * yb[j]; acc1 += la[j + 1] * yb[j + 1]; acc2 += la[j + 2] * yb[j + 2]; acc3 += la[j + 3] * yb[j + 3];
+         }
+         if (b + 1 < nblk) load_half(la, b + 1, 0);
+#pragma unroll
+         for (int j = 0; j < 32; j += 4) {
+            acc0 += lb[j] * yb[64 + j]; acc1 += lb[j + 1] * yb[64 + j + 1]; acc2 += lb[j + 2] * yb[64 + j + 2]; acc3 += lb[j + 3] * yb[64 + j + 3];
+         }
+      }
+   } else {
+      for (int b = 0; b < nblk; ++b) {
+         load_half(lb, b, 1);
+         use_half(la, b, 0);
+         if (b + 1 < nblk) load_half(la, b + 1, 0);
+         use_half(lb, b, 1);
+      }
    }
+   CHAIN_TICK(2);
    red[g * CH + i] = (acc0 + acc1) + (acc2 + acc3);
    __syncthreads();
    if (!owner) {
@@ -466,7 +707,8 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
    if (g == 0) xs[i] = rv ? x0 - (red[i] + red[CH + i]) : 0.0;
    cp_async_wait<0>();
    __syncthreads();
-   if (use_inv) smem_solve_lower_inv(S, SLD, kb, xs, Inv, iflag);
+   if (full) smem_apply_inverse(S, SLD, xs, part);
+   else if (use_inv) smem_solve_lower_inv(S, SLD, kb, xs, Inv, iflag);
    else smem_solve_lower(S, SLD, kb, xs);
    if (threadIdx.x < kb) {
       const double v = xs[threadIdx.x];
@@ -474,33 +716,51 @@ __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict
       // the solved pivots go straight into x (L_chol = L sqrt(D) for posdef; D is stored inverted)
       x[f.perm[rbase + threadIdx.x]] = posdef_scale ? v * sqrt(f.D[2 * (rbase + threadIdx.x)]) : v;
    }
+   CHAIN_TICK(3);
 }
 
 __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
                                                       unsigned long long* counter, const int64_t* __restrict__ xw_off, double* XW,
-                                                      double* CY, double* x, int kind, int* err, int use_inv) {
+                                                      double* CY, double* x, int kind, int* err, int use_inv,
+                                                      const double* __restrict__ Minv, const int* __restrict__ minv_off,
+                                                      const int* __restrict__ mflag, const double* __restrict__ TAIL,
+                                                      const int64_t* __restrict__ tail_off, unsigned long long* dbg) {
    constexpr int SLD = KB + 1;
    __shared__ int2 role;
    __shared__ int iflag[4];
-   if (threadIdx.x == 0) role = roles[(int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles)];
+   __shared__ int ticket;
+   pdl_launch_dependents();
+   if (threadIdx.x == 0) { ticket = (int)(atomicAdd(counter, 1ULL) % (unsigned long long)nroles); role = roles[ticket]; }
    __syncthreads();
    const int s = role.x, c = role.y;
    const FrontDev& f = fr[s];
    if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
    const int ne = f.nelim, m = f.m, nb = (ne + KB - 1) / KB;
    const int cbase = c * KB, kb = min(KB, ne - cbase);
-   const int ntail = (m - ne + CH - 1) / CH;
+   const int ntail = (TAIL != nullptr && tail_off[s] >= 0) ? 0 : (m - ne + CH - 1) / CH;
    extern __shared__ double sm[];
    double* S = sm;                    // KB x SLD
    double* xs = sm + KB * SLD;        // KB
    double* dots = xs + KB;            // 32 + KB
    double* Inv = dots + 32 + KB + 2 * KB;   // 4 x 32 x ILD (behind the forward kernel's layout: one size for both)
+   double* part = Inv + 4 * 32 * ILD;       // 2 x KB
    double* xw = XW + xw_off[s];
    const double* cy = CY + xw_off[s];
    const size_t ldl = f.ldl;
-   stage_triangle(S, SLD, f.L + (size_t)cbase * ldl + cbase, ldl, kb);
+   const int mq = (use_inv > 1 && Minv != nullptr && minv_off[s] >= 0) ? minv_off[s] + c : -1;
+   const bool full = mq >= 0 && mflag[mq] != 0;
+   if (full) stage_triangle(S, SLD, Minv + (size_t)mq * KB * KB, KB, KB);
+   else stage_triangle(S, SLD, f.L + (size_t)cbase * ldl + cbase, ldl, kb);
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-   const double x0 = threadIdx.x < kb ? xw[cbase + threadIdx.x] : 0.0;
+   // the rows below the pivots: partial sums of k_bwd_tail (chunks of TAIL_ROWS rows, added in chunk order), else by this role
+   const bool tailed = TAIL != nullptr && tail_off[s] >= 0;
+   pdl_wait();       // the gather (and the tail sums) of this level
+   double x0 = threadIdx.x < kb ? xw[cbase + threadIdx.x] : 0.0;
+   if (tailed && threadIdx.x < kb) {
+      const int ntc = (m - ne + TAIL_ROWS - 1) / TAIL_ROWS;
+      const double* tp = TAIL + tail_off[s] + cbase + threadIdx.x;
+      for (int q = 0; q < ntc; ++q) x0 -= tp[(size_t)q * nb * KB];
+   }
    // warp wid takes columns cbase + 16 wid + q; a half chunk is 64 rows: two loads per lane and column
    const double* __restrict__ Lc = f.L + (size_t)(cbase + 16 * wid) * ldl + lane;
    double va[16][2], vb[16][2], acc[16];
@@ -537,18 +797,50 @@ __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict
       for (int q = 0; q < 16; ++q) acc[q] += buf[q][0] * xv[0] + buf[q][1] * xv[1];
    };
    const int H = 2 * (ntail + nb - 1 - c);
+   CHAIN_TICK(0);
    if (H > 0) load_half(va, 0);
-   if (use_inv) {
+   if (use_inv && !full) {
       cp_async_wait<0>();
       __syncthreads();
       smem_invert_subtriangles(S, SLD, kb, Inv, iflag);
    }
-   for (int hh = 0; hh < H; hh += 2) {
-      load_half(vb, hh + 1);
-      use_half(va, hh);
-      if (hh + 2 < H) load_half(va, hh + 2);
-      use_half(vb, hh + 1);
+   CHAIN_TICK(1);
+   if (use_inv > 1) {
+      // one warp per 32 rows fetches (or waits for) the chunk's x into shared memory, one barrier per chunk of 128 rows
+      double* ybuf = part + 2 * KB;         // 2 x KB, double buffered
+      for (int k = 0; 2 * k < H; ++k) {
+         int r0, r1, b;
+         rows_of(2 * k, r0, r1, b);
+         load_half(vb, 2 * k + 1);
+         if (wid < 4) {
+            const int r = r0 + 32 * wid;
+            if (b >= 0) cy_wait_warp(ybuf + (k & 1) * KB + 32 * wid, cy + r, r1 - r, err);
+            else ybuf[(k & 1) * KB + 32 * wid + lane] = (r + lane < r1) ? xw[r + lane] : 0.0;
+         }
+         __syncthreads();
+         const double* yb = ybuf + (k & 1) * KB + lane;
+         {
+            const double y0 = yb[0], y1 = yb[32];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] += va[q][0] * y0 + va[q][1] * y1;
+         }
+         if (2 * k + 2 < H) load_half(va, 2 * k + 2);
+         {
+            const double y0 = yb[64], y1 = yb[96];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] += vb[q][0] * y0 + vb[q][1] * y1;
+         }
+      }
+   } else {
+      for (int hh = 0; hh < H; hh += 2) {
+         load_half(vb, hh + 1);
+         use_half(va, hh);
+         if (hh + 2 < H) load_half(va, hh + 2);
+         use_half(vb, hh + 1);
+      }
    }
+   CHAIN_TICK(2);
+   if (dbg && lane == 0) dbg[16 * (size_t)ticket + 8 + wid] = chain_now();
 #pragma unroll
    for (int q = 0; q < 16; ++q) {
       double a = acc[q];
@@ -557,15 +849,21 @@ __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict
       if (lane == 0) dots[32 + 16 * wid + q] = a;
    }
    __syncthreads();
+   CHAIN_TICK(4);
    if (threadIdx.x < KB) xs[threadIdx.x] = threadIdx.x < kb ? x0 - dots[32 + threadIdx.x] : 0.0;
    cp_async_wait<0>();
    __syncthreads();
-   if (use_inv) smem_solve_lower_t_inv(S, SLD, kb, xs, dots, Inv, iflag);
+   CHAIN_TICK(5);
+   if (full) smem_apply_inverse_t(S, SLD, xs, part);
+   else if (use_inv) smem_solve_lower_t_inv(S, SLD, kb, xs, dots, Inv, iflag);
    else smem_solve_lower_t(S, SLD, kb, xs, dots);
+   CHAIN_TICK(6);
+   if (threadIdx.x == 0 && dbg) dbg[16 * (size_t)ticket + 7] = (unsigned long long)(full ? 1 : 0);
    if (threadIdx.x < kb) {
       cy_store(CY + xw_off[s] + cbase + threadIdx.x, xs[threadIdx.x]);
       x[f.perm[cbase + threadIdx.x]] = xs[threadIdx.x];
    }
+   CHAIN_TICK(3);
 }
 
 // XY: the solved blocks (k_fwd_step)
@@ -627,6 +925,7 @@ __global__ void __launch_bounds__(256) k_bwd_gather(const FrontDev* __restrict__
                                                     const int* __restrict__ rlist, const int64_t* __restrict__ xw_off,
                                                     double* XW, const double* __restrict__ x, int slot0, int do_diag,
                                                     int posdef_scale, int kind) {
+   pdl_launch_dependents();
    const int s = slot0 + blockIdx.x;
    const FrontDev& f = fr[s];
    if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
@@ -642,6 +941,7 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const Front
                                                   const int64_t* __restrict__ xw_off, double* XW,
                                                   const int64_t* __restrict__ part_off, double* PART, int* ticket, int step, int kind, GatherArgs ga) {
    constexpr int RD = SE / KBC, CW = KBC / 8, RL = RD / 32, SLD = KBC + 1;
+   pdl_launch_dependents();
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
    if (f.state != 2 || (kind >= 0 && f.part_kind != kind)) return;
@@ -659,6 +959,15 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const Front
    double* part = PART + part_off[s];
    const size_t ldl = f.ldl;
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   if (FUSED) {
+      // this front's part of L towards L2 while the level before is still running
+      const int nlines = (m - k0 + 15) / 16;
+      for (int e = threadIdx.x; e < kb * nlines; e += 256) {
+         const int j = e / nlines, q = e - j * nlines;
+         asm volatile("prefetch.global.L2 [%0];" ::"l"(f.L + (size_t)(k0 + j) * ldl + min(k0 + 16 * q, m - 1)));
+      }
+   }
+   pdl_wait();
    if (FUSED) {
       bwd_gather_front(f, ga.rlist + ga.ss[s].rl_off, xw, ga.x, ga.do_diag, ga.posdef_scale, threadIdx.x, 256);
       __syncthreads();
