@@ -834,6 +834,18 @@ class Numeric {
    unsigned long long* d_chain_counter = nullptr;   // [2 * nlevels]
    int* d_chain_err = nullptr;
    unsigned long long* d_chain_dbg = nullptr;       // B200LDLT_SOLVE_TRACE: four time stamps per chain role
+   // B200LDLT_SOLVE_TIMELINE: an event after every launch of a solve, printed per launch at its end
+   bool solve_tl = getenv("B200LDLT_SOLVE_TIMELINE") != nullptr;
+   std::vector<cudaEvent_t> stl_ev;
+   std::vector<std::string> stl_name;
+   void smark(const char* what, int l) {
+      if (!solve_tl) return;
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, st);
+      stl_ev.push_back(e);
+      stl_name.push_back(std::string(what) + " " + std::to_string(l));
+   }
    // chain fronts: inverses of the 128 x 128 diagonal blocks (k_chain_inverses, once per factorisation) and the partial
    // sums of the rows below the pivots for the backward sweep (k_bwd_tail)
    double* d_minv = nullptr; size_t minv_cap = 0;   // blocks of KB x KB doubles
@@ -2139,16 +2151,19 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
          // every front of the level is one block and one CTA: gather, solve, update and store in one launch
          launch_fwd_step<true>(kb0, dim3(ns, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, 0, kind, ga);
          ++nlaunch;
+         smark("fwd_fused", l);
          continue;
       }
       k_fwd_gather<<<ns, lvl_maxm[l] > 1024 ? 1024 : 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xa, d_xp, s0, kind);
       ++nlaunch;
+      smark("k_fwd_gather", l);
       if (roles_fwd_n[l] > 0) {
          launch_dep(solve_pdl(), k_fwd_chain, dim3(roles_fwd_n[l]), dim3(256), chain_smem(), st, d_fr, d_roles + roles_fwd_off[l], roles_fwd_n[l],
                     d_chain_counter + 2 * l, d_xw_off, d_xw, d_cy, d_xp, posdef ? 1 : 0, kind, d_chain_err, use_solve_inv,
                     have_minv ? d_minv : nullptr, d_minv_off, d_mflag, d_chain_dbg);
          if (d_chain_dbg) chain_trace("fwd", l, roles_fwd_n[l], roles_fwd_off[l]);
          ++nlaunch;
+         smark("k_fwd_chain", l);
          continue;      // the owners stored their pivots themselves
       }
       for (int sp = 0; sp < lvl_steps[l]; ++sp) {
@@ -2160,9 +2175,11 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
          const int rc = SE / (kbmax <= 32 ? 32 : kbmax <= 64 ? 64 : 128);
          launch_fwd_step<false>(kbmax, dim3(na, step_grid_y(rows, rc, step_slots(kbmax, false), na)), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, sp, kind, ga);
          ++nlaunch;
+         smark("fwd_step", l);
       }
       k_fwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xa, d_xp, s0, posdef ? 1 : 0, kind);
       ++nlaunch;
+      smark("k_fwd_store", l);
    }
 }
 
@@ -2176,23 +2193,27 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
       if (use_fused && lvl_steps[l] == 1 && step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, true), ns) == 1) {
          launch_bwd_step<true>(kb0, dim3(lvl_nact[l][0], 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga);
          ++nlaunch;
+         smark("bwd_fused", l);
          continue;
       }
       {
          const int gy = std::max(1, std::min((lvl_maxm[l] + 255) / 256, 592 / ns));
          k_bwd_gather<<<dim3(ns, gy), 256, 0, st>>>(d_fr, P->d_ss, P->d_rlist, d_xw_off, d_xw, d_xp, s0, diag ? 1 : 0, posdef ? 1 : 0, kind);
          ++nlaunch;
+         smark("k_bwd_gather", l);
       }
       if (roles_bwd_n[l] > 0) {
          if (have_tail && troles_n[l] > 0) {
             k_bwd_tail<<<troles_n[l], 256, 0, st>>>(d_fr, d_troles + troles_off[l], d_xw_off, d_xw, d_tail, d_tail_off, kind);
             ++nlaunch;
+            smark("k_bwd_tail", l);
          }
          launch_dep(solve_pdl(), k_bwd_chain, dim3(roles_bwd_n[l]), dim3(256), chain_smem(), st, d_fr, d_roles + roles_bwd_off[l], roles_bwd_n[l],
                     d_chain_counter + 2 * l + 1, d_xw_off, d_xw, d_cy, d_xp, kind, d_chain_err, use_solve_inv, have_minv ? d_minv : nullptr, d_minv_off,
                     d_mflag, have_tail ? d_tail : nullptr, d_tail_off, d_chain_dbg);
          if (d_chain_dbg) chain_trace("bwd", l, roles_bwd_n[l], roles_bwd_off[l]);
          ++nlaunch;
+         smark("k_bwd_chain", l);
          continue;
       }
       for (int sp = lvl_steps[l] - 1; sp >= 0; --sp) {
@@ -2204,9 +2225,11 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
          launch_bwd_step<false>(kbmax, dim3(na, step_grid_y(rows, rd, step_slots(kbmax, true), na)), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part,
                                 d_ticket, sp, kind, ga);
          ++nlaunch;
+         smark("bwd_step", l);
       }
       k_bwd_store<<<ns, 256, 0, st>>>(d_fr, d_xw_off, d_xw, d_xp, s0, kind);
       ++nlaunch;
+      smark("k_bwd_store", l);
    }
 }
 
@@ -2255,6 +2278,18 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
    cudaEventElapsedTime(&ms, ev0, ev1);
    if (seconds) *seconds = ms * 1e-3;
    if (nl) *nl = nlaunch;
+   if (solve_tl && !stl_ev.empty()) {
+      cudaEvent_t prev = ev0;
+      for (size_t i = 0; i < stl_ev.size(); ++i) {
+         float d = 0;
+         cudaEventElapsedTime(&d, prev, stl_ev[i]);
+         fprintf(stderr, "[b200ldlt] solve %-22s %8.1f us\n", stl_name[i].c_str(), d * 1e3);
+         prev = stl_ev[i];
+      }
+      for (cudaEvent_t e : stl_ev) cudaEventDestroy(e);
+      stl_ev.clear();
+      stl_name.clear();
+   }
    return 0;
 }
 
