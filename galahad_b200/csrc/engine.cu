@@ -2003,8 +2003,10 @@ int Numeric::build_solve_tables() {
                   const int ne = hfr[s].state == 2 ? hfr[s].nelim : 0;
                   if (ne <= 0) continue;
                   const int nb = (ne + KB - 1) / KB, ntc = (hfr[s].m - ne + TAIL_ROWS - 1) / TAIL_ROWS;
-                  moff[s] = (int)blist.size();
-                  for (int c = 0; c < nb; ++c) blist.push_back(make_int2(s, c));
+                  if (nb > 1) {       // a single block is no chain: it keeps the sub-triangle path (and no 128 KB of inverse)
+                     moff[s] = (int)blist.size();
+                     for (int c = 0; c < nb; ++c) blist.push_back(make_int2(s, c));
+                  }
                   if (ntc > 0 && nb > 1) {
                      toff[s] = tail_total;
                      tail_total += (int64_t)ntc * nb * KB;
