@@ -868,6 +868,8 @@ class Numeric {
    // chain kernels of the solve: 0 substitution, 1 the 32 x 32 sub-triangles through their inverses, 2 the whole 128 x 128
    // diagonal block through its inverse and one warp polling per 32 published values
    int use_solve_inv = getenv("B200LDLT_SOLVE_INV") ? atoi(getenv("B200LDLT_SOLVE_INV")) : 2;
+   // fused levels of very small fronts (at most SMALL_T_MAXM rows) in CTAs of 64 threads
+   bool use_st64 = !(getenv("B200LDLT_SOLVE_T64") && atoi(getenv("B200LDLT_SOLVE_T64")) == 0);
    int* d_ticket = nullptr;         // per slot: arrival counter of the backward step's CTAs (left at zero by the last one)
    int* d_slist = nullptr;
    std::vector<int> slist, lvl_steps, lvl_maxm, lvl_maxne;
@@ -2099,20 +2101,33 @@ static inline bool solve_pdl() {
    static const bool on = !(getenv("B200LDLT_SOLVE_PDL") && atoi(getenv("B200LDLT_SOLVE_PDL")) == 0);
    return on;
 }
+// ST: the 64-thread instantiations, for FUSED levels whose fronts have at most SMALL_T_MAXM rows and 64 pivots (six CTAs per SM
+// instead of two: a level of thousands of tiny fronts is bound by how many of them are resident)
+constexpr int SMALL_T = 64, SMALL_T_MAXM = 96;
+static inline size_t step_smem_fwd_t(int kbc, int t) { return (size_t)(kbc * (kbc + 1) + kbc + t) * 8; }
+static inline size_t step_smem_bwd_t(int kbc, int t) { return (size_t)(kbc * (kbc + 1) + std::max(kbc, t * 32 / kbc) + 32) * 8; }
 template <bool FUSED>
 static void launch_fwd_step(int kbmax, dim3 grid, cudaStream_t st, const FrontDev* fr, const int* list, const int64_t* xw_off, double* xw,
-                            double* xy, int sp, int kind, const GatherArgs& ga) {
+                            double* xy, int sp, int kind, const GatherArgs& ga, bool st64 = false) {
    // levels of one launch each follow one another as programmatic dependents: the next level stages its L while this one runs
    const bool dep = FUSED && solve_pdl();
-   if (kbmax <= 32) launch_dep(dep, k_fwd_step<32, FUSED>, grid, dim3(256), step_smem_fwd(32), st, fr, list, xw_off, xw, xy, sp, kind, ga);
+   if (FUSED && st64 && kbmax <= 32)
+      launch_dep(dep, k_fwd_step<32, true, SMALL_T>, grid, dim3(SMALL_T), step_smem_fwd_t(32, SMALL_T), st, fr, list, xw_off, xw, xy, sp, kind, ga);
+   else if (FUSED && st64 && kbmax <= 64)
+      launch_dep(dep, k_fwd_step<64, true, SMALL_T>, grid, dim3(SMALL_T), step_smem_fwd_t(64, SMALL_T), st, fr, list, xw_off, xw, xy, sp, kind, ga);
+   else if (kbmax <= 32) launch_dep(dep, k_fwd_step<32, FUSED>, grid, dim3(256), step_smem_fwd(32), st, fr, list, xw_off, xw, xy, sp, kind, ga);
    else if (kbmax <= 64) launch_dep(dep, k_fwd_step<64, FUSED>, grid, dim3(256), step_smem_fwd(64), st, fr, list, xw_off, xw, xy, sp, kind, ga);
    else launch_dep(dep, k_fwd_step<128, FUSED>, grid, dim3(256), step_smem_fwd(128), st, fr, list, xw_off, xw, xy, sp, kind, ga);
 }
 template <bool FUSED>
 static void launch_bwd_step(int kbmax, dim3 grid, cudaStream_t st, const FrontDev* fr, const int* list, const int64_t* xw_off, double* xw,
-                            const int64_t* part_off, double* part, int* ticket, int sp, int kind, const GatherArgs& ga) {
+                            const int64_t* part_off, double* part, int* ticket, int sp, int kind, const GatherArgs& ga, bool st64 = false) {
    const bool dep = FUSED && solve_pdl();
-   if (kbmax <= 32) launch_dep(dep, k_bwd_step<32, FUSED>, grid, dim3(256), step_smem_bwd(32), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
+   if (FUSED && st64 && kbmax <= 32)
+      launch_dep(dep, k_bwd_step<32, true, SMALL_T>, grid, dim3(SMALL_T), step_smem_bwd_t(32, SMALL_T), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
+   else if (FUSED && st64 && kbmax <= 64)
+      launch_dep(dep, k_bwd_step<64, true, SMALL_T>, grid, dim3(SMALL_T), step_smem_bwd_t(64, SMALL_T), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
+   else if (kbmax <= 32) launch_dep(dep, k_bwd_step<32, FUSED>, grid, dim3(256), step_smem_bwd(32), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
    else if (kbmax <= 64) launch_dep(dep, k_bwd_step<64, FUSED>, grid, dim3(256), step_smem_bwd(64), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
    else launch_dep(dep, k_bwd_step<128, FUSED>, grid, dim3(256), step_smem_bwd(128), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
 }
@@ -2151,7 +2166,7 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
       const int kb0 = std::min(KB, lvl_maxne[l]), rows0 = lvl_steps[l] > 0 ? std::max(0, lvl_actm[l][0] - 1) : 0;
       if (use_fused && lvl_steps[l] == 1 && step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, false), ns) == 1) {
          // every front of the level is one block and one CTA: gather, solve, update and store in one launch
-         launch_fwd_step<true>(kb0, dim3(ns, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, 0, kind, ga);
+         launch_fwd_step<true>(kb0, dim3(ns, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, 0, kind, ga, use_st64 && lvl_maxm[l] <= SMALL_T_MAXM);
          ++nlaunch;
          smark("fwd_fused", l);
          continue;
@@ -2193,7 +2208,8 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
       if (ns == 0) continue;
       const int kb0 = std::min(KB, lvl_maxne[l]), rows0 = lvl_steps[l] > 0 ? std::max(0, lvl_actm[l][0] - 1) : 0;
       if (use_fused && lvl_steps[l] == 1 && step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, true), ns) == 1) {
-         launch_bwd_step<true>(kb0, dim3(lvl_nact[l][0], 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga);
+         launch_bwd_step<true>(kb0, dim3(lvl_nact[l][0], 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga,
+                               use_st64 && lvl_maxm[l] <= SMALL_T_MAXM);
          ++nlaunch;
          smark("bwd_fused", l);
          continue;

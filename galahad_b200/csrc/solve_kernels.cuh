@@ -469,10 +469,11 @@ struct GatherArgs {
    const SlotStatic* ss; const int* child_idx; const int* child_doff; const int* rel; const int* rlist;
    double* x; int posdef_scale, do_diag;
 };
-template <int KBC, bool FUSED>
-__global__ void __launch_bounds__(256, KBC <= 64 ? 2 : 1) k_fwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
+// T: threads per CTA (256; 64 for the FUSED levels of very small fronts, where six times as many fronts fit on an SM)
+template <int KBC, bool FUSED, int T = 256>
+__global__ void __launch_bounds__(T, T == 64 ? 6 : (KBC <= 64 ? 2 : 1)) k_fwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
                                                   const int64_t* __restrict__ xw_off, double* XW, double* XY, int step, int kind, GatherArgs ga) {
-   constexpr int RC = SE / KBC, NG = 256 / RC, SLD = KBC + 1;
+   constexpr int RC = T * 32 / KBC, NG = T / RC, SLD = KBC + 1;
    pdl_launch_dependents();
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 2 : 1) k_fwd_step(const Front
    extern __shared__ double sm[];
    double* S = sm;                    // KBC x SLD
    double* xs = sm + KBC * SLD;       // KBC
-   double* red = xs + KBC;            // 256
+   double* red = xs + KBC;            // T
    double* xw = XW + xw_off[s];
    const size_t ldl = f.ldl;
    const double* __restrict__ Lb = f.L + (size_t)k0 * ldl + k0;
@@ -503,15 +504,15 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 2 : 1) k_fwd_step(const Front
       fwd_gather_front(fr, ga.ss, ga.child_idx, ga.child_doff, ga.rel, xw_off, XW, XY, ga.x, s);
       __syncthreads();
    }
-   for (int i = threadIdx.x; i < KBC; i += 256) xs[i] = i < kb ? xw[k0 + i] : 0.0;
+   for (int i = threadIdx.x; i < KBC; i += T) xs[i] = i < kb ? xw[k0 + i] : 0.0;
    cp_async_wait<0>();
    __syncthreads();
    smem_solve_lower(S, SLD, kb, xs);
    if (FUSED) {
-      for (int i = threadIdx.x; i < kb; i += 256) ga.x[f.perm[i]] = ga.posdef_scale ? xs[i] * sqrt(f.D[2 * i]) : xs[i];
+      for (int i = threadIdx.x; i < kb; i += T) ga.x[f.perm[i]] = ga.posdef_scale ? xs[i] * sqrt(f.D[2 * i]) : xs[i];
    } else if (blockIdx.y == 0) {
       double* xy = XY + xw_off[s];
-      for (int i = threadIdx.x; i < kb; i += 256) xy[k0 + i] = xs[i];
+      for (int i = threadIdx.x; i < kb; i += T) xy[k0 + i] = xs[i];
    }
    double xg[KBC / NG];
 #pragma unroll
@@ -936,11 +937,11 @@ __global__ void __launch_bounds__(256) k_bwd_gather(const FrontDev* __restrict__
 // Backward step for column block `step`: PART[front][chunk][j] = sum_{r in chunk} L(r, k0+j) xw(r) by every CTA
 // (one warp per group of KBC / 8 columns, lanes down the rows), then the last CTA to arrive computes
 // x(block) = L(block,block)^{-T} (xw(block) - sum of the partials, in chunk order).
-template <int KBC, bool FUSED>
-__global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
+template <int KBC, bool FUSED, int T = 256>
+__global__ void __launch_bounds__(T, T == 64 ? 6 : (KBC <= 64 ? 3 : 1)) k_bwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
                                                   const int64_t* __restrict__ xw_off, double* XW,
                                                   const int64_t* __restrict__ part_off, double* PART, int* ticket, int step, int kind, GatherArgs ga) {
-   constexpr int RD = SE / KBC, CW = KBC / 8, RL = RD / 32, SLD = KBC + 1;
+   constexpr int RD = T * 32 / KBC, CW = KBC / (T / 32), RL = RD / 32, SLD = KBC + 1;
    pdl_launch_dependents();
    const int s = list[blockIdx.x];
    const FrontDev& f = fr[s];
@@ -962,14 +963,14 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const Front
    if (FUSED) {
       // this front's part of L towards L2 while the level before is still running
       const int nlines = (m - k0 + 15) / 16;
-      for (int e = threadIdx.x; e < kb * nlines; e += 256) {
+      for (int e = threadIdx.x; e < kb * nlines; e += T) {
          const int j = e / nlines, q = e - j * nlines;
          asm volatile("prefetch.global.L2 [%0];" ::"l"(f.L + (size_t)(k0 + j) * ldl + min(k0 + 16 * q, m - 1)));
       }
    }
    pdl_wait();
    if (FUSED) {
-      bwd_gather_front(f, ga.rlist + ga.ss[s].rl_off, xw, ga.x, ga.do_diag, ga.posdef_scale, threadIdx.x, 256);
+      bwd_gather_front(f, ga.rlist + ga.ss[s].rl_off, xw, ga.x, ga.do_diag, ga.posdef_scale, threadIdx.x, T);
       __syncthreads();
    }
    if (nchunk > 0) {
@@ -985,7 +986,7 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const Front
             for (int u = 0; u < RL; ++u) v[c][u] = (j < kb && r0 + lane + 32 * u < r1) ? col[lane + 32 * u] : 0.0;
          }
          __syncthreads();
-         for (int i = threadIdx.x; i < RD; i += 256) xs[i] = (r0 + i < r1) ? xw[r0 + i] : 0.0;
+         for (int i = threadIdx.x; i < RD; i += T) xs[i] = (r0 + i < r1) ? xw[r0 + i] : 0.0;
          __syncthreads();
          double* pc = part + (size_t)ch * KB;
 #pragma unroll
@@ -1014,7 +1015,7 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const Front
       }
    }
    stage_triangle(S, SLD, f.L + (size_t)k0 * ldl + k0, ldl, kb);
-   for (int i = threadIdx.x; i < kb; i += 256) {
+   for (int i = threadIdx.x; i < kb; i += T) {
       double vv = xw[k0 + i];
       for (int c = 0; c < nchunk; ++c) vv -= __ldcg(part + (size_t)c * KB + i);
       xs[i] = vv;
@@ -1022,8 +1023,8 @@ __global__ void __launch_bounds__(256, KBC <= 64 ? 3 : 1) k_bwd_step(const Front
    cp_async_wait<0>();
    __syncthreads();
    smem_solve_lower_t(S, SLD, kb, xs, dots);
-   if (FUSED) { for (int i = threadIdx.x; i < kb; i += 256) ga.x[f.perm[i]] = xs[i]; }
-   else for (int i = threadIdx.x; i < kb; i += 256) xw[k0 + i] = xs[i];
+   if (FUSED) { for (int i = threadIdx.x; i < kb; i += T) ga.x[f.perm[i]] = xs[i]; }
+   else for (int i = threadIdx.x; i < kb; i += T) xw[k0 + i] = xs[i];
 }
 
 __global__ void __launch_bounds__(256) k_bwd_store(const FrontDev* __restrict__ fr, const int64_t* __restrict__ xw_off,
