@@ -842,13 +842,20 @@ __global__ void __launch_bounds__(256, 1) k_bwd_chain(const FrontDev* __restrict
    }
    CHAIN_TICK(2);
    if (dbg && lane == 0) dbg[16 * (size_t)ticket + 8 + wid] = chain_now();
-#pragma unroll
-   for (int q = 0; q < 16; ++q) {
-      double a = acc[q];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-      if (lane == 0) dots[32 + 16 * wid + q] = a;
+   // transposing reduction of the 16 sums over the 32 lanes: each round halves the sums a lane carries (16 shuffles in all
+   // instead of 80); lanes 2 q and 2 q + 1 end with column q
+#define B200_FOLD(OFF, N)                                                                         \
+   {                                                                                              \
+      const bool up = (lane & (OFF)) != 0;                                                        \
+      _Pragma("unroll") for (int i = 0; i < (N); ++i) {                                           \
+         const double keep = up ? acc[i + (N)] : acc[i], send = up ? acc[i] : acc[i + (N)];       \
+         acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, (OFF));                               \
+      }                                                                                           \
    }
+   B200_FOLD(16, 8) B200_FOLD(8, 4) B200_FOLD(4, 2) B200_FOLD(2, 1)
+#undef B200_FOLD
+   acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+   if ((lane & 1) == 0) dots[32 + 16 * wid + (lane >> 1)] = acc[0];
    __syncthreads();
    CHAIN_TICK(4);
    if (threadIdx.x < KB) xs[threadIdx.x] = threadIdx.x < kb ? x0 - dots[32 + threadIdx.x] : 0.0;
