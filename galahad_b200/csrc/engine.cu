@@ -2043,8 +2043,9 @@ int Numeric::build_solve_tables() {
                if (!d_tail_off) CU(cudaMalloc(&d_tail_off, sizeof(int64_t) * std::max(nn, 1)));
                if (tail_cap < (size_t)tail_total) {
                   cudaFree(d_tail); d_tail = nullptr;
-                  CU(cudaMalloc(&d_tail, sizeof(double) * (size_t)tail_total));
-                  tail_cap = (size_t)tail_total;
+                  tail_cap = 0;
+                  if (cudaMalloc(&d_tail, sizeof(double) * (size_t)tail_total) == cudaSuccess) tail_cap = (size_t)tail_total;
+                  else { cudaGetLastError(); d_tail = nullptr; }      // no room: the chain roles sum their rows themselves
                }
                if (troles_cap < troles.size()) {
                   cudaFree(d_troles); d_troles = nullptr;
@@ -2053,7 +2054,7 @@ int Numeric::build_solve_tables() {
                }
                CU(cudaMemcpy(d_tail_off, toff.data(), sizeof(int64_t) * std::max(nn, 1), cudaMemcpyHostToDevice));
                CU(cudaMemcpy(d_troles, troles.data(), sizeof(int4) * troles.size(), cudaMemcpyHostToDevice));
-               have_tail = true;
+               have_tail = d_tail != nullptr;
             }
          }
       }
