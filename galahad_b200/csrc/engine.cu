@@ -2098,10 +2098,7 @@ int Numeric::solve_prepare() {
 }
 
 // launch helpers: instantiation by the widest block of the launch
-static inline bool solve_pdl() {
-   static const bool on = !(getenv("B200LDLT_SOLVE_PDL") && atoi(getenv("B200LDLT_SOLVE_PDL")) == 0);
-   return on;
-}
+static inline bool solve_pdl() { return !(getenv("B200LDLT_SOLVE_PDL") && atoi(getenv("B200LDLT_SOLVE_PDL")) == 0); }
 // ST: the 64-thread instantiations, for FUSED levels whose fronts have at most SMALL_T_MAXM rows and 64 pivots (six CTAs per SM
 // instead of two: a level of thousands of tiny fronts is bound by how many of them are resident)
 constexpr int SMALL_T = 64, SMALL_T_MAXM = 96;

@@ -203,6 +203,43 @@ def test_solve_block_boundaries_and_partial_jobs():
         assert np.array_equal(X[:, 2], x3), n
 
 
+@pytest.mark.parametrize("env", [{"B200LDLT_SOLVE_INV": "0"}, {"B200LDLT_SOLVE_INV": "1"}, {"B200LDLT_SOLVE_PDL": "0"},
+                                 {"B200LDLT_SOLVE_T64": "0"}, {"B200LDLT_SOLVE_INV_MB": "0"}, {"B200LDLT_CHAIN": "0"}],
+                         ids=lambda e: ",".join(f"{k[9:]}={v}" for k, v in e.items()))
+def test_solve_paths_agree(monkeypatch, env):
+    """The switchable paths of the solve (substitution / sub-triangle inverses / block inverses in the
+    chain kernels, no room for the block inverses, no programmatic dependent launches, 256-thread CTAs for tiny fronts, step
+    kernels instead of chains) against the default path: same problem, same right-hand side, solutions equal to rounding
+    and each backward stable.  A grid problem (small fronts, fused levels, chains with tails) and a dense indefinite front
+    with failed pivots (blocks whose inverses exceed their bounds)."""
+    probs = [("grid", None, P.kkt_grid_problem(14)), ("lap", None, P.laplace_problem(24))]
+    A, dp = P.dense_front_problem(1300, "indef", seed=7)
+    probs.append(("dense", A, dp))
+    ref = {}
+    for name, A, prob in probs:
+        s, flag = gpu_factor(prob)
+        assert flag >= 0
+        b = np.cos(np.arange(prob["n"]))
+        f, x = s.solve(b)
+        assert f == 0
+        ref[name] = (b, x)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for name, A, prob in probs:
+        s, flag = gpu_factor(prob)
+        assert flag >= 0
+        b, x0 = ref[name]
+        f, x = s.solve(b)
+        assert f == 0
+        if A is None:
+            assert P.backward_error(prob, x, b) <= 1e-14, name
+        else:
+            assert np.abs(A @ x - b).max() / (np.abs(A).sum(1).max() * np.abs(x).max() + np.abs(b).max()) <= 1e-13
+        assert np.abs(x - x0).max() <= 1e-9 * np.abs(x0).max(), (name, np.abs(x - x0).max())
+        f, x2 = s.solve(b)
+        assert np.array_equal(x, x2), name
+
+
 def test_c2_full_size_properties():
     """BASELINE configs[1] at full size (64^3 7-point Laplacian, n = 262 144): size-independent properties --
     SPD so no negative pivots and no delays, the posdef and the pivoted path agree, backward error <= 1e-14,
