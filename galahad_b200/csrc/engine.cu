@@ -834,6 +834,40 @@ class Numeric {
    unsigned long long* d_chain_counter = nullptr;   // [2 * nlevels]
    int* d_chain_err = nullptr;
    unsigned long long* d_chain_dbg = nullptr;       // B200LDLT_SOLVE_TRACE: four time stamps per chain role
+   // Several right-hand sides: the columns are solved on up to SOLVE_STREAMS streams at once, each with a set of solve
+   // workspaces of its own (the sweeps read the workspace pointers and the stream from the members below, which the host
+   // swaps between enqueues: a solve of one column is bound by dependent launches, not by the machine)
+   struct SolveWs {
+      cudaStream_t st = nullptr;
+      double *x = nullptr, *xp = nullptr, *xw = nullptr, *cy = nullptr, *part = nullptr, *tail = nullptr;
+      int* ticket = nullptr;
+      unsigned long long* counter = nullptr;
+      cudaEvent_t done = nullptr;
+   };
+   static constexpr int SOLVE_STREAMS = 4;
+   SolveWs extra_ws[SOLVE_STREAMS - 1];
+   int n_extra_ws = 0;
+   size_t extra_sig[6] = {0, 0, 0, 0, 0, 0};     // the capacities the extra sets were allocated for
+   cudaEvent_t ev_ws_fork = nullptr;
+   SolveWs current_ws() const {
+      SolveWs w;
+      w.st = st; w.x = d_x; w.xp = d_xp; w.xw = d_xw; w.cy = d_cy; w.part = d_part; w.tail = d_tail; w.ticket = d_ticket; w.counter = d_chain_counter;
+      return w;
+   }
+   void use_ws(const SolveWs& w) {
+      st = w.st; d_x = w.x; d_xp = w.xp; d_xw = w.xw; d_cy = w.cy; d_part = w.part; d_tail = w.tail; d_ticket = w.ticket; d_chain_counter = w.counter;
+   }
+   void free_extra_ws() {
+      for (int i = 0; i < n_extra_ws; ++i) {
+         SolveWs& w = extra_ws[i];
+         cudaFree(w.x); cudaFree(w.xp); cudaFree(w.xw); cudaFree(w.cy); cudaFree(w.part); cudaFree(w.tail); cudaFree(w.ticket); cudaFree(w.counter);
+         if (w.st) cudaStreamDestroy(w.st);
+         if (w.done) cudaEventDestroy(w.done);
+         w = SolveWs();
+      }
+      n_extra_ws = 0;
+   }
+   int ensure_extra_ws(int want);
    // B200LDLT_SOLVE_TIMELINE: an event after every launch of a solve, printed per launch at its end
    bool solve_tl = getenv("B200LDLT_SOLVE_TIMELINE") != nullptr;
    std::vector<cudaEvent_t> stl_ev;
@@ -936,6 +970,8 @@ class Numeric {
       cudaSetDevice(P->device);
       fac.release(); dar.release(); par.release(); car[0].release(); car[1].release(); war.release(); bar.release();
       cudaFree(d_fr); cudaFree(d_child_doff); cudaFree(d_list); cudaFree(d_collect); cudaFree(d_counters);
+      free_extra_ws();
+      if (ev_ws_fork) cudaEventDestroy(ev_ws_fork);
       cudaFree(d_root_mask); cudaFree(d_mine_mask); cudaFree(d_tileptr); cudaFree(d_xw_off); cudaFree(d_part_off); cudaFree(d_ticket); cudaFree(d_roles); cudaFree(d_cy); cudaFree(d_chain_counter); cudaFree(d_chain_err); cudaFree(d_chain_dbg); cudaFree(d_minv); cudaFree(d_minv_off); cudaFree(d_mflag); cudaFree(d_blist); cudaFree(d_tail); cudaFree(d_tail_off); cudaFree(d_troles); cudaFree(d_slist); cudaFree(d_scale); cudaFree(d_a_rowi); cudaFree(d_a_coli); cudaFree(d_um_rptr); cudaFree(d_um_rent); cudaFree(d_um_rcol); cudaFree(d_rb); cudaFree(d_rx); cudaFree(d_rr); cudaFree(d_rnorm);
       cudaFree(d_chg_idx); cudaFree(d_chg_val);
       cudaFree(d_part); cudaFree(d_val); cudaFree(d_uval); cudaFree(d_vm_src); cudaFree(d_vm_dst); cudaFree(d_vm_dup_dst); cudaFree(d_vm_dup_ptr); cudaFree(d_vm_dup_src); cudaFree(d_x); cudaFree(d_xp); cudaFree(d_xw);
@@ -2249,6 +2285,44 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
    }
 }
 
+// up to `want` extra sets of solve workspaces, as many as fit in a quarter of the free memory; returns how many there are
+int Numeric::ensure_extra_ws(int want) {
+   const int nn = P->nnodes;
+   const size_t sig[6] = {x_cap, xw_cap, cy_cap, part_cap, tail_cap, (size_t)nn};
+   bool same = true;
+   for (int i = 0; i < 6; ++i) same = same && sig[i] == extra_sig[i];
+   if (!same) free_extra_ws();
+   for (int i = 0; i < 6; ++i) extra_sig[i] = sig[i];
+   want = std::min(want, SOLVE_STREAMS - 1);
+   const size_t bytes = 8 * (2 * x_cap + xw_cap + cy_cap + part_cap + tail_cap) + 4 * (size_t)(nn + 1) + 16 * (size_t)(P->nlevels + 1) + 1024;
+   while (n_extra_ws < want) {
+      size_t fr_b = 0, tot_b = 0;
+      if (cudaMemGetInfo(&fr_b, &tot_b) != cudaSuccess || bytes > fr_b / 4) break;
+      SolveWs w;
+      bool ok = cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming) == cudaSuccess &&
+                cudaMalloc(&w.x, 8 * std::max<size_t>(x_cap, 1)) == cudaSuccess && cudaMalloc(&w.xp, 8 * std::max<size_t>(x_cap, 1)) == cudaSuccess &&
+                cudaMalloc(&w.xw, 8 * std::max<size_t>(xw_cap, 1)) == cudaSuccess && cudaMalloc(&w.cy, 8 * std::max<size_t>(cy_cap, 1)) == cudaSuccess &&
+                cudaMalloc(&w.part, 8 * std::max<size_t>(part_cap, 1)) == cudaSuccess && cudaMalloc(&w.tail, 8 * std::max<size_t>(tail_cap, 1)) == cudaSuccess &&
+                cudaMalloc(&w.ticket, 4 * (size_t)(nn + 1)) == cudaSuccess &&
+                cudaMalloc(&w.counter, sizeof(unsigned long long) * 2 * (P->nlevels + 1)) == cudaSuccess;
+      if (ok) ok = cudaMemset(w.ticket, 0, 4 * (size_t)(nn + 1)) == cudaSuccess &&
+                   cudaMemset(w.counter, 0, sizeof(unsigned long long) * 2 * (P->nlevels + 1)) == cudaSuccess;
+      extra_ws[n_extra_ws++] = w;
+      if (!ok) {           // out of memory half way: give this set back, keep the ones before it
+         cudaGetLastError();
+         SolveWs& b = extra_ws[n_extra_ws - 1];
+         cudaFree(b.x); cudaFree(b.xp); cudaFree(b.xw); cudaFree(b.cy); cudaFree(b.part); cudaFree(b.tail); cudaFree(b.ticket); cudaFree(b.counter);
+         if (b.st) cudaStreamDestroy(b.st);
+         if (b.done) cudaEventDestroy(b.done);
+         b = SolveWs();
+         --n_extra_ws;
+         break;
+      }
+   }
+   return std::min(n_extra_ws, want);
+}
+
 int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double* seconds, int64_t* nl) {
    if (!have) return SSIDS_ERROR_CALL_SEQUENCE;
    if (job < 0 || job > 4) return SSIDS_ERROR_JOB_OOR;
@@ -2262,21 +2336,51 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
    if (rc) return rc;
    CU(cudaEventRecord(ev0, st));
    const int nb = (n + 255) / 256;
-   for (int j = 0; j < nrhs; ++j) {
-      double* xj = x + (size_t)j * ldx;
-      double* dx = d_x;
-      if (on_device) dx = xj;
-      else CU(cudaMemcpyAsync(d_x, xj, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-      if (n > 0) { k_permute_in<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, (scaled && (job == 0 || job == 1)) ? d_scale : nullptr, n); ++nlaunch; }
-      const bool fwd = (job == 0 || job == 1), bwd = (job == 0 || job == 3 || job == 4);
-      const bool diag = !posdef && (job == 0 || job == 2 || job == 4);
-      // posdef: LL^T semantics with L_chol = L sqrt(D); sqrt(D^-1) is folded into each sweep so
-      // that the partial solves match SSIDS's posdef jobs
-      if (fwd) sweep_fwd(-1, nlaunch);
-      if (diag && !bwd && nn > 0) { k_solve_diag<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, d_xp, nn); ++nlaunch; }
-      if (bwd) sweep_bwd(-1, diag, nlaunch);
-      if (n > 0) { k_permute_out<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, (scaled && (job == 0 || job == 3 || job == 4)) ? d_scale : nullptr, n); ++nlaunch; }
-      if (!on_device) CU(cudaMemcpyAsync(xj, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+   // columns j, j + nws, ... on workspace set j mod nws (set 0 = the members, on the engine's stream)
+   const int max_streams = getenv("B200LDLT_SOLVE_STREAMS") ? std::max(1, atoi(getenv("B200LDLT_SOLVE_STREAMS"))) : SOLVE_STREAMS;
+   const SolveWs main_ws = current_ws();
+   int nws = 1;
+   if (nrhs > 1 && max_streams > 1 && nranks <= 1 && !solve_tl && !d_chain_dbg) nws = 1 + ensure_extra_ws(std::min(nrhs, max_streams) - 1);
+   if (nws > 1) {
+      if (!ev_ws_fork) CU(cudaEventCreateWithFlags(&ev_ws_fork, cudaEventDisableTiming));
+      CU(cudaEventRecord(ev_ws_fork, st));
+      for (int w = 0; w + 1 < nws; ++w) {
+         CU(cudaStreamWaitEvent(extra_ws[w].st, ev_ws_fork, 0));
+         // the ticket counters count modulo the roles of a level, which a new factorisation may have changed
+         CU(cudaMemsetAsync(extra_ws[w].counter, 0, sizeof(unsigned long long) * 2 * (P->nlevels + 1), extra_ws[w].st));
+      }
+   }
+   // groups of nws columns: everything of a group is enqueued before its results are copied back, because a copy to
+   // pageable host memory holds the host until the column's stream has drained
+   for (int j0 = 0; j0 < nrhs; j0 += nws) {
+      for (int j = j0; j < std::min(nrhs, j0 + nws); ++j) {
+         if (nws > 1) use_ws(j % nws == 0 ? main_ws : extra_ws[j % nws - 1]);
+         double* xj = x + (size_t)j * ldx;
+         double* dx = d_x;
+         if (on_device) dx = xj;
+         else CU(cudaMemcpyAsync(d_x, xj, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+         if (n > 0) { k_permute_in<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, (scaled && (job == 0 || job == 1)) ? d_scale : nullptr, n); ++nlaunch; }
+         const bool fwd = (job == 0 || job == 1), bwd = (job == 0 || job == 3 || job == 4);
+         const bool diag = !posdef && (job == 0 || job == 2 || job == 4);
+         // posdef: LL^T semantics with L_chol = L sqrt(D); sqrt(D^-1) is folded into each sweep so
+         // that the partial solves match SSIDS's posdef jobs
+         if (fwd) sweep_fwd(-1, nlaunch);
+         if (diag && !bwd && nn > 0) { k_solve_diag<<<(nn + 7) / 8, 256, 0, st>>>(d_fr, d_xp, nn); ++nlaunch; }
+         if (bwd) sweep_bwd(-1, diag, nlaunch);
+         if (n > 0) { k_permute_out<<<nb, 256, 0, st>>>(dx, d_xp, P->d_order, (scaled && (job == 0 || job == 3 || job == 4)) ? d_scale : nullptr, n); ++nlaunch; }
+      }
+      if (!on_device)
+         for (int j = j0; j < std::min(nrhs, j0 + nws); ++j) {
+            if (nws > 1) use_ws(j % nws == 0 ? main_ws : extra_ws[j % nws - 1]);
+            CU(cudaMemcpyAsync(x + (size_t)j * ldx, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+         }
+   }
+   if (nws > 1) {
+      use_ws(main_ws);
+      for (int w = 0; w + 1 < nws; ++w) {
+         CU(cudaEventRecord(extra_ws[w].done, extra_ws[w].st));
+         CU(cudaStreamWaitEvent(st, extra_ws[w].done, 0));
+      }
    }
    CU(cudaEventRecord(ev1, st));
    pin_i[pin_i_cap - 1] = 0;
