@@ -2045,7 +2045,9 @@ int Numeric::build_solve_tables() {
                      moff[s] = (int)blist.size();
                      for (int c = 0; c < nb; ++c) blist.push_back(make_int2(s, c));
                   }
-                  if (ntc > 0 && nb > 1) {
+                  // (a single block is worth the extra launch's partial sums only if its rows are many: the role would
+                  // stream them alone, 20 MB through one SM for a 128-column front of 20 000 rows)
+                  if (ntc > 0 && (nb > 1 || ntc >= 4)) {
                      toff[s] = tail_total;
                      tail_total += (int64_t)ntc * nb * KB;
                      for (int c = nb - 1; c >= 0; --c)
