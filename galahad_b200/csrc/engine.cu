@@ -904,6 +904,8 @@ class Numeric {
    int use_solve_inv = getenv("B200LDLT_SOLVE_INV") ? atoi(getenv("B200LDLT_SOLVE_INV")) : 2;
    // fused levels of very small fronts (at most SMALL_T_MAXM rows) in CTAs of 64 threads
    bool use_st64 = !(getenv("B200LDLT_SOLVE_T64") && atoi(getenv("B200LDLT_SOLVE_T64")) == 0);
+   // levels with a front of this many rows go through the chain kernels whatever their pivot counts
+   int chain_tall_m = getenv("B200LDLT_CHAIN_TALL") ? atoi(getenv("B200LDLT_CHAIN_TALL")) : 4096;
    int* d_ticket = nullptr;         // per slot: arrival counter of the backward step's CTAs (left at zero by the last one)
    int* d_slist = nullptr;
    std::vector<int> slist, lvl_steps, lvl_maxm, lvl_maxne;
@@ -1994,7 +1996,9 @@ int Numeric::build_solve_tables() {
          roles_fwd_off.assign(P->nlevels, 0); roles_bwd_off.assign(P->nlevels, 0);
          roles_fwd_n.assign(P->nlevels, 0); roles_bwd_n.assign(P->nlevels, 0);
          for (int l = 0; l < P->nlevels; ++l) {
-            if (!use_chain || lvl_maxne[l] <= KB) continue;
+            // ... and for the levels with a tall front (one block of pivots over thousands of rows, the separator chains of a
+            // KKT order): a level launch gives such a front one CTA, which then streams megabytes of L alone
+            if (!use_chain || (lvl_maxne[l] <= KB && lvl_maxm[l] < chain_tall_m)) continue;
             const int a0 = P->lvl_ptr[l], a1 = P->lvl_ptr[l + 1];
             auto ne_of = [&](int s) { return hfr[s].state == 2 ? hfr[s].nelim : 0; };
             int maxr = 0;
@@ -2200,7 +2204,8 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
       const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
       if (ns == 0) continue;
       const int kb0 = std::min(KB, lvl_maxne[l]), rows0 = lvl_steps[l] > 0 ? std::max(0, lvl_actm[l][0] - 1) : 0;
-      if (use_fused && lvl_steps[l] == 1 && step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, false), ns) == 1) {
+      if (use_fused && roles_fwd_n[l] == 0 && lvl_steps[l] == 1 &&
+          step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, false), ns) == 1) {
          // every front of the level is one block and one CTA: gather, solve, update and store in one launch
          launch_fwd_step<true>(kb0, dim3(ns, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, 0, kind, ga, use_st64 && lvl_maxm[l] <= SMALL_T_MAXM);
          ++nlaunch;
@@ -2243,7 +2248,8 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
       const int s0 = P->lvl_ptr[l], ns = P->lvl_ptr[l + 1] - s0;
       if (ns == 0) continue;
       const int kb0 = std::min(KB, lvl_maxne[l]), rows0 = lvl_steps[l] > 0 ? std::max(0, lvl_actm[l][0] - 1) : 0;
-      if (use_fused && lvl_steps[l] == 1 && step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, true), ns) == 1) {
+      if (use_fused && roles_bwd_n[l] == 0 && lvl_steps[l] == 1 &&
+          step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, true), ns) == 1) {
          launch_bwd_step<true>(kb0, dim3(lvl_nact[l][0], 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga,
                                use_st64 && lvl_maxm[l] <= SMALL_T_MAXM);
          ++nlaunch;
