@@ -47,8 +47,11 @@ __device__ __forceinline__ void fwd_gather_front(const FrontDev* __restrict__ fr
    double* acc = XA + xw_off[s];   // indexed by the parent's ASSEMBLY order
    const int m = f.m, ne = f.nelim;
    const bool has_children = st.child_end > st.child_begin;
+   // four rows per thread and round, the loads of a round issued together: a tall front (thousands of rows, one CTA) is bound
+   // by the latency of these dependent loads, not by their number
+   const int nt = blockDim.x;
    if (has_children) {
-      for (int r = threadIdx.x; r < m; r += blockDim.x) acc[r] = 0.0;
+      for (int r = threadIdx.x; r < m; r += nt) acc[r] = 0.0;
       __syncthreads();
       for (int ci = st.child_begin; ci < st.child_end; ++ci) {
          const int cs = child_idx[ci];
@@ -56,20 +59,47 @@ __device__ __forceinline__ void fwd_gather_front(const FrontDev* __restrict__ fr
          const int t = fc.m - fc.nelim, nd = fc.n - fc.nelim, doff = child_doff[ci];
          const double* xc = XW + xw_off[cs] + fc.nelim;
          const int* relc = rel + ss[cs].rel_off;
-         for (int rr = threadIdx.x; rr < t; rr += blockDim.x) {
-            int d;
-            if (rr < nd) d = f.ncol + doff + rr;
-            else { d = relc[rr - nd]; if (d >= f.ncol) d += f.ndelay_in; }
-            acc[d] += xc[rr];
+         for (int r0 = threadIdx.x; r0 < t; r0 += 4 * nt) {
+            int d[4];
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+               const int rr = r0 + u * nt;
+               d[u] = (rr < t && rr >= nd) ? relc[rr - nd] : 0;
+               v[u] = rr < t ? xc[rr] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+               const int rr = r0 + u * nt;
+               if (rr < t) {
+                  int dd = d[u];
+                  if (rr < nd) dd = f.ncol + doff + rr;
+                  else if (dd >= f.ncol) dd += f.ndelay_in;
+                  acc[dd] += v[u];
+               }
+            }
          }
          __syncthreads();
       }
    }
    // pivoting permuted the candidate rows after assembly: orig[] maps them back
-   for (int r = threadIdx.x; r < m; r += blockDim.x) {
-      double v = r < ne ? x[f.perm[r]] : 0.0;
-      if (has_children) v += acc[r < f.n ? f.orig[r] : r];
-      xw[r] = v;
+   const int fn = f.n;
+   for (int r0 = threadIdx.x; r0 < m; r0 += 4 * nt) {
+      int pi[4], oi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+         const int r = r0 + u * nt;
+         pi[u] = r < ne ? f.perm[r] : -1;
+         oi[u] = (has_children && r < fn) ? f.orig[r] : r;
+      }
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = pi[u] >= 0 ? x[pi[u]] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+         const int r = r0 + u * nt;
+         if (r < m) xw[r] = has_children ? v[u] + acc[oi[u]] : v[u];
+      }
    }
 }
 
@@ -912,10 +942,20 @@ __global__ void k_solve_diag(const FrontDev* __restrict__ fr, double* x, int nsl
 __device__ __forceinline__ void bwd_gather_front(const FrontDev& f, const int* __restrict__ rl, double* xw, const double* __restrict__ x,
                                                  int do_diag, int posdef_scale, int rfirst, int rstride) {
    const int m = f.m, ne = f.nelim;
-   for (int r = rfirst; r < m; r += rstride) {
+   // the rows below the pivots four at a time (index loads, then value loads), the pivots one by one
+   for (int r0 = ne + rfirst; r0 < m; r0 += 4 * rstride) {
+      int gi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int r = r0 + u * rstride; gi[u] = r < m ? row_gidx(f, rl, r) : -1; }
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = gi[u] >= 0 ? x[gi[u]] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int r = r0 + u * rstride; if (r < m) xw[r] = v[u]; }
+   }
+   for (int r = rfirst; r < ne; r += rstride) {
       double v;
-      if (r >= ne) v = x[row_gidx(f, rl, r)];
-      else {
+      {
          v = x[f.perm[r]];
          if (posdef_scale) v *= sqrt(f.D[2 * r]);
          else if (do_diag) {
