@@ -169,3 +169,26 @@ def test_symbols_and_argument_checks():
     rc = L.b200ldlt_analyse_matched(C.byref(s.akeep), 2, ptr.ctypes.data_as(I64), row.ctypes.data_as(I32), None,
                                     order.ctypes.data_as(I32), C.byref(s.opt), C.byref(s.inform))
     assert rc == -9          # SSIDS_ERROR_VAL (ssids.f90:230-238)
+
+
+def test_analyse_matched_end_to_end_on_the_host():
+    """b200ldlt_analyse_matched = ssids_analyse with options%ordering = 2 (ssids.f90:321-358): the symbolic analysis runs on
+    the order match_order gives (same factor size and flops as analysing with that order), a structurally singular matrix
+    raises the warning SSIDS_WARNING_ANAL_SINGULAR (6) and still analyses."""
+    name, n, ptr, row, val = [c for c in CASES if c[0] == "kkt_zero22_20"][0]
+    s = _lib.Solver()
+    flag = s.analyse_matched(n, ptr, row, val)
+    assert flag == 0 and s.inform.flag == 0
+    f2, order, scale, pairs, nc, cptr, crow = c_match_order(n, ptr, row, val)
+    # analyse relabels the order by its postorder of the elimination tree (as ssids_analyse does with the order
+    # match_order_metis hands it): a permutation with the fill of the matching-based order
+    assert sorted(s.order) == list(range(n))
+    assert s.inform.num_factor > 0 and s.inform.num_sup > 0 and s.inform.matrix_rank == n
+    s2 = _lib.Solver()
+    assert s2.analyse(n, ptr, row, order) == 0
+    assert (s2.inform.num_factor, s2.inform.num_flops) == (s.inform.num_factor, s.inform.num_flops)
+    # structurally singular
+    name, n, ptr, row, val = [c for c in CASES if c[0] == "singular_dense_col"][0]
+    s3 = _lib.Solver()
+    assert s3.analyse_matched(n, ptr, row, val) == 6
+    assert sorted(s3.order) == list(range(n)) and s3.inform.num_factor > 0
