@@ -118,7 +118,8 @@ int b200ldlt_order(int n, const int64_t *ptr, const int *row, int kind, int *ord
  * match_order_metis, src/spral/match_order.f90:135-208).  A maximum-product matching of |a_ij| (the Hungarian algorithm
  * of the scaling) is split into singletons and pairs, each pair becomes one vertex of a compressed graph, the compressed
  * graph is ordered by nested dissection (this library's, where the reference calls METIS) and each pair takes two
- * consecutive places of the pivot order; the matching's scaling is kept in akeep for b200ldlt_factor_scaled with
+ * consecutive places of the order handed to the symbolic analysis (whose postorder of the elimination tree, as in
+ * ssids_analyse, is what `order` returns); the matching's scaling is kept in akeep for b200ldlt_factor_scaled with
  * scaling 3.  val[] aligned with ptr / row (host).  order[n]: out.  Flag 6 (SSIDS_WARNING_ANAL_SINGULAR) when the
  * matrix is structurally singular, -9 (SSIDS_ERROR_VAL) without val.
  * b200ldlt_match_order: the order alone on 0-based arrays; kind 1 orders the compressed graph by minimum degree, else
