@@ -10,6 +10,10 @@
 //   backward (k_bwd_step): every CTA forms the partial dot products of its chunk of rows with the block's
 //            columns; the CTA that finishes last (ticket counter) sums the partials in chunk order and solves
 //            the transposed triangle.
+// Levels with fronts of more than KB pivots (or with one very tall front) take the chain kernels further down instead: one
+// launch per level and direction, the blocks of a front passed from CTA to CTA through global memory, the diagonal blocks
+// through inverses computed once per factorisation (k_chain_inverses), the rows below the pivots of the backward sweep
+// in k_bwd_tail (profiles/r2_notes.md part 7).  Consecutive launches overlap as programmatic dependents (pdl_*).
 // Everything here is bound by memory latency, not bandwidth (ncu launch list, profiles/r1_notes.md part 3):
 // each thread therefore has all of its loads (32 per thread) in flight at once, and dependent work runs from
 // shared memory.  No floating-point atomics: children's contributions are gathered by the parent in child
@@ -633,7 +637,8 @@ __device__ __forceinline__ unsigned long long chain_now() {
    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
    return t;
 }
-// dbg (B200LDLT_SOLVE_TRACE): per role {start, inverses done, last dependency arrived, published} in ns
+// dbg (B200LDLT_SOLVE_TRACE), 16 slots per role: {start, block staged / sub-inverses done, last dependency arrived, published;
+// backward: reduced, staged, applied, whether the block inverse was used, loop exit of each warp} in ns
 #define CHAIN_TICK(k) do { if (dbg && threadIdx.x == 0) dbg[16 * (size_t)ticket + (k)] = chain_now(); } while (0)
 
 __global__ void __launch_bounds__(256, 1) k_fwd_chain(const FrontDev* __restrict__ fr, const int2* __restrict__ roles, int nroles,
