@@ -127,3 +127,46 @@ def test_structural_invariants_on_a_larger_grid():
     m = np.diff(rptr) - np.diff(sptr)
     k = np.diff(sptr)
     assert a["num_factor"] == int((k * (k + 1) // 2 + k * m).sum())
+
+
+def random_pattern(seed):
+    """Small random symmetric patterns: sparse to dense, random user orders, null columns, disconnected components."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 60))
+    dens = [0.03, 0.08, 0.2, 0.6][seed % 4]
+    M = np.tril(rng.random((n, n)) < dens, -1)
+    if seed % 5 == 0 and n > 6:                       # two components and a few variables without any entry
+        h = n // 2
+        M[h:, :h] = False
+    diag = np.ones(n, bool)
+    null = np.zeros(n, bool)
+    if seed % 7 == 0 and n > 4:
+        null[rng.choice(n, size=2, replace=False)] = True
+        M[null, :] = False
+        M[:, null] = False
+        diag[null] = False
+    ptr, row = [0], []
+    for c in range(n):
+        if diag[c]:
+            row.append(c)
+        row.extend(int(r) for r in np.nonzero(M[:, c])[0])
+        ptr.append(len(row))
+    order = rng.permutation(n).astype(np.int32) if seed % 3 else np.arange(n, dtype=np.int32)
+    nemin = int([1, 2, 8, 32][(seed // 4) % 4])
+    return dict(n=n, ptr=np.array(ptr, np.int64), row=np.array(row, np.int32), val=np.ones(len(row)), order=order), nemin
+
+
+@pytest.mark.parametrize("chunk", range(6))
+def test_random_patterns_entry_by_entry(chunk):
+    """A sweep of 180 random patterns / orders / nemin values beside the fixed cases: every integer output equal."""
+    for seed in range(chunk, 180, 6):
+        prob, nemin = random_pattern(seed)
+        a = product_arrays(prob, nemin)
+        b = oracle_arrays(prob, nemin)
+        # basic_analyse's warning 1 (structurally singular, core_analyse.f90) is SSIDS_WARNING_ANAL_SINGULAR (6) once
+        # analyse_phase has translated it (anal.f90)
+        assert a["flag"] == {0: 0, 1: 6}[b["flag"]], seed
+        assert a["nnodes"] == b["nnodes"], seed
+        assert a["num_factor"] == b["num_factor"] and a["num_flops"] == b["num_flops"], seed
+        for k in KEYS:
+            assert np.array_equal(np.asarray(a[k], dtype=np.int64), np.asarray(b[k], dtype=np.int64)), (seed, k)
