@@ -233,3 +233,65 @@ def test_matching_based_scaling_through_sls():
             assert s2.information().negative_eigenvalues == prob["inertia"][1]
             st, x2 = s2.solve_system(b)
             assert st == 0 and P.backward_error(bad, x2, b) <= 1e-14
+
+
+def _sorted_csr_reference(n, row, col):
+    """What SLS_coord_to_sorted_csr (sls.f90:8409-8578) must return, stated from its contract rather than from its loops:
+    upper triangle by rows, every row led by its diagonal slot (present or not), then its distinct columns ascending;
+    the first entry of a position (in input order) owns it, later ones carry minus the position, out-of-range entries 0."""
+    ne = len(row)
+    inr = (row >= 1) & (row <= n) & (col >= 1) & (col <= n)
+    r = np.minimum(row, col)
+    c = np.maximum(row, col)
+    cols = [set() for _ in range(n + 1)]
+    for l in range(ne):
+        if inr[l] and c[l] != r[l]:
+            cols[r[l]].add(int(c[l]))
+    ptr = np.ones(n + 1, np.int64)
+    slot = {}
+    k = 1
+    for i in range(1, n + 1):
+        ptr[i - 1] = k
+        slot[(i, i)] = k
+        k += 1
+        for cc in sorted(cols[i]):
+            slot[(i, cc)] = k
+            k += 1
+    ptr[n] = k
+    m = np.zeros(ne, np.int64)
+    seen = set()
+    for l in range(ne):
+        if not inr[l]:
+            continue
+        key = (int(r[l]), int(c[l]))
+        m[l] = slot[key] if key not in seen else -slot[key]
+        seen.add(key)
+    has_any = {int(v) for v in r[inr]}
+    has_diag = {int(v) for v in r[inr & (row == col)]}
+    cnt = dict(dup=int((m < 0).sum()), oor=int((~inr).sum()), upper=int((inr & (row < col)).sum()),
+               missing_diagonals=len(has_any - has_diag))
+    return m, ptr, cnt
+
+
+def test_coord_to_sorted_csr_random_inputs():
+    """300 random coordinate lists (duplicates, both triangles, out-of-range indices, rows without a diagonal or without any
+    entry) against the contract above: MAPS, PTR and the four counters exactly."""
+    rng = np.random.default_rng(8409)
+    for t in range(300):
+        n = int(rng.integers(1, 30))
+        ne = int(rng.integers(0, 4 * n + 2))
+        row = rng.integers(1, n + 1, ne)
+        col = rng.integers(1, n + 1, ne)
+        if t % 3 == 0 and ne > 2:                      # out of range on either side
+            bad = rng.choice(ne, size=max(1, ne // 6), replace=False)
+            row[bad[::2]] = rng.choice([0, -3, n + 1, n + 7], size=len(bad[::2]))
+            col[bad[1::2]] = rng.choice([0, n + 1], size=len(bad[1::2]))
+        if t % 4 == 0 and ne > 0:                      # many repeats of a few positions
+            k = rng.integers(0, ne, ne // 2)
+            row[: len(k)] = row[k]
+            col[: len(k)] = col[k]
+        m, p, cnt = coord_to_sorted_csr(n, row, col)
+        m0, p0, cnt0 = _sorted_csr_reference(n, row, col)
+        assert cnt == cnt0, (t, cnt, cnt0)
+        assert np.array_equal(np.asarray(p, np.int64), p0), t
+        assert np.array_equal(np.asarray(m, np.int64), m0), t
