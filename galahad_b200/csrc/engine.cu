@@ -2360,6 +2360,8 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
    }
    // groups of nws columns: everything of a group is enqueued before its results are copied back, because a copy to
    // pageable host memory holds the host until the column's stream has drained
+   // (in a lambda: a failing CUDA call must not leave the members pointing at another column's workspaces)
+   const int rc_cols = [&]() -> int {
    for (int j0 = 0; j0 < nrhs; j0 += nws) {
       for (int j = j0; j < std::min(nrhs, j0 + nws); ++j) {
          if (nws > 1) use_ws(j % nws == 0 ? main_ws : extra_ws[j % nws - 1]);
@@ -2383,8 +2385,11 @@ int Numeric::solve(int job, int nrhs, double* x, int ldx, bool on_device, double
             CU(cudaMemcpyAsync(x + (size_t)j * ldx, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
          }
    }
+   return 0;
+   }();
+   if (nws > 1) use_ws(main_ws);
+   if (rc_cols) return rc_cols;
    if (nws > 1) {
-      use_ws(main_ws);
       for (int w = 0; w + 1 < nws; ++w) {
          CU(cudaEventRecord(extra_ws[w].done, extra_ws[w].st));
          CU(cudaStreamWaitEvent(st, extra_ws[w].done, 0));
