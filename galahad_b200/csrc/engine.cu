@@ -904,11 +904,24 @@ class Numeric {
    int use_solve_inv = getenv("B200LDLT_SOLVE_INV") ? atoi(getenv("B200LDLT_SOLVE_INV")) : 2;
    // fused levels of very small fronts (at most SMALL_T_MAXM rows) in CTAs of 64 threads
    bool use_st64 = !(getenv("B200LDLT_SOLVE_T64") && atoi(getenv("B200LDLT_SOLVE_T64")) == 0);
+   bool split_classes = !(getenv("B200LDLT_SOLVE_SPLIT") && atoi(getenv("B200LDLT_SOLVE_SPLIT")) == 0);
    // levels with a front of this many rows go through the chain kernels whatever their pivot counts
    int chain_tall_m = getenv("B200LDLT_CHAIN_TALL") ? atoi(getenv("B200LDLT_CHAIN_TALL")) : 4096;
    int* d_ticket = nullptr;         // per slot: arrival counter of the backward step's CTAs (left at zero by the last one)
    int* d_slist = nullptr;
    std::vector<int> slist, lvl_steps, lvl_maxm, lvl_maxne;
+   std::vector<int> lvl_ngt32, lvl_ngt64;     // fronts of the level with more than 32 / 64 eliminated columns (a prefix of its sorted list)
+   // the first `total` fronts of level l's list by width class (128 / 64 / 32 columns of triangle per CTA): a class is split
+   // off when it is the minority of what is left, else it takes the narrower fronts along
+   void split_by_width(int l, int kb0, int total, int& n128, int& n64, int& n32) const {
+      n128 = kb0 > 64 ? std::min(lvl_ngt64[l], total) : 0;
+      if (kb0 > 64 && (!split_classes || 2 * n128 > total)) n128 = total;
+      const int rest = total - n128;
+      n64 = kb0 > 32 ? std::min(std::max(0, lvl_ngt32[l] - (kb0 > 64 ? lvl_ngt64[l] : 0)), rest) : 0;
+      if (kb0 > 32 && kb0 <= 64 && n64 == 0) n64 = rest;
+      if (n64 > 0 && (!split_classes || 2 * n64 > rest)) n64 = rest;
+      n32 = rest - n64;
+   }
    std::vector<std::vector<int>> lvl_nact, lvl_actm;
    int64_t part_total = 0;
    double* d_part = nullptr;
@@ -1965,6 +1978,8 @@ int Numeric::build_solve_tables() {
       lvl_steps.assign(P->nlevels, 0);
       lvl_maxne.assign(P->nlevels, 0);
       lvl_maxm.assign(P->nlevels, 0);
+      lvl_ngt32.assign(P->nlevels, 0);
+      lvl_ngt64.assign(P->nlevels, 0);
       lvl_nact.assign(P->nlevels, std::vector<int>());
       lvl_actm.assign(P->nlevels, std::vector<int>());
       for (int l = 0; l < P->nlevels; ++l) {
@@ -1980,6 +1995,11 @@ int Numeric::build_solve_tables() {
          lvl_steps[l] = steps;
          lvl_maxne[l] = a1 > a0 ? ne_of(slist[a0]) : 0;
          for (int s = a0; s < a1; ++s) if (hfr[s].state == 2) lvl_maxm[l] = std::max(lvl_maxm[l], hfr[s].m);
+         lvl_ngt32[l] = lvl_ngt64[l] = 0;
+         for (int q = a0; q < a1; ++q) {
+            if (ne_of(slist[q]) > 64) ++lvl_ngt64[l];
+            if (ne_of(slist[q]) > 32) ++lvl_ngt32[l];
+         }
          lvl_nact[l].assign(steps, 0);
          lvl_actm[l].assign(steps, 0);
          for (int st2 = 0; st2 < steps; ++st2) {
@@ -2207,9 +2227,14 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
       if (use_fused && roles_fwd_n[l] == 0 && lvl_steps[l] == 1 &&
           step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, false), ns) == 1) {
          // every front of the level is one block and one CTA: gather, solve, update and store in one launch
-         launch_fwd_step<true>(kb0, dim3(ns, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, 0, kind, ga, use_st64 && lvl_maxm[l] <= SMALL_T_MAXM);
-         ++nlaunch;
-         smark("fwd_fused", l);
+         // one launch per width class when the wide fronts are a minority (the list is sorted by width): the narrow ones then
+         // run two or three CTAs to the SM instead of one
+         const bool st64 = use_st64 && lvl_maxm[l] <= SMALL_T_MAXM;
+         int n128, n64, n32;
+         split_by_width(l, kb0, ns, n128, n64, n32);
+         if (n128 > 0) { launch_fwd_step<true>(128, dim3(n128, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, 0, kind, ga, st64); ++nlaunch; smark("fwd_fused", l); }
+         if (n64 > 0) { launch_fwd_step<true>(64, dim3(n64, 1), st, d_fr, d_slist + s0 + n128, d_xw_off, d_xw, d_xa, 0, kind, ga, st64); ++nlaunch; smark("fwd_fused", l); }
+         if (n32 > 0) { launch_fwd_step<true>(32, dim3(n32, 1), st, d_fr, d_slist + s0 + n128 + n64, d_xw_off, d_xw, d_xa, 0, kind, ga, st64); ++nlaunch; smark("fwd_fused", l); }
          continue;
       }
       k_fwd_gather<<<ns, lvl_maxm[l] > 1024 ? 1024 : 256, 0, st>>>(d_fr, P->d_ss, P->d_child_idx, d_child_doff, P->d_rel, d_xw_off, d_xw, d_xa, d_xp, s0, kind);
@@ -2250,10 +2275,13 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
       const int kb0 = std::min(KB, lvl_maxne[l]), rows0 = lvl_steps[l] > 0 ? std::max(0, lvl_actm[l][0] - 1) : 0;
       if (use_fused && roles_bwd_n[l] == 0 && lvl_steps[l] == 1 &&
           step_grid_y(rows0, SE / (kb0 <= 32 ? 32 : kb0 <= 64 ? 64 : 128), step_slots(kb0, true), ns) == 1) {
-         launch_bwd_step<true>(kb0, dim3(lvl_nact[l][0], 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga,
-                               use_st64 && lvl_maxm[l] <= SMALL_T_MAXM);
-         ++nlaunch;
-         smark("bwd_fused", l);
+         const bool st64 = use_st64 && lvl_maxm[l] <= SMALL_T_MAXM;
+         const int na = lvl_nact[l][0];
+         int n128, n64, n32;
+         split_by_width(l, kb0, na, n128, n64, n32);
+         if (n128 > 0) { launch_bwd_step<true>(128, dim3(n128, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga, st64); ++nlaunch; smark("bwd_fused", l); }
+         if (n64 > 0) { launch_bwd_step<true>(64, dim3(n64, 1), st, d_fr, d_slist + s0 + n128, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga, st64); ++nlaunch; smark("bwd_fused", l); }
+         if (n32 > 0) { launch_bwd_step<true>(32, dim3(n32, 1), st, d_fr, d_slist + s0 + n128 + n64, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga, st64); ++nlaunch; smark("bwd_fused", l); }
          continue;
       }
       {
