@@ -134,6 +134,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+def solve_roofline(gbs):
+    """The solve against the HBM copy rate: MEASURED_PEAKS.json (driver-written) if present, else the profiling recipe's fallback."""
+    peak, src = 6650.0, "fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)"
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as fh:
+            peak, src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": src,
+            "bytes": "2 sweeps x 8 B x (entries of L + n): every entry of the factors read once per sweep"}
+
+
 def measure_fp64_peak(torch):
     """cuBLAS Dgemm through torch (float64 4096^3, best of 5): the FP64 denominator.  The driver's
     MEASURED_PEAKS.json has no FP64 entry, so it is measured here, same method as its bf16 entry."""
@@ -356,6 +368,7 @@ def run_ours(args):
             "factor_ms": tf * 1e3, "solve_ms": ts * 1e3,
             "solve_gbs": (2 * 8 * nfact + 2 * 8 * n) / ts / 1e9,
             "solve_8rhs_ms": ts8 * 1e3,
+            "solve_roofline": solve_roofline((2 * 8 * nfact + 2 * 8 * n) / ts / 1e9),
             "backward_error": berr,
             "gpu_launches": launches,
             "e2e": {"value": world * flops / ef / 1e12, "unit": UNIT, "h2d_bytes_per_step": int(8 * prob["val"].size + 8 * n),
