@@ -436,6 +436,9 @@ __global__ void k_stats(const FrontDev* fr, int nslots, int* counters) {
 #include "solve_kernels.cuh"
 
 static inline size_t step_smem_fwd(int kbc) { return (size_t)(kbc * (kbc + 1) + kbc + 256) * 8; }
+// the instantiations with t threads per CTA (64: very small fronts, 192: blocks of 65..96 pivots)
+static inline size_t step_smem_fwd_t(int kbc, int t) { return (size_t)(kbc * (kbc + 1) + kbc + t) * 8; }
+static inline size_t step_smem_bwd_t(int kbc, int t) { return (size_t)(kbc * (kbc + 1) + std::max(kbc, t * 32 / kbc) + 32) * 8; }
 static inline size_t chain_smem() {
    return (size_t)(KB * (KB + 1) + KB + 2 * KB + 32 + 2 * KB + 4 * 32 * ILD + KB + 4 * KB + 32) * 8;
 }
@@ -1064,6 +1067,8 @@ int Numeric::init() {
    CU(cudaFuncSetAttribute(k_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem()));
    CU(cudaFuncSetAttribute(k_bwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem()));
    CU(cudaFuncSetAttribute(k_chain_inverses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_inv_smem()));
+   CU(cudaFuncSetAttribute(k_fwd_step<96, true, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_fwd_t(96, 192)));
+   CU(cudaFuncSetAttribute(k_bwd_step<96, true, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd_t(96, 192)));
    CU(cudaFuncSetAttribute(k_bwd_step<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    CU(cudaFuncSetAttribute(k_bwd_step<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bwd(128)));
    const int nn = std::max(P->nnodes, 1);
@@ -2164,8 +2169,6 @@ static inline bool solve_pdl() { return !(getenv("B200LDLT_SOLVE_PDL") && atoi(g
 // ST: the 64-thread instantiations, for FUSED levels whose fronts have at most SMALL_T_MAXM rows and 64 pivots (six CTAs per SM
 // instead of two: a level of thousands of tiny fronts is bound by how many of them are resident)
 constexpr int SMALL_T = 64, SMALL_T_MAXM = 96;
-static inline size_t step_smem_fwd_t(int kbc, int t) { return (size_t)(kbc * (kbc + 1) + kbc + t) * 8; }
-static inline size_t step_smem_bwd_t(int kbc, int t) { return (size_t)(kbc * (kbc + 1) + std::max(kbc, t * 32 / kbc) + 32) * 8; }
 template <bool FUSED>
 static void launch_fwd_step(int kbmax, dim3 grid, cudaStream_t st, const FrontDev* fr, const int* list, const int64_t* xw_off, double* xw,
                             double* xy, int sp, int kind, const GatherArgs& ga, bool st64 = false) {
@@ -2175,6 +2178,8 @@ static void launch_fwd_step(int kbmax, dim3 grid, cudaStream_t st, const FrontDe
       launch_dep(dep, k_fwd_step<32, true, SMALL_T>, grid, dim3(SMALL_T), step_smem_fwd_t(32, SMALL_T), st, fr, list, xw_off, xw, xy, sp, kind, ga);
    else if (FUSED && st64 && kbmax <= 64)
       launch_dep(dep, k_fwd_step<64, true, SMALL_T>, grid, dim3(SMALL_T), step_smem_fwd_t(64, SMALL_T), st, fr, list, xw_off, xw, xy, sp, kind, ga);
+   else if (FUSED && kbmax > 64 && kbmax <= 96)
+      launch_dep(dep, k_fwd_step<96, true, 192>, grid, dim3(192), step_smem_fwd_t(96, 192), st, fr, list, xw_off, xw, xy, sp, kind, ga);
    else if (kbmax <= 32) launch_dep(dep, k_fwd_step<32, FUSED>, grid, dim3(256), step_smem_fwd(32), st, fr, list, xw_off, xw, xy, sp, kind, ga);
    else if (kbmax <= 64) launch_dep(dep, k_fwd_step<64, FUSED>, grid, dim3(256), step_smem_fwd(64), st, fr, list, xw_off, xw, xy, sp, kind, ga);
    else launch_dep(dep, k_fwd_step<128, FUSED>, grid, dim3(256), step_smem_fwd(128), st, fr, list, xw_off, xw, xy, sp, kind, ga);
@@ -2187,6 +2192,8 @@ static void launch_bwd_step(int kbmax, dim3 grid, cudaStream_t st, const FrontDe
       launch_dep(dep, k_bwd_step<32, true, SMALL_T>, grid, dim3(SMALL_T), step_smem_bwd_t(32, SMALL_T), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
    else if (FUSED && st64 && kbmax <= 64)
       launch_dep(dep, k_bwd_step<64, true, SMALL_T>, grid, dim3(SMALL_T), step_smem_bwd_t(64, SMALL_T), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
+   else if (FUSED && kbmax > 64 && kbmax <= 96)
+      launch_dep(dep, k_bwd_step<96, true, 192>, grid, dim3(192), step_smem_bwd_t(96, 192), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
    else if (kbmax <= 32) launch_dep(dep, k_bwd_step<32, FUSED>, grid, dim3(256), step_smem_bwd(32), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
    else if (kbmax <= 64) launch_dep(dep, k_bwd_step<64, FUSED>, grid, dim3(256), step_smem_bwd(64), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
    else launch_dep(dep, k_bwd_step<128, FUSED>, grid, dim3(256), step_smem_bwd(128), st, fr, list, xw_off, xw, part_off, part, ticket, sp, kind, ga);
@@ -2232,7 +2239,7 @@ void Numeric::sweep_fwd(int kind, int64_t& nlaunch) {
          const bool st64 = use_st64 && lvl_maxm[l] <= SMALL_T_MAXM;
          int n128, n64, n32;
          split_by_width(l, kb0, ns, n128, n64, n32);
-         if (n128 > 0) { launch_fwd_step<true>(128, dim3(n128, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, 0, kind, ga, st64); ++nlaunch; smark("fwd_fused", l); }
+         if (n128 > 0) { launch_fwd_step<true>(kb0, dim3(n128, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_xa, 0, kind, ga, st64); ++nlaunch; smark("fwd_fused", l); }
          if (n64 > 0) { launch_fwd_step<true>(64, dim3(n64, 1), st, d_fr, d_slist + s0 + n128, d_xw_off, d_xw, d_xa, 0, kind, ga, st64); ++nlaunch; smark("fwd_fused", l); }
          if (n32 > 0) { launch_fwd_step<true>(32, dim3(n32, 1), st, d_fr, d_slist + s0 + n128 + n64, d_xw_off, d_xw, d_xa, 0, kind, ga, st64); ++nlaunch; smark("fwd_fused", l); }
          continue;
@@ -2279,7 +2286,7 @@ void Numeric::sweep_bwd(int kind, bool diag, int64_t& nlaunch) {
          const int na = lvl_nact[l][0];
          int n128, n64, n32;
          split_by_width(l, kb0, na, n128, n64, n32);
-         if (n128 > 0) { launch_bwd_step<true>(128, dim3(n128, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga, st64); ++nlaunch; smark("bwd_fused", l); }
+         if (n128 > 0) { launch_bwd_step<true>(kb0, dim3(n128, 1), st, d_fr, d_slist + s0, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga, st64); ++nlaunch; smark("bwd_fused", l); }
          if (n64 > 0) { launch_bwd_step<true>(64, dim3(n64, 1), st, d_fr, d_slist + s0 + n128, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga, st64); ++nlaunch; smark("bwd_fused", l); }
          if (n32 > 0) { launch_bwd_step<true>(32, dim3(n32, 1), st, d_fr, d_slist + s0 + n128 + n64, d_xw_off, d_xw, d_part_off, d_part, d_ticket, 0, kind, ga, st64); ++nlaunch; smark("bwd_fused", l); }
          continue;

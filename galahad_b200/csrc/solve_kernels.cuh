@@ -503,9 +503,10 @@ struct GatherArgs {
    const SlotStatic* ss; const int* child_idx; const int* child_doff; const int* rel; const int* rlist;
    double* x; int posdef_scale, do_diag;
 };
-// T: threads per CTA (256; 64 for the FUSED levels of very small fronts, where six times as many fronts fit on an SM)
+// T: threads per CTA (256; 64 for the FUSED levels of very small fronts, where six times as many fronts fit on an SM;
+// 192 with KBC = 96 for the FUSED levels of 65..96 pivots: two CTAs per SM where the 128-column instantiation has one)
 template <int KBC, bool FUSED, int T = 256>
-__global__ void __launch_bounds__(T, T == 64 ? 6 : (KBC <= 64 ? 2 : 1)) k_fwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
+__global__ void __launch_bounds__(T, T == 64 ? 6 : (KBC <= 96 ? 2 : 1)) k_fwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
                                                   const int64_t* __restrict__ xw_off, double* XW, double* XY, int step, int kind, GatherArgs ga) {
    constexpr int RC = T * 32 / KBC, NG = T / RC, SLD = KBC + 1;
    pdl_launch_dependents();
@@ -990,7 +991,7 @@ __global__ void __launch_bounds__(256) k_bwd_gather(const FrontDev* __restrict__
 // (one warp per group of KBC / 8 columns, lanes down the rows), then the last CTA to arrive computes
 // x(block) = L(block,block)^{-T} (xw(block) - sum of the partials, in chunk order).
 template <int KBC, bool FUSED, int T = 256>
-__global__ void __launch_bounds__(T, T == 64 ? 6 : (KBC <= 64 ? 3 : 1)) k_bwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
+__global__ void __launch_bounds__(T, T == 64 ? 6 : (KBC <= 64 ? 3 : (KBC <= 96 ? 2 : 1))) k_bwd_step(const FrontDev* __restrict__ fr, const int* __restrict__ list,
                                                   const int64_t* __restrict__ xw_off, double* XW,
                                                   const int64_t* __restrict__ part_off, double* PART, int* ticket, int step, int kind, GatherArgs ga) {
    constexpr int RD = T * 32 / KBC, CW = KBC / (T / 32), RL = RD / 32, SLD = KBC + 1;
