@@ -152,8 +152,9 @@ def test_restatement_against_live_reference_on_random_matrices(chunk):
     """The pin beyond the committed runs: 36 random sparse matrices (SPD, indefinite with tiny diagonals, KKT; random pivot
     orders; nemin 1 / 8 / 32 so that fronts come in all shapes) through the reference's own engine and through the C
     restatement: flags, inertia and zero pivots exact, solutions equal to rounding.  (The number of 2 x 2 pivots is not
-    compared: inside a 32 x 32 block the restatement, like the engine, tries the largest diagonal entry as a 1 x 1 pivot
-    before it falls back to the reference's complete pivoting -- DESIGN.md section 5, known divergences.)"""
+    compared: the reference sends ragged blocks -- fronts narrower than 32 columns, the last columns of a front -- through
+    its TPP kernel, which takes 2 x 2 pivots even on SPD matrices, where the restatement keeps block pivoting; the pivot
+    sequence is not part of the result contract -- DESIGN.md section 5, known divergences.)"""
     for t in range(chunk, 36, 3):
         kind = ("spd", "indef", "kkt")[t % 3]
         n = 40 + 29 * (t % 9)
